@@ -1,0 +1,294 @@
+/**
+ * evqlref - a command line front-end to the UNMODIFIED reference engine.
+ * (TEST INFRASTRUCTURE - oracle/_ref only; never on the product path.)
+ *
+ * This is our own code; it only *calls* the reference the way its own tools do:
+ *   - `sql`   mirrors test/sql_tests.cc:232-274 (runTest) and the timing loop of
+ *             cli/benchmarks/local_sql.cc:249 (evqlbench local-sql): default runtime,
+ *             one CSTableScanProvider per table, buildQueryPlan + execute.
+ *   - `write` drives cstable::CSTableWriter the way cstable_test.cc:587-650 does, so
+ *             synthetic tables used by the parity tests are reference-authentic.
+ *
+ * Output format of `sql` (one line per row, fields separated by ';'):
+ *   #<name>:<type>;...           header
+ *   uint64/timestamp64 -> decimal, int64 -> decimal, float64 -> %.17g, bool -> true|false,
+ *   string -> raw bytes, NULL -> NULL
+ * Timing lines go to stderr:  TIMING rep=<i> ms=<t>
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <chrono>
+#include <string>
+#include <vector>
+#include <eventql/sql/runtime/defaultruntime.h>
+#include <eventql/sql/runtime/runtime.h>
+#include <eventql/sql/CSTableScanProvider.h>
+#include <eventql/sql/result_cursor.h>
+#include <eventql/sql/query_plan.h>
+#include <eventql/sql/svalue.h>
+#include <eventql/io/cstable/cstable_writer.h>
+#include <eventql/io/cstable/cstable_reader.h>
+#include <eventql/io/cstable/TableSchema.h>
+#include <eventql/util/io/fileutil.h>
+
+namespace evqlref {
+void registerExtensionAggregates(csql::SymbolTable* sym);
+}
+
+static int usage() {
+  fprintf(stderr,
+      "usage:\n"
+      "  evqlref sql [-t name=file.cst]... [-n reps] [-x] -q 'SQL'\n"
+      "      -x  do NOT register the extension aggregates (min/max/mean/sum<float64>)\n"
+      "  evqlref write <out.cst> <v1|v2> <nrows> <name>:<uint|datetime|float|bool>:<encoding>:<optional 0|1>:<datafile>[:<nullfile>] ...\n"
+      "      datafile = nrows x 8 B little-endian (u64 / double bits / 0|1); nullfile = nrows x 1 B (1 = NULL)\n"
+      "      encoding = leb128 | uint64 | uint32 | bitpacked | ieee754 | boolean\n"
+      "  evqlref info <file.cst>\n");
+  return 2;
+}
+
+static std::string fmtValue(csql::SType type, const void* data) {
+  const uint8_t* p = (const uint8_t*) data;
+  char buf[64];
+  switch (type) {
+    case csql::SType::UINT64:
+    case csql::SType::TIMESTAMP64: {
+      if (p[8] & csql::STAG_NULL) return "NULL";
+      uint64_t v; memcpy(&v, p, 8);
+      snprintf(buf, sizeof(buf), "%llu", (unsigned long long) v);
+      return buf;
+    }
+    case csql::SType::INT64: {
+      if (p[8] & csql::STAG_NULL) return "NULL";
+      int64_t v; memcpy(&v, p, 8);
+      snprintf(buf, sizeof(buf), "%lld", (long long) v);
+      return buf;
+    }
+    case csql::SType::FLOAT64: {
+      if (p[8] & csql::STAG_NULL) return "NULL";
+      double v; memcpy(&v, p, 8);
+      snprintf(buf, sizeof(buf), "%.17g", v);
+      return buf;
+    }
+    case csql::SType::BOOL: {
+      if (p[1] & csql::STAG_NULL) return "NULL";
+      return p[0] ? "true" : "false";
+    }
+    case csql::SType::STRING: {
+      uint32_t len; memcpy(&len, p, 4);
+      if (p[4 + len] & csql::STAG_NULL) return "NULL";
+      return std::string((const char*) p + 4, len);
+    }
+    case csql::SType::NIL:
+      return "NULL";
+  }
+  return "?";
+}
+
+static int cmdSql(int argc, char** argv) {
+  std::vector<std::pair<std::string, std::string>> tables;
+  std::string query;
+  int reps = 1;
+  bool ext = true;
+  for (int i = 0; i < argc; ++i) {
+    std::string a = argv[i];
+    if (a == "-t" && i + 1 < argc) {
+      std::string spec = argv[++i];
+      auto eq = spec.find('=');
+      if (eq == std::string::npos) return usage();
+      tables.emplace_back(spec.substr(0, eq), spec.substr(eq + 1));
+    } else if (a == "-q" && i + 1 < argc) {
+      query = argv[++i];
+    } else if (a == "-n" && i + 1 < argc) {
+      reps = atoi(argv[++i]);
+    } else if (a == "-x") {
+      ext = false;
+    } else {
+      return usage();
+    }
+  }
+  if (query.empty()) return usage();
+
+  auto runtime = csql::Runtime::getDefaultRuntime();
+  if (ext) {
+    evqlref::registerExtensionAggregates(runtime->symbols());
+  }
+
+  for (int rep = 0; rep < reps; ++rep) {
+    try {
+      auto txn = runtime->newTransaction();
+      auto repo = mkScoped(new csql::TableRepository());
+      for (const auto& t : tables) {
+        repo->addProvider(new csql::CSTableScanProvider(t.first, t.second));
+      }
+      txn->setTableProvider(std::move(repo));
+
+      auto t0 = std::chrono::steady_clock::now();
+      auto qplan = runtime->buildQueryPlan(txn.get(), query);
+      auto cursor = qplan->execute(0);
+      size_t ncols = cursor->getColumnCount();
+      bool print = (rep == reps - 1);
+      if (print) {
+        const auto& names = qplan->getStatementgetResultColumns(0);
+        std::string hdr = "#";
+        for (size_t i = 0; i < ncols; ++i) {
+          if (i) hdr += ";";
+          hdr += (i < names.size() ? names[i] : std::string("?"));
+          hdr += ":";
+          hdr += csql::sql_typename(cursor->getColumnType(i));
+        }
+        puts(hdr.c_str());
+      }
+      size_t nrows = 0;
+      while (cursor->isValid()) {
+        if (print) {
+          std::string line;
+          for (size_t i = 0; i < ncols; ++i) {
+            if (i) line += ";";
+            line += fmtValue(cursor->getColumnType(i), cursor->getColumnData(i));
+          }
+          puts(line.c_str());
+        }
+        ++nrows;
+        auto rc = cursor->next();
+        if (!rc.isSuccess()) {
+          fprintf(stdout, "ERROR!\n%s\n", rc.getMessage().c_str());
+          return 1;
+        }
+      }
+      auto t1 = std::chrono::steady_clock::now();
+      fprintf(stderr, "TIMING rep=%d ms=%.3f rows_out=%zu\n", rep,
+          std::chrono::duration<double, std::milli>(t1 - t0).count(), nrows);
+    } catch (const std::exception& e) {
+      fprintf(stdout, "ERROR!\n%s\n", e.what());
+      return 1;
+    }
+  }
+  return 0;
+}
+
+struct ColSpec {
+  std::string name, type, enc, datafile, nullfile;
+  bool optional;
+};
+
+static std::vector<std::string> split(const std::string& s, char c) {
+  std::vector<std::string> out;
+  size_t b = 0;
+  for (;;) {
+    auto e = s.find(c, b);
+    if (e == std::string::npos) { out.push_back(s.substr(b)); break; }
+    out.push_back(s.substr(b, e - b));
+    b = e + 1;
+  }
+  return out;
+}
+
+static cstable::ColumnEncoding parseEnc(const std::string& e) {
+  if (e == "leb128") return cstable::ColumnEncoding::UINT64_LEB128;
+  if (e == "uint64") return cstable::ColumnEncoding::UINT64_PLAIN;
+  if (e == "uint32") return cstable::ColumnEncoding::UINT32_PLAIN;
+  if (e == "bitpacked") return cstable::ColumnEncoding::UINT32_BITPACKED;
+  if (e == "ieee754") return cstable::ColumnEncoding::FLOAT_IEEE754;
+  if (e == "boolean") return cstable::ColumnEncoding::BOOLEAN_BITPACKED;
+  fprintf(stderr, "bad encoding %s\n", e.c_str());
+  exit(2);
+}
+
+static int cmdWrite(int argc, char** argv) {
+  if (argc < 4) return usage();
+  std::string out = argv[0];
+  std::string ver = argv[1];
+  size_t nrows = strtoull(argv[2], NULL, 10);
+  std::vector<ColSpec> cols;
+  for (int i = 3; i < argc; ++i) {
+    auto p = split(argv[i], ':');
+    if (p.size() < 5) return usage();
+    ColSpec c;
+    c.name = p[0]; c.type = p[1]; c.enc = p[2]; c.optional = (p[3] == "1"); c.datafile = p[4];
+    if (p.size() > 5) c.nullfile = p[5];
+    cols.push_back(c);
+  }
+
+  cstable::TableSchema schema;
+  for (const auto& c : cols) {
+    cstable::ColumnType t;
+    if (c.type == "uint") t = cstable::ColumnType::UNSIGNED_INT;
+    else if (c.type == "datetime") t = cstable::ColumnType::DATETIME;
+    else if (c.type == "float") t = cstable::ColumnType::FLOAT;
+    else if (c.type == "bool") t = cstable::ColumnType::BOOLEAN;
+    else return usage();
+    schema.addColumn(c.name, t, parseEnc(c.enc), false, c.optional);
+  }
+
+  FileUtil::rm(out);
+  auto writer = cstable::CSTableWriter::createFile(
+      out,
+      ver == "v1" ? cstable::BinaryFormatVersion::v0_1_0 : cstable::BinaryFormatVersion::v0_2_0,
+      schema);
+
+  for (const auto& c : cols) {
+    auto cw = writer->getColumnWriter(c.name);
+    FILE* df = fopen(c.datafile.c_str(), "rb");
+    if (!df) { perror(c.datafile.c_str()); return 1; }
+    FILE* nf = NULL;
+    if (!c.nullfile.empty()) {
+      nf = fopen(c.nullfile.c_str(), "rb");
+      if (!nf) { perror(c.nullfile.c_str()); return 1; }
+    }
+    uint64_t dmax = c.optional ? 1 : 0;
+    const size_t CH = 1 << 16;
+    std::vector<uint64_t> buf(CH);
+    std::vector<uint8_t> nbuf(CH);
+    for (size_t done = 0; done < nrows; ) {
+      size_t n = std::min(CH, nrows - done);
+      if (fread(buf.data(), 8, n, df) != n) { fprintf(stderr, "short read %s\n", c.datafile.c_str()); return 1; }
+      if (nf && fread(nbuf.data(), 1, n, nf) != n) { fprintf(stderr, "short read %s\n", c.nullfile.c_str()); return 1; }
+      for (size_t i = 0; i < n; ++i) {
+        if (nf && nbuf[i]) {
+          cw->writeNull(0, 0);
+        } else if (c.type == "float") {
+          double d; memcpy(&d, &buf[i], 8);
+          cw->writeFloat(0, dmax, d);
+        } else if (c.type == "bool") {
+          cw->writeBoolean(0, dmax, buf[i] != 0);
+        } else {
+          cw->writeUnsignedInt(0, dmax, buf[i]);
+        }
+      }
+      done += n;
+    }
+    fclose(df);
+    if (nf) fclose(nf);
+  }
+  writer->addRows(nrows);
+  writer->commit();
+  return 0;
+}
+
+static int cmdInfo(int argc, char** argv) {
+  if (argc < 1) return usage();
+  auto reader = cstable::CSTableReader::openFile(argv[0]);
+  printf("rows=%llu\n", (unsigned long long) reader->numRecords());
+  for (const auto& c : reader->columns()) {
+    printf("column id=%u name=%s logical=%d storage=%d rmax=%llu dmax=%llu\n",
+        (unsigned) c.column_id, c.column_name.c_str(), (int) c.logical_type, (int) c.storage_type,
+        (unsigned long long) c.rlevel_max, (unsigned long long) c.dlevel_max);
+  }
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2) return usage();
+  std::string cmd = argv[1];
+  try {
+    if (cmd == "sql") return cmdSql(argc - 2, argv + 2);
+    if (cmd == "write") return cmdWrite(argc - 2, argv + 2);
+    if (cmd == "info") return cmdInfo(argc - 2, argv + 2);
+  } catch (const std::exception& e) {
+    fprintf(stdout, "ERROR!\n%s\n", e.what());
+    return 1;
+  }
+  return usage();
+}
