@@ -1,0 +1,331 @@
+/*
+ * evqgpu.h - C ABI of the B200-native columnar scan / filter / GROUP BY engine.
+ *
+ * This is the drop-in boundary.  Everything above it is host C++ that
+ * keeps EventQL's operator surface (csql::TableExpression / FastCSTableScan /
+ * GroupByExpression / TableProvider - see eventql_b200/host/); everything below it is
+ * hand-written CUDA for sm_100a.  Plain pointers and sizes only: no C++ types, no
+ * torch types, no exceptions cross this line.
+ *
+ * Conventions
+ *   - every call returns an evqgpu_status (0 = ok); on failure the message is available
+ *     from evqgpu_last_error() (per calling thread)
+ *   - handles are opaque; the caller owns host buffers, the library owns device memory
+ *   - one host thread per context at a time (single-threaded pull, like
+ *     csql::TableExpression: sql/table_expression.h:35-50 in the reference)
+ *   - there is NO CPU fallback: a query the device path cannot run fails with
+ *     EVQGPU_ERR_UNSUPPORTED
+ *
+ * Reference interfaces replaced (paths relative to the reference's src/eventql/):
+ *   evqgpu_table_open / _column_info     io/cstable/cstable_reader.cc:133-200 (CSTableReader::openFile),
+ *                                        io/cstable/cstable.cc:35-84,200-255  (readHeader/readIndex)
+ *   evqgpu_table_load_columns            io/cstable/cstable_reader.cc:78-131  (openColumnV2: bind level +
+ *                                        data page readers), io/cstable/page_manager.cc:125-171
+ *   evqgpu_table_create/_add_*           io/cstable/cstable_file.cc (in-memory cstable arena)
+ *   evqgpu_query_create                  sql/CSTableScan.cc:726-755 (FastCSTableScan::execute: compile
+ *                                        select list + WHERE) and sql/runtime/compiler.cc:50-104
+ *                                        (split of a select item into accumulate / get programs)
+ *   evqgpu_query_execute                 sql/CSTableScan.cc:757-858 (nextBatch: decode, WHERE, project) fused
+ *                                        with sql/statements/select/groupby.cc:69-185 (GroupByExpression::execute)
+ *   evqgpu_query_fetch                   sql/statements/select/groupby.cc:187-220 (GroupByExpression::nextBatch)
+ *                                        output in the packed SVector encoding of sql/svalue.cc:533-549
+ *   evqgpu_query_merge                   sql/statements/select/groupby.cc:528-637 (GroupByMergeExpression)
+ *   evqgpu_function_lookup               sql/runtime/symboltable.cc:33-39,162-175 (symbol strings)
+ */
+#ifndef EVQGPU_H
+#define EVQGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVQGPU_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define EVQGPU_API __attribute__((visibility("default")))
+#else
+#define EVQGPU_API
+#endif
+
+typedef struct evqgpu_ctx evqgpu_ctx;
+typedef struct evqgpu_table evqgpu_table;
+typedef struct evqgpu_query evqgpu_query;
+
+typedef enum evqgpu_status {
+  EVQGPU_OK = 0,
+  EVQGPU_ERR_ARG = 1,          /* malformed argument / plan */
+  EVQGPU_ERR_UNSUPPORTED = 2,  /* valid, but not runnable on the device path (no CPU fallback) */
+  EVQGPU_ERR_CUDA = 3,         /* CUDA / NVRTC / NCCL failure, incl. "no device" */
+  EVQGPU_ERR_RUNTIME = 4,      /* query-time error the reference raises too (division by zero ...) */
+  EVQGPU_ERR_FORMAT = 5,       /* not a valid cstable file */
+  EVQGPU_ERR_NOMEM = 6
+} evqgpu_status;
+
+/* value types == csql::SType (sql/svalue.h:41-49) */
+enum {
+  EVQ_NIL = 0,
+  EVQ_UINT64 = 1,
+  EVQ_INT64 = 2,
+  EVQ_FLOAT64 = 3,
+  EVQ_BOOL = 4,
+  EVQ_STRING = 5,
+  EVQ_TIMESTAMP64 = 6
+};
+
+/* value tag == csql::STag (sql/svalue.h:51-56) */
+#define EVQ_STAG_NULL 1
+
+/* cstable logical column types == cstable::ColumnType (io/cstable/cstable.h:112-120) */
+enum {
+  EVQ_COL_SUBRECORD = 0,
+  EVQ_COL_BOOLEAN = 1,
+  EVQ_COL_UNSIGNED_INT = 2,
+  EVQ_COL_SIGNED_INT = 3,
+  EVQ_COL_STRING = 4,
+  EVQ_COL_FLOAT = 5,
+  EVQ_COL_DATETIME = 6
+};
+
+/* cstable storage encodings == cstable::ColumnEncoding (io/cstable/cstable.h:122-130) */
+enum {
+  EVQ_ENC_BOOLEAN_BITPACKED = 1,
+  EVQ_ENC_UINT32_BITPACKED = 10,
+  EVQ_ENC_UINT32_PLAIN = 11,
+  EVQ_ENC_UINT64_PLAIN = 12,
+  EVQ_ENC_UINT64_LEB128 = 13,
+  EVQ_ENC_FLOAT_IEEE754 = 14,
+  EVQ_ENC_STRING_PLAIN = 100
+};
+
+/* page stream kinds == cstable::PageIndexEntryType (io/cstable/cstable.h:186-190) */
+enum { EVQ_STREAM_DATA = 1, EVQ_STREAM_RLEVEL = 2, EVQ_STREAM_DLEVEL = 3 };
+
+/* ------------------------------------------------------------------------------------------
+ * context
+ * ---------------------------------------------------------------------------------------- */
+
+/* Bind a context to one CUDA device (one process per GPU; the device must exist - there is
+ * no host execution mode).  flags: reserved, pass 0. */
+EVQGPU_API int evqgpu_ctx_create(int device, uint64_t flags, evqgpu_ctx** out);
+EVQGPU_API void evqgpu_ctx_destroy(evqgpu_ctx* ctx);
+
+/* Message of the last failed call on this thread ("" if none). Never NULL. */
+EVQGPU_API const char* evqgpu_last_error(void);
+
+/* ABI version of the loaded library (== EVQGPU_ABI_VERSION it was built with). */
+EVQGPU_API int evqgpu_abi_version(void);
+
+/* Pinned host memory helpers (so that evqgpu_table_load_columns can DMA straight from the
+ * caller's file image).  evqgpu_host_register pins an existing allocation in place. */
+EVQGPU_API int evqgpu_host_alloc(evqgpu_ctx* ctx, uint64_t nbytes, void** out);
+EVQGPU_API int evqgpu_host_free(evqgpu_ctx* ctx, void* ptr);
+EVQGPU_API int evqgpu_host_register(evqgpu_ctx* ctx, void* ptr, uint64_t nbytes);
+EVQGPU_API int evqgpu_host_unregister(evqgpu_ctx* ctx, void* ptr);
+
+/* The CUDA stream (cudaStream_t) all work of this context is issued on. */
+EVQGPU_API void* evqgpu_ctx_stream(evqgpu_ctx* ctx);
+EVQGPU_API int evqgpu_ctx_synchronize(evqgpu_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------
+ * tables (one cstable file / partition segment, resident in HBM)
+ * ---------------------------------------------------------------------------------------- */
+
+typedef struct evqgpu_column_info {
+  const char* name;         /* owned by the table */
+  uint32_t column_id;
+  uint32_t logical_type;    /* EVQ_COL_* */
+  uint32_t encoding;        /* EVQ_ENC_* */
+  uint32_t rlevel_max;
+  uint32_t dlevel_max;
+  uint32_t sql_type;        /* EVQ_* SType as mapped by sql/CSTableScanProvider.cc:79-107 */
+  uint32_t loaded;          /* 1 once resident in HBM */
+  uint64_t data_bytes;      /* payload bytes of the DATA stream (algorithmic bytes, padding excluded) */
+  uint64_t level_bytes;     /* payload bytes of the DLEVEL stream, 0 if the column is required */
+  uint64_t num_values;      /* non-NULL values (known once loaded) */
+  uint64_t min_value;       /* raw 64-bit min / max over non-NULL values (unsigned order; once loaded) */
+  uint64_t max_value;
+} evqgpu_column_info;
+
+/* Parse header + page index of a cstable file image (v0.1.0 and v0.2.0).  Host only: nothing
+ * is copied yet.  `file` must stay valid until the columns of interest are loaded. */
+EVQGPU_API int evqgpu_table_open(evqgpu_ctx* ctx, const void* file, uint64_t nbytes, evqgpu_table** out);
+
+/* Build a table from logical streams instead of a file image (in-memory arena, generators).
+ * Streams are the concatenation of a column's pages in index order, without the bit-packed
+ * page's 4-byte max_value header (pass it as `bitpack_max`; ignored for other encodings).
+ * ptr may be a host pointer or - with EVQGPU_STREAM_DEVICE - a device pointer (copied). */
+EVQGPU_API int evqgpu_table_create(evqgpu_ctx* ctx, uint64_t num_rows, evqgpu_table** out);
+EVQGPU_API int evqgpu_table_add_column(evqgpu_table* tbl, const char* name, uint32_t logical_type,
+                                       uint32_t encoding, uint32_t rlevel_max, uint32_t dlevel_max);
+#define EVQGPU_STREAM_DEVICE 1u
+EVQGPU_API int evqgpu_table_add_stream(evqgpu_table* tbl, const char* column, uint32_t kind, const void* ptr,
+                                       uint64_t nbytes, uint32_t bitpack_max, uint32_t flags);
+
+EVQGPU_API void evqgpu_table_destroy(evqgpu_table* tbl);
+
+EVQGPU_API uint64_t evqgpu_table_num_rows(const evqgpu_table* tbl);
+EVQGPU_API uint32_t evqgpu_table_num_columns(const evqgpu_table* tbl);
+EVQGPU_API int evqgpu_table_column_info(const evqgpu_table* tbl, uint32_t idx, evqgpu_column_info* out);
+EVQGPU_API int evqgpu_table_find_column(const evqgpu_table* tbl, const char* name); /* index or -1 */
+
+/* Make the named columns resident: host->device copy of their pages (async DMA when the file
+ * image is pinned), then the device-side row-tile index and min/max statistics.  Idempotent.
+ * names == NULL loads every flat, non-string column. */
+EVQGPU_API int evqgpu_table_load_columns(evqgpu_table* tbl, const char* const* names, uint32_t n);
+
+/* Device -> host copy of one logical stream (tests, cstable export). nbytes_out may exceed cap:
+ * nothing is copied then. */
+EVQGPU_API int evqgpu_table_read_stream(evqgpu_table* tbl, const char* column, uint32_t kind, void* dst,
+                                        uint64_t cap, uint64_t* nbytes_out, uint32_t* bitpack_max_out);
+
+/* Decode a loaded flat column to one 9-byte packed SVector element per row ([8 B value][1 B tag],
+ * 2 B for BOOL) on the device and copy rows [row0, row0+nrows) to `dst` (host).  This is
+ * FastCSTableScan::fetchColumn* (sql/CSTableScan.cc:860-968) on its own, used by the decode parity tests. */
+EVQGPU_API int evqgpu_table_decode_column(evqgpu_table* tbl, const char* column, uint64_t row0, uint64_t nrows,
+                                          void* dst, uint64_t cap);
+
+/* Write the table as a v0.2.0 cstable file (the layout of io/cstable/cstable_writer.cc:267-293). */
+EVQGPU_API int evqgpu_table_write_file(evqgpu_table* tbl, const char* path);
+
+/* ------------------------------------------------------------------------------------------
+ * synthetic tables, generated on the device (bench / tests; BASELINE.json's configs)
+ * ---------------------------------------------------------------------------------------- */
+
+typedef struct evqgpu_synth_column {
+  const char* name;
+  uint32_t logical_type;   /* EVQ_COL_UNSIGNED_INT | EVQ_COL_DATETIME | EVQ_COL_FLOAT | EVQ_COL_BOOLEAN */
+  uint32_t encoding;       /* EVQ_ENC_* */
+  uint32_t null_every;     /* 0 = required column; k>0 = optional, row i is NULL iff i % k == k-1 */
+  uint32_t transform;      /* 0: v = lo + r % span;  1: v = splitmix64(lo + r % span)  (full-range keys);
+                              2 (float): v = (double)(lo + r % span) / 100.0 */
+  uint64_t seed;           /* r = splitmix64(seed + row) */
+  uint64_t lo;
+  uint64_t span;           /* >= 1 */
+} evqgpu_synth_column;
+
+EVQGPU_API int evqgpu_table_synthesize(evqgpu_ctx* ctx, uint64_t num_rows, uint64_t row_offset,
+                                       const evqgpu_synth_column* cols, uint32_t ncols, evqgpu_table** out);
+
+/* ------------------------------------------------------------------------------------------
+ * expressions: postfix programs, the shape of csql::vm::Program (sql/runtime/vm.h:44-75)
+ * ---------------------------------------------------------------------------------------- */
+
+enum {
+  EVQ_X_INPUT = 4,    /* push input column `arg` (index into evqgpu_query_desc.input_columns), keeps its NULL tag */
+  EVQ_X_LITERAL = 3,  /* push literal: imm = raw 64-bit value (u64 / i64 / double bits / bool);
+                         STRING: imm = (offset << 32 | length) into evqgpu_expr.strings */
+  EVQ_X_CALL = 1,     /* pop nargs, push fn(args); arg = function id from evqgpu_function_lookup.
+                         Pure functions drop NULL tags; aggregate functions mark the
+                         split point between the accumulate and the get program (compiler.cc:67-100) */
+  EVQ_X_IF = 6        /* pop else, then, cond (pushed in the order cond, then, else); lazily evaluated
+                         like the X_CJUMP/X_JUMP form of compiler.cc:174-209 */
+};
+
+typedef struct evqgpu_insn {
+  uint8_t op;      /* EVQ_X_* */
+  uint8_t type;    /* result SType of this node */
+  uint16_t nargs;  /* EVQ_X_CALL only */
+  uint32_t arg;
+  uint64_t imm;
+} evqgpu_insn;
+
+typedef struct evqgpu_expr {
+  const evqgpu_insn* code;
+  uint32_t len;            /* 0 = absent */
+  const char* strings;     /* string literal pool, may be NULL */
+  uint32_t strings_len;
+} evqgpu_expr;
+
+/* Resolve a reference symbol string ("lt#bool/uint64;uint64;", "sum#uint64/uint64;",
+ * "count#uint64/nil;" ...) to a function id; -1 if the device path does not implement it.
+ * Besides the reference's registry (sql/defaults.cc:38-171) the typed extension aggregates
+ * min / max / mean / sum#float64 of oracle/ref_tools/ext_aggregates.cc are known. */
+EVQGPU_API int evqgpu_function_lookup(const char* symbol);
+EVQGPU_API const char* evqgpu_function_symbol(int function_id); /* NULL if out of range */
+EVQGPU_API int evqgpu_function_is_aggregate(int function_id);
+
+/* ------------------------------------------------------------------------------------------
+ * queries: fused FastCSTableScan (+ GroupByExpression)
+ * ---------------------------------------------------------------------------------------- */
+
+#define EVQGPU_QUERY_GROUPBY 1u       /* aggregate plan: select items are GroupByNode select expressions */
+#define EVQGPU_QUERY_PARTIAL 2u       /* results stay as mergeable partials until evqgpu_query_merge */
+
+typedef struct evqgpu_query_desc {
+  uint32_t struct_size;                 /* sizeof(evqgpu_query_desc) */
+  uint32_t flags;                       /* EVQGPU_QUERY_* */
+  uint32_t num_input_columns;
+  const char* const* input_columns;     /* SequentialScanNode::selectedColumns() */
+  evqgpu_expr where;                    /* BOOL program or len == 0 */
+  uint32_t num_group;                   /* GROUP BY expressions (0 with EVQGPU_QUERY_GROUPBY = one global group) */
+  const evqgpu_expr* group;
+  uint32_t num_select;
+  const evqgpu_expr* select;            /* output columns; at most one aggregate call each */
+  uint64_t expected_groups;             /* hint, 0 = unknown */
+} evqgpu_query_desc;
+
+EVQGPU_API int evqgpu_query_create(evqgpu_ctx* ctx, const evqgpu_query_desc* desc, evqgpu_query** out);
+EVQGPU_API void evqgpu_query_destroy(evqgpu_query* q);
+
+EVQGPU_API uint32_t evqgpu_query_num_columns(const evqgpu_query* q);
+EVQGPU_API uint32_t evqgpu_query_column_type(const evqgpu_query* q, uint32_t idx); /* SType */
+
+/* Scan the given tables (partitions of one logical table; each must have the query's input
+ * columns loaded) and aggregate / project.  Resets previous results of q.  Work is issued on
+ * the context stream; the call returns once the result row count is known. */
+EVQGPU_API int evqgpu_query_execute(evqgpu_query* q, evqgpu_table* const* tables, uint32_t ntables);
+
+/* Same, but only enqueues the device work (no host synchronisation); finish with
+ * evqgpu_query_finish.  Lets a caller time the device portion with CUDA events on
+ * evqgpu_ctx_stream(). */
+EVQGPU_API int evqgpu_query_enqueue(evqgpu_query* q, evqgpu_table* const* tables, uint32_t ntables);
+EVQGPU_API int evqgpu_query_finish(evqgpu_query* q);
+
+EVQGPU_API int evqgpu_query_num_rows(evqgpu_query* q, uint64_t* out);
+
+/* Copy result rows [row0, row0 + max_rows) to the host in the packed SVector encoding:
+ * numeric columns 9 B per row ([8 B value][1 B STag]), BOOL 2 B per row.  columns[i] receives
+ * column i and must hold max_rows * elem_size bytes.  *nrows_out = rows written (0 = EOF).
+ * Group order is unspecified, like the reference's. */
+EVQGPU_API int evqgpu_query_fetch(evqgpu_query* q, uint64_t row0, uint64_t max_rows, void* const* columns,
+                                  uint64_t* nrows_out);
+
+/* Statistics of the last execute. */
+typedef struct evqgpu_query_stats {
+  uint64_t rows_scanned;
+  uint64_t rows_passed;          /* rows that satisfied WHERE */
+  uint64_t algorithmic_bytes;    /* payload bytes of the referenced streams */
+  uint64_t num_groups;
+  uint32_t kernel_launches;      /* device kernels launched by the last execute */
+  uint32_t strategy;             /* 0 scan-only, 1 register/shared-memory low-cardinality, 2 global hash table */
+  float jit_ms;                  /* NVRTC time spent by evqgpu_query_create (0 when cached) */
+  float reserved;
+} evqgpu_query_stats;
+EVQGPU_API int evqgpu_query_get_stats(evqgpu_query* q, evqgpu_query_stats* out);
+
+/* The generated CUDA source of the query's scan kernel (debugging, profiles/). */
+EVQGPU_API const char* evqgpu_query_kernel_source(evqgpu_query* q);
+
+/* ------------------------------------------------------------------------------------------
+ * multi-GPU: one process per GPU, partial aggregate tables merged over NVLink with NCCL
+ * ---------------------------------------------------------------------------------------- */
+
+#define EVQGPU_COMM_ID_BYTES 128
+/* rank 0 creates the id; the launcher broadcasts it (torch.distributed / MPI / file). */
+EVQGPU_API int evqgpu_comm_unique_id(void* id_out /* EVQGPU_COMM_ID_BYTES */);
+EVQGPU_API int evqgpu_comm_init(evqgpu_ctx* ctx, const void* id, int rank, int nranks);
+EVQGPU_API int evqgpu_comm_destroy(evqgpu_ctx* ctx);
+
+/* GroupByMergeExpression: combine the partial aggregates of all ranks (count/sum: +, min/max:
+ * min/max over non-empty, mean: (sum, n) pairs).  Low-cardinality results are all-reduced and
+ * every rank ends with the full result; high-cardinality results are repartitioned by key hash
+ * (all-to-all) and every rank ends with its share of the groups. */
+EVQGPU_API int evqgpu_query_merge(evqgpu_query* q);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVQGPU_H */
