@@ -1,0 +1,66 @@
+// debug.cc - evqgpu_debug_generate: codegen + NVRTC without a device (the "does it build" check of the JIT text).
+#include <string.h>
+#include "query.h"
+
+using namespace evq;
+
+namespace evq {
+void query_intake(evqgpu_query* q, const evqgpu_query_desc* desc);
+}
+
+extern "C" int evqgpu_debug_generate(const evqgpu_query_desc* desc, const evqgpu_debug_column* columns, uint32_t tier,
+                                     uint32_t dense_slots, char* src_out, uint64_t src_cap, uint64_t* src_len_out, int compile,
+                                     uint64_t* cubin_bytes_out) {
+  return guarded([&] {
+    if (!desc || !columns) fail(EVQGPU_ERR_ARG, "evqgpu_debug_generate: null argument");
+    evqgpu_query q;
+    query_intake(&q, desc);
+    KernelShape s;
+    s.cols.resize(q.input_columns.size());
+    for (size_t i = 0; i < q.input_columns.size(); ++i) {
+      if (!q.col_used[i]) continue;
+      ColSig& cs = s.cols[i];
+      cs.used = true;
+      cs.sql_type = columns[i].sql_type;
+      switch (columns[i].encoding) {
+        case EVQ_ENC_UINT64_PLAIN:
+        case EVQ_ENC_FLOAT_IEEE754: cs.kind = EVQ_KIND_PLAIN64; break;
+        case EVQ_ENC_UINT32_PLAIN: cs.kind = EVQ_KIND_PLAIN32; break;
+        case EVQ_ENC_UINT64_LEB128: cs.kind = EVQ_KIND_LEB128; break;
+        default: cs.kind = EVQ_KIND_BITPACK; break;
+      }
+      cs.nullable = columns[i].dlevel_max > 0;
+      cs.dmax = columns[i].dlevel_max;
+      cs.data_stream = s.nstreams++;
+      if (cs.nullable) { cs.level_stream = s.nstreams++; cs.null_slot = s.nnull++; }
+      if (cs.kind == EVQ_KIND_LEB128) cs.leb_slot = s.nleb++;
+    }
+    const bool groupby = q.flags & EVQGPU_QUERY_GROUPBY;
+    std::vector<int> tiers;
+    if (!groupby) tiers = {0, 3};
+    else tiers = {(int) tier};
+    std::string all;
+    uint64_t cubin_total = 0;
+    for (int t : tiers) {
+      s.tier = t;
+      s.g1 = 1;
+      if (t == 1 && !q.group.empty()) {
+        s.g1 = 2;
+        while ((uint32_t) s.g1 < dense_slots) s.g1 <<= 1;
+      }
+      s.ncons = 256;
+      s.nstages = 3;
+      s.min_ctas = 2;
+      std::string src = generate_source(q, s);
+      if (compile) {
+        std::string log;
+        std::vector<char> cubin = jit_compile_to_cubin(src, &log);
+        cubin_total += cubin.size();
+      }
+      all += src;
+    }
+    if (src_len_out) *src_len_out = all.size();
+    if (src_out && src_cap > all.size()) memcpy(src_out, all.c_str(), all.size() + 1);
+    if (cubin_bytes_out) *cubin_bytes_out = cubin_total;
+  });
+}

@@ -1,0 +1,77 @@
+// evq_abi.h - types, constants and kernel parameter blocks shared by the host library (g++) and the
+// device code (nvcc / NVRTC).  Plain C structs only; this text is pasted in front of every JIT kernel.
+#ifndef EVQ_ABI_H
+#define EVQ_ABI_H
+
+typedef unsigned char u8;
+typedef unsigned short u16;
+typedef unsigned int u32;
+typedef int i32;
+typedef unsigned long long u64;
+typedef long long i64;
+typedef double f64;
+
+#ifndef EVQ_TILE_ROWS
+#define EVQ_TILE_ROWS 1024
+#endif
+
+#define EVQ_KIND_PLAIN64 0
+#define EVQ_KIND_PLAIN32 1
+#define EVQ_KIND_BITPACK 2
+#define EVQ_KIND_LEB128 3
+#define EVQ_KIND_LEVEL 4
+
+#define EVQ_ERR_DIV_ZERO 1u
+#define EVQ_ERR_MOD_ZERO 2u
+#define EVQ_ERR_TABLE_FULL 4u
+#define EVQ_ERR_SLOT_RANGE 8u
+#define EVQ_ERR_STAGE_OVERFLOW 16u
+
+#define EVQ_MAX_STREAMS 32
+#define EVQ_MAX_KEYS 8
+
+// ---- kernel parameter blocks ----------------------------------------------------------------------------------
+
+struct EvqStream {
+  const u8* base;        // logical stream (pages concatenated), 16-byte aligned, padded
+  const u64* off_index;  // LEB128: byte offset of the first value of every row tile [ntiles + 1]
+  const u64* val_index;  // optional column: non-NULL values before every row tile [ntiles + 1]
+  u64 nbytes;            // payload bytes
+  u32 kind;              // EVQ_KIND_*
+  u32 bits;              // bit width (BITPACK / LEVEL)
+  u32 smem_off;          // byte offset of this stream inside a pipeline stage
+  u32 smem_cap;          // bytes reserved in a stage
+};
+
+struct EvqHashTable {
+  u64* fp;      // [cap] 0 = empty; bit0 = 1 always; bit1 = 1 while the claiming thread still writes the key
+  u64* keys;    // [nkeys][cap] raw 64-bit key values
+  u8* ktags;    // [nkeys][cap] STag of each key value
+  u64* state;   // [nstate][cap] aggregate states
+  u64 cap;      // power of two
+};
+
+struct EvqScanParams {
+  u64 num_rows;
+  u32 num_tiles;
+  u32 num_streams;
+  EvqStream streams[EVQ_MAX_STREAMS];
+  // aggregation state
+  u64* dense_state;                 // tier 1: [G1][NSTATE] merged across CTAs with atomics
+  EvqHashTable ht;                  // tier 2
+  u64 key_min[EVQ_MAX_KEYS];        // tier 1 dense slot = sum((key - min) * stride), NULL -> null_idx * stride
+  u64 key_stride[EVQ_MAX_KEYS];
+  u64 key_null_idx[EVQ_MAX_KEYS];
+  u64 dense_slots;                  // number of valid dense slots (<= EVQ_G1)
+  // scan-only output
+  u64* tile_counts;                 // pass 1: rows passing WHERE per tile
+  const u64* tile_out_base;         // pass 2: exclusive prefix of tile_counts (+ table base)
+  u8* out_cols[EVQ_MAX_STREAMS];    // pass 2: packed SVector output per select item
+  // bookkeeping
+  u32* status;                      // [0] error bits, [1] unused
+  u64* counters;                    // [0] rows passed, [1] groups claimed (tier 2)
+  u64 tile_row_base;                // first tile index of this table inside tile_counts
+};
+
+
+#endif  // EVQ_ABI_H

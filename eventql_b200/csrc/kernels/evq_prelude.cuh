@@ -1,0 +1,421 @@
+// evq_prelude.cuh - fixed device-side prelude of every query kernel (sm_100a).
+//
+// This text is compiled twice: by nvcc (static checks in build.py, -lineinfo / -Xptxas -v) and by
+// NVRTC at query time, specialised by the #defines + generated row functions that
+// csrc/codegen.cc puts in front of / behind it.  It must therefore not include any header.
+//
+// What is in here
+//   * PTX wrappers: mbarrier, cp.async.bulk (TMA 1-D bulk copy global -> shared), named barriers
+//   * the tile pipeline structures shared by producer warp and consumer warps
+//   * cstable page decoders reading from the staged shared-memory tile:
+//       plain u64/u32/f64      io/cstable/columns/page_reader_uint64.cc:50-70, _uint32.cc:50-71, _ieee754.cc:38-59
+//       libsimdcomp vertical   deps/3rdparty/libsimdcomp/simdbitpacking.c:13793 (simdunpack), SURVEY A.4
+//       unsigned LEB128        io/cstable/columns/page_reader_leb128.cc:50-72
+//       definition levels      io/cstable/columns/column_reader_uint.cc:92-115 (value only if d == dmax)
+//   * the global open-addressing group table (GroupByExpression's unordered_map,
+//     sql/statements/select/groupby.cc:129-149) with atomics for the aggregate states
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ u32 evq_smem_u32(const void* p) {
+  return (u32) __cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void evq_mbar_init(u64* bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(evq_smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void evq_mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void evq_mbar_arrive(u64* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(evq_smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void evq_mbar_arrive_expect_tx(u64* bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(evq_smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void evq_mbar_wait(u64* bar, u32 parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "EVQ_WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra EVQ_WAIT_DONE;\n"
+      "bra EVQ_WAIT_LOOP;\n"
+      "EVQ_WAIT_DONE:\n"
+      "}\n" :: "r"(evq_smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP).
+// dst, src and bytes must be multiples of 16.
+__device__ __forceinline__ void evq_bulk_g2s(void* dst_smem, const void* src_gmem, u32 bytes, u64* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(evq_smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(evq_smem_u32(bar)) : "memory");
+}
+
+// named barrier over the consumer warps only (the producer warp never joins it)
+__device__ __forceinline__ void evq_cons_sync() {
+  asm volatile("bar.sync 1, %0;" :: "n"(EVQ_NCONS) : "memory");
+}
+
+__device__ __forceinline__ u32 evq_lane() { return threadIdx.x & 31u; }
+
+// ---- pipeline stage bookkeeping ------------------------------------------------------------------------------------
+
+struct EvqStreamDesc {   // written by the producer lane that issued the copy, read by all consumers
+  u32 delta;   // offset of the first payload byte inside the stream's stage region
+  u32 nbytes;  // payload bytes of this tile
+  u32 nvals;   // values of this tile in the stream
+  u32 skew;    // BITPACK: index of the first value inside its first 128-block
+};
+
+struct EvqTile {         // per-consumer-thread view of the tile being processed
+  const u8* stage;             // shared memory base of the stage
+  const EvqStreamDesc* desc;   // [EVQ_NSTREAMS]
+  u32 rows;                    // rows in this tile
+  u32 ctid;                    // consumer thread id 0..EVQ_NCONS-1
+  u32 parity;                  // scratch double-buffer selector
+  u64 row0;                    // table row of the tile's first row
+};
+
+// Issue the bulk copies of one row tile. Called by all 32 lanes of the producer warp; lane i owns stream i.
+__device__ __forceinline__ void evq_producer_issue(const EvqScanParams& P, u32 tile, u8* stage, EvqStreamDesc* desc,
+                                                   u64* full_bar) {
+  const u32 lane = evq_lane();
+  u32 bytes = 0;
+  const u8* src = 0;
+  u32 dst_off = 0;
+  if (lane < P.num_streams) {
+    const EvqStream& S = P.streams[lane];
+    const u64 row0 = (u64) tile * EVQ_TILE_ROWS;
+    const u64 rem = P.num_rows - row0;
+    const u32 rows = rem < EVQ_TILE_ROWS ? (u32) rem : EVQ_TILE_ROWS;
+    u64 start, end;
+    u32 nvals = rows, skew = 0;
+    if (S.kind == EVQ_KIND_LEVEL) {
+      const u64 blk0 = row0 >> 7, blk1 = (row0 + rows + 127) >> 7;
+      start = blk0 * 16 * S.bits;
+      end = blk1 * 16 * S.bits;
+    } else {
+      u64 v0 = row0, v1 = row0 + rows;
+      if (S.val_index) {
+        v0 = S.val_index[tile];
+        v1 = S.val_index[tile + 1];
+      }
+      nvals = (u32) (v1 - v0);
+      if (S.kind == EVQ_KIND_PLAIN64) {
+        start = v0 * 8; end = v1 * 8;
+      } else if (S.kind == EVQ_KIND_PLAIN32) {
+        start = v0 * 4; end = v1 * 4;
+      } else if (S.kind == EVQ_KIND_BITPACK) {
+        const u64 blk0 = v0 >> 7, blk1 = (v1 + 127) >> 7;
+        start = blk0 * 16 * S.bits;
+        end = blk1 * 16 * S.bits;
+        skew = (u32) (v0 - (blk0 << 7));
+      } else {
+        start = S.off_index[tile];
+        end = S.off_index[tile + 1];
+      }
+    }
+    const u64 al = start & ~15ull;
+    bytes = (u32) (((end - al) + 15) & ~15ull);
+    if (end == start) bytes = 0;
+    if (bytes > S.smem_cap) {   // the host sized the stage from the tile index: cannot happen unless that is wrong
+      atomicOr(P.status, EVQ_ERR_STAGE_OVERFLOW);
+      bytes = S.smem_cap & ~15u;
+    }
+    src = S.base + al;
+    dst_off = S.smem_off;
+    EvqStreamDesc d;
+    d.delta = (u32) (start - al);
+    d.nbytes = (u32) (end - start);
+    d.nvals = nvals;
+    d.skew = skew;
+    desc[lane] = d;
+  }
+  u32 total = bytes;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+  __syncwarp();
+  if (lane == 0) evq_mbar_arrive_expect_tx(full_bar, total);
+  __syncwarp();
+  if (bytes) evq_bulk_g2s(stage + dst_off, src, bytes, full_bar);
+}
+
+// ---- decoders over the staged tile ------------------------------------------------------------------------------------
+
+__device__ __forceinline__ u64 evq_ld_plain64(const EvqTile& T, u32 s, u32 off, u32 idx) {
+  return *(const u64*) (T.stage + off + T.desc[s].delta + 8u * idx);
+}
+
+__device__ __forceinline__ u64 evq_ld_plain32(const EvqTile& T, u32 s, u32 off, u32 idx) {
+  return (u64) * (const u32*) (T.stage + off + T.desc[s].delta + 4u * idx);
+}
+
+// libsimdcomp vertical layout: value i of a 128-block lives in lane i%4 at bit (i/4)*b of that lane's stream
+__device__ __forceinline__ u32 evq_unpack_vertical(const u32* words, u32 v, u32 b) {
+  const u32 blk = v >> 7, i = v & 127u;
+  const u32 o = (i >> 2) * b;
+  const u32* w = words + blk * 4u * b + 4u * (o >> 5) + (i & 3u);
+  const u32 sh = o & 31u;
+  u32 x = w[0] >> sh;
+  if (sh + b > 32u) x |= w[4] << (32u - sh);
+  return b >= 32u ? x : (x & ((1u << b) - 1u));
+}
+
+__device__ __forceinline__ u64 evq_ld_bitpack(const EvqTile& T, u32 s, u32 off, u32 idx, u32 bits) {
+  const EvqStreamDesc& d = T.desc[s];
+  return (u64) evq_unpack_vertical((const u32*) (T.stage + off + d.delta), d.skew + idx, bits);
+}
+
+// definition level of row r of the tile (LEVEL streams are row-indexed; tiles start on a 128-block boundary)
+__device__ __forceinline__ u32 evq_ld_level(const EvqTile& T, u32 s, u32 off, u32 r, u32 bits) {
+  return evq_unpack_vertical((const u32*) (T.stage + off + T.desc[s].delta), r, bits);
+}
+
+// 8 bytes at an arbitrary shared-memory byte offset (regions are padded, over-read is safe)
+__device__ __forceinline__ void evq_lds_unaligned64(const u8* p, u32& lo, u32& hi) {
+  const u32 a = evq_smem_u32(p);
+  const u32* w = (const u32*) (p - (a & 3u));
+  const u32 sh = (a & 3u) * 8u;
+  const u32 w0 = w[0], w1 = w[1], w2 = w[2];
+  lo = __funnelshift_r(w0, w1, sh);
+  hi = __funnelshift_r(w1, w2, sh);
+}
+
+__device__ __forceinline__ u32 evq_leb_pack4(u32 x) {
+  return (x & 0x7fu) | ((x & 0x7f00u) >> 1) | ((x & 0x7f0000u) >> 2) | ((x & 0x7f000000u) >> 3);
+}
+
+// decode one unsigned LEB128 value of `len` bytes (1..10) starting at p
+__device__ __forceinline__ u64 evq_leb_decode(const u8* p, u32 len) {
+  u32 lo, hi;
+  evq_lds_unaligned64(p, lo, hi);
+  u64 v = evq_leb_pack4(lo);
+  if (len < 4u) {
+    v &= (1ull << (7u * len)) - 1ull;
+  } else if (len > 4u) {
+    u64 h = evq_leb_pack4(hi);
+    if (len < 8u) h &= (1ull << (7u * (len - 4u))) - 1ull;
+    v |= h << 28;
+    if (len > 8u) {
+      v |= ((u64) (p[8] & 0x7fu)) << 56;
+      if (len > 9u) v |= ((u64) (p[9] & 0x7fu)) << 63;
+    }
+  }
+  return v;
+}
+
+// bit i of the result = byte i of the 16-byte chunk terminates a value (msb clear)
+__device__ __forceinline__ u32 evq_term_mask16(uint4 c) {
+  u32 m = 0;
+  u32 w[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const u32 t = ~w[k] & 0x80808080u;                 // 0x80 in every terminating byte
+    const u32 nib = (t * 0x00204081u) >> 28;           // gather bits 7,15,23,31 -> 4 bits
+    m |= (nib & 0xfu) << (4 * k);
+  }
+  return m;
+}
+
+// terminator bit pattern of a run of w-byte values: bit k set iff k % w == w-1
+__device__ __forceinline__ u64 evq_uniform_pattern(u32 w) {
+  switch (w) {
+    case 1: return 0xffffffffffffffffull;
+    case 2: return 0xaaaaaaaaaaaaaaaaull;
+    case 3: return 0x4924924924924924ull;
+    case 4: return 0x8888888888888888ull;
+    case 5: return 0x0842108421084210ull;
+    case 6: return 0x0820820820820820ull;
+    case 7: return 0x4081020408102040ull;
+    case 8: return 0x8080808080808080ull;
+    case 9: return 0x4020100804020100ull;
+    default: return 0x0802008020080200ull;  // 10
+  }
+}
+
+// Per-tile state of one LEB128 column
+struct EvqLebState {
+  u32 mode;     // 0 = every value is 1 byte, >0 = every value is `mode` bytes, 0xffffffff = general (use endpos)
+  u32 base;     // smem byte offset of the first payload byte
+};
+
+#define EVQ_LEB_GENERAL 0xffffffffu
+
+// ---- group table (tier 2) ------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ u64 evq_mix64(u64 x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull;
+  x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull;
+  x ^= x >> 33;
+  return x;
+}
+
+// Group-table words are read and written at L2 (relaxed, gpu scope): no L1 line can go stale and no probe pays
+// for an L1 invalidation.  The claimant orders "key written" before "fingerprint published" with one fence.
+__device__ __forceinline__ u64 evq_ld_l2(const u64* p) {
+  u64 v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ u32 evq_ld_l2_u8(const u8* p) {
+  u32 v;
+  asm volatile("ld.relaxed.gpu.global.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void evq_st_l2(u64* p, u64 v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void evq_st_l2_u8(u8* p, u32 v) {
+  asm volatile("st.relaxed.gpu.global.u8 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// find or claim the slot of a key tuple. Returns the slot, or ~0ull when the table is full.
+template <int NK>
+__device__ __forceinline__ u64 evq_ht_upsert(const EvqHashTable& H, const u64* key, const u32* tag, u64* claimed_counter) {
+  u64 h = 0x9e3779b97f4a7c15ull;
+#pragma unroll
+  for (int i = 0; i < NK; ++i) h = evq_mix64(h ^ key[i] ^ ((u64) tag[i] << 57)) + 0x632be59bd9b4e019ull * (u64) (i + 1);
+  const u64 fpv = (h & ~3ull) | 1ull;
+  const u64 mask = H.cap - 1;
+  u64 slot = (h >> 7) & mask;
+  for (u64 probes = 0; probes <= mask; ++probes) {
+    u64 cur = evq_ld_l2(H.fp + slot);
+    if (cur == 0) {
+      cur = atomicCAS(H.fp + slot, 0ull, fpv | 2ull);
+      if (cur == 0) {
+#pragma unroll
+        for (int i = 0; i < NK; ++i) {
+          evq_st_l2(H.keys + (u64) i * H.cap + slot, key[i]);
+          evq_st_l2_u8(H.ktags + (u64) i * H.cap + slot, tag[i]);
+        }
+        __threadfence();
+        evq_st_l2(H.fp + slot, fpv);
+        atomicAdd(claimed_counter, 1ull);
+        return slot;
+      }
+    }
+    if ((cur | 2ull) == (fpv | 2ull)) {
+      while (cur & 2ull) cur = evq_ld_l2(H.fp + slot);   // the claimant is still writing the key
+      bool same = true;
+#pragma unroll
+      for (int i = 0; i < NK; ++i) {
+        same = same && (evq_ld_l2(H.keys + (u64) i * H.cap + slot) == key[i]) &&
+               (evq_ld_l2_u8(H.ktags + (u64) i * H.cap + slot) == (tag[i] & 0xffu));
+      }
+      if (same) return slot;
+    }
+    slot = (slot + 1) & mask;
+  }
+  return ~0ull;
+}
+
+// ---- aggregate state updates ------------------------------------------------------------------------------------------
+// state identities: sum/count 0; min = all ones (u64) / INT64_MAX / +inf; max = 0 / INT64_MIN / -inf; "seen" counters 0
+
+__device__ __forceinline__ void evq_atomic_min_f64(u64* addr, f64 v) {
+  u64 old = *addr;
+  while (v < __longlong_as_double((i64) old)) {
+    const u64 prev = atomicCAS(addr, old, (u64) __double_as_longlong(v));
+    if (prev == old) break;
+    old = prev;
+  }
+}
+
+__device__ __forceinline__ void evq_atomic_max_f64(u64* addr, f64 v) {
+  u64 old = *addr;
+  while (v > __longlong_as_double((i64) old)) {
+    const u64 prev = atomicCAS(addr, old, (u64) __double_as_longlong(v));
+    if (prev == old) break;
+    old = prev;
+  }
+}
+
+// op codes of one state word (mirrored in csrc/codegen.cc)
+#define EVQ_OP_ADD_U64 0
+#define EVQ_OP_ADD_F64 1
+#define EVQ_OP_MIN_U64 2
+#define EVQ_OP_MAX_U64 3
+#define EVQ_OP_MIN_I64 4
+#define EVQ_OP_MAX_I64 5
+#define EVQ_OP_MIN_F64 6
+#define EVQ_OP_MAX_F64 7
+
+template <int OP>
+__device__ __forceinline__ u64 evq_state_identity() {
+  switch (OP) {
+    case EVQ_OP_MIN_U64: return ~0ull;
+    case EVQ_OP_MIN_I64: return 0x7fffffffffffffffull;
+    case EVQ_OP_MAX_I64: return 0x8000000000000000ull;
+    case EVQ_OP_MIN_F64: return 0x7ff0000000000000ull;
+    case EVQ_OP_MAX_F64: return 0xfff0000000000000ull;
+    default: return 0ull;
+  }
+}
+
+// combine two partial states (thread-private -> CTA -> global; also the cross-GPU merge)
+template <int OP>
+__device__ __forceinline__ u64 evq_state_combine(u64 a, u64 b) {
+  switch (OP) {
+    case EVQ_OP_ADD_U64: return a + b;
+    case EVQ_OP_ADD_F64: return (u64) __double_as_longlong(__longlong_as_double((i64) a) + __longlong_as_double((i64) b));
+    case EVQ_OP_MIN_U64: return a < b ? a : b;
+    case EVQ_OP_MAX_U64: return a > b ? a : b;
+    case EVQ_OP_MIN_I64: return (i64) a < (i64) b ? a : b;
+    case EVQ_OP_MAX_I64: return (i64) a > (i64) b ? a : b;
+    case EVQ_OP_MIN_F64: return __longlong_as_double((i64) a) < __longlong_as_double((i64) b) ? a : b;
+    default: return __longlong_as_double((i64) a) > __longlong_as_double((i64) b) ? a : b;
+  }
+}
+
+template <int OP>
+__device__ __forceinline__ void evq_state_atomic(u64* addr, u64 v) {
+  switch (OP) {
+    case EVQ_OP_ADD_U64: atomicAdd(addr, v); break;
+    case EVQ_OP_ADD_F64: atomicAdd((f64*) addr, __longlong_as_double((i64) v)); break;
+    case EVQ_OP_MIN_U64: atomicMin(addr, v); break;
+    case EVQ_OP_MAX_U64: atomicMax(addr, v); break;
+    case EVQ_OP_MIN_I64: atomicMin((i64*) addr, (i64) v); break;
+    case EVQ_OP_MAX_I64: atomicMax((i64*) addr, (i64) v); break;
+    case EVQ_OP_MIN_F64: evq_atomic_min_f64(addr, __longlong_as_double((i64) v)); break;
+    default: evq_atomic_max_f64(addr, __longlong_as_double((i64) v)); break;
+  }
+}
+
+// ---- expression helpers (semantics of sql/expressions/math.cc, boolean.cc, conversion.cc) ------------------------------
+
+__device__ __forceinline__ u64 evq_div_u64(u64 a, u64 b, u32& err) {
+  if (b == 0) { err |= EVQ_ERR_DIV_ZERO; return 0; }
+  return a / b;
+}
+__device__ __forceinline__ u64 evq_mod_u64(u64 a, u64 b, u32& err) {
+  if (b == 0) { err |= EVQ_ERR_MOD_ZERO; return 0; }
+  return a % b;
+}
+__device__ __forceinline__ i64 evq_div_i64(i64 a, i64 b, u32& err) {
+  if (b == 0) { err |= EVQ_ERR_DIV_ZERO; return 0; }
+  if (b == -1) return (i64) (0ull - (u64) a);
+  return a / b;
+}
+__device__ __forceinline__ i64 evq_mod_i64(i64 a, i64 b, u32& err) {
+  if (b == 0) { err |= EVQ_ERR_MOD_ZERO; return 0; }
+  if (b == -1) return 0;
+  return a % b;
+}
+__device__ __forceinline__ f64 evq_f64(u64 bits) { return __longlong_as_double((i64) bits); }
+__device__ __forceinline__ u64 evq_bits(f64 v) { return (u64) __double_as_longlong(v); }
+
+// write one packed SVector element (sql/svalue.cc:533-549): [8 B value][1 B tag], unaligned
+__device__ __forceinline__ void evq_store_packed9(u8* dst, u64 v, u32 tag) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dst[i] = (u8) (v >> (8 * i));
+  dst[8] = (u8) tag;
+}
+__device__ __forceinline__ void evq_store_packed2(u8* dst, u64 v, u32 tag) {
+  dst[0] = (u8) (v != 0);
+  dst[1] = (u8) tag;
+}

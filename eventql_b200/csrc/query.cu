@@ -1,0 +1,767 @@
+// query.cc - evqgpu_query: plan intake, kernel specialisation, launches, result fetch.
+//
+// Operator mapping (reference, src/eventql/sql/):
+//   evqgpu_query_create   FastCSTableScan::execute (CSTableScan.cc:726-755) + Compiler::compile's split of every
+//                         select item into an accumulate program and a get program (runtime/compiler.cc:50-104)
+//   evqgpu_query_execute  the nextBatch loop of FastCSTableScan (CSTableScan.cc:757-858) drained by
+//                         GroupByExpression::execute (statements/select/groupby.cc:69-185)
+//   evqgpu_query_fetch    GroupByExpression::nextBatch (groupby.cc:187-220) / the scan's own output batches
+#include "query.h"
+#include <cub/device/device_scan.cuh>
+#include <string.h>
+#include <algorithm>
+#include <cmath>
+
+using namespace evq;
+
+namespace evq {
+
+static uint64_t next_pow2(uint64_t v) {
+  uint64_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+static void launch(evqgpu_ctx* ctx, cudaKernel_t k, dim3 grid, dim3 block, size_t smem, void** args) {
+  EVQ_CUDA(cudaLaunchKernel((const void*) k, grid, block, args, smem, ctx->stream));
+  ctx->kernel_launches++;
+}
+
+static void ensure(DevBuf& b, uint64_t bytes) {
+  if (b.bytes < bytes) b.alloc(bytes);
+}
+
+// ---- binding of the plan's input columns to one table -------------------------------------------------------------
+struct Binding {
+  std::vector<int> col_index;   // plan input column -> table column (or -1 when unused)
+};
+
+static Binding bind_table(const evqgpu_query& q, evqgpu_table* t) {
+  Binding b;
+  b.col_index.assign(q.input_columns.size(), -1);
+  for (size_t i = 0; i < q.input_columns.size(); ++i) {
+    if (!q.col_used[i]) continue;
+    const int ci = t->find(q.input_columns[i].c_str());
+    if (ci < 0) fail(EVQGPU_ERR_ARG, "column not found: %s", q.input_columns[i].c_str());
+    if (!t->cols[ci].loaded) table_load_column(t, t->cols[ci]);
+    b.col_index[i] = ci;
+  }
+  return b;
+}
+
+static KernelShape shape_for(const evqgpu_query& q, evqgpu_table* t, const Binding& b) {
+  KernelShape s;
+  s.cols.resize(q.input_columns.size());
+  for (size_t i = 0; i < q.input_columns.size(); ++i) {
+    if (b.col_index[i] < 0) continue;
+    const Column& c = t->cols[b.col_index[i]];
+    ColSig& cs = s.cols[i];
+    cs.used = true;
+    cs.sql_type = c.sql_type;
+    cs.kind = c.data_kind;
+    cs.nullable = c.meta.dlevel_max > 0;
+    cs.dmax = c.meta.dlevel_max;
+    cs.data_stream = s.nstreams++;
+    if (cs.nullable) {
+      cs.level_stream = s.nstreams++;
+      cs.null_slot = s.nnull++;
+    }
+    if (cs.kind == EVQ_KIND_LEB128) cs.leb_slot = s.nleb++;
+  }
+  if (s.nstreams > EVQ_MAX_STREAMS)
+    fail(EVQGPU_ERR_UNSUPPORTED, "query reads %d column streams; the scan kernel stages at most %d", s.nstreams, EVQ_MAX_STREAMS);
+  return s;
+}
+
+static std::string shape_key(const KernelShape& s) {
+  std::string k;
+  for (const auto& c : s.cols) {
+    char buf[64];
+    snprintf(buf, sizeof(buf), "%d:%u:%u:%d:%u|", (int) c.used, c.sql_type, c.kind, (int) c.nullable, c.dmax);
+    k += buf;
+  }
+  return k;
+}
+
+// per-table stage layout: where every stream lands inside one pipeline stage
+struct StageLayout {
+  uint32_t smem_off[EVQ_MAX_STREAMS] = {0};
+  uint32_t smem_cap[EVQ_MAX_STREAMS] = {0};
+  uint32_t stage_bytes = 0;
+};
+
+static StageLayout stage_layout(const evqgpu_query& q, evqgpu_table* t, const Binding& b, const KernelShape& s) {
+  StageLayout L;
+  L = StageLayout();
+  uint32_t off = 0;
+  for (size_t i = 0; i < s.cols.size(); ++i) {
+    const ColSig& cs = s.cols[i];
+    if (!cs.used) continue;
+    const Column& c = t->cols[b.col_index[i]];
+    auto place = [&](int stream, uint32_t cap) {
+      cap = (uint32_t) round_up(cap, 16) + 16;   // decoders may read up to 12 bytes past the payload
+      L.smem_off[stream] = off;
+      L.smem_cap[stream] = cap;
+      off += (uint32_t) round_up(cap, 128);
+    };
+    place(cs.data_stream, c.data_tile_cap);
+    if (cs.nullable) place(cs.level_stream, c.level_tile_cap);
+  }
+  L.stage_bytes = std::max<uint32_t>(off, 128);
+  (void) q;
+  return L;
+}
+
+static size_t scratch_bytes(const KernelShape& s) {
+  const size_t nwarps = s.ncons / 32;
+  const size_t one = 4 * std::max(1, s.nleb) * nwarps + 4 * std::max(1, s.nnull) * (EVQ_TILE_ROWS / 32) +
+                     2 * std::max(1, s.nleb) * EVQ_TILE_ROWS + 4 * nwarps;
+  return round_up(2 * round_up(one, 8), 128) + 128;
+}
+
+static size_t header_bytes(const KernelShape& s) {
+  const size_t raw = 8 * 4 + 8 * 4 + 4 * 4 + 16 * 4 * std::max(1, s.nstreams);
+  return round_up(raw, 128);
+}
+
+static size_t acc_bytes(const evqgpu_query& q, const KernelShape& s) {
+  if (s.tier != 1 || s.g1 <= 1) return 0;
+  return (size_t) s.g1 * q.state_ops.size() * s.ncons * 8;
+}
+
+}  // namespace evq
+
+// ---- plan intake -----------------------------------------------------------------------------------------------------
+
+static void check_scalar_item(const evqgpu_query& q, const Expr* e) {
+  // non-aggregate select items must be functions of the GROUP BY key (the reference takes the group's first row,
+  // groupby.cc:161-172, which is only deterministic in that case); verified by trying to generate the emit code
+  CodegenEnv env;
+  env.col_value.assign(q.input_columns.size(), "");
+  env.col_tag.assign(q.input_columns.size(), "");
+  for (size_t i = 0; i < q.group.size(); ++i) env.subst.push_back({q.group[i]->signature(), {"k", "t"}});
+  (void) gen_expr(e, env);
+}
+
+namespace evq {
+
+void query_intake(evqgpu_query* q, const evqgpu_query_desc* desc) {
+  if (desc->struct_size != sizeof(evqgpu_query_desc)) fail(EVQGPU_ERR_ARG, "evqgpu_query_desc: struct_size mismatch");
+  q->flags = desc->flags;
+  q->expected_groups = desc->expected_groups;
+  for (uint32_t i = 0; i < desc->num_input_columns; ++i) q->input_columns.push_back(desc->input_columns[i]);
+  q->where = parse_program(desc->where);
+  if (q->where && q->where->type != EVQ_BOOL) fail(EVQGPU_ERR_ARG, "WHERE expression must be of type bool");
+  if (q->where && find_aggregate(q->where.get())) fail(EVQGPU_ERR_ARG, "aggregate call in WHERE");
+  if (desc->num_group > EVQ_MAX_KEYS) fail(EVQGPU_ERR_UNSUPPORTED, "at most %d GROUP BY expressions", EVQ_MAX_KEYS);
+  if (desc->num_select == 0 || desc->num_select > EVQ_MAX_STREAMS)
+    fail(EVQGPU_ERR_UNSUPPORTED, "select list must have 1..%d items", EVQ_MAX_STREAMS);
+  for (uint32_t i = 0; i < desc->num_group; ++i) {
+    ExprPtr g = parse_program(desc->group[i]);
+    if (!g) fail(EVQGPU_ERR_ARG, "empty GROUP BY expression");
+    if (find_aggregate(g.get())) fail(EVQGPU_ERR_ARG, "aggregate call in GROUP BY");
+    if (g->type == EVQ_STRING || g->type == EVQ_NIL) fail(EVQGPU_ERR_UNSUPPORTED, "GROUP BY key type is outside the numeric device path");
+    q->group.push_back(std::move(g));
+  }
+  const bool groupby = q->flags & EVQGPU_QUERY_GROUPBY;
+  q->state_ops.push_back(OP_ADD_U64);   // word 0: rows per group
+  for (uint32_t i = 0; i < desc->num_select; ++i) {
+    SelectItem item;
+    item.expr = parse_program(desc->select[i]);
+    if (!item.expr) fail(EVQGPU_ERR_ARG, "empty select expression");
+    if (item.expr->type == EVQ_STRING || item.expr->type == EVQ_NIL)
+      fail(EVQGPU_ERR_UNSUPPORTED, "select item %u: result type is outside the numeric device path", i);
+    item.agg = find_aggregate(item.expr.get());
+    if (item.agg && !groupby) fail(EVQGPU_ERR_ARG, "aggregate call in a scan-only plan");
+    if (item.agg) {
+      const FnInfo& fi = item.agg->info();
+      const int words = state_words_of(fi);
+      if (words > 0) {
+        item.state0 = (int) q->state_ops.size();
+        const int ty = fi.args[0];
+        if (fi.fn == Fn::SUM) q->state_ops.push_back(ty == EVQ_FLOAT64 ? OP_ADD_F64 : OP_ADD_U64);
+        else if (fi.fn == Fn::MEAN) { q->state_ops.push_back(OP_ADD_F64); q->state_ops.push_back(OP_ADD_U64); }
+        else {
+          const bool mx = fi.fn == Fn::MAX;
+          q->state_ops.push_back(ty == EVQ_INT64 ? (mx ? OP_MAX_I64 : OP_MIN_I64)
+                                 : ty == EVQ_FLOAT64 ? (mx ? OP_MAX_F64 : OP_MIN_F64) : (mx ? OP_MAX_U64 : OP_MIN_U64));
+          q->state_ops.push_back(OP_ADD_U64);
+        }
+      } else {
+        item.state0 = 0;
+      }
+      for (const auto& a : item.agg->args)
+        if (find_aggregate(a.get())) fail(EVQGPU_ERR_ARG, "nested aggregate call");
+    }
+    q->select.push_back(std::move(item));
+  }
+  if (groupby)
+    for (const auto& item : q->select)
+      if (!item.agg) check_scalar_item(*q, item.expr.get());
+  // which input columns does the device actually have to read
+  q->col_used.assign(q->input_columns.size(), false);
+  collect_columns(q->where.get(), q->col_used);
+  for (const auto& g : q->group) collect_columns(g.get(), q->col_used);
+  for (const auto& item : q->select) {
+    if (!groupby) collect_columns(item.expr.get(), q->col_used);
+    else if (item.agg) for (const auto& a : item.agg->args) collect_columns(a.get(), q->col_used);
+  }
+}
+
+}  // namespace evq
+
+extern "C" {
+
+int evqgpu_query_create(evqgpu_ctx* ctx, const evqgpu_query_desc* desc, evqgpu_query** out) {
+  return guarded([&] {
+    if (!ctx || !desc || !out) fail(EVQGPU_ERR_ARG, "evqgpu_query_create: null argument");
+    std::unique_ptr<evqgpu_query> q(new evqgpu_query());
+    q->ctx = ctx;
+    query_intake(q.get(), desc);
+    use_device(ctx);
+    q->status.alloc(16);
+    q->counters.alloc(32);
+    q->out_count.alloc(8);
+    *out = q.release();
+  });
+}
+
+void evqgpu_query_destroy(evqgpu_query* q) {
+  if (!q) return;
+  cudaSetDevice(q->ctx->device);
+  delete q;
+}
+
+uint32_t evqgpu_query_num_columns(const evqgpu_query* q) { return q ? (uint32_t) q->select.size() : 0; }
+uint32_t evqgpu_query_column_type(const evqgpu_query* q, uint32_t idx) {
+  return (q && idx < q->select.size()) ? (uint32_t) q->select[idx].expr->type : 0;
+}
+
+}  // extern "C"
+
+// ---- execution -------------------------------------------------------------------------------------------------------
+namespace evq {
+
+struct TablePlan {
+  evqgpu_table* table;
+  Binding binding;
+  StageLayout layout;
+  size_t smem = 0;
+};
+
+static void fill_streams(EvqScanParams& P, evqgpu_table* t, const Binding& b, const KernelShape& s, const StageLayout& L) {
+  P.num_rows = t->num_rows;
+  P.num_tiles = t->num_tiles;
+  P.num_streams = (u32) s.nstreams;
+  for (size_t i = 0; i < s.cols.size(); ++i) {
+    const ColSig& cs = s.cols[i];
+    if (!cs.used) continue;
+    const Column& c = t->cols[b.col_index[i]];
+    EvqStream& d = P.streams[cs.data_stream];
+    d.base = c.data.buf.as<u8>();
+    d.off_index = c.data_kind == EVQ_KIND_LEB128 ? c.off_index.as<u64>() : nullptr;
+    d.val_index = cs.nullable ? c.val_index.as<u64>() : nullptr;
+    d.nbytes = c.data.nbytes;
+    d.kind = c.data_kind;
+    d.bits = c.data_bits;
+    d.smem_off = L.smem_off[cs.data_stream];
+    d.smem_cap = L.smem_cap[cs.data_stream];
+    if (cs.nullable) {
+      EvqStream& l = P.streams[cs.level_stream];
+      l.base = c.dlevel.buf.as<u8>();
+      l.off_index = nullptr;
+      l.val_index = nullptr;
+      l.nbytes = c.dlevel.nbytes;
+      l.kind = EVQ_KIND_LEVEL;
+      l.bits = c.level_bits;
+      l.smem_off = L.smem_off[cs.level_stream];
+      l.smem_cap = L.smem_cap[cs.level_stream];
+    }
+  }
+}
+
+static uint64_t algorithmic_bytes(const evqgpu_query& q, const std::vector<TablePlan>& plans) {
+  uint64_t n = 0;
+  for (const auto& p : plans)
+    for (size_t i = 0; i < q.input_columns.size(); ++i)
+      if (p.binding.col_index[i] >= 0) {
+        const Column& c = p.table->cols[p.binding.col_index[i]];
+        n += c.data_payload_bytes + c.level_payload_bytes;
+      }
+  return n;
+}
+
+// choose thread count / stages so the CTA fits; returns dynamic smem bytes of the largest table
+static void fit_shape(evqgpu_query& q, KernelShape& s, std::vector<TablePlan>& plans) {
+  const size_t limit = (size_t) q.ctx->smem_optin;
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    s.ncons = (attempt & 1) ? 128 : 256;
+    s.nstages = (attempt & 2) ? 2 : 3;
+    size_t worst = 0;
+    for (auto& p : plans) {
+      p.layout = stage_layout(q, p.table, p.binding, s);
+      p.smem = header_bytes(s) + (size_t) s.nstages * p.layout.stage_bytes + scratch_bytes(s) + acc_bytes(q, s);
+      worst = std::max(worst, p.smem);
+    }
+    if (worst <= limit) {
+      // two CTAs per SM when they fit: better latency hiding for the decode phases
+      s.min_ctas = (worst * 2 + 2048 <= 228 * 1024) ? 2 : 1;
+      return;
+    }
+  }
+  fail(EVQGPU_ERR_UNSUPPORTED, "row tile of this query does not fit shared memory (%zu columns)", q.input_columns.size());
+}
+
+static void run_scan(evqgpu_query& q, const KernelShape& s, std::vector<TablePlan>& plans, EvqScanParams base) {
+  evqgpu_ctx* ctx = q.ctx;
+  cudaKernel_t kern = q.module->kernels.at("evq_scan");
+  size_t max_smem = 0;
+  for (const auto& p : plans) max_smem = std::max(max_smem, p.smem);
+  EVQ_CUDA(cudaFuncSetAttribute((const void*) kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) max_smem));
+  uint64_t tile_row_base = 0;
+  for (auto& p : plans) {
+    if (p.table->num_tiles == 0) continue;
+    EvqScanParams P = base;
+    fill_streams(P, p.table, p.binding, s, p.layout);
+    P.tile_row_base = tile_row_base;
+    tile_row_base += p.table->num_tiles;
+    u32 stage_bytes = p.layout.stage_bytes;
+    const int ctas_per_sm = std::max<int>(1, std::min<size_t>(s.min_ctas == 2 ? 2 : 1, (228 * 1024) / (p.smem + 1024)));
+    const unsigned grid = (unsigned) std::min<uint64_t>(p.table->num_tiles, (uint64_t) ctx->sm_count * ctas_per_sm);
+    void* args[] = {&P, &stage_bytes};
+    launch(ctx, kern, dim3(grid), dim3(s.ncons + 32), p.smem, args);
+    q.stats.kernel_launches++;
+  }
+}
+
+// smallest dense slot capacity the kernel is specialised for
+static int g1_for(uint64_t slots) {
+  int g = 2;
+  while ((uint64_t) g < slots) g <<= 1;
+  return g;
+}
+
+// only a bare column reference (possibly through `if`) keeps its NULL tag; every function call drops it
+static bool key_may_be_null(const Expr* e, const std::vector<bool>& nullable_cols) {
+  if (e->op == EVQ_X_INPUT) return e->col < nullable_cols.size() && nullable_cols[e->col];
+  if (e->op == EVQ_X_IF) return key_may_be_null(e->args[1].get(), nullable_cols) || key_may_be_null(e->args[2].get(), nullable_cols);
+  return false;
+}
+
+static bool key_dense_capable(const Expr* g) {
+  return g->type == EVQ_UINT64 || g->type == EVQ_TIMESTAMP64 || g->type == EVQ_BOOL || g->type == EVQ_INT64;
+}
+
+// Bounds pre-pass: min/max of every GROUP BY expression over the tables, computed with the scan kernel itself
+// (a single-group aggregate query), so that a handful of groups can be mapped to dense accumulator slots.
+static bool compute_dense_map(evqgpu_query& q, std::vector<evqgpu_table*>& tables, DenseMap& dm) {
+  const size_t nk = q.group.size();
+  for (const auto& g : q.group)
+    if (!key_dense_capable(g.get())) return false;
+  // plan: select min(k0), max(k0), count_null(k0)... -> min/max + "has NULL" via a second pair on the tag
+  std::vector<std::vector<evqgpu_insn>> codes;
+  std::vector<evqgpu_expr> sel;
+  std::vector<const char*> names;
+  for (const auto& n : q.input_columns) names.push_back(n.c_str());
+  // serialise group expression i back to postfix and wrap it in min()/max()
+  struct Ser {
+    static void emit(const Expr* e, std::vector<evqgpu_insn>& out) {
+      for (const auto& a : e->args) emit(a.get(), out);
+      evqgpu_insn in;
+      memset(&in, 0, sizeof(in));
+      in.op = (uint8_t) e->op;
+      in.type = (uint8_t) e->type;
+      in.nargs = (uint16_t) e->args.size();
+      in.arg = e->op == EVQ_X_CALL ? (uint32_t) e->fn : e->col;
+      in.imm = e->imm;
+      out.push_back(in);
+    }
+  };
+  auto type_name = [](int t) { return t == EVQ_INT64 ? "int64" : "uint64"; };
+  for (size_t i = 0; i < nk; ++i) {
+    const Expr* g = q.group[i].get();
+    // bool / timestamp keys are compared through their raw bits as uint64: wrap in a cast-free min/max on the bits
+    for (int mm = 0; mm < 2; ++mm) {
+      std::vector<evqgpu_insn> code;
+      Ser::emit(g, code);
+      if (code.back().type == EVQ_BOOL || code.back().type == EVQ_TIMESTAMP64) {
+        // to_int64(bool|timestamp64) keeps the order of these non-negative values
+        std::string conv = std::string("to_int64#int64/") + (g->type == EVQ_BOOL ? "bool;" : "timestamp64;");
+        evqgpu_insn c;
+        memset(&c, 0, sizeof(c));
+        c.op = EVQ_X_CALL; c.type = EVQ_INT64; c.nargs = 1; c.arg = (uint32_t) function_lookup(conv);
+        code.push_back(c);
+      }
+      const int ty = code.back().type;
+      std::string sym = std::string(mm ? "max#" : "min#") + type_name(ty) + "/" + type_name(ty) + ";";
+      evqgpu_insn c;
+      memset(&c, 0, sizeof(c));
+      c.op = EVQ_X_CALL; c.type = (uint8_t) ty; c.nargs = 1; c.arg = (uint32_t) function_lookup(sym);
+      code.push_back(c);
+      codes.push_back(std::move(code));
+    }
+  }
+  // count of rows (to detect NULL keys we compare "seen" with rows: a tagged bare column skips NULLs in min/max)
+  for (auto& c : codes) sel.push_back({c.data(), (uint32_t) c.size(), nullptr, 0});
+  evqgpu_query_desc d;
+  memset(&d, 0, sizeof(d));
+  d.struct_size = sizeof(d);
+  d.flags = EVQGPU_QUERY_GROUPBY;
+  d.num_input_columns = (uint32_t) names.size();
+  d.input_columns = names.data();
+  d.num_select = (uint32_t) sel.size();
+  d.select = sel.data();
+  evqgpu_query* bq = nullptr;
+  if (evqgpu_query_create(q.ctx, &d, &bq) != EVQGPU_OK) return false;
+  std::unique_ptr<evqgpu_query, void (*)(evqgpu_query*)> guard(bq, evqgpu_query_destroy);
+  if (evqgpu_query_execute(bq, tables.data(), (uint32_t) tables.size()) != EVQGPU_OK) return false;
+  q.stats.kernel_launches += bq->stats.kernel_launches;
+  q.jit_ms_total += bq->jit_ms_total;
+  uint64_t nrows = 0;
+  evqgpu_query_num_rows(bq, &nrows);
+  if (nrows == 0) {   // empty input: any mapping works
+    for (size_t i = 0; i < nk; ++i) { dm.key_min[i] = 0; dm.key_range[i] = 2; dm.key_null_idx[i] = 1; }
+  } else {
+    std::vector<bool> nullable_cols(q.input_columns.size(), false);
+    for (auto* t : tables)
+      for (size_t i = 0; i < q.input_columns.size(); ++i) {
+        const int ci = t->find(q.input_columns[i].c_str());
+        if (ci >= 0 && t->cols[ci].meta.dlevel_max > 0) nullable_cols[i] = true;
+      }
+    std::vector<std::vector<uint8_t>> bufs(sel.size(), std::vector<uint8_t>(9));
+    std::vector<void*> ptrs;
+    for (auto& b : bufs) ptrs.push_back(b.data());
+    uint64_t got = 0;
+    if (evqgpu_query_fetch(bq, 0, 1, ptrs.data(), &got) != EVQGPU_OK || got != 1) return false;
+    for (size_t i = 0; i < nk; ++i) {
+      uint64_t mn, mx;
+      memcpy(&mn, bufs[2 * i].data(), 8);
+      memcpy(&mx, bufs[2 * i + 1].data(), 8);
+      // signed and unsigned keys alike: (key - min) as an unsigned difference
+      const uint64_t span = mx - mn;
+      if (span > 1000000) return false;
+      dm.key_min[i] = mn;
+      // one extra index for NULL keys, only when the expression can carry a NULL tag at all
+      const bool may_null = key_may_be_null(q.group[i].get(), nullable_cols);
+      dm.key_range[i] = span + (may_null ? 2 : 1);
+      dm.key_null_idx[i] = may_null ? span + 1 : ~0ull;
+    }
+  }
+  uint64_t slots = 1;
+  for (size_t i = nk; i-- > 0;) {
+    dm.key_stride[i] = slots;
+    if (dm.key_range[i] > 4096 || slots * dm.key_range[i] > 4096) return false;
+    slots *= dm.key_range[i];
+  }
+  dm.slots = slots;
+  return true;
+}
+
+static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std::vector<evqgpu_table*>& tables, bool sync) {
+  evqgpu_ctx* ctx = q.ctx;
+  KernelShape s = shape_for(q, plans[0].table, plans[0].binding);
+  for (size_t i = 1; i < plans.size(); ++i)
+    if (shape_key(shape_for(q, plans[i].table, plans[i].binding)) != shape_key(s))
+      fail(EVQGPU_ERR_UNSUPPORTED, "partitions of one query must share column encodings and nullability");
+  uint64_t total_rows = 0;
+  for (auto* t : tables) total_rows += t->num_rows;
+
+  // ---- tier decision
+  const size_t nk = q.group.size();
+  DenseMap dm;
+  s.tier = 1;
+  s.g1 = 1;
+  if (nk > 0) {
+    bool dense = false;
+    std::vector<uint64_t> uids;
+    for (auto* t : tables) uids.push_back(t->uid);
+    if (q.dense_cache_valid && uids == q.dense_cache_uids) {
+      dense = q.dense_cache_ok;
+      dm = q.dense;
+    } else if (q.expected_groups == 0 || q.expected_groups <= 64) {
+      dense = compute_dense_map(q, tables, dm);
+      q.dense_cache_valid = true;
+      q.dense_cache_ok = dense;
+      q.dense_cache_uids = uids;
+    }
+    if (dense) {
+      s.g1 = g1_for(dm.slots);
+      // thread-private accumulators must fit next to the pipeline stages
+      const size_t acc = (size_t) s.g1 * q.state_ops.size() * 128 * 8;
+      if (s.g1 > 64 || acc > 96 * 1024) dense = false;
+    }
+    if (!dense) { s.tier = 2; s.g1 = 1; }
+  }
+  fit_shape(q, s, plans);
+  q.shape = s;
+  q.dense = dm;
+  q.stats.strategy = (uint32_t) s.tier;
+
+  // ---- kernel text
+  q.kernel_source = generate_source(q, s);
+  float ms = 0;
+  q.module = jit_compile(ctx, q.kernel_source, {"evq_scan", "evq_init", "evq_emit"}, &ms);
+  q.jit_ms_total += ms;
+
+  // ---- state
+  const size_t nstate = q.state_ops.size();
+  EvqScanParams base;
+  memset(&base, 0, sizeof(base));
+  base.status = q.status.as<u32>();
+  base.counters = q.counters.as<u64>();
+  EVQ_CUDA(cudaMemsetAsync(q.status.p, 0, 16, ctx->stream));
+  EVQ_CUDA(cudaMemsetAsync(q.counters.p, 0, 32, ctx->stream));
+  EVQ_CUDA(cudaMemsetAsync(q.out_count.p, 0, 8, ctx->stream));
+  InitParams ip;
+  memset(&ip, 0, sizeof(ip));
+  uint64_t emit_slots = 0;
+  if (s.tier == 1) {
+    const uint64_t slots = s.g1 > 1 ? (uint64_t) s.g1 : 1;
+    ensure(q.dense_state, slots * nstate * 8);
+    base.dense_state = q.dense_state.as<u64>();
+    base.dense_slots = s.g1 > 1 ? dm.slots : 1;
+    for (size_t i = 0; i < nk; ++i) {
+      base.key_min[i] = dm.key_min[i];
+      base.key_stride[i] = dm.key_stride[i];
+      base.key_null_idx[i] = dm.key_null_idx[i];
+    }
+    ip.dense_state = base.dense_state;
+    ip.slots = slots;
+    emit_slots = s.g1 > 1 ? dm.slots : 1;
+  } else {
+    uint64_t want = q.ht_cap;
+    if (want == 0) {
+      uint64_t est = q.expected_groups ? q.expected_groups : std::min<uint64_t>(total_rows, 1ull << 26);
+      want = next_pow2(std::max<uint64_t>(1024, est * 2));
+    }
+    q.ht_cap = want;
+    ensure(q.ht_fp, want * 8);
+    ensure(q.ht_keys, want * 8 * std::max<size_t>(1, nk));
+    ensure(q.ht_ktags, want * std::max<size_t>(1, nk));
+    ensure(q.ht_state, want * 8 * nstate);
+    base.ht.fp = q.ht_fp.as<u64>();
+    base.ht.keys = q.ht_keys.as<u64>();
+    base.ht.ktags = q.ht_ktags.as<u8>();
+    base.ht.state = q.ht_state.as<u64>();
+    base.ht.cap = want;
+    ip.ht = base.ht;
+    ip.slots = want;
+    emit_slots = want;
+  }
+  {
+    void* args[] = {&ip};
+    launch(ctx, q.module->kernels.at("evq_init"), dim3((unsigned) ((ip.slots + 255) / 256)), dim3(256), 0, args);
+    q.stats.kernel_launches++;
+  }
+
+  run_scan(q, s, plans, base);
+
+  // ---- emit
+  const uint64_t out_cap = s.tier == 1 ? emit_slots : std::min<uint64_t>(emit_slots, std::max<uint64_t>(total_rows, 1));
+  q.out_cols.resize(q.select.size());
+  for (size_t i = 0; i < q.select.size(); ++i)
+    ensure(q.out_cols[i], out_cap * (q.select[i].expr->type == EVQ_BOOL ? 2 : 9) + 16);
+  q.out_capacity = out_cap;
+  EmitParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.dense_state = base.dense_state;
+  ep.ht = base.ht;
+  for (size_t i = 0; i < nk; ++i) {
+    ep.key_min[i] = dm.key_min[i];
+    ep.key_stride[i] = dm.key_stride[i];
+    ep.key_null_idx[i] = dm.key_null_idx[i];
+    ep.key_range[i] = dm.key_range[i];
+  }
+  ep.slots = emit_slots;
+  ep.out_count = q.out_count.as<u64>();
+  ep.out_capacity = out_cap;
+  for (size_t i = 0; i < q.select.size(); ++i) ep.out_cols[i] = q.out_cols[i].as<u8>();
+  {
+    void* args[] = {&ep};
+    launch(ctx, q.module->kernels.at("evq_emit"), dim3((unsigned) ((emit_slots + 255) / 256)), dim3(256), 0, args);
+    q.stats.kernel_launches++;
+  }
+  (void) sync;
+}
+
+static void execute_scan_only(evqgpu_query& q, std::vector<TablePlan>& plans, std::vector<evqgpu_table*>& tables) {
+  evqgpu_ctx* ctx = q.ctx;
+  KernelShape s = shape_for(q, plans[0].table, plans[0].binding);
+  for (size_t i = 1; i < plans.size(); ++i)
+    if (shape_key(shape_for(q, plans[i].table, plans[i].binding)) != shape_key(s))
+      fail(EVQGPU_ERR_UNSUPPORTED, "partitions of one query must share column encodings and nullability");
+  uint64_t total_tiles = 0, total_rows = 0;
+  for (auto* t : tables) { total_tiles += t->num_tiles; total_rows += t->num_rows; }
+  s.tier = 0;
+  fit_shape(q, s, plans);
+  q.stats.strategy = 0;
+  EvqScanParams base;
+  memset(&base, 0, sizeof(base));
+  base.status = q.status.as<u32>();
+  base.counters = q.counters.as<u64>();
+  EVQ_CUDA(cudaMemsetAsync(q.status.p, 0, 16, ctx->stream));
+  EVQ_CUDA(cudaMemsetAsync(q.counters.p, 0, 32, ctx->stream));
+  ensure(q.tile_counts, (total_tiles + 1) * 8);
+  ensure(q.tile_base, (total_tiles + 1) * 8);
+  EVQ_CUDA(cudaMemsetAsync(q.tile_counts.p, 0, (total_tiles + 1) * 8, ctx->stream));
+  base.tile_counts = q.tile_counts.as<u64>();
+
+  // pass 1: rows passing WHERE per tile
+  q.shape = s;
+  std::string src0 = generate_source(q, s);
+  float ms = 0;
+  q.module = jit_compile(ctx, src0, {"evq_scan"}, &ms);
+  q.jit_ms_total += ms;
+  run_scan(q, s, plans, base);
+
+  // exclusive prefix -> output row of every tile's first passing row
+  {
+    size_t tmp_bytes = 0;
+    EVQ_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, q.tile_counts.as<u64>(), q.tile_base.as<u64>(),
+                                           (int64_t) (total_tiles + 1), ctx->stream));
+    DevBuf tmp;
+    tmp.alloc(tmp_bytes);
+    EVQ_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, q.tile_counts.as<u64>(), q.tile_base.as<u64>(),
+                                           (int64_t) (total_tiles + 1), ctx->stream));
+    u64 total = 0;
+    EVQ_CUDA(cudaMemcpyAsync(&total, q.tile_base.as<u64>() + total_tiles, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->kernel_launches += 2;
+    q.stats.kernel_launches += 2;
+    q.num_rows_out = total;
+  }
+  // pass 2: projection of the passing rows at their final position
+  q.out_cols.resize(q.select.size());
+  for (size_t i = 0; i < q.select.size(); ++i)
+    ensure(q.out_cols[i], q.num_rows_out * (q.select[i].expr->type == EVQ_BOOL ? 2 : 9) + 16);
+  q.out_capacity = q.num_rows_out;
+  s.tier = 3;
+  q.shape = s;
+  q.kernel_source = generate_source(q, s);
+  q.module = jit_compile(ctx, q.kernel_source, {"evq_scan"}, &ms);
+  q.jit_ms_total += ms;
+  EVQ_CUDA(cudaMemsetAsync(q.counters.p, 0, 32, ctx->stream));
+  base.tile_out_base = q.tile_base.as<u64>();
+  for (size_t i = 0; i < q.select.size(); ++i) base.out_cols[i] = q.out_cols[i].as<u8>();
+  run_scan(q, s, plans, base);
+  (void) total_rows;
+}
+
+static void finish_query(evqgpu_query& q) {
+  evqgpu_ctx* ctx = q.ctx;
+  use_device(ctx);
+  struct { u32 status[4]; u64 counters[4]; u64 out_count; } host;
+  EVQ_CUDA(cudaMemcpyAsync(host.status, q.status.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  EVQ_CUDA(cudaMemcpyAsync(host.counters, q.counters.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  EVQ_CUDA(cudaMemcpyAsync(&host.out_count, q.out_count.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  q.pending = false;
+  const u32 err = host.status[0];
+  q.stats.rows_passed = host.counters[0];
+  if (err & EVQ_ERR_DIV_ZERO) fail(EVQGPU_ERR_RUNTIME, "division by zero");
+  if (err & EVQ_ERR_MOD_ZERO) fail(EVQGPU_ERR_RUNTIME, "modulo by zero");
+  if (err & EVQ_ERR_STAGE_OVERFLOW) fail(EVQGPU_ERR_RUNTIME, "internal error: row tile larger than its pipeline stage");
+  if (err & EVQ_ERR_SLOT_RANGE) fail(EVQGPU_ERR_RUNTIME, "internal error: group key outside the dense slot range");
+  if (q.flags & EVQGPU_QUERY_GROUPBY) {
+    if (err & EVQ_ERR_TABLE_FULL) {
+      // grow the group table and run again (resize policy: double until it fits)
+      if (q.ht_cap >= (1ull << 31)) fail(EVQGPU_ERR_NOMEM, "group table exceeds 2^31 slots");
+      q.ht_cap *= 4;
+      std::vector<evqgpu_table*> tables = q.tables;
+      const uint64_t hint = q.ht_cap;
+      (void) hint;
+      int rc = evqgpu_query_execute(&q, tables.data(), (uint32_t) tables.size());
+      if (rc != EVQGPU_OK) throw Error{rc, last_error()};
+      return;
+    }
+    q.num_rows_out = std::min<uint64_t>(host.out_count, q.out_capacity);
+    q.stats.num_groups = q.num_rows_out;
+  } else {
+    q.stats.num_groups = 0;
+  }
+}
+
+}  // namespace evq
+
+extern "C" {
+
+int evqgpu_query_enqueue(evqgpu_query* q, evqgpu_table* const* tables, uint32_t ntables) {
+  return guarded([&] {
+    if (!q || (!tables && ntables)) fail(EVQGPU_ERR_ARG, "evqgpu_query_enqueue: null argument");
+    if (ntables == 0) fail(EVQGPU_ERR_ARG, "evqgpu_query_enqueue: no tables");
+    use_device(q->ctx);
+    q->tables.assign(tables, tables + ntables);
+    const uint64_t keep_cap = q->ht_cap;
+    q->stats = evqgpu_query_stats();
+    q->jit_ms_total = 0;
+    q->num_rows_out = 0;
+    q->merged = false;
+    std::vector<TablePlan> plans;
+    std::vector<evqgpu_table*> tv(tables, tables + ntables);
+    for (auto* t : tv) {
+      if (!t) fail(EVQGPU_ERR_ARG, "null table");
+      if (t->ctx != q->ctx) fail(EVQGPU_ERR_ARG, "table belongs to another context");
+      TablePlan p;
+      p.table = t;
+      p.binding = bind_table(*q, t);
+      plans.push_back(std::move(p));
+      q->stats.rows_scanned += t->num_rows;
+    }
+    q->ht_cap = keep_cap;
+    q->stats.algorithmic_bytes = algorithmic_bytes(*q, plans);
+    if (q->flags & EVQGPU_QUERY_GROUPBY) execute_groupby(*q, plans, tv, false);
+    else execute_scan_only(*q, plans, tv);
+    q->stats.jit_ms = q->jit_ms_total;
+    q->pending = true;
+  });
+}
+
+int evqgpu_query_finish(evqgpu_query* q) {
+  return guarded([&] {
+    if (!q) fail(EVQGPU_ERR_ARG, "evqgpu_query_finish: null query");
+    if (q->pending) finish_query(*q);
+  });
+}
+
+int evqgpu_query_execute(evqgpu_query* q, evqgpu_table* const* tables, uint32_t ntables) {
+  int rc = evqgpu_query_enqueue(q, tables, ntables);
+  if (rc != EVQGPU_OK) return rc;
+  return evqgpu_query_finish(q);
+}
+
+int evqgpu_query_num_rows(evqgpu_query* q, uint64_t* out) {
+  return guarded([&] {
+    if (!q || !out) fail(EVQGPU_ERR_ARG, "evqgpu_query_num_rows: null argument");
+    if (q->pending) finish_query(*q);
+    *out = q->num_rows_out;
+  });
+}
+
+int evqgpu_query_fetch(evqgpu_query* q, uint64_t row0, uint64_t max_rows, void* const* columns, uint64_t* nrows_out) {
+  return guarded([&] {
+    if (!q || !columns || !nrows_out) fail(EVQGPU_ERR_ARG, "evqgpu_query_fetch: null argument");
+    if (q->pending) finish_query(*q);
+    use_device(q->ctx);
+    uint64_t n = 0;
+    if (row0 < q->num_rows_out) n = std::min<uint64_t>(max_rows, q->num_rows_out - row0);
+    for (size_t i = 0; n && i < q->select.size(); ++i) {
+      const uint64_t w = q->select[i].expr->type == EVQ_BOOL ? 2 : 9;
+      if (!columns[i]) fail(EVQGPU_ERR_ARG, "evqgpu_query_fetch: null column buffer");
+      EVQ_CUDA(cudaMemcpyAsync(columns[i], q->out_cols[i].as<u8>() + row0 * w, n * w, cudaMemcpyDeviceToHost, q->ctx->stream));
+    }
+    if (n) EVQ_CUDA(cudaStreamSynchronize(q->ctx->stream));
+    *nrows_out = n;
+  });
+}
+
+int evqgpu_query_get_stats(evqgpu_query* q, evqgpu_query_stats* out) {
+  return guarded([&] {
+    if (!q || !out) fail(EVQGPU_ERR_ARG, "evqgpu_query_get_stats: null argument");
+    if (q->pending) finish_query(*q);
+    *out = q->stats;
+  });
+}
+
+const char* evqgpu_query_kernel_source(evqgpu_query* q) { return q ? q->kernel_source.c_str() : ""; }
+
+}  // extern "C"

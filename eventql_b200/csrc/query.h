@@ -1,0 +1,110 @@
+// query.h - evqgpu_query: a fused FastCSTableScan (+ GroupByExpression) plan and its device state.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+#include "context.h"
+#include "expr.h"
+#include "jit.h"
+#include "kernels/evq_abi.h"
+#include "table.h"
+
+namespace evq {
+
+// state-word op codes (kernels/evq_prelude.cuh EVQ_OP_*)
+enum { OP_ADD_U64 = 0, OP_ADD_F64 = 1, OP_MIN_U64 = 2, OP_MAX_U64 = 3, OP_MIN_I64 = 4, OP_MAX_I64 = 5, OP_MIN_F64 = 6, OP_MAX_F64 = 7 };
+
+struct SelectItem {
+  ExprPtr expr;
+  const Expr* agg = nullptr;   // the (single) aggregate call inside expr, if any
+  int state0 = -1;             // first state word of the aggregate
+};
+
+// how one input column is laid out on the device (part of the kernel's specialisation key)
+struct ColSig {
+  bool used = false;
+  uint32_t sql_type = 0;
+  uint32_t kind = 0;       // EVQ_KIND_* of the DATA stream
+  bool nullable = false;
+  uint32_t dmax = 0;
+  int data_stream = -1, level_stream = -1;
+  int leb_slot = -1, null_slot = -1;
+};
+
+struct KernelShape {
+  std::vector<ColSig> cols;
+  int tier = 1;        // 0 count pass, 3 projection pass (scan-only); 1 dense / single group; 2 global hash table
+  int g1 = 1;          // dense slots (power of two >= groups) for tier 1
+  int ncons = 256;     // consumer threads
+  int nstages = 3;
+  int min_ctas = 1;
+  int nstreams = 0, nleb = 0, nnull = 0;
+};
+
+struct DenseMap {
+  uint64_t key_min[EVQ_MAX_KEYS] = {0}, key_stride[EVQ_MAX_KEYS] = {0}, key_null_idx[EVQ_MAX_KEYS] = {0},
+           key_range[EVQ_MAX_KEYS] = {0};
+  uint64_t slots = 1;
+};
+
+// parameter block of the emit kernel (mirrors the struct spelled in the generated text)
+struct EmitParams {
+  const u64* dense_state;
+  EvqHashTable ht;
+  u64 key_min[EVQ_MAX_KEYS];
+  u64 key_stride[EVQ_MAX_KEYS];
+  u64 key_null_idx[EVQ_MAX_KEYS];
+  u64 key_range[EVQ_MAX_KEYS];
+  u64 slots;              // dense slots or hash capacity
+  u64* out_count;
+  u64 out_capacity;
+  u8* out_cols[EVQ_MAX_STREAMS];
+};
+
+struct InitParams {
+  u64* dense_state;
+  EvqHashTable ht;
+  u64 slots;
+};
+
+}  // namespace evq
+
+struct evqgpu_query {
+  evqgpu_ctx* ctx = nullptr;
+  uint32_t flags = 0;
+  std::vector<std::string> input_columns;
+  evq::ExprPtr where;
+  std::vector<evq::ExprPtr> group;
+  std::vector<evq::SelectItem> select;
+  std::vector<int> state_ops;       // op of every aggregate state word; word 0 = rows per group
+  uint64_t expected_groups = 0;
+  std::vector<bool> col_used;
+
+  // device state, reused across executions
+  evq::DevBuf dense_state, ht_fp, ht_keys, ht_ktags, ht_state, status, counters, out_count, tile_counts, tile_base;
+  std::vector<evq::DevBuf> out_cols;
+  uint64_t out_capacity = 0;
+  uint64_t ht_cap = 0;
+
+  // last execution
+  evq::KernelShape shape;
+  evq::DenseMap dense;
+  bool dense_cache_valid = false, dense_cache_ok = false;
+  std::vector<uint64_t> dense_cache_uids;   // bounds of the GROUP BY expressions are cached per set of (immutable) tables
+  std::shared_ptr<evq::JitModule> module;
+  std::vector<evqgpu_table*> tables;
+  bool pending = false;
+  bool merged = false;
+  uint64_t num_rows_out = 0;
+  evqgpu_query_stats stats = {};
+  std::string kernel_source;
+  float jit_ms_total = 0;
+};
+
+namespace evq {
+// codegen.cc
+std::string generate_source(const evqgpu_query& q, const KernelShape& shape);
+int state_words_of(const FnInfo& fi);
+// merge.cu
+void merge_query(evqgpu_query& q);
+}  // namespace evq

@@ -1,0 +1,520 @@
+// table.cu - table residency: host->device copies of column pages and the device-side row-tile index.
+//
+// Replaces CSTableReader::openFile / getColumnReader / PageManager::readPage
+// (io/cstable/cstable_reader.cc:78-200, page_manager.cc:125-171): instead of pread()ing 512 KiB pages on
+// demand, the pages of the referenced columns are DMA'd once into contiguous HBM streams.  Values are NOT
+// decoded here - the query kernels decode the page encodings themselves; the only derived data is the small
+// row-tile index that makes row i of column A line up with row i of column B (SURVEY §7 "hard parts").
+#include "table.h"
+#include <cub/device/device_scan.cuh>
+#include <string.h>
+#include <algorithm>
+
+namespace evq {
+
+uint32_t sql_type_of(const ColumnMeta& m) {   // sql/CSTableScanProvider.cc:79-107
+  switch (m.logical_type) {
+    case EVQ_COL_BOOLEAN: return EVQ_BOOL;
+    case EVQ_COL_UNSIGNED_INT: return EVQ_UINT64;
+    case EVQ_COL_SIGNED_INT: return EVQ_INT64;
+    case EVQ_COL_FLOAT: return EVQ_FLOAT64;
+    case EVQ_COL_STRING: return EVQ_STRING;
+    case EVQ_COL_DATETIME: return EVQ_UINT64;
+    default: return EVQ_NIL;
+  }
+}
+
+static uint64_t g_next_table_uid = 1;
+
+void table_init_columns(evqgpu_table* t) {
+  if (t->uid == 0) t->uid = __atomic_fetch_add(&g_next_table_uid, 1, __ATOMIC_RELAXED);
+  t->num_tiles = (uint32_t) ((t->num_rows + EVQ_TILE_ROWS - 1) / EVQ_TILE_ROWS);
+  for (auto& c : t->cols) {
+    c.sql_type = sql_type_of(c.meta);
+    const bool numeric = c.sql_type == EVQ_UINT64 || c.sql_type == EVQ_FLOAT64 || c.sql_type == EVQ_BOOL;
+    c.scannable = numeric && c.meta.rlevel_max == 0;
+    switch (c.meta.encoding) {
+      case EVQ_ENC_UINT64_PLAIN:
+      case EVQ_ENC_FLOAT_IEEE754: c.data_kind = EVQ_KIND_PLAIN64; break;
+      case EVQ_ENC_UINT32_PLAIN: c.data_kind = EVQ_KIND_PLAIN32; break;
+      case EVQ_ENC_UINT32_BITPACKED:
+      case EVQ_ENC_BOOLEAN_BITPACKED: c.data_kind = EVQ_KIND_BITPACK; break;
+      case EVQ_ENC_UINT64_LEB128: c.data_kind = EVQ_KIND_LEB128; break;
+      default: c.scannable = false; break;
+    }
+  }
+}
+
+// ---- kernels -------------------------------------------------------------------------------------------------------
+
+// present-value count of every row tile of an optional column (definition level == dmax)
+__global__ void k_level_tile_counts(const u32* __restrict__ words, u32 bits, u32 dmax, u64 num_rows, u32 num_tiles,
+                                    u64* __restrict__ counts) {
+  // one warp per tile; lane handles 128-row blocks round robin
+  const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u32 lane = threadIdx.x & 31;
+  if (warp >= num_tiles) return;
+  const u64 row0 = (u64) warp * EVQ_TILE_ROWS;
+  const u64 rows = min((u64) EVQ_TILE_ROWS, num_rows - row0);
+  u32 cnt = 0;
+  for (u32 r = lane; r < rows; r += 32) {
+    const u64 v = row0 + r;
+    const u64 blk = v >> 7;
+    const u32 i = v & 127u;
+    const u32 o = (i >> 2) * bits;
+    const u32* w = words + blk * 4u * bits + 4u * (o >> 5) + (i & 3u);
+    const u32 sh = o & 31u;
+    u32 x = w[0] >> sh;
+    if (sh + bits > 32u) x |= w[4] << (32u - sh);
+    if (bits < 32u) x &= (1u << bits) - 1u;
+    cnt += (x == dmax);
+  }
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) counts[warp] = cnt;
+}
+
+#define EVQ_LEB_CHUNK 1024u   // bytes per terminator-count chunk
+
+__device__ __forceinline__ u32 term_count16(uint4 c, u32 valid) {
+  // valid = number of leading bytes of the 16 that belong to the payload (0..16)
+  u32 w[4] = {c.x, c.y, c.z, c.w};
+  u32 n = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    u32 t = ~w[k] & 0x80808080u;
+    const int rem = (int) valid - 4 * k;
+    if (rem <= 0) t = 0;
+    else if (rem < 4) t &= (1u << (8 * rem)) - 1u;
+    n += __popc(t);
+  }
+  return n;
+}
+
+// terminator bytes (msb clear) per EVQ_LEB_CHUNK bytes of payload
+__global__ void k_leb_chunk_counts(const uint4* __restrict__ data, u64 nbytes, u64 nchunks, u64* __restrict__ counts) {
+  const u64 warp = ((u64) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u32 lane = threadIdx.x & 31;
+  if (warp >= nchunks) return;
+  const u64 base = warp * EVQ_LEB_CHUNK;
+  u32 cnt = 0;
+#pragma unroll
+  for (u32 k = 0; k < EVQ_LEB_CHUNK / 16 / 32; ++k) {
+    const u64 off = base + (u64) (k * 32 + lane) * 16;
+    if (off < nbytes) {
+      const u64 rem = nbytes - off;
+      cnt += term_count16(data[off >> 4], rem < 16 ? (u32) rem : 16u);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) counts[warp] = cnt;
+}
+
+// off_index[t] = byte offset at which value number boundary(t) starts, boundary(t) = val_index[t] or t*TILE
+__global__ void k_leb_select(const u8* __restrict__ data, u64 nbytes, const u64* __restrict__ chunk_base, u64 nchunks,
+                             const u64* __restrict__ val_index, u64 num_rows, u32 num_tiles, u64* __restrict__ off_index) {
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > num_tiles) return;
+  u64 V;
+  if (val_index) V = val_index[t];
+  else V = min((u64) t * EVQ_TILE_ROWS, num_rows);
+  if (V == 0) { off_index[t] = 0; return; }
+  const u64 o = V - 1;   // ordinal of the terminator that ends the previous value
+  // chunk c with chunk_base[c] <= o < chunk_base[c+1]
+  u64 lo = 0, hi = nchunks;
+  while (hi - lo > 1) {
+    const u64 mid = (lo + hi) >> 1;
+    if (chunk_base[mid] <= o) lo = mid; else hi = mid;
+  }
+  u64 need = o - chunk_base[lo];   // terminators to skip inside the chunk
+  u64 pos = lo * EVQ_LEB_CHUNK;
+  const u64 end = min(nbytes, pos + EVQ_LEB_CHUNK);
+  const uint4* d4 = (const uint4*) data;
+  for (; pos < end; pos += 16) {
+    const u64 rem = nbytes - pos;
+    const uint4 q = d4[pos >> 4];
+    const u32 n = term_count16(q, rem < 16 ? (u32) rem : 16u);
+    if (n > need) {
+      const u8* b = (const u8*) &q;
+      for (u32 k = 0; k < 16; ++k) {
+        if (!(b[k] & 0x80)) {
+          if (need == 0) { off_index[t] = pos + k + 1; return; }
+          --need;
+        }
+      }
+    }
+    need -= n;
+  }
+  off_index[t] = nbytes;   // fewer values than expected: the scan kernel never reads past nbytes
+}
+
+// max over tiles of the 16-byte aligned copy size of [idx[t]*scale, idx[t+1]*scale)
+__global__ void k_max_span(const u64* __restrict__ idx, u32 num_tiles, u32 scale_bytes, u32 block_values, u32 block_bytes,
+                           unsigned int* __restrict__ out) {
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= num_tiles) return;
+  u64 start, end;
+  if (block_values) {   // bit-packed: whole 128-value blocks
+    start = (idx[t] / block_values) * block_bytes;
+    end = ((idx[t + 1] + block_values - 1) / block_values) * block_bytes;
+  } else {
+    start = idx[t] * scale_bytes;
+    end = idx[t + 1] * scale_bytes;
+  }
+  const u64 al = start & ~15ull;
+  const u32 span = (u32) (((end - al) + 15) & ~15ull);
+  atomicMax(out, span);
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------------
+
+static void exclusive_scan_u64(evqgpu_ctx* ctx, const u64* in, u64* out, uint64_t n) {
+  size_t tmp_bytes = 0;
+  EVQ_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, (int64_t) n, ctx->stream));
+  DevBuf tmp;
+  tmp.alloc(tmp_bytes);
+  EVQ_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, in, out, (int64_t) n, ctx->stream));
+  EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->kernel_launches += 2;
+}
+
+static void upload_stream(evqgpu_table* t, DeviceStream& ds, const StreamLayout& L) {
+  ds.present = L.present;
+  ds.bitpack_max = L.bitpack_max;
+  ds.nbytes = L.total;
+  const uint64_t alloc = round_up(L.total, 256) + 256;
+  ds.buf.alloc(alloc);
+  // zero the tail padding so that over-reads of tile copies see defined bytes
+  const uint64_t tail0 = L.total & ~255ull;
+  EVQ_CUDA(cudaMemsetAsync((uint8_t*) ds.buf.p + tail0, 0, alloc - tail0, t->ctx->stream));
+  uint64_t dst = 0;
+  for (const auto& e : L.extents) {
+    EVQ_CUDA(cudaMemcpyAsync((uint8_t*) ds.buf.p + dst, t->file + e.file_offset, e.nbytes, cudaMemcpyHostToDevice,
+                             t->ctx->stream));
+    dst += e.nbytes;
+  }
+}
+
+void table_load_column(evqgpu_table* t, Column& c) {
+  if (c.loaded) return;
+  if (!c.scannable)
+    fail(EVQGPU_ERR_UNSUPPORTED, "column '%s' (logical type %u, encoding %u, rlevel_max %u) is outside the flat numeric scan path",
+         c.meta.name.c_str(), c.meta.logical_type, c.meta.encoding, c.meta.rlevel_max);
+  if (!t->from_file) fail(EVQGPU_ERR_ARG, "column '%s' has no streams", c.meta.name.c_str());
+  use_device(t->ctx);
+  StreamLayout dl = stream_layout(t->meta, c.meta, EVQ_STREAM_DATA, t->file, t->file_bytes);
+  upload_stream(t, c.data, dl);
+  if (c.meta.dlevel_max > 0) {
+    StreamLayout ll = stream_layout(t->meta, c.meta, EVQ_STREAM_DLEVEL, t->file, t->file_bytes);
+    upload_stream(t, c.dlevel, ll);
+    if (t->meta.version == 1) c.dlevel.bitpack_max = c.meta.dlevel_max;
+  }
+  table_finish_column(t, c);
+}
+
+void table_finish_column(evqgpu_table* t, Column& c) {
+  evqgpu_ctx* ctx = t->ctx;
+  use_device(ctx);
+  const uint32_t ntiles = t->num_tiles;
+  c.num_values = t->num_rows;
+  c.level_bits = 0;
+  c.level_payload_bytes = 0;
+
+  DevBuf maxspan;
+  maxspan.alloc(sizeof(unsigned int));
+
+  // ---- optional column: present values per tile -> val_index
+  const bool nullable = c.meta.dlevel_max > 0;
+  if (nullable) {
+    c.level_bits = bits_needed(c.dlevel.bitpack_max);
+    if (c.level_bits == 0)
+      fail(EVQGPU_ERR_FORMAT, "column '%s': definition level stream has bit width 0", c.meta.name.c_str());
+    const uint64_t need = (t->num_rows + 127) / 128 * 16 * c.level_bits;
+    if (c.dlevel.nbytes < need)
+      fail(EVQGPU_ERR_FORMAT, "column '%s': definition level stream too short (%llu < %llu)", c.meta.name.c_str(),
+           (unsigned long long) c.dlevel.nbytes, (unsigned long long) need);
+    c.level_payload_bytes = need;
+    c.level_tile_cap = (uint32_t) round_up((uint64_t) (EVQ_TILE_ROWS / 128) * 16 * c.level_bits, 16) + 16;
+    DevBuf counts;
+    counts.alloc((uint64_t) (ntiles + 1) * 8);
+    c.val_index.alloc((uint64_t) (ntiles + 1) * 8);
+    EVQ_CUDA(cudaMemsetAsync(counts.p, 0, counts.bytes, ctx->stream));
+    if (ntiles) {
+      const uint32_t threads = 256, warps_per_block = threads / 32;
+      k_level_tile_counts<<<(ntiles + warps_per_block - 1) / warps_per_block, threads, 0, ctx->stream>>>(
+          c.dlevel.buf.as<u32>(), c.level_bits, c.meta.dlevel_max, t->num_rows, ntiles, counts.as<u64>());
+      EVQ_CUDA(cudaGetLastError());
+      ctx->kernel_launches++;
+    }
+    exclusive_scan_u64(ctx, counts.as<u64>(), c.val_index.as<u64>(), ntiles + 1);
+    u64 total = 0;
+    EVQ_CUDA(cudaMemcpyAsync(&total, c.val_index.as<u64>() + ntiles, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    c.num_values = total;
+  }
+
+  // ---- data stream geometry
+  const uint64_t nv = c.num_values;
+  auto span_from_index = [&](const u64* idx, u32 scale, u32 block_values, u32 block_bytes) -> uint32_t {
+    EVQ_CUDA(cudaMemsetAsync(maxspan.p, 0, sizeof(unsigned int), ctx->stream));
+    if (ntiles) {
+      k_max_span<<<(ntiles + 255) / 256, 256, 0, ctx->stream>>>(idx, ntiles, scale, block_values, block_bytes,
+                                                                  maxspan.as<unsigned int>());
+      EVQ_CUDA(cudaGetLastError());
+      ctx->kernel_launches++;
+    }
+    unsigned int v = 0;
+    EVQ_CUDA(cudaMemcpyAsync(&v, maxspan.p, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+    EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    return v + 16;
+  };
+
+  switch (c.data_kind) {
+    case EVQ_KIND_PLAIN64:
+    case EVQ_KIND_PLAIN32: {
+      const uint32_t w = c.data_kind == EVQ_KIND_PLAIN64 ? 8 : 4;
+      if (c.data.nbytes < nv * w)
+        fail(EVQGPU_ERR_FORMAT, "column '%s': data stream too short", c.meta.name.c_str());
+      c.data_payload_bytes = nv * w;
+      c.data_bits = w * 8;
+      if (nullable) c.data_tile_cap = span_from_index(c.val_index.as<u64>(), w, 0, 0);
+      else c.data_tile_cap = EVQ_TILE_ROWS * w + 32;
+      break;
+    }
+    case EVQ_KIND_BITPACK: {
+      c.data_bits = bits_needed(c.data.bitpack_max);
+      const uint64_t need = (nv + 127) / 128 * 16 * c.data_bits;
+      if (c.data_bits && c.data.nbytes < need)
+        fail(EVQGPU_ERR_FORMAT, "column '%s': bit-packed stream too short", c.meta.name.c_str());
+      c.data_payload_bytes = need + (c.data_bits ? 4 : 0);
+      if (nullable) c.data_tile_cap = span_from_index(c.val_index.as<u64>(), 0, 128, 16 * c.data_bits);
+      else c.data_tile_cap = (EVQ_TILE_ROWS / 128) * 16 * c.data_bits + 32;
+      break;
+    }
+    case EVQ_KIND_LEB128: {
+      const uint64_t nchunks = std::max<uint64_t>(1, (c.data.nbytes + EVQ_LEB_CHUNK - 1) / EVQ_LEB_CHUNK);
+      DevBuf counts, base;
+      counts.alloc((nchunks + 1) * 8);
+      base.alloc((nchunks + 1) * 8);
+      EVQ_CUDA(cudaMemsetAsync(counts.p, 0, counts.bytes, ctx->stream));
+      {
+        const uint32_t threads = 256;
+        const uint64_t blocks = (nchunks * 32 + threads - 1) / threads;
+        k_leb_chunk_counts<<<(unsigned) blocks, threads, 0, ctx->stream>>>(c.data.buf.as<uint4>(), c.data.nbytes, nchunks,
+                                                                           counts.as<u64>());
+        EVQ_CUDA(cudaGetLastError());
+        ctx->kernel_launches++;
+      }
+      exclusive_scan_u64(ctx, counts.as<u64>(), base.as<u64>(), nchunks + 1);
+      u64 total_terms = 0;
+      EVQ_CUDA(cudaMemcpyAsync(&total_terms, base.as<u64>() + nchunks, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (total_terms < nv)
+        fail(EVQGPU_ERR_FORMAT, "column '%s': LEB128 stream holds %llu values, %llu expected", c.meta.name.c_str(),
+             (unsigned long long) total_terms, (unsigned long long) nv);
+      c.off_index.alloc((uint64_t) (ntiles + 1) * 8);
+      k_leb_select<<<(ntiles + 1 + 127) / 128, 128, 0, ctx->stream>>>(
+          c.data.buf.as<u8>(), c.data.nbytes, base.as<u64>(), nchunks, nullable ? c.val_index.as<u64>() : nullptr,
+          t->num_rows, ntiles, c.off_index.as<u64>());
+      EVQ_CUDA(cudaGetLastError());
+      ctx->kernel_launches++;
+      u64 used = 0;
+      EVQ_CUDA(cudaMemcpyAsync(&used, c.off_index.as<u64>() + ntiles, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
+      c.data_payload_bytes = used;
+      c.data_bits = 0;
+      c.data_tile_cap = span_from_index(c.off_index.as<u64>(), 1, 0, 0);
+      break;
+    }
+  }
+  c.loaded = true;
+}
+
+}  // namespace evq
+
+// ---- C ABI ---------------------------------------------------------------------------------------------------------
+using namespace evq;
+
+extern "C" {
+
+int evqgpu_table_open(evqgpu_ctx* ctx, const void* file, uint64_t nbytes, evqgpu_table** out) {
+  return guarded([&] {
+    if (!ctx || !file || !out) fail(EVQGPU_ERR_ARG, "evqgpu_table_open: null argument");
+    std::unique_ptr<evqgpu_table> t(new evqgpu_table());
+    t->ctx = ctx;
+    t->file = (const uint8_t*) file;
+    t->file_bytes = nbytes;
+    t->from_file = true;
+    t->meta = parse_cstable(t->file, nbytes);
+    t->num_rows = t->meta.num_rows;
+    for (const auto& cm : t->meta.columns) {
+      Column c;
+      c.meta = cm;
+      t->cols.push_back(std::move(c));
+    }
+    table_init_columns(t.get());
+    *out = t.release();
+  });
+}
+
+int evqgpu_table_create(evqgpu_ctx* ctx, uint64_t num_rows, evqgpu_table** out) {
+  return guarded([&] {
+    if (!ctx || !out) fail(EVQGPU_ERR_ARG, "evqgpu_table_create: null argument");
+    std::unique_ptr<evqgpu_table> t(new evqgpu_table());
+    t->ctx = ctx;
+    t->num_rows = num_rows;
+    t->meta.version = 2;
+    t->meta.num_rows = num_rows;
+    table_init_columns(t.get());
+    *out = t.release();
+  });
+}
+
+int evqgpu_table_add_column(evqgpu_table* tbl, const char* name, uint32_t logical_type, uint32_t encoding,
+                            uint32_t rlevel_max, uint32_t dlevel_max) {
+  int idx = -1;
+  int rc = guarded([&] {
+    if (!tbl || !name) fail(EVQGPU_ERR_ARG, "evqgpu_table_add_column: null argument");
+    if (tbl->find(name) >= 0) fail(EVQGPU_ERR_ARG, "duplicate column '%s'", name);
+    Column c;
+    c.meta.name = name;
+    c.meta.column_id = (uint32_t) tbl->cols.size() + 1;   // TableSchema.cc:55-70: ids 1.. in add order
+    c.meta.logical_type = logical_type;
+    c.meta.encoding = encoding;
+    c.meta.rlevel_max = rlevel_max;
+    c.meta.dlevel_max = dlevel_max;
+    tbl->cols.push_back(std::move(c));
+    table_init_columns(tbl);
+    idx = (int) tbl->cols.size() - 1;
+  });
+  return rc == EVQGPU_OK ? idx : -rc;
+}
+
+int evqgpu_table_add_stream(evqgpu_table* tbl, const char* column, uint32_t kind, const void* ptr, uint64_t nbytes,
+                            uint32_t bitpack_max, uint32_t flags) {
+  return guarded([&] {
+    if (!tbl || !column || (!ptr && nbytes)) fail(EVQGPU_ERR_ARG, "evqgpu_table_add_stream: null argument");
+    const int ci = tbl->find(column);
+    if (ci < 0) fail(EVQGPU_ERR_ARG, "unknown column '%s'", column);
+    Column& c = tbl->cols[ci];
+    if (kind != EVQ_STREAM_DATA && kind != EVQ_STREAM_DLEVEL)
+      fail(EVQGPU_ERR_UNSUPPORTED, "only DATA and DLEVEL streams are supported (flat columns)");
+    use_device(tbl->ctx);
+    DeviceStream& ds = kind == EVQ_STREAM_DATA ? c.data : c.dlevel;
+    ds.present = true;
+    ds.bitpack_max = bitpack_max;
+    ds.nbytes = nbytes;
+    const uint64_t alloc = round_up(nbytes, 256) + 256;
+    ds.buf.alloc(alloc);
+    const uint64_t tail0 = nbytes & ~255ull;
+    EVQ_CUDA(cudaMemsetAsync((uint8_t*) ds.buf.p + tail0, 0, alloc - tail0, tbl->ctx->stream));
+    if (nbytes)
+      EVQ_CUDA(cudaMemcpyAsync(ds.buf.p, ptr, nbytes,
+                               (flags & EVQGPU_STREAM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                               tbl->ctx->stream));
+    const bool ready = c.data.present && (c.meta.dlevel_max == 0 || c.dlevel.present);
+    if (ready) {
+      if (!c.scannable) fail(EVQGPU_ERR_UNSUPPORTED, "column '%s' is outside the flat numeric scan path", column);
+      table_finish_column(tbl, c);
+    }
+  });
+}
+
+void evqgpu_table_destroy(evqgpu_table* tbl) {
+  if (!tbl) return;
+  cudaSetDevice(tbl->ctx->device);
+  delete tbl;
+}
+
+uint64_t evqgpu_table_num_rows(const evqgpu_table* tbl) { return tbl ? tbl->num_rows : 0; }
+uint32_t evqgpu_table_num_columns(const evqgpu_table* tbl) { return tbl ? (uint32_t) tbl->cols.size() : 0; }
+
+int evqgpu_table_column_info(const evqgpu_table* tbl, uint32_t idx, evqgpu_column_info* out) {
+  return guarded([&] {
+    if (!tbl || !out || idx >= tbl->cols.size()) fail(EVQGPU_ERR_ARG, "evqgpu_table_column_info: bad argument");
+    const Column& c = tbl->cols[idx];
+    memset(out, 0, sizeof(*out));
+    out->name = c.meta.name.c_str();
+    out->column_id = c.meta.column_id;
+    out->logical_type = c.meta.logical_type;
+    out->encoding = c.meta.encoding;
+    out->rlevel_max = c.meta.rlevel_max;
+    out->dlevel_max = c.meta.dlevel_max;
+    out->sql_type = c.sql_type;
+    out->loaded = c.loaded;
+    out->data_bytes = c.data_payload_bytes;
+    out->level_bytes = c.level_payload_bytes;
+    out->num_values = c.num_values;
+  });
+}
+
+int evqgpu_table_find_column(const evqgpu_table* tbl, const char* name) { return (tbl && name) ? tbl->find(name) : -1; }
+
+int evqgpu_table_load_columns(evqgpu_table* tbl, const char* const* names, uint32_t n) {
+  return guarded([&] {
+    if (!tbl) fail(EVQGPU_ERR_ARG, "evqgpu_table_load_columns: null table");
+    if (!names) {
+      for (auto& c : tbl->cols)
+        if (c.scannable && !c.loaded) table_load_column(tbl, c);
+      return;
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+      const int ci = tbl->find(names[i]);
+      if (ci < 0) fail(EVQGPU_ERR_ARG, "column not found: %s", names[i]);
+      table_load_column(tbl, tbl->cols[ci]);
+    }
+  });
+}
+
+int evqgpu_table_read_stream(evqgpu_table* tbl, const char* column, uint32_t kind, void* dst, uint64_t cap,
+                             uint64_t* nbytes_out, uint32_t* bitpack_max_out) {
+  return guarded([&] {
+    if (!tbl || !column || !nbytes_out) fail(EVQGPU_ERR_ARG, "evqgpu_table_read_stream: null argument");
+    const int ci = tbl->find(column);
+    if (ci < 0) fail(EVQGPU_ERR_ARG, "column not found: %s", column);
+    Column& c = tbl->cols[ci];
+    DeviceStream& ds = kind == EVQ_STREAM_DATA ? c.data : c.dlevel;
+    if (!ds.present) { *nbytes_out = 0; return; }
+    uint64_t n = ds.nbytes;
+    if (kind == EVQ_STREAM_DATA && c.loaded && c.data_kind == EVQ_KIND_LEB128) n = c.data_payload_bytes;
+    if (kind == EVQ_STREAM_DLEVEL && c.loaded) n = c.level_payload_bytes;
+    *nbytes_out = n;
+    if (bitpack_max_out) *bitpack_max_out = ds.bitpack_max;
+    if (dst && cap >= n && n) {
+      use_device(tbl->ctx);
+      EVQ_CUDA(cudaMemcpyAsync(dst, ds.buf.p, n, cudaMemcpyDeviceToHost, tbl->ctx->stream));
+      EVQ_CUDA(cudaStreamSynchronize(tbl->ctx->stream));
+    }
+  });
+}
+
+int evqgpu_table_write_file(evqgpu_table* tbl, const char* path) {
+  return guarded([&] {
+    if (!tbl || !path) fail(EVQGPU_ERR_ARG, "evqgpu_table_write_file: null argument");
+    use_device(tbl->ctx);
+    std::vector<ColumnMeta> metas;
+    std::vector<std::vector<uint8_t>> payloads;
+    std::vector<WriteStream> streams;
+    payloads.reserve(tbl->cols.size() * 2);
+    for (auto& c : tbl->cols) {
+      if (!c.loaded) fail(EVQGPU_ERR_ARG, "column '%s' is not resident", c.meta.name.c_str());
+      metas.push_back(c.meta);
+      auto fetch = [&](DeviceStream& ds, uint64_t n) -> const uint8_t* {
+        payloads.emplace_back(n);
+        if (n) EVQ_CUDA(cudaMemcpyAsync(payloads.back().data(), ds.buf.p, n, cudaMemcpyDeviceToHost, tbl->ctx->stream));
+        return payloads.back().data();
+      };
+      if (c.meta.dlevel_max > 0) {
+        const uint8_t* p = fetch(c.dlevel, c.level_payload_bytes);
+        streams.push_back({EVQ_STREAM_DLEVEL, c.meta.column_id, p, c.level_payload_bytes, true, c.dlevel.bitpack_max});
+      }
+      const bool bp = c.data_kind == EVQ_KIND_BITPACK;
+      const uint64_t n = bp ? (c.data_payload_bytes >= 4 ? c.data_payload_bytes - 4 : 0) : c.data_payload_bytes;
+      const uint8_t* p = fetch(c.data, n);
+      streams.push_back({EVQ_STREAM_DATA, c.meta.column_id, p, n, bp, c.data.bitpack_max});
+    }
+    EVQ_CUDA(cudaStreamSynchronize(tbl->ctx->stream));
+    write_cstable_v2(path, tbl->num_rows, metas, streams);
+  });
+}
+
+}  // extern "C"

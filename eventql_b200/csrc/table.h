@@ -1,0 +1,68 @@
+// table.h - evqgpu_table: one cstable file / partition segment resident in HBM.
+//
+// HBM layout per loaded column:
+//   data    : the column's DATA pages concatenated in index order (page padding dropped, bit-packed header
+//             stripped), 256-byte aligned, zero-padded by >= 128 bytes so tile copies may over-read
+//   dlevel  : same for the DLEVEL pages of optional columns (bit-packed, libsimdcomp vertical layout)
+//   val_index[t] : number of non-NULL values before row tile t        (optional columns)   u64[ntiles+1]
+//   off_index[t] : byte offset of the first value of row tile t       (LEB128 columns)     u64[ntiles+1]
+// A row tile is EVQ_TILE_ROWS = 1024 records.
+#pragma once
+#include <string>
+#include <vector>
+#include "context.h"
+#include "cstable_format.h"
+#include "kernels/evq_abi.h"
+
+namespace evq {
+
+struct DeviceStream {
+  DevBuf buf;
+  uint64_t nbytes = 0;         // payload bytes (logical stream length, may include the zero tail of the last page)
+  uint32_t bitpack_max = 0;
+  bool present = false;
+};
+
+struct Column {
+  ColumnMeta meta;
+  uint32_t sql_type = 0;
+  bool loaded = false;
+  bool scannable = false;      // flat, numeric
+  DeviceStream data, dlevel;
+  DevBuf off_index, val_index;
+  uint64_t num_values = 0;
+  uint64_t data_payload_bytes = 0;    // algorithmic bytes of the DATA stream
+  uint64_t level_payload_bytes = 0;
+  uint32_t data_kind = 0;      // EVQ_KIND_*
+  uint32_t data_bits = 0;
+  uint32_t level_bits = 0;
+  uint32_t data_tile_cap = 0;  // max bytes one tile copy of the data stream can need (multiple of 16)
+  uint32_t level_tile_cap = 0;
+};
+
+}  // namespace evq
+
+struct evqgpu_table {
+  evqgpu_ctx* ctx = nullptr;
+  evq::FileMeta meta;
+  const uint8_t* file = nullptr;
+  uint64_t file_bytes = 0;
+  uint64_t num_rows = 0;
+  uint32_t num_tiles = 0;
+  std::vector<evq::Column> cols;
+  bool from_file = false;
+  uint64_t uid = 0;   // unique per table object (pointers can be reused after destroy)
+
+  int find(const char* name) const {
+    for (size_t i = 0; i < cols.size(); ++i)
+      if (cols[i].meta.name == name) return (int) i;
+    return -1;
+  }
+};
+
+namespace evq {
+uint32_t sql_type_of(const ColumnMeta& m);
+void table_init_columns(evqgpu_table* t);
+void table_load_column(evqgpu_table* t, Column& c);
+void table_finish_column(evqgpu_table* t, Column& c);   // indexes + tile caps after the streams are on the device
+}  // namespace evq

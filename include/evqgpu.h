@@ -145,8 +145,6 @@ typedef struct evqgpu_column_info {
   uint64_t data_bytes;      /* payload bytes of the DATA stream (algorithmic bytes, padding excluded) */
   uint64_t level_bytes;     /* payload bytes of the DLEVEL stream, 0 if the column is required */
   uint64_t num_values;      /* non-NULL values (known once loaded) */
-  uint64_t min_value;       /* raw 64-bit min / max over non-NULL values (unsigned order; once loaded) */
-  uint64_t max_value;
 } evqgpu_column_info;
 
 /* Parse header + page index of a cstable file image (v0.1.0 and v0.2.0).  Host only: nothing
@@ -324,6 +322,23 @@ EVQGPU_API int evqgpu_comm_destroy(evqgpu_ctx* ctx);
  * every rank ends with the full result; high-cardinality results are repartitioned by key hash
  * (all-to-all) and every rank ends with its share of the groups. */
 EVQGPU_API int evqgpu_query_merge(evqgpu_query* q);
+
+/* ------------------------------------------------------------------------------------------
+ * build-time check (no device needed): generate the scan kernel text for a plan against a
+ * described column layout and compile it with NVRTC for sm_100a.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct evqgpu_debug_column {
+  uint32_t sql_type;   /* EVQ_* SType */
+  uint32_t encoding;   /* EVQ_ENC_* */
+  uint32_t dlevel_max; /* 0 = required */
+} evqgpu_debug_column;
+
+/* tier: 1 = dense / single group (dense_slots groups), 2 = global hash table; ignored for scan-only plans.
+ * src_out (may be NULL) receives the NUL-terminated kernel text when src_cap suffices; *src_len_out its length.
+ * compile != 0 runs NVRTC; *cubin_bytes_out receives the cubin size. */
+EVQGPU_API int evqgpu_debug_generate(const evqgpu_query_desc* desc, const evqgpu_debug_column* columns, uint32_t tier,
+                                     uint32_t dense_slots, char* src_out, uint64_t src_cap, uint64_t* src_len_out,
+                                     int compile, uint64_t* cubin_bytes_out);
 
 #ifdef __cplusplus
 }
