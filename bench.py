@@ -1,0 +1,497 @@
+#!/usr/bin/env python3
+"""bench.py - rows/s and GB/s of scan + filter + GROUP BY (BASELINE.json) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3_q1|c2_q6|c4_highcard|c5_timeseries]
+  python bench.py --impl reference ...      the reference's own CPU engine (oracle/_ref/evqlref) on the host cores
+
+One "step" = one pass of the query over every partition resident on this rank + the cross-GPU merge of the partial
+aggregates.  Default workload at every N: C3 of SURVEY.md 8(d) - the TPC-H-Q1-style query over 8 x 125 M-row lineitem
+partitions (1 B rows) PER GPU (weak scaling: partitions are the independent units; the one exchange step is the merge).
+The exact "1 B rows over N GPUs" split of BASELINE.json's configs[2] is timed in the same run and reported as
+`c3_strong`.
+
+Prints ONE JSON line (rank 0).  Timing: CUDA events on the library's stream, max over ranks; inputs (10.8 GB per GPU)
+are far larger than the 126 MB L2, so no explicit flush is needed between steps.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+EVQLREF = os.path.join(ROOT, "oracle", "_ref", "evqlref")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="evq", choices=["evq", "reference"])
+    ap.add_argument("--workload", default="c3_q1", choices=["c3_q1", "c2_q6", "c4_highcard", "c5_timeseries"])
+    ap.add_argument("--rows-per-partition", type=int, default=0, help="0 = the workload's default")
+    ap.add_argument("--partitions-per-gpu", type=int, default=0, help="0 = the workload's default")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-partitions", type=int, default=2)
+    ap.add_argument("--cpu-sample-rows", type=int, default=8_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ref-rows-per-core", type=int, default=1_000_000)
+    return ap.parse_args()
+
+
+# ---- workloads ------------------------------------------------------------------------------------------
+
+def workload(name):
+    """-> dict(spec(partition index) -> column specs, query(spec) -> (sql, plan), table alias, default partition layout)"""
+    from tests import common as T   # table / query definitions shared with the parity tests (no oracle import)
+    if name == "c3_q1":
+        return dict(spec=lambda p: T.lineitem_spec(), query=lambda s: T.q1(s), alias="lineitem", rows=125_000_000, parts=8,
+                    desc="C3: TPC-H-Q1-style scan+filter+GROUP BY (4 groups, 8 aggregates + 3 means), lineitem UINT64_LEB128")
+    if name == "c2_q6":
+        return dict(spec=lambda p: T.lineitem_spec(), query=lambda s: T.q6(s), alias="lineitem", rows=100_000_000, parts=1,
+                    desc="C2: TPC-H-Q6-style selective filter + global SUM, 100 M-row lineitem UINT64_LEB128")
+    if name == "c4_highcard":
+        return dict(spec=lambda p: T.events_spec(10_000_000), query=lambda s: T.q_highcard(s, expected_groups=10_000_000),
+                    alias="events", rows=125_000_000, parts=8,
+                    desc="C4: high-cardinality GROUP BY (10 M distinct u64 keys) count/sum/mean")
+    if name == "c5_timeseries":
+        return dict(spec=lambda p: T.readings_spec(p), query=lambda s: T.q_timeseries(s, expected_groups=1_440_000),
+                    alias="readings", rows=125_000_000, parts=1,
+                    desc="C5: 1-minute bucket x 1 K sensors GROUP BY, one time partition per GPU")
+    raise SystemExit("unknown workload " + name)
+
+
+# ---- clocks -----------------------------------------------------------------------------------------------------------
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                f = [x.strip() for x in line.split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for f in self.samples:
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---- the reference's CPU engine on host cores --------------------------------------------------------------------------------
+
+def run_evqlref(alias, path, sql, reps=1):
+    """-> (best ms over reps, header, rows) running the unmodified reference engine on one cstable file"""
+    r = subprocess.run([EVQLREF, "sql", "-t", "%s=%s" % (alias, path), "-n", str(reps), "-q", sql],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    if r.returncode != 0 or "ERROR!" in r.stdout:
+        raise RuntimeError("evqlref failed: %s %s" % (r.stdout[-500:], r.stderr[-500:]))
+    ms = [float(l.split("ms=")[1].split()[0]) for l in r.stderr.splitlines() if l.startswith("TIMING")]
+    lines = [l for l in r.stdout.split("\n") if l]
+    return min(ms), lines[0], [l.split(";") for l in lines[1:]]
+
+
+def _write_partition(args):
+    path, wl_name, part, rows = args
+    from tests import common as T
+    wl = workload(wl_name)
+    T.write_table(path, wl["spec"](part), rows, row_offset=part * rows)
+    return path
+
+
+def reference_arm(args):
+    """bench.py --impl reference: the reference's own CPU implementation of the path (FastCSTableScan +
+    GroupByExpression through its planner: oracle/_ref/evqlref, built from the unmodified sources) on all host cores:
+    one process per partition file, as the reference has no intra-query threading."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = workload(args.workload)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    rows = args.ref_rows_per_core
+    spec0 = wl["spec"](0)
+    sql, _plan = wl["query"](spec0)
+    kind = "reference"
+    if not os.path.exists(EVQLREF):
+        kind = "port"
+    tmp = tempfile.mkdtemp(prefix="evqref")
+    import multiprocessing as mp
+    with mp.Pool(min(cores, 64)) as pool:
+        files = pool.map(_write_partition, [(os.path.join(tmp, "p%d.cst" % i), args.workload, i, rows) for i in range(cores)])
+
+    def step():
+        t0 = time.perf_counter()
+        if kind == "reference":
+            procs = [subprocess.Popen([EVQLREF, "sql", "-t", "%s=%s" % (wl["alias"], f), "-q", sql], stdout=subprocess.DEVNULL,
+                                      stderr=subprocess.DEVNULL) for f in files]
+            rcs = [p.wait() for p in procs]
+            if any(rcs):
+                raise RuntimeError("evqlref exited with %r" % rcs)
+        else:
+            from oracle import evq_oracle as O
+            for f in files:
+                O.run_query([O.read_cstable(f)], _plan)
+        return time.perf_counter() - t0
+
+    for _ in range(args.warmup):
+        step()
+    times = [step() for _ in range(args.steps)]
+    total = sum(times)
+    nrows = rows * len(files) * (1 if kind == "reference" else 1)
+    value = nrows * args.steps / total
+    used = cores if kind == "reference" else 1
+    sample = "%d partition files x %d rows (%s), one reference process per host core" % (len(files), rows, args.workload)
+    out = {
+        "impl": "reference", "metric": "scan+filter+GROUP BY throughput", "value": value, "unit": "rows/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "sql": sql, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": used, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+    for f in files:
+        try:
+            os.unlink(f)
+        except OSError:
+            pass
+
+
+def cpu_baseline(ctx, wl, args, q_rows_check=True):
+    """The reference's CPU engine, one query on ONE host core (it is single-threaded per query), on a bounded sample of
+    the same workload written as a cstable file by the device-side writer; its rows are also compared with the CUDA
+    result on the same file (a parity check at bench time)."""
+    from tests import common as T
+    spec = wl["spec"](0)
+    sql, plan = wl["query"](spec)
+    rows = args.cpu_sample_rows
+    tmp = tempfile.mkdtemp(prefix="evqcpu")
+    path = os.path.join(tmp, "sample.cst")
+    tbl = ctx.synthesize(rows, spec)
+    tbl.write_file(path)
+    q = ctx.query(plan)
+    q.execute([tbl])
+    gpu_rows = q.rows()
+    q.close()
+    tbl.close()
+    sample = "%d rows of %s, 1 query, best of 2 runs" % (rows, args.workload)
+    parity = None
+    if os.path.exists(EVQLREF):
+        kind = "reference"
+        ms, hdr, raw = run_evqlref(wl["alias"], path, sql, reps=2)
+        types = [h.rsplit(":", 1)[1] for h in hdr[1:].split(";")]
+        ref_rows = T.parse_ref_rows(raw, types)
+        parity, why = T.rows_equal(gpu_rows, ref_rows)
+        if not parity:
+            raise RuntimeError("bench: CUDA result differs from the reference engine on the CPU sample: " + why)
+    else:
+        kind = "port"
+        from oracle import evq_oracle as O
+        f = O.read_cstable(path)
+        t0 = time.perf_counter()
+        res = O.run_query([f], plan)
+        ms = 1000.0 * (time.perf_counter() - t0)
+        parity, why = T.rows_equal(gpu_rows, res.rows())
+        if not parity:
+            raise RuntimeError("bench: CUDA result differs from the oracle on the CPU sample: " + why)
+    os.unlink(path)
+    return {"value": rows / (ms / 1000.0), "unit": "rows/s", "cores": 1, "kind": kind, "sample": sample,
+            "parity_with_cuda_on_sample": bool(parity), "host_cpus": os.cpu_count()}
+
+
+# ---- our arm ------------------------------------------------------------------------------------------------------------
+
+def referenced_columns(plan):
+    """Names of the input columns the plan's expressions actually read."""
+    from eventql_b200 import plan as P
+    seen = set()
+
+    def walk(e):
+        if e is None:
+            return
+        if isinstance(e, P.Col):
+            seen.add(e.index)
+        elif isinstance(e, P.Call):
+            for a in e.args:
+                walk(a)
+        elif isinstance(e, P.If):
+            walk(e.cond), walk(e.then), walk(e.otherwise)
+
+    walk(plan.where)
+    for e in list(plan.group) + list(plan.select):
+        walk(e)
+    return [n for i, n in enumerate(plan.input_columns) if i in seen]
+
+
+def evq_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from eventql_b200 import capi, plan as P
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run --nproc-per-node %d)" % (args.gpus, world, args.gpus))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = capi.Context(local)          # raises without a device: there is no CPU fallback
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(capi.Context.comm_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(idt, 0)
+        ctx.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+
+    wl = workload(args.workload)
+    rows = args.rows_per_partition or wl["rows"]
+    parts = args.partitions_per_gpu or wl["parts"]
+    tables = []
+    for p in range(parts):
+        gp = rank * parts + p                      # global partition index: every rank holds different rows
+        tables.append(ctx.synthesize(rows, wl["spec"](gp), row_offset=gp * rows))
+    sql, plan = wl["query"](wl["spec"](0))
+    if world > 1:
+        plan.flags |= P.QUERY_PARTIAL
+    q = ctx.query(plan)
+
+    def step(tbls):
+        q.enqueue(tbls)
+        if world > 1:
+            q.merge()
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def timed(tbls, k):
+        """k steps, CUDA events on the library's stream; returns (ms max over ranks, stats of the last step)"""
+        ext = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(ext)
+        for _ in range(k):
+            step(tbls)
+        e1.record(ext)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        q.finish()
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, q.stats()
+
+    # warm-up (also JIT + the one-off key-bounds pre-pass of the dense tier)
+    for _ in range(max(args.warmup, 1)):
+        step(tables)
+    q.finish()
+    first_stats = q.stats()
+
+    ctx.set_profiling(True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    launches0 = ctx.kernel_launches
+    ms, stats = timed(tables, args.steps)
+    launches = ctx.kernel_launches - launches0
+    # keep the GPU busy a little longer when the region is shorter than the sampler period, so the clocks are seen under load
+    if ms < 400:
+        extra = int(min(200, max(1, 400 / max(ms / args.steps, 0.01))))
+        timed(tables, extra)
+    sampler.stop()
+    ctx.set_profiling(False)
+    result_rows = q.rows()
+    total_rows_rank = rows * parts
+    total_rows = total_rows_rank * world
+    value = total_rows * args.steps / (ms / 1000.0)
+    algo_bytes_rank = stats["algorithmic_bytes"]
+
+    # correctness guard inside the bench: every row passes Q1's predicate, so the counts must add up to the table size
+    if args.workload == "c3_q1":
+        cnt = sum(r[2] for r in result_rows)
+        expect = total_rows
+        if cnt != expect:
+            raise RuntimeError("bench: count(1) over all groups is %d, expected %d" % (cnt, expect))
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    nscan = max(1, stats["scan_launches"])
+    scan_ms_avg = stats["scan_ms"] / nscan
+    bytes_per_launch = algo_bytes_rank / parts
+    achieved = bytes_per_launch / (scan_ms_avg / 1000.0) / 1e9 if scan_ms_avg > 0 else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload)
+    roofline = {"bound": "hbm", "kernel": "evq_scan", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_per_launch, "launch_ms": scan_ms_avg,
+                "launches_timed": nscan, "bytes_per_row": algo_bytes_rank / total_rows_rank,
+                "step_gbs_all_gpus": algo_bytes_rank * world * args.steps / (ms / 1000.0) / 1e9,
+                "step_frac_of_aggregate_peak": algo_bytes_rank * args.steps / (ms / 1000.0) / 1e9 / peak}
+
+    # the exact BASELINE configs[2] split: 1 B rows over the N GPUs (8/N partitions per GPU)
+    strong = None
+    if args.workload == "c3_q1" and parts * world >= 8 and 8 % world == 0 and parts >= 8 // world:
+        sub = tables[: 8 // world]
+        for _ in range(2):
+            step(sub)
+        q.finish()
+        sms, _ = timed(sub, args.steps)
+        strong = {"rows": rows * 8, "partitions_per_gpu": 8 // world, "ms_per_step": sms / args.steps,
+                  "value": rows * 8 * args.steps / (sms / 1000.0), "unit": "rows/s"}
+
+    # ---- end to end through the C ABI with HOST buffers: per step H2D of the encoded column streams (pinned), index
+    # build, scan, merge, D2H of the result rows
+    e2e = None
+    if not args.no_e2e:
+        nparts = min(args.e2e_partitions, parts)
+        host = []
+        used = referenced_columns(plan)
+        h2d = 0
+        for t in tables[:nparts]:
+            cols = []
+            for info in t.columns():
+                if info["name"] not in used:
+                    continue
+                data, mx = t.read_stream(info["name"], P.STREAM_DATA)
+                pin = ctx.host_alloc(max(1, data.nbytes))
+                pin[: data.nbytes] = data
+                cols.append((info, pin[: data.nbytes], mx))
+                h2d += data.nbytes
+            host.append((t.num_rows, cols))
+        q2 = ctx.query(plan)
+
+        def e2e_step():
+            tbls = []
+            for nrows_t, cols in host:
+                t = ctx.create_table(nrows_t)
+                for info, pin, mx in cols:
+                    t.add_column(info["name"], info["logical_type"], info["encoding"], info["dlevel_max"])
+                    t.add_stream(info["name"], P.STREAM_DATA, pin, mx)
+                tbls.append(t)
+            q2.execute(tbls)
+            if world > 1:
+                q2.merge()
+            out = q2.fetch_packed()
+            for t in tbls:
+                t.close()
+            return sum(len(c) for c in out)
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        d2h = 0
+        for _ in range(args.e2e_steps):
+            d2h = e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e_rows = sum(h[0] for h in host) * world
+        e2e = {"value": e2e_rows * args.e2e_steps / dt, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h + 56,
+               "rows_per_step": e2e_rows, "steps": args.e2e_steps, "ms_per_step": 1000.0 * dt / args.e2e_steps,
+               "path": "evqgpu_table_create/add_stream (pinned host -> HBM) + evqgpu_query_execute + merge + evqgpu_query_fetch"}
+        q2.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(ctx, wl, args)
+
+    clocks = sampler.summary()
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        out = {
+            "metric": "scan+filter+GROUP BY throughput", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 1), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": wl["desc"], "sql": sql, "rows_per_gpu": total_rows_rank, "partitions_per_gpu": parts,
+                       "rows_per_partition": rows, "total_rows": total_rows, "groups": len(result_rows),
+                       "strategy": {0: "scan-only", 1: "dense (registers/shared memory)", 2: "global hash table"}[stats["strategy"]],
+                       "l2": "inputs (%.1f GB per GPU) are larger than L2; no flush" % (algo_bytes_rank / 1e9),
+                       "merge": "none (1 GPU)" if world == 1 else "NCCL over NVLink inside every step",
+                       "jit_ms_first_query": first_stats["jit_ms"]},
+            "gbs": algo_bytes_rank * world * args.steps / (ms / 1000.0) / 1e9,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if strong:
+            out["c3_strong"] = strong
+        print(json.dumps(out), flush=True)
+    q.close()
+    for t in tables:
+        t.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.gpus > 1 and "RANK" not in os.environ:
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr",
+               "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        evq_arm(args)
+
+
+if __name__ == "__main__":
+    main()

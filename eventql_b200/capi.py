@@ -56,7 +56,7 @@ class SynthColumn(C.Structure):
 class QueryStats(C.Structure):
     _fields_ = [("rows_scanned", C.c_uint64), ("rows_passed", C.c_uint64), ("algorithmic_bytes", C.c_uint64),
                 ("num_groups", C.c_uint64), ("kernel_launches", C.c_uint32), ("strategy", C.c_uint32),
-                ("jit_ms", C.c_float), ("reserved", C.c_float)]
+                ("jit_ms", C.c_float), ("scan_ms", C.c_float), ("scan_launches", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class DebugColumn(C.Structure):
@@ -67,6 +67,7 @@ class DebugColumn(C.Structure):
 SYMBOLS = [
     "evqgpu_ctx_create", "evqgpu_ctx_destroy", "evqgpu_last_error", "evqgpu_abi_version", "evqgpu_host_alloc",
     "evqgpu_host_free", "evqgpu_host_register", "evqgpu_host_unregister", "evqgpu_ctx_stream", "evqgpu_ctx_synchronize",
+    "evqgpu_ctx_set_profiling", "evqgpu_ctx_kernel_launches",
     "evqgpu_table_open", "evqgpu_table_create", "evqgpu_table_add_column", "evqgpu_table_add_stream",
     "evqgpu_table_destroy", "evqgpu_table_num_rows", "evqgpu_table_num_columns", "evqgpu_table_column_info",
     "evqgpu_table_find_column", "evqgpu_table_load_columns", "evqgpu_table_read_stream", "evqgpu_table_decode_column",
@@ -100,6 +101,9 @@ def lib() -> C.CDLL:
     L.evqgpu_ctx_stream.argtypes = [vp]
     L.evqgpu_ctx_stream.restype = vp
     L.evqgpu_ctx_synchronize.argtypes = [vp]
+    L.evqgpu_ctx_set_profiling.argtypes = [vp, C.c_int]
+    L.evqgpu_ctx_kernel_launches.argtypes = [vp]
+    L.evqgpu_ctx_kernel_launches.restype = u64
     L.evqgpu_table_open.argtypes = [vp, vp, u64, C.POINTER(vp)]
     L.evqgpu_table_create.argtypes = [vp, u64, C.POINTER(vp)]
     L.evqgpu_table_add_column.argtypes = [vp, cp, u32, u32, u32, u32]
@@ -216,6 +220,7 @@ class Context:
         self._h = C.c_void_p()
         check(lib().evqgpu_ctx_create(device, 0, C.byref(self._h)))
         self.device = device
+        self.rank, self.nranks = 0, 1
 
     def close(self):
         if self._h:
@@ -234,6 +239,26 @@ class Context:
 
     def synchronize(self):
         check(lib().evqgpu_ctx_synchronize(self._h))
+
+    def set_profiling(self, on: bool):
+        check(lib().evqgpu_ctx_set_profiling(self._h, 1 if on else 0))
+
+    @property
+    def kernel_launches(self) -> int:
+        return lib().evqgpu_ctx_kernel_launches(self._h)
+
+    # ---- multi-GPU (one process per GPU; the launcher distributes the id, e.g. with torch.distributed)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        check(lib().evqgpu_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        assert len(unique_id) == 128
+        buf = C.create_string_buffer(unique_id, 128)
+        check(lib().evqgpu_comm_init(self._h, buf, rank, nranks))
+        self.rank, self.nranks = rank, nranks
 
     # ---- tables
     def open_table(self, data) -> "Table":

@@ -83,6 +83,15 @@ int evqgpu_host_unregister(evqgpu_ctx* ctx, void* ptr) {
   });
 }
 
+int evqgpu_ctx_set_profiling(evqgpu_ctx* ctx, int on) {
+  return guarded([&] {
+    if (!ctx) fail(EVQGPU_ERR_ARG, "evqgpu_ctx_set_profiling: null context");
+    ctx->profiling = on != 0;
+  });
+}
+
+uint64_t evqgpu_ctx_kernel_launches(const evqgpu_ctx* ctx) { return ctx ? ctx->kernel_launches : 0; }
+
 void* evqgpu_ctx_stream(evqgpu_ctx* ctx) { return ctx ? (void*) ctx->stream : nullptr; }
 
 int evqgpu_ctx_synchronize(evqgpu_ctx* ctx) {

@@ -3,6 +3,8 @@
 // error at evqgpu_comm_init, never a silent single-GPU fallback.
 #include <dlfcn.h>
 #include <string.h>
+#include <algorithm>
+#include <vector>
 #include "context.h"
 #include "query.h"
 
@@ -116,6 +118,22 @@ namespace evq {
 // Used by merge.cu
 void comm_all_gather(evqgpu_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank) {
   EVQ_NCCL(nccl().AllGather(send, recv, bytes_per_rank, ncclUint8, (ncclComm_t) ctx->nccl_comm, ctx->stream));
+}
+
+// small host-side all-gather (bounds, counts): staged through device memory because NCCL moves device buffers
+std::vector<uint64_t> comm_all_gather_host(evqgpu_ctx* ctx, const std::vector<uint64_t>& mine) {
+  use_device(ctx);
+  const size_t n = mine.size();
+  DevBuf send, recv;
+  send.alloc(std::max<size_t>(n, 1) * 8);
+  recv.alloc(std::max<size_t>(n, 1) * 8 * ctx->nranks);
+  std::vector<uint64_t> all(n * ctx->nranks);
+  if (n == 0) return all;
+  EVQ_CUDA(cudaMemcpyAsync(send.p, mine.data(), n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  comm_all_gather(ctx, send.p, recv.p, n * 8);
+  EVQ_CUDA(cudaMemcpyAsync(all.data(), recv.p, all.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return all;
 }
 
 void comm_all_to_all(evqgpu_ctx* ctx, const void* send, const uint64_t* send_off, const uint64_t* send_bytes, void* recv,

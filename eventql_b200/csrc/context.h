@@ -25,6 +25,7 @@ struct evqgpu_ctx {
   // scratch for small device->host reads
   void* pinned_scratch = nullptr;   // 4 KiB pinned
   uint64_t kernel_launches = 0;     // total kernels launched through this context
+  bool profiling = false;           // bracket scan kernel launches with events (evqgpu_ctx_set_profiling)
 };
 
 namespace evq {

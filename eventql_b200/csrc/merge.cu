@@ -1,14 +1,294 @@
 // merge.cu - GroupByMergeExpression (sql/statements/select/groupby.cc:528-637) across GPUs.
+//
+// The reference merges partial aggregates on a coordinator: every shard ships rows of (SHA-1 of the group key bytes,
+// saved aggregate states) over TCP (transport/native/ops/query_partialaggr.cc:41-126) and the coordinator calls
+// SFunction.vtable.merge per group (groupby.cc:577-612; count/sum: += , aggregate.cc:48-50,196-198).  Here every GPU
+// is a shard and the exchange runs over NVLink with NCCL; group identity is byte equality of the evaluated key tuple
+// incl. NULL tags (an exact substitute for the SHA-1 of those bytes).
+//
+//   dense tier (<= 64 slots, canonical slot assignment agreed on before the scan, query.cu:compute_dense_map):
+//       all-gather of the [slots][nstate] state arrays (a few KB), combined in rank order by one small kernel ->
+//       every rank ends with the full result; fully stream-ordered (no host synchronisation)
+//   hash tier: owner(group) = bits of the key hash mod nranks; each rank packs its groups per owner, the packed
+//       records cross NVLink in one grouped ncclSend/ncclRecv (all-to-all) and the owner re-inserts them into a
+//       fresh open-addressing table with the same upsert + atomics as the scan kernel -> results stay distributed
+#include <string.h>
+#include <algorithm>
+#include <vector>
 #include "query.h"
+
+#define EVQ_NCONS 256
+#include "kernels/evq_prelude.cuh"
 
 namespace evq {
 
+struct MergeOps {
+  int nstate;
+  int nkeys;
+  int ops[72];   // EVQ_OP_* per state word
+};
+
+__device__ __forceinline__ u64 merge_identity(int op) {
+  switch (op) {
+    case EVQ_OP_MIN_U64: return evq_state_identity<EVQ_OP_MIN_U64>();
+    case EVQ_OP_MIN_I64: return evq_state_identity<EVQ_OP_MIN_I64>();
+    case EVQ_OP_MAX_I64: return evq_state_identity<EVQ_OP_MAX_I64>();
+    case EVQ_OP_MIN_F64: return evq_state_identity<EVQ_OP_MIN_F64>();
+    case EVQ_OP_MAX_F64: return evq_state_identity<EVQ_OP_MAX_F64>();
+    default: return 0ull;
+  }
+}
+
+__device__ __forceinline__ u64 merge_combine(int op, u64 a, u64 b) {
+  switch (op) {
+    case EVQ_OP_ADD_U64: return evq_state_combine<EVQ_OP_ADD_U64>(a, b);
+    case EVQ_OP_ADD_F64: return evq_state_combine<EVQ_OP_ADD_F64>(a, b);
+    case EVQ_OP_MIN_U64: return evq_state_combine<EVQ_OP_MIN_U64>(a, b);
+    case EVQ_OP_MAX_U64: return evq_state_combine<EVQ_OP_MAX_U64>(a, b);
+    case EVQ_OP_MIN_I64: return evq_state_combine<EVQ_OP_MIN_I64>(a, b);
+    case EVQ_OP_MAX_I64: return evq_state_combine<EVQ_OP_MAX_I64>(a, b);
+    case EVQ_OP_MIN_F64: return evq_state_combine<EVQ_OP_MIN_F64>(a, b);
+    default: return evq_state_combine<EVQ_OP_MAX_F64>(a, b);
+  }
+}
+
+__device__ __forceinline__ void merge_atomic(int op, u64* addr, u64 v) {
+  switch (op) {
+    case EVQ_OP_ADD_U64: evq_state_atomic<EVQ_OP_ADD_U64>(addr, v); break;
+    case EVQ_OP_ADD_F64: evq_state_atomic<EVQ_OP_ADD_F64>(addr, v); break;
+    case EVQ_OP_MIN_U64: evq_state_atomic<EVQ_OP_MIN_U64>(addr, v); break;
+    case EVQ_OP_MAX_U64: evq_state_atomic<EVQ_OP_MAX_U64>(addr, v); break;
+    case EVQ_OP_MIN_I64: evq_state_atomic<EVQ_OP_MIN_I64>(addr, v); break;
+    case EVQ_OP_MAX_I64: evq_state_atomic<EVQ_OP_MAX_I64>(addr, v); break;
+    case EVQ_OP_MIN_F64: evq_state_atomic<EVQ_OP_MIN_F64>(addr, v); break;
+    default: evq_state_atomic<EVQ_OP_MAX_F64>(addr, v); break;
+  }
+}
+
+// ---- dense tier ------------------------------------------------------------------------------------------------------
+// gathered: [nranks][nwords]; state[i] = combine over ranks in rank order (deterministic, also for double sums)
+__global__ void k_merge_dense(u64* __restrict__ state, const u64* __restrict__ gathered, int nranks, u64 nwords, MergeOps mo) {
+  const u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nwords) return;
+  const int op = mo.ops[i % mo.nstate];
+  u64 acc = gathered[i];
+  for (int r = 1; r < nranks; ++r) acc = merge_combine(op, acc, gathered[(u64) r * nwords + i]);
+  state[i] = acc;
+}
+
+// ---- hash tier -------------------------------------------------------------------------------------------------------
+// packed record: [keys nk][tag word][state nstate]   (u64 words)
+__device__ __forceinline__ u32 owner_of(u64 fp, int nranks) { return (u32) ((fp >> 40) % (u64) nranks); }
+
+__global__ void k_merge_count(EvqHashTable H, int nranks, u64* __restrict__ counts) {
+  __shared__ u32 local[16];
+  if (threadIdx.x < 16) local[threadIdx.x] = 0;
+  __syncthreads();
+  for (u64 slot = (u64) blockIdx.x * blockDim.x + threadIdx.x; slot < H.cap; slot += (u64) gridDim.x * blockDim.x) {
+    const u64 fp = H.fp[slot];
+    if (fp) atomicAdd(&local[owner_of(fp, nranks)], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < nranks && local[threadIdx.x]) atomicAdd(counts + threadIdx.x, (u64) local[threadIdx.x]);
+}
+
+__global__ void k_merge_pack(EvqHashTable H, int nranks, MergeOps mo, const u64* __restrict__ offsets, u64* __restrict__ cursors,
+                             u64* __restrict__ out) {
+  const int rec = mo.nkeys + 1 + mo.nstate;
+  for (u64 slot = (u64) blockIdx.x * blockDim.x + threadIdx.x; slot < H.cap; slot += (u64) gridDim.x * blockDim.x) {
+    const u64 fp = H.fp[slot];
+    if (!fp) continue;
+    const u32 o = owner_of(fp, nranks);
+    const u64 pos = offsets[o] + atomicAdd(cursors + o, 1ull);
+    u64* dst = out + pos * rec;
+    u64 tags = 0;
+    for (int k = 0; k < mo.nkeys; ++k) {
+      dst[k] = H.keys[(u64) k * H.cap + slot];
+      tags |= (u64) H.ktags[(u64) k * H.cap + slot] << (8 * k);
+    }
+    dst[mo.nkeys] = tags;
+    for (int s = 0; s < mo.nstate; ++s) dst[mo.nkeys + 1 + s] = H.state[(u64) s * H.cap + slot];
+  }
+}
+
+__global__ void k_merge_init(EvqHashTable H, MergeOps mo) {
+  const u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H.cap) return;
+  H.fp[i] = 0ull;
+  for (int s = 0; s < mo.nstate; ++s) H.state[(u64) s * H.cap + i] = merge_identity(mo.ops[s]);
+}
+
+template <int NK>
+__global__ void k_merge_insert(EvqHashTable H, MergeOps mo, const u64* __restrict__ recs, u64 nrecs, u64* __restrict__ counters,
+                               u32* __restrict__ status) {
+  const int rec = NK + 1 + mo.nstate;
+  for (u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x; i < nrecs; i += (u64) gridDim.x * blockDim.x) {
+    const u64* src = recs + i * rec;
+    u64 key[NK > 0 ? NK : 1];
+    u32 tag[NK > 0 ? NK : 1];
+    const u64 tags = src[NK];
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      key[k] = src[k];
+      tag[k] = (u32) ((tags >> (8 * k)) & 0xffu);
+    }
+    const u64 slot = evq_ht_upsert<NK>(H, key, tag, counters + 1);
+    if (slot == ~0ull) {
+      atomicOr(status, EVQ_ERR_TABLE_FULL);
+      continue;
+    }
+    for (int s = 0; s < mo.nstate; ++s) {
+      const u64 v = src[NK + 1 + s];
+      if (v != merge_identity(mo.ops[s])) merge_atomic(mo.ops[s], H.state + (u64) s * H.cap + slot, v);
+    }
+  }
+}
+
+static uint64_t next_pow2_(uint64_t v) {
+  uint64_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+static MergeOps merge_ops_of(const evqgpu_query& q) {
+  MergeOps mo;
+  memset(&mo, 0, sizeof(mo));
+  mo.nstate = (int) q.state_ops.size();
+  mo.nkeys = (int) q.group.size();
+  if (mo.nstate > 72) fail(EVQGPU_ERR_UNSUPPORTED, "merge: more than 72 aggregate state words");
+  for (int i = 0; i < mo.nstate; ++i) mo.ops[i] = q.state_ops[i];
+  return mo;
+}
+
+static void merge_dense(evqgpu_query& q) {
+  evqgpu_ctx* ctx = q.ctx;
+  const MergeOps mo = merge_ops_of(q);
+  const uint64_t slots = q.shape.g1 > 1 ? (uint64_t) q.shape.g1 : 1;
+  const uint64_t nwords = slots * mo.nstate;
+  if (q.merge_recv.bytes < nwords * 8 * ctx->nranks) q.merge_recv.alloc(nwords * 8 * ctx->nranks);
+  comm_all_gather(ctx, q.dense_state.p, q.merge_recv.p, nwords * 8);
+  k_merge_dense<<<(unsigned) ((nwords + 127) / 128), 128, 0, ctx->stream>>>(q.dense_state.as<u64>(), q.merge_recv.as<u64>(),
+                                                                           ctx->nranks, nwords, mo);
+  EVQ_CUDA(cudaGetLastError());
+  ctx->kernel_launches++;
+  q.stats.kernel_launches++;
+  emit_results(q);
+  q.pending = true;   // row count is read by the next finish
+}
+
+template <int NK>
+static void launch_insert(evqgpu_ctx* ctx, EvqHashTable H, const MergeOps& mo, const u64* recs, u64 nrecs, u64* counters, u32* status) {
+  const unsigned grid = (unsigned) std::min<uint64_t>((nrecs + 255) / 256, (uint64_t) ctx->sm_count * 8);
+  k_merge_insert<NK><<<grid, 256, 0, ctx->stream>>>(H, mo, recs, nrecs, counters, status);
+}
+
+static void merge_hash(evqgpu_query& q) {
+  evqgpu_ctx* ctx = q.ctx;
+  const int n = ctx->nranks;
+  if (n > 16) fail(EVQGPU_ERR_UNSUPPORTED, "merge: at most 16 ranks");
+  const MergeOps mo = merge_ops_of(q);
+  const int rec = mo.nkeys + 1 + mo.nstate;
+  if (q.pending) finish_query(q);   // the local table must be complete (and large enough) before it is shipped
+
+  EvqHashTable H = q.emit.ht;
+  // 1. groups per owner
+  DevBuf counts;
+  counts.alloc(3 * 16 * 8);   // [0..16) counts, [16..32) offsets, [32..48) cursors
+  EVQ_CUDA(cudaMemsetAsync(counts.p, 0, counts.bytes, ctx->stream));
+  const unsigned grid = (unsigned) std::min<uint64_t>((H.cap + 255) / 256, (uint64_t) ctx->sm_count * 8);
+  k_merge_count<<<grid, 256, 0, ctx->stream>>>(H, n, counts.as<u64>());
+  EVQ_CUDA(cudaGetLastError());
+  std::vector<uint64_t> mine(16, 0);
+  EVQ_CUDA(cudaMemcpyAsync(mine.data(), counts.p, 16 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  // 2. everybody learns everybody's counts
+  std::vector<uint64_t> all = comm_all_gather_host(ctx, mine);   // [rank][16]
+  std::vector<uint64_t> send_off(n), send_bytes(n), recv_off(n), recv_bytes(n), offs(16, 0);
+  uint64_t send_total = 0, recv_total = 0;
+  for (int r = 0; r < n; ++r) {
+    offs[r] = send_total;
+    send_off[r] = send_total * rec * 8;
+    send_bytes[r] = mine[r] * rec * 8;
+    send_total += mine[r];
+    const uint64_t from_r = all[(size_t) r * 16 + ctx->rank];
+    recv_off[r] = recv_total * rec * 8;
+    recv_bytes[r] = from_r * rec * 8;
+    recv_total += from_r;
+  }
+  // 3. pack per owner
+  DevBuf sendbuf, recvbuf;
+  sendbuf.alloc(std::max<uint64_t>(send_total, 1) * rec * 8);
+  recvbuf.alloc(std::max<uint64_t>(recv_total, 1) * rec * 8);
+  EVQ_CUDA(cudaMemcpyAsync(counts.as<u64>() + 16, offs.data(), 16 * 8, cudaMemcpyHostToDevice, ctx->stream));
+  k_merge_pack<<<grid, 256, 0, ctx->stream>>>(H, n, mo, counts.as<u64>() + 16, counts.as<u64>() + 32, sendbuf.as<u64>());
+  EVQ_CUDA(cudaGetLastError());
+  // 4. all-to-all over NVLink
+  comm_all_to_all(ctx, sendbuf.p, send_off.data(), send_bytes.data(), recvbuf.p, recv_off.data(), recv_bytes.data());
+  // 5. owner-side merge into a fresh table
+  const size_t nk = std::max<size_t>(1, (size_t) mo.nkeys);
+  const uint64_t cap = next_pow2_(std::max<uint64_t>(1024, recv_total * 2));
+  DevBuf fp, keys, ktags, state;
+  fp.alloc(cap * 8);
+  keys.alloc(cap * 8 * nk);
+  ktags.alloc(cap * nk);
+  state.alloc(cap * 8 * mo.nstate);
+  EvqHashTable M;
+  M.fp = fp.as<u64>();
+  M.keys = keys.as<u64>();
+  M.ktags = ktags.as<u8>();
+  M.state = state.as<u64>();
+  M.cap = cap;
+  k_merge_init<<<(unsigned) ((cap + 255) / 256), 256, 0, ctx->stream>>>(M, mo);
+  EVQ_CUDA(cudaGetLastError());
+  EVQ_CUDA(cudaMemsetAsync(q.counters.as<u64>() + 1, 0, 8, ctx->stream));
+  if (recv_total) {
+    u64* cnt = q.counters.as<u64>();
+    u32* st = q.status.as<u32>();
+    const u64* recs = recvbuf.as<u64>();
+    switch (mo.nkeys) {
+      case 0: launch_insert<0>(ctx, M, mo, recs, recv_total, cnt, st); break;
+      case 1: launch_insert<1>(ctx, M, mo, recs, recv_total, cnt, st); break;
+      case 2: launch_insert<2>(ctx, M, mo, recs, recv_total, cnt, st); break;
+      case 3: launch_insert<3>(ctx, M, mo, recs, recv_total, cnt, st); break;
+      case 4: launch_insert<4>(ctx, M, mo, recs, recv_total, cnt, st); break;
+      case 5: launch_insert<5>(ctx, M, mo, recs, recv_total, cnt, st); break;
+      case 6: launch_insert<6>(ctx, M, mo, recs, recv_total, cnt, st); break;
+      case 7: launch_insert<7>(ctx, M, mo, recs, recv_total, cnt, st); break;
+      default: launch_insert<8>(ctx, M, mo, recs, recv_total, cnt, st); break;
+    }
+    EVQ_CUDA(cudaGetLastError());
+  }
+  ctx->kernel_launches += 4;
+  q.stats.kernel_launches += 4;
+  // the merged table replaces the local one
+  q.ht_fp = std::move(fp);
+  q.ht_keys = std::move(keys);
+  q.ht_ktags = std::move(ktags);
+  q.ht_state = std::move(state);
+  q.ht_cap = 0;   // next execute sizes its table afresh
+  q.emit.ht = M;
+  q.emit.slots = cap;
+  q.emit_total_rows = std::max<uint64_t>(recv_total, 1);
+  emit_results(q);
+  q.pending = true;
+  finish_query(q);
+}
+
 void merge_query(evqgpu_query& q) {
-  if (q.ctx->nranks <= 1) {
+  if (!(q.flags & EVQGPU_QUERY_GROUPBY)) fail(EVQGPU_ERR_ARG, "evqgpu_query_merge: not an aggregate plan");
+  if (q.tables.empty()) fail(EVQGPU_ERR_ARG, "evqgpu_query_merge: the query has not been executed");
+  if (q.merged) return;
+  use_device(q.ctx);
+  if (q.ctx->nranks <= 1 || !q.ctx->nccl_comm) {
+    if (!q.emitted) emit_results(q), q.pending = true;
     q.merged = true;
     return;
   }
-  fail(EVQGPU_ERR_UNSUPPORTED, "multi-rank merge is not implemented yet");
+  if (!(q.flags & EVQGPU_QUERY_PARTIAL))
+    fail(EVQGPU_ERR_ARG, "evqgpu_query_merge: the plan was not created with EVQGPU_QUERY_PARTIAL");
+  if (q.shape.tier == 1) merge_dense(q);
+  else merge_hash(q);
+  q.merged = true;
 }
 
 }  // namespace evq

@@ -329,7 +329,17 @@ static void run_scan(evqgpu_query& q, const KernelShape& s, std::vector<TablePla
     const int ctas_per_sm = std::max<int>(1, std::min<size_t>(s.min_ctas == 2 ? 2 : 1, (228 * 1024) / (p.smem + 1024)));
     const unsigned grid = (unsigned) std::min<uint64_t>(p.table->num_tiles, (uint64_t) ctx->sm_count * ctas_per_sm);
     void* args[] = {&P, &stage_bytes};
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ctx->profiling) {
+      EVQ_CUDA(cudaEventCreate(&e0));
+      EVQ_CUDA(cudaEventCreate(&e1));
+      EVQ_CUDA(cudaEventRecord(e0, ctx->stream));
+    }
     launch(ctx, kern, dim3(grid), dim3(s.ncons + 32), p.smem, args);
+    if (e0) {
+      EVQ_CUDA(cudaEventRecord(e1, ctx->stream));
+      q.prof_events.push_back({e0, e1});
+    }
     q.stats.kernel_launches++;
   }
 }
@@ -419,33 +429,66 @@ static bool compute_dense_map(evqgpu_query& q, std::vector<evqgpu_table*>& table
   q.jit_ms_total += bq->jit_ms_total;
   uint64_t nrows = 0;
   evqgpu_query_num_rows(bq, &nrows);
-  if (nrows == 0) {   // empty input: any mapping works
-    for (size_t i = 0; i < nk; ++i) { dm.key_min[i] = 0; dm.key_range[i] = 2; dm.key_null_idx[i] = 1; }
-  } else {
-    std::vector<bool> nullable_cols(q.input_columns.size(), false);
-    for (auto* t : tables)
-      for (size_t i = 0; i < q.input_columns.size(); ++i) {
-        const int ci = t->find(q.input_columns[i].c_str());
-        if (ci >= 0 && t->cols[ci].meta.dlevel_max > 0) nullable_cols[i] = true;
-      }
+  // local bounds per key: {valid, min, max, may be NULL}
+  std::vector<bool> nullable_cols(q.input_columns.size(), false);
+  for (auto* t : tables)
+    for (size_t i = 0; i < q.input_columns.size(); ++i) {
+      const int ci = t->find(q.input_columns[i].c_str());
+      if (ci >= 0 && t->cols[ci].meta.dlevel_max > 0) nullable_cols[i] = true;
+    }
+  const size_t BW = 4;
+  std::vector<uint64_t> bounds(BW * nk, 0);
+  // only a bare column reference keeps its NULL tag as a key: one extra slot index then
+  for (size_t i = 0; i < nk; ++i) bounds[BW * i + 3] = key_may_be_null(q.group[i].get(), nullable_cols) ? 1 : 0;
+  std::vector<bool> is_signed(nk, false);
+  for (size_t i = 0; i < nk; ++i) is_signed[i] = q.group[i]->type != EVQ_UINT64;   // int64 / bool / timestamp64 went through int64
+  if (nrows != 0) {
     std::vector<std::vector<uint8_t>> bufs(sel.size(), std::vector<uint8_t>(9));
     std::vector<void*> ptrs;
     for (auto& b : bufs) ptrs.push_back(b.data());
     uint64_t got = 0;
     if (evqgpu_query_fetch(bq, 0, 1, ptrs.data(), &got) != EVQGPU_OK || got != 1) return false;
     for (size_t i = 0; i < nk; ++i) {
-      uint64_t mn, mx;
-      memcpy(&mn, bufs[2 * i].data(), 8);
-      memcpy(&mx, bufs[2 * i + 1].data(), 8);
-      // signed and unsigned keys alike: (key - min) as an unsigned difference
-      const uint64_t span = mx - mn;
-      if (span > 1000000) return false;
-      dm.key_min[i] = mn;
-      // one extra index for NULL keys, only when the expression can carry a NULL tag at all
-      const bool may_null = key_may_be_null(q.group[i].get(), nullable_cols);
-      dm.key_range[i] = span + (may_null ? 2 : 1);
-      dm.key_null_idx[i] = may_null ? span + 1 : ~0ull;
+      bounds[BW * i] = 1;
+      memcpy(&bounds[BW * i + 1], bufs[2 * i].data(), 8);
+      memcpy(&bounds[BW * i + 2], bufs[2 * i + 1].data(), 8);
     }
+  }
+  // every rank must arrive at the same slot assignment: combine the bounds of all ranks (SURVEY 8e "canonical slot assignment")
+  if (q.ctx->nccl_comm && q.ctx->nranks > 1) {
+    std::vector<uint64_t> all = comm_all_gather_host(q.ctx, bounds);
+    for (size_t i = 0; i < nk; ++i) {
+      uint64_t valid = 0, mn = 0, mx = 0, may_null = 0;
+      for (int r = 0; r < q.ctx->nranks; ++r) {
+        const uint64_t* b = &all[(size_t) r * bounds.size() + BW * i];
+        may_null |= b[3];
+        if (!b[0]) continue;
+        if (!valid) { valid = 1; mn = b[1]; mx = b[2]; continue; }
+        if (is_signed[i]) {
+          if ((int64_t) b[1] < (int64_t) mn) mn = b[1];
+          if ((int64_t) b[2] > (int64_t) mx) mx = b[2];
+        } else {
+          if (b[1] < mn) mn = b[1];
+          if (b[2] > mx) mx = b[2];
+        }
+      }
+      bounds[BW * i] = valid; bounds[BW * i + 1] = mn; bounds[BW * i + 2] = mx; bounds[BW * i + 3] = may_null;
+    }
+  }
+  for (size_t i = 0; i < nk; ++i) {
+    if (!bounds[BW * i]) {   // no row anywhere: any mapping works
+      dm.key_min[i] = 0; dm.key_range[i] = 2; dm.key_null_idx[i] = 1;
+      continue;
+    }
+    const uint64_t mn = bounds[BW * i + 1], mx = bounds[BW * i + 2];
+    // signed and unsigned keys alike: (key - min) as an unsigned difference
+    const uint64_t span = mx - mn;
+    if (span > 1000000) return false;
+    dm.key_min[i] = mn;
+    // one extra index for NULL keys, only when the expression can carry a NULL tag at all
+    const bool may_null = bounds[BW * i + 3] != 0;
+    dm.key_range[i] = span + (may_null ? 2 : 1);
+    dm.key_null_idx[i] = may_null ? span + 1 : ~0ull;
   }
   uint64_t slots = 1;
   for (size_t i = nk; i-- > 0;) {
@@ -455,6 +498,27 @@ static bool compute_dense_map(evqgpu_query& q, std::vector<evqgpu_table*>& table
   }
   dm.slots = slots;
   return true;
+}
+
+// GroupByExpression::nextBatch (groupby.cc:187-220) for all groups at once: the emit kernel evaluates every select
+// item's `get` side per group and writes packed SVector columns
+void emit_results(evqgpu_query& q) {
+  evqgpu_ctx* ctx = q.ctx;
+  const uint64_t emit_slots = q.emit.slots;
+  const uint64_t out_cap = q.shape.tier == 1 ? emit_slots : std::min<uint64_t>(emit_slots, std::max<uint64_t>(q.emit_total_rows, 1));
+  q.out_cols.resize(q.select.size());
+  for (size_t i = 0; i < q.select.size(); ++i)
+    ensure(q.out_cols[i], out_cap * (q.select[i].expr->type == EVQ_BOOL ? 2 : 9) + 16);
+  q.out_capacity = out_cap;
+  EVQ_CUDA(cudaMemsetAsync(q.out_count.p, 0, 8, ctx->stream));
+  EmitParams ep = q.emit;
+  ep.out_count = q.out_count.as<u64>();
+  ep.out_capacity = out_cap;
+  for (size_t i = 0; i < q.select.size(); ++i) ep.out_cols[i] = q.out_cols[i].as<u8>();
+  void* args[] = {&ep};
+  launch(ctx, q.module->kernels.at("evq_emit"), dim3((unsigned) ((emit_slots + 255) / 256)), dim3(256), 0, args);
+  q.stats.kernel_launches++;
+  q.emitted = true;
 }
 
 static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std::vector<evqgpu_table*>& tables, bool sync) {
@@ -511,7 +575,6 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
   base.counters = q.counters.as<u64>();
   EVQ_CUDA(cudaMemsetAsync(q.status.p, 0, 16, ctx->stream));
   EVQ_CUDA(cudaMemsetAsync(q.counters.p, 0, 32, ctx->stream));
-  EVQ_CUDA(cudaMemsetAsync(q.out_count.p, 0, 8, ctx->stream));
   InitParams ip;
   memset(&ip, 0, sizeof(ip));
   uint64_t emit_slots = 0;
@@ -556,31 +619,21 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
 
   run_scan(q, s, plans, base);
 
-  // ---- emit
-  const uint64_t out_cap = s.tier == 1 ? emit_slots : std::min<uint64_t>(emit_slots, std::max<uint64_t>(total_rows, 1));
-  q.out_cols.resize(q.select.size());
-  for (size_t i = 0; i < q.select.size(); ++i)
-    ensure(q.out_cols[i], out_cap * (q.select[i].expr->type == EVQ_BOOL ? 2 : 9) + 16);
-  q.out_capacity = out_cap;
-  EmitParams ep;
-  memset(&ep, 0, sizeof(ep));
-  ep.dense_state = base.dense_state;
-  ep.ht = base.ht;
+  // ---- emit (deferred to evqgpu_query_merge for partial plans of a multi-rank job)
+  q.emit_total_rows = total_rows;
+  q.emit = EmitParams();
+  memset(&q.emit, 0, sizeof(q.emit));
+  q.emit.dense_state = base.dense_state;
+  q.emit.ht = base.ht;
   for (size_t i = 0; i < nk; ++i) {
-    ep.key_min[i] = dm.key_min[i];
-    ep.key_stride[i] = dm.key_stride[i];
-    ep.key_null_idx[i] = dm.key_null_idx[i];
-    ep.key_range[i] = dm.key_range[i];
+    q.emit.key_min[i] = dm.key_min[i];
+    q.emit.key_stride[i] = dm.key_stride[i];
+    q.emit.key_null_idx[i] = dm.key_null_idx[i];
+    q.emit.key_range[i] = dm.key_range[i];
   }
-  ep.slots = emit_slots;
-  ep.out_count = q.out_count.as<u64>();
-  ep.out_capacity = out_cap;
-  for (size_t i = 0; i < q.select.size(); ++i) ep.out_cols[i] = q.out_cols[i].as<u8>();
-  {
-    void* args[] = {&ep};
-    launch(ctx, q.module->kernels.at("evq_emit"), dim3((unsigned) ((emit_slots + 255) / 256)), dim3(256), 0, args);
-    q.stats.kernel_launches++;
-  }
+  q.emit.slots = emit_slots;
+  q.emitted = false;
+  if (!((q.flags & EVQGPU_QUERY_PARTIAL) && ctx->nranks > 1)) emit_results(q);
   (void) sync;
 }
 
@@ -647,7 +700,7 @@ static void execute_scan_only(evqgpu_query& q, std::vector<TablePlan>& plans, st
   (void) total_rows;
 }
 
-static void finish_query(evqgpu_query& q) {
+void finish_query(evqgpu_query& q) {
   evqgpu_ctx* ctx = q.ctx;
   use_device(ctx);
   struct { u32 status[4]; u64 counters[4]; u64 out_count; } host;
@@ -656,6 +709,15 @@ static void finish_query(evqgpu_query& q) {
   EVQ_CUDA(cudaMemcpyAsync(&host.out_count, q.out_count.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
   EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
   q.pending = false;
+  q.stats.scan_ms = 0;
+  q.stats.scan_launches = (uint32_t) q.prof_events.size();
+  for (auto& e : q.prof_events) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, e.first, e.second) == cudaSuccess) q.stats.scan_ms += ms;
+    cudaEventDestroy(e.first);
+    cudaEventDestroy(e.second);
+  }
+  q.prof_events.clear();
   const u32 err = host.status[0];
   q.stats.rows_passed = host.counters[0];
   if (err & EVQ_ERR_DIV_ZERO) fail(EVQGPU_ERR_RUNTIME, "division by zero");

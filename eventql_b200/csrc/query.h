@@ -81,6 +81,7 @@ struct evqgpu_query {
   std::vector<bool> col_used;
 
   // device state, reused across executions
+  evq::DevBuf merge_recv;
   evq::DevBuf dense_state, ht_fp, ht_keys, ht_ktags, ht_state, status, counters, out_count, tile_counts, tile_base;
   std::vector<evq::DevBuf> out_cols;
   uint64_t out_capacity = 0;
@@ -99,12 +100,27 @@ struct evqgpu_query {
   evqgpu_query_stats stats = {};
   std::string kernel_source;
   float jit_ms_total = 0;
+  evq::EmitParams emit;             // parameters of the (possibly deferred) emit kernel
+  uint64_t emit_total_rows = 0;
+  bool emitted = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;   // around scan launches, summed at finish
+  ~evqgpu_query() {
+    for (auto& e : prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  }
 };
 
 namespace evq {
 // codegen.cc
 std::string generate_source(const evqgpu_query& q, const KernelShape& shape);
 int state_words_of(const FnInfo& fi);
+// query.cu
+void emit_results(evqgpu_query& q);
+void finish_query(evqgpu_query& q);
 // merge.cu
 void merge_query(evqgpu_query& q);
+// comm.cc
+std::vector<uint64_t> comm_all_gather_host(evqgpu_ctx* ctx, const std::vector<uint64_t>& mine);   // [rank][mine.size()]
+void comm_all_gather(evqgpu_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank);
+void comm_all_to_all(evqgpu_ctx* ctx, const void* send, const uint64_t* send_off, const uint64_t* send_bytes, void* recv,
+                     const uint64_t* recv_off, const uint64_t* recv_bytes);
 }  // namespace evq

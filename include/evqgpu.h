@@ -129,6 +129,12 @@ EVQGPU_API int evqgpu_host_unregister(evqgpu_ctx* ctx, void* ptr);
 EVQGPU_API void* evqgpu_ctx_stream(evqgpu_ctx* ctx);
 EVQGPU_API int evqgpu_ctx_synchronize(evqgpu_ctx* ctx);
 
+/* Profiling: when on, every scan kernel launch is bracketed by CUDA events on the context stream and
+ * evqgpu_query_stats.scan_ms reports their summed device time (bench.py's roofline figure). */
+EVQGPU_API int evqgpu_ctx_set_profiling(evqgpu_ctx* ctx, int on);
+/* Kernels launched through this context since it was created (bench.py's gpu_launches claim). */
+EVQGPU_API uint64_t evqgpu_ctx_kernel_launches(const evqgpu_ctx* ctx);
+
 /* ------------------------------------------------------------------------------------------
  * tables (one cstable file / partition segment, resident in HBM)
  * ---------------------------------------------------------------------------------------- */
@@ -300,7 +306,10 @@ typedef struct evqgpu_query_stats {
   uint32_t kernel_launches;      /* device kernels launched by the last execute */
   uint32_t strategy;             /* 0 scan-only, 1 register/shared-memory low-cardinality, 2 global hash table */
   float jit_ms;                  /* NVRTC time spent by evqgpu_query_create (0 when cached) */
-  float reserved;
+  float scan_ms;                 /* summed device time of the scan kernel launches since the last finish
+                                    (only with evqgpu_ctx_set_profiling) */
+  uint32_t scan_launches;        /* number of scan kernel launches scan_ms covers */
+  uint32_t reserved;
 } evqgpu_query_stats;
 EVQGPU_API int evqgpu_query_get_stats(evqgpu_query* q, evqgpu_query_stats* out);
 

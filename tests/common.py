@@ -56,7 +56,7 @@ def lineitem_spec(encoding=P.ENC_UINT64_LEB128, null_every=0):
 
 
 def events_spec(num_keys=10_000_000, key_encoding=P.ENC_UINT64_PLAIN):   # C4
-    return [dict(name="key", logical_type=P.COL_UNSIGNED_INT, encoding=key_encoding, seed=SEED0 + 100, lo=0, span=num_keys, transform=1),
+    return [dict(name="ekey", logical_type=P.COL_UNSIGNED_INT, encoding=key_encoding, seed=SEED0 + 100, lo=0, span=num_keys, transform=1),
             dict(name="v", logical_type=P.COL_UNSIGNED_INT, encoding=P.ENC_UINT64_LEB128, seed=SEED0 + 101, lo=0, span=1000000)]
 
 
@@ -131,9 +131,9 @@ def q1(spec, means=True):
 
 def q_highcard(spec, expected_groups=0):
     c, names = cols_of(spec)
-    sql = "select key, count(1), sum(v), mean(v) from events where v >= 0 group by key;"
-    return sql, P.QueryPlan(names, [c["key"], P.call("count", P.lit(1)), P.call("sum", c["v"]), P.call("mean", c["v"])],
-                            where=c["v"] >= 0, group=[c["key"]], expected_groups=expected_groups)
+    sql = "select ekey, count(1), sum(v), mean(v) from events where v >= 0 group by ekey;"   # `key` is a reserved word in csql
+    return sql, P.QueryPlan(names, [c["ekey"], P.call("count", P.lit(1)), P.call("sum", c["v"]), P.call("mean", c["v"])],
+                            where=c["v"] >= 0, group=[c["ekey"]], expected_groups=expected_groups)
 
 
 def q_timeseries(spec, expected_groups=0):
@@ -168,3 +168,197 @@ def rows_equal(a, b, rel=1e-9):
             elif x != y:
                 return False, "%r != %r" % (ra, rb)
     return True, ""
+
+
+# ---- semantics cases over mixed_spec(): NULL handling (SURVEY H7/H8), floats, bools, if(), division by zero ----
+def semantic_queries(spec):
+    """[(name, sql, plan)] - every SQL is accepted by the reference planner."""
+    c, names = cols_of(spec)
+    Q = []
+
+    def add(name, sql, select, where=None, group=(), flags=P.QUERY_GROUPBY):
+        Q.append((name, sql, P.QueryPlan(names, list(select), where=where, group=list(group), flags=flags)))
+
+    cnt = P.call("count", P.lit(1))
+    add("null_group_bare", "select k, count(1), sum(k) from t where b >= 0 group by k;",
+        [c["k"], cnt, P.call("sum", c["k"])], where=c["b"] >= 0, group=[c["k"]])
+    add("null_group_expr", "select k + 1, count(1) from t where b >= 0 group by k + 1;",
+        [c["k"] + 1, cnt], where=c["b"] >= 0, group=[c["k"] + 1])
+    add("null_where_lt", "select count(1), sum(a) from t where k < 1 and a >= 0;",
+        [cnt, P.call("sum", c["a"])], where=(c["k"] < 1) & (c["a"] >= 0))
+    add("null_minmaxmean", "select min(a), max(a), mean(a), count(1), min(d), max(d), mean(d) from t where a >= 0 and d >= 0;",
+        [P.call("min", c["a"]), P.call("max", c["a"]), P.call("mean", c["a"]), cnt, P.call("min", c["d"]),
+         P.call("max", c["d"]), P.call("mean", c["d"])], where=(c["a"] >= 0) & (c["d"] >= 0))
+    add("float_aggs", "select bo, sum(f), min(f), max(f), mean(f), count(1) from t where f >= 0.0 group by bo;",
+        [c["bo"], P.call("sum", c["f"]), P.call("min", c["f"]), P.call("max", c["f"]), P.call("mean", c["f"]), cnt],
+        where=c["f"] >= 0.0, group=[c["bo"]])
+    add("float_pred", "select count(1), sum(c) from t where f * 2.0 > 700.5 and c > 0;",
+        [cnt, P.call("sum", c["c"])], where=((c["f"] * 2.0) > 700.5) & (c["c"] > 0))
+    add("if_expr", "select if(b < 50, 1, 2), count(1), sum(if(b < 50, c, d)) from t where b >= 0 and c >= 0 and d >= 0 group by if(b < 50, 1, 2);",
+        [P.If(c["b"] < 50, P.lit(1), P.lit(2)), cnt, P.call("sum", P.If(c["b"] < 50, c["c"], c["d"]))],
+        where=(c["b"] >= 0) & (c["c"] >= 0) & (c["d"] >= 0), group=[P.If(c["b"] < 50, P.lit(1), P.lit(2))])
+    add("wrap_sum", "select count(1), sum(big), sum(big * big), min(big), max(big) from t where big >= 0;",
+        [cnt, P.call("sum", c["big"]), P.call("sum", c["big"] * c["big"]), P.call("min", c["big"]), P.call("max", c["big"])],
+        where=c["big"] >= 0)
+    add("mod_div", "select b % 7, count(1), sum(c / (b + 1)) from t where b >= 0 and c >= 0 group by b % 7;",
+        [c["b"] % 7, cnt, P.call("sum", c["c"] / (c["b"] + 1))], where=(c["b"] >= 0) & (c["c"] >= 0), group=[c["b"] % 7])
+    add("time_bucket", "select t / 3600000000, count(1), min(t), max(t) from t where t > 0 group by t / 3600000000;",
+        [c["t"] / 3600000000, cnt, P.call("min", c["t"]), P.call("max", c["t"])], where=c["t"] > 0,
+        group=[c["t"] / 3600000000])
+    add("or_neg", "select count(1) from t where not (b < 10 or bo) and d >= 0;",
+        [cnt], where=(~((c["b"] < 10) | c["bo"])) & (c["d"] >= 0))
+    add("empty_result", "select count(1), sum(b) from t where b > 1000;", [cnt, P.call("sum", c["b"])], where=c["b"] > 1000)
+    add("empty_groups", "select b, count(1) from t where b > 1000 group by b;", [c["b"], cnt], where=c["b"] > 1000, group=[c["b"]])
+    add("div_zero", "select count(1), sum(c / b) from t where b >= 0 and c >= 0;",
+        [cnt, P.call("sum", c["c"] / c["b"])], where=(c["b"] >= 0) & (c["c"] >= 0))
+    add("signed", "select count(1), sum(to_int64(b) - 50), min(to_int64(b) - 50), max(to_int64(b) - 50) from t where b >= 0;",
+        [cnt, P.call("sum", P.call("sub", P.call("to_int64", c["b"]), P.lit(50))),
+         P.call("min", P.call("sub", P.call("to_int64", c["b"]), P.lit(50))),
+         P.call("max", P.call("sub", P.call("to_int64", c["b"]), P.lit(50)))], where=c["b"] >= 0)
+    # scan-only plans (FastCSTableScan alone): filtered projection keeps table order
+    add("scan_project", "select a, d, f, bo, c + d from t where b < 5;",
+        [c["a"], c["d"], c["f"], c["bo"], c["c"] + c["d"]], where=c["b"] < 5, flags=0)
+    add("scan_all", "select k, big from t;", [c["k"], c["big"]], flags=0)
+    return Q
+
+
+def testtbl_queries():
+    """C1: the reference's own fixture test/sql_testdata/testtbl.cst (v0.1.0, 213 rows). Input column: time."""
+    t = P.Col(0, P.UINT64)
+    names = ["time"]
+    cnt = P.call("count", P.lit(1))
+    aggs = [cnt, P.call("sum", t), P.call("min", t), P.call("max", t)]
+    return [
+        ("c1_group_time", "select time, count(1), sum(time), min(time), max(time) from testtable group by time;",
+         P.QueryPlan(names, [t] + aggs, group=[t])),
+        ("c1_group_hour", "select time / 3600000000, count(1), sum(time), min(time), max(time) from testtable group by time / 3600000000;",
+         P.QueryPlan(names, [t / 3600000000] + aggs, group=[t / 3600000000])),
+        ("c1_global", "select count(1), sum(time), min(time), max(time), mean(time) from testtable where time > 0;",
+         P.QueryPlan(names, aggs + [P.call("mean", t)], where=t > 0)),
+        ("c1_filtered", "select count(1), sum(time) from testtable where time > 1438055000000000;",
+         P.QueryPlan(names, [cnt, P.call("sum", t)], where=t > 1438055000000000)),
+        ("c1_scan", "select testtable.time from testtable;", P.QueryPlan(names, [t], flags=0)),
+    ]
+
+
+def parse_ref_rows(rows, types):
+    """Golden rows (lists of strings as printed by oracle/ref_tools/evqlref.cc) -> python tuples."""
+    out = []
+    for r in rows:
+        vals = []
+        for s, t in zip(r, types):
+            if s == "NULL":
+                vals.append(None)
+            elif t == "float64":
+                vals.append(float(s))
+            elif t == "bool":
+                vals.append(s == "true")
+            else:
+                vals.append(int(s))
+        out.append(tuple(vals))
+    return out
+
+
+# the golden case table: name -> (spec builder, rows, query builder).  tests/golden/make_golden.py runs the
+# REFERENCE on these; tests compare the oracle (CPU) and the CUDA path against the stored reference rows.
+GOLDEN_TABLES = {
+    "lineitem_leb": (lambda: lineitem_spec(), 120_000),
+    "lineitem_plain": (lambda: lineitem_spec(P.ENC_UINT64_PLAIN), 40_000),
+    "lineitem_null": (lambda: lineitem_spec(null_every=7), 60_000),
+    "events": (lambda: events_spec(5000), 80_000),
+    "readings": (lambda: readings_spec(0), 60_000),
+    "mixed": (lambda: mixed_spec(), 70_000),
+}
+
+
+def golden_cases():
+    """[(case name, table name, sql table alias, sql, plan)]"""
+    out = []
+    for tname in ("lineitem_leb", "lineitem_plain", "lineitem_null"):
+        spec = GOLDEN_TABLES[tname][0]()
+        sql, plan = q6(spec)
+        out.append(("q6_" + tname, tname, "lineitem", sql, plan))
+        sql, plan = q1(spec)
+        out.append(("q1_" + tname, tname, "lineitem", sql, plan))
+    spec = GOLDEN_TABLES["events"][0]()
+    sql, plan = q_highcard(spec)
+    out.append(("highcard_events", "events", "events", sql, plan))
+    spec = GOLDEN_TABLES["readings"][0]()
+    sql, plan = q_timeseries(spec)
+    out.append(("timeseries_readings", "readings", "readings", sql, plan))
+    spec = GOLDEN_TABLES["mixed"][0]()
+    for name, sql, plan in semantic_queries(spec):
+        out.append(("sem_" + name, "mixed", "t", sql, plan))
+    return out
+
+
+def rows_digest(rows, types, ordered):
+    """sha256 over the exact (non-float) columns of the rows; GROUP BY results are sorted first."""
+    import hashlib
+    keep = [i for i, t in enumerate(types) if t != "float64"]
+    lines = [";".join("NULL" if r[i] is None else str(int(r[i])) if not isinstance(r[i], bool) else str(r[i]).lower() for i in keep)
+             for r in rows]
+    if not ordered:
+        lines.sort()
+    return hashlib.sha256("\n".join(lines).encode()).hexdigest()
+
+
+_GOLDEN = None
+
+
+def golden():
+    """tests/golden/ref_results.json: rows returned by the REFERENCE engine (tests/golden/make_golden.py)."""
+    global _GOLDEN
+    if _GOLDEN is None:
+        import json
+        with open(os.path.join(ROOT, "tests", "golden", "ref_results.json")) as fh:
+            _GOLDEN = json.load(fh)["cases"]
+    return _GOLDEN
+
+
+def check_against_golden(case: str, got_rows, ordered: bool):
+    """Compare result rows (python tuples, None = NULL) with the reference's stored rows for `case`."""
+    g = golden()[case]
+    assert "error" not in g, "case %s expects an error: %s" % (case, g.get("error"))
+    assert len(got_rows) == g["num_rows"], "%s: %d rows, reference returned %d" % (case, len(got_rows), g["num_rows"])
+    if "sha256" in g:
+        assert rows_digest(got_rows, g["types"], ordered) == g["sha256"], "%s: digest of exact columns differs" % case
+        head = parse_ref_rows(g["rows"], g["types"])
+        mine = got_rows if ordered else sorted(got_rows, key=lambda r: [";".join("NULL" if v is None else str(v) for v in r)])
+        if ordered:
+            for a, b in zip(mine[:len(head)], head):
+                ok, why = rows_equal([a], [b])
+                assert ok, "%s: %s" % (case, why)
+        return
+    want = parse_ref_rows(g["rows"], g["types"])
+    if ordered:
+        for i, (a, b) in enumerate(zip(got_rows, want)):
+            ok, why = rows_equal([a], [b])
+            assert ok, "%s row %d: %s" % (case, i, why)
+    else:
+        ok, why = rows_equal(got_rows, want)
+        assert ok, "%s: %s" % (case, why)
+
+
+_TABLE_CACHE = {}
+
+
+def golden_table_path(tname: str) -> str:
+    """The golden table `tname`, written (once per session) with the oracle's writer into a temp dir."""
+    import tempfile
+    if tname == "testtbl.cst":
+        return os.path.join(ROOT, "tests", "golden", "testtbl.cst")
+    if tname not in _TABLE_CACHE:
+        d = _TABLE_CACHE.setdefault("__dir__", tempfile.mkdtemp(prefix="evqtables"))
+        mk, nrows = GOLDEN_TABLES[tname]
+        p = os.path.join(d, tname + ".cst")
+        write_table(p, mk(), nrows)
+        _TABLE_CACHE[tname] = p
+    return _TABLE_CACHE[tname]
+
+
+def all_golden_cases():
+    """[(case, table name, plan, ordered)] incl. the C1 fixture cases"""
+    out = [(name, tname, plan, not plan.is_groupby) for name, tname, _alias, _sql, plan in golden_cases()]
+    out += [(name, "testtbl.cst", plan, not plan.is_groupby) for name, _sql, plan in testtbl_queries()]
+    return out

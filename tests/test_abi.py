@@ -1,0 +1,150 @@
+"""The C-ABI library loads and exports every symbol include/evqgpu.h declares (no GPU needed).
+
+Also the device-free half of the product: plan intake, kernel text generation and NVRTC compilation
+for sm_100a of every kernel variant (evqgpu_debug_generate), and the "fails loudly" contract.
+"""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from eventql_b200 import capi, plan as P
+from tests import common as T
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "evqgpu.h")
+
+
+def header_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"EVQGPU_API\s+[^;(]*?\b(evqgpu_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_what_binding_lists():
+    assert header_symbols() == sorted(capi.SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol(native_lib):
+    for sym in header_symbols():
+        assert hasattr(native_lib, sym), sym
+    out = subprocess.run(["nm", "-D", "--defined-only", capi.LIB_PATH], stdout=subprocess.PIPE, text=True, check=True).stdout
+    exported = set(re.findall(r"\bT (evqgpu_[a-z0-9_]+)", out))
+    assert set(header_symbols()) <= exported
+    # nothing else leaks out of the library: the ABI is exactly the header
+    assert exported == set(header_symbols())
+
+
+def test_abi_version(native_lib):
+    m = re.search(r"#define EVQGPU_ABI_VERSION (\d+)", open(HEADER).read())
+    assert native_lib.evqgpu_abi_version() == int(m.group(1))
+
+
+def test_no_torch_types_in_header():
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)   # declarations only
+    assert "torch" not in text.lower() and "at::" not in text and "std::" not in text and "Tensor" not in text
+
+
+def test_function_registry_matches_plan_module(native_lib):
+    """Every symbol the plan module can resolve is known to the device path, with the same aggregate flag."""
+    missing = []
+    for name, sigs in P.REGISTRY.items():
+        for args, ret, _conv, agg in sigs:
+            sym = P.symbol(name, ret, args)
+            fid = native_lib.evqgpu_function_lookup(sym.encode())
+            if fid < 0:
+                missing.append(sym)
+                continue
+            assert native_lib.evqgpu_function_symbol(fid).decode() == sym
+            assert bool(native_lib.evqgpu_function_is_aggregate(fid)) == agg, sym
+    # string / pow / cmp helpers are not part of the numeric device path; everything the named configs need is
+    allowed_missing = {s for s in missing if s.split("#")[0] in ("cmp", "pow", "from_timestamp")}
+    assert set(missing) == allowed_missing, sorted(set(missing) - allowed_missing)
+    assert native_lib.evqgpu_function_lookup(b"no_such_fn#uint64/uint64;") == -1
+    assert native_lib.evqgpu_function_symbol(100000) is None
+
+
+def _cols(spec):
+    return [(T.sql_type_of(s), s["encoding"], 1 if s.get("null_every") else 0) for s in spec]
+
+
+@pytest.mark.parametrize("case", ["q6_leb", "q6_plain", "q1_dense", "q1_null", "hc_hash", "ts_hash", "scan_only_mixed"])
+def test_kernel_text_compiles_for_sm100a(native_lib, case):
+    """Codegen + NVRTC (--gpu-architecture=sm_100a) of every kernel tier, without a device."""
+    if case == "q6_leb":
+        spec = T.lineitem_spec()
+        _, plan = T.q6(spec)
+        tier, slots = 1, 1
+    elif case == "q6_plain":
+        spec = T.lineitem_spec(P.ENC_UINT64_PLAIN)
+        _, plan = T.q6(spec)
+        tier, slots = 1, 1
+    elif case == "q1_dense":
+        spec = T.lineitem_spec()
+        _, plan = T.q1(spec)
+        tier, slots = 1, 4
+    elif case == "q1_null":
+        spec = T.lineitem_spec(null_every=7)
+        _, plan = T.q1(spec)
+        tier, slots = 1, 9
+    elif case == "hc_hash":
+        spec = T.events_spec()
+        _, plan = T.q_highcard(spec)
+        tier, slots = 2, 0
+    elif case == "ts_hash":
+        spec = T.readings_spec(0)
+        _, plan = T.q_timeseries(spec)
+        tier, slots = 2, 0
+    else:
+        spec = T.mixed_spec()
+        c, names = T.cols_of(spec)
+        plan = P.QueryPlan(names, [c["a"], c["f"], c["bo"], c["c"] + c["d"]], where=c["b"] < 50, flags=0)
+        tier, slots = 0, 0
+    src, cubin_bytes = capi.debug_generate(plan, _cols(spec), tier=tier, dense_slots=slots, compile=True)
+    assert "evq_scan" in src and cubin_bytes > 1000
+    # the TMA bulk copy + mbarrier pipeline is part of every variant
+    assert "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes" in src
+
+
+def test_unsupported_plans_fail_loudly(native_lib):
+    spec = T.lineitem_spec()
+    c, names = T.cols_of(spec)
+    # string group key: outside the numeric device path -> EVQGPU_ERR_UNSUPPORTED, never a CPU fallback
+    plan = P.QueryPlan(names, [P.call("count", P.lit(1))], group=[P.lit("x")])
+    with pytest.raises(capi.EvqError) as ei:
+        capi.debug_generate(plan, _cols(spec), compile=False)
+    assert ei.value.status == 2
+    # aggregate in WHERE -> malformed plan
+    plan = P.QueryPlan(names, [P.call("count", P.lit(1))], where=P.call("sum", c["price"]) > 0)
+    with pytest.raises(capi.EvqError) as ei:
+        capi.debug_generate(plan, _cols(spec), compile=False)
+    assert ei.value.status == 1
+    # scalar select item that is not a function of the group key (reference: first row wins, non-deterministic)
+    plan = P.QueryPlan(names, [c["price"], P.call("count", P.lit(1))], group=[c["flag"]])
+    with pytest.raises(capi.EvqError):
+        capi.debug_generate(plan, _cols(spec), compile=False)
+
+
+def test_context_without_device_raises(native_lib):
+    """The product path has no host execution mode: no CUDA device -> hard error."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    with pytest.raises(capi.EvqError) as ei:
+        capi.Context(0)
+    assert ei.value.status == 3
+    assert "no CUDA device" in ei.value.message
+
+
+def test_product_never_imports_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/."""
+    pkg = os.path.join(ROOT, "eventql_b200")
+    for dirpath, _dirs, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cc", ".cu", ".h", ".cuh")) and "_build" not in dirpath:
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "import oracle" not in text and "from oracle" not in text and "oracle/" not in text.replace(
+                    "oracle/ref_tools/ext_aggregates.cc", ""), os.path.join(dirpath, f)
+    assert "oracle" not in open(HEADER).read().replace("oracle/ref_tools/ext_aggregates.cc", "")

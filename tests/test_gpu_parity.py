@@ -1,0 +1,344 @@
+"""Parity of the CUDA path (through the C ABI, include/evqgpu.h) with the reference - runs on the B200 box.
+
+  * every golden case: CUDA result == rows the unmodified reference engine returned (tests/golden/ref_results.json)
+    and == the CPU oracle on the same table
+  * column decode of every encoding, bit for bit in the packed SVector layout (FastCSTableScan::fetchColumn*)
+  * ragged sizes around the 128-value block and 1024-row tile boundaries, empty tables, partitions
+  * BASELINE.json's full sizes through size-independent properties (partition additivity, closed forms, idempotence)
+
+Tolerances: integers, counts, min/max, group keys, NULL tags: bit-exact.  float64 sum/mean: 1e-9 relative
+(BASELINE.json north_star; summation order differs).
+"""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+from eventql_b200 import capi, plan as P
+from oracle import evq_oracle as O
+from tests import common as T
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(T.ROOT, "tests", "golden")
+
+
+def run_gpu(ctx, tables, plan):
+    q = ctx.query(plan)
+    try:
+        q.execute(tables)
+        return q.rows(), q.stats()
+    finally:
+        q.close()
+
+
+def compare(got, want, ordered):
+    if ordered:
+        assert len(got) == len(want)
+        for i, (a, b) in enumerate(zip(got, want)):
+            ok, why = T.rows_equal([a], [b])
+            assert ok, "row %d: %s" % (i, why)
+    else:
+        ok, why = T.rows_equal(got, want)
+        assert ok, why
+
+
+_CASES = T.all_golden_cases()
+
+
+@pytest.mark.parametrize("case,tname,plan,ordered", _CASES, ids=[c[0] for c in _CASES])
+def test_cuda_equals_reference_engine(gpu_ctx, case, tname, plan, ordered):
+    path = T.golden_table_path(tname)
+    tbl = gpu_ctx.open_table_file(path)
+    g = T.golden()[case]
+    try:
+        if "error" in g:
+            with pytest.raises(capi.EvqError) as ei:
+                run_gpu(gpu_ctx, [tbl], plan)
+            assert ei.value.status == 4 and g["error"] in ei.value.message
+            return
+        got, stats = run_gpu(gpu_ctx, [tbl], plan)
+        T.check_against_golden(case, got, ordered)
+        res = O.run_query([O.read_cstable(path)], plan)
+        compare(got, res.rows(), ordered)
+        assert stats["rows_scanned"] == res.rows_scanned and stats["rows_passed"] == res.rows_passed
+        assert stats["kernel_launches"] >= 1
+    finally:
+        tbl.close()
+
+
+def _decode_parity(ctx, tbl, f, names):
+    for name in names:
+        d = O.decode_column(f, name)
+        st = d.sql_type
+        vals = d.values.view(np.float64) if st == P.FLOAT64 else (d.values.astype(bool) if st == P.BOOL else d.values)
+        want = O.pack_svector(O.Vec(st, vals, np.where(d.present, 0, 1).astype(np.uint8)))
+        got = tbl.decode_column(name)
+        assert got == want, "column %s" % name
+
+
+@pytest.mark.parametrize("ver", ["v1", "v2"])
+def test_decode_reference_written_files(gpu_ctx, ver):
+    """Tables written by the reference's CSTableWriter, both file format versions, every numeric encoding."""
+    raw = np.frombuffer(gzip.open(os.path.join(GOLD, "ref_mixed_%s.cst.gz" % ver)).read(), dtype=np.uint8).copy()
+    tbl = gpu_ctx.open_table(raw)
+    f = O.parse_cstable(raw.tobytes())
+    assert tbl.num_rows == 3000
+    _decode_parity(gpu_ctx, tbl, f, [s["name"] for s in T.mixed_spec()])
+    tbl.close()
+
+
+@pytest.mark.parametrize("nrows", [0, 1, 127, 128, 129, 1023, 1024, 1025, 4096, 70001])
+def test_decode_and_aggregate_ragged_sizes(gpu_ctx, nrows, tmp_path):
+    spec = T.mixed_spec(null_every=3)
+    path = str(tmp_path / "m.cst")
+    T.write_table(path, spec, nrows)
+    tbl = gpu_ctx.open_table_file(path)
+    f = O.read_cstable(path)
+    assert tbl.num_rows == nrows
+    if nrows:
+        _decode_parity(gpu_ctx, tbl, f, [s["name"] for s in spec])
+    for name, _sql, plan in T.semantic_queries(spec):
+        if name == "div_zero" and nrows > 100:
+            continue
+        got, _ = run_gpu(gpu_ctx, [tbl], plan)
+        compare(got, O.run_query([f], plan).rows(), not plan.is_groupby)
+    tbl.close()
+
+
+def test_testtbl_v010_fixture_through_cuda(gpu_ctx):
+    """C1: the reference's fixture (v0.1.0) + its golden file test/sql/00001 through the CUDA decode path."""
+    tbl = gpu_ctx.open_table_file(os.path.join(GOLD, "testtbl.cst"))
+    lines = open(os.path.join(GOLD, "sql_00001.result.txt")).read().split("\n")
+    times = [int(x) for x in lines[1:] if x.strip()]
+    got, _ = run_gpu(gpu_ctx, [tbl], P.QueryPlan(["time"], [P.Col(0, P.UINT64)], flags=0))
+    assert [r[0] for r in got] == times
+    got, _ = run_gpu(gpu_ctx, [tbl], P.QueryPlan(["time"], [P.call("count", P.lit(1))]))
+    assert got == [(213,)]
+    tbl.close()
+
+
+def test_partitions_are_scanned_as_one_table(gpu_ctx, tmp_path):
+    """PartitionCursor semantics: a scan over several segment files is the concatenation of the scans."""
+    spec = T.lineitem_spec(null_every=5)
+    sizes = [10_000, 1, 2_047, 33_333]
+    tables, files, off = [], [], 0
+    for i, n in enumerate(sizes):
+        p = str(tmp_path / ("p%d.cst" % i))
+        T.write_table(p, spec, n, row_offset=off)
+        off += n
+        tables.append(gpu_ctx.open_table_file(p))
+        files.append(O.read_cstable(p))
+    for qf in (T.q1, T.q6):
+        _sql, plan = qf(spec)
+        got, stats = run_gpu(gpu_ctx, tables, plan)
+        compare(got, O.run_query(files, plan).rows(), False)
+        assert stats["rows_scanned"] == sum(sizes)
+    # scan-only plans keep table order across partitions
+    c, names = T.cols_of(spec)
+    plan = P.QueryPlan(names, [c["price"], c["shipdate"]], where=c["quantity"] < 3, flags=0)
+    got, _ = run_gpu(gpu_ctx, tables, plan)
+    compare(got, O.run_query(files, plan).rows(), True)
+    for t in tables:
+        t.close()
+
+
+def test_device_generator_matches_numpy(gpu_ctx):
+    """The synthetic tables of bench.py are generated on the device; pin the generator to tests/common.py:synth_values
+    (same splitmix64 definition) through the CUDA decode path, for every encoding, with a row offset."""
+    spec = T.mixed_spec(null_every=7)
+    n, off = 50_000, 123_457
+    tbl = gpu_ctx.synthesize(n, [s for s in spec if not (s["encoding"] == P.ENC_UINT32_BITPACKED and s.get("null_every"))], row_offset=off)
+    for s in spec:
+        want, nulls = T.synth_values(s, n, row_offset=off)
+        if s["encoding"] in (P.ENC_UINT32_BITPACKED, P.ENC_UINT32_PLAIN):
+            want = want & np.uint64(0xFFFFFFFF)
+        st = T.sql_type_of(s)
+        vals = want.view(np.float64) if st == P.FLOAT64 else (want.astype(bool) if st == P.BOOL else want)
+        packed = O.pack_svector(O.Vec(st, vals, nulls.astype(np.uint8)))
+        assert tbl.decode_column(s["name"]) == packed, s["name"]
+    tbl.close()
+
+
+def test_device_written_file_is_read_by_the_oracle(gpu_ctx, tmp_path):
+    """evqgpu_table_write_file produces a v0.2.0 cstable the reference format reader (oracle restatement) accepts."""
+    spec = [s for s in T.mixed_spec(null_every=7) if not (s["encoding"] == P.ENC_UINT32_BITPACKED and s.get("null_every"))]
+    n = 200_000
+    tbl = gpu_ctx.synthesize(n, spec)
+    p = str(tmp_path / "dev.cst")
+    tbl.write_file(p)
+    f = O.read_cstable(p)
+    assert f.num_rows == n
+    for s in spec:
+        want, nulls = T.synth_values(s, n)
+        d = O.decode_column(f, s["name"])
+        assert np.array_equal(d.present, ~nulls), s["name"]
+        got = d.values.view(np.uint64) if d.values.dtype == np.float64 else d.values.astype(np.uint64)
+        if s["encoding"] in (P.ENC_UINT32_BITPACKED, P.ENC_UINT32_PLAIN):
+            want = want & np.uint64(0xFFFFFFFF)
+        assert np.array_equal(got[~nulls], want[~nulls]), s["name"]
+    tbl.close()
+
+
+def test_group_table_grows_when_the_hint_is_too_small(gpu_ctx):
+    spec = T.events_spec(200_000)
+    n = 400_000
+    tbl = gpu_ctx.synthesize(n, spec)
+    _sql, plan = T.q_highcard(spec, expected_groups=100)       # 100 -> table of 1024 slots, needs ~180 K
+    got, stats = run_gpu(gpu_ctx, [tbl], plan)
+    key, nulls = T.synth_values(spec[0], n)
+    v, _ = T.synth_values(spec[1], n)
+    uk, inv = np.unique(key, return_inverse=True)
+    cnt = np.bincount(inv)
+    sm = np.bincount(inv, weights=v.astype(np.float64)).astype(np.uint64)
+    want = [(int(k), int(c), int(s), float(s) / int(c)) for k, c, s in zip(uk.tolist(), cnt.tolist(), sm.tolist())]
+    compare(got, want, False)
+    assert stats["strategy"] == 2 and stats["num_groups"] == len(uk)
+    tbl.close()
+
+
+def test_errors_are_loud(gpu_ctx, tmp_path):
+    spec = T.lineitem_spec()
+    tbl = gpu_ctx.synthesize(1000, spec)
+    c, names = T.cols_of(spec)
+    with pytest.raises(capi.EvqError) as ei:      # unknown column
+        run_gpu(gpu_ctx, [tbl], P.QueryPlan(["nope"], [P.call("count", P.lit(1))], where=P.Col(0, P.UINT64) > 0))
+    assert ei.value.status == 1
+    with pytest.raises(capi.EvqError) as ei:      # modulo by zero raises like math.cc:176-216
+        run_gpu(gpu_ctx, [tbl], P.QueryPlan(names, [P.call("sum", c["price"] % c["flag"])], where=c["price"] > 0))
+    assert ei.value.status == 4 and "modulo by zero" in ei.value.message
+    with pytest.raises(capi.EvqError):            # not a cstable
+        gpu_ctx.open_table(np.zeros(1000, dtype=np.uint8))
+    tbl.close()
+    # string columns are outside the numeric device path: loud, not silently skipped
+    t2 = gpu_ctx.open_table_file(os.path.join(GOLD, "testtbl.cst"))
+    with pytest.raises(capi.EvqError) as ei:
+        t2.load(["session_id"])
+    assert ei.value.status == 2
+    t2.close()
+
+
+# ---- BASELINE.json sizes: size-independent properties ------------------------------------------------------------------
+
+def _merge_partials(rows_list, plan):
+    """Merge per-partition results of a count/sum plan by key (GroupByMergeExpression semantics, groupby.cc:577-612)."""
+    nk = len(plan.group)
+    acc = {}
+    for rows in rows_list:
+        for r in rows:
+            k = r[:nk]
+            if k not in acc:
+                acc[k] = list(r[nk:])
+            else:
+                acc[k] = [a + b for a, b in zip(acc[k], r[nk:])]
+    return [k + tuple(v) for k, v in acc.items()]
+
+
+def test_q6_100m_rows_properties(gpu_ctx):
+    """C2: 100 M-row lineitem, Q6.  (a) whole table == sum over 4 partitions generated with row offsets,
+    (b) a closed-form column, (c) idempotence, (d) the first 2 M rows against the oracle."""
+    spec = T.lineitem_spec()
+    n = 100_000_000
+    _sql, plan = T.q6(spec)
+    whole = gpu_ctx.synthesize(n, spec)
+    got, stats = run_gpu(gpu_ctx, [whole], plan)
+    assert stats["rows_scanned"] == n and len(got) == 1
+    again, _ = run_gpu(gpu_ctx, [whole], plan)
+    assert again == got
+    whole.close()
+    parts = [gpu_ctx.synthesize(n // 4, spec, row_offset=i * (n // 4)) for i in range(4)]
+    per = [run_gpu(gpu_ctx, [p], plan)[0] for p in parts]
+    assert _merge_partials(per, plan) == got
+    allp, _ = run_gpu(gpu_ctx, parts, plan)
+    assert allp == got
+    for p in parts:
+        p.close()
+    # selectivity of the synthetic Q6 is 1.81 % by construction
+    assert abs(got[0][0] / n - 0.0181) < 0.001
+    m = 2_000_000
+    inputs = [O.Vec(P.UINT64, T.synth_values(s, m)[0], np.zeros(m, dtype=np.uint8)) for s in spec]
+    small = gpu_ctx.synthesize(m, spec)
+    got_small, _ = run_gpu(gpu_ctx, [small], plan)
+    assert got_small == O.run_query_on(inputs, m, plan).rows()
+    small.close()
+
+
+def test_q1_250m_rows_properties(gpu_ctx):
+    """C3 shape (Q1, 4 groups, 8 aggregates + 3 means): two 125 M-row partitions as in the 8-file layout."""
+    spec = T.lineitem_spec()
+    n = 125_000_000
+    _sql, plan = T.q1(spec)
+    _sql, plan_int = T.q1(spec, means=False)
+    parts = [gpu_ctx.synthesize(n, spec, row_offset=i * n) for i in range(2)]
+    both, stats = run_gpu(gpu_ctx, parts, plan_int)
+    assert stats["rows_scanned"] == 2 * n and stats["strategy"] == 1 and len(both) == 4
+    per = [run_gpu(gpu_ctx, [p], plan_int)[0] for p in parts]
+    compare(_merge_partials(per, plan_int), both, False)
+    # every row passes the Q1 predicate by construction: counts add up to the table size; sum(discount) etc. are
+    # bounded by their value ranges
+    assert sum(r[2] for r in both) == 2 * n
+    for r in both:
+        assert r[2] * 1 <= r[3] <= r[2] * 50 and r[2] * 90000 <= r[4] <= r[2] * 10089999
+    # means == sum / count of the same run (1e-9)
+    full, _ = run_gpu(gpu_ctx, parts, plan)
+    for r in full:
+        assert abs(r[8] - r[3] / r[2]) <= 1e-9 * r[8] and abs(r[9] - r[4] / r[2]) <= 1e-9 * r[9]
+    for p in parts:
+        p.close()
+    m = 3_000_000
+    inputs = [O.Vec(P.UINT64, T.synth_values(s, m)[0], np.zeros(m, dtype=np.uint8)) for s in spec]
+    small = gpu_ctx.synthesize(m, spec)
+    compare(run_gpu(gpu_ctx, [small], plan)[0], O.run_query_on(inputs, m, plan).rows(), False)
+    small.close()
+
+
+def test_highcard_10m_keys_properties(gpu_ctx):
+    """C4 shape: 10 M distinct full-range u64 keys over 100 M rows (hash tier): counts add up, keys are distinct,
+    every key is splitmix64 of a value below 10 M, partition merge == whole."""
+    spec = T.events_spec(10_000_000)
+    n = 100_000_000
+    c, names = T.cols_of(spec)
+    plan = P.QueryPlan(names, [c["ekey"], P.call("count", P.lit(1)), P.call("sum", c["v"])], where=c["v"] >= 0,
+                       group=[c["ekey"]], expected_groups=10_000_000)
+    tbl = gpu_ctx.synthesize(n, spec)
+    q = gpu_ctx.query(plan)
+    q.execute([tbl])
+    cols = q.fetch_packed()
+    stats = q.stats()
+    q.close()
+    ng = len(cols[0]) // 9
+    keys = np.ascontiguousarray(np.frombuffer(cols[0], dtype=np.uint8).reshape(ng, 9)[:, :8]).view("<u8").reshape(ng)
+    cnt = np.ascontiguousarray(np.frombuffer(cols[1], dtype=np.uint8).reshape(ng, 9)[:, :8]).view("<u8").reshape(ng)
+    sm = np.ascontiguousarray(np.frombuffer(cols[2], dtype=np.uint8).reshape(ng, 9)[:, :8]).view("<u8").reshape(ng)
+    assert stats["strategy"] == 2
+    assert int(cnt.sum()) == n and len(np.unique(keys)) == ng
+    assert 9_990_000 < ng <= 10_000_000          # 100 M draws cover all but ~450 of the 10 M keys
+    assert np.isin(keys[:100000], T.splitmix64(np.arange(10_000_000, dtype=np.uint64))).all()
+    # total of sums == sum of the v column, which the Q6-style global aggregate computes independently
+    tot, _ = run_gpu(gpu_ctx, [tbl], P.QueryPlan(names, [P.call("sum", c["v"])], where=c["v"] >= 0))
+    assert int(sm.sum()) == tot[0][0]
+    tbl.close()
+    m = 2_000_000
+    small_spec = T.events_spec(100_000)
+    small = gpu_ctx.synthesize(m, small_spec)
+    _sql, p2 = T.q_highcard(small_spec)
+    inputs = [O.Vec(P.UINT64, T.synth_values(s, m)[0], np.zeros(m, dtype=np.uint8)) for s in small_spec]
+    compare(run_gpu(gpu_ctx, [small], p2)[0], O.run_query_on(inputs, m, p2).rows(), False)
+    small.close()
+
+
+def test_timeseries_partition_properties(gpu_ctx):
+    """C5 shape: 1-minute buckets x 1 K sensors; partitions of different days have disjoint groups (merge = concatenation)."""
+    n = 20_000_000
+    parts = [gpu_ctx.synthesize(n, T.readings_spec(d)) for d in range(2)]
+    _sql, plan = T.q_timeseries(T.readings_spec(0), expected_groups=1_440_000)
+    per = [run_gpu(gpu_ctx, [p], plan)[0] for p in parts]
+    both, stats = run_gpu(gpu_ctx, parts, plan)
+    assert stats["strategy"] == 2
+    assert len(both) == len(per[0]) + len(per[1])
+    assert sorted(both) == sorted(per[0] + per[1])
+    assert sum(r[2] for r in both) == 2 * n
+    day0 = 1_438_041_600_000_000 // 60_000_000
+    assert all(day0 <= r[0] < day0 + 1440 for r in per[0]) and all(day0 + 1440 <= r[0] < day0 + 2880 for r in per[1])
+    for p in parts:
+        p.close()
