@@ -355,12 +355,17 @@ def evq_arm(args):
     value = total_rows * args.steps / (ms / 1000.0)
     algo_bytes_rank = stats["algorithmic_bytes"]
 
-    # correctness guard inside the bench: every row passes Q1's predicate, so the counts must add up to the table size
+    # correctness guard inside the bench: the per-group counts must add up to the rows that passed WHERE on all ranks
+    # (96.4 % of the rows pass Q1's shipdate predicate by construction)
     if args.workload == "c3_q1":
         cnt = sum(r[2] for r in result_rows)
-        expect = total_rows
-        if cnt != expect:
-            raise RuntimeError("bench: count(1) over all groups is %d, expected %d" % (cnt, expect))
+        passed = stats["rows_passed"]
+        if world > 1:
+            t = torch.tensor([passed], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t)
+            passed = int(t.item())
+        if cnt != passed or abs(cnt / total_rows - 2436 / 2526) > 1e-3:
+            raise RuntimeError("bench: count(1) over all groups is %d, rows passed %d of %d" % (cnt, passed, total_rows))
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):

@@ -38,13 +38,24 @@ static const char* col_ctype(uint32_t sql_type) {
   }
 }
 
+// C type a column is carried in by the fast kernel
+static const char* fast_ctype(const ColSig& c) {
+  if (c.sql_type == EVQ_FLOAT64) return "f64";
+  if (c.sql_type == EVQ_BOOL) return "u32";
+  if (c.bits <= 32) return "u32";
+  return c.sql_type == EVQ_INT64 ? "i64" : "u64";
+}
+
 static CodegenEnv row_env(const KernelShape& shape) {
   CodegenEnv env;
   env.col_value.resize(shape.cols.size());
   env.col_tag.resize(shape.cols.size());
   for (size_t i = 0; i < shape.cols.size(); ++i) {
     if (!shape.cols[i].used) continue;
-    env.col_value[i] = "row.c" + std::to_string(i);
+    // columns carried as u32 (values known to fit) are widened at every use: the query's arithmetic stays 64-bit, the
+    // compiler narrows what the known-zero upper halves allow
+    const bool widen = shape.fast && fast_ctype(shape.cols[i]) == std::string("u32") && shape.cols[i].sql_type != EVQ_BOOL;
+    env.col_value[i] = widen ? "((u64) row.c" + std::to_string(i) + ")" : "row.c" + std::to_string(i);
     env.col_tag[i] = shape.cols[i].nullable ? "row.t" + std::to_string(i) : std::string("0u");
   }
   return env;
@@ -90,8 +101,7 @@ static void gen_updates(std::ostringstream& os, const evqgpu_query& q, const Ker
   }
 }
 
-static std::string gen_row_functions(const evqgpu_query& q, const KernelShape& shape) {
-  std::ostringstream os;
+static void gen_general_layout(std::ostringstream& os, const KernelShape& shape) {
   const size_t ncols = shape.cols.size();
   // ---- row + prep structs
   os << "struct EvqRow {\n";
@@ -170,6 +180,95 @@ static std::string gen_row_functions(const evqgpu_query& q, const KernelShape& s
     os << "  }\n";
   }
   os << "}\n";
+
+}
+
+// fast kernel (kernels/evq_scan_fast.cuh): structs + cooperative boundary search + per-thread decode of 4 consecutive rows
+static void gen_fast_layout(std::ostringstream& os, const KernelShape& shape) {
+  const size_t ncols = shape.cols.size();
+  os << "struct EvqRow {\n";
+  for (size_t i = 0; i < ncols; ++i)
+    if (shape.cols[i].used) os << "  " << fast_ctype(shape.cols[i]) << " c" << i << ";\n";
+  os << "  u32 _unused;\n};\n";
+  os << "struct EvqCols {\n";
+  for (size_t i = 0; i < ncols; ++i)
+    if (shape.cols[i].used) os << "  " << fast_ctype(shape.cols[i]) << " c" << i << "[EVQ_RPT];\n";
+  os << "  u32 _unused;\n};\n";
+  const int ngen = std::max(1, shape.ngen);
+  os << "struct EvqFastPrep {\n  bool general[" << ngen << "];\n  u32 count[" << ngen << "];\n  u32 incl[" << ngen << "];\n};\n";
+
+  // ---- boundary search of the variable-length columns: 2 consumer barriers per tile, only when a tile needs them
+  os << "__device__ __forceinline__ void evq_fast_prep(const EvqTile& T, const EvqScanParams& P, EvqFastScratch* scr, EvqFastPrep& prep) {\n";
+  if (shape.ngen > 0) {
+    os << "  bool any = false;\n";
+    for (size_t i = 0; i < ncols; ++i) {
+      const ColSig& c = shape.cols[i];
+      if (!c.used || c.gen_slot < 0) continue;
+      os << "  evq_fast_count<" << c.data_stream << ", " << c.leb_len << ">(T, P, prep.general[" << c.gen_slot << "], prep.count["
+         << c.gen_slot << "]);\n  any = any || prep.general[" << c.gen_slot << "];\n";
+    }
+    os << "  if (any) {\n";
+    for (size_t i = 0; i < ncols; ++i) {
+      const ColSig& c = shape.cols[i];
+      if (!c.used || c.gen_slot < 0) continue;
+      os << "    if (prep.general[" << c.gen_slot << "]) prep.incl[" << c.gen_slot << "] = evq_fast_publish<" << c.gen_slot
+         << ">(T, scr, prep.count[" << c.gen_slot << "]);\n";
+    }
+    os << "    evq_cons_sync();\n";
+    for (size_t i = 0; i < ncols; ++i) {
+      const ColSig& c = shape.cols[i];
+      if (!c.used || c.gen_slot < 0) continue;
+      os << "    if (prep.general[" << c.gen_slot << "]) evq_fast_write_starts<" << c.data_stream << ", " << c.gen_slot
+         << ">(T, P, scr, prep.count[" << c.gen_slot << "], prep.incl[" << c.gen_slot << "]);\n";
+    }
+    os << "    evq_cons_sync();\n  }\n";
+  }
+  os << "}\n";
+
+  // ---- FastCSTableScan::fetchColumn* (sql/CSTableScan.cc:860-968) for the thread's 4 rows
+  os << "__device__ __forceinline__ void evq_fast_decode(const EvqTile& T, const EvqScanParams& P, const EvqFastScratch* scr, const EvqFastPrep& prep, EvqCols& cols) {\n";
+  for (size_t i = 0; i < ncols; ++i) {
+    const ColSig& c = shape.cols[i];
+    if (!c.used) continue;
+    const std::string S = std::to_string(c.data_stream);
+    const std::string ct = fast_ctype(c);
+    const bool narrow = ct == "u32";
+    const std::string raw_t = (c.kind == EVQ_KIND_PLAIN64 && !(narrow && c.sql_type != EVQ_BOOL && c.sql_type != EVQ_FLOAT64)) || (c.kind == EVQ_KIND_LEB128 && c.leb_len > 4) ? "u64" : "u32";
+    os << "  {\n    " << raw_t << " raw[EVQ_RPT];\n";
+    switch (c.kind) {
+      case EVQ_KIND_PLAIN64:
+        if (raw_t == "u32") os << "    evq_fast_ld_plain64_lo<" << S << ">(T, P, raw);\n";
+        else os << "    evq_fast_ld_plain64<" << S << ">(T, P, raw);\n";
+        break;
+      case EVQ_KIND_PLAIN32: os << "    evq_fast_ld_plain32<" << S << ">(T, P, raw);\n"; break;
+      case EVQ_KIND_BITPACK: os << "    evq_fast_ld_bitpack<" << S << ">(T, P, raw);\n"; break;
+      default:
+        if (c.leb_len <= 1) os << "    evq_fast_ld_leb1<" << S << ">(T, P, raw);\n";
+        else if (c.leb_len <= 4)
+          os << "    evq_fast_ld_leb32<" << S << ", " << c.gen_slot << ", " << c.leb_len << ">(T, P, scr, prep.general[" << c.gen_slot << "], raw);\n";
+        else
+          os << "    evq_fast_ld_leb64<" << S << ", " << c.gen_slot << ", " << c.leb_len << ">(T, P, scr, prep.general[" << c.gen_slot << "], raw);\n";
+        break;
+    }
+    std::string conv;
+    switch (c.sql_type) {
+      case EVQ_FLOAT64: conv = "evq_f64(raw[k])"; break;
+      case EVQ_BOOL: conv = "(u32) (raw[k] > 0)"; break;   // column_reader_uint.cc:76-90: readBoolean = value > 0
+      default: conv = std::string("(") + ct + ") raw[k]"; break;
+    }
+    os << "#pragma unroll\n    for (int k = 0; k < EVQ_RPT; ++k) cols.c" << i << "[k] = " << conv << ";\n  }\n";
+  }
+  os << "}\n";
+  os << "__device__ __forceinline__ void evq_fast_row(const EvqCols& cols, int k, EvqRow& row) {\n";
+  for (size_t i = 0; i < ncols; ++i)
+    if (shape.cols[i].used) os << "  row.c" << i << " = cols.c" << i << "[k];\n";
+  os << "}\n";
+}
+
+static std::string gen_row_functions(const evqgpu_query& q, const KernelShape& shape) {
+  std::ostringstream os;
+  if (shape.fast) gen_fast_layout(os, shape);
+  else gen_general_layout(os, shape);
 
   // ---- WHERE
   CodegenEnv env = row_env(shape);
@@ -348,9 +447,10 @@ std::string generate_source(const evqgpu_query& q, const KernelShape& shape) {
      << shape.nstreams << "\n#define EVQ_TIER " << shape.tier << "\n#define EVQ_G1 " << shape.g1 << "\n#define EVQ_NSTATE "
      << std::max<size_t>(1, q.state_ops.size()) << "\n#define EVQ_NKEYS " << q.group.size() << "\n#define EVQ_NLEB "
      << shape.nleb << "\n#define EVQ_NNULL " << shape.nnull << "\n#define EVQ_HAS_PREP "
-     << ((shape.nleb > 0 || shape.nnull > 0) ? 1 : 0) << "\n#define EVQ_MIN_CTAS " << shape.min_ctas << "\n";
+     << ((shape.nleb > 0 || shape.nnull > 0) ? 1 : 0) << "\n#define EVQ_MIN_CTAS " << shape.min_ctas << "\n#define EVQ_NGEN "
+     << shape.ngen << "\n";
   os << kSrcAbi << "\n" << kSrcPrelude << "\n";
-  const std::string kern = kSrcScanKernel;
+  const std::string kern = shape.fast ? kSrcScanFast : kSrcScanKernel;
   const std::string marker = "//@@EVQ_GENERATED@@";
   const size_t pos = kern.find(marker);
   if (pos == std::string::npos) fail(EVQGPU_ERR_RUNTIME, "kernel text lacks the generated-code marker");

@@ -31,9 +31,16 @@ extern "C" int evqgpu_debug_generate(const evqgpu_query_desc* desc, const evqgpu
       }
       cs.nullable = columns[i].dlevel_max > 0;
       cs.dmax = columns[i].dlevel_max;
+      cs.bits = columns[i].value_bits ? columns[i].value_bits : 64;
+      cs.leb_len = columns[i].leb_max_len ? columns[i].leb_max_len : 10;
       cs.data_stream = s.nstreams++;
       if (cs.nullable) { cs.level_stream = s.nstreams++; cs.null_slot = s.nnull++; }
       if (cs.kind == EVQ_KIND_LEB128) cs.leb_slot = s.nleb++;
+    }
+    s.fast = s.nnull == 0;
+    for (auto& c : s.cols) {
+      c.gen_slot = -1;
+      if (s.fast && c.used && c.kind == EVQ_KIND_LEB128 && c.leb_len >= 2) c.gen_slot = s.ngen++;
     }
     const bool groupby = q.flags & EVQGPU_QUERY_GROUPBY;
     std::vector<int> tiers;

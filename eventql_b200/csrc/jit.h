@@ -30,5 +30,6 @@ std::vector<char> jit_compile_to_cubin(const std::string& source, std::string* l
 extern const char* const kSrcAbi;
 extern const char* const kSrcPrelude;
 extern const char* const kSrcScanKernel;
+extern const char* const kSrcScanFast;
 
 }  // namespace evq

@@ -222,6 +222,23 @@ __device__ __forceinline__ u32 evq_term_mask16(uint4 c) {
   return m;
 }
 
+// terminator mask of 16-byte chunk c of a stage region whose payload is bytes [delta, tb)
+__device__ __forceinline__ u32 evq_leb_chunk_mask(const u8* region, u32 c, u32 delta, u32 tb) {
+  const uint4 q = *(const uint4*) (region + 16u * c);
+  u32 m = evq_term_mask16(q);
+  const u32 pos = 16u * c;
+  if (pos < delta) m &= ~((1u << (delta - pos)) - 1u);
+  if (tb - pos < 16u) m &= (1u << (tb - pos)) - 1u;
+  return m;
+}
+
+// 4 bytes at an arbitrary shared-memory byte offset (regions are padded, over-read is safe)
+__device__ __forceinline__ u32 evq_lds_unaligned32(const u8* p) {
+  const u32 a = evq_smem_u32(p);
+  const u32* w = (const u32*) (p - (a & 3u));
+  return __funnelshift_r(w[0], w[1], (a & 3u) * 8u);
+}
+
 // terminator bit pattern of a run of w-byte values: bit k set iff k % w == w-1
 __device__ __forceinline__ u64 evq_uniform_pattern(u32 w) {
   switch (w) {

@@ -1,0 +1,418 @@
+// evq_scan_fast.cuh - the fused decode + WHERE + GROUP BY kernel for tables whose referenced columns are all
+// required (no definition levels): the layout production cstables have.  Optional columns take the
+// general kernel of evq_scan_kernel.cuh.
+//
+// Same operator fusion as the general kernel (FastCSTableScan::nextBatch, sql/CSTableScan.cc:757-858 +
+// VM::evaluatePredicateVector, sql/runtime/vm.cc:231-272 + GroupByExpression::execute,
+// sql/statements/select/groupby.cc:69-185) and the same producer warp / TMA bulk-copy pipeline; what differs is the
+// work assignment of the consumer threads, chosen so that the decode is a few straight-line instructions per value:
+//
+//   * thread t owns the EVQ_RPT = 4 CONSECUTIVE rows 4t..4t+3 of the 1024-row tile.  A 1-byte LEB128 column is then one
+//     32-bit shared-memory load per thread, a plain column one vector load, and a variable-length LEB128 column a
+//     sequential decode of 4 values from one known byte offset.
+//   * the longest value of every LEB128 column (Column::leb_max_len, a statistic computed when the column is loaded)
+//     is a compile-time constant L of the specialised kernel: L == 1 needs no boundary search at all; L <= 4 decodes
+//     from a 32-bit window; a tile with nbytes == L * nvals holds only L-byte values (uniform fast path, decided from the
+//     tile descriptor alone).  Otherwise the consumers locate the start of every 4th value with one popcount scan
+//     (2 consumer barriers per tile, shared by all such columns).
+//   * columns whose values are known to fit 32 bits are carried as u32, so the compiler narrows the query's
+//     comparisons and multiplications (64-bit results are formed where the expression needs them).
+//
+// The generated part (csrc/codegen.cc) defines:
+//   EVQ_NCONS EVQ_NSTAGES EVQ_NSTREAMS EVQ_TIER EVQ_G1 EVQ_NSTATE EVQ_NKEYS EVQ_NGEN EVQ_MIN_CTAS
+//   struct EvqRow; struct EvqCols; struct EvqFastPrep;
+//   evq_fast_prep      cooperative boundary search of the variable-length columns of the tile
+//   evq_fast_decode    decode the thread's 4 rows of every referenced column into registers
+//   evq_fast_row       pick row k out of EvqCols
+//   evq_where / evq_keys / evq_accumulate_* / evq_state_* / evq_project   as in the general kernel
+
+#define EVQ_NWARPS (EVQ_NCONS / 32)
+#define EVQ_RPT 4
+#define EVQ_NTHREADS (EVQ_NCONS + 32)
+
+struct EvqFastScratch {
+  u32 wtot[EVQ_NGEN > 0 ? EVQ_NGEN : 1][EVQ_NWARPS];   // per-warp terminator counts of the boundary scan
+  u16 start[EVQ_NGEN > 0 ? EVQ_NGEN : 1][EVQ_NCONS];   // byte offset (from the payload start) of value 4t
+  u32 scan[EVQ_NWARPS];                                // scan-only plans: pass counts per warp
+};
+
+// ---- boundary search of a variable-length LEB128 column ------------------------------------------------------------------
+
+// A tile is uniform when all its values have the column's maximal length L; otherwise count this thread's terminators.
+template <int S, int L>
+__device__ __forceinline__ void evq_fast_count(const EvqTile& T, const EvqScanParams& P, bool& general, u32& count) {
+  const EvqStreamDesc d = T.desc[S];
+  general = d.nbytes != (u32) L * d.nvals;   // the same for every thread of the CTA
+  count = 0;
+  if (!general) return;
+  const u8* region = T.stage + P.streams[S].smem_off;
+  const u32 tb = d.delta + d.nbytes;
+  const u32 nchunks = (tb + 15u) >> 4;
+  const u32 per = (nchunks + EVQ_NCONS - 1) / EVQ_NCONS;
+  const u32 c0 = T.ctid * per;
+  const u32 c1 = c0 + per < nchunks ? c0 + per : nchunks;
+  for (u32 c = c0; c < c1; ++c) count += __popc(evq_leb_chunk_mask(region, c, d.delta, tb));
+}
+
+// inclusive warp scan of the counts; the warp totals go to shared memory (read after the next consumer barrier)
+template <int G>
+__device__ __forceinline__ u32 evq_fast_publish(const EvqTile& T, EvqFastScratch* scr, u32 count) {
+  const u32 lane = evq_lane();
+  u32 incl = count;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const u32 n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (u32) o) incl += n;
+  }
+  if (lane == 31) scr->wtot[G][T.ctid >> 5] = incl;
+  return incl;
+}
+
+// terminator number j ends value j: every terminator with j % 4 == 3 marks the start of value j + 1 = 4 * ((j + 1) / 4)
+template <int S, int G>
+__device__ __forceinline__ void evq_fast_write_starts(const EvqTile& T, const EvqScanParams& P, EvqFastScratch* scr, u32 count,
+                                                      u32 incl) {
+  const u32 warp = T.ctid >> 5;
+  u32 j = incl - count;
+  for (u32 w = 0; w < warp; ++w) j += scr->wtot[G][w];
+  const EvqStreamDesc d = T.desc[S];
+  const u8* region = T.stage + P.streams[S].smem_off;
+  const u32 tb = d.delta + d.nbytes;
+  const u32 nchunks = (tb + 15u) >> 4;
+  const u32 per = (nchunks + EVQ_NCONS - 1) / EVQ_NCONS;
+  const u32 c0 = T.ctid * per;
+  const u32 c1 = c0 + per < nchunks ? c0 + per : nchunks;
+  for (u32 c = c0; c < c1; ++c) {
+    u32 m = evq_leb_chunk_mask(region, c, d.delta, tb);
+    const u32 n = __popc(m);
+    u32 jj = j;
+    const u32 skip = (3u - jj) & 3u;
+    for (u32 k = 0; k < skip; ++k) m &= m - 1u;
+    jj += skip;
+    while (m) {
+      const u32 k = __ffs(m) - 1u;
+      const u32 idx = (jj + 1u) >> 2;
+      if (idx < EVQ_NCONS) scr->start[G][idx] = (u16) (16u * c + k + 1u - d.delta);
+      m &= m - 1u; m &= m - 1u; m &= m - 1u; m &= m - 1u;
+      jj += 4u;
+    }
+    j += n;
+  }
+  if (T.ctid == 0) scr->start[G][0] = 0;
+}
+
+// ---- per-thread decode of 4 consecutive values -------------------------------------------------------------------------
+
+// index of the thread's first value inside the tile; threads past the end of a short tile decode (and discard) the
+// bytes behind the payload, which the stage regions are padded for
+__device__ __forceinline__ u32 evq_fast_first(const EvqTile& T, int s) {
+  const u32 i = EVQ_RPT * T.ctid, n = T.desc[s].nvals;
+  return i < n ? i : n;
+}
+
+__device__ __forceinline__ u32 evq_leb_pack2(u32 x) { return (x & 0x7fu) | ((x & 0x7f00u) >> 1); }
+
+__device__ __forceinline__ u32 evq_fixed_mask(u32 len) { return len >= 4u ? 0x7f7f7f7fu : ((1u << (8u * len)) - 1u) & 0x7f7f7f7fu; }
+
+// L == 1: value i is byte i
+template <int S>
+__device__ __forceinline__ void evq_fast_ld_leb1(const EvqTile& T, const EvqScanParams& P, u32 (&v)[EVQ_RPT]) {
+  const u32 x = evq_lds_unaligned32(T.stage + P.streams[S].smem_off + T.desc[S].delta + evq_fast_first(T, S));
+#pragma unroll
+  for (int i = 0; i < EVQ_RPT; ++i) v[i] = (x >> (8 * i)) & 0xffu;
+}
+
+// 2 <= L <= 4: 32-bit window
+template <int S, int G, int L>
+__device__ __forceinline__ void evq_fast_ld_leb32(const EvqTile& T, const EvqScanParams& P, const EvqFastScratch* scr, bool general,
+                                                  u32 (&v)[EVQ_RPT]) {
+  const u8* pay = T.stage + P.streams[S].smem_off + T.desc[S].delta;
+  if (!general) {
+    const u8* p = pay + (u32) L * evq_fast_first(T, S);
+#pragma unroll
+    for (int i = 0; i < EVQ_RPT; ++i) {
+      const u32 x = evq_lds_unaligned32(p + L * i) & evq_fixed_mask(L);
+      v[i] = L == 2 ? evq_leb_pack2(x) : evq_leb_pack4(x);
+    }
+  } else {
+    const u8* p = pay + (EVQ_RPT * T.ctid < T.desc[S].nvals ? (u32) scr->start[G][T.ctid] : 0u);
+#pragma unroll
+    for (int i = 0; i < EVQ_RPT; ++i) {
+      const u32 x = evq_lds_unaligned32(p);
+      const u32 tm = ~x & 0x80808080u;
+      const u32 low = tm & (0u - tm);            // terminator bit of the first value in the window
+      const u32 msk = (low << 1) - 1u;           // every bit up to and including it
+      const u32 y = x & msk & 0x7f7f7f7fu;
+      v[i] = L == 2 ? evq_leb_pack2(y) : evq_leb_pack4(y);
+      p += (32u - __clz(low)) >> 3;
+    }
+  }
+}
+
+// 5 <= L <= 10: 64-bit window (+ 2 bytes for 9- and 10-byte values)
+template <int S, int G, int L>
+__device__ __forceinline__ void evq_fast_ld_leb64(const EvqTile& T, const EvqScanParams& P, const EvqFastScratch* scr, bool general,
+                                                  u64 (&v)[EVQ_RPT]) {
+  const u8* pay = T.stage + P.streams[S].smem_off + T.desc[S].delta;
+  const u8* p;
+  if (!general) p = pay + (u32) L * evq_fast_first(T, S);
+  else p = pay + (EVQ_RPT * T.ctid < T.desc[S].nvals ? (u32) scr->start[G][T.ctid] : 0u);
+#pragma unroll
+  for (int i = 0; i < EVQ_RPT; ++i) {
+    u32 lo, hi;
+    evq_lds_unaligned64(p, lo, hi);
+    u32 len;
+    if (!general) {
+      len = L;
+    } else {
+      const u32 tl = ~lo & 0x80808080u, th = ~hi & 0x80808080u;
+      if (tl) len = (32u - __clz(tl & (0u - tl))) >> 3;
+      else if (th) len = 4u + ((32u - __clz(th & (0u - th))) >> 3);
+      else len = (L > 9 && (p[8] & 0x80u)) ? 10u : 9u;
+    }
+    u64 val;
+    if (len <= 4u) {
+      val = evq_leb_pack4(lo & evq_fixed_mask(len));
+    } else {
+      val = (u64) evq_leb_pack4(lo & 0x7f7f7f7fu) | ((u64) evq_leb_pack4(hi & evq_fixed_mask(len - 4u)) << 28);
+      if (L > 8 && len > 8u) {
+        val |= ((u64) (p[8] & 0x7fu)) << 56;
+        if (L > 9 && len > 9u) val |= ((u64) (p[9] & 0x7fu)) << 63;
+      }
+    }
+    v[i] = val;
+    p += len;
+  }
+}
+
+template <int S>
+__device__ __forceinline__ void evq_fast_ld_plain64(const EvqTile& T, const EvqScanParams& P, u64 (&v)[EVQ_RPT]) {
+  const u64* p = (const u64*) (T.stage + P.streams[S].smem_off + T.desc[S].delta) + evq_fast_first(T, S);
+#pragma unroll
+  for (int i = 0; i < EVQ_RPT; ++i) v[i] = p[i];
+}
+
+// the low halves only: for PLAIN64 columns whose values are known to fit 32 bits
+template <int S>
+__device__ __forceinline__ void evq_fast_ld_plain64_lo(const EvqTile& T, const EvqScanParams& P, u32 (&v)[EVQ_RPT]) {
+  const u32* p = (const u32*) (T.stage + P.streams[S].smem_off + T.desc[S].delta) + 2 * evq_fast_first(T, S);
+#pragma unroll
+  for (int i = 0; i < EVQ_RPT; ++i) v[i] = p[2 * i];
+}
+
+template <int S>
+__device__ __forceinline__ void evq_fast_ld_plain32(const EvqTile& T, const EvqScanParams& P, u32 (&v)[EVQ_RPT]) {
+  const u32* p = (const u32*) (T.stage + P.streams[S].smem_off + T.desc[S].delta) + evq_fast_first(T, S);
+#pragma unroll
+  for (int i = 0; i < EVQ_RPT; ++i) v[i] = p[i];
+}
+
+template <int S>
+__device__ __forceinline__ void evq_fast_ld_bitpack(const EvqTile& T, const EvqScanParams& P, u32 (&v)[EVQ_RPT]) {
+  const EvqStreamDesc& d = T.desc[S];
+  const u32* words = (const u32*) (T.stage + P.streams[S].smem_off + d.delta);
+  const u32 bits = P.streams[S].bits;
+#pragma unroll
+  const u32 i0 = evq_fast_first(T, S);
+#pragma unroll
+  for (int i = 0; i < EVQ_RPT; ++i) v[i] = evq_unpack_vertical(words, d.skew + i0 + i, bits);
+}
+
+// ---- the kernel ------------------------------------------------------------------------------------------------------
+
+struct EvqSmemHeader {
+  u64 full[4];
+  u64 empty[4];
+  EvqStreamDesc desc[4][EVQ_NSTREAMS > 0 ? EVQ_NSTREAMS : 1];
+};
+
+#define EVQ_HDR_BYTES ((sizeof(EvqSmemHeader) + 127) & ~127)
+
+// The generated row functions are pasted at the next line by csrc/codegen.cc.
+//@@EVQ_GENERATED@@
+
+extern "C" __global__ void __launch_bounds__(EVQ_NTHREADS, EVQ_MIN_CTAS)
+evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
+  extern __shared__ __align__(128) u8 evq_smem[];
+  EvqSmemHeader* hdr = (EvqSmemHeader*) evq_smem;
+  u8* stages = evq_smem + EVQ_HDR_BYTES;
+  EvqFastScratch* scr = (EvqFastScratch*) (stages + (size_t) EVQ_NSTAGES * stage_bytes);
+#if EVQ_TIER == 1 && EVQ_G1 > 1
+  u64* sacc = (u64*) ((u8*) scr + ((sizeof(EvqFastScratch) + 127) & ~127));
+#endif
+
+  const u32 tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < EVQ_NSTAGES; ++s) {
+      evq_mbar_init(&hdr->full[s], 1);
+      evq_mbar_init(&hdr->empty[s], EVQ_NWARPS);
+    }
+    evq_mbar_fence_init();
+  }
+  __syncthreads();
+
+  const u32 first_tile = blockIdx.x;
+  const u32 tile_step = gridDim.x;
+
+  if (tid >= EVQ_NCONS) {
+    // ===================== producer warp: one TMA bulk copy per column stream and tile =====================
+    u32 it = 0;
+    for (u32 tile = first_tile; tile < P.num_tiles; tile += tile_step, ++it) {
+      const u32 s = it % EVQ_NSTAGES;
+      const u32 round = it / EVQ_NSTAGES;
+      if (round > 0) evq_mbar_wait(&hdr->empty[s], (round - 1) & 1u);
+      evq_producer_issue(P, tile, stages + (size_t) s * stage_bytes, hdr->desc[s], &hdr->full[s]);
+    }
+    return;
+  }
+
+  // ===================== consumer warps =====================
+  u32 err = 0;
+  u64 passed = 0;
+  EvqTile T;
+  T.ctid = tid;
+  T.parity = 0;
+
+#if EVQ_TIER == 1
+#if EVQ_G1 > 1
+  for (u32 g = 0; g < EVQ_G1; ++g) evq_state_init_slot(sacc, g, tid);
+#else
+  u64 racc[EVQ_NSTATE];
+  evq_state_init_regs(racc);
+#endif
+#endif
+
+  u32 it = 0;
+  for (u32 tile = first_tile; tile < P.num_tiles; tile += tile_step, ++it) {
+    const u32 s = it % EVQ_NSTAGES;
+    evq_mbar_wait(&hdr->full[s], (it / EVQ_NSTAGES) & 1u);
+    T.stage = stages + (size_t) s * stage_bytes;
+    T.desc = hdr->desc[s];
+    T.row0 = (u64) tile * EVQ_TILE_ROWS;
+    {
+      const u64 rem = P.num_rows - T.row0;
+      T.rows = rem < EVQ_TILE_ROWS ? (u32) rem : EVQ_TILE_ROWS;
+    }
+
+    EvqFastPrep prep;
+    evq_fast_prep(T, P, scr, prep);
+    EvqCols cols;
+    evq_fast_decode(T, P, scr, prep, cols);
+
+#if EVQ_TIER == 0 || EVQ_TIER == 3
+    // scan-only plans: ordered compaction (CSTableScan.cc:826-857 keeps table order).  Rows are owned in table order
+    // (thread t: rows 4t..4t+3), so the output position is an exclusive scan of the per-thread pass counts.
+    bool pass_k[EVQ_RPT];
+    u32 mine = 0;
+#pragma unroll
+    for (int k = 0; k < EVQ_RPT; ++k) {
+      EvqRow row;
+      evq_fast_row(cols, k, row);
+      pass_k[k] = (EVQ_RPT * tid + k < T.rows) && evq_where(row, err);
+      mine += pass_k[k] ? 1u : 0u;
+    }
+    u32 incl = mine;
+    {
+      const u32 lane = evq_lane();
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (u32) o) incl += n;
+      }
+      if (lane == 31) scr->scan[tid >> 5] = incl;
+    }
+    evq_cons_sync();
+    u32 before = incl - mine, total = 0;
+#pragma unroll
+    for (int w = 0; w < EVQ_NWARPS; ++w) {
+      const u32 c = scr->scan[w];
+      if ((u32) w < (tid >> 5)) before += c;
+      total += c;
+    }
+    evq_cons_sync();
+    passed += mine;
+#if EVQ_TIER == 0
+    if (tid == 0) P.tile_counts[P.tile_row_base + tile] = total;
+#else
+    {
+      u64 out_row = P.tile_out_base[P.tile_row_base + tile] + before;
+#pragma unroll
+      for (int k = 0; k < EVQ_RPT; ++k) {
+        if (pass_k[k]) {
+          EvqRow row;
+          evq_fast_row(cols, k, row);
+          evq_project(row, P, out_row, err);
+          ++out_row;
+        }
+      }
+    }
+#endif
+#else
+#pragma unroll
+    for (int k = 0; k < EVQ_RPT; ++k) {
+      EvqRow row;
+      evq_fast_row(cols, k, row);
+      const bool pass = (EVQ_RPT * tid + k < T.rows) && evq_where(row, err);
+#if EVQ_TIER == 1
+      if (pass) {
+        ++passed;
+#if EVQ_G1 > 1
+        u64 key[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
+        u32 ktag[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
+        evq_keys(row, key, ktag, err);
+        u64 slot = 0;
+#pragma unroll
+        for (int i = 0; i < EVQ_NKEYS; ++i) {
+          const u64 idx = ktag[i] ? P.key_null_idx[i] : key[i] - P.key_min[i];
+          slot += idx * P.key_stride[i];
+        }
+        if (slot >= P.dense_slots) {
+          err |= EVQ_ERR_SLOT_RANGE;
+        } else {
+          evq_accumulate_smem(row, sacc, (u32) slot, tid, err);
+        }
+#else
+        evq_accumulate_regs(row, racc, err);
+#endif
+      }
+#else   // EVQ_TIER == 2
+      if (pass) {
+        ++passed;
+        u64 key[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
+        u32 ktag[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
+        evq_keys(row, key, ktag, err);
+        const u64 slot = evq_ht_upsert<EVQ_NKEYS>(P.ht, key, ktag, P.counters + 1);
+        if (slot == ~0ull) {
+          err |= EVQ_ERR_TABLE_FULL;
+        } else {
+          evq_accumulate_global(row, P.ht.state, P.ht.cap, slot, err);
+        }
+      }
+#endif
+    }
+#endif
+
+    __syncwarp();
+    if (evq_lane() == 0) evq_mbar_arrive(&hdr->empty[s]);
+  }
+
+  // ===================== epilogue: merge this CTA's partial state =====================
+#if EVQ_TIER == 1
+#if EVQ_G1 > 1
+  for (u32 g = 0; g < EVQ_G1; ++g) evq_state_flush_smem(sacc, g, tid, P.dense_state);
+#else
+  evq_state_flush_regs(racc, P.dense_state);
+#endif
+#endif
+  {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      passed += __shfl_xor_sync(0xffffffffu, passed, o);
+      err |= __shfl_xor_sync(0xffffffffu, err, o);
+    }
+    if (evq_lane() == 0) {
+      if (passed) atomicAdd(P.counters, passed);
+      if (err) atomicOr(P.status, err);
+    }
+  }
+}

@@ -42,15 +42,6 @@ struct EvqScratch {
 
 // ---- LEB128 boundary resolution -------------------------------------------------------------------------------------
 
-__device__ __forceinline__ u32 evq_leb_chunk_mask(const u8* region, u32 c, u32 delta, u32 tb) {
-  const uint4 q = *(const uint4*) (region + 16u * c);
-  u32 m = evq_term_mask16(q);
-  const u32 pos = 16u * c;
-  if (pos < delta) m &= ~((1u << (delta - pos)) - 1u);
-  if (tb - pos < 16u) m &= (1u << (tb - pos)) - 1u;
-  return m;
-}
-
 // phase A: classify the tile (all 1-byte / uniform width / general) and count this thread's terminators
 template <int S, int L>
 __device__ __forceinline__ void evq_leb_phase_a(const EvqTile& T, const EvqScanParams& P, EvqScratch* scr,

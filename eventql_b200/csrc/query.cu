@@ -52,6 +52,7 @@ static Binding bind_table(const evqgpu_query& q, evqgpu_table* t) {
 static KernelShape shape_for(const evqgpu_query& q, evqgpu_table* t, const Binding& b) {
   KernelShape s;
   s.cols.resize(q.input_columns.size());
+  s.fast = true;
   for (size_t i = 0; i < q.input_columns.size(); ++i) {
     if (b.col_index[i] < 0) continue;
     const Column& c = t->cols[b.col_index[i]];
@@ -61,10 +62,13 @@ static KernelShape shape_for(const evqgpu_query& q, evqgpu_table* t, const Bindi
     cs.kind = c.data_kind;
     cs.nullable = c.meta.dlevel_max > 0;
     cs.dmax = c.meta.dlevel_max;
+    cs.bits = c.value_bits;
+    cs.leb_len = c.leb_max_len;
     cs.data_stream = s.nstreams++;
     if (cs.nullable) {
       cs.level_stream = s.nstreams++;
       cs.null_slot = s.nnull++;
+      s.fast = false;
     }
     if (cs.kind == EVQ_KIND_LEB128) cs.leb_slot = s.nleb++;
   }
@@ -73,6 +77,24 @@ static KernelShape shape_for(const evqgpu_query& q, evqgpu_table* t, const Bindi
   return s;
 }
 
+// the value-range statistics only widen a kernel, they never make it wrong: take the widest over the partitions
+static void widen_shape(KernelShape& s, const KernelShape& o) {
+  for (size_t i = 0; i < s.cols.size(); ++i) {
+    s.cols[i].bits = std::max(s.cols[i].bits, o.cols[i].bits);
+    s.cols[i].leb_len = std::max(s.cols[i].leb_len, o.cols[i].leb_len);
+  }
+}
+
+static void finish_shape(KernelShape& s) {
+  s.ngen = 0;
+  for (auto& c : s.cols) {
+    c.gen_slot = -1;
+    if (s.fast && c.used && c.kind == EVQ_KIND_LEB128 && c.leb_len >= 2) c.gen_slot = s.ngen++;
+  }
+  if (getenv("EVQGPU_NO_FAST")) s.fast = false;
+}
+
+// layout (not the value ranges) must agree between the partitions of one query
 static std::string shape_key(const KernelShape& s) {
   std::string k;
   for (const auto& c : s.cols) {
@@ -99,7 +121,7 @@ static StageLayout stage_layout(const evqgpu_query& q, evqgpu_table* t, const Bi
     if (!cs.used) continue;
     const Column& c = t->cols[b.col_index[i]];
     auto place = [&](int stream, uint32_t cap) {
-      cap = (uint32_t) round_up(cap, 16) + 16;   // decoders may read up to 12 bytes past the payload
+      cap = (uint32_t) round_up(cap, 16) + 64;   // decoders may read a few values past the payload (short last tile)
       L.smem_off[stream] = off;
       L.smem_cap[stream] = cap;
       off += (uint32_t) round_up(cap, 128);
@@ -114,13 +136,17 @@ static StageLayout stage_layout(const evqgpu_query& q, evqgpu_table* t, const Bi
 
 static size_t scratch_bytes(const KernelShape& s) {
   const size_t nwarps = s.ncons / 32;
+  if (s.fast) {   // EvqFastScratch
+    const size_t ngen = std::max(1, s.ngen);
+    return round_up(4 * ngen * nwarps + 2 * ngen * s.ncons + 4 * nwarps, 128) + 128;
+  }
   const size_t one = 4 * std::max(1, s.nleb) * nwarps + 4 * std::max(1, s.nnull) * (EVQ_TILE_ROWS / 32) +
                      2 * std::max(1, s.nleb) * EVQ_TILE_ROWS + 4 * nwarps;
   return round_up(2 * round_up(one, 8), 128) + 128;
 }
 
 static size_t header_bytes(const KernelShape& s) {
-  const size_t raw = 8 * 4 + 8 * 4 + 4 * 4 + 16 * 4 * std::max(1, s.nstreams);
+  const size_t raw = 8 * 4 + 8 * 4 + (s.fast ? 0 : 4 * 4) + 16 * 4 * std::max(1, s.nstreams);
   return round_up(raw, 128);
 }
 
@@ -249,6 +275,18 @@ struct TablePlan {
   size_t smem = 0;
 };
 
+static KernelShape shape_of_plans(const evqgpu_query& q, const std::vector<TablePlan>& plans) {
+  KernelShape s = shape_for(q, plans[0].table, plans[0].binding);
+  for (size_t i = 1; i < plans.size(); ++i) {
+    const KernelShape o = shape_for(q, plans[i].table, plans[i].binding);
+    if (shape_key(o) != shape_key(s))
+      fail(EVQGPU_ERR_UNSUPPORTED, "partitions of one query must share column encodings and nullability");
+    widen_shape(s, o);
+  }
+  finish_shape(s);
+  return s;
+}
+
 static void fill_streams(EvqScanParams& P, evqgpu_table* t, const Binding& b, const KernelShape& s, const StageLayout& L) {
   P.num_rows = t->num_rows;
   P.num_tiles = t->num_tiles;
@@ -297,6 +335,10 @@ static void fit_shape(evqgpu_query& q, KernelShape& s, std::vector<TablePlan>& p
   for (int attempt = 0; attempt < 4; ++attempt) {
     s.ncons = (attempt & 1) ? 128 : 256;
     s.nstages = (attempt & 2) ? 2 : 3;
+    if (s.fast) {
+      if (attempt & 1) continue;
+      s.ncons = 256;
+    }
     size_t worst = 0;
     for (auto& p : plans) {
       p.layout = stage_layout(q, p.table, p.binding, s);
@@ -523,10 +565,7 @@ void emit_results(evqgpu_query& q) {
 
 static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std::vector<evqgpu_table*>& tables, bool sync) {
   evqgpu_ctx* ctx = q.ctx;
-  KernelShape s = shape_for(q, plans[0].table, plans[0].binding);
-  for (size_t i = 1; i < plans.size(); ++i)
-    if (shape_key(shape_for(q, plans[i].table, plans[i].binding)) != shape_key(s))
-      fail(EVQGPU_ERR_UNSUPPORTED, "partitions of one query must share column encodings and nullability");
+  KernelShape s = shape_of_plans(q, plans);
   uint64_t total_rows = 0;
   for (auto* t : tables) total_rows += t->num_rows;
 
@@ -551,7 +590,7 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
     if (dense) {
       s.g1 = g1_for(dm.slots);
       // thread-private accumulators must fit next to the pipeline stages
-      const size_t acc = (size_t) s.g1 * q.state_ops.size() * 128 * 8;
+      const size_t acc = (size_t) s.g1 * q.state_ops.size() * (s.fast ? 256 : 128) * 8;
       if (s.g1 > 64 || acc > 96 * 1024) dense = false;
     }
     if (!dense) { s.tier = 2; s.g1 = 1; }
@@ -639,10 +678,7 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
 
 static void execute_scan_only(evqgpu_query& q, std::vector<TablePlan>& plans, std::vector<evqgpu_table*>& tables) {
   evqgpu_ctx* ctx = q.ctx;
-  KernelShape s = shape_for(q, plans[0].table, plans[0].binding);
-  for (size_t i = 1; i < plans.size(); ++i)
-    if (shape_key(shape_for(q, plans[i].table, plans[i].binding)) != shape_key(s))
-      fail(EVQGPU_ERR_UNSUPPORTED, "partitions of one query must share column encodings and nullability");
+  KernelShape s = shape_of_plans(q, plans);
   uint64_t total_tiles = 0, total_rows = 0;
   for (auto* t : tables) { total_tiles += t->num_tiles; total_rows += t->num_rows; }
   s.tier = 0;

@@ -29,6 +29,9 @@ struct ColSig {
   uint32_t dmax = 0;
   int data_stream = -1, level_stream = -1;
   int leb_slot = -1, null_slot = -1;
+  uint32_t bits = 64;      // every value < 2^bits (max over the scanned tables)
+  uint32_t leb_len = 10;   // LEB128: longest value in bytes (max over the scanned tables)
+  int gen_slot = -1;       // fast kernel: index among the LEB128 columns that may need the boundary search (leb_len >= 2)
 };
 
 struct KernelShape {
@@ -39,6 +42,8 @@ struct KernelShape {
   int nstages = 3;
   int min_ctas = 1;
   int nstreams = 0, nleb = 0, nnull = 0;
+  bool fast = false;   // all referenced columns are required: kernels/evq_scan_fast.cuh (4 consecutive rows per thread)
+  int ngen = 0;        // fast kernel: LEB128 columns with leb_len >= 2
 };
 
 struct DenseMap {

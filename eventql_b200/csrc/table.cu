@@ -90,23 +90,61 @@ __device__ __forceinline__ u32 term_count16(uint4 c, u32 valid) {
   return n;
 }
 
-// terminator bytes (msb clear) per EVQ_LEB_CHUNK bytes of payload
-__global__ void k_leb_chunk_counts(const uint4* __restrict__ data, u64 nbytes, u64 nchunks, u64* __restrict__ counts) {
+// bit i of the result = byte i of the 16-byte chunk is a continuation byte (msb set)
+__device__ __forceinline__ u32 cont_mask16(uint4 c) {
+  u32 w[4] = {c.x, c.y, c.z, c.w};
+  u32 m = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const u32 t = w[k] & 0x80808080u;
+    m |= (((t * 0x00204081u) >> 28) & 0xfu) << (4 * k);
+  }
+  return m;
+}
+
+// terminator bytes (msb clear) per EVQ_LEB_CHUNK bytes of payload; also the column statistic "longest value":
+// bit k-1 of *runs is set when k consecutive continuation bytes occur somewhere (k = 1..9), i.e. a value of k+1 bytes
+__global__ void k_leb_chunk_counts(const uint4* __restrict__ data, u64 nbytes, u64 nchunks, u64* __restrict__ counts,
+                                   unsigned int* __restrict__ runs) {
   const u64 warp = ((u64) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const u32 lane = threadIdx.x & 31;
   if (warp >= nchunks) return;
   const u64 base = warp * EVQ_LEB_CHUNK;
-  u32 cnt = 0;
+  u32 cnt = 0, seen = 0;
 #pragma unroll
   for (u32 k = 0; k < EVQ_LEB_CHUNK / 16 / 32; ++k) {
     const u64 off = base + (u64) (k * 32 + lane) * 16;
     if (off < nbytes) {
       const u64 rem = nbytes - off;
-      cnt += term_count16(data[off >> 4], rem < 16 ? (u32) rem : 16u);
+      const uint4 q = data[off >> 4];
+      cnt += term_count16(q, rem < 16 ? (u32) rem : 16u);
+      // continuation bits of this chunk and the next one (streams are zero padded by >= 128 bytes: reading on is safe)
+      u32 c = cont_mask16(q) | (cont_mask16(data[(off >> 4) + 1]) << 16);
+      if (rem < 32) c &= (1u << rem) - 1u;   // only payload bytes
+      u32 r = c;
+#pragma unroll
+      for (u32 len = 1; len <= 9; ++len) {
+        if (r & 0xffffu) seen |= 1u << (len - 1);   // a run of `len` continuation bytes starts inside this chunk
+        r &= c >> len;
+      }
     }
   }
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if (lane == 0) counts[warp] = cnt;
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    seen |= __shfl_xor_sync(0xffffffffu, seen, o);
+  }
+  if (lane == 0) {
+    counts[warp] = cnt;
+    if (seen) atomicOr(runs, seen);
+  }
+}
+
+// column statistic of fixed-width streams: OR of all values (its highest bit bounds every value)
+__global__ void k_or_reduce64(const u64* __restrict__ v, u64 n, unsigned long long* __restrict__ out) {
+  u64 acc = 0;
+  for (u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64) gridDim.x * blockDim.x) acc |= v[i];
+  for (int o = 16; o > 0; o >>= 1) acc |= __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicOr(out, acc);
 }
 
 // off_index[t] = byte offset at which value number boundary(t) starts, boundary(t) = val_index[t] or t*TILE
@@ -226,6 +264,7 @@ void table_finish_column(evqgpu_table* t, Column& c) {
   const bool nullable = c.meta.dlevel_max > 0;
   if (nullable) {
     c.level_bits = bits_needed(c.dlevel.bitpack_max);
+    if (t->num_rows == 0 && c.level_bits == 0) c.level_bits = bits_needed(c.meta.dlevel_max);   // empty table: no level page at all
     if (c.level_bits == 0)
       fail(EVQGPU_ERR_FORMAT, "column '%s': definition level stream has bit width 0", c.meta.name.c_str());
     const uint64_t need = (t->num_rows + 127) / 128 * 16 * c.level_bits;
@@ -276,12 +315,26 @@ void table_finish_column(evqgpu_table* t, Column& c) {
         fail(EVQGPU_ERR_FORMAT, "column '%s': data stream too short", c.meta.name.c_str());
       c.data_payload_bytes = nv * w;
       c.data_bits = w * 8;
+      c.value_bits = w * 8;
+      if (w == 8 && nv && c.sql_type != EVQ_FLOAT64) {
+        DevBuf acc;
+        acc.alloc(8);
+        EVQ_CUDA(cudaMemsetAsync(acc.p, 0, 8, ctx->stream));
+        k_or_reduce64<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(c.data.buf.as<u64>(), nv, acc.as<unsigned long long>());
+        EVQ_CUDA(cudaGetLastError());
+        ctx->kernel_launches++;
+        u64 ored = 0;
+        EVQ_CUDA(cudaMemcpyAsync(&ored, acc.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
+        c.value_bits = ored ? 64 - (uint32_t) __builtin_clzll(ored) : 1;
+      }
       if (nullable) c.data_tile_cap = span_from_index(c.val_index.as<u64>(), w, 0, 0);
       else c.data_tile_cap = EVQ_TILE_ROWS * w + 32;
       break;
     }
     case EVQ_KIND_BITPACK: {
       c.data_bits = bits_needed(c.data.bitpack_max);
+      c.value_bits = std::max<uint32_t>(1, c.data_bits);
       const uint64_t need = (nv + 127) / 128 * 16 * c.data_bits;
       if (c.data_bits && c.data.nbytes < need)
         fail(EVQGPU_ERR_FORMAT, "column '%s': bit-packed stream too short", c.meta.name.c_str());
@@ -296,13 +349,23 @@ void table_finish_column(evqgpu_table* t, Column& c) {
       counts.alloc((nchunks + 1) * 8);
       base.alloc((nchunks + 1) * 8);
       EVQ_CUDA(cudaMemsetAsync(counts.p, 0, counts.bytes, ctx->stream));
+      EVQ_CUDA(cudaMemsetAsync(maxspan.p, 0, sizeof(unsigned int), ctx->stream));
       {
         const uint32_t threads = 256;
         const uint64_t blocks = (nchunks * 32 + threads - 1) / threads;
         k_leb_chunk_counts<<<(unsigned) blocks, threads, 0, ctx->stream>>>(c.data.buf.as<uint4>(), c.data.nbytes, nchunks,
-                                                                           counts.as<u64>());
+                                                                           counts.as<u64>(), maxspan.as<unsigned int>());
         EVQ_CUDA(cudaGetLastError());
         ctx->kernel_launches++;
+      }
+      {
+        // longest value of the column in bytes -> static decode width of the query kernels
+        unsigned int runs = 0;
+        EVQ_CUDA(cudaMemcpyAsync(&runs, maxspan.p, sizeof(runs), cudaMemcpyDeviceToHost, ctx->stream));
+        EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
+        c.leb_max_len = 1;
+        while (c.leb_max_len < 10 && (runs >> (c.leb_max_len - 1)) & 1u) ++c.leb_max_len;
+        c.value_bits = std::min<uint32_t>(64, 7 * c.leb_max_len);
       }
       exclusive_scan_u64(ctx, counts.as<u64>(), base.as<u64>(), nchunks + 1);
       u64 total_terms = 0;
@@ -444,6 +507,8 @@ int evqgpu_table_column_info(const evqgpu_table* tbl, uint32_t idx, evqgpu_colum
     out->data_bytes = c.data_payload_bytes;
     out->level_bytes = c.level_payload_bytes;
     out->num_values = c.num_values;
+    out->value_bits = c.value_bits;
+    out->leb_max_len = c.leb_max_len;
   });
 }
 

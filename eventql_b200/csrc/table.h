@@ -36,6 +36,8 @@ struct Column {
   uint32_t data_kind = 0;      // EVQ_KIND_*
   uint32_t data_bits = 0;
   uint32_t level_bits = 0;
+  uint32_t value_bits = 64;    // statistic: every value of the column is < 2^value_bits (computed when the column is loaded)
+  uint32_t leb_max_len = 10;   // LEB128: the longest value in bytes
   uint32_t data_tile_cap = 0;  // max bytes one tile copy of the data stream can need (multiple of 16)
   uint32_t level_tile_cap = 0;
 };

@@ -151,6 +151,8 @@ typedef struct evqgpu_column_info {
   uint64_t data_bytes;      /* payload bytes of the DATA stream (algorithmic bytes, padding excluded) */
   uint64_t level_bytes;     /* payload bytes of the DLEVEL stream, 0 if the column is required */
   uint64_t num_values;      /* non-NULL values (known once loaded) */
+  uint32_t value_bits;      /* statistic: every value < 2^value_bits (known once loaded) */
+  uint32_t leb_max_len;     /* statistic: longest LEB128 value in bytes (known once loaded) */
 } evqgpu_column_info;
 
 /* Parse header + page index of a cstable file image (v0.1.0 and v0.2.0).  Host only: nothing
@@ -340,6 +342,8 @@ typedef struct evqgpu_debug_column {
   uint32_t sql_type;   /* EVQ_* SType */
   uint32_t encoding;   /* EVQ_ENC_* */
   uint32_t dlevel_max; /* 0 = required */
+  uint32_t value_bits;   /* column statistic: every value < 2^value_bits; 0 = unknown (64) */
+  uint32_t leb_max_len;  /* column statistic: longest LEB128 value in bytes; 0 = unknown (10) */
 } evqgpu_debug_column;
 
 /* tier: 1 = dense / single group (dense_slots groups), 2 = global hash table; ignored for scan-only plans.

@@ -66,11 +66,18 @@ def test_function_registry_matches_plan_module(native_lib):
     assert native_lib.evqgpu_function_symbol(100000) is None
 
 
-def _cols(spec):
-    return [(T.sql_type_of(s), s["encoding"], 1 if s.get("null_every") else 0) for s in spec]
+# column statistics (value bits, longest LEB128 value) as the loader computes them for the synthetic tables
+STATS = {"shipdate": (14, 2), "discount": (7, 1), "quantity": (7, 1), "price": (28, 4), "tax": (7, 1), "flag": (7, 1),
+         "status": (7, 1), "ekey": (64, 0), "v": (21, 3), "time": (56, 8), "sensor_id": (14, 2), "value": (21, 3)}
 
 
-@pytest.mark.parametrize("case", ["q6_leb", "q6_plain", "q1_dense", "q1_null", "hc_hash", "ts_hash", "scan_only_mixed"])
+def _cols(spec, stats=True):
+    return [(T.sql_type_of(s), s["encoding"], 1 if s.get("null_every") else 0) + (STATS.get(s["name"], (0, 0)) if stats else (0, 0))
+            for s in spec]
+
+
+@pytest.mark.parametrize("case", ["q6_leb", "q6_plain", "q1_dense", "q1_nostats", "q1_null", "hc_hash", "ts_hash", "scan_only_mixed",
+                                  "scan_only_required"])
 def test_kernel_text_compiles_for_sm100a(native_lib, case):
     """Codegen + NVRTC (--gpu-architecture=sm_100a) of every kernel tier, without a device."""
     if case == "q6_leb":
@@ -82,6 +89,10 @@ def test_kernel_text_compiles_for_sm100a(native_lib, case):
         _, plan = T.q6(spec)
         tier, slots = 1, 1
     elif case == "q1_dense":
+        spec = T.lineitem_spec()
+        _, plan = T.q1(spec)
+        tier, slots = 1, 4
+    elif case == "q1_nostats":
         spec = T.lineitem_spec()
         _, plan = T.q1(spec)
         tier, slots = 1, 4
@@ -98,12 +109,15 @@ def test_kernel_text_compiles_for_sm100a(native_lib, case):
         _, plan = T.q_timeseries(spec)
         tier, slots = 2, 0
     else:
-        spec = T.mixed_spec()
+        spec = T.mixed_spec(0 if case == "scan_only_required" else 7)
         c, names = T.cols_of(spec)
-        plan = P.QueryPlan(names, [c["a"], c["f"], c["bo"], c["c"] + c["d"]], where=c["b"] < 50, flags=0)
+        plan = P.QueryPlan(names, [c["a"], c["f"], c["bo"], c["c"] + c["d"], c["big"]], where=c["b"] < 50, flags=0)
         tier, slots = 0, 0
-    src, cubin_bytes = capi.debug_generate(plan, _cols(spec), tier=tier, dense_slots=slots, compile=True)
+    src, cubin_bytes = capi.debug_generate(plan, _cols(spec, case != "q1_nostats"), tier=tier, dense_slots=slots, compile=True)
     assert "evq_scan" in src and cubin_bytes > 1000
+    # required columns take the fast kernel (4 consecutive rows per thread), optional ones the general kernel
+    nullable = any(s.get("null_every") for s in spec)
+    assert ("evq_fast_decode" in src) == (not nullable)
     # the TMA bulk copy + mbarrier pipeline is part of every variant
     assert "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes" in src
 

@@ -88,9 +88,11 @@ def test_decode_reference_written_files(gpu_ctx, ver):
     tbl.close()
 
 
-@pytest.mark.parametrize("nrows", [0, 1, 127, 128, 129, 1023, 1024, 1025, 4096, 70001])
-def test_decode_and_aggregate_ragged_sizes(gpu_ctx, nrows, tmp_path):
-    spec = T.mixed_spec(null_every=3)
+@pytest.mark.parametrize("null_every", [3, 0], ids=["optional", "required"])
+@pytest.mark.parametrize("nrows", [0, 1, 3, 127, 128, 129, 1023, 1024, 1025, 4096, 70001])
+def test_decode_and_aggregate_ragged_sizes(gpu_ctx, nrows, null_every, tmp_path):
+    """optional columns run the general kernel, required ones the fast kernel (4 consecutive rows per thread)"""
+    spec = T.mixed_spec(null_every=null_every)
     path = str(tmp_path / "m.cst")
     T.write_table(path, spec, nrows)
     tbl = gpu_ctx.open_table_file(path)
@@ -103,6 +105,23 @@ def test_decode_and_aggregate_ragged_sizes(gpu_ctx, nrows, tmp_path):
             continue
         got, _ = run_gpu(gpu_ctx, [tbl], plan)
         compare(got, O.run_query([f], plan).rows(), not plan.is_groupby)
+    tbl.close()
+
+
+def test_column_statistics(gpu_ctx):
+    """value_bits / leb_max_len (computed when a column is loaded) bound every value: the fast kernel's static types"""
+    spec = T.lineitem_spec() + [dict(name="wide", logical_type=P.COL_UNSIGNED_INT, encoding=P.ENC_UINT64_PLAIN, seed=77, lo=0, span=1 << 40),
+                                dict(name="big", logical_type=P.COL_UNSIGNED_INT, encoding=P.ENC_UINT64_LEB128, seed=9, lo=0,
+                                     span=(1 << 64) - 1, transform=1)]
+    tbl = gpu_ctx.synthesize(300_000, spec)
+    info = {c["name"]: c for c in tbl.columns()}
+    assert info["flag"]["leb_max_len"] == 1 and info["quantity"]["leb_max_len"] == 1 and info["shipdate"]["leb_max_len"] == 2
+    assert info["price"]["leb_max_len"] == 4 and info["price"]["value_bits"] == 28
+    assert info["wide"]["value_bits"] == 40
+    assert info["big"]["leb_max_len"] == 10 and info["big"]["value_bits"] == 64
+    for s in spec:
+        v, _ = T.synth_values(s, 300_000)
+        assert int(v.max()) < (1 << info[s["name"]]["value_bits"]) or info[s["name"]]["value_bits"] == 64
     tbl.close()
 
 
@@ -274,9 +293,10 @@ def test_q1_250m_rows_properties(gpu_ctx):
     assert stats["rows_scanned"] == 2 * n and stats["strategy"] == 1 and len(both) == 4
     per = [run_gpu(gpu_ctx, [p], plan_int)[0] for p in parts]
     compare(_merge_partials(per, plan_int), both, False)
-    # every row passes the Q1 predicate by construction: counts add up to the table size; sum(discount) etc. are
-    # bounded by their value ranges
-    assert sum(r[2] for r in both) == 2 * n
+    # counts add up to the rows that pass WHERE (shipdate <= 10471: 2436 of 2526 values); sums are bounded by the
+    # value ranges of their columns
+    assert sum(r[2] for r in both) == stats["rows_passed"]
+    assert abs(stats["rows_passed"] / (2 * n) - 2436 / 2526) < 1e-3
     for r in both:
         assert r[2] * 1 <= r[3] <= r[2] * 50 and r[2] * 90000 <= r[4] <= r[2] * 10089999
     # means == sum / count of the same run (1e-9)
