@@ -9,17 +9,6 @@
 
 namespace evq {
 
-int state_words_of(const FnInfo& fi) {
-  switch (fi.fn) {
-    case Fn::COUNT: return 0;   // shares the per-group row counter (state word 0)
-    case Fn::SUM: return 1;
-    case Fn::MIN:
-    case Fn::MAX:
-    case Fn::MEAN: return 2;
-    default: return 0;
-  }
-}
-
 static int minmax_op(Fn fn, int type) {
   const bool mx = fn == Fn::MAX;
   switch (type) {
@@ -61,10 +50,89 @@ static CodegenEnv row_env(const KernelShape& shape) {
   return env;
 }
 
-// one aggregate update: "state[st] = combine<OP>(state[st], bits)" spelled through the UPD macro of the variant
+// Can the value of `e` carry a NULL tag?  Only bare column references (possibly through `if`) do.
+static bool tag_is_static_zero(const Expr* e, const KernelShape& shape) {
+  switch (e->op) {
+    case EVQ_X_INPUT: return !(e->col < shape.cols.size() && shape.cols[e->col].nullable);
+    case EVQ_X_IF: return tag_is_static_zero(e->args[1].get(), shape) && tag_is_static_zero(e->args[2].get(), shape);
+    case EVQ_X_LITERAL: return e->type != EVQ_NIL;
+    default: return true;
+  }
+}
+
+// Aggregate state layout of one execution.  Words are shared wherever two aggregates accumulate the same thing:
+//   word 0            rows of the group: count(...) of any argument (aggregate.cc:35-38) and the "seen" counter of
+//                     min / max / mean whenever the argument cannot be NULL
+//   "sum:<expr>"      sum_uint64 / sum_int64 (wrapping, aggregate.cc:184-219) AND the low 64 bits of mean(<expr>) over a
+//                     uint64 argument; mean adds "carry:<expr>", the number of wraps of that word, so its sum is the exact
+//                     128-bit integer sum (converted to double once, in the emit kernel) instead of one I2F + DADD per row
+//   "fsum:<expr>"     double sums (sum_float64, mean over int64 / float64 arguments)
+//   "min:" / "max:"   extrema, "seen:<expr>" their non-NULL counters
+// The layout depends on the plan and on which columns are optional; evqgpu_query_merge checks that all ranks agree.
+void layout_states(evqgpu_query& q, const KernelShape& shape) {
+  q.state_ops.clear();
+  q.state_keys.clear();
+  q.state_carry_of.clear();
+  auto word = [&](const std::string& key, int op, int carry_of = -1) -> int {
+    for (size_t i = 0; i < q.state_keys.size(); ++i)
+      if (q.state_keys[i] == key) return (int) i;
+    q.state_keys.push_back(key);
+    q.state_ops.push_back(op);
+    q.state_carry_of.push_back(carry_of);
+    return (int) q.state_keys.size() - 1;
+  };
+  word("rows", OP_ADD_U64);
+  for (auto& item : q.select) {
+    item.state0 = item.state_seen = item.state_carry = -1;
+    if (!item.agg) continue;
+    const FnInfo& fi = item.agg->info();
+    const Expr* arg = item.agg->args.empty() ? nullptr : item.agg->args[0].get();
+    const std::string sig = arg ? arg->signature() : std::string();
+    const int ty = fi.args.empty() ? EVQ_NIL : fi.args[0];
+    const bool never_null = arg && tag_is_static_zero(arg, shape);
+    switch (fi.fn) {
+      case Fn::COUNT: item.state0 = 0; break;
+      case Fn::SUM:
+        item.state0 = ty == EVQ_FLOAT64 ? word("fsum:" + sig, OP_ADD_F64) : word("sum:" + sig, OP_ADD_U64);
+        break;
+      case Fn::MIN:
+      case Fn::MAX:
+        item.state0 = word(std::string(fi.fn == Fn::MAX ? "max:" : "min:") + sig, minmax_op(fi.fn, ty));
+        item.state_seen = never_null ? 0 : word("seen:" + sig, OP_ADD_U64);
+        break;
+      case Fn::MEAN:
+        if (ty == EVQ_UINT64) {
+          item.state0 = word("sum:" + sig, OP_ADD_U64);
+          item.state_carry = word("carry:" + sig, OP_ADD_U64, item.state0);
+        } else {
+          item.state0 = word((ty == EVQ_FLOAT64 ? "fsum:" : "fsumi:") + sig, OP_ADD_F64);
+        }
+        item.state_seen = never_null ? 0 : word("seen:" + sig, OP_ADD_U64);
+        break;
+      default: fail(EVQGPU_ERR_UNSUPPORTED, "aggregate %s", fi.symbol.c_str());
+    }
+  }
+  // carry words are touched once in 2^64 / value rows: they live in the global state only, never in thread-private storage
+  q.state_smem.assign(q.state_ops.size(), -1);
+  q.nstate_smem = 0;
+  for (size_t i = 0; i < q.state_ops.size(); ++i)
+    if (q.state_carry_of[i] < 0) q.state_smem[i] = q.nstate_smem++;
+}
+
+static int carry_word_of(const evqgpu_query& q, int sum_word) {
+  for (size_t i = 0; i < q.state_carry_of.size(); ++i)
+    if (q.state_carry_of[i] == sum_word) return (int) i;
+  return -1;
+}
+
+// The per-row aggregate updates, one per state WORD (not per select item): spelled through the macros of the variant
+//   EVQ_UPD(word, op, v)            state[word] = combine<op>(state[word], v)
+//   EVQ_UPD_C(word, carry, v)       state[word] += v; if that wrapped: state[carry] += 1
 static void gen_updates(std::ostringstream& os, const evqgpu_query& q, const KernelShape& shape) {
   CodegenEnv env = row_env(shape);
-  os << "  EVQ_UPD(0, " << OP_ADD_U64 << ", 1ull);\n";   // rows per group (count(...) reads this word too)
+  std::vector<bool> done(q.state_ops.size(), false);
+  os << "  EVQ_UPD(0, " << OP_ADD_U64 << ", 1ull);\n";   // rows per group
+  done[0] = true;
   for (const auto& item : q.select) {
     if (!item.agg) continue;
     const FnInfo& fi = item.agg->info();
@@ -79,25 +147,33 @@ static void gen_updates(std::ostringstream& os, const evqgpu_query& q, const Ker
     }
     Code c = gen_expr(arg, env);
     const int ty = fi.args[0];
-    os << "  {\n";
-    if (fi.fn == Fn::SUM) {
-      // sum_*: acc += v, NULL contributes its value bits 0 (aggregate.cc:184-219)
-      os << "    const u64 v = " << as_bits(c, ty) << ";\n";
-      os << "    EVQ_UPD(" << item.state0 << ", " << (ty == EVQ_FLOAT64 ? OP_ADD_F64 : OP_ADD_U64) << ", v);\n";
-    } else if (fi.fn == Fn::MIN || fi.fn == Fn::MAX) {
-      os << "    if (!(" << c.tag << ")) {\n";
-      os << "      const u64 v = " << as_bits(c, ty) << ";\n";
-      os << "      EVQ_UPD(" << item.state0 << ", " << minmax_op(fi.fn, ty) << ", v);\n";
-      os << "      EVQ_UPD(" << item.state0 + 1 << ", " << OP_ADD_U64 << ", 1ull);\n";
-      os << "    }\n";
-    } else {   // MEAN
-      os << "    if (!(" << c.tag << ")) {\n";
-      os << "      const u64 v = evq_bits((f64) (" << c.value << "));\n";
-      os << "      EVQ_UPD(" << item.state0 << ", " << OP_ADD_F64 << ", v);\n";
-      os << "      EVQ_UPD(" << item.state0 + 1 << ", " << OP_ADD_U64 << ", 1ull);\n";
-      os << "    }\n";
+    const int w = item.state0;
+    if (!done[w]) {
+      done[w] = true;
+      os << "  {\n";
+      const int op = q.state_ops[w];
+      if (q.state_keys[w].compare(0, 4, "sum:") == 0) {
+        // sum_*: acc += v; a NULL contributes its value bits, which are 0 (aggregate.cc:184-219)
+        const int cw = carry_word_of(q, w);
+        os << "    const u64 v = " << as_bits(c, ty) << ";\n";
+        if (cw >= 0) os << "    EVQ_UPD_C(" << w << ", " << cw << ", v);\n";
+        else os << "    EVQ_UPD(" << w << ", " << OP_ADD_U64 << ", v);\n";
+      } else if (op == OP_ADD_F64) {
+        // double sums; NULL rows are skipped (their value bits are 0 anyway, but -0.0 + 0.0 and NaN payloads differ)
+        const bool skip_null = c.tag != "0u" && fi.fn == Fn::MEAN;
+        if (skip_null) os << "    if (!(" << c.tag << "))\n  ";
+        os << "    EVQ_UPD(" << w << ", " << OP_ADD_F64 << ", evq_bits((f64) (" << c.value << ")));\n";
+      } else {   // min / max
+        if (c.tag != "0u") os << "    if (!(" << c.tag << "))\n  ";
+        os << "    EVQ_UPD(" << w << ", " << op << ", " << as_bits(c, ty) << ");\n";
+      }
+      os << "  }\n";
     }
-    os << "  }\n";
+    const int sw = item.state_seen;
+    if (sw > 0 && !done[sw]) {
+      done[sw] = true;
+      os << "  if (!(" << c.tag << ")) EVQ_UPD(" << sw << ", " << OP_ADD_U64 << ", 1ull);\n";
+    }
   }
 }
 
@@ -195,7 +271,8 @@ static void gen_fast_layout(std::ostringstream& os, const KernelShape& shape) {
     if (shape.cols[i].used) os << "  " << fast_ctype(shape.cols[i]) << " c" << i << "[EVQ_RPT];\n";
   os << "  u32 _unused;\n};\n";
   const int ngen = std::max(1, shape.ngen);
-  os << "struct EvqFastPrep {\n  bool general[" << ngen << "];\n  u32 count[" << ngen << "];\n  u32 incl[" << ngen << "];\n};\n";
+  os << "struct EvqFastPrep {\n  bool general[" << ngen << "];\n  u32 count[" << ngen << "];\n  u32 incl[" << ngen << "];\n  u32 mask0[" << ngen
+     << "];\n};\n";
 
   // ---- boundary search of the variable-length columns: 2 consumer barriers per tile, only when a tile needs them
   os << "__device__ __forceinline__ void evq_fast_prep(const EvqTile& T, const EvqScanParams& P, EvqFastScratch* scr, EvqFastPrep& prep) {\n";
@@ -205,7 +282,7 @@ static void gen_fast_layout(std::ostringstream& os, const KernelShape& shape) {
       const ColSig& c = shape.cols[i];
       if (!c.used || c.gen_slot < 0) continue;
       os << "  evq_fast_count<" << c.data_stream << ", " << c.leb_len << ">(T, P, prep.general[" << c.gen_slot << "], prep.count["
-         << c.gen_slot << "]);\n  any = any || prep.general[" << c.gen_slot << "];\n";
+         << c.gen_slot << "], prep.mask0[" << c.gen_slot << "]);\n  any = any || prep.general[" << c.gen_slot << "];\n";
     }
     os << "  if (any) {\n";
     for (size_t i = 0; i < ncols; ++i) {
@@ -219,7 +296,7 @@ static void gen_fast_layout(std::ostringstream& os, const KernelShape& shape) {
       const ColSig& c = shape.cols[i];
       if (!c.used || c.gen_slot < 0) continue;
       os << "    if (prep.general[" << c.gen_slot << "]) evq_fast_write_starts<" << c.data_stream << ", " << c.gen_slot
-         << ">(T, P, scr, prep.count[" << c.gen_slot << "], prep.incl[" << c.gen_slot << "]);\n";
+         << ">(T, P, scr, prep.count[" << c.gen_slot << "], prep.incl[" << c.gen_slot << "], prep.mask0[" << c.gen_slot << "]);\n";
     }
     os << "    evq_cons_sync();\n  }\n";
   }
@@ -291,49 +368,87 @@ static std::string gen_row_functions(const evqgpu_query& q, const KernelShape& s
   }
   os << "}\n";
 
-  const int nstate = (int) q.state_ops.size();
-  if (shape.tier == 1) {
-    if (shape.g1 > 1) {
-      os << "#define EVQ_SIDX(g, st) ((((g) * " << nstate << ") + (st)) * EVQ_NCONS + tid)\n";
-      os << "__device__ __forceinline__ void evq_state_init_slot(u64* sacc, u32 g, u32 tid) {\n";
-      for (int s = 0; s < nstate; ++s) os << "  sacc[EVQ_SIDX(g, " << s << ")] = evq_state_identity<" << q.state_ops[s] << ">();\n";
-      os << "}\n";
-      os << "#define EVQ_UPD(st, op, v) sacc[EVQ_SIDX(g, st)] = evq_state_combine<op>(sacc[EVQ_SIDX(g, st)], (v))\n";
-      os << "__device__ __forceinline__ void evq_accumulate_smem(const EvqRow& row, u64* sacc, u32 g, u32 tid, u32& err) {\n";
-      gen_updates(os, q, shape);
-      os << "}\n#undef EVQ_UPD\n";
-      os << "__device__ __forceinline__ void evq_state_flush_smem(u64* sacc, u32 g, u32 tid, u64* dense_state) {\n";
-      for (int s = 0; s < nstate; ++s) {
-        os << "  {\n    u64 v = sacc[EVQ_SIDX(g, " << s << ")];\n";
-        os << "#pragma unroll\n    for (int o = 16; o > 0; o >>= 1) v = evq_state_combine<" << q.state_ops[s]
-           << ">(v, __shfl_xor_sync(0xffffffffu, v, o));\n";
-        os << "    if (evq_lane() == 0 && v != evq_state_identity<" << q.state_ops[s] << ">()) evq_state_atomic<" << q.state_ops[s]
-           << ">(dense_state + (u64) g * " << nstate << " + " << s << ", v);\n  }\n";
+  // ---- dense tier: group key tuple -> accumulator slot, with the key bounds of this execution as constants
+  if (shape.tier == 1 && shape.g1 > 1) {
+    os << "__device__ __forceinline__ u32 evq_dense_slot(const u64* key, const u32* ktag, u32& err) {\n  u32 slot = 0;\n  bool ok = true;\n";
+    for (size_t i = 0; i < q.group.size(); ++i) {
+      const DenseMap& dm = shape.dense;
+      const bool may_null = dm.key_null_idx[i] != ~0ull;
+      const uint64_t span = dm.key_range[i] - (may_null ? 2 : 1);   // largest non-NULL index
+      os << "  {\n    const u64 d = key[" << i << "] - " << dm.key_min[i] << "ull;\n";
+      if (may_null) {
+        os << "    const u32 idx = ktag[" << i << "] ? " << dm.key_null_idx[i] << "u : (u32) d;\n";
+        os << "    ok = ok && (ktag[" << i << "] || d <= " << span << "ull);\n";
+      } else {
+        os << "    const u32 idx = (u32) d;\n    ok = ok && d <= " << span << "ull;\n";
       }
+      os << "    slot += idx * " << dm.key_stride[i] << "u;\n  }\n";
+    }
+    os << "  if (!ok) {\n    err |= EVQ_ERR_SLOT_RANGE;\n    return ~0u;\n  }\n  return slot;\n}\n";
+  }
+
+  const int nstate = (int) q.state_ops.size();
+  // thread-private -> warp -> global merge of one accumulator word; sum words with a carry partner count the wraps of
+  // every addition on the way (the butterfly leaves the same totals in all lanes)
+  auto gen_flush_word = [&](int w, const std::string& load, const std::string& global_base) {
+    const int op = q.state_ops[w];
+    const int cw = carry_word_of(q, w);
+    os << "  {\n    u64 v = " << load << ";\n";
+    if (cw >= 0) {
+      os << "    u64 c = 0;\n#pragma unroll\n    for (int o = 16; o > 0; o >>= 1) {\n      const u64 n = __shfl_xor_sync(0xffffffffu, v, o);\n"
+            "      c += __shfl_xor_sync(0xffffffffu, c, o);\n      v += n;\n      c += v < n ? 1ull : 0ull;\n    }\n";
+      os << "    if (evq_lane() == 0 && (v | c)) {\n      const u64 old = atomicAdd(" << global_base << " + " << w << ", v);\n"
+            "      if (old + v < v) ++c;\n      if (c) atomicAdd(" << global_base << " + " << cw << ", c);\n    }\n  }\n";
+    } else {
+      os << "#pragma unroll\n    for (int o = 16; o > 0; o >>= 1) v = evq_state_combine<" << op << ">(v, __shfl_xor_sync(0xffffffffu, v, o));\n";
+      os << "    if (evq_lane() == 0 && v != evq_state_identity<" << op << ">()) evq_state_atomic<" << op << ">(" << global_base
+         << " + " << w << ", v);\n  }\n";
+    }
+  };
+  if (shape.tier == 1) {
+    const int nsm = std::max(1, q.nstate_smem);
+    if (shape.g1 > 1) {
+      os << "#define EVQ_SIDX(g, st) ((((g) * " << nsm << ") + (st)) * EVQ_NCONS + tid)\n";
+      os << "__device__ __forceinline__ void evq_state_init_slot(u64* sacc, u32 g, u32 tid) {\n";
+      for (int w = 0; w < nstate; ++w)
+        if (q.state_smem[w] >= 0) os << "  sacc[EVQ_SIDX(g, " << q.state_smem[w] << ")] = evq_state_identity<" << q.state_ops[w] << ">();\n";
+      os << "}\n";
+      for (int w = 0; w < nstate; ++w) os << "#define EVQ_SM_" << w << " " << q.state_smem[w] << "\n";
+      os << "#define EVQ_UPD(st, op, v) sacc[EVQ_SIDX(g, EVQ_SM_##st)] = evq_state_combine<op>(sacc[EVQ_SIDX(g, EVQ_SM_##st)], (v))\n";
+      os << "#define EVQ_UPD_C(st, cw, v) { const u64 _o = sacc[EVQ_SIDX(g, EVQ_SM_##st)]; const u64 _n = _o + (v); "
+            "sacc[EVQ_SIDX(g, EVQ_SM_##st)] = _n; if (_n < _o) atomicAdd(dense_state + (u64) g * " << nstate << " + (cw), 1ull); }\n";
+      os << "__device__ __forceinline__ void evq_accumulate_smem(const EvqRow& row, u64* sacc, u32 g, u32 tid, u64* dense_state, u32& err) {\n";
+      gen_updates(os, q, shape);
+      os << "}\n#undef EVQ_UPD\n#undef EVQ_UPD_C\n";
+      os << "__device__ __forceinline__ void evq_state_flush_smem(u64* sacc, u32 g, u32 tid, u64* dense_state) {\n";
+      for (int w = 0; w < nstate; ++w)
+        if (q.state_smem[w] >= 0)
+          gen_flush_word(w, "sacc[EVQ_SIDX(g, " + std::to_string(q.state_smem[w]) + ")]", "dense_state + (u64) g * " + std::to_string(nstate));
       os << "}\n";
     } else {
       os << "__device__ __forceinline__ void evq_state_init_regs(u64* acc) {\n";
-      for (int s = 0; s < nstate; ++s) os << "  acc[" << s << "] = evq_state_identity<" << q.state_ops[s] << ">();\n";
+      for (int w = 0; w < nstate; ++w)
+        if (q.state_smem[w] >= 0) os << "  acc[" << q.state_smem[w] << "] = evq_state_identity<" << q.state_ops[w] << ">();\n";
       os << "}\n";
-      os << "#define EVQ_UPD(st, op, v) acc[st] = evq_state_combine<op>(acc[st], (v))\n";
-      os << "__device__ __forceinline__ void evq_accumulate_regs(const EvqRow& row, u64* acc, u32& err) {\n";
+      for (int w = 0; w < nstate; ++w) os << "#define EVQ_SM_" << w << " " << q.state_smem[w] << "\n";
+      os << "#define EVQ_UPD(st, op, v) acc[EVQ_SM_##st] = evq_state_combine<op>(acc[EVQ_SM_##st], (v))\n";
+      os << "#define EVQ_UPD_C(st, cw, v) { const u64 _o = acc[EVQ_SM_##st]; const u64 _n = _o + (v); acc[EVQ_SM_##st] = _n; "
+            "if (_n < _o) atomicAdd(dense_state + (cw), 1ull); }\n";
+      os << "__device__ __forceinline__ void evq_accumulate_regs(const EvqRow& row, u64* acc, u64* dense_state, u32& err) {\n";
       gen_updates(os, q, shape);
-      os << "}\n#undef EVQ_UPD\n";
+      os << "}\n#undef EVQ_UPD\n#undef EVQ_UPD_C\n";
       os << "__device__ __forceinline__ void evq_state_flush_regs(u64* acc, u64* dense_state) {\n";
-      for (int s = 0; s < nstate; ++s) {
-        os << "  {\n    u64 v = acc[" << s << "];\n";
-        os << "#pragma unroll\n    for (int o = 16; o > 0; o >>= 1) v = evq_state_combine<" << q.state_ops[s]
-           << ">(v, __shfl_xor_sync(0xffffffffu, v, o));\n";
-        os << "    if (evq_lane() == 0 && v != evq_state_identity<" << q.state_ops[s] << ">()) evq_state_atomic<" << q.state_ops[s]
-           << ">(dense_state + " << s << ", v);\n  }\n";
-      }
+      for (int w = 0; w < nstate; ++w)
+        if (q.state_smem[w] >= 0) gen_flush_word(w, "acc[" + std::to_string(q.state_smem[w]) + "]", "dense_state");
       os << "}\n";
     }
   } else if (shape.tier == 2) {
     os << "#define EVQ_UPD(st, op, v) evq_state_atomic<op>(state + (u64) (st) * cap + slot, (v))\n";
+    os << "#define EVQ_UPD_C(st, cw, v) { const u64 _v = (v); const u64 _o = atomicAdd(state + (u64) (st) * cap + slot, _v); "
+          "if (_o + _v < _v) atomicAdd(state + (u64) (cw) * cap + slot, 1ull); }\n";
     os << "__device__ __forceinline__ void evq_accumulate_global(const EvqRow& row, u64* state, u64 cap, u64 slot, u32& err) {\n";
     gen_updates(os, q, shape);
-    os << "}\n#undef EVQ_UPD\n";
+    os << "}\n#undef EVQ_UPD\n#undef EVQ_UPD_C\n";
   } else if (shape.tier == 3) {
     // scan-only projection: select list evaluated on the rows that pass, packed SVector elements in table order
     os << "__device__ __forceinline__ void evq_project(const EvqRow& row, const EvqScanParams& P, u64 out_row, u32& err) {\n";
@@ -417,14 +532,20 @@ static std::string gen_group_kernels(const evqgpu_query& q, const KernelShape& s
     if (item.agg) {
       const FnInfo& fi = item.agg->info();
       const std::string s0 = "st[" + std::to_string(std::max(0, item.state0)) + "]";
-      const std::string s1 = "st[" + std::to_string(item.state0 + 1) + "]";
+      const std::string s1 = "st[" + std::to_string(std::max(0, item.state_seen)) + "]";
       std::string val;
       switch (fi.fn) {
         case Fn::COUNT: val = "st[0]"; break;                                       // count_get (aggregate.cc:40-42)
         case Fn::SUM: val = from_bits(s0, fi.ret); break;                           // sum_*_get
         case Fn::MIN:
         case Fn::MAX: val = "(" + s1 + " ? " + from_bits(s0, fi.ret) + " : " + from_bits("0ull", fi.ret) + ")"; break;
-        case Fn::MEAN: val = "(evq_f64(" + s0 + ") / (f64) " + s1 + ")"; break;
+        case Fn::MEAN:
+          // uint64 arguments: the exact 128-bit integer sum (carry word : sum word), rounded to double once
+          if (item.state_carry >= 0)
+            val = "((((f64) st[" + std::to_string(item.state_carry) + "]) * 18446744073709551616.0 + (f64) " + s0 + ") / (f64) " + s1 + ")";
+          else
+            val = "(evq_f64(" + s0 + ") / (f64) " + s1 + ")";
+          break;
         default: fail(EVQGPU_ERR_UNSUPPORTED, "aggregate %s", fi.symbol.c_str());
       }
       e2.subst.push_back({item.agg->signature(), {val, "0u"}});
@@ -445,7 +566,7 @@ std::string generate_source(const evqgpu_query& q, const KernelShape& shape) {
   os << "// generated by eventql_b200 csrc/codegen.cc - one fused scan kernel per (plan, column layout)\n";
   os << "#define EVQ_NCONS " << shape.ncons << "\n#define EVQ_NSTAGES " << shape.nstages << "\n#define EVQ_NSTREAMS "
      << shape.nstreams << "\n#define EVQ_TIER " << shape.tier << "\n#define EVQ_G1 " << shape.g1 << "\n#define EVQ_NSTATE "
-     << std::max<size_t>(1, q.state_ops.size()) << "\n#define EVQ_NKEYS " << q.group.size() << "\n#define EVQ_NLEB "
+     << std::max(1, q.nstate_smem) << "\n#define EVQ_NKEYS " << q.group.size() << "\n#define EVQ_NLEB "
      << shape.nleb << "\n#define EVQ_NNULL " << shape.nnull << "\n#define EVQ_HAS_PREP "
      << ((shape.nleb > 0 || shape.nnull > 0) ? 1 : 0) << "\n#define EVQ_MIN_CTAS " << shape.min_ctas << "\n#define EVQ_NGEN "
      << shape.ngen << "\n";

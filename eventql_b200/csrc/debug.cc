@@ -42,6 +42,7 @@ extern "C" int evqgpu_debug_generate(const evqgpu_query_desc* desc, const evqgpu
       c.gen_slot = -1;
       if (s.fast && c.used && c.kind == EVQ_KIND_LEB128 && c.leb_len >= 2) c.gen_slot = s.ngen++;
     }
+    layout_states(q, s);
     const bool groupby = q.flags & EVQGPU_QUERY_GROUPBY;
     std::vector<int> tiers;
     if (!groupby) tiers = {0, 3};
@@ -54,6 +55,17 @@ extern "C" int evqgpu_debug_generate(const evqgpu_query_desc* desc, const evqgpu
       if (t == 1 && !q.group.empty()) {
         s.g1 = 2;
         while ((uint32_t) s.g1 < dense_slots) s.g1 <<= 1;
+      }
+      if (s.tier == 1 && s.g1 > 1) {   // a plausible dense map: every key spans [0, 1], last key fastest
+        uint64_t stride = 1;
+        for (size_t k = q.group.size(); k-- > 0;) {
+          s.dense.key_min[k] = 0;
+          s.dense.key_range[k] = 2;
+          s.dense.key_null_idx[k] = ~0ull;
+          s.dense.key_stride[k] = stride;
+          stride *= 2;
+        }
+        s.dense.slots = stride;
       }
       s.ncons = 256;
       s.nstages = 3;

@@ -40,10 +40,11 @@ struct EvqFastScratch {
 
 // A tile is uniform when all its values have the column's maximal length L; otherwise count this thread's terminators.
 template <int S, int L>
-__device__ __forceinline__ void evq_fast_count(const EvqTile& T, const EvqScanParams& P, bool& general, u32& count) {
+__device__ __forceinline__ void evq_fast_count(const EvqTile& T, const EvqScanParams& P, bool& general, u32& count, u32& mask0) {
   const EvqStreamDesc d = T.desc[S];
   general = d.nbytes != (u32) L * d.nvals;   // the same for every thread of the CTA
   count = 0;
+  mask0 = 0;
   if (!general) return;
   const u8* region = T.stage + P.streams[S].smem_off;
   const u32 tb = d.delta + d.nbytes;
@@ -51,7 +52,11 @@ __device__ __forceinline__ void evq_fast_count(const EvqTile& T, const EvqScanPa
   const u32 per = (nchunks + EVQ_NCONS - 1) / EVQ_NCONS;
   const u32 c0 = T.ctid * per;
   const u32 c1 = c0 + per < nchunks ? c0 + per : nchunks;
-  for (u32 c = c0; c < c1; ++c) count += __popc(evq_leb_chunk_mask(region, c, d.delta, tb));
+  for (u32 c = c0; c < c1; ++c) {
+    const u32 m = evq_leb_chunk_mask(region, c, d.delta, tb);
+    if (c == c0) mask0 = m;   // the common case is one chunk per thread: the write phase reuses its mask
+    count += __popc(m);
+  }
 }
 
 // inclusive warp scan of the counts; the warp totals go to shared memory (read after the next consumer barrier)
@@ -71,10 +76,11 @@ __device__ __forceinline__ u32 evq_fast_publish(const EvqTile& T, EvqFastScratch
 // terminator number j ends value j: every terminator with j % 4 == 3 marks the start of value j + 1 = 4 * ((j + 1) / 4)
 template <int S, int G>
 __device__ __forceinline__ void evq_fast_write_starts(const EvqTile& T, const EvqScanParams& P, EvqFastScratch* scr, u32 count,
-                                                      u32 incl) {
+                                                      u32 incl, u32 mask0) {
   const u32 warp = T.ctid >> 5;
   u32 j = incl - count;
-  for (u32 w = 0; w < warp; ++w) j += scr->wtot[G][w];
+#pragma unroll
+  for (u32 w = 0; w < EVQ_NWARPS; ++w) j += w < warp ? scr->wtot[G][w] : 0u;
   const EvqStreamDesc d = T.desc[S];
   const u8* region = T.stage + P.streams[S].smem_off;
   const u32 tb = d.delta + d.nbytes;
@@ -83,11 +89,13 @@ __device__ __forceinline__ void evq_fast_write_starts(const EvqTile& T, const Ev
   const u32 c0 = T.ctid * per;
   const u32 c1 = c0 + per < nchunks ? c0 + per : nchunks;
   for (u32 c = c0; c < c1; ++c) {
-    u32 m = evq_leb_chunk_mask(region, c, d.delta, tb);
+    u32 m = c == c0 ? mask0 : evq_leb_chunk_mask(region, c, d.delta, tb);
     const u32 n = __popc(m);
     u32 jj = j;
     const u32 skip = (3u - jj) & 3u;
-    for (u32 k = 0; k < skip; ++k) m &= m - 1u;
+    if (skip > 0u) m &= m - 1u;
+    if (skip > 1u) m &= m - 1u;
+    if (skip > 2u) m &= m - 1u;
     jj += skip;
     while (m) {
       const u32 k = __ffs(m) - 1u;
@@ -110,6 +118,12 @@ __device__ __forceinline__ u32 evq_fast_first(const EvqTile& T, int s) {
   return i < n ? i : n;
 }
 
+// 4 bytes at byte offset `off` of a 128-byte aligned stage
+__device__ __forceinline__ u32 evq_stage_u32(const u8* stage, u32 off) {
+  const u32* w = (const u32*) (stage + (off & ~3u));
+  return __funnelshift_r(w[0], w[1], (off & 3u) * 8u);
+}
+
 __device__ __forceinline__ u32 evq_leb_pack2(u32 x) { return (x & 0x7fu) | ((x & 0x7f00u) >> 1); }
 
 __device__ __forceinline__ u32 evq_fixed_mask(u32 len) { return len >= 4u ? 0x7f7f7f7fu : ((1u << (8u * len)) - 1u) & 0x7f7f7f7fu; }
@@ -117,7 +131,7 @@ __device__ __forceinline__ u32 evq_fixed_mask(u32 len) { return len >= 4u ? 0x7f
 // L == 1: value i is byte i
 template <int S>
 __device__ __forceinline__ void evq_fast_ld_leb1(const EvqTile& T, const EvqScanParams& P, u32 (&v)[EVQ_RPT]) {
-  const u32 x = evq_lds_unaligned32(T.stage + P.streams[S].smem_off + T.desc[S].delta + evq_fast_first(T, S));
+  const u32 x = evq_stage_u32(T.stage, P.streams[S].smem_off + T.desc[S].delta + evq_fast_first(T, S));
 #pragma unroll
   for (int i = 0; i < EVQ_RPT; ++i) v[i] = (x >> (8 * i)) & 0xffu;
 }
@@ -126,19 +140,19 @@ __device__ __forceinline__ void evq_fast_ld_leb1(const EvqTile& T, const EvqScan
 template <int S, int G, int L>
 __device__ __forceinline__ void evq_fast_ld_leb32(const EvqTile& T, const EvqScanParams& P, const EvqFastScratch* scr, bool general,
                                                   u32 (&v)[EVQ_RPT]) {
-  const u8* pay = T.stage + P.streams[S].smem_off + T.desc[S].delta;
+  const u32 pay = P.streams[S].smem_off + T.desc[S].delta;
   if (!general) {
-    const u8* p = pay + (u32) L * evq_fast_first(T, S);
+    const u32 p = pay + (u32) L * evq_fast_first(T, S);
 #pragma unroll
     for (int i = 0; i < EVQ_RPT; ++i) {
-      const u32 x = evq_lds_unaligned32(p + L * i) & evq_fixed_mask(L);
+      const u32 x = evq_stage_u32(T.stage, p + L * i) & evq_fixed_mask(L);
       v[i] = L == 2 ? evq_leb_pack2(x) : evq_leb_pack4(x);
     }
   } else {
-    const u8* p = pay + (EVQ_RPT * T.ctid < T.desc[S].nvals ? (u32) scr->start[G][T.ctid] : 0u);
+    u32 p = pay + (EVQ_RPT * T.ctid < T.desc[S].nvals ? (u32) scr->start[G][T.ctid] : 0u);
 #pragma unroll
     for (int i = 0; i < EVQ_RPT; ++i) {
-      const u32 x = evq_lds_unaligned32(p);
+      const u32 x = evq_stage_u32(T.stage, p);
       const u32 tm = ~x & 0x80808080u;
       const u32 low = tm & (0u - tm);            // terminator bit of the first value in the window
       const u32 msk = (low << 1) - 1u;           // every bit up to and including it
@@ -360,19 +374,10 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
         u64 key[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
         u32 ktag[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
         evq_keys(row, key, ktag, err);
-        u64 slot = 0;
-#pragma unroll
-        for (int i = 0; i < EVQ_NKEYS; ++i) {
-          const u64 idx = ktag[i] ? P.key_null_idx[i] : key[i] - P.key_min[i];
-          slot += idx * P.key_stride[i];
-        }
-        if (slot >= P.dense_slots) {
-          err |= EVQ_ERR_SLOT_RANGE;
-        } else {
-          evq_accumulate_smem(row, sacc, (u32) slot, tid, err);
-        }
+        const u32 g = evq_dense_slot(key, ktag, err);
+        if (g != ~0u) evq_accumulate_smem(row, sacc, g, tid, P.dense_state, err);
 #else
-        evq_accumulate_regs(row, racc, err);
+        evq_accumulate_regs(row, racc, P.dense_state, err);
 #endif
       }
 #else   // EVQ_TIER == 2

@@ -287,20 +287,10 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
         u64 key[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
         u32 ktag[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
         evq_keys(row, key, ktag, err);
-        u64 slot = 0;
-#pragma unroll
-        for (int i = 0; i < EVQ_NKEYS; ++i) {
-          const u64 idx = ktag[i] ? P.key_null_idx[i] : key[i] - P.key_min[i];
-          slot += idx * P.key_stride[i];
-        }
-        if (slot >= P.dense_slots) {
-          err |= EVQ_ERR_SLOT_RANGE;
-        } else {
-          const u32 g = (u32) slot;
-          evq_accumulate_smem(row, sacc, g, tid, err);
-        }
+        const u32 g = evq_dense_slot(key, ktag, err);
+        if (g != ~0u) evq_accumulate_smem(row, sacc, g, tid, P.dense_state, err);
 #else
-        evq_accumulate_regs(row, racc, err);
+        evq_accumulate_regs(row, racc, P.dense_state, err);
 #endif
       }
 #elif EVQ_TIER == 2

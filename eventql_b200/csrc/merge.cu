@@ -25,7 +25,9 @@ namespace evq {
 struct MergeOps {
   int nstate;
   int nkeys;
-  int ops[72];   // EVQ_OP_* per state word
+  int ops[72];        // EVQ_OP_* per state word
+  int carry_of[72];   // for a carry word: the sum word whose 64-bit wraps it counts (exact 128-bit sums of mean()), else -1
+  int carry_at[72];   // for a sum word: its carry word, else -1
 };
 
 __device__ __forceinline__ u64 merge_identity(int op) {
@@ -70,9 +72,20 @@ __device__ __forceinline__ void merge_atomic(int op, u64* addr, u64 v) {
 __global__ void k_merge_dense(u64* __restrict__ state, const u64* __restrict__ gathered, int nranks, u64 nwords, MergeOps mo) {
   const u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nwords) return;
-  const int op = mo.ops[i % mo.nstate];
+  const int w = (int) (i % mo.nstate);
+  const int op = mo.ops[w];
   u64 acc = gathered[i];
   for (int r = 1; r < nranks; ++r) acc = merge_combine(op, acc, gathered[(u64) r * nwords + i]);
+  if (mo.carry_of[w] >= 0) {
+    // add the wraps of re-summing the partner word in the same rank order
+    const u64 j = i - w + mo.carry_of[w];
+    u64 lo = gathered[j];
+    for (int r = 1; r < nranks; ++r) {
+      const u64 n = gathered[(u64) r * nwords + j];
+      lo += n;
+      acc += lo < n ? 1ull : 0ull;
+    }
+  }
   state[i] = acc;
 }
 
@@ -139,7 +152,14 @@ __global__ void k_merge_insert(EvqHashTable H, MergeOps mo, const u64* __restric
     }
     for (int s = 0; s < mo.nstate; ++s) {
       const u64 v = src[NK + 1 + s];
-      if (v != merge_identity(mo.ops[s])) merge_atomic(mo.ops[s], H.state + (u64) s * H.cap + slot, v);
+      if (mo.carry_at[s] >= 0) {
+        if (v) {
+          const u64 old = atomicAdd(H.state + (u64) s * H.cap + slot, v);
+          if (old + v < v) atomicAdd(H.state + (u64) mo.carry_at[s] * H.cap + slot, 1ull);
+        }
+      } else if (v != merge_identity(mo.ops[s])) {
+        merge_atomic(mo.ops[s], H.state + (u64) s * H.cap + slot, v);
+      }
     }
   }
 }
@@ -156,7 +176,12 @@ static MergeOps merge_ops_of(const evqgpu_query& q) {
   mo.nstate = (int) q.state_ops.size();
   mo.nkeys = (int) q.group.size();
   if (mo.nstate > 72) fail(EVQGPU_ERR_UNSUPPORTED, "merge: more than 72 aggregate state words");
-  for (int i = 0; i < mo.nstate; ++i) mo.ops[i] = q.state_ops[i];
+  for (int i = 0; i < 72; ++i) mo.carry_of[i] = mo.carry_at[i] = -1;
+  for (int i = 0; i < mo.nstate; ++i) {
+    mo.ops[i] = q.state_ops[i];
+    mo.carry_of[i] = q.state_carry_of[i];
+    if (q.state_carry_of[i] >= 0) mo.carry_at[q.state_carry_of[i]] = i;
+  }
   return mo;
 }
 
@@ -286,6 +311,20 @@ void merge_query(evqgpu_query& q) {
   }
   if (!(q.flags & EVQGPU_QUERY_PARTIAL))
     fail(EVQGPU_ERR_ARG, "evqgpu_query_merge: the plan was not created with EVQGPU_QUERY_PARTIAL");
+  // the state layout depends on which columns are optional: all ranks must have arrived at the same one
+  {
+    std::string sig = std::to_string(q.shape.tier) + "/" + std::to_string(q.shape.g1) + "/";
+    for (size_t i = 0; i < q.state_keys.size(); ++i) sig += q.state_keys[i] + "#" + std::to_string(q.state_ops[i]) + ";";
+    if (sig != q.merge_checked_layout) {
+      uint64_t h = 1469598103934665603ull;
+      for (unsigned char ch : sig) h = (h ^ ch) * 1099511628211ull;
+      std::vector<uint64_t> all = comm_all_gather_host(q.ctx, std::vector<uint64_t>{h});
+      for (uint64_t o : all)
+        if (o != h) fail(EVQGPU_ERR_ARG, "evqgpu_query_merge: ranks disagree on the aggregate state layout (partitions differ in "
+                         "which columns are optional, or in the number of groups strategy)");
+      q.merge_checked_layout = sig;
+    }
+  }
   if (q.shape.tier == 1) merge_dense(q);
   else merge_hash(q);
   q.merged = true;

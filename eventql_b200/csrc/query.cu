@@ -152,7 +152,7 @@ static size_t header_bytes(const KernelShape& s) {
 
 static size_t acc_bytes(const evqgpu_query& q, const KernelShape& s) {
   if (s.tier != 1 || s.g1 <= 1) return 0;
-  return (size_t) s.g1 * q.state_ops.size() * s.ncons * 8;
+  return (size_t) s.g1 * q.nstate_smem * s.ncons * 8;
 }
 
 }  // namespace evq
@@ -190,7 +190,6 @@ void query_intake(evqgpu_query* q, const evqgpu_query_desc* desc) {
     q->group.push_back(std::move(g));
   }
   const bool groupby = q->flags & EVQGPU_QUERY_GROUPBY;
-  q->state_ops.push_back(OP_ADD_U64);   // word 0: rows per group
   for (uint32_t i = 0; i < desc->num_select; ++i) {
     SelectItem item;
     item.expr = parse_program(desc->select[i]);
@@ -199,26 +198,9 @@ void query_intake(evqgpu_query* q, const evqgpu_query_desc* desc) {
       fail(EVQGPU_ERR_UNSUPPORTED, "select item %u: result type is outside the numeric device path", i);
     item.agg = find_aggregate(item.expr.get());
     if (item.agg && !groupby) fail(EVQGPU_ERR_ARG, "aggregate call in a scan-only plan");
-    if (item.agg) {
-      const FnInfo& fi = item.agg->info();
-      const int words = state_words_of(fi);
-      if (words > 0) {
-        item.state0 = (int) q->state_ops.size();
-        const int ty = fi.args[0];
-        if (fi.fn == Fn::SUM) q->state_ops.push_back(ty == EVQ_FLOAT64 ? OP_ADD_F64 : OP_ADD_U64);
-        else if (fi.fn == Fn::MEAN) { q->state_ops.push_back(OP_ADD_F64); q->state_ops.push_back(OP_ADD_U64); }
-        else {
-          const bool mx = fi.fn == Fn::MAX;
-          q->state_ops.push_back(ty == EVQ_INT64 ? (mx ? OP_MAX_I64 : OP_MIN_I64)
-                                 : ty == EVQ_FLOAT64 ? (mx ? OP_MAX_F64 : OP_MIN_F64) : (mx ? OP_MAX_U64 : OP_MIN_U64));
-          q->state_ops.push_back(OP_ADD_U64);
-        }
-      } else {
-        item.state0 = 0;
-      }
+    if (item.agg)
       for (const auto& a : item.agg->args)
         if (find_aggregate(a.get())) fail(EVQGPU_ERR_ARG, "nested aggregate call");
-    }
     q->select.push_back(std::move(item));
   }
   if (groupby)
@@ -566,6 +548,7 @@ void emit_results(evqgpu_query& q) {
 static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std::vector<evqgpu_table*>& tables, bool sync) {
   evqgpu_ctx* ctx = q.ctx;
   KernelShape s = shape_of_plans(q, plans);
+  layout_states(q, s);
   uint64_t total_rows = 0;
   for (auto* t : tables) total_rows += t->num_rows;
 
@@ -590,11 +573,12 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
     if (dense) {
       s.g1 = g1_for(dm.slots);
       // thread-private accumulators must fit next to the pipeline stages
-      const size_t acc = (size_t) s.g1 * q.state_ops.size() * (s.fast ? 256 : 128) * 8;
+      const size_t acc = (size_t) s.g1 * q.nstate_smem * (s.fast ? 256 : 128) * 8;
       if (s.g1 > 64 || acc > 96 * 1024) dense = false;
     }
     if (!dense) { s.tier = 2; s.g1 = 1; }
   }
+  if (s.tier == 1 && s.g1 > 1) s.dense = dm;
   fit_shape(q, s, plans);
   q.shape = s;
   q.dense = dm;

@@ -17,7 +17,10 @@ enum { OP_ADD_U64 = 0, OP_ADD_F64 = 1, OP_MIN_U64 = 2, OP_MAX_U64 = 3, OP_MIN_I6
 struct SelectItem {
   ExprPtr expr;
   const Expr* agg = nullptr;   // the (single) aggregate call inside expr, if any
-  int state0 = -1;             // first state word of the aggregate
+  // aggregate state words (indices into evqgpu_query::state_ops; decided per execution by layout_states()):
+  int state0 = -1;             // count: rows word; sum: the sum; min/max: the extremum; mean: the sum (u64 low word or f64)
+  int state_seen = -1;         // min/max/mean: number of non-NULL arguments (the rows word when the argument cannot be NULL)
+  int state_carry = -1;        // mean over a uint64 argument: wraps of the 64-bit sum word (exact 128-bit integer sum)
 };
 
 // how one input column is laid out on the device (part of the kernel's specialisation key)
@@ -34,6 +37,12 @@ struct ColSig {
   int gen_slot = -1;       // fast kernel: index among the LEB128 columns that may need the boundary search (leb_len >= 2)
 };
 
+struct DenseMap {
+  uint64_t key_min[EVQ_MAX_KEYS] = {0}, key_stride[EVQ_MAX_KEYS] = {0}, key_null_idx[EVQ_MAX_KEYS] = {0},
+           key_range[EVQ_MAX_KEYS] = {0};
+  uint64_t slots = 1;
+};
+
 struct KernelShape {
   std::vector<ColSig> cols;
   int tier = 1;        // 0 count pass, 3 projection pass (scan-only); 1 dense / single group; 2 global hash table
@@ -44,12 +53,7 @@ struct KernelShape {
   int nstreams = 0, nleb = 0, nnull = 0;
   bool fast = false;   // all referenced columns are required: kernels/evq_scan_fast.cuh (4 consecutive rows per thread)
   int ngen = 0;        // fast kernel: LEB128 columns with leb_len >= 2
-};
-
-struct DenseMap {
-  uint64_t key_min[EVQ_MAX_KEYS] = {0}, key_stride[EVQ_MAX_KEYS] = {0}, key_null_idx[EVQ_MAX_KEYS] = {0},
-           key_range[EVQ_MAX_KEYS] = {0};
-  uint64_t slots = 1;
+  DenseMap dense;      // tier 1 with g1 > 1: the key -> slot map is baked into the kernel text as constants
 };
 
 // parameter block of the emit kernel (mirrors the struct spelled in the generated text)
@@ -82,6 +86,11 @@ struct evqgpu_query {
   std::vector<evq::ExprPtr> group;
   std::vector<evq::SelectItem> select;
   std::vector<int> state_ops;       // op of every aggregate state word; word 0 = rows per group
+  std::vector<std::string> state_keys;   // what the word accumulates ("sum:<expr>" ...): equal keys share one word
+  std::vector<int> state_carry_of;  // for a carry word: index of the sum word whose wraps it counts, else -1
+  std::vector<int> state_smem;      // index of the word among the thread-private accumulators (-1 for carry words)
+  int nstate_smem = 0;
+  std::string merge_checked_layout;  // state layout all ranks were last verified to share
   uint64_t expected_groups = 0;
   std::vector<bool> col_used;
 
@@ -117,7 +126,7 @@ struct evqgpu_query {
 namespace evq {
 // codegen.cc
 std::string generate_source(const evqgpu_query& q, const KernelShape& shape);
-int state_words_of(const FnInfo& fi);
+void layout_states(evqgpu_query& q, const KernelShape& shape);
 // query.cu
 void emit_results(evqgpu_query& q);
 void finish_query(evqgpu_query& q);
