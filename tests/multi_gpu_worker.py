@@ -1,0 +1,87 @@
+"""Run under torchrun (one rank per GPU): partial aggregates on every rank, merged over NVLink with NCCL
+(evqgpu_query_merge), compared on rank 0 with the oracle on the whole table.  Launched by tests/test_multi_gpu.py."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from eventql_b200 import capi, plan as P, sharding  # noqa: E402
+from oracle import evq_oracle as O  # noqa: E402
+from tests import common as T  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = capi.Context(local)
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt = torch.frombuffer(bytearray(capi.Context.comm_unique_id()), dtype=torch.uint8).cuda()
+    dist.broadcast(idt, 0)
+    ctx.comm_init(idt.cpu().numpy().tobytes(), rank, world)
+
+    nparts, rows = 2 * world + 1, 150_000
+    cases = []
+    spec = T.lineitem_spec()
+    cases.append(("q1_dense_required", spec, T.q1(spec)[1]))
+    cases.append(("q6_single_group", spec, T.q6(spec)[1]))
+    spec = T.lineitem_spec(null_every=7)
+    cases.append(("q1_dense_optional", spec, T.q1(spec)[1]))
+    spec = T.events_spec(40_000)
+    c, names = T.cols_of(spec)
+    cases.append(("highcard_hash", spec, P.QueryPlan(names, [c["ekey"], P.call("count", P.lit(1)), P.call("sum", c["v"]), P.call("mean", c["v"]),
+                                                            P.call("min", c["v"]), P.call("max", c["v"])], where=c["v"] >= 0, group=[c["ekey"]])))
+    spec = T.mixed_spec(null_every=5)
+    c, names = T.cols_of(spec)
+    cases.append(("minmax_float_dense", spec, P.QueryPlan(names, [c["bo"], P.call("count", P.lit(1)), P.call("sum", c["f"]), P.call("min", c["f"]),
+                                                                 P.call("max", c["a"]), P.call("mean", c["big"]), P.call("sum", c["big"])],
+                                                          where=c["b"] >= 0, group=[c["bo"]])))
+    failures = []
+    for name, spec, plan in cases:
+        ts = name == "timeseries"
+        mine = sharding.assign_partitions(nparts, rank, world)
+        dev_spec = [s for s in spec if not (s["encoding"] == P.ENC_UINT32_BITPACKED and s.get("null_every"))]
+        tables = [ctx.synthesize(rows, dev_spec, row_offset=p * rows) for p in mine]
+        plan.flags |= P.QUERY_PARTIAL
+        q = ctx.query(plan)
+        for _ in range(2):          # twice: the second run reuses the cached kernels and the agreed dense slot map
+            q.execute(tables)
+            q.merge()
+            part = q.rows()
+        stats = q.stats()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, part)
+        if rank == 0:
+            cols = []
+            n = rows * nparts
+            for s in spec:
+                vs, ns = zip(*[T.synth_values(s, rows, row_offset=p * rows) for p in range(nparts)])
+                cols.append(O.Vec(T.sql_type_of(s), np.concatenate(vs), np.concatenate(ns).astype(np.uint8)))
+            want = O.run_query_on(cols, n, plan).rows()
+            if stats["strategy"] == 1:
+                got_sets = gathered            # dense tier: every rank ends with the full result
+            else:
+                got_sets = [sum(gathered, [])]  # hash tier: results stay distributed, each group on exactly one rank
+            for got in got_sets:
+                ok, why = T.rows_equal(got, want)
+                if not ok:
+                    failures.append("%s: %s" % (name, why))
+            print("case %-22s tier=%d groups=%d %s" % (name, stats["strategy"], len(want), "ok" if not failures else failures[-1]), flush=True)
+        q.close()
+        for t in tables:
+            t.close()
+    flag = torch.tensor([len(failures)], device="cuda")
+    dist.broadcast(flag, 0)
+    ctx.close()
+    dist.destroy_process_group()
+    sys.exit(1 if int(flag.item()) else 0)
+
+
+if __name__ == "__main__":
+    main()
