@@ -62,7 +62,9 @@ def main():
             n = rows * nparts
             for s in spec:
                 vs, ns = zip(*[T.synth_values(s, rows, row_offset=p * rows) for p in range(nparts)])
-                cols.append(O.Vec(T.sql_type_of(s), np.concatenate(vs), np.concatenate(ns).astype(np.uint8)))
+                v, st = np.concatenate(vs), T.sql_type_of(s)
+                v = v.view(np.float64) if st == P.FLOAT64 else (v.astype(bool) if st == P.BOOL else v)
+                cols.append(O.Vec(st, v, np.concatenate(ns).astype(np.uint8)))
             want = O.run_query_on(cols, n, plan).rows()
             if stats["strategy"] == 1:
                 got_sets = gathered            # dense tier: every rank ends with the full result
