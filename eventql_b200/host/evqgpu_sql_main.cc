@@ -1,0 +1,132 @@
+// evqgpu_sql - drives the drop-in operators the way the reference's sql_tests runner drives its own
+// (test/sql_tests.cc:232-274: provider -> plan -> execute -> pull batches -> print), for the named query shapes.
+// The query trees are built by hand in the exact shape QueryPlanBuilder::buildGroupBy produces (runtime/queryplanbuilder.cc:
+// 439-540): the scan's select list holds bare column references appended by getComputedColumnIndex, the GroupByNode's
+// expressions index that list.
+//
+//   evqgpu_sql q1    <lineitem partition .cst>...     Q1-style GROUP BY flag, status (C3)
+//   evqgpu_sql q6    <lineitem .cst>...               Q6-style global aggregate (C2)
+//   evqgpu_sql count <file.cst> <column>              select count(1), sum(c), min(c), max(c), mean(c) ... where c > 0
+//   evqgpu_sql scan  <file.cst> <column>              select <column> from t        (FastCSTableScan alone)
+//
+// Output: one line per row, ';' separated (uint64 decimal, float64 %.17g, bool true|false, NULL).
+#include <stdio.h>
+#include <string.h>
+#include "gpu_operators.h"
+
+using namespace csql;
+using namespace evql_b200;
+
+static const char* tname(SType t) {
+  static const char* n[] = {"nil", "uint64", "int64", "float64", "bool", "string", "timestamp64"};
+  return n[(int) t];
+}
+
+static ExprRef call(const std::string& name, SType ret, std::vector<ExprRef> args) {
+  std::string sym = name + "#" + tname(ret) + "/";
+  for (const auto& a : args) sym += std::string(tname(name == "count" ? SType::NIL : a->getReturnType())) + ";";
+  return ExprRef(new CallExpressionNode(sym, ret, std::move(args)));
+}
+static ExprRef col(size_t i, SType t = SType::UINT64) { return ExprRef(new ColumnReferenceNode(i, t)); }
+static ExprRef u(uint64_t v) { return LiteralExpressionNode::u64(v); }
+static ExprRef cmp(const char* op, ExprRef a, ExprRef b) { return call(op, SType::BOOL, {a, b}); }
+static ExprRef land(ExprRef a, ExprRef b) { return call("logical_and", SType::BOOL, {a, b}); }
+static ExprRef arith(const char* op, ExprRef a, ExprRef b) { return call(op, SType::UINT64, {a, b}); }
+static ExprRef count1() { return call("count", SType::UINT64, {call("to_nil", SType::NIL, {u(1)})}); }
+static ExprRef agg(const char* fn, ExprRef a, SType ret = SType::UINT64) { return call(fn, ret, {a}); }
+static SelectRef sel(ExprRef e) { return SelectRef(new SelectListNode(std::move(e))); }
+
+static int pull(TableExpression* te) {
+  ReturnCode rc = te->execute();
+  if (!rc.isSuccess()) { printf("ERROR!\n%s\n", rc.getMessage().c_str()); return 1; }
+  const size_t nc = te->getColumnCount();
+  std::vector<SVector> cols;
+  for (size_t i = 0; i < nc; ++i) cols.emplace_back(te->getColumnType(i));
+  for (;;) {
+    for (auto& c : cols) c.clear();
+    size_t n = 0;
+    rc = te->nextBatch(cols.data(), &n);
+    if (!rc.isSuccess()) { printf("ERROR!\n%s\n", rc.getMessage().c_str()); return 1; }
+    if (n == 0) break;
+    for (size_t r = 0; r < n; ++r) {
+      std::string line;
+      for (size_t i = 0; i < nc; ++i) {
+        const SType t = te->getColumnType(i);
+        const uint8_t* p = (const uint8_t*) cols[i].getData() + r * sql_sizeof_fixed(t);
+        char buf[64];
+        if (i) line += ";";
+        if (t == SType::BOOL) { line += (p[1] & STAG_NULL) ? "NULL" : (p[0] ? "true" : "false"); continue; }
+        if (p[8] & STAG_NULL) { line += "NULL"; continue; }
+        uint64_t v; memcpy(&v, p, 8);
+        if (t == SType::FLOAT64) { double d; memcpy(&d, p, 8); snprintf(buf, sizeof(buf), "%.17g", d); }
+        else if (t == SType::INT64) snprintf(buf, sizeof(buf), "%lld", (long long) v);
+        else snprintf(buf, sizeof(buf), "%llu", (unsigned long long) v);
+        line += buf;
+      }
+      puts(line.c_str());
+    }
+  }
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 3) { fprintf(stderr, "usage: evqgpu_sql q1|q6|count|scan <file.cst>... [column]\n"); return 2; }
+  const std::string mode = argv[1];
+  try {
+    GpuContext gpu(0);
+    const SType U = SType::UINT64;
+    if (mode == "q1" || mode == "q6") {
+      std::vector<std::string> files(argv + 2, argv + argc);
+      GpuTableProvider provider(&gpu, "lineitem", files);
+      std::shared_ptr<GroupByNode> node;
+      if (mode == "q1") {
+        // input columns in first-reference order: WHERE columns first, then those pulled in by GROUP BY / select
+        std::vector<std::pair<std::string, SType>> in = {{"shipdate", U}, {"quantity", U}, {"price", U}, {"discount", U}, {"tax", U},
+                                                         {"flag", U}, {"status", U}};
+        ExprRef where = land(land(land(land(cmp("lte", col(0), u(10471)), cmp("gt", col(1), u(0))), cmp("gt", col(2), u(0))),
+                                  cmp("gte", col(3), u(0))), cmp("gte", col(4), u(0)));
+        // scan select list = bare columns in the order the GROUP BY / select resolution asked for them
+        std::vector<SelectRef> scan_sel = {sel(col(5)), sel(col(6)), sel(col(1)), sel(col(2)), sel(col(3)), sel(col(4))};
+        auto scan = std::make_shared<SequentialScanNode>("lineitem", in, scan_sel, where);
+        // GroupByNode space: 0 flag, 1 status, 2 quantity, 3 price, 4 discount, 5 tax
+        ExprRef disc = arith("mul", col(3), arith("sub", u(100), col(4)));
+        std::vector<SelectRef> gsel = {sel(col(0)), sel(col(1)), sel(count1()), sel(agg("sum", col(2))), sel(agg("sum", col(3))),
+                                       sel(agg("sum", disc)), sel(agg("sum", arith("mul", disc, arith("add", u(100), col(5))))),
+                                       sel(agg("sum", col(4))), sel(agg("mean", col(2), SType::FLOAT64)),
+                                       sel(agg("mean", col(3), SType::FLOAT64)), sel(agg("mean", col(4), SType::FLOAT64))};
+        node = std::make_shared<GroupByNode>(gsel, std::vector<ExprRef>{col(0), col(1)}, scan);
+      } else {
+        std::vector<std::pair<std::string, SType>> in = {{"shipdate", U}, {"discount", U}, {"quantity", U}, {"price", U}};
+        ExprRef where = land(land(land(land(land(cmp("gte", col(0), u(8766)), cmp("lt", col(0), u(9131))), cmp("gte", col(1), u(5))),
+                                       cmp("lte", col(1), u(7))), cmp("lt", col(2), u(24))), cmp("gt", col(3), u(0)));
+        std::vector<SelectRef> scan_sel = {sel(col(3)), sel(col(1))};
+        auto scan = std::make_shared<SequentialScanNode>("lineitem", in, scan_sel, where);
+        std::vector<SelectRef> gsel = {sel(count1()), sel(agg("sum", arith("mul", col(0), col(1))))};
+        node = std::make_shared<GroupByNode>(gsel, std::vector<ExprRef>{}, scan);
+      }
+      auto te = provider.buildGroupByExpression(node);
+      if (!te) { fprintf(stderr, "provider declined the plan\n"); return 1; }
+      return pull(te.get());
+    }
+    if ((mode == "count" || mode == "scan") && argc >= 4) {
+      GpuTableProvider provider(&gpu, "t", {argv[2]});
+      std::vector<std::pair<std::string, SType>> in = {{argv[3], U}};
+      if (mode == "scan") {
+        auto scan = std::make_shared<SequentialScanNode>("t", in, std::vector<SelectRef>{sel(col(0))}, nullptr);
+        auto te = provider.buildSequentialScan(scan);
+        return pull(te.get());
+      }
+      auto scan = std::make_shared<SequentialScanNode>("t", in, std::vector<SelectRef>{sel(col(0))}, cmp("gt", col(0), u(0)));
+      std::vector<SelectRef> gsel = {sel(count1()), sel(agg("sum", col(0))), sel(agg("min", col(0))), sel(agg("max", col(0))),
+                                     sel(agg("mean", col(0), SType::FLOAT64))};
+      auto node = std::make_shared<GroupByNode>(gsel, std::vector<ExprRef>{}, scan);
+      auto te = provider.buildGroupByExpression(node);
+      return pull(te.get());
+    }
+    fprintf(stderr, "bad arguments\n");
+    return 2;
+  } catch (const std::exception& e) {
+    printf("ERROR!\n%s\n", e.what());
+    return 1;
+  }
+}

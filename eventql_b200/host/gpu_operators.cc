@@ -1,0 +1,225 @@
+// gpu_operators.cc - see gpu_operators.h.  Host logic only: plan translation, file mapping, the pull protocol.
+#include "gpu_operators.h"
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <stdexcept>
+
+using namespace csql;
+
+namespace evql_b200 {
+
+static std::string lastError() { return evqgpu_last_error(); }
+
+GpuContext::GpuContext(int device) : ctx_(nullptr) {
+  if (evqgpu_ctx_create(device, 0, &ctx_) != EVQGPU_OK) throw std::runtime_error("evqgpu_ctx_create: " + lastError());
+}
+
+GpuContext::~GpuContext() {
+  for (auto& t : tables_) {
+    evqgpu_table_destroy(t.second.table);
+    munmap(t.second.addr, t.second.len);
+  }
+  evqgpu_ctx_destroy(ctx_);
+}
+
+evqgpu_table* GpuContext::openTable(const std::string& filename) {
+  auto it = tables_.find(filename);
+  if (it != tables_.end()) return it->second.table;
+  const int fd = open(filename.c_str(), O_RDONLY);
+  if (fd < 0) throw std::runtime_error("cannot open " + filename);
+  struct stat st;
+  if (fstat(fd, &st) != 0 || st.st_size == 0) { close(fd); throw std::runtime_error("cannot stat " + filename); }
+  void* addr = mmap(nullptr, (size_t) st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+  close(fd);
+  if (addr == MAP_FAILED) throw std::runtime_error("cannot map " + filename);
+  evqgpu_table* t = nullptr;
+  if (evqgpu_table_open(ctx_, addr, (uint64_t) st.st_size, &t) != EVQGPU_OK) {
+    munmap(addr, (size_t) st.st_size);
+    throw std::runtime_error("evqgpu_table_open(" + filename + "): " + lastError());
+  }
+  tables_[filename] = Mapped{addr, (size_t) st.st_size, t};
+  return t;
+}
+
+evqgpu_expr Program::view() const {
+  evqgpu_expr e;
+  e.code = code.data();
+  e.len = (uint32_t) code.size();
+  e.strings = strings.empty() ? nullptr : strings.data();
+  e.strings_len = (uint32_t) strings.size();
+  return e;
+}
+
+static void emit(const ExprRef& e, const std::vector<ExprRef>* column_map, Program* out) {
+  evqgpu_insn in;
+  memset(&in, 0, sizeof(in));
+  in.type = (uint8_t) e->getReturnType();
+  if (auto* c = dynamic_cast<const ColumnReferenceNode*>(e.get())) {
+    if (column_map) {
+      // GroupByNode column space: index into the scan's select list (sql/qtree/SequentialScanNode.cc:216-245)
+      if (c->columnIndex() >= column_map->size()) throw std::runtime_error("column reference out of range");
+      emit((*column_map)[c->columnIndex()], nullptr, out);
+      return;
+    }
+    in.op = EVQ_X_INPUT;
+    in.arg = (uint32_t) c->columnIndex();
+  } else if (auto* l = dynamic_cast<const LiteralExpressionNode*>(e.get())) {
+    in.op = EVQ_X_LITERAL;
+    if (l->getReturnType() == SType::STRING) {
+      in.imm = ((uint64_t) out->strings.size() << 32) | (uint64_t) l->str().size();
+      out->strings += l->str();
+    } else {
+      in.imm = l->bits();
+    }
+  } else if (auto* call = dynamic_cast<const CallExpressionNode*>(e.get())) {
+    for (const auto& a : call->arguments()) emit(a, column_map, out);
+    const int fid = evqgpu_function_lookup(call->getSymbol().c_str());
+    if (fid < 0) throw std::runtime_error("method not available on the device path: " + call->getSymbol());
+    in.op = EVQ_X_CALL;
+    in.nargs = (uint16_t) call->arguments().size();
+    in.arg = (uint32_t) fid;
+  } else if (auto* iff = dynamic_cast<const IfExpressionNode*>(e.get())) {
+    emit(iff->conditional(), column_map, out);
+    emit(iff->trueBranch(), column_map, out);
+    emit(iff->falseBranch(), column_map, out);
+    in.op = EVQ_X_IF;
+    in.nargs = 3;
+  } else {
+    throw std::runtime_error("unsupported expression node");
+  }
+  out->code.push_back(in);
+}
+
+Program translate(const ExprRef& expr, const std::vector<ExprRef>* column_map) {
+  Program p;
+  if (expr) emit(expr, column_map, &p);
+  return p;
+}
+
+// ---- pull protocol ---------------------------------------------------------------------------------------------------
+
+GpuQueryExpression::~GpuQueryExpression() {
+  if (query_) evqgpu_query_destroy(query_);
+}
+
+ReturnCode GpuQueryExpression::run(const evqgpu_query_desc& desc) {
+  try {
+    std::vector<evqgpu_table*> tables;
+    for (const auto& f : filenames_) tables.push_back(gpu_->openTable(f));
+    if (query_) { evqgpu_query_destroy(query_); query_ = nullptr; }
+    if (evqgpu_query_create(gpu_->handle(), &desc, &query_) != EVQGPU_OK) return ReturnCode::error("ERUNTIME", lastError());
+    if (evqgpu_query_execute(query_, tables.data(), (uint32_t) tables.size()) != EVQGPU_OK)
+      return ReturnCode::error("ERUNTIME", lastError());
+    if (evqgpu_query_num_rows(query_, &num_rows_) != EVQGPU_OK) return ReturnCode::error("ERUNTIME", lastError());
+    cursor_ = 0;
+    staging_.assign(getColumnCount(), std::vector<uint8_t>(kOutputBatchSize * 9));
+    return ReturnCode::success();
+  } catch (const std::exception& e) {
+    return ReturnCode::error("ERUNTIME", e.what());
+  }
+}
+
+ReturnCode GpuQueryExpression::nextBatch(SVector* columns, size_t* len) {
+  *len = 0;
+  if (!query_) return ReturnCode::error("ERUNTIME", "nextBatch before execute");
+  if (cursor_ >= num_rows_) return ReturnCode::success();   // EOF: *len == 0
+  std::vector<void*> ptrs;
+  for (auto& s : staging_) ptrs.push_back(s.data());
+  uint64_t got = 0;
+  if (evqgpu_query_fetch(query_, cursor_, kOutputBatchSize, ptrs.data(), &got) != EVQGPU_OK)
+    return ReturnCode::error("ERUNTIME", lastError());
+  for (size_t i = 0; i < staging_.size(); ++i)
+    columns[i].append(staging_[i].data(), got * sql_sizeof_fixed(getColumnType(i)));   // already in the packed SVector encoding
+  cursor_ += got;
+  *len = (size_t) got;
+  return ReturnCode::success();
+}
+
+size_t GpuQueryExpression::getColumnCount() const { return query_ ? evqgpu_query_num_columns(query_) : 0; }
+SType GpuQueryExpression::getColumnType(size_t idx) const { return (SType) evqgpu_query_column_type(query_, (uint32_t) idx); }
+
+// ---- FastCSTableScan ---------------------------------------------------------------------------------------------------
+
+GpuCSTableScan::GpuCSTableScan(GpuContext* gpu, std::shared_ptr<SequentialScanNode> stmt, const std::string& cstable_filename)
+    : GpuQueryExpression(gpu, {cstable_filename}), stmt_(std::move(stmt)) {}
+
+ReturnCode GpuCSTableScan::execute() {
+  try {
+    const std::vector<std::string> cols = stmt_->selectedColumns();
+    std::vector<const char*> names;
+    for (const auto& c : cols) names.push_back(c.c_str());
+    Program where = translate(stmt_->whereExpression());
+    std::vector<Program> sel;
+    for (const auto& s : stmt_->selectList()) sel.push_back(translate(s->expression()));
+    std::vector<evqgpu_expr> selv;
+    for (const auto& p : sel) selv.push_back(p.view());
+    evqgpu_query_desc d;
+    memset(&d, 0, sizeof(d));
+    d.struct_size = sizeof(d);
+    d.flags = 0;
+    d.num_input_columns = (uint32_t) names.size();
+    d.input_columns = names.data();
+    d.where = where.view();
+    d.num_select = (uint32_t) selv.size();
+    d.select = selv.data();
+    return run(d);
+  } catch (const std::exception& e) {
+    return ReturnCode::error("ERUNTIME", e.what());
+  }
+}
+
+// ---- GroupByExpression over a scan --------------------------------------------------------------------------------------
+
+GpuGroupByExpression::GpuGroupByExpression(GpuContext* gpu, std::shared_ptr<GroupByNode> node, std::vector<std::string> partition_files)
+    : GpuQueryExpression(gpu, std::move(partition_files)), node_(std::move(node)) {}
+
+ReturnCode GpuGroupByExpression::execute() {
+  try {
+    auto scan = node_->inputTable();
+    const std::vector<std::string> cols = scan->selectedColumns();
+    std::vector<const char*> names;
+    for (const auto& c : cols) names.push_back(c.c_str());
+    // the two column-index spaces: group / select expressions reference the scan's select list
+    std::vector<ExprRef> column_map;
+    for (const auto& s : scan->selectList()) column_map.push_back(s->expression());
+    Program where = translate(scan->whereExpression());
+    std::vector<Program> grp, sel;
+    for (const auto& g : node_->groupExpressions()) grp.push_back(translate(g, &column_map));
+    for (const auto& s : node_->selectList()) sel.push_back(translate(s->expression(), &column_map));
+    std::vector<evqgpu_expr> grpv, selv;
+    for (const auto& p : grp) grpv.push_back(p.view());
+    for (const auto& p : sel) selv.push_back(p.view());
+    evqgpu_query_desc d;
+    memset(&d, 0, sizeof(d));
+    d.struct_size = sizeof(d);
+    d.flags = EVQGPU_QUERY_GROUPBY | (node_->isPartialAggregation() ? EVQGPU_QUERY_PARTIAL : 0);
+    d.num_input_columns = (uint32_t) names.size();
+    d.input_columns = names.data();
+    d.where = where.view();
+    d.num_group = (uint32_t) grpv.size();
+    d.group = grpv.data();
+    d.num_select = (uint32_t) selv.size();
+    d.select = selv.data();
+    return run(d);
+  } catch (const std::exception& e) {
+    return ReturnCode::error("ERUNTIME", e.what());
+  }
+}
+
+// ---- provider / scheduler hooks ----------------------------------------------------------------------------------------
+
+std::unique_ptr<TableExpression> GpuTableProvider::buildSequentialScan(std::shared_ptr<SequentialScanNode> seqscan) const {
+  if (seqscan->tableName() != table_name_) return nullptr;
+  if (files_.size() != 1) throw std::runtime_error("a scan-only plan reads one cstable file (PartitionCursor concatenates)");
+  return std::unique_ptr<TableExpression>(new GpuCSTableScan(gpu_, std::move(seqscan), files_[0]));
+}
+
+std::unique_ptr<TableExpression> GpuTableProvider::buildGroupByExpression(std::shared_ptr<GroupByNode> node) const {
+  auto scan = node->inputTable();
+  if (!scan || scan->tableName() != table_name_) return nullptr;
+  return std::unique_ptr<TableExpression>(new GpuGroupByExpression(gpu_, std::move(node), files_));
+}
+
+}  // namespace evql_b200

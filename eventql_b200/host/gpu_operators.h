@@ -1,0 +1,98 @@
+// gpu_operators.h - the drop-in operators: csql::TableExpression implementations that run on a B200 through the C ABI
+// of include/evqgpu.h.  They replace, with the same constructor shape and pull protocol:
+//
+//   evql_b200::GpuCSTableScan          csql::FastCSTableScan        sql/CSTableScan.h:126-189, CSTableScan.cc:691-995
+//   evql_b200::GpuGroupByExpression    csql::GroupByExpression over a FastCSTableScan input, fused into one device pass
+//                                      sql/statements/select/groupby.h:34-66, groupby.cc:69-220
+//   evql_b200::GpuTableProvider        csql::CSTableScanProvider     sql/CSTableScanProvider.cc:38-113
+//   evql_b200::buildGroupByExpression  what a DefaultScheduler subclass returns from its virtual buildGroupByExpression
+//                                      (sql/scheduler.cc:153-182), cf. eventql::Scheduler (server/sql/scheduler.cc:55-77)
+//
+// There is no CPU fallback: a plan the device path cannot run makes execute() return ReturnCode::error (the reference's
+// convention, util/return_code.h) carrying evqgpu_last_error().
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+#include "../../include/evqgpu.h"
+#include "csql_mirror.h"
+
+namespace evql_b200 {
+
+// one CUDA device; owns the evqgpu context and the resident tables (the analogue of the page cache)
+class GpuContext {
+public:
+  explicit GpuContext(int device);   // throws std::runtime_error without a device
+  ~GpuContext();
+  GpuContext(const GpuContext&) = delete;
+  evqgpu_ctx* handle() const { return ctx_; }
+  // open (once) a cstable file: mmap + evqgpu_table_open; columns are loaded lazily by the first query that reads them
+  evqgpu_table* openTable(const std::string& filename);
+private:
+  struct Mapped { void* addr; size_t len; evqgpu_table* table; };
+  evqgpu_ctx* ctx_;
+  std::map<std::string, Mapped> tables_;
+};
+
+// qtree expression -> evqgpu postfix program (the shape of csql::vm::Program, sql/runtime/vm.h:44-75)
+struct Program {
+  std::vector<evqgpu_insn> code;
+  std::string strings;
+  evqgpu_expr view() const;
+};
+// column_map: rewrites ColumnReferenceNode indexes (GroupByNode space -> scan input columns); nullptr = identity
+Program translate(const csql::ExprRef& expr, const std::vector<csql::ExprRef>* column_map = nullptr);
+
+// common pull protocol over a finished evqgpu_query
+class GpuQueryExpression : public csql::TableExpression {
+public:
+  ~GpuQueryExpression() override;
+  csql::ReturnCode nextBatch(csql::SVector* columns, size_t* len) override;
+  size_t getColumnCount() const override;
+  csql::SType getColumnType(size_t idx) const override;
+  static const size_t kOutputBatchSize = 1024;   // sql/CSTableScan.h:142, groupby.h:36
+protected:
+  GpuQueryExpression(GpuContext* gpu, std::vector<std::string> filenames) : gpu_(gpu), filenames_(std::move(filenames)) {}
+  csql::ReturnCode run(const evqgpu_query_desc& desc);
+  GpuContext* gpu_;
+  std::vector<std::string> filenames_;
+  evqgpu_query* query_ = nullptr;
+  uint64_t cursor_ = 0, num_rows_ = 0;
+  std::vector<std::vector<uint8_t>> staging_;
+};
+
+// FastCSTableScan: WHERE + projection, rows in table order
+class GpuCSTableScan : public GpuQueryExpression {
+public:
+  GpuCSTableScan(GpuContext* gpu, std::shared_ptr<csql::SequentialScanNode> stmt, const std::string& cstable_filename);
+  csql::ReturnCode execute() override;
+private:
+  std::shared_ptr<csql::SequentialScanNode> stmt_;
+};
+
+// GroupByExpression whose input is a sequential scan of cstable partitions: scan + filter + aggregate in one device pass
+class GpuGroupByExpression : public GpuQueryExpression {
+public:
+  GpuGroupByExpression(GpuContext* gpu, std::shared_ptr<csql::GroupByNode> node, std::vector<std::string> partition_files);
+  csql::ReturnCode execute() override;
+private:
+  std::shared_ptr<csql::GroupByNode> node_;
+};
+
+// CSTableScanProvider: table name -> cstable file(s)
+class GpuTableProvider {
+public:
+  GpuTableProvider(GpuContext* gpu, std::string table_name, std::vector<std::string> partition_files)
+      : gpu_(gpu), table_name_(std::move(table_name)), files_(std::move(partition_files)) {}
+  // TableProvider::buildSequentialScan: nullptr (the reference's None) when the table is not ours
+  std::unique_ptr<csql::TableExpression> buildSequentialScan(std::shared_ptr<csql::SequentialScanNode> seqscan) const;
+  // DefaultScheduler::buildGroupByExpression override: fuse when the input is a scan of our table, else nullptr
+  std::unique_ptr<csql::TableExpression> buildGroupByExpression(std::shared_ptr<csql::GroupByNode> node) const;
+private:
+  GpuContext* gpu_;
+  std::string table_name_;
+  std::vector<std::string> files_;
+};
+
+}  // namespace evql_b200

@@ -1,0 +1,85 @@
+"""The C++ host mirror of the reference's operator surface (eventql_b200/host/): GpuTableProvider /
+GpuGroupByExpression / GpuCSTableScan pulled through TableExpression::execute + nextBatch by the evqgpu_sql driver,
+the way test/sql_tests.cc drives the reference's operators."""
+import ctypes
+import os
+import subprocess
+
+import pytest
+
+from eventql_b200 import capi
+from tests import common as T
+
+EXE = os.path.join(T.ROOT, "eventql_b200", "evqgpu_sql")
+HOSTLIB = os.path.join(T.ROOT, "eventql_b200", "libevqhost.so")
+GOLD = os.path.join(T.ROOT, "tests", "golden")
+
+
+def run_sql(*args):
+    r = subprocess.run([EXE] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    lines = [l for l in r.stdout.split("\n") if l]
+    return r.returncode, lines, r.stderr
+
+
+def test_host_library_builds_and_loads(native_lib):
+    assert os.path.exists(HOSTLIB) and os.path.exists(EXE)
+    ctypes.CDLL(capi.LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+    ctypes.CDLL(HOSTLIB)
+    out = subprocess.run(["nm", "-D", "--defined-only", "-C", HOSTLIB], stdout=subprocess.PIPE, text=True, check=True).stdout
+    for sym in ("evql_b200::GpuGroupByExpression::execute()", "evql_b200::GpuCSTableScan::execute()",
+                "evql_b200::GpuQueryExpression::nextBatch(csql::SVector*, unsigned long*)",
+                "evql_b200::GpuTableProvider::buildSequentialScan", "evql_b200::GpuTableProvider::buildGroupByExpression",
+                "evql_b200::translate("):
+        assert sym in out, sym
+
+
+def test_operators_fail_loudly_without_a_device(native_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    rc, lines, _ = run_sql("q1", os.path.join(GOLD, "testtbl.cst"))
+    assert rc == 1 and lines[0] == "ERROR!" and "no CUDA device" in lines[1]
+
+
+def _parse(lines, types):
+    return T.parse_ref_rows([l.split(";") for l in lines], types)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,case,table", [("q1", "q1_lineitem_leb", "lineitem_leb"), ("q6", "q6_lineitem_leb", "lineitem_leb"),
+                                             ("q1", "q1_lineitem_plain", "lineitem_plain"), ("q1", "q1_lineitem_null", "lineitem_null")])
+def test_fused_groupby_operator_equals_reference_rows(native_lib, mode, case, table):
+    rc, lines, err = run_sql(mode, T.golden_table_path(table))
+    assert rc == 0, (lines, err)
+    g = T.golden()[case]
+    T.check_against_golden(case, _parse(lines, g["types"]), ordered=False)
+
+
+@pytest.mark.gpu
+def test_partitions_through_the_provider(native_lib, tmp_path):
+    """three partition files through one GpuGroupByExpression == the golden single-file result of the same rows"""
+    spec = T.lineitem_spec()
+    n = T.GOLDEN_TABLES["lineitem_leb"][1]
+    cuts = [0, 1000, 70_001, n]
+    files = []
+    for i in range(3):
+        p = str(tmp_path / ("part%d.cst" % i))
+        T.write_table(p, spec, cuts[i + 1] - cuts[i], row_offset=cuts[i])
+        files.append(p)
+    rc, lines, err = run_sql("q1", *files)
+    assert rc == 0, (lines, err)
+    g = T.golden()["q1_lineitem_leb"]
+    T.check_against_golden("q1_lineitem_leb", _parse(lines, g["types"]), ordered=False)
+
+
+@pytest.mark.gpu
+def test_scan_and_aggregates_on_the_reference_fixture(native_lib):
+    fx = os.path.join(GOLD, "testtbl.cst")
+    rc, lines, err = run_sql("scan", fx, "time")
+    assert rc == 0, err
+    want = [l for l in open(os.path.join(GOLD, "sql_00001.result.txt")).read().split("\n")[1:] if l.strip()]
+    assert lines == want                       # test/sql/00001: 213 rows, table order, through nextBatch batches
+    rc, lines, err = run_sql("count", fx, "time")
+    assert rc == 0, err
+    g = T.golden()["c1_global"]
+    T.check_against_golden("c1_global", _parse(lines, g["types"]), ordered=False)
