@@ -119,6 +119,41 @@ void layout_states(evqgpu_query& q, const KernelShape& shape) {
     if (q.state_carry_of[i] < 0) q.state_smem[i] = q.nstate_smem++;
 }
 
+// Upper bound on the bit length of a uint64-valued expression, from the column statistics of the scanned tables
+// (Column::value_bits).  64 = unknown / may wrap.
+static uint32_t expr_bits(const Expr* e, const KernelShape& shape) {
+  auto sat = [](uint32_t b) { return b > 64u ? 64u : b; };
+  switch (e->op) {
+    case EVQ_X_INPUT:
+      if (e->col >= shape.cols.size()) return 64;
+      if (shape.cols[e->col].sql_type == EVQ_BOOL) return 1;
+      if (shape.cols[e->col].sql_type == EVQ_FLOAT64) return 64;
+      return sat(shape.cols[e->col].bits);
+    case EVQ_X_LITERAL: {
+      if (e->type == EVQ_BOOL) return 1;
+      if (e->type != EVQ_UINT64 && e->type != EVQ_TIMESTAMP64) return 64;
+      uint32_t b = 0;
+      for (uint64_t v = e->imm; v; v >>= 1) ++b;
+      return b ? b : 1;
+    }
+    case EVQ_X_IF: return std::max(expr_bits(e->args[1].get(), shape), expr_bits(e->args[2].get(), shape));
+    case EVQ_X_CALL: break;
+    default: return 64;
+  }
+  const FnInfo& fi = e->info();
+  if (fi.ret != EVQ_UINT64 && fi.ret != EVQ_TIMESTAMP64 && fi.ret != EVQ_BOOL) return 64;
+  if (fi.ret == EVQ_BOOL) return 1;
+  if (fi.args.empty() || (fi.args[0] != EVQ_UINT64 && fi.args[0] != EVQ_TIMESTAMP64)) return 64;
+  switch (fi.fn) {
+    case Fn::ADD: return sat(std::max(expr_bits(e->args[0].get(), shape), expr_bits(e->args[1].get(), shape)) + 1);
+    case Fn::MUL: return sat(expr_bits(e->args[0].get(), shape) + expr_bits(e->args[1].get(), shape));
+    case Fn::DIV: return expr_bits(e->args[0].get(), shape);
+    case Fn::MOD: return std::min(expr_bits(e->args[0].get(), shape), expr_bits(e->args[1].get(), shape));
+    case Fn::DATE_TRUNC: return expr_bits(e->args[1].get(), shape);
+    default: return 64;   // sub may wrap, conversions may reinterpret
+  }
+}
+
 static int carry_word_of(const evqgpu_query& q, int sum_word) {
   for (size_t i = 0; i < q.state_carry_of.size(); ++i)
     if (q.state_carry_of[i] == sum_word) return (int) i;
@@ -154,7 +189,12 @@ static void gen_updates(std::ostringstream& os, const evqgpu_query& q, const Ker
       const int op = q.state_ops[w];
       if (q.state_keys[w].compare(0, 4, "sum:") == 0) {
         // sum_*: acc += v; a NULL contributes its value bits, which are 0 (aggregate.cc:184-219)
-        const int cw = carry_word_of(q, w);
+        int cw = carry_word_of(q, w);
+        // the wrap check per row is dropped where the accumulator provably cannot wrap: a thread-private word needs more
+        // than 2^32 rows of < 2^32 values, a global word more than 2^40 rows of < 2^24 values (flushes and merges still
+        // propagate carries, the layout does not change)
+        const uint32_t vb = ty == EVQ_UINT64 ? expr_bits(arg, shape) : 64;
+        if (cw >= 0 && ((shape.tier == 1 && vb <= 32) || (shape.tier == 2 && vb <= 24))) cw = -1;
         os << "    const u64 v = " << as_bits(c, ty) << ";\n";
         if (cw >= 0) os << "    EVQ_UPD_C(" << w << ", " << cw << ", v);\n";
         else os << "    EVQ_UPD(" << w << ", " << OP_ADD_U64 << ", v);\n";
@@ -271,34 +311,26 @@ static void gen_fast_layout(std::ostringstream& os, const KernelShape& shape) {
     if (shape.cols[i].used) os << "  " << fast_ctype(shape.cols[i]) << " c" << i << "[EVQ_RPT];\n";
   os << "  u32 _unused;\n};\n";
   const int ngen = std::max(1, shape.ngen);
-  os << "struct EvqFastPrep {\n  bool general[" << ngen << "];\n  u32 count[" << ngen << "];\n  u32 incl[" << ngen << "];\n  u32 mask0[" << ngen
-     << "];\n};\n";
+  os << "struct EvqFastPrep {\n  bool general[" << ngen << "];\n  u32 start[" << ngen << "];\n};\n";
 
-  // ---- boundary search of the variable-length columns: 2 consumer barriers per tile, only when a tile needs them
+  // ---- boundary search of the variable-length columns: ONE consumer barrier per tile, only when a tile needs it
   os << "__device__ __forceinline__ void evq_fast_prep(const EvqTile& T, const EvqScanParams& P, EvqFastScratch* scr, EvqFastPrep& prep) {\n";
   if (shape.ngen > 0) {
     os << "  bool any = false;\n";
     for (size_t i = 0; i < ncols; ++i) {
       const ColSig& c = shape.cols[i];
       if (!c.used || c.gen_slot < 0) continue;
-      os << "  evq_fast_count<" << c.data_stream << ", " << c.leb_len << ">(T, P, prep.general[" << c.gen_slot << "], prep.count["
-         << c.gen_slot << "], prep.mask0[" << c.gen_slot << "]);\n  any = any || prep.general[" << c.gen_slot << "];\n";
+      os << "  evq_fast_prep_a<" << c.data_stream << ", " << c.gen_slot << ", " << c.leb_len << ">(T, P, scr, prep.general[" << c.gen_slot
+         << "]);\n  any = any || prep.general[" << c.gen_slot << "];\n  prep.start[" << c.gen_slot << "] = 0u;\n";
     }
-    os << "  if (any) {\n";
+    os << "  if (any) {\n    evq_cons_sync();\n";
     for (size_t i = 0; i < ncols; ++i) {
       const ColSig& c = shape.cols[i];
       if (!c.used || c.gen_slot < 0) continue;
-      os << "    if (prep.general[" << c.gen_slot << "]) prep.incl[" << c.gen_slot << "] = evq_fast_publish<" << c.gen_slot
-         << ">(T, scr, prep.count[" << c.gen_slot << "]);\n";
+      os << "    if (prep.general[" << c.gen_slot << "]) prep.start[" << c.gen_slot << "] = evq_fast_prep_b<" << c.data_stream << ", "
+         << c.gen_slot << ">(T, P, scr);\n";
     }
-    os << "    evq_cons_sync();\n";
-    for (size_t i = 0; i < ncols; ++i) {
-      const ColSig& c = shape.cols[i];
-      if (!c.used || c.gen_slot < 0) continue;
-      os << "    if (prep.general[" << c.gen_slot << "]) evq_fast_write_starts<" << c.data_stream << ", " << c.gen_slot
-         << ">(T, P, scr, prep.count[" << c.gen_slot << "], prep.incl[" << c.gen_slot << "], prep.mask0[" << c.gen_slot << "]);\n";
-    }
-    os << "    evq_cons_sync();\n  }\n";
+    os << "  }\n";
   }
   os << "}\n";
 
@@ -322,9 +354,11 @@ static void gen_fast_layout(std::ostringstream& os, const KernelShape& shape) {
       default:
         if (c.leb_len <= 1) os << "    evq_fast_ld_leb1<" << S << ">(T, P, raw);\n";
         else if (c.leb_len <= 4)
-          os << "    evq_fast_ld_leb32<" << S << ", " << c.gen_slot << ", " << c.leb_len << ">(T, P, scr, prep.general[" << c.gen_slot << "], raw);\n";
+          os << "    evq_fast_ld_leb32<" << S << ", " << c.gen_slot << ", " << c.leb_len << ">(T, P, prep.general[" << c.gen_slot
+             << "], prep.start[" << c.gen_slot << "], raw);\n";
         else
-          os << "    evq_fast_ld_leb64<" << S << ", " << c.gen_slot << ", " << c.leb_len << ">(T, P, scr, prep.general[" << c.gen_slot << "], raw);\n";
+          os << "    evq_fast_ld_leb64<" << S << ", " << c.gen_slot << ", " << c.leb_len << ">(T, P, prep.general[" << c.gen_slot
+             << "], prep.start[" << c.gen_slot << "], raw);\n";
         break;
     }
     std::string conv;
@@ -561,6 +595,14 @@ static std::string gen_group_kernels(const evqgpu_query& q, const KernelShape& s
   return os.str();
 }
 
+// 16-byte chunks one tile of the longest variable-length column can span (+2: unaligned start, rounding)
+int gen_chunks(const KernelShape& shape) {
+  uint32_t L = 1;
+  for (const auto& c : shape.cols)
+    if (c.used && c.gen_slot >= 0) L = std::max(L, c.leb_len);
+  return (int) ((L * EVQ_TILE_ROWS + 15) / 16 + 2);
+}
+
 std::string generate_source(const evqgpu_query& q, const KernelShape& shape) {
   std::ostringstream os;
   os << "// generated by eventql_b200 csrc/codegen.cc - one fused scan kernel per (plan, column layout)\n";
@@ -569,7 +611,7 @@ std::string generate_source(const evqgpu_query& q, const KernelShape& shape) {
      << std::max(1, q.nstate_smem) << "\n#define EVQ_NKEYS " << q.group.size() << "\n#define EVQ_NLEB "
      << shape.nleb << "\n#define EVQ_NNULL " << shape.nnull << "\n#define EVQ_HAS_PREP "
      << ((shape.nleb > 0 || shape.nnull > 0) ? 1 : 0) << "\n#define EVQ_MIN_CTAS " << shape.min_ctas << "\n#define EVQ_NGEN "
-     << shape.ngen << "\n";
+     << shape.ngen << "\n#define EVQ_GEN_CHUNKS " << gen_chunks(shape) << "\n";
   os << kSrcAbi << "\n" << kSrcPrelude << "\n";
   const std::string kern = shape.fast ? kSrcScanFast : kSrcScanKernel;
   const std::string marker = "//@@EVQ_GENERATED@@";

@@ -67,9 +67,9 @@ extern "C" int evqgpu_debug_generate(const evqgpu_query_desc* desc, const evqgpu
         }
         s.dense.slots = stride;
       }
-      s.ncons = 256;
+      s.ncons = s.fast ? 128 : 256;   // what fit_shape picks first
       s.nstages = 3;
-      s.min_ctas = 2;
+      s.min_ctas = s.fast ? 4 : 2;
       std::string src = generate_source(q, s);
       if (compile) {
         std::string log;

@@ -27,24 +27,28 @@
 //   evq_where / evq_keys / evq_accumulate_* / evq_state_* / evq_project   as in the general kernel
 
 #define EVQ_NWARPS (EVQ_NCONS / 32)
-#define EVQ_RPT 4
+#define EVQ_RPT (EVQ_TILE_ROWS / EVQ_NCONS)   // consecutive rows per thread: 4 (256 consumers) or 8 (128)
 #define EVQ_NTHREADS (EVQ_NCONS + 32)
 
+// EVQ_GEN_CHUNKS: 16-byte chunks a tile of the longest variable-length column can span (generated)
 struct EvqFastScratch {
-  u32 wtot[EVQ_NGEN > 0 ? EVQ_NGEN : 1][EVQ_NWARPS];   // per-warp terminator counts of the boundary scan
-  u16 start[EVQ_NGEN > 0 ? EVQ_NGEN : 1][EVQ_NCONS];   // byte offset (from the payload start) of value 4t
-  u32 scan[EVQ_NWARPS];                                // scan-only plans: pass counts per warp
+  u32 wtot[EVQ_NGEN > 0 ? EVQ_NGEN : 1][EVQ_NWARPS];          // terminators per consumer warp (boundary search)
+  u32 chunk[EVQ_NGEN > 0 ? EVQ_NGEN : 1][EVQ_GEN_CHUNKS];     // per chunk: terminators before it in its warp << 16 | terminator mask
+  u32 scan[EVQ_NWARPS];                                       // scan-only plans: pass counts per warp
 };
 
 // ---- boundary search of a variable-length LEB128 column ------------------------------------------------------------------
+// Thread t must find the byte at which value RPT*t starts, i.e. the byte behind terminator number RPT*t - 1 of the tile.
+// Phase A (chunk-parallel, before the one consumer barrier): every thread takes `per` consecutive 16-byte chunks, builds
+// their terminator masks, and a warp scan turns the counts into "terminators before this chunk inside my warp"; mask and
+// count go to the chunk table, the warp total to wtot.  Phase B (row-parallel, after the barrier): pick the warp from the
+// <= 8 warp totals, binary-search the chunk table of that warp, then drop set bits of the chunk's mask.
 
-// A tile is uniform when all its values have the column's maximal length L; otherwise count this thread's terminators.
-template <int S, int L>
-__device__ __forceinline__ void evq_fast_count(const EvqTile& T, const EvqScanParams& P, bool& general, u32& count, u32& mask0) {
+// A tile is uniform when all its values have the column's maximal length L (decided from the tile descriptor alone).
+template <int S, int G, int L>
+__device__ __forceinline__ void evq_fast_prep_a(const EvqTile& T, const EvqScanParams& P, EvqFastScratch* scr, bool& general) {
   const EvqStreamDesc d = T.desc[S];
   general = d.nbytes != (u32) L * d.nvals;   // the same for every thread of the CTA
-  count = 0;
-  mask0 = 0;
   if (!general) return;
   const u8* region = T.stage + P.streams[S].smem_off;
   const u32 tb = d.delta + d.nbytes;
@@ -52,16 +56,11 @@ __device__ __forceinline__ void evq_fast_count(const EvqTile& T, const EvqScanPa
   const u32 per = (nchunks + EVQ_NCONS - 1) / EVQ_NCONS;
   const u32 c0 = T.ctid * per;
   const u32 c1 = c0 + per < nchunks ? c0 + per : nchunks;
-  for (u32 c = c0; c < c1; ++c) {
-    const u32 m = evq_leb_chunk_mask(region, c, d.delta, tb);
-    if (c == c0) mask0 = m;   // the common case is one chunk per thread: the write phase reuses its mask
-    count += __popc(m);
-  }
-}
-
-// inclusive warp scan of the counts; the warp totals go to shared memory (read after the next consumer barrier)
-template <int G>
-__device__ __forceinline__ u32 evq_fast_publish(const EvqTile& T, EvqFastScratch* scr, u32 count) {
+  // the first two masks stay in registers (L <= 4: at most 2 chunks per thread with 128 consumers, 1 with 256)
+  const u32 m0 = c0 < c1 ? evq_leb_chunk_mask(region, c0, d.delta, tb) : 0u;
+  const u32 m1 = c0 + 1u < c1 ? evq_leb_chunk_mask(region, c0 + 1u, d.delta, tb) : 0u;
+  u32 count = __popc(m0) + __popc(m1);
+  for (u32 c = c0 + 2u; c < c1; ++c) count += __popc(evq_leb_chunk_mask(region, c, d.delta, tb));
   const u32 lane = evq_lane();
   u32 incl = count;
 #pragma unroll
@@ -70,43 +69,49 @@ __device__ __forceinline__ u32 evq_fast_publish(const EvqTile& T, EvqFastScratch
     if (lane >= (u32) o) incl += n;
   }
   if (lane == 31) scr->wtot[G][T.ctid >> 5] = incl;
-  return incl;
+  u32 before = incl - count;
+  if (c0 < c1) scr->chunk[G][c0] = (before << 16) | m0;
+  before += __popc(m0);
+  if (c0 + 1u < c1) scr->chunk[G][c0 + 1u] = (before << 16) | m1;
+  before += __popc(m1);
+  for (u32 c = c0 + 2u; c < c1; ++c) {
+    const u32 m = evq_leb_chunk_mask(region, c, d.delta, tb);
+    scr->chunk[G][c] = (before << 16) | m;
+    before += __popc(m);
+  }
 }
 
-// terminator number j ends value j: every terminator with j % 4 == 3 marks the start of value j + 1 = 4 * ((j + 1) / 4)
+// byte offset (from the payload start) of the thread's first value
 template <int S, int G>
-__device__ __forceinline__ void evq_fast_write_starts(const EvqTile& T, const EvqScanParams& P, EvqFastScratch* scr, u32 count,
-                                                      u32 incl, u32 mask0) {
-  const u32 warp = T.ctid >> 5;
-  u32 j = incl - count;
-#pragma unroll
-  for (u32 w = 0; w < EVQ_NWARPS; ++w) j += w < warp ? scr->wtot[G][w] : 0u;
+__device__ __forceinline__ u32 evq_fast_prep_b(const EvqTile& T, const EvqScanParams& P, const EvqFastScratch* scr) {
   const EvqStreamDesc d = T.desc[S];
-  const u8* region = T.stage + P.streams[S].smem_off;
+  const u32 first = EVQ_RPT * T.ctid;
+  if (first == 0u || first >= d.nvals) return 0u;
+  u32 r = first - 1u;                              // number of the terminator in front of the value
+  // warp whose chunks hold it
+  u32 w = 0;
+#pragma unroll
+  for (int i = 0; i < EVQ_NWARPS - 1; ++i) {
+    const u32 n = scr->wtot[G][i];
+    const bool beyond = (w == (u32) i) && r >= n;
+    r -= beyond ? n : 0u;
+    w += beyond ? 1u : 0u;
+  }
   const u32 tb = d.delta + d.nbytes;
   const u32 nchunks = (tb + 15u) >> 4;
   const u32 per = (nchunks + EVQ_NCONS - 1) / EVQ_NCONS;
-  const u32 c0 = T.ctid * per;
-  const u32 c1 = c0 + per < nchunks ? c0 + per : nchunks;
-  for (u32 c = c0; c < c1; ++c) {
-    u32 m = c == c0 ? mask0 : evq_leb_chunk_mask(region, c, d.delta, tb);
-    const u32 n = __popc(m);
-    u32 jj = j;
-    const u32 skip = (3u - jj) & 3u;
-    if (skip > 0u) m &= m - 1u;
-    if (skip > 1u) m &= m - 1u;
-    if (skip > 2u) m &= m - 1u;
-    jj += skip;
-    while (m) {
-      const u32 k = __ffs(m) - 1u;
-      const u32 idx = (jj + 1u) >> 2;
-      if (idx < EVQ_NCONS) scr->start[G][idx] = (u16) (16u * c + k + 1u - d.delta);
-      m &= m - 1u; m &= m - 1u; m &= m - 1u; m &= m - 1u;
-      jj += 4u;
-    }
-    j += n;
+  // last chunk of warp w whose "before" count is <= r
+  u32 lo = w * 32u * per;
+  u32 hi = lo + 32u * per;
+  hi = hi < nchunks ? hi : nchunks;
+  while (hi - lo > 1u) {
+    const u32 mid = (lo + hi) >> 1;
+    if ((scr->chunk[G][mid] >> 16) <= r) lo = mid; else hi = mid;
   }
-  if (T.ctid == 0) scr->start[G][0] = 0;
+  const u32 e = scr->chunk[G][lo];
+  u32 m = e & 0xffffu;
+  for (u32 k = r - (e >> 16); k > 0u; --k) m &= m - 1u;
+  return 16u * lo + (u32) __ffs(m) - d.delta;      // (__ffs - 1) is the terminator's byte; the value starts behind it
 }
 
 // ---- per-thread decode of 4 consecutive values -------------------------------------------------------------------------
@@ -131,14 +136,18 @@ __device__ __forceinline__ u32 evq_fixed_mask(u32 len) { return len >= 4u ? 0x7f
 // L == 1: value i is byte i
 template <int S>
 __device__ __forceinline__ void evq_fast_ld_leb1(const EvqTile& T, const EvqScanParams& P, u32 (&v)[EVQ_RPT]) {
-  const u32 x = evq_stage_u32(T.stage, P.streams[S].smem_off + T.desc[S].delta + evq_fast_first(T, S));
+  const u32 off = P.streams[S].smem_off + T.desc[S].delta + evq_fast_first(T, S);
 #pragma unroll
-  for (int i = 0; i < EVQ_RPT; ++i) v[i] = (x >> (8 * i)) & 0xffu;
+  for (int j = 0; j < EVQ_RPT / 4; ++j) {
+    const u32 x = evq_stage_u32(T.stage, off + 4 * j);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[4 * j + i] = (x >> (8 * i)) & 0xffu;
+  }
 }
 
 // 2 <= L <= 4: 32-bit window
 template <int S, int G, int L>
-__device__ __forceinline__ void evq_fast_ld_leb32(const EvqTile& T, const EvqScanParams& P, const EvqFastScratch* scr, bool general,
+__device__ __forceinline__ void evq_fast_ld_leb32(const EvqTile& T, const EvqScanParams& P, bool general, u32 start,
                                                   u32 (&v)[EVQ_RPT]) {
   const u32 pay = P.streams[S].smem_off + T.desc[S].delta;
   if (!general) {
@@ -149,7 +158,7 @@ __device__ __forceinline__ void evq_fast_ld_leb32(const EvqTile& T, const EvqSca
       v[i] = L == 2 ? evq_leb_pack2(x) : evq_leb_pack4(x);
     }
   } else {
-    u32 p = pay + (EVQ_RPT * T.ctid < T.desc[S].nvals ? (u32) scr->start[G][T.ctid] : 0u);
+    u32 p = pay + start;
 #pragma unroll
     for (int i = 0; i < EVQ_RPT; ++i) {
       const u32 x = evq_stage_u32(T.stage, p);
@@ -165,12 +174,12 @@ __device__ __forceinline__ void evq_fast_ld_leb32(const EvqTile& T, const EvqSca
 
 // 5 <= L <= 10: 64-bit window (+ 2 bytes for 9- and 10-byte values)
 template <int S, int G, int L>
-__device__ __forceinline__ void evq_fast_ld_leb64(const EvqTile& T, const EvqScanParams& P, const EvqFastScratch* scr, bool general,
+__device__ __forceinline__ void evq_fast_ld_leb64(const EvqTile& T, const EvqScanParams& P, bool general, u32 start,
                                                   u64 (&v)[EVQ_RPT]) {
   const u8* pay = T.stage + P.streams[S].smem_off + T.desc[S].delta;
   const u8* p;
   if (!general) p = pay + (u32) L * evq_fast_first(T, S);
-  else p = pay + (EVQ_RPT * T.ctid < T.desc[S].nvals ? (u32) scr->start[G][T.ctid] : 0u);
+  else p = pay + start;
 #pragma unroll
   for (int i = 0; i < EVQ_RPT; ++i) {
     u32 lo, hi;

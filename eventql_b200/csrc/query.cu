@@ -138,7 +138,7 @@ static size_t scratch_bytes(const KernelShape& s) {
   const size_t nwarps = s.ncons / 32;
   if (s.fast) {   // EvqFastScratch
     const size_t ngen = std::max(1, s.ngen);
-    return round_up(4 * ngen * nwarps + 2 * ngen * s.ncons + 4 * nwarps, 128) + 128;
+    return round_up(4 * ngen * nwarps + 4 * ngen * (size_t) gen_chunks(s) + 4 * nwarps, 128) + 128;
   }
   const size_t one = 4 * std::max(1, s.nleb) * nwarps + 4 * std::max(1, s.nnull) * (EVQ_TILE_ROWS / 32) +
                      2 * std::max(1, s.nleb) * EVQ_TILE_ROWS + 4 * nwarps;
@@ -317,9 +317,9 @@ static void fit_shape(evqgpu_query& q, KernelShape& s, std::vector<TablePlan>& p
   for (int attempt = 0; attempt < 4; ++attempt) {
     s.ncons = (attempt & 1) ? 128 : 256;
     s.nstages = (attempt & 2) ? 2 : 3;
-    if (s.fast) {
-      if (attempt & 1) continue;
-      s.ncons = 256;
+    if (s.fast) {   // 8 consecutive rows per thread first: halves the per-thread fixed work of every tile
+      s.ncons = (attempt & 1) ? 256 : 128;
+      if (const char* e = getenv("EVQGPU_FAST_NCONS")) s.ncons = atoi(e) == 256 ? 256 : 128;
     }
     size_t worst = 0;
     for (auto& p : plans) {
@@ -328,8 +328,12 @@ static void fit_shape(evqgpu_query& q, KernelShape& s, std::vector<TablePlan>& p
       worst = std::max(worst, p.smem);
     }
     if (worst <= limit) {
-      // two CTAs per SM when they fit: better latency hiding for the decode phases
-      s.min_ctas = (worst * 2 + 2048 <= 228 * 1024) ? 2 : 1;
+      // as many CTAs per SM as shared memory allows (latency hiding for the decode phases), within the register budget
+      // the launch bounds leave per thread: 2 x 288 threads or 4 x 160 threads
+      const int by_smem = (int) ((227 * 1024) / (worst + 1024));
+      const int cap = s.ncons <= 128 ? 4 : 2;
+      s.min_ctas = std::max(1, std::min(by_smem, cap));
+      if (const char* e = getenv("EVQGPU_MAX_CTAS")) s.min_ctas = std::max(1, std::min(s.min_ctas, atoi(e)));
       return;
     }
   }
@@ -350,7 +354,7 @@ static void run_scan(evqgpu_query& q, const KernelShape& s, std::vector<TablePla
     P.tile_row_base = tile_row_base;
     tile_row_base += p.table->num_tiles;
     u32 stage_bytes = p.layout.stage_bytes;
-    const int ctas_per_sm = std::max<int>(1, std::min<size_t>(s.min_ctas == 2 ? 2 : 1, (228 * 1024) / (p.smem + 1024)));
+    const int ctas_per_sm = std::max<int>(1, std::min<size_t>(s.min_ctas, (227 * 1024) / (p.smem + 1024)));
     const unsigned grid = (unsigned) std::min<uint64_t>(p.table->num_tiles, (uint64_t) ctx->sm_count * ctas_per_sm);
     void* args[] = {&P, &stage_bytes};
     cudaEvent_t e0 = nullptr, e1 = nullptr;

@@ -127,6 +127,7 @@ namespace evq {
 // codegen.cc
 std::string generate_source(const evqgpu_query& q, const KernelShape& shape);
 void layout_states(evqgpu_query& q, const KernelShape& shape);
+int gen_chunks(const KernelShape& shape);
 // query.cu
 void emit_results(evqgpu_query& q);
 void finish_query(evqgpu_query& q);
