@@ -117,6 +117,40 @@ void layout_states(evqgpu_query& q, const KernelShape& shape) {
   q.nstate_smem = 0;
   for (size_t i = 0; i < q.state_ops.size(); ++i)
     if (q.state_carry_of[i] < 0) q.state_smem[i] = q.nstate_smem++;
+  q.state_narrow.assign(q.state_ops.size(), -1);
+  q.narrow_col.clear();
+  q.nnarrow = 0;
+}
+
+// Byte-wide aggregates of the fast dense kernel with a handful of groups: the rows counter and sums of required 1-byte
+// LEB128 columns.  The thread keeps them as u32 registers per group and feeds them 4 rows at a time with dp4a (the packed
+// bytes of the column against a 0/1 byte mask "row belongs to group g"), so they cost ~1.5 instructions per row instead
+// of a shared-memory read-modify-write each.  Only the thread-private storage changes, not the global state layout.
+void layout_narrow(evqgpu_query& q, const KernelShape& shape) {
+  q.state_narrow.assign(q.state_ops.size(), -1);
+  q.narrow_col.clear();
+  q.nnarrow = 0;
+  if (!shape.fast || shape.tier != 1 || shape.g1 < 2 || shape.g1 > 4 || getenv("EVQGPU_NO_NARROW")) return;
+  auto take = [&](int w, int col) {
+    if (q.state_narrow[w] >= 0) return;
+    q.state_narrow[w] = q.nnarrow++;
+    q.narrow_col.push_back(col);
+  };
+  take(0, -1);
+  for (const auto& item : q.select) {
+    if (!item.agg || item.state0 <= 0) continue;
+    if (q.state_keys[item.state0].compare(0, 4, "sum:") != 0) continue;
+    const Expr* arg = item.agg->args[0].get();
+    if (arg->op != EVQ_X_INPUT || arg->col >= shape.cols.size()) continue;
+    const ColSig& c = shape.cols[arg->col];
+    if (c.kind == EVQ_KIND_LEB128 && c.leb_len == 1 && !c.nullable && c.sql_type != EVQ_BOOL) take(item.state0, (int) arg->col);
+  }
+  // re-number the words that stay in shared memory
+  q.nstate_smem = 0;
+  for (size_t i = 0; i < q.state_ops.size(); ++i) {
+    q.state_smem[i] = -1;
+    if (q.state_carry_of[i] < 0 && q.state_narrow[i] < 0) q.state_smem[i] = q.nstate_smem++;
+  }
 }
 
 // Upper bound on the bit length of a uint64-valued expression, from the column statistics of the scanned tables
@@ -166,7 +200,9 @@ static int carry_word_of(const evqgpu_query& q, int sum_word) {
 static void gen_updates(std::ostringstream& os, const evqgpu_query& q, const KernelShape& shape) {
   CodegenEnv env = row_env(shape);
   std::vector<bool> done(q.state_ops.size(), false);
-  os << "  EVQ_UPD(0, " << OP_ADD_U64 << ", 1ull);\n";   // rows per group
+  for (size_t w = 0; w < q.state_ops.size(); ++w)
+    if (w < q.state_narrow.size() && q.state_narrow[w] >= 0) done[w] = true;   // fed by evq_accumulate_narrow
+  if (!done[0]) os << "  EVQ_UPD(0, " << OP_ADD_U64 << ", 1ull);\n";   // rows per group
   done[0] = true;
   for (const auto& item : q.select) {
     if (!item.agg) continue;
@@ -309,6 +345,8 @@ static void gen_fast_layout(std::ostringstream& os, const KernelShape& shape) {
   os << "struct EvqCols {\n";
   for (size_t i = 0; i < ncols; ++i)
     if (shape.cols[i].used) os << "  " << fast_ctype(shape.cols[i]) << " c" << i << "[EVQ_RPT];\n";
+  for (size_t i = 0; i < ncols; ++i)
+    if (shape.cols[i].used && shape.cols[i].packed) os << "  u32 p" << i << "[EVQ_RPT / 4];\n";   // the raw bytes, 4 rows per word
   os << "  u32 _unused;\n};\n";
   const int ngen = std::max(1, shape.ngen);
   os << "struct EvqFastPrep {\n  bool general[" << ngen << "];\n  u32 start[" << ngen << "];\n};\n";
@@ -352,7 +390,8 @@ static void gen_fast_layout(std::ostringstream& os, const KernelShape& shape) {
       case EVQ_KIND_PLAIN32: os << "    evq_fast_ld_plain32<" << S << ">(T, P, raw);\n"; break;
       case EVQ_KIND_BITPACK: os << "    evq_fast_ld_bitpack<" << S << ">(T, P, raw);\n"; break;
       default:
-        if (c.leb_len <= 1) os << "    evq_fast_ld_leb1<" << S << ">(T, P, raw);\n";
+        if (c.leb_len <= 1 && c.packed) os << "    evq_fast_ld_leb1p<" << S << ">(T, P, raw, cols.p" << i << ");\n";
+        else if (c.leb_len <= 1) os << "    evq_fast_ld_leb1<" << S << ">(T, P, raw);\n";
         else if (c.leb_len <= 4)
           os << "    evq_fast_ld_leb32<" << S << ", " << c.gen_slot << ", " << c.leb_len << ">(T, P, prep.general[" << c.gen_slot
              << "], prep.start[" << c.gen_slot << "], raw);\n";
@@ -459,6 +498,27 @@ static std::string gen_row_functions(const evqgpu_query& q, const KernelShape& s
         if (q.state_smem[w] >= 0)
           gen_flush_word(w, "sacc[EVQ_SIDX(g, " + std::to_string(q.state_smem[w]) + ")]", "dense_state + (u64) g * " + std::to_string(nstate));
       os << "}\n";
+      if (q.nnarrow > 0) {
+        // byte-wide aggregates: u32 registers per (word, group), fed 4 rows at a time.  `selector` holds one nibble per
+        // row of the quad: its dense slot, or 4 when the row did not pass WHERE; PRMT turns it into the 0/1 byte mask of
+        // group g, dp4a sums the column's 4 bytes under that mask.
+        os << "__device__ __forceinline__ void evq_accumulate_narrow(const EvqCols& cols, int j, u32 selector, u32* nacc) {\n";
+        os << "#pragma unroll\n  for (int g = 0; g < EVQ_G1; ++g) {\n    const u32 sel = __byte_perm(1u << (8 * g), 0u, selector);\n";
+        for (int w = 0; w < nstate; ++w) {
+          const int a = q.state_narrow[w];
+          if (a < 0) continue;
+          if (q.narrow_col[a] < 0) os << "    nacc[" << a << " * EVQ_G1 + g] += __popc(sel);\n";
+          else os << "    nacc[" << a << " * EVQ_G1 + g] = __dp4a(cols.p" << q.narrow_col[a] << "[j], sel, nacc[" << a << " * EVQ_G1 + g]);\n";
+        }
+        os << "  }\n}\n";
+        os << "__device__ __forceinline__ void evq_narrow_flush(const u32* nacc, u64* dense_state) {\n";
+        for (int g = 0; g < shape.g1; ++g)
+          for (int w = 0; w < nstate; ++w)
+            if (q.state_narrow[w] >= 0)
+              gen_flush_word(w, "(u64) nacc[" + std::to_string(q.state_narrow[w] * shape.g1 + g) + "]",
+                             "dense_state + " + std::to_string((uint64_t) g * nstate));
+        os << "}\n";
+      }
     } else {
       os << "__device__ __forceinline__ void evq_state_init_regs(u64* acc) {\n";
       for (int w = 0; w < nstate; ++w)
@@ -603,7 +663,10 @@ int gen_chunks(const KernelShape& shape) {
   return (int) ((L * EVQ_TILE_ROWS + 15) / 16 + 2);
 }
 
-std::string generate_source(const evqgpu_query& q, const KernelShape& shape) {
+std::string generate_source(const evqgpu_query& q, const KernelShape& shape_in) {
+  KernelShape shape = shape_in;
+  for (int col : q.narrow_col)
+    if (col >= 0) shape.cols[col].packed = true;
   std::ostringstream os;
   os << "// generated by eventql_b200 csrc/codegen.cc - one fused scan kernel per (plan, column layout)\n";
   os << "#define EVQ_NCONS " << shape.ncons << "\n#define EVQ_NSTAGES " << shape.nstages << "\n#define EVQ_NSTREAMS "
@@ -611,7 +674,7 @@ std::string generate_source(const evqgpu_query& q, const KernelShape& shape) {
      << std::max(1, q.nstate_smem) << "\n#define EVQ_NKEYS " << q.group.size() << "\n#define EVQ_NLEB "
      << shape.nleb << "\n#define EVQ_NNULL " << shape.nnull << "\n#define EVQ_HAS_PREP "
      << ((shape.nleb > 0 || shape.nnull > 0) ? 1 : 0) << "\n#define EVQ_MIN_CTAS " << shape.min_ctas << "\n#define EVQ_NGEN "
-     << shape.ngen << "\n#define EVQ_GEN_CHUNKS " << gen_chunks(shape) << "\n";
+     << shape.ngen << "\n#define EVQ_GEN_CHUNKS " << gen_chunks(shape) << "\n#define EVQ_NNARROW " << q.nnarrow << "\n";
   os << kSrcAbi << "\n" << kSrcPrelude << "\n";
   const std::string kern = shape.fast ? kSrcScanFast : kSrcScanKernel;
   const std::string marker = "//@@EVQ_GENERATED@@";

@@ -67,6 +67,8 @@ extern "C" int evqgpu_debug_generate(const evqgpu_query_desc* desc, const evqgpu
         }
         s.dense.slots = stride;
       }
+      layout_states(q, s);
+      layout_narrow(q, s);
       s.ncons = s.fast ? 128 : 256;   // what fit_shape picks first
       s.nstages = 3;
       s.min_ctas = s.fast ? 4 : 2;

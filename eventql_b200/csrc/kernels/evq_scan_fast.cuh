@@ -137,9 +137,24 @@ __device__ __forceinline__ u32 evq_fixed_mask(u32 len) { return len >= 4u ? 0x7f
 template <int S>
 __device__ __forceinline__ void evq_fast_ld_leb1(const EvqTile& T, const EvqScanParams& P, u32 (&v)[EVQ_RPT]) {
   const u32 off = P.streams[S].smem_off + T.desc[S].delta + evq_fast_first(T, S);
+  const bool aligned = (off & 3u) == 0u;   // the same for all threads: tiles of 1-byte columns start at multiples of 1024
 #pragma unroll
   for (int j = 0; j < EVQ_RPT / 4; ++j) {
-    const u32 x = evq_stage_u32(T.stage, off + 4 * j);
+    const u32 x = aligned ? *(const u32*) (T.stage + off + 4 * j) : evq_stage_u32(T.stage, off + 4 * j);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[4 * j + i] = (x >> (8 * i)) & 0xffu;
+  }
+}
+
+// same, also keeping the raw bytes (4 rows per word) for the dp4a aggregates
+template <int S>
+__device__ __forceinline__ void evq_fast_ld_leb1p(const EvqTile& T, const EvqScanParams& P, u32 (&v)[EVQ_RPT], u32 (&packed)[EVQ_RPT / 4]) {
+  const u32 off = P.streams[S].smem_off + T.desc[S].delta + evq_fast_first(T, S);
+  const bool aligned = (off & 3u) == 0u;
+#pragma unroll
+  for (int j = 0; j < EVQ_RPT / 4; ++j) {
+    const u32 x = aligned ? *(const u32*) (T.stage + off + 4 * j) : evq_stage_u32(T.stage, off + 4 * j);
+    packed[j] = x;
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[4 * j + i] = (x >> (8 * i)) & 0xffu;
   }
@@ -152,10 +167,19 @@ __device__ __forceinline__ void evq_fast_ld_leb32(const EvqTile& T, const EvqSca
   const u32 pay = P.streams[S].smem_off + T.desc[S].delta;
   if (!general) {
     const u32 p = pay + (u32) L * evq_fast_first(T, S);
+    if ((L == 2 || L == 4) && (p & 3u) == 0u) {   // whole words: two 2-byte values or one 4-byte value each
+      const u32* w = (const u32*) (T.stage + p);
 #pragma unroll
-    for (int i = 0; i < EVQ_RPT; ++i) {
-      const u32 x = evq_stage_u32(T.stage, p + L * i) & evq_fixed_mask(L);
-      v[i] = L == 2 ? evq_leb_pack2(x) : evq_leb_pack4(x);
+      for (int i = 0; i < EVQ_RPT; ++i) {
+        if (L == 2) v[i] = evq_leb_pack2((w[i >> 1] >> (16 * (i & 1))) & 0x7f7fu);
+        else v[i] = evq_leb_pack4(w[i] & 0x7f7f7f7fu);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < EVQ_RPT; ++i) {
+        const u32 x = evq_stage_u32(T.stage, p + L * i) & evq_fixed_mask(L);
+        v[i] = L == 2 ? evq_leb_pack2(x) : evq_leb_pack4(x);
+      }
     }
   } else {
     u32 p = pay + start;
@@ -299,6 +323,11 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
 #if EVQ_TIER == 1
 #if EVQ_G1 > 1
   for (u32 g = 0; g < EVQ_G1; ++g) evq_state_init_slot(sacc, g, tid);
+#if EVQ_NNARROW > 0
+  u32 nacc[EVQ_NNARROW * EVQ_G1];
+#pragma unroll
+  for (int i = 0; i < EVQ_NNARROW * EVQ_G1; ++i) nacc[i] = 0u;
+#endif
 #else
   u64 racc[EVQ_NSTATE];
   evq_state_init_regs(racc);
@@ -370,6 +399,32 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
       }
     }
 #endif
+#elif EVQ_TIER == 1 && EVQ_G1 > 1 && EVQ_NNARROW > 0
+    // dense tier with byte-wide aggregates: rows are handled in quads; the quad's selector (one nibble per row: dense slot,
+    // or 4 = did not pass) drives the dp4a accumulators, the remaining (wide) words take the shared-memory path per row
+#pragma unroll
+    for (int j = 0; j < EVQ_RPT / 4; ++j) {
+      u32 selector = 0x4444u;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const int k = 4 * j + kk;
+        EvqRow row;
+        evq_fast_row(cols, k, row);
+        const bool pass = (EVQ_RPT * tid + k < T.rows) && evq_where(row, err);
+        if (pass) {
+          ++passed;
+          u64 key[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
+          u32 ktag[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
+          evq_keys(row, key, ktag, err);
+          const u32 g = evq_dense_slot(key, ktag, err);
+          if (g != ~0u) {
+            selector ^= (g ^ 4u) << (4 * kk);
+            evq_accumulate_smem(row, sacc, g, tid, P.dense_state, err);
+          }
+        }
+      }
+      evq_accumulate_narrow(cols, j, selector, nacc);
+    }
 #else
 #pragma unroll
     for (int k = 0; k < EVQ_RPT; ++k) {
@@ -414,6 +469,9 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
 #if EVQ_TIER == 1
 #if EVQ_G1 > 1
   for (u32 g = 0; g < EVQ_G1; ++g) evq_state_flush_smem(sacc, g, tid, P.dense_state);
+#if EVQ_NNARROW > 0
+  evq_narrow_flush(nacc, P.dense_state);
+#endif
 #else
   evq_state_flush_regs(racc, P.dense_state);
 #endif

@@ -317,10 +317,15 @@ static void fit_shape(evqgpu_query& q, KernelShape& s, std::vector<TablePlan>& p
   for (int attempt = 0; attempt < 4; ++attempt) {
     s.ncons = (attempt & 1) ? 128 : 256;
     s.nstages = (attempt & 2) ? 2 : 3;
-    if (s.fast) {   // 8 consecutive rows per thread first: halves the per-thread fixed work of every tile
+    if (s.fast) {
+      // 8 consecutive rows per thread first (halves the per-thread fixed work of every tile).  The kernel is bound by
+      // dependent shared-memory / ALU chains, not by the depth of the copy pipeline (profiles/r01_sweep_q1.txt: 2, 3 and 4
+      // stages time the same, every extra resident CTA adds throughput): 2 stages, as many CTAs per SM as fit
       s.ncons = (attempt & 1) ? 256 : 128;
+      s.nstages = 2;
       if (const char* e = getenv("EVQGPU_FAST_NCONS")) s.ncons = atoi(e) == 256 ? 256 : 128;
     }
+    if (const char* e = getenv("EVQGPU_NSTAGES")) s.nstages = std::max(2, std::min(4, atoi(e)));
     size_t worst = 0;
     for (auto& p : plans) {
       p.layout = stage_layout(q, p.table, p.binding, s);
@@ -331,7 +336,7 @@ static void fit_shape(evqgpu_query& q, KernelShape& s, std::vector<TablePlan>& p
       // as many CTAs per SM as shared memory allows (latency hiding for the decode phases), within the register budget
       // the launch bounds leave per thread: 2 x 288 threads or 4 x 160 threads
       const int by_smem = (int) ((227 * 1024) / (worst + 1024));
-      const int cap = s.ncons <= 128 ? 4 : 2;
+      const int cap = s.ncons <= 128 ? 5 : 2;
       s.min_ctas = std::max(1, std::min(by_smem, cap));
       if (const char* e = getenv("EVQGPU_MAX_CTAS")) s.min_ctas = std::max(1, std::min(s.min_ctas, atoi(e)));
       return;
@@ -583,6 +588,7 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
     if (!dense) { s.tier = 2; s.g1 = 1; }
   }
   if (s.tier == 1 && s.g1 > 1) s.dense = dm;
+  layout_narrow(q, s);
   fit_shape(q, s, plans);
   q.shape = s;
   q.dense = dm;

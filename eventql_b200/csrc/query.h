@@ -35,6 +35,7 @@ struct ColSig {
   uint32_t bits = 64;      // every value < 2^bits (max over the scanned tables)
   uint32_t leb_len = 10;   // LEB128: longest value in bytes (max over the scanned tables)
   int gen_slot = -1;       // fast kernel: index among the LEB128 columns that may need the boundary search (leb_len >= 2)
+  bool packed = false;     // fast kernel: keep the column's raw bytes (4 rows per word) for the dp4a aggregates
 };
 
 struct DenseMap {
@@ -90,6 +91,11 @@ struct evqgpu_query {
   std::vector<int> state_carry_of;  // for a carry word: index of the sum word whose wraps it counts, else -1
   std::vector<int> state_smem;      // index of the word among the thread-private accumulators (-1 for carry words)
   int nstate_smem = 0;
+  // byte-wide aggregates of the fast dense kernel (rows counter, sums of 1-byte columns): accumulated with dp4a into
+  // thread-private u32 registers instead of shared memory (codegen.cc: layout_narrow)
+  std::vector<int> state_narrow;    // index among the narrow accumulators, -1 otherwise
+  std::vector<int> narrow_col;      // per narrow accumulator: input column whose bytes are summed, -1 = rows counter
+  int nnarrow = 0;
   std::string merge_checked_layout;  // state layout all ranks were last verified to share
   uint64_t expected_groups = 0;
   std::vector<bool> col_used;
@@ -127,6 +133,7 @@ namespace evq {
 // codegen.cc
 std::string generate_source(const evqgpu_query& q, const KernelShape& shape);
 void layout_states(evqgpu_query& q, const KernelShape& shape);
+void layout_narrow(evqgpu_query& q, const KernelShape& shape);   // after tier / g1 are known
 int gen_chunks(const KernelShape& shape);
 // query.cu
 void emit_results(evqgpu_query& q);
