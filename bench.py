@@ -36,7 +36,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="evq", choices=["evq", "reference"])
-    ap.add_argument("--workload", default="c3_q1", choices=["c3_q1", "c2_q6", "c4_highcard", "c5_timeseries"])
+    ap.add_argument("--workload", default="c3_q1", choices=["c3_q1", "c3_q1_plain", "c2_q6", "c4_highcard", "c5_timeseries"])
     ap.add_argument("--rows-per-partition", type=int, default=0, help="0 = the workload's default")
     ap.add_argument("--partitions-per-gpu", type=int, default=0, help="0 = the workload's default")
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -56,6 +56,10 @@ def workload(name):
     if name == "c3_q1":
         return dict(spec=lambda p: T.lineitem_spec(), query=lambda s: T.q1(s), alias="lineitem", rows=125_000_000, parts=8,
                     desc="C3: TPC-H-Q1-style scan+filter+GROUP BY (4 groups, 8 aggregates + 3 means), lineitem UINT64_LEB128")
+    if name == "c3_q1_plain":
+        from eventql_b200 import plan as P
+        return dict(spec=lambda p: T.lineitem_spec(P.ENC_UINT64_PLAIN), query=lambda s: T.q1(s), alias="lineitem", rows=125_000_000, parts=2,
+                    desc="C3 (PLAIN twin): the same Q1 over lineitem stored UINT64_PLAIN (56 B/row)")
     if name == "c2_q6":
         return dict(spec=lambda p: T.lineitem_spec(), query=lambda s: T.q6(s), alias="lineitem", rows=100_000_000, parts=1,
                     desc="C2: TPC-H-Q6-style selective filter + global SUM, 100 M-row lineitem UINT64_LEB128")
@@ -357,7 +361,7 @@ def evq_arm(args):
 
     # correctness guard inside the bench: the per-group counts must add up to the rows that passed WHERE on all ranks
     # (96.4 % of the rows pass Q1's shipdate predicate by construction)
-    if args.workload == "c3_q1":
+    if args.workload in ("c3_q1", "c3_q1_plain"):
         cnt = sum(r[2] for r in result_rows)
         passed = stats["rows_passed"]
         if world > 1:

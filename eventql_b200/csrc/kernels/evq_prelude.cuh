@@ -37,16 +37,18 @@ __device__ __forceinline__ void evq_mbar_arrive_expect_tx(u64* bar, u32 bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(evq_smem_u32(bar)), "r"(bytes) : "memory");
 }
 
+// potentially-blocking wait: the hardware suspends the warp up to the time hint instead of spinning on the barrier
+// (a spinning producer warp would otherwise burn issue slots the consumer warps need)
 __device__ __forceinline__ void evq_mbar_wait(u64* bar, u32 parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "EVQ_WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra EVQ_WAIT_DONE;\n"
       "bra EVQ_WAIT_LOOP;\n"
       "EVQ_WAIT_DONE:\n"
-      "}\n" :: "r"(evq_smem_u32(bar)), "r"(parity) : "memory");
+      "}\n" :: "r"(evq_smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
 
 // TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP).
@@ -143,6 +145,76 @@ __device__ __forceinline__ void evq_producer_issue(const EvqScanParams& P, u32 t
   if (lane == 0) evq_mbar_arrive_expect_tx(full_bar, total);
   __syncwarp();
   if (bytes) evq_bulk_g2s(stage + dst_off, src, bytes, full_bar);
+}
+
+// The same in two steps, so that the index loads of the NEXT tile are in flight while the producer still waits for a free
+// stage: plan (global loads of the row-tile index, no shared-memory side effects), then commit (descriptor + copy).
+struct EvqCopyPlan {
+  const u8* src;
+  u32 bytes;
+  EvqStreamDesc desc;
+};
+
+__device__ __forceinline__ void evq_producer_plan(const EvqScanParams& P, const EvqStream& S, bool active, u32 tile, EvqCopyPlan& cp) {
+  cp.src = 0;
+  cp.bytes = 0;
+  if (!active || tile >= P.num_tiles) return;
+  const u64 row0 = (u64) tile * EVQ_TILE_ROWS;
+  const u64 rem = P.num_rows - row0;
+  const u32 rows = rem < EVQ_TILE_ROWS ? (u32) rem : EVQ_TILE_ROWS;
+  u64 start, end;
+  u32 nvals = rows, skew = 0;
+  if (S.kind == EVQ_KIND_LEVEL) {
+    const u64 blk0 = row0 >> 7, blk1 = (row0 + rows + 127) >> 7;
+    start = blk0 * 16 * S.bits;
+    end = blk1 * 16 * S.bits;
+  } else {
+    u64 v0 = row0, v1 = row0 + rows;
+    if (S.val_index) {
+      v0 = S.val_index[tile];
+      v1 = S.val_index[tile + 1];
+    }
+    nvals = (u32) (v1 - v0);
+    if (S.kind == EVQ_KIND_PLAIN64) {
+      start = v0 * 8; end = v1 * 8;
+    } else if (S.kind == EVQ_KIND_PLAIN32) {
+      start = v0 * 4; end = v1 * 4;
+    } else if (S.kind == EVQ_KIND_BITPACK) {
+      const u64 blk0 = v0 >> 7, blk1 = (v1 + 127) >> 7;
+      start = blk0 * 16 * S.bits;
+      end = blk1 * 16 * S.bits;
+      skew = (u32) (v0 - (blk0 << 7));
+    } else {
+      start = S.off_index[tile];
+      end = S.off_index[tile + 1];
+    }
+  }
+  const u64 al = start & ~15ull;
+  u32 bytes = (u32) (((end - al) + 15) & ~15ull);
+  if (end == start) bytes = 0;
+  if (bytes > S.smem_cap) {   // the host sized the stage from the tile index: cannot happen unless that is wrong
+    atomicOr(P.status, EVQ_ERR_STAGE_OVERFLOW);
+    bytes = S.smem_cap & ~15u;
+  }
+  cp.src = S.base + al;
+  cp.bytes = bytes;
+  cp.desc.delta = (u32) (start - al);
+  cp.desc.nbytes = (u32) (end - start);
+  cp.desc.nvals = nvals;
+  cp.desc.skew = skew;
+}
+
+__device__ __forceinline__ void evq_producer_commit(const EvqStream& S, bool active, const EvqCopyPlan& cp, u8* stage, EvqStreamDesc* desc,
+                                                    u64* full_bar) {
+  const u32 lane = evq_lane();
+  if (active) desc[lane] = cp.desc;
+  u32 total = cp.bytes;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+  __syncwarp();
+  if (lane == 0) evq_mbar_arrive_expect_tx(full_bar, total);
+  __syncwarp();
+  if (cp.bytes) evq_bulk_g2s(stage + S.smem_off, cp.src, cp.bytes, full_bar);
 }
 
 // ---- decoders over the staged tile ------------------------------------------------------------------------------------

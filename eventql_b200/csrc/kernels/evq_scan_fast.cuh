@@ -87,30 +87,31 @@ __device__ __forceinline__ u32 evq_fast_prep_b(const EvqTile& T, const EvqScanPa
   const EvqStreamDesc d = T.desc[S];
   const u32 first = EVQ_RPT * T.ctid;
   if (first == 0u || first >= d.nvals) return 0u;
-  u32 r = first - 1u;                              // number of the terminator in front of the value
-  // warp whose chunks hold it
-  u32 w = 0;
+  const u32 r = first - 1u;                        // number (in the tile) of the terminator in front of the value
+  u32 wt[EVQ_NWARPS];
 #pragma unroll
-  for (int i = 0; i < EVQ_NWARPS - 1; ++i) {
-    const u32 n = scr->wtot[G][i];
-    const bool beyond = (w == (u32) i) && r >= n;
-    r -= beyond ? n : 0u;
-    w += beyond ? 1u : 0u;
-  }
+  for (int i = 0; i < EVQ_NWARPS - 1; ++i) wt[i] = scr->wtot[G][i];
   const u32 tb = d.delta + d.nbytes;
   const u32 nchunks = (tb + 15u) >> 4;
   const u32 per = (nchunks + EVQ_NCONS - 1) / EVQ_NCONS;
-  // last chunk of warp w whose "before" count is <= r
-  u32 lo = w * 32u * per;
-  u32 hi = lo + 32u * per;
-  hi = hi < nchunks ? hi : nchunks;
-  while (hi - lo > 1u) {
-    const u32 mid = (lo + hi) >> 1;
-    if ((scr->chunk[G][mid] >> 16) <= r) lo = mid; else hi = mid;
-  }
-  const u32 e = scr->chunk[G][lo];
+  const u32 span = 32u * per;                      // chunks per warp
+  // terminators in front of chunk c: the warp-local count of the chunk table + the totals of the warps before it
+  auto before = [&](u32 c, u32& entry) -> u32 {
+    entry = scr->chunk[G][c];
+    u32 base = entry >> 16;
+#pragma unroll
+    for (int i = 1; i < EVQ_NWARPS; ++i) base += c >= (u32) i * span ? wt[i - 1] : 0u;
+    return base;
+  };
+  // values have nearly uniform length inside a tile: start at the interpolated chunk and walk (typically 0-1 steps)
+  u32 lo = (u32) ((float) r * __fdividef((float) nchunks, (float) d.nvals));
+  lo = lo < nchunks ? lo : nchunks - 1u;
+  u32 e;
+  u32 b = before(lo, e);
+  while (b > r) { --lo; b = before(lo, e); }
+  while (lo + 1u < nchunks && b + __popc(e & 0xffffu) <= r) { ++lo; b = before(lo, e); }
   u32 m = e & 0xffffu;
-  for (u32 k = r - (e >> 16); k > 0u; --k) m &= m - 1u;
+  for (u32 k = r - b; k > 0u; --k) m &= m - 1u;
   return 16u * lo + (u32) __ffs(m) - d.delta;      // (__ffs - 1) is the terminator's byte; the value starts behind it
 }
 
@@ -303,12 +304,22 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
 
   if (tid >= EVQ_NCONS) {
     // ===================== producer warp: one TMA bulk copy per column stream and tile =====================
+    // lane i owns stream i; its descriptor lives in registers, and the row-tile index of the next tile is read while
+    // the warp still waits for that tile's stage to be released
+    const u32 lane = evq_lane();
+    const bool active = lane < P.num_streams;
+    EvqStream S;
+    S.base = 0; S.off_index = 0; S.val_index = 0; S.nbytes = 0; S.kind = 0; S.bits = 0; S.smem_off = 0; S.smem_cap = 0;
+    if (active) S = P.streams[lane];
+    EvqCopyPlan cp;
+    evq_producer_plan(P, S, active, first_tile, cp);
     u32 it = 0;
     for (u32 tile = first_tile; tile < P.num_tiles; tile += tile_step, ++it) {
       const u32 s = it % EVQ_NSTAGES;
       const u32 round = it / EVQ_NSTAGES;
       if (round > 0) evq_mbar_wait(&hdr->empty[s], (round - 1) & 1u);
-      evq_producer_issue(P, tile, stages + (size_t) s * stage_bytes, hdr->desc[s], &hdr->full[s]);
+      evq_producer_commit(S, active, cp, stages + (size_t) s * stage_bytes, hdr->desc[s], &hdr->full[s]);
+      evq_producer_plan(P, S, active, tile + tile_step, cp);
     }
     return;
   }
