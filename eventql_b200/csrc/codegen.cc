@@ -537,10 +537,11 @@ static std::string gen_row_functions(const evqgpu_query& q, const KernelShape& s
       os << "}\n";
     }
   } else if (shape.tier == 2) {
-    os << "#define EVQ_UPD(st, op, v) evq_state_atomic<op>(state + (u64) (st) * cap + slot, (v))\n";
-    os << "#define EVQ_UPD_C(st, cw, v) { const u64 _v = (v); const u64 _o = atomicAdd(state + (u64) (st) * cap + slot, _v); "
-          "if (_o + _v < _v) atomicAdd(state + (u64) (cw) * cap + slot, 1ull); }\n";
-    os << "__device__ __forceinline__ void evq_accumulate_global(const EvqRow& row, u64* state, u64 cap, u64 slot, u32& err) {\n";
+    // `state` = the group's state words inside its slot (kernels/evq_abi.h EvqHashTable)
+    os << "#define EVQ_UPD(st, op, v) evq_state_atomic<op>(state + (st), (v))\n";
+    os << "#define EVQ_UPD_C(st, cw, v) { const u64 _v = (v); const u64 _o = atomicAdd(state + (st), _v); "
+          "if (_o + _v < _v) atomicAdd(state + (cw), 1ull); }\n";
+    os << "__device__ __forceinline__ void evq_accumulate_global(const EvqRow& row, u64* state, u32& err) {\n";
     gen_updates(os, q, shape);
     os << "}\n#undef EVQ_UPD\n#undef EVQ_UPD_C\n";
   } else if (shape.tier == 3) {
@@ -582,9 +583,9 @@ static std::string gen_group_kernels(const evqgpu_query& q, const KernelShape& s
     for (int s = 0; s < nstate; ++s)
       os << "  I.dense_state[i * " << nstate << " + " << s << "] = evq_state_identity<" << q.state_ops[s] << ">();\n";
   } else {
-    os << "  I.ht.fp[i] = 0ull;\n";
+    os << "  u64* sp = I.ht.slots + i * I.ht.stride;\n  sp[0] = 0ull;\n";
     for (int s = 0; s < nstate; ++s)
-      os << "  I.ht.state[(u64) " << s << " * I.ht.cap + i] = evq_state_identity<" << q.state_ops[s] << ">();\n";
+      os << "  sp[" << 1 + nk + s << "] = evq_state_identity<" << q.state_ops[s] << ">();\n";
   }
   os << "}\n";
 
@@ -604,11 +605,11 @@ static std::string gen_group_kernels(const evqgpu_query& q, const KernelShape& s
       os << "    key[" << i << "] = ktag[" << i << "] ? 0ull : E.key_min[" << i << "] + idx;\n  }\n";
     }
   } else {
-    os << "  if (E.ht.fp[slot] == 0) return;\n";
-    for (int s = 0; s < nstate; ++s) os << "  st[" << s << "] = E.ht.state[(u64) " << s << " * E.ht.cap + slot];\n";
+    os << "  const u64* sp = E.ht.slots + slot * E.ht.stride;\n  const u64 fp = sp[0];\n  if (fp == 0) return;\n";
+    for (int s = 0; s < nstate; ++s) os << "  st[" << s << "] = sp[" << 1 + nk + s << "];\n";
     for (int i = 0; i < nk; ++i) {
-      os << "  key[" << i << "] = E.ht.keys[(u64) " << i << " * E.ht.cap + slot];\n";
-      os << "  ktag[" << i << "] = E.ht.ktags[(u64) " << i << " * E.ht.cap + slot];\n";
+      os << "  key[" << i << "] = sp[" << 1 + i << "];\n";
+      os << "  ktag[" << i << "] = (u32) (fp >> " << 2 + i << ") & 1u;\n";
     }
   }
   os << "  const u64 out_row = atomicAdd(E.out_count, 1ull);\n  if (out_row >= E.out_capacity) return;\n";

@@ -43,12 +43,18 @@ struct EvqStream {
   u32 smem_cap;          // bytes reserved in a stage
 };
 
+// Global group table (tier 2): open addressing, linear probing, array of slots.  One slot = `stride` 64-bit words:
+//   [0]                fingerprint word: bit 0 = occupied, bit 1 = the claiming thread still writes the keys,
+//                      bits 2..9 = NULL tags of keys 0..7, bits 10..63 = hash bits
+//   [1 .. nkeys]       raw 64-bit key values
+//   [1 + nkeys ..]     aggregate state words
+// so that probing a group, comparing its key and updating its aggregates touch ONE 64-byte DRAM atom for the usual
+// <= 7 payload words (the table is far larger than L2: every distinct line touched per row is HBM traffic).
 struct EvqHashTable {
-  u64* fp;      // [cap] 0 = empty; bit0 = 1 always; bit1 = 1 while the claiming thread still writes the key
-  u64* keys;    // [nkeys][cap] raw 64-bit key values
-  u8* ktags;    // [nkeys][cap] STag of each key value
-  u64* state;   // [nstate][cap] aggregate states
-  u64 cap;      // power of two
+  u64* slots;
+  u64 cap;       // slots, power of two
+  u32 stride;    // words per slot, multiple of 4
+  u32 nkeys;
 };
 
 struct EvqScanParams {

@@ -363,44 +363,43 @@ __device__ __forceinline__ void evq_st_l2_u8(u8* p, u32 v) {
   asm volatile("st.relaxed.gpu.global.u8 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
-// find or claim the slot of a key tuple. Returns the slot, or ~0ull when the table is full.
+// find or claim the slot of a key tuple. Returns the slot's first word, or 0 when the table is full.
 template <int NK>
-__device__ __forceinline__ u64 evq_ht_upsert(const EvqHashTable& H, const u64* key, const u32* tag, u64* claimed_counter) {
+__device__ __forceinline__ u64* evq_ht_upsert(const EvqHashTable& H, const u64* key, const u32* tag, u64* claimed_counter) {
   u64 h = 0x9e3779b97f4a7c15ull;
+  u64 tagbits = 0;
 #pragma unroll
-  for (int i = 0; i < NK; ++i) h = evq_mix64(h ^ key[i] ^ ((u64) tag[i] << 57)) + 0x632be59bd9b4e019ull * (u64) (i + 1);
-  const u64 fpv = (h & ~3ull) | 1ull;
+  for (int i = 0; i < NK; ++i) {
+    h = evq_mix64(h ^ key[i] ^ ((u64) tag[i] << 57)) + 0x632be59bd9b4e019ull * (u64) (i + 1);
+    tagbits |= (u64) (tag[i] & 1u) << (2 + i);
+  }
+  const u64 fpv = (h & ~0x3ffull) | tagbits | 1ull;
   const u64 mask = H.cap - 1;
-  u64 slot = (h >> 7) & mask;
+  u64 slot = (h >> 10) & mask;
   for (u64 probes = 0; probes <= mask; ++probes) {
-    u64 cur = evq_ld_l2(H.fp + slot);
+    u64* s = H.slots + slot * H.stride;
+    u64 cur = evq_ld_l2(s);
     if (cur == 0) {
-      cur = atomicCAS(H.fp + slot, 0ull, fpv | 2ull);
+      cur = atomicCAS(s, 0ull, fpv | 2ull);
       if (cur == 0) {
 #pragma unroll
-        for (int i = 0; i < NK; ++i) {
-          evq_st_l2(H.keys + (u64) i * H.cap + slot, key[i]);
-          evq_st_l2_u8(H.ktags + (u64) i * H.cap + slot, tag[i]);
-        }
+        for (int i = 0; i < NK; ++i) evq_st_l2(s + 1 + i, key[i]);
         __threadfence();
-        evq_st_l2(H.fp + slot, fpv);
+        evq_st_l2(s, fpv);
         atomicAdd(claimed_counter, 1ull);
-        return slot;
+        return s;
       }
     }
     if ((cur | 2ull) == (fpv | 2ull)) {
-      while (cur & 2ull) cur = evq_ld_l2(H.fp + slot);   // the claimant is still writing the key
+      while (cur & 2ull) cur = evq_ld_l2(s);   // the claimant is still writing the keys
       bool same = true;
 #pragma unroll
-      for (int i = 0; i < NK; ++i) {
-        same = same && (evq_ld_l2(H.keys + (u64) i * H.cap + slot) == key[i]) &&
-               (evq_ld_l2_u8(H.ktags + (u64) i * H.cap + slot) == (tag[i] & 0xffu));
-      }
-      if (same) return slot;
+      for (int i = 0; i < NK; ++i) same = same && evq_ld_l2(s + 1 + i) == key[i];
+      if (same) return s;
     }
     slot = (slot + 1) & mask;
   }
-  return ~0ull;
+  return (u64*) 0;
 }
 
 // ---- aggregate state updates ------------------------------------------------------------------------------------------

@@ -461,11 +461,11 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
         u64 key[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
         u32 ktag[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
         evq_keys(row, key, ktag, err);
-        const u64 slot = evq_ht_upsert<EVQ_NKEYS>(P.ht, key, ktag, P.counters + 1);
-        if (slot == ~0ull) {
+        u64* sp = evq_ht_upsert<EVQ_NKEYS>(P.ht, key, ktag, P.counters + 1);
+        if (!sp) {
           err |= EVQ_ERR_TABLE_FULL;
         } else {
-          evq_accumulate_global(row, P.ht.state, P.ht.cap, slot, err);
+          evq_accumulate_global(row, sp + 1 + EVQ_NKEYS, err);
         }
       }
 #endif

@@ -98,7 +98,7 @@ __global__ void k_merge_count(EvqHashTable H, int nranks, u64* __restrict__ coun
   if (threadIdx.x < 16) local[threadIdx.x] = 0;
   __syncthreads();
   for (u64 slot = (u64) blockIdx.x * blockDim.x + threadIdx.x; slot < H.cap; slot += (u64) gridDim.x * blockDim.x) {
-    const u64 fp = H.fp[slot];
+    const u64 fp = H.slots[slot * H.stride];
     if (fp) atomicAdd(&local[owner_of(fp, nranks)], 1u);
   }
   __syncthreads();
@@ -109,26 +109,28 @@ __global__ void k_merge_pack(EvqHashTable H, int nranks, MergeOps mo, const u64*
                              u64* __restrict__ out) {
   const int rec = mo.nkeys + 1 + mo.nstate;
   for (u64 slot = (u64) blockIdx.x * blockDim.x + threadIdx.x; slot < H.cap; slot += (u64) gridDim.x * blockDim.x) {
-    const u64 fp = H.fp[slot];
+    const u64* sp = H.slots + slot * H.stride;
+    const u64 fp = sp[0];
     if (!fp) continue;
     const u32 o = owner_of(fp, nranks);
     const u64 pos = offsets[o] + atomicAdd(cursors + o, 1ull);
     u64* dst = out + pos * rec;
     u64 tags = 0;
     for (int k = 0; k < mo.nkeys; ++k) {
-      dst[k] = H.keys[(u64) k * H.cap + slot];
-      tags |= (u64) H.ktags[(u64) k * H.cap + slot] << (8 * k);
+      dst[k] = sp[1 + k];
+      tags |= ((fp >> (2 + k)) & 1ull) << (8 * k);
     }
     dst[mo.nkeys] = tags;
-    for (int s = 0; s < mo.nstate; ++s) dst[mo.nkeys + 1 + s] = H.state[(u64) s * H.cap + slot];
+    for (int s = 0; s < mo.nstate; ++s) dst[mo.nkeys + 1 + s] = sp[1 + mo.nkeys + s];
   }
 }
 
 __global__ void k_merge_init(EvqHashTable H, MergeOps mo) {
   const u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= H.cap) return;
-  H.fp[i] = 0ull;
-  for (int s = 0; s < mo.nstate; ++s) H.state[(u64) s * H.cap + i] = merge_identity(mo.ops[s]);
+  u64* sp = H.slots + i * H.stride;
+  sp[0] = 0ull;
+  for (int s = 0; s < mo.nstate; ++s) sp[1 + mo.nkeys + s] = merge_identity(mo.ops[s]);
 }
 
 template <int NK>
@@ -145,20 +147,21 @@ __global__ void k_merge_insert(EvqHashTable H, MergeOps mo, const u64* __restric
       key[k] = src[k];
       tag[k] = (u32) ((tags >> (8 * k)) & 0xffu);
     }
-    const u64 slot = evq_ht_upsert<NK>(H, key, tag, counters + 1);
-    if (slot == ~0ull) {
+    u64* sp = evq_ht_upsert<NK>(H, key, tag, counters + 1);
+    if (!sp) {
       atomicOr(status, EVQ_ERR_TABLE_FULL);
       continue;
     }
+    u64* state = sp + 1 + NK;
     for (int s = 0; s < mo.nstate; ++s) {
       const u64 v = src[NK + 1 + s];
       if (mo.carry_at[s] >= 0) {
         if (v) {
-          const u64 old = atomicAdd(H.state + (u64) s * H.cap + slot, v);
-          if (old + v < v) atomicAdd(H.state + (u64) mo.carry_at[s] * H.cap + slot, 1ull);
+          const u64 old = atomicAdd(state + s, v);
+          if (old + v < v) atomicAdd(state + mo.carry_at[s], 1ull);
         }
       } else if (v != merge_identity(mo.ops[s])) {
-        merge_atomic(mo.ops[s], H.state + (u64) s * H.cap + slot, v);
+        merge_atomic(mo.ops[s], state + s, v);
       }
     }
   }
@@ -250,18 +253,11 @@ static void merge_hash(evqgpu_query& q) {
   // 4. all-to-all over NVLink
   comm_all_to_all(ctx, sendbuf.p, send_off.data(), send_bytes.data(), recvbuf.p, recv_off.data(), recv_bytes.data());
   // 5. owner-side merge into a fresh table
-  const size_t nk = std::max<size_t>(1, (size_t) mo.nkeys);
   const uint64_t cap = next_pow2_(std::max<uint64_t>(1024, recv_total * 2));
-  DevBuf fp, keys, ktags, state;
-  fp.alloc(cap * 8);
-  keys.alloc(cap * 8 * nk);
-  ktags.alloc(cap * nk);
-  state.alloc(cap * 8 * mo.nstate);
-  EvqHashTable M;
-  M.fp = fp.as<u64>();
-  M.keys = keys.as<u64>();
-  M.ktags = ktags.as<u8>();
-  M.state = state.as<u64>();
+  DevBuf slots;
+  slots.alloc(cap * 8 * H.stride);
+  EvqHashTable M = H;
+  M.slots = slots.as<u64>();
   M.cap = cap;
   k_merge_init<<<(unsigned) ((cap + 255) / 256), 256, 0, ctx->stream>>>(M, mo);
   EVQ_CUDA(cudaGetLastError());
@@ -286,10 +282,7 @@ static void merge_hash(evqgpu_query& q) {
   ctx->kernel_launches += 4;
   q.stats.kernel_launches += 4;
   // the merged table replaces the local one
-  q.ht_fp = std::move(fp);
-  q.ht_keys = std::move(keys);
-  q.ht_ktags = std::move(ktags);
-  q.ht_state = std::move(state);
+  q.ht_slots = std::move(slots);
   q.ht_cap = 0;   // next execute sizes its table afresh
   q.emit.ht = M;
   q.emit.slots = cap;

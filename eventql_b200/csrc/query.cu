@@ -631,14 +631,11 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
       want = next_pow2(std::max<uint64_t>(1024, est * 2));
     }
     q.ht_cap = want;
-    ensure(q.ht_fp, want * 8);
-    ensure(q.ht_keys, want * 8 * std::max<size_t>(1, nk));
-    ensure(q.ht_ktags, want * std::max<size_t>(1, nk));
-    ensure(q.ht_state, want * 8 * nstate);
-    base.ht.fp = q.ht_fp.as<u64>();
-    base.ht.keys = q.ht_keys.as<u64>();
-    base.ht.ktags = q.ht_ktags.as<u8>();
-    base.ht.state = q.ht_state.as<u64>();
+    const uint32_t stride = (uint32_t) round_up(1 + nk + nstate, 4);   // whole 32-byte sectors; 8 words = one 64-byte DRAM atom
+    ensure(q.ht_slots, want * 8 * stride);
+    base.ht.slots = q.ht_slots.as<u64>();
+    base.ht.stride = stride;
+    base.ht.nkeys = (u32) nk;
     base.ht.cap = want;
     ip.ht = base.ht;
     ip.slots = want;

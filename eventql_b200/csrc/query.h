@@ -102,7 +102,7 @@ struct evqgpu_query {
 
   // device state, reused across executions
   evq::DevBuf merge_recv;
-  evq::DevBuf dense_state, ht_fp, ht_keys, ht_ktags, ht_state, status, counters, out_count, tile_counts, tile_base;
+  evq::DevBuf dense_state, ht_slots, status, counters, out_count, tile_counts, tile_base;
   std::vector<evq::DevBuf> out_cols;
   uint64_t out_capacity = 0;
   uint64_t ht_cap = 0;
