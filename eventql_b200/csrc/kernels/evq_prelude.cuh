@@ -363,9 +363,9 @@ __device__ __forceinline__ void evq_st_l2_u8(u8* p, u32 v) {
   asm volatile("st.relaxed.gpu.global.u8 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
-// find or claim the slot of a key tuple. Returns the slot's first word, or 0 when the table is full.
+// hash of a key tuple -> fingerprint word and home slot
 template <int NK>
-__device__ __forceinline__ u64* evq_ht_upsert(const EvqHashTable& H, const u64* key, const u32* tag, u64* claimed_counter) {
+__device__ __forceinline__ void evq_ht_hash(const EvqHashTable& H, const u64* key, const u32* tag, u64& fpv, u64& slot) {
   u64 h = 0x9e3779b97f4a7c15ull;
   u64 tagbits = 0;
 #pragma unroll
@@ -373,12 +373,26 @@ __device__ __forceinline__ u64* evq_ht_upsert(const EvqHashTable& H, const u64* 
     h = evq_mix64(h ^ key[i] ^ ((u64) tag[i] << 57)) + 0x632be59bd9b4e019ull * (u64) (i + 1);
     tagbits |= (u64) (tag[i] & 1u) << (2 + i);
   }
-  const u64 fpv = (h & ~0x3ffull) | tagbits | 1ull;
+  fpv = (h & ~0x3ffull) | tagbits | 1ull;
+  slot = (h >> 10) & (H.cap - 1);
+}
+
+// the first two words of a slot (fingerprint, key 0) in one 16-byte load: issued for several rows before any of them is
+// resolved, so that the DRAM round trips of a thread's rows overlap instead of queueing behind each other
+__device__ __forceinline__ void evq_ht_prefetch(const EvqHashTable& H, u64 slot, u64& w0, u64& w1) {
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(H.slots + slot * H.stride) : "memory");
+}
+
+// find or claim the slot of a key tuple, starting from a prefetched first probe (w0 = fingerprint word, w1 = key 0 of the
+// home slot).  Returns the slot's first word, or 0 when the table is full.
+template <int NK>
+__device__ __forceinline__ u64* evq_ht_upsert_from(const EvqHashTable& H, const u64* key, u64 fpv, u64 slot, u64 w0, u64 w1,
+                                                  u64* claimed_counter) {
   const u64 mask = H.cap - 1;
-  u64 slot = (h >> 10) & mask;
+  bool first = true;
   for (u64 probes = 0; probes <= mask; ++probes) {
     u64* s = H.slots + slot * H.stride;
-    u64 cur = evq_ld_l2(s);
+    u64 cur = first ? w0 : evq_ld_l2(s);
     if (cur == 0) {
       cur = atomicCAS(s, 0ull, fpv | 2ull);
       if (cur == 0) {
@@ -389,17 +403,34 @@ __device__ __forceinline__ u64* evq_ht_upsert(const EvqHashTable& H, const u64* 
         atomicAdd(claimed_counter, 1ull);
         return s;
       }
+      first = false;   // somebody else claimed it meanwhile: its keys must be (re)read
     }
     if ((cur | 2ull) == (fpv | 2ull)) {
+      const bool stale = !first || (cur & 2ull);
       while (cur & 2ull) cur = evq_ld_l2(s);   // the claimant is still writing the keys
       bool same = true;
 #pragma unroll
-      for (int i = 0; i < NK; ++i) same = same && evq_ld_l2(s + 1 + i) == key[i];
+      for (int i = 0; i < NK; ++i) {
+        u64 k = (i == 0 && !stale) ? w1 : evq_ld_l2(s + 1 + i);
+        // a prefetched key that differs under an equal fingerprint is re-read (the 16-byte load is not formally atomic)
+        if (i == 0 && !stale && k != key[0]) k = evq_ld_l2(s + 1);
+        same = same && k == key[i];
+      }
       if (same) return s;
     }
+    first = false;
     slot = (slot + 1) & mask;
   }
   return (u64*) 0;
+}
+
+// find or claim the slot of a key tuple. Returns the slot's first word, or 0 when the table is full.
+template <int NK>
+__device__ __forceinline__ u64* evq_ht_upsert(const EvqHashTable& H, const u64* key, const u32* tag, u64* claimed_counter) {
+  u64 fpv, slot, w0, w1;
+  evq_ht_hash<NK>(H, key, tag, fpv, slot);
+  evq_ht_prefetch(H, slot, w0, w1);
+  return evq_ht_upsert_from<NK>(H, key, fpv, slot, w0, w1, claimed_counter);
 }
 
 // ---- aggregate state updates ------------------------------------------------------------------------------------------

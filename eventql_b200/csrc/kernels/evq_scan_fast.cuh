@@ -410,6 +410,44 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
       }
     }
 #endif
+#elif EVQ_TIER == 2
+    // hash tier: the group table lives in HBM, every probe is a DRAM round trip.  Rows are handled in quads: first the
+    // home slots of all 4 rows are computed and their first probes issued, then the rows are resolved and their
+    // aggregates updated with fire-and-forget atomics.
+#pragma unroll
+    for (int j = 0; j < EVQ_RPT / 4; ++j) {
+      u64 key[4][EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
+      u64 fpv[4], slot[4], w0[4], w1[4];
+      bool pass[4];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const int k = 4 * j + kk;
+        EvqRow row;
+        evq_fast_row(cols, k, row);
+        pass[kk] = (EVQ_RPT * tid + k < T.rows) && evq_where(row, err);
+        fpv[kk] = slot[kk] = w0[kk] = w1[kk] = 0;
+        if (pass[kk]) {
+          u32 ktag[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
+          evq_keys(row, key[kk], ktag, err);
+          evq_ht_hash<EVQ_NKEYS>(P.ht, key[kk], ktag, fpv[kk], slot[kk]);
+          evq_ht_prefetch(P.ht, slot[kk], w0[kk], w1[kk]);
+        }
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        if (pass[kk]) {
+          ++passed;
+          u64* sp = evq_ht_upsert_from<EVQ_NKEYS>(P.ht, key[kk], fpv[kk], slot[kk], w0[kk], w1[kk], P.counters + 1);
+          if (!sp) {
+            err |= EVQ_ERR_TABLE_FULL;
+          } else {
+            EvqRow row;
+            evq_fast_row(cols, 4 * j + kk, row);
+            evq_accumulate_global(row, sp + 1 + EVQ_NKEYS, err);
+          }
+        }
+      }
+    }
 #elif EVQ_TIER == 1 && EVQ_G1 > 1 && EVQ_NNARROW > 0
     // dense tier with byte-wide aggregates: rows are handled in quads; the quad's selector (one nibble per row: dense slot,
     // or 4 = did not pass) drives the dp4a accumulators, the remaining (wide) words take the shared-memory path per row
