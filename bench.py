@@ -28,6 +28,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 EVQLREF = os.path.join(ROOT, "oracle", "_ref", "evqlref")
+_JSON_OUT = sys.stdout
 
 
 def parse_args():
@@ -197,7 +198,8 @@ def reference_arm(args):
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    _JSON_OUT.write(json.dumps(out) + "\n")
+    _JSON_OUT.flush()
     for f in files:
         try:
             os.unlink(f)
@@ -480,7 +482,8 @@ def evq_arm(args):
         }
         if strong:
             out["c3_strong"] = strong
-        print(json.dumps(out), flush=True)
+        _JSON_OUT.write(json.dumps(out) + "\n")
+        _JSON_OUT.flush()
     q.close()
     for t in tables:
         t.close()
@@ -491,10 +494,15 @@ def evq_arm(args):
 
 def main():
     args = parse_args()
+    # libraries (NCCL's version banner, torchrun's notices) write to stdout: keep fd 1 for the ONE JSON line
+    global _JSON_OUT
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.gpus > 1 and "RANK" not in os.environ:
         # convenience: re-launch under torchrun, one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr",
                "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"), os.path.abspath(__file__)] + sys.argv[1:]
+        os.dup2(_JSON_OUT.fileno(), 1)   # the ranks inherit the real stdout
         raise SystemExit(subprocess.call(cmd))
     if args.impl == "reference":
         reference_arm(args)

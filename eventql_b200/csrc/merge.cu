@@ -220,8 +220,8 @@ static void merge_hash(evqgpu_query& q) {
 
   EvqHashTable H = q.emit.ht;
   // 1. groups per owner
-  DevBuf counts;
-  counts.alloc(3 * 16 * 8);   // [0..16) counts, [16..32) offsets, [32..48) cursors
+  DevBuf& counts = q.merge_counts;
+  if (counts.bytes < 3 * 16 * 8) counts.alloc(3 * 16 * 8);   // [0..16) counts, [16..32) offsets, [32..48) cursors
   EVQ_CUDA(cudaMemsetAsync(counts.p, 0, counts.bytes, ctx->stream));
   const unsigned grid = (unsigned) std::min<uint64_t>((H.cap + 255) / 256, (uint64_t) ctx->sm_count * 8);
   k_merge_count<<<grid, 256, 0, ctx->stream>>>(H, n, counts.as<u64>());
@@ -244,9 +244,11 @@ static void merge_hash(evqgpu_query& q) {
     recv_total += from_r;
   }
   // 3. pack per owner
-  DevBuf sendbuf, recvbuf;
-  sendbuf.alloc(std::max<uint64_t>(send_total, 1) * rec * 8);
-  recvbuf.alloc(std::max<uint64_t>(recv_total, 1) * rec * 8);
+  // exchange buffers and the merged table are kept across executions (cudaMalloc of hundreds of MB per step would dominate)
+  DevBuf& sendbuf = q.merge_send;
+  DevBuf& recvbuf = q.merge_recv;
+  if (sendbuf.bytes < std::max<uint64_t>(send_total, 1) * rec * 8) sendbuf.alloc(std::max<uint64_t>(send_total, 1) * rec * 8 * 5 / 4);
+  if (recvbuf.bytes < std::max<uint64_t>(recv_total, 1) * rec * 8) recvbuf.alloc(std::max<uint64_t>(recv_total, 1) * rec * 8 * 5 / 4);
   EVQ_CUDA(cudaMemcpyAsync(counts.as<u64>() + 16, offs.data(), 16 * 8, cudaMemcpyHostToDevice, ctx->stream));
   k_merge_pack<<<grid, 256, 0, ctx->stream>>>(H, n, mo, counts.as<u64>() + 16, counts.as<u64>() + 32, sendbuf.as<u64>());
   EVQ_CUDA(cudaGetLastError());
@@ -254,8 +256,8 @@ static void merge_hash(evqgpu_query& q) {
   comm_all_to_all(ctx, sendbuf.p, send_off.data(), send_bytes.data(), recvbuf.p, recv_off.data(), recv_bytes.data());
   // 5. owner-side merge into a fresh table
   const uint64_t cap = next_pow2_(std::max<uint64_t>(1024, recv_total * 2));
-  DevBuf slots;
-  slots.alloc(cap * 8 * H.stride);
+  DevBuf& slots = q.merge_slots;
+  if (slots.bytes < cap * 8 * H.stride) slots.alloc(cap * 8 * H.stride);
   EvqHashTable M = H;
   M.slots = slots.as<u64>();
   M.cap = cap;
@@ -281,9 +283,7 @@ static void merge_hash(evqgpu_query& q) {
   }
   ctx->kernel_launches += 4;
   q.stats.kernel_launches += 4;
-  // the merged table replaces the local one
-  q.ht_slots = std::move(slots);
-  q.ht_cap = 0;   // next execute sizes its table afresh
+  // results are emitted from the merged table; the local table stays allocated for the next execution
   q.emit.ht = M;
   q.emit.slots = cap;
   q.emit_total_rows = std::max<uint64_t>(recv_total, 1);

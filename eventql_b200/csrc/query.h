@@ -101,7 +101,7 @@ struct evqgpu_query {
   std::vector<bool> col_used;
 
   // device state, reused across executions
-  evq::DevBuf merge_recv;
+  evq::DevBuf merge_recv, merge_send, merge_slots, merge_counts;
   evq::DevBuf dense_state, ht_slots, status, counters, out_count, tile_counts, tile_base;
   std::vector<evq::DevBuf> out_cols;
   uint64_t out_capacity = 0;
