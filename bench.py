@@ -285,6 +285,14 @@ def evq_arm(args):
     if world != args.gpus:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run --nproc-per-node %d)" % (args.gpus, world, args.gpus))
     torch.cuda.set_device(local)
+    # run (and allocate the pinned host buffers of the e2e leg) on the CPUs next to this GPU: the H2D copies of the
+    # encoded streams otherwise cross the socket interconnect
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+    except Exception:
+        pass
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = capi.Context(local)          # raises without a device: there is no CPU fallback

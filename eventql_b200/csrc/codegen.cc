@@ -392,12 +392,20 @@ static void gen_fast_layout(std::ostringstream& os, const KernelShape& shape) {
       default:
         if (c.leb_len <= 1 && c.packed) os << "    evq_fast_ld_leb1p<" << S << ">(T, P, raw, cols.p" << i << ");\n";
         else if (c.leb_len <= 1) os << "    evq_fast_ld_leb1<" << S << ">(T, P, raw);\n";
-        else if (c.leb_len <= 4)
-          os << "    evq_fast_ld_leb32<" << S << ", " << c.gen_slot << ", " << c.leb_len << ">(T, P, prep.general[" << c.gen_slot
-             << "], prep.start[" << c.gen_slot << "], raw);\n";
         else
-          os << "    evq_fast_ld_leb64<" << S << ", " << c.gen_slot << ", " << c.leb_len << ">(T, P, prep.general[" << c.gen_slot
-             << "], prep.start[" << c.gen_slot << "], raw);\n";
+        {
+          // where this thread's 8 values start: from the column's sub-index (staged with the tile), or searched by evq_fast_prep
+          std::string general, start;
+          if (c.sub_stream >= 0) {
+            general = "evq_fast_general<" + S + ", " + std::to_string(c.leb_len) + ">(T)";
+            start = "evq_fast_substart<" + std::to_string(c.sub_stream) + ">(T, P)";
+          } else {
+            general = "prep.general[" + std::to_string(c.gen_slot) + "]";
+            start = "prep.start[" + std::to_string(c.gen_slot) + "]";
+          }
+          os << "    evq_fast_ld_leb" << (c.leb_len <= 4 ? "32" : "64") << "<" << S << ", 0, " << c.leb_len << ">(T, P, " << general << ", "
+             << start << ", raw);\n";
+        }
         break;
     }
     std::string conv;

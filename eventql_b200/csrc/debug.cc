@@ -38,9 +38,12 @@ extern "C" int evqgpu_debug_generate(const evqgpu_query_desc* desc, const evqgpu
       if (cs.kind == EVQ_KIND_LEB128) cs.leb_slot = s.nleb++;
     }
     s.fast = s.nnull == 0;
+    s.use_subidx = s.fast && !getenv("EVQGPU_NO_SUBIDX");
     for (auto& c : s.cols) {
       c.gen_slot = -1;
-      if (s.fast && c.used && c.kind == EVQ_KIND_LEB128 && c.leb_len >= 2) c.gen_slot = s.ngen++;
+      if (!(s.fast && c.used && c.kind == EVQ_KIND_LEB128 && c.leb_len >= 2)) continue;
+      if (s.use_subidx) c.sub_stream = s.nstreams++;
+      else c.gen_slot = s.ngen++;
     }
     layout_states(q, s);
     const bool groupby = q.flags & EVQGPU_QUERY_GROUPBY;

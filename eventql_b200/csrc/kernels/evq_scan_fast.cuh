@@ -115,6 +115,17 @@ __device__ __forceinline__ u32 evq_fast_prep_b(const EvqTile& T, const EvqScanPa
   return 16u * lo + (u32) __ffs(m) - d.delta;      // (__ffs - 1) is the terminator's byte; the value starts behind it
 }
 
+// with a sub-index (Column::sub_index, staged with the tile as its own stream) nothing has to be searched
+template <int S, int L>
+__device__ __forceinline__ bool evq_fast_general(const EvqTile& T) {
+  return T.desc[S].nbytes != (u32) L * T.desc[S].nvals;
+}
+
+template <int X>
+__device__ __forceinline__ u32 evq_fast_substart(const EvqTile& T, const EvqScanParams& P) {
+  return (u32) ((const u16*) (T.stage + P.streams[X].smem_off + T.desc[X].delta))[T.ctid];   // EVQ_RPT == 8: one entry per thread
+}
+
 // ---- per-thread decode of 4 consecutive values -------------------------------------------------------------------------
 
 // index of the thread's first value inside the tile; threads past the end of a short tile decode (and discard) the

@@ -85,13 +85,19 @@ static void widen_shape(KernelShape& s, const KernelShape& o) {
   }
 }
 
-static void finish_shape(KernelShape& s) {
+static void finish_shape(KernelShape& s, bool have_subidx) {
+  if (getenv("EVQGPU_NO_FAST")) s.fast = false;
+  s.use_subidx = s.fast && have_subidx && !getenv("EVQGPU_NO_SUBIDX");
   s.ngen = 0;
   for (auto& c : s.cols) {
     c.gen_slot = -1;
-    if (s.fast && c.used && c.kind == EVQ_KIND_LEB128 && c.leb_len >= 2) c.gen_slot = s.ngen++;
+    c.sub_stream = -1;
+    if (!(s.fast && c.used && c.kind == EVQ_KIND_LEB128 && c.leb_len >= 2)) continue;
+    if (s.use_subidx) c.sub_stream = s.nstreams++;
+    else c.gen_slot = s.ngen++;
   }
-  if (getenv("EVQGPU_NO_FAST")) s.fast = false;
+  if (s.nstreams > EVQ_MAX_STREAMS)
+    fail(EVQGPU_ERR_UNSUPPORTED, "query reads %d column streams; the scan kernel stages at most %d", s.nstreams, EVQ_MAX_STREAMS);
 }
 
 // layout (not the value ranges) must agree between the partitions of one query
@@ -128,6 +134,7 @@ static StageLayout stage_layout(const evqgpu_query& q, evqgpu_table* t, const Bi
     };
     place(cs.data_stream, c.data_tile_cap);
     if (cs.nullable) place(cs.level_stream, c.level_tile_cap);
+    if (cs.sub_stream >= 0) place(cs.sub_stream, (EVQ_TILE_ROWS / 8) * 2);
   }
   L.stage_bytes = std::max<uint32_t>(off, 128);
   (void) q;
@@ -265,7 +272,15 @@ static KernelShape shape_of_plans(const evqgpu_query& q, const std::vector<Table
       fail(EVQGPU_ERR_UNSUPPORTED, "partitions of one query must share column encodings and nullability");
     widen_shape(s, o);
   }
-  finish_shape(s);
+  // every variable-length LEB128 column of every partition must carry a sub-index for the kernel to rely on it
+  bool have_subidx = true;
+  for (const auto& p : plans)
+    for (size_t i = 0; i < s.cols.size(); ++i) {
+      if (p.binding.col_index[i] < 0) continue;
+      const Column& c = p.table->cols[p.binding.col_index[i]];
+      if (c.data_kind == EVQ_KIND_LEB128 && s.cols[i].leb_len >= 2 && !c.sub_index.p) have_subidx = false;
+    }
+  finish_shape(s, have_subidx);
   return s;
 }
 
@@ -286,6 +301,17 @@ static void fill_streams(EvqScanParams& P, evqgpu_table* t, const Binding& b, co
     d.bits = c.data_bits;
     d.smem_off = L.smem_off[cs.data_stream];
     d.smem_cap = L.smem_cap[cs.data_stream];
+    if (cs.sub_stream >= 0) {
+      EvqStream& x = P.streams[cs.sub_stream];
+      x.base = c.sub_index.as<u8>();
+      x.off_index = nullptr;
+      x.val_index = nullptr;
+      x.nbytes = c.sub_index.bytes;
+      x.kind = EVQ_KIND_SUBIDX;
+      x.bits = 0;
+      x.smem_off = L.smem_off[cs.sub_stream];
+      x.smem_cap = L.smem_cap[cs.sub_stream];
+    }
     if (cs.nullable) {
       EvqStream& l = P.streams[cs.level_stream];
       l.base = c.dlevel.buf.as<u8>();
@@ -324,6 +350,7 @@ static void fit_shape(evqgpu_query& q, KernelShape& s, std::vector<TablePlan>& p
       s.ncons = (attempt & 1) ? 256 : 128;
       s.nstages = 2;
       if (const char* e = getenv("EVQGPU_FAST_NCONS")) s.ncons = atoi(e) == 256 ? 256 : 128;
+      if (s.use_subidx) s.ncons = 128;   // the sub-index holds the entry point of every 8th value = one per thread
     }
     if (const char* e = getenv("EVQGPU_NSTAGES")) s.nstages = std::max(2, std::min(4, atoi(e)));
     size_t worst = 0;

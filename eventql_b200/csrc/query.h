@@ -36,6 +36,7 @@ struct ColSig {
   uint32_t leb_len = 10;   // LEB128: longest value in bytes (max over the scanned tables)
   int gen_slot = -1;       // fast kernel: index among the LEB128 columns that may need the boundary search (leb_len >= 2)
   bool packed = false;     // fast kernel: keep the column's raw bytes (4 rows per word) for the dp4a aggregates
+  int sub_stream = -1;     // fast kernel: stream of the column's sub-index (entry points of every 8th value), -1 = none
 };
 
 struct DenseMap {
@@ -53,7 +54,8 @@ struct KernelShape {
   int min_ctas = 1;
   int nstreams = 0, nleb = 0, nnull = 0;
   bool fast = false;   // all referenced columns are required: kernels/evq_scan_fast.cuh (4 consecutive rows per thread)
-  int ngen = 0;        // fast kernel: LEB128 columns with leb_len >= 2
+  int ngen = 0;        // fast kernel: LEB128 columns with leb_len >= 2 whose value boundaries are searched in the kernel
+  bool use_subidx = false;   // fast kernel: variable-length columns take their decode entry points from Column::sub_index
   DenseMap dense;      // tier 1 with g1 > 1: the key -> slot map is baked into the kernel text as constants
 };
 

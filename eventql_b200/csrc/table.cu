@@ -185,6 +185,54 @@ __global__ void k_leb_select(const u8* __restrict__ data, u64 nbytes, const u64*
   off_index[t] = nbytes;   // fewer values than expected: the scan kernel never reads past nbytes
 }
 
+// sub_index[t][g] = byte offset, from the tile's first byte, at which value 8g of tile t starts.  One warp per tile walks
+// the tile's bytes in 16-byte chunks (32 chunks per step), numbers the terminator bytes with a warp scan and records the
+// byte behind every 8th one.
+__global__ void k_leb_sub_index(const u8* __restrict__ data, const u64* __restrict__ off_index, u32 num_tiles, u16* __restrict__ sub) {
+  const u32 tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u32 lane = threadIdx.x & 31;
+  if (tile >= num_tiles) return;
+  const u64 start = off_index[tile], end = off_index[tile + 1];
+  const u64 al = start & ~15ull;
+  const u32 delta = (u32) (start - al);
+  const u32 tb = (u32) (end - al);                 // bytes [delta, tb) of the aligned window are the tile
+  const u32 nchunks = (tb + 15u) >> 4;
+  u16* out = sub + (u64) tile * (EVQ_TILE_ROWS / 8);
+  if (lane == 0) out[0] = 0;
+  u32 running = 0;
+  for (u32 base = 0; base < nchunks; base += 32) {
+    const u32 c = base + lane;
+    u32 m = 0;
+    if (c < nchunks) {
+      const uint4 q = *(const uint4*) (data + al + 16ull * c);
+      u32 w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) m |= ((((~w[k] & 0x80808080u) * 0x00204081u) >> 28) & 0xfu) << (4 * k);
+      const u32 pos = 16u * c;
+      if (pos < delta) m &= ~((1u << (delta - pos)) - 1u);
+      if (tb - pos < 16u) m &= (1u << (tb - pos)) - 1u;
+    }
+    const u32 cnt = __popc(m);
+    u32 incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (u32) o) incl += n;
+    }
+    u32 j = running + incl - cnt;                  // number of this chunk's first terminator
+    while (m) {
+      const u32 k = __ffs(m) - 1u;
+      m &= m - 1u;
+      if ((j & 7u) == 7u) {
+        const u32 g = (j + 1u) >> 3;
+        if (g < EVQ_TILE_ROWS / 8) out[g] = (u16) (16u * c + k + 1u - delta);
+      }
+      ++j;
+    }
+    running += __shfl_sync(0xffffffffu, incl, 31);
+  }
+}
+
 // max over tiles of the 16-byte aligned copy size of [idx[t]*scale, idx[t+1]*scale)
 __global__ void k_max_span(const u64* __restrict__ idx, u32 num_tiles, u32 scale_bytes, u32 block_values, u32 block_bytes,
                            unsigned int* __restrict__ out) {
@@ -386,6 +434,15 @@ void table_finish_column(evqgpu_table* t, Column& c) {
       c.data_payload_bytes = used;
       c.data_bits = 0;
       c.data_tile_cap = span_from_index(c.off_index.as<u64>(), 1, 0, 0);
+      if (c.leb_max_len >= 2 && !nullable && ntiles) {
+        // where the values of the column differ in length: starts of every 8th value (the fast kernel's decode entry points)
+        c.sub_index.alloc((uint64_t) ntiles * (EVQ_TILE_ROWS / 8) * 2 + 256);
+        EVQ_CUDA(cudaMemsetAsync(c.sub_index.p, 0, c.sub_index.bytes, ctx->stream));
+        k_leb_sub_index<<<(unsigned) (((uint64_t) ntiles * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+            c.data.buf.as<u8>(), c.off_index.as<u64>(), ntiles, c.sub_index.as<u16>());
+        EVQ_CUDA(cudaGetLastError());
+        ctx->kernel_launches++;
+      }
       break;
     }
   }
