@@ -127,16 +127,18 @@ static StageLayout stage_layout(const evqgpu_query& q, evqgpu_table* t, const Bi
     if (!cs.used) continue;
     const Column& c = t->cols[b.col_index[i]];
     auto place = [&](int stream, uint32_t cap) {
-      cap = (uint32_t) round_up(cap, 16) + 64;   // decoders may read a few values past the payload (short last tile)
+      // regions are packed at TMA granularity (16 bytes); decoders may read a few values past a payload (short last
+      // tile), which lands in the next region or in the tail pad of the stage
+      cap = (uint32_t) round_up(cap, 16);
       L.smem_off[stream] = off;
       L.smem_cap[stream] = cap;
-      off += (uint32_t) round_up(cap, 128);
+      off += cap;
     };
     place(cs.data_stream, c.data_tile_cap);
     if (cs.nullable) place(cs.level_stream, c.level_tile_cap);
     if (cs.sub_stream >= 0) place(cs.sub_stream, (EVQ_TILE_ROWS / 8) * 2);
   }
-  L.stage_bytes = std::max<uint32_t>(off, 128);
+  L.stage_bytes = (uint32_t) round_up(off + 128, 128);
   (void) q;
   return L;
 }
@@ -363,7 +365,7 @@ static void fit_shape(evqgpu_query& q, KernelShape& s, std::vector<TablePlan>& p
       // as many CTAs per SM as shared memory allows (latency hiding for the decode phases), within the register budget
       // the launch bounds leave per thread: 2 x 288 threads or 4 x 160 threads
       const int by_smem = (int) ((227 * 1024) / (worst + 1024));
-      const int cap = s.ncons <= 128 ? 5 : 2;
+      const int cap = s.ncons <= 128 ? 6 : 2;
       s.min_ctas = std::max(1, std::min(by_smem, cap));
       if (const char* e = getenv("EVQGPU_MAX_CTAS")) s.min_ctas = std::max(1, std::min(s.min_ctas, atoi(e)));
       return;
