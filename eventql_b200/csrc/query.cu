@@ -623,10 +623,33 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
   q.dense = dm;
   q.stats.strategy = (uint32_t) s.tier;
 
-  // ---- kernel text
-  q.kernel_source = generate_source(q, s);
+  // ---- kernel text: everything the generated text depends on is summarised in a short signature, so that a repeated
+  // execution (the common case: same plan, same partitions) skips spelling and hashing ~300 KB of source
   float ms = 0;
-  q.module = jit_compile(ctx, q.kernel_source, {"evq_scan", "evq_init", "evq_emit"}, &ms);
+  {
+    std::string sig;
+    char buf[160];
+    snprintf(buf, sizeof(buf), "t%d g%d n%d s%d c%d f%d x%d N%d|", s.tier, s.g1, s.ncons, s.nstages, s.min_ctas, (int) s.fast,
+             (int) s.use_subidx, q.nnarrow);
+    sig += buf;
+    for (const auto& c : s.cols) {
+      snprintf(buf, sizeof(buf), "%d.%u.%u.%d.%u.%u.%u.%d.%d.%d;", (int) c.used, c.sql_type, c.kind, (int) c.nullable, c.dmax, c.bits,
+               c.leb_len, c.gen_slot, c.sub_stream, c.data_stream);
+      sig += buf;
+    }
+    for (size_t i = 0; i < nk; ++i) {
+      snprintf(buf, sizeof(buf), "k%llu.%llu.%llu.%llu;", (unsigned long long) s.dense.key_min[i], (unsigned long long) s.dense.key_stride[i],
+               (unsigned long long) s.dense.key_null_idx[i], (unsigned long long) s.dense.key_range[i]);
+      sig += buf;
+    }
+    for (size_t i = 0; i < q.state_keys.size(); ++i) sig += q.state_keys[i] + "#" + std::to_string(q.state_narrow[i]) + ";";
+    for (int c : q.narrow_col) sig += "p" + std::to_string(c);
+    if (!q.module || sig != q.module_sig) {
+      q.kernel_source = generate_source(q, s);
+      q.module = jit_compile(ctx, q.kernel_source, {"evq_scan", "evq_init", "evq_emit"}, &ms);
+      q.module_sig = sig;
+    }
+  }
   q.jit_ms_total += ms;
 
   // ---- state

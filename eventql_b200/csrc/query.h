@@ -115,6 +115,7 @@ struct evqgpu_query {
   bool dense_cache_valid = false, dense_cache_ok = false;
   std::vector<uint64_t> dense_cache_uids;   // bounds of the GROUP BY expressions are cached per set of (immutable) tables
   std::shared_ptr<evq::JitModule> module;
+  std::string module_sig;   // what `module` was specialised for (group-by plans)
   std::vector<evqgpu_table*> tables;
   bool pending = false;
   bool merged = false;
