@@ -76,6 +76,7 @@ struct EvqStreamDesc {   // written by the producer lane that issued the copy, r
 
 struct EvqTile {         // per-consumer-thread view of the tile being processed
   const u8* stage;             // shared memory base of the stage
+  u32 stage_sa;                // the same as a 32-bit shared-window address (for ld.shared with 32-bit address arithmetic)
   const EvqStreamDesc* desc;   // [EVQ_NSTREAMS]
   u32 rows;                    // rows in this tile
   u32 ctid;                    // consumer thread id 0..EVQ_NCONS-1

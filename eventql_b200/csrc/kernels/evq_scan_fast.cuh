@@ -135,10 +135,18 @@ __device__ __forceinline__ u32 evq_fast_first(const EvqTile& T, int s) {
   return i < n ? i : n;
 }
 
-// 4 bytes at byte offset `off` of a 128-byte aligned stage
-__device__ __forceinline__ u32 evq_stage_u32(const u8* stage, u32 off) {
-  const u32* w = (const u32*) (stage + (off & ~3u));
-  return __funnelshift_r(w[0], w[1], (off & 3u) * 8u);
+// 4 bytes at byte offset `off` of a 128-byte aligned stage: two aligned ld.shared (32-bit address arithmetic) + funnel shift
+__device__ __forceinline__ u32 evq_stage_u32(const EvqTile& T, u32 off) {
+  const u32 a = T.stage_sa + (off & ~3u);
+  u32 w0, w1;
+  asm volatile("ld.shared.u32 %0, [%2];\n\tld.shared.u32 %1, [%2+4];" : "=r"(w0), "=r"(w1) : "r"(a));
+  return __funnelshift_r(w0, w1, off << 3);   // the shift count is taken modulo 32
+}
+
+__device__ __forceinline__ u32 evq_stage_word(const EvqTile& T, u32 off) {   // off is a multiple of 4
+  u32 w;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(T.stage_sa + off));
+  return w;
 }
 
 __device__ __forceinline__ u32 evq_leb_pack2(u32 x) { return (x & 0x7fu) | ((x & 0x7f00u) >> 1); }
@@ -152,9 +160,9 @@ __device__ __forceinline__ void evq_fast_ld_leb1(const EvqTile& T, const EvqScan
   const bool aligned = (off & 3u) == 0u;   // the same for all threads: tiles of 1-byte columns start at multiples of 1024
 #pragma unroll
   for (int j = 0; j < EVQ_RPT / 4; ++j) {
-    const u32 x = aligned ? *(const u32*) (T.stage + off + 4 * j) : evq_stage_u32(T.stage, off + 4 * j);
+    const u32 x = aligned ? evq_stage_word(T, off + 4 * j) : evq_stage_u32(T, off + 4 * j);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[4 * j + i] = (x >> (8 * i)) & 0xffu;
+    for (int i = 0; i < 4; ++i) v[4 * j + i] = __byte_perm(x, 0u, 0x4440u + i);   // byte i, zero extended (one PRMT)
   }
 }
 
@@ -165,10 +173,10 @@ __device__ __forceinline__ void evq_fast_ld_leb1p(const EvqTile& T, const EvqSca
   const bool aligned = (off & 3u) == 0u;
 #pragma unroll
   for (int j = 0; j < EVQ_RPT / 4; ++j) {
-    const u32 x = aligned ? *(const u32*) (T.stage + off + 4 * j) : evq_stage_u32(T.stage, off + 4 * j);
+    const u32 x = aligned ? evq_stage_word(T, off + 4 * j) : evq_stage_u32(T, off + 4 * j);
     packed[j] = x;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[4 * j + i] = (x >> (8 * i)) & 0xffu;
+    for (int i = 0; i < 4; ++i) v[4 * j + i] = __byte_perm(x, 0u, 0x4440u + i);
   }
 }
 
@@ -180,16 +188,15 @@ __device__ __forceinline__ void evq_fast_ld_leb32(const EvqTile& T, const EvqSca
   if (!general) {
     const u32 p = pay + (u32) L * evq_fast_first(T, S);
     if ((L == 2 || L == 4) && (p & 3u) == 0u) {   // whole words: two 2-byte values or one 4-byte value each
-      const u32* w = (const u32*) (T.stage + p);
 #pragma unroll
       for (int i = 0; i < EVQ_RPT; ++i) {
-        if (L == 2) v[i] = evq_leb_pack2((w[i >> 1] >> (16 * (i & 1))) & 0x7f7fu);
-        else v[i] = evq_leb_pack4(w[i] & 0x7f7f7f7fu);
+        if (L == 2) v[i] = evq_leb_pack2((evq_stage_word(T, p + 4 * (i >> 1)) >> (16 * (i & 1))) & 0x7f7fu);
+        else v[i] = evq_leb_pack4(evq_stage_word(T, p + 4 * i) & 0x7f7f7f7fu);
       }
     } else {
 #pragma unroll
       for (int i = 0; i < EVQ_RPT; ++i) {
-        const u32 x = evq_stage_u32(T.stage, p + L * i) & evq_fixed_mask(L);
+        const u32 x = evq_stage_u32(T, p + L * i) & evq_fixed_mask(L);
         v[i] = L == 2 ? evq_leb_pack2(x) : evq_leb_pack4(x);
       }
     }
@@ -197,7 +204,7 @@ __device__ __forceinline__ void evq_fast_ld_leb32(const EvqTile& T, const EvqSca
     u32 p = pay + start;
 #pragma unroll
     for (int i = 0; i < EVQ_RPT; ++i) {
-      const u32 x = evq_stage_u32(T.stage, p);
+      const u32 x = evq_stage_u32(T, p);
       const u32 tm = ~x & 0x80808080u;
       const u32 low = tm & (0u - tm);            // terminator bit of the first value in the window
       const u32 msk = (low << 1) - 1u;           // every bit up to and including it
@@ -361,6 +368,7 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
     const u32 s = it % EVQ_NSTAGES;
     evq_mbar_wait(&hdr->full[s], (it / EVQ_NSTAGES) & 1u);
     T.stage = stages + (size_t) s * stage_bytes;
+    T.stage_sa = evq_smem_u32(T.stage);
     T.desc = hdr->desc[s];
     T.row0 = (u64) tile * EVQ_TILE_ROWS;
     {
@@ -471,8 +479,7 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
         EvqRow row;
         evq_fast_row(cols, k, row);
         const bool pass = (EVQ_RPT * tid + k < T.rows) && evq_where(row, err);
-        if (pass) {
-          ++passed;
+        if (pass) {   // (rows passed are counted from the rows accumulators at the end)
           u64 key[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
           u32 ktag[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
           evq_keys(row, key, ktag, err);
@@ -530,6 +537,8 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
 #if EVQ_G1 > 1
   for (u32 g = 0; g < EVQ_G1; ++g) evq_state_flush_smem(sacc, g, tid, P.dense_state);
 #if EVQ_NNARROW > 0
+#pragma unroll
+  for (int g = 0; g < EVQ_G1; ++g) passed += nacc[g];   // narrow accumulator 0 is the rows counter
   evq_narrow_flush(nacc, P.dense_state);
 #endif
 #else
