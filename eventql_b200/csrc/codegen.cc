@@ -47,6 +47,11 @@ static CodegenEnv row_env(const KernelShape& shape) {
     env.col_value[i] = widen ? "((u64) row.c" + std::to_string(i) + ")" : "row.c" + std::to_string(i);
     env.col_tag[i] = shape.cols[i].nullable ? "row.t" + std::to_string(i) : std::string("0u");
   }
+  if (shape.fast) {   // column statistics -> narrowing hints for the expression code
+    env.col_bits.assign(shape.cols.size(), 64);
+    for (size_t i = 0; i < shape.cols.size(); ++i)
+      if (shape.cols[i].used) env.col_bits[i] = shape.cols[i].bits;
+  }
   return env;
 }
 
@@ -495,10 +500,12 @@ static std::string gen_row_functions(const evqgpu_query& q, const KernelShape& s
         if (q.state_smem[w] >= 0) os << "  sacc[EVQ_SIDX(g, " << q.state_smem[w] << ")] = evq_state_identity<" << q.state_ops[w] << ">();\n";
       os << "}\n";
       for (int w = 0; w < nstate; ++w) os << "#define EVQ_SM_" << w << " " << q.state_smem[w] << "\n";
-      os << "#define EVQ_UPD(st, op, v) sacc[EVQ_SIDX(g, EVQ_SM_##st)] = evq_state_combine<op>(sacc[EVQ_SIDX(g, EVQ_SM_##st)], (v))\n";
-      os << "#define EVQ_UPD_C(st, cw, v) { const u64 _o = sacc[EVQ_SIDX(g, EVQ_SM_##st)]; const u64 _n = _o + (v); "
-            "sacc[EVQ_SIDX(g, EVQ_SM_##st)] = _n; if (_n < _o) atomicAdd(dense_state + (u64) g * " << nstate << " + (cw), 1ull); }\n";
+      // one base address per row (group g, this thread); the words of the group sit at constant offsets from it
+      os << "#define EVQ_UPD(st, op, v) _acc[EVQ_SM_##st * EVQ_NCONS] = evq_state_combine<op>(_acc[EVQ_SM_##st * EVQ_NCONS], (v))\n";
+      os << "#define EVQ_UPD_C(st, cw, v) { const u64 _o = _acc[EVQ_SM_##st * EVQ_NCONS]; const u64 _n = _o + (v); "
+            "_acc[EVQ_SM_##st * EVQ_NCONS] = _n; if (_n < _o) atomicAdd(dense_state + (u64) g * " << nstate << " + (cw), 1ull); }\n";
       os << "__device__ __forceinline__ void evq_accumulate_smem(const EvqRow& row, u64* sacc, u32 g, u32 tid, u64* dense_state, u32& err) {\n";
+      os << "  u64* _acc = sacc + g * " << nsm << "u * EVQ_NCONS + tid;\n";
       gen_updates(os, q, shape);
       os << "}\n#undef EVQ_UPD\n#undef EVQ_UPD_C\n";
       os << "__device__ __forceinline__ void evq_state_flush_smem(u64* sacc, u32 g, u32 tid, u64* dense_state) {\n";

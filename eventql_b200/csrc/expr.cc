@@ -240,7 +240,52 @@ static std::string hex64(uint64_t v) {
   return buf;
 }
 
+// Upper bound on the bit length of a uint64-valued expression given the bounds of the input columns (64 = unknown).
+uint32_t expr_value_bits(const Expr* e, const CodegenEnv& env) {
+  auto sat = [](uint32_t b) { return b > 64u ? 64u : b; };
+  switch (e->op) {
+    case EVQ_X_INPUT:
+      if (e->type == EVQ_BOOL) return 1;
+      if (e->type != EVQ_UINT64 && e->type != EVQ_TIMESTAMP64) return 64;
+      return e->col < env.col_bits.size() ? sat(env.col_bits[e->col]) : 64;
+    case EVQ_X_LITERAL: {
+      if (e->type == EVQ_BOOL) return 1;
+      if (e->type != EVQ_UINT64 && e->type != EVQ_TIMESTAMP64) return 64;
+      uint32_t b = 0;
+      for (uint64_t v = e->imm; v; v >>= 1) ++b;
+      return b ? b : 1;
+    }
+    case EVQ_X_IF: return std::max(expr_value_bits(e->args[1].get(), env), expr_value_bits(e->args[2].get(), env));
+    case EVQ_X_CALL: break;
+    default: return 64;
+  }
+  const FnInfo& fi = e->info();
+  if (fi.ret == EVQ_BOOL) return 1;
+  if (fi.ret != EVQ_UINT64 && fi.ret != EVQ_TIMESTAMP64) return 64;
+  if (fi.args.empty() || (fi.args[0] != EVQ_UINT64 && fi.args[0] != EVQ_TIMESTAMP64)) return 64;
+  switch (fi.fn) {
+    case Fn::ADD: return sat(std::max(expr_value_bits(e->args[0].get(), env), expr_value_bits(e->args[1].get(), env)) + 1);
+    case Fn::MUL: return sat(expr_value_bits(e->args[0].get(), env) + expr_value_bits(e->args[1].get(), env));
+    case Fn::DIV: return expr_value_bits(e->args[0].get(), env);
+    case Fn::MOD: return std::min(expr_value_bits(e->args[0].get(), env), expr_value_bits(e->args[1].get(), env));
+    case Fn::DATE_TRUNC: return expr_value_bits(e->args[1].get(), env);
+    default: return 64;   // sub may wrap, conversions may reinterpret
+  }
+}
+
+static Code gen_expr_impl(const Expr* e, const CodegenEnv& env);
+
+// Sub-expressions whose value provably fits 32 bits are re-typed through u32: same value, but the compiler can then use
+// 32-bit compares and 32x32->64 / 64x32 multiplies instead of full 64-bit arithmetic.
 Code gen_expr(const Expr* e, const CodegenEnv& env) {
+  Code c = gen_expr_impl(e, env);
+  if (!env.col_bits.empty() && e->op == EVQ_X_CALL && (e->type == EVQ_UINT64 || e->type == EVQ_TIMESTAMP64) &&
+      !e->info().aggregate && expr_value_bits(e, env) <= 32)
+    c.value = "((u64) (u32) (" + c.value + "))";
+  return c;
+}
+
+static Code gen_expr_impl(const Expr* e, const CodegenEnv& env) {
   const std::string sig = e->signature();
   for (const auto& s : env.subst)
     if (s.first == sig) return {s.second.first, s.second.second};

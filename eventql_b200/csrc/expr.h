@@ -62,6 +62,8 @@ struct CodegenEnv {
   // substitution of whole subtrees by signature (group key i -> stored key value; the aggregate call -> its result)
   std::vector<std::pair<std::string, std::pair<std::string, std::string>>> subst;   // signature -> (value, tag)
   std::string err = "err";   // name of the u32 error accumulator in scope
+  // upper bound on the bit length of the values of input column i (column statistics); empty = unknown (64)
+  std::vector<uint32_t> col_bits;
 };
 
 struct Code {
