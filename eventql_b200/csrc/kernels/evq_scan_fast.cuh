@@ -131,8 +131,9 @@ __device__ __forceinline__ u32 evq_fast_substart(const EvqTile& T, const EvqScan
 // index of the thread's first value inside the tile; threads past the end of a short tile decode (and discard) the
 // bytes behind the payload, which the stage regions are padded for
 __device__ __forceinline__ u32 evq_fast_first(const EvqTile& T, int s) {
-  const u32 i = EVQ_RPT * T.ctid, n = T.desc[s].nvals;
-  return i < n ? i : n;
+  (void) s;   // required columns: every stream holds one value per row of the tile
+  const u32 i = EVQ_RPT * T.ctid;
+  return i < T.rows ? i : T.rows;
 }
 
 // 4 bytes at byte offset `off` of a 128-byte aligned stage: two aligned ld.shared (32-bit address arithmetic) + funnel shift
@@ -149,18 +150,21 @@ __device__ __forceinline__ u32 evq_stage_word(const EvqTile& T, u32 off) {   // 
   return w;
 }
 
-__device__ __forceinline__ u32 evq_leb_pack2(u32 x) { return (x & 0x7fu) | ((x & 0x7f00u) >> 1); }
+// 7-bit groups -> value with integer dot products (the continuation bits of x must be cleared):
+// byte0 + 128 * byte1 is one dp2a against the 16-bit weights (1, 128); a 4-byte value is two of them + one multiply-add
+__device__ __forceinline__ u32 evq_leb_pack2(u32 x) { return __dp2a_lo(0x00800001u, x, 0u); }
+__device__ __forceinline__ u32 evq_fast_pack4(u32 x) { return __dp2a_hi(0x00800001u, x, 0u) * 16384u + __dp2a_lo(0x00800001u, x, 0u); }
 
 __device__ __forceinline__ u32 evq_fixed_mask(u32 len) { return len >= 4u ? 0x7f7f7f7fu : ((1u << (8u * len)) - 1u) & 0x7f7f7f7fu; }
 
 // L == 1: value i is byte i
 template <int S>
 __device__ __forceinline__ void evq_fast_ld_leb1(const EvqTile& T, const EvqScanParams& P, u32 (&v)[EVQ_RPT]) {
-  const u32 off = P.streams[S].smem_off + T.desc[S].delta + evq_fast_first(T, S);
-  const bool aligned = (off & 3u) == 0u;   // the same for all threads: tiles of 1-byte columns start at multiples of 1024
+  // every value is one byte: byte offset == row index, so a tile starts at a multiple of 1024 (delta == 0, word aligned)
+  const u32 off = P.streams[S].smem_off + evq_fast_first(T, S);
 #pragma unroll
   for (int j = 0; j < EVQ_RPT / 4; ++j) {
-    const u32 x = aligned ? evq_stage_word(T, off + 4 * j) : evq_stage_u32(T, off + 4 * j);
+    const u32 x = evq_stage_word(T, off + 4 * j);
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[4 * j + i] = __byte_perm(x, 0u, 0x4440u + i);   // byte i, zero extended (one PRMT)
   }
@@ -169,11 +173,10 @@ __device__ __forceinline__ void evq_fast_ld_leb1(const EvqTile& T, const EvqScan
 // same, also keeping the raw bytes (4 rows per word) for the dp4a aggregates
 template <int S>
 __device__ __forceinline__ void evq_fast_ld_leb1p(const EvqTile& T, const EvqScanParams& P, u32 (&v)[EVQ_RPT], u32 (&packed)[EVQ_RPT / 4]) {
-  const u32 off = P.streams[S].smem_off + T.desc[S].delta + evq_fast_first(T, S);
-  const bool aligned = (off & 3u) == 0u;
+  const u32 off = P.streams[S].smem_off + evq_fast_first(T, S);
 #pragma unroll
   for (int j = 0; j < EVQ_RPT / 4; ++j) {
-    const u32 x = aligned ? evq_stage_word(T, off + 4 * j) : evq_stage_u32(T, off + 4 * j);
+    const u32 x = evq_stage_word(T, off + 4 * j);
     packed[j] = x;
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[4 * j + i] = __byte_perm(x, 0u, 0x4440u + i);
@@ -190,14 +193,19 @@ __device__ __forceinline__ void evq_fast_ld_leb32(const EvqTile& T, const EvqSca
     if ((L == 2 || L == 4) && (p & 3u) == 0u) {   // whole words: two 2-byte values or one 4-byte value each
 #pragma unroll
       for (int i = 0; i < EVQ_RPT; ++i) {
-        if (L == 2) v[i] = evq_leb_pack2((evq_stage_word(T, p + 4 * (i >> 1)) >> (16 * (i & 1))) & 0x7f7fu);
-        else v[i] = evq_leb_pack4(evq_stage_word(T, p + 4 * i) & 0x7f7f7f7fu);
+        // two 2-byte values per word: dp2a_lo / dp2a_hi pick their byte pair; one 4-byte value per word
+        if (L == 2) {
+          const u32 w = evq_stage_word(T, p + 4 * (i >> 1)) & 0x7f7f7f7fu;
+          v[i] = (i & 1) ? __dp2a_hi(0x00800001u, w, 0u) : __dp2a_lo(0x00800001u, w, 0u);
+        } else {
+          v[i] = evq_fast_pack4(evq_stage_word(T, p + 4 * i) & 0x7f7f7f7fu);
+        }
       }
     } else {
 #pragma unroll
       for (int i = 0; i < EVQ_RPT; ++i) {
         const u32 x = evq_stage_u32(T, p + L * i) & evq_fixed_mask(L);
-        v[i] = L == 2 ? evq_leb_pack2(x) : evq_leb_pack4(x);
+        v[i] = L == 2 ? evq_leb_pack2(x) : evq_fast_pack4(x);
       }
     }
   } else {
@@ -205,12 +213,11 @@ __device__ __forceinline__ void evq_fast_ld_leb32(const EvqTile& T, const EvqSca
 #pragma unroll
     for (int i = 0; i < EVQ_RPT; ++i) {
       const u32 x = evq_stage_u32(T, p);
-      const u32 tm = ~x & 0x80808080u;
-      const u32 low = tm & (0u - tm);            // terminator bit of the first value in the window
-      const u32 msk = (low << 1) - 1u;           // every bit up to and including it
+      const u32 tm = ~x & 0x80808080u;           // terminator bits of the window
+      const u32 msk = tm ^ (tm - 1u);            // every bit up to and including the first of them
       const u32 y = x & msk & 0x7f7f7f7fu;
-      v[i] = L == 2 ? evq_leb_pack2(y) : evq_leb_pack4(y);
-      p += (32u - __clz(low)) >> 3;
+      v[i] = L == 2 ? evq_leb_pack2(y) : evq_fast_pack4(y);
+      p += __popc(msk) >> 3;
     }
   }
 }
