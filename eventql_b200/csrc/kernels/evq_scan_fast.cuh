@@ -133,7 +133,7 @@ __device__ __forceinline__ u32 evq_fast_substart(const EvqTile& T, const EvqScan
 __device__ __forceinline__ u32 evq_fast_first(const EvqTile& T, int s) {
   (void) s;   // required columns: every stream holds one value per row of the tile
   const u32 i = EVQ_RPT * T.ctid;
-  return i < T.rows ? i : T.rows;
+  return i < T.rows ? i : (T.rows & ~(EVQ_RPT - 1u));   // threads past the end re-read the last group (keeps word alignment)
 }
 
 // 4 bytes at byte offset `off` of a 128-byte aligned stage: two aligned ld.shared (32-bit address arithmetic) + funnel shift
