@@ -48,9 +48,9 @@ static CodegenEnv row_env(const KernelShape& shape) {
     env.col_tag[i] = shape.cols[i].nullable ? "row.t" + std::to_string(i) : std::string("0u");
   }
   if (shape.fast) {   // column statistics -> narrowing hints for the expression code
-    env.col_bits.assign(shape.cols.size(), 64);
+    env.col_max.assign(shape.cols.size(), ~0ull);
     for (size_t i = 0; i < shape.cols.size(); ++i)
-      if (shape.cols[i].used) env.col_bits[i] = shape.cols[i].bits;
+      if (shape.cols[i].used) env.col_max[i] = shape.cols[i].vmax;
   }
   return env;
 }
@@ -462,7 +462,11 @@ static std::string gen_row_functions(const evqgpu_query& q, const KernelShape& s
       const bool may_null = dm.key_null_idx[i] != ~0ull;
       const uint64_t span = dm.key_range[i] - (may_null ? 2 : 1);   // largest non-NULL index
       os << "  {\n    const u64 d = key[" << i << "] - " << dm.key_min[i] << "ull;\n";
-      if (may_null) {
+      // the range check is dropped when the column statistics already bound the key inside the slot range
+      const bool proven = !may_null && dm.key_min[i] == 0 && expr_value_max(q.group[i].get(), env) <= span;
+      if (proven) {
+        os << "    const u32 idx = (u32) d;\n";
+      } else if (may_null) {
         os << "    const u32 idx = ktag[" << i << "] ? " << dm.key_null_idx[i] << "u : (u32) d;\n";
         os << "    ok = ok && (ktag[" << i << "] || d <= " << span << "ull);\n";
       } else {

@@ -240,38 +240,58 @@ static std::string hex64(uint64_t v) {
   return buf;
 }
 
-// Upper bound on the bit length of a uint64-valued expression given the bounds of the input columns (64 = unknown).
-uint32_t expr_value_bits(const Expr* e, const CodegenEnv& env) {
-  auto sat = [](uint32_t b) { return b > 64u ? 64u : b; };
+// Value range [lo, hi] of a uint64-valued expression given the upper bounds of the input columns (column statistics).
+// {0, ~0} = unknown / may wrap.
+struct Range { uint64_t lo, hi; };
+static const Range kAny = {0, ~0ull};
+
+static Range expr_range(const Expr* e, const CodegenEnv& env) {
   switch (e->op) {
     case EVQ_X_INPUT:
-      if (e->type == EVQ_BOOL) return 1;
-      if (e->type != EVQ_UINT64 && e->type != EVQ_TIMESTAMP64) return 64;
-      return e->col < env.col_bits.size() ? sat(env.col_bits[e->col]) : 64;
-    case EVQ_X_LITERAL: {
-      if (e->type == EVQ_BOOL) return 1;
-      if (e->type != EVQ_UINT64 && e->type != EVQ_TIMESTAMP64) return 64;
-      uint32_t b = 0;
-      for (uint64_t v = e->imm; v; v >>= 1) ++b;
-      return b ? b : 1;
+      if (e->type == EVQ_BOOL) return {0, 1};
+      if (e->type != EVQ_UINT64 && e->type != EVQ_TIMESTAMP64) return kAny;
+      return {0, e->col < env.col_max.size() ? env.col_max[e->col] : ~0ull};
+    case EVQ_X_LITERAL:
+      if (e->type == EVQ_BOOL) return {e->imm ? 1ull : 0ull, e->imm ? 1ull : 0ull};
+      if (e->type != EVQ_UINT64 && e->type != EVQ_TIMESTAMP64) return kAny;
+      return {e->imm, e->imm};
+    case EVQ_X_IF: {
+      const Range a = expr_range(e->args[1].get(), env), b = expr_range(e->args[2].get(), env);
+      return {std::min(a.lo, b.lo), std::max(a.hi, b.hi)};
     }
-    case EVQ_X_IF: return std::max(expr_value_bits(e->args[1].get(), env), expr_value_bits(e->args[2].get(), env));
     case EVQ_X_CALL: break;
-    default: return 64;
+    default: return kAny;
   }
   const FnInfo& fi = e->info();
-  if (fi.ret == EVQ_BOOL) return 1;
-  if (fi.ret != EVQ_UINT64 && fi.ret != EVQ_TIMESTAMP64) return 64;
-  if (fi.args.empty() || (fi.args[0] != EVQ_UINT64 && fi.args[0] != EVQ_TIMESTAMP64)) return 64;
+  if (fi.ret == EVQ_BOOL) return {0, 1};
+  if (fi.ret != EVQ_UINT64 && fi.ret != EVQ_TIMESTAMP64) return kAny;
+  if (fi.args.empty() || (fi.args[0] != EVQ_UINT64 && fi.args[0] != EVQ_TIMESTAMP64)) return kAny;
+  if (fi.fn == Fn::DATE_TRUNC) return {0, expr_range(e->args[1].get(), env).hi};
+  if (e->args.size() != 2) return kAny;
+  const Range a = expr_range(e->args[0].get(), env), b = expr_range(e->args[1].get(), env);
   switch (fi.fn) {
-    case Fn::ADD: return sat(std::max(expr_value_bits(e->args[0].get(), env), expr_value_bits(e->args[1].get(), env)) + 1);
-    case Fn::MUL: return sat(expr_value_bits(e->args[0].get(), env) + expr_value_bits(e->args[1].get(), env));
-    case Fn::DIV: return expr_value_bits(e->args[0].get(), env);
-    case Fn::MOD: return std::min(expr_value_bits(e->args[0].get(), env), expr_value_bits(e->args[1].get(), env));
-    case Fn::DATE_TRUNC: return expr_value_bits(e->args[1].get(), env);
-    default: return 64;   // sub may wrap, conversions may reinterpret
+    case Fn::ADD:
+      if (a.hi > ~0ull - b.hi) return kAny;
+      return {a.lo + b.lo, a.hi + b.hi};
+    case Fn::SUB:
+      if (a.lo < b.hi) return kAny;   // may wrap below zero
+      return {a.lo - b.hi, a.hi - b.lo};
+    case Fn::MUL:
+      if (b.hi != 0 && a.hi > ~0ull / b.hi) return kAny;
+      return {a.lo * b.lo, a.hi * b.hi};
+    case Fn::DIV: return {0, a.hi};
+    case Fn::MOD: return {0, b.hi ? std::min(a.hi, b.hi - 1) : a.hi};
+    default: return kAny;
   }
 }
+
+uint32_t expr_value_bits(const Expr* e, const CodegenEnv& env) {
+  uint32_t b = 0;
+  for (uint64_t v = expr_range(e, env).hi; v; v >>= 1) ++b;
+  return b ? b : 1;
+}
+
+uint64_t expr_value_max(const Expr* e, const CodegenEnv& env) { return expr_range(e, env).hi; }
 
 static Code gen_expr_impl(const Expr* e, const CodegenEnv& env);
 
@@ -279,7 +299,7 @@ static Code gen_expr_impl(const Expr* e, const CodegenEnv& env);
 // 32-bit compares and 32x32->64 / 64x32 multiplies instead of full 64-bit arithmetic.
 Code gen_expr(const Expr* e, const CodegenEnv& env) {
   Code c = gen_expr_impl(e, env);
-  if (!env.col_bits.empty() && e->op == EVQ_X_CALL && (e->type == EVQ_UINT64 || e->type == EVQ_TIMESTAMP64) &&
+  if (!env.col_max.empty() && e->op == EVQ_X_CALL && (e->type == EVQ_UINT64 || e->type == EVQ_TIMESTAMP64) &&
       !e->info().aggregate && expr_value_bits(e, env) <= 32)
     c.value = "((u64) (u32) (" + c.value + "))";
   return c;

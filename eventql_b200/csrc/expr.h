@@ -62,8 +62,8 @@ struct CodegenEnv {
   // substitution of whole subtrees by signature (group key i -> stored key value; the aggregate call -> its result)
   std::vector<std::pair<std::string, std::pair<std::string, std::string>>> subst;   // signature -> (value, tag)
   std::string err = "err";   // name of the u32 error accumulator in scope
-  // upper bound on the bit length of the values of input column i (column statistics); empty = unknown (64)
-  std::vector<uint32_t> col_bits;
+  // upper bound of the values of input column i (column statistics); empty = unknown
+  std::vector<uint64_t> col_max;
 };
 
 struct Code {
@@ -72,6 +72,8 @@ struct Code {
 };
 
 Code gen_expr(const Expr* e, const CodegenEnv& env);
+uint32_t expr_value_bits(const Expr* e, const CodegenEnv& env);   // bit length bound of a uint64-valued expression (64 = unknown)
+uint64_t expr_value_max(const Expr* e, const CodegenEnv& env);
 // the value as raw 64-bit pattern (u64), e.g. for key tuples and aggregate state words
 std::string as_bits(const Code& c, int type);
 const char* ctype_of(int type);

@@ -63,6 +63,7 @@ static KernelShape shape_for(const evqgpu_query& q, evqgpu_table* t, const Bindi
     cs.nullable = c.meta.dlevel_max > 0;
     cs.dmax = c.meta.dlevel_max;
     cs.bits = c.value_bits;
+    cs.vmax = c.value_max;
     cs.leb_len = c.leb_max_len;
     cs.data_stream = s.nstreams++;
     if (cs.nullable) {
@@ -81,6 +82,7 @@ static KernelShape shape_for(const evqgpu_query& q, evqgpu_table* t, const Bindi
 static void widen_shape(KernelShape& s, const KernelShape& o) {
   for (size_t i = 0; i < s.cols.size(); ++i) {
     s.cols[i].bits = std::max(s.cols[i].bits, o.cols[i].bits);
+    s.cols[i].vmax = std::max(s.cols[i].vmax, o.cols[i].vmax);
     s.cols[i].leb_len = std::max(s.cols[i].leb_len, o.cols[i].leb_len);
   }
 }
@@ -633,8 +635,8 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
              (int) s.use_subidx, q.nnarrow);
     sig += buf;
     for (const auto& c : s.cols) {
-      snprintf(buf, sizeof(buf), "%d.%u.%u.%d.%u.%u.%u.%d.%d.%d;", (int) c.used, c.sql_type, c.kind, (int) c.nullable, c.dmax, c.bits,
-               c.leb_len, c.gen_slot, c.sub_stream, c.data_stream);
+      snprintf(buf, sizeof(buf), "%d.%u.%u.%d.%u.%u.%u.%d.%d.%d.%llu;", (int) c.used, c.sql_type, c.kind, (int) c.nullable, c.dmax, c.bits,
+               c.leb_len, c.gen_slot, c.sub_stream, c.data_stream, (unsigned long long) c.vmax);
       sig += buf;
     }
     for (size_t i = 0; i < nk; ++i) {

@@ -33,6 +33,7 @@ struct ColSig {
   int data_stream = -1, level_stream = -1;
   int leb_slot = -1, null_slot = -1;
   uint32_t bits = 64;      // every value < 2^bits (max over the scanned tables)
+  uint64_t vmax = ~0ull;   // every value <= vmax (max over the scanned tables)
   uint32_t leb_len = 10;   // LEB128: longest value in bytes (max over the scanned tables)
   int gen_slot = -1;       // fast kernel: index among the LEB128 columns that may need the boundary search (leb_len >= 2)
   bool packed = false;     // fast kernel: keep the column's raw bytes (4 rows per word) for the dp4a aggregates

@@ -139,12 +139,24 @@ __global__ void k_leb_chunk_counts(const uint4* __restrict__ data, u64 nbytes, u
   }
 }
 
-// column statistic of fixed-width streams: OR of all values (its highest bit bounds every value)
-__global__ void k_or_reduce64(const u64* __restrict__ v, u64 n, unsigned long long* __restrict__ out) {
+// column statistic of PLAIN64 streams: the largest value
+__global__ void k_max_reduce64(const u64* __restrict__ v, u64 n, unsigned long long* __restrict__ out) {
   u64 acc = 0;
-  for (u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64) gridDim.x * blockDim.x) acc |= v[i];
-  for (int o = 16; o > 0; o >>= 1) acc |= __shfl_xor_sync(0xffffffffu, acc, o);
-  if ((threadIdx.x & 31) == 0 && acc) atomicOr(out, acc);
+  for (u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64) gridDim.x * blockDim.x) acc = max(acc, v[i]);
+  for (int o = 16; o > 0; o >>= 1) acc = max(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+  if ((threadIdx.x & 31) == 0 && acc) atomicMax(out, acc);
+}
+
+// column statistic of LEB128 streams whose values are all one byte long: the largest byte
+__global__ void k_max_reduce8(const uint4* __restrict__ v, u64 n16, unsigned int* __restrict__ out) {
+  u32 acc = 0;
+  for (u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (u64) gridDim.x * blockDim.x) {
+    const uint4 q = v[i];
+    acc = __vmaxu4(acc, __vmaxu4(__vmaxu4(q.x, q.y), __vmaxu4(q.z, q.w)));
+  }
+  acc = max(max(acc & 0xffu, (acc >> 8) & 0xffu), max((acc >> 16) & 0xffu, acc >> 24));
+  for (int o = 16; o > 0; o >>= 1) acc = max(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+  if ((threadIdx.x & 31) == 0 && acc) atomicMax(out, acc);
 }
 
 // off_index[t] = byte offset at which value number boundary(t) starts, boundary(t) = val_index[t] or t*TILE
@@ -364,17 +376,19 @@ void table_finish_column(evqgpu_table* t, Column& c) {
       c.data_payload_bytes = nv * w;
       c.data_bits = w * 8;
       c.value_bits = w * 8;
+      c.value_max = w == 8 ? ~0ull : 0xffffffffull;
       if (w == 8 && nv && c.sql_type != EVQ_FLOAT64) {
         DevBuf acc;
         acc.alloc(8);
         EVQ_CUDA(cudaMemsetAsync(acc.p, 0, 8, ctx->stream));
-        k_or_reduce64<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(c.data.buf.as<u64>(), nv, acc.as<unsigned long long>());
+        k_max_reduce64<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(c.data.buf.as<u64>(), nv, acc.as<unsigned long long>());
         EVQ_CUDA(cudaGetLastError());
         ctx->kernel_launches++;
         u64 ored = 0;
         EVQ_CUDA(cudaMemcpyAsync(&ored, acc.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
         EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
         c.value_bits = ored ? 64 - (uint32_t) __builtin_clzll(ored) : 1;
+        c.value_max = ored;
       }
       if (nullable) c.data_tile_cap = span_from_index(c.val_index.as<u64>(), w, 0, 0);
       else c.data_tile_cap = EVQ_TILE_ROWS * w + 32;
@@ -383,6 +397,7 @@ void table_finish_column(evqgpu_table* t, Column& c) {
     case EVQ_KIND_BITPACK: {
       c.data_bits = bits_needed(c.data.bitpack_max);
       c.value_bits = std::max<uint32_t>(1, c.data_bits);
+      c.value_max = c.value_bits >= 64 ? ~0ull : (1ull << c.value_bits) - 1;
       const uint64_t need = (nv + 127) / 128 * 16 * c.data_bits;
       if (c.data_bits && c.data.nbytes < need)
         fail(EVQGPU_ERR_FORMAT, "column '%s': bit-packed stream too short", c.meta.name.c_str());
@@ -414,6 +429,18 @@ void table_finish_column(evqgpu_table* t, Column& c) {
         c.leb_max_len = 1;
         while (c.leb_max_len < 10 && (runs >> (c.leb_max_len - 1)) & 1u) ++c.leb_max_len;
         c.value_bits = std::min<uint32_t>(64, 7 * c.leb_max_len);
+        c.value_max = c.value_bits >= 64 ? ~0ull : (1ull << c.value_bits) - 1;
+        if (c.leb_max_len == 1 && c.data.nbytes) {
+          // all values are single bytes (zero padded stream): the exact maximum is one more cheap pass
+          EVQ_CUDA(cudaMemsetAsync(maxspan.p, 0, sizeof(unsigned int), ctx->stream));
+          k_max_reduce8<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(c.data.buf.as<uint4>(), (c.data.nbytes + 15) / 16, maxspan.as<unsigned int>());
+          EVQ_CUDA(cudaGetLastError());
+          ctx->kernel_launches++;
+          unsigned int mx = 0;
+          EVQ_CUDA(cudaMemcpyAsync(&mx, maxspan.p, sizeof(mx), cudaMemcpyDeviceToHost, ctx->stream));
+          EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
+          c.value_max = mx;
+        }
       }
       exclusive_scan_u64(ctx, counts.as<u64>(), base.as<u64>(), nchunks + 1);
       u64 total_terms = 0;
