@@ -144,6 +144,15 @@ __device__ __forceinline__ u32 evq_stage_u32(const EvqTile& T, u32 off) {
   return __funnelshift_r(w0, w1, off << 3);   // the shift count is taken modulo 32
 }
 
+// vector loads: a thread's 8 consecutive values are 8 / 16 / 32 / 64 contiguous bytes; one wide load per thread keeps the
+// warp's access conflict-free where 32-bit loads at an 8- or 16-byte lane stride would collide 2- or 4-way on the banks
+__device__ __forceinline__ void evq_stage_v2(const EvqTile& T, u32 off, u32& a, u32& b) {   // off is a multiple of 8
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(T.stage_sa + off));
+}
+__device__ __forceinline__ void evq_stage_v4(const EvqTile& T, u32 off, u32& a, u32& b, u32& c, u32& d) {   // multiple of 16
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(T.stage_sa + off));
+}
+
 __device__ __forceinline__ u32 evq_stage_word(const EvqTile& T, u32 off) {   // off is a multiple of 4
   u32 w;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(T.stage_sa + off));
@@ -162,11 +171,13 @@ template <int S>
 __device__ __forceinline__ void evq_fast_ld_leb1(const EvqTile& T, const EvqScanParams& P, u32 (&v)[EVQ_RPT]) {
   // every value is one byte: byte offset == row index, so a tile starts at a multiple of 1024 (delta == 0, word aligned)
   const u32 off = P.streams[S].smem_off + evq_fast_first(T, S);
+  u32 x[EVQ_RPT / 4];
+  if (EVQ_RPT == 8) evq_stage_v2(T, off, x[0], x[EVQ_RPT / 4 - 1]);
+  else x[0] = evq_stage_word(T, off);
 #pragma unroll
   for (int j = 0; j < EVQ_RPT / 4; ++j) {
-    const u32 x = evq_stage_word(T, off + 4 * j);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[4 * j + i] = __byte_perm(x, 0u, 0x4440u + i);   // byte i, zero extended (one PRMT)
+    for (int i = 0; i < 4; ++i) v[4 * j + i] = __byte_perm(x[j], 0u, 0x4440u + i);   // byte i, zero extended (one PRMT)
   }
 }
 
@@ -174,12 +185,12 @@ __device__ __forceinline__ void evq_fast_ld_leb1(const EvqTile& T, const EvqScan
 template <int S>
 __device__ __forceinline__ void evq_fast_ld_leb1p(const EvqTile& T, const EvqScanParams& P, u32 (&v)[EVQ_RPT], u32 (&packed)[EVQ_RPT / 4]) {
   const u32 off = P.streams[S].smem_off + evq_fast_first(T, S);
+  if (EVQ_RPT == 8) evq_stage_v2(T, off, packed[0], packed[EVQ_RPT / 4 - 1]);
+  else packed[0] = evq_stage_word(T, off);
 #pragma unroll
   for (int j = 0; j < EVQ_RPT / 4; ++j) {
-    const u32 x = evq_stage_word(T, off + 4 * j);
-    packed[j] = x;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[4 * j + i] = __byte_perm(x, 0u, 0x4440u + i);
+    for (int i = 0; i < 4; ++i) v[4 * j + i] = __byte_perm(packed[j], 0u, 0x4440u + i);
   }
 }
 
@@ -190,10 +201,24 @@ __device__ __forceinline__ void evq_fast_ld_leb32(const EvqTile& T, const EvqSca
   const u32 pay = P.streams[S].smem_off + T.desc[S].delta;
   if (!general) {
     const u32 p = pay + (u32) L * evq_fast_first(T, S);
-    if ((L == 2 || L == 4) && (p & 3u) == 0u) {   // whole words: two 2-byte values or one 4-byte value each
+    if ((L == 2 || L == 4) && EVQ_RPT == 8 && (p & 15u) == 0u) {
+      // the thread's 8 values are 16 (L == 2) or 32 (L == 4) aligned bytes: 128-bit loads
+      u32 w[L == 2 ? 4 : 8];
+      evq_stage_v4(T, p, w[0], w[1], w[2], w[3]);
+      if (L == 4) evq_stage_v4(T, p + 16u, w[L == 2 ? 0 : 4], w[L == 2 ? 1 : 5], w[L == 2 ? 2 : 6], w[L == 2 ? 3 : 7]);
 #pragma unroll
       for (int i = 0; i < EVQ_RPT; ++i) {
         // two 2-byte values per word: dp2a_lo / dp2a_hi pick their byte pair; one 4-byte value per word
+        if (L == 2) {
+          const u32 ww = w[i >> 1] & 0x7f7f7f7fu;
+          v[i] = (i & 1) ? __dp2a_hi(0x00800001u, ww, 0u) : __dp2a_lo(0x00800001u, ww, 0u);
+        } else {
+          v[i] = evq_fast_pack4(w[L == 2 ? 0 : i] & 0x7f7f7f7fu);
+        }
+      }
+    } else if ((L == 2 || L == 4) && (p & 3u) == 0u) {   // whole words: two 2-byte values or one 4-byte value each
+#pragma unroll
+      for (int i = 0; i < EVQ_RPT; ++i) {
         if (L == 2) {
           const u32 w = evq_stage_word(T, p + 4 * (i >> 1)) & 0x7f7f7f7fu;
           v[i] = (i & 1) ? __dp2a_hi(0x00800001u, w, 0u) : __dp2a_lo(0x00800001u, w, 0u);
@@ -260,24 +285,50 @@ __device__ __forceinline__ void evq_fast_ld_leb64(const EvqTile& T, const EvqSca
 
 template <int S>
 __device__ __forceinline__ void evq_fast_ld_plain64(const EvqTile& T, const EvqScanParams& P, u64 (&v)[EVQ_RPT]) {
-  const u64* p = (const u64*) (T.stage + P.streams[S].smem_off + T.desc[S].delta) + evq_fast_first(T, S);
+  const u32 off = P.streams[S].smem_off + T.desc[S].delta + 8u * evq_fast_first(T, S);
+  if ((off & 15u) == 0u) {   // 16-byte vector loads (two values each)
 #pragma unroll
-  for (int i = 0; i < EVQ_RPT; ++i) v[i] = p[i];
+    for (int i = 0; i < EVQ_RPT; i += 2) {
+      u32 a, b, c, d;
+      evq_stage_v4(T, off + 8u * i, a, b, c, d);
+      v[i] = (u64) a | ((u64) b << 32);
+      v[i + 1] = (u64) c | ((u64) d << 32);
+    }
+  } else {
+    const u64* p = (const u64*) (T.stage + off);
+#pragma unroll
+    for (int i = 0; i < EVQ_RPT; ++i) v[i] = p[i];
+  }
 }
 
 // the low halves only: for PLAIN64 columns whose values are known to fit 32 bits
 template <int S>
 __device__ __forceinline__ void evq_fast_ld_plain64_lo(const EvqTile& T, const EvqScanParams& P, u32 (&v)[EVQ_RPT]) {
-  const u32* p = (const u32*) (T.stage + P.streams[S].smem_off + T.desc[S].delta) + 2 * evq_fast_first(T, S);
+  const u32 off = P.streams[S].smem_off + T.desc[S].delta + 8u * evq_fast_first(T, S);
+  if ((off & 15u) == 0u) {
 #pragma unroll
-  for (int i = 0; i < EVQ_RPT; ++i) v[i] = p[2 * i];
+    for (int i = 0; i < EVQ_RPT; i += 2) {
+      u32 b, d;
+      evq_stage_v4(T, off + 8u * i, v[i], b, v[i + 1], d);
+    }
+  } else {
+    const u32* p = (const u32*) (T.stage + off);
+#pragma unroll
+    for (int i = 0; i < EVQ_RPT; ++i) v[i] = p[2 * i];
+  }
 }
 
 template <int S>
 __device__ __forceinline__ void evq_fast_ld_plain32(const EvqTile& T, const EvqScanParams& P, u32 (&v)[EVQ_RPT]) {
-  const u32* p = (const u32*) (T.stage + P.streams[S].smem_off + T.desc[S].delta) + evq_fast_first(T, S);
+  const u32 off = P.streams[S].smem_off + T.desc[S].delta + 4u * evq_fast_first(T, S);
+  if ((off & 15u) == 0u) {
 #pragma unroll
-  for (int i = 0; i < EVQ_RPT; ++i) v[i] = p[i];
+    for (int i = 0; i < EVQ_RPT; i += 4) evq_stage_v4(T, off + 4u * i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+  } else {
+    const u32* p = (const u32*) (T.stage + off);
+#pragma unroll
+    for (int i = 0; i < EVQ_RPT; ++i) v[i] = p[i];
+  }
 }
 
 template <int S>
