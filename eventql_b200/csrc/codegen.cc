@@ -456,6 +456,14 @@ static std::string gen_row_functions(const evqgpu_query& q, const KernelShape& s
 
   // ---- dense tier: group key tuple -> accumulator slot, with the key bounds of this execution as constants
   if (shape.tier == 1 && shape.g1 > 1) {
+    bool all_proven = true;
+    for (size_t i = 0; i < q.group.size(); ++i) {
+      const DenseMap& dm = shape.dense;
+      const bool may_null = dm.key_null_idx[i] != ~0ull;
+      const uint64_t span = dm.key_range[i] - (may_null ? 2 : 1);
+      if (may_null || dm.key_min[i] != 0 || expr_value_max(q.group[i].get(), env) > span) all_proven = false;
+    }
+    if (all_proven) os << "#define EVQ_SLOT_ALWAYS_VALID 1\n";
     os << "__device__ __forceinline__ u32 evq_dense_slot(const u64* key, const u32* ktag, u32& err) {\n  u32 slot = 0;\n  bool ok = true;\n";
     for (size_t i = 0; i < q.group.size(); ++i) {
       const DenseMap& dm = shape.dense;
@@ -526,7 +534,7 @@ static std::string gen_row_functions(const evqgpu_query& q, const KernelShape& s
         for (int w = 0; w < nstate; ++w) {
           const int a = q.state_narrow[w];
           if (a < 0) continue;
-          if (q.narrow_col[a] < 0) os << "    nacc[" << a << " * EVQ_G1 + g] += __popc(sel);\n";
+          if (q.narrow_col[a] < 0) os << "    nacc[" << a << " * EVQ_G1 + g] = __dp4a(0x01010101u, sel, nacc[" << a << " * EVQ_G1 + g]);\n";
           else os << "    nacc[" << a << " * EVQ_G1 + g] = __dp4a(cols.p" << q.narrow_col[a] << "[j], sel, nacc[" << a << " * EVQ_G1 + g]);\n";
         }
         os << "  }\n}\n";

@@ -542,7 +542,11 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
           u32 ktag[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
           evq_keys(row, key, ktag, err);
           const u32 g = evq_dense_slot(key, ktag, err);
+#ifdef EVQ_SLOT_ALWAYS_VALID   // the column statistics bound every key inside the slot range
+          {
+#else
           if (g != ~0u) {
+#endif
             selector ^= (g ^ 4u) << (4 * kk);
             evq_accumulate_smem(row, sacc, g, tid, P.dense_state, err);
           }
