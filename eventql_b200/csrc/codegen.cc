@@ -4,6 +4,7 @@
 // VM::evaluate, sql/runtime/vm.cc:107-157), this file does once per query: the WHERE program, the GROUP BY
 // expressions and every aggregate's accumulate program become straight-line C inside the hand-written kernel of
 // kernels/evq_scan_kernel.cuh, and the `get` side of the select list becomes the emit kernel.
+#include <functional>
 #include <sstream>
 #include "query.h"
 
@@ -435,6 +436,18 @@ static std::string gen_row_functions(const evqgpu_query& q, const KernelShape& s
 
   // ---- WHERE
   CodegenEnv env = row_env(shape);
+  {
+    // a WHERE program without integer division cannot raise: rows past the end of a short tile may then run it too,
+    // which lets the kernel fold the validity test into the predicate instead of branching around it
+    std::function<bool(const Expr*)> may_raise = [&](const Expr* e) -> bool {
+      if (!e) return false;
+      if (e->op == EVQ_X_CALL && (e->info().fn == Fn::DIV || e->info().fn == Fn::MOD) && e->info().args[0] != EVQ_FLOAT64) return true;
+      for (const auto& a : e->args)
+        if (may_raise(a.get())) return true;
+      return false;
+    };
+    if (!may_raise(q.where.get())) os << "#define EVQ_WHERE_PURE 1\n";
+  }
   os << "__device__ __forceinline__ bool evq_where(const EvqRow& row, u32& err) {\n";
   if (q.where) {
     Code c = gen_expr(q.where.get(), env);

@@ -536,7 +536,11 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
         const int k = 4 * j + kk;
         EvqRow row;
         evq_fast_row(cols, k, row);
+#ifdef EVQ_WHERE_PURE
+        const bool pass = evq_where(row, err) & (EVQ_RPT * tid + k < T.rows);
+#else
         const bool pass = (EVQ_RPT * tid + k < T.rows) && evq_where(row, err);
+#endif
         if (pass) {   // (rows passed are counted from the rows accumulators at the end)
           u64 key[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
           u32 ktag[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
