@@ -409,9 +409,8 @@ static void gen_fast_layout(std::ostringstream& os, const KernelShape& shape) {
             general = "prep.general[" + std::to_string(c.gen_slot) + "]";
             start = "prep.start[" + std::to_string(c.gen_slot) + "]";
           }
-          // second template argument: 2 = two sub-index entry points packed in `start`, 1 = one searched entry point
-          os << "    evq_fast_ld_leb" << (c.leb_len <= 4 ? "32" : "64") << "<" << S << ", " << (c.sub_stream >= 0 ? 2 : 1) << ", " << c.leb_len
-             << ">(T, P, " << general << ", " << start << ", raw);\n";
+          os << "    evq_fast_ld_leb" << (c.leb_len <= 4 ? "32" : "64") << "<" << S << ", 0, " << c.leb_len << ">(T, P, " << general << ", "
+             << start << ", raw);\n";
         }
         break;
     }

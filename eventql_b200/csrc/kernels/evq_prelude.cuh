@@ -170,8 +170,8 @@ __device__ __forceinline__ void evq_producer_plan(const EvqScanParams& P, const 
     start = blk0 * 16 * S.bits;
     end = blk1 * 16 * S.bits;
   } else if (S.kind == EVQ_KIND_SUBIDX) {
-    start = (u64) tile * EVQ_SUB_ENTRIES * 2;
-    end = start + EVQ_SUB_ENTRIES * 2;
+    start = (u64) tile * (EVQ_TILE_ROWS / 8) * 2;
+    end = start + (EVQ_TILE_ROWS / 8) * 2;
   } else {
     u64 v0 = row0, v1 = row0 + rows;
     if (S.val_index) {

@@ -121,10 +121,9 @@ __device__ __forceinline__ bool evq_fast_general(const EvqTile& T) {
   return T.desc[S].nbytes != (u32) L * T.desc[S].nvals;
 }
 
-// EVQ_RPT == 8, EVQ_SUB_GRAN == 4: two entries per thread (low half: value 8t, high half: value 8t + 4) in one word
 template <int X>
 __device__ __forceinline__ u32 evq_fast_substart(const EvqTile& T, const EvqScanParams& P) {
-  return ((const u32*) (T.stage + P.streams[X].smem_off + T.desc[X].delta))[T.ctid];
+  return (u32) ((const u16*) (T.stage + P.streams[X].smem_off + T.desc[X].delta))[T.ctid];   // EVQ_RPT == 8: one entry per thread
 }
 
 // ---- per-thread decode of 4 consecutive values -------------------------------------------------------------------------
@@ -235,20 +234,15 @@ __device__ __forceinline__ void evq_fast_ld_leb32(const EvqTile& T, const EvqSca
       }
     }
   } else {
-    // G == 2: `start` packs two entry points from the sub-index (value 0 and value EVQ_RPT / 2 of the thread), decoded as
-    // two independent chains; G == 1: one entry point (searched by evq_fast_prep), one chain over all values
-    u32 p[2] = {pay + (G == 2 ? (start & 0xffffu) : start), pay + (start >> 16)};
+    u32 p = pay + start;
 #pragma unroll
-    for (int i = 0; i < EVQ_RPT / G; ++i) {
-#pragma unroll
-      for (int h = 0; h < G; ++h) {
-        const u32 x = evq_stage_u32(T, p[h]);
-        const u32 tm = ~x & 0x80808080u;           // terminator bits of the window
-        const u32 msk = tm ^ (tm - 1u);            // every bit up to and including the first of them
-        const u32 y = x & msk & 0x7f7f7f7fu;
-        v[h * (EVQ_RPT / 2) + i] = L == 2 ? evq_leb_pack2(y) : evq_fast_pack4(y);
-        p[h] += __popc(msk) >> 3;
-      }
+    for (int i = 0; i < EVQ_RPT; ++i) {
+      const u32 x = evq_stage_u32(T, p);
+      const u32 tm = ~x & 0x80808080u;           // terminator bits of the window
+      const u32 msk = tm ^ (tm - 1u);            // every bit up to and including the first of them
+      const u32 y = x & msk & 0x7f7f7f7fu;
+      v[i] = L == 2 ? evq_leb_pack2(y) : evq_fast_pack4(y);
+      p += __popc(msk) >> 3;
     }
   }
 }
@@ -260,7 +254,7 @@ __device__ __forceinline__ void evq_fast_ld_leb64(const EvqTile& T, const EvqSca
   const u8* pay = T.stage + P.streams[S].smem_off + T.desc[S].delta;
   const u8* p;
   if (!general) p = pay + (u32) L * evq_fast_first(T, S);
-  else p = pay + (G == 2 ? (start & 0xffffu) : start);   // (one chain: the second sub-index entry is not needed)
+  else p = pay + start;
 #pragma unroll
   for (int i = 0; i < EVQ_RPT; ++i) {
     u32 lo, hi;

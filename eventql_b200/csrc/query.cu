@@ -138,7 +138,7 @@ static StageLayout stage_layout(const evqgpu_query& q, evqgpu_table* t, const Bi
     };
     place(cs.data_stream, c.data_tile_cap);
     if (cs.nullable) place(cs.level_stream, c.level_tile_cap);
-    if (cs.sub_stream >= 0) place(cs.sub_stream, EVQ_SUB_ENTRIES * 2);
+    if (cs.sub_stream >= 0) place(cs.sub_stream, (EVQ_TILE_ROWS / 8) * 2);
   }
   L.stage_bytes = (uint32_t) round_up(off + 128, 128);
   (void) q;

@@ -197,9 +197,9 @@ __global__ void k_leb_select(const u8* __restrict__ data, u64 nbytes, const u64*
   off_index[t] = nbytes;   // fewer values than expected: the scan kernel never reads past nbytes
 }
 
-// sub_index[t][g] = byte offset, from the tile's first byte, at which value EVQ_SUB_GRAN * g of tile t starts.  One warp per tile walks
+// sub_index[t][g] = byte offset, from the tile's first byte, at which value 8g of tile t starts.  One warp per tile walks
 // the tile's bytes in 16-byte chunks (32 chunks per step), numbers the terminator bytes with a warp scan and records the
-// byte behind every EVQ_SUB_GRAN-th one.
+// byte behind every 8th one.
 __global__ void k_leb_sub_index(const u8* __restrict__ data, const u64* __restrict__ off_index, u32 num_tiles, u16* __restrict__ sub) {
   const u32 tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const u32 lane = threadIdx.x & 31;
@@ -209,7 +209,7 @@ __global__ void k_leb_sub_index(const u8* __restrict__ data, const u64* __restri
   const u32 delta = (u32) (start - al);
   const u32 tb = (u32) (end - al);                 // bytes [delta, tb) of the aligned window are the tile
   const u32 nchunks = (tb + 15u) >> 4;
-  u16* out = sub + (u64) tile * EVQ_SUB_ENTRIES;
+  u16* out = sub + (u64) tile * (EVQ_TILE_ROWS / 8);
   if (lane == 0) out[0] = 0;
   u32 running = 0;
   for (u32 base = 0; base < nchunks; base += 32) {
@@ -235,9 +235,9 @@ __global__ void k_leb_sub_index(const u8* __restrict__ data, const u64* __restri
     while (m) {
       const u32 k = __ffs(m) - 1u;
       m &= m - 1u;
-      if ((j & (EVQ_SUB_GRAN - 1u)) == EVQ_SUB_GRAN - 1u) {
-        const u32 g = (j + 1u) / EVQ_SUB_GRAN;
-        if (g < EVQ_SUB_ENTRIES) out[g] = (u16) (16u * c + k + 1u - delta);
+      if ((j & 7u) == 7u) {
+        const u32 g = (j + 1u) >> 3;
+        if (g < EVQ_TILE_ROWS / 8) out[g] = (u16) (16u * c + k + 1u - delta);
       }
       ++j;
     }
@@ -463,7 +463,7 @@ void table_finish_column(evqgpu_table* t, Column& c) {
       c.data_tile_cap = span_from_index(c.off_index.as<u64>(), 1, 0, 0);
       if (c.leb_max_len >= 2 && !nullable && ntiles) {
         // where the values of the column differ in length: starts of every 8th value (the fast kernel's decode entry points)
-        c.sub_index.alloc((uint64_t) ntiles * EVQ_SUB_ENTRIES * 2 + 256);
+        c.sub_index.alloc((uint64_t) ntiles * (EVQ_TILE_ROWS / 8) * 2 + 256);
         EVQ_CUDA(cudaMemsetAsync(c.sub_index.p, 0, c.sub_index.bytes, ctx->stream));
         k_leb_sub_index<<<(unsigned) (((uint64_t) ntiles * 32 + 255) / 256), 256, 0, ctx->stream>>>(
             c.data.buf.as<u8>(), c.off_index.as<u64>(), ntiles, c.sub_index.as<u16>());

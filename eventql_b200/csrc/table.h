@@ -6,9 +6,9 @@
 //   dlevel  : same for the DLEVEL pages of optional columns (bit-packed, libsimdcomp vertical layout)
 //   val_index[t] : number of non-NULL values before row tile t        (optional columns)   u64[ntiles+1]
 //   off_index[t] : byte offset of the first value of row tile t       (LEB128 columns)     u64[ntiles+1]
-//   sub_index[t][g] : byte offset inside tile t of its value 4g        (LEB128 columns whose values differ in length)
-//                     u16[ntiles][256] = 0.5 B per row; lets the fast scan kernel start two independent 4-value decode
-//                     chains per thread without searching value boundaries
+//   sub_index[t][g] : byte offset inside tile t of its value 8g        (LEB128 columns whose values differ in length)
+//                     u16[ntiles][128] = 0.25 B per row; lets the fast scan kernel start its per-thread sequential decode
+//                     without searching value boundaries
 // A row tile is EVQ_TILE_ROWS = 1024 records.
 #pragma once
 #include <string>
@@ -33,7 +33,7 @@ struct Column {
   bool scannable = false;      // flat, numeric
   DeviceStream data, dlevel;
   DevBuf off_index, val_index;
-  DevBuf sub_index;            // variable-length LEB128 columns: u16[ntiles][256] byte offset (from the tile's first byte) of every 4th value
+  DevBuf sub_index;            // variable-length LEB128 columns: u16[ntiles][128] byte offset (from the tile's first byte) of every 8th value
   uint64_t num_values = 0;
   uint64_t data_payload_bytes = 0;    // algorithmic bytes of the DATA stream
   uint64_t level_payload_bytes = 0;
