@@ -46,6 +46,7 @@ void evqgpu_ctx_destroy(evqgpu_ctx* ctx) {
   cudaSetDevice(ctx->device);
   evqgpu_comm_destroy(ctx);
   ctx->jit_cache.clear();
+  evq::pool_trim(ctx->device);
   if (ctx->pinned_scratch) cudaFreeHost(ctx->pinned_scratch);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;

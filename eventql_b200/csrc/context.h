@@ -32,6 +32,14 @@ namespace evq {
 
 inline void use_device(const evqgpu_ctx* ctx) { EVQ_CUDA(cudaSetDevice(ctx->device)); }
 
+// Device memory goes through a small per-device pool: loading a column allocates ~8 buffers (stream, indexes, scan
+// scratch) and cudaMalloc / cudaFree of hundreds of MB cost about a millisecond each (cudaFree also synchronises the
+// device), which dominated the per-column load time.  Blocks are reused by best fit (within 25 % slack); the pool is
+// trimmed when it holds more than 24 GiB or when the last context of the device goes away.
+void* pool_alloc(uint64_t bytes, uint64_t* granted);
+void pool_free(void* p, uint64_t granted);
+void pool_trim(int device);
+
 // device allocation that frees itself
 struct DevBuf {
   void* p = nullptr;
@@ -48,12 +56,12 @@ struct DevBuf {
   void alloc(uint64_t n) {
     release();
     if (n == 0) n = 16;
-    cudaError_t e = cudaMalloc(&p, n);
-    if (e != cudaSuccess) { p = nullptr; fail(EVQGPU_ERR_NOMEM, "cudaMalloc(%llu) failed: %s", (unsigned long long) n, cudaGetErrorString(e)); }
-    bytes = n;
+    uint64_t granted = 0;
+    p = pool_alloc(n, &granted);
+    bytes = granted;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) pool_free(p, bytes);
     p = nullptr;
     bytes = 0;
   }
