@@ -46,7 +46,7 @@ class ColumnInfo(C.Structure):
     _fields_ = [("name", C.c_char_p), ("column_id", C.c_uint32), ("logical_type", C.c_uint32), ("encoding", C.c_uint32),
                 ("rlevel_max", C.c_uint32), ("dlevel_max", C.c_uint32), ("sql_type", C.c_uint32), ("loaded", C.c_uint32),
                 ("data_bytes", C.c_uint64), ("level_bytes", C.c_uint64), ("num_values", C.c_uint64),
-                ("value_bits", C.c_uint32), ("leb_max_len", C.c_uint32)]
+                ("value_bits", C.c_uint32), ("leb_max_len", C.c_uint32), ("value_min", C.c_uint64), ("value_max", C.c_uint64)]
 
 
 class SynthColumn(C.Structure):
@@ -62,7 +62,7 @@ class QueryStats(C.Structure):
 
 class DebugColumn(C.Structure):
     _fields_ = [("sql_type", C.c_uint32), ("encoding", C.c_uint32), ("dlevel_max", C.c_uint32), ("value_bits", C.c_uint32),
-                ("leb_max_len", C.c_uint32)]
+                ("leb_max_len", C.c_uint32), ("reserved", C.c_uint32), ("value_min", C.c_uint64), ("value_max", C.c_uint64)]
 
 
 # every symbol include/evqgpu.h declares (tests/test_abi.py checks header and library against this list)
@@ -205,10 +205,10 @@ class _PlanC:
 
 
 def debug_generate(plan: P.QueryPlan, columns: Sequence[tuple], tier: int = 1, dense_slots: int = 1, compile: bool = True):
-    """Device-free: kernel text (and NVRTC compilation for sm_100a) of a plan over columns [(sql_type, encoding, dlevel_max)]."""
+    """Device-free: kernel text (and NVRTC compilation for sm_100a) of a plan over columns [(sql_type, encoding, dlevel_max[, value_bits, leb_max_len, 0, value_min, value_max])]."""
     L = lib()
     pc = _PlanC(plan)
-    cols = (DebugColumn * max(1, len(columns)))(*[DebugColumn(*(tuple(c) + (0,) * (5 - len(c)))) for c in columns])
+    cols = (DebugColumn * max(1, len(columns)))(*[DebugColumn(*(tuple(c) + (0,) * (8 - len(c)))) for c in columns])
     n = C.c_uint64(0)
     cub = C.c_uint64(0)
     check(L.evqgpu_debug_generate(C.byref(pc.desc), cols, tier, dense_slots, None, 0, C.byref(n), 0, None))

@@ -52,6 +52,9 @@ static CodegenEnv row_env(const KernelShape& shape) {
     env.col_max.assign(shape.cols.size(), ~0ull);
     for (size_t i = 0; i < shape.cols.size(); ++i)
       if (shape.cols[i].used) env.col_max[i] = shape.cols[i].vmax;
+    env.col_min.assign(shape.cols.size(), 0ull);
+    for (size_t i = 0; i < shape.cols.size(); ++i)
+      if (shape.cols[i].used && !shape.cols[i].nullable) env.col_min[i] = shape.cols[i].vmin;
   }
   return env;
 }
@@ -128,28 +131,128 @@ void layout_states(evqgpu_query& q, const KernelShape& shape) {
   q.nnarrow = 0;
 }
 
-// Byte-wide aggregates of the fast dense kernel with a handful of groups: the rows counter and sums of required 1-byte
-// LEB128 columns.  The thread keeps them as u32 registers per group and feeds them 4 rows at a time with dp4a (the packed
-// bytes of the column against a 0/1 byte mask "row belongs to group g"), so they cost ~1.5 instructions per row instead
-// of a shared-memory read-modify-write each.  Only the thread-private storage changes, not the global state layout.
+// Byte-plane sums of the fast dense kernel with a handful of groups (<= 4).  A sum(W * B) - W an expression below 2^32,
+// B one below 256 or absent - is kept as u32 registers per (byte plane of W, group) and fed 4 rows at a time with dp4a:
+// the 4 rows' bytes of plane p against the 4 rows' B bytes masked by "row belongs to group g".  That replaces a 64-bit
+// shared-memory read-modify-write per row and word (the fast kernel's shared-memory bandwidth limit) by about
+// planes / 4 dot products per row, and the value is  SUM_p 256^p * acc[p][g].  The rows counter is W = B = 1; sums of
+// 1-byte LEB128 columns are one plane: the column's raw bytes.  Only the thread-private storage changes, not the global
+// state layout.
+static bool is_packed_byte_column(const Expr* e, const KernelShape& shape) {
+  if (e->op != EVQ_X_INPUT || e->col >= shape.cols.size()) return false;
+  const ColSig& c = shape.cols[e->col];
+  return c.used && c.kind == EVQ_KIND_LEB128 && c.leb_len == 1 && !c.nullable && c.sql_type != EVQ_BOOL && c.sql_type != EVQ_FLOAT64 &&
+         c.sql_type != EVQ_INT64;
+}
+
 void layout_narrow(evqgpu_query& q, const KernelShape& shape) {
   q.state_narrow.assign(q.state_ops.size(), -1);
   q.narrow_col.clear();
   q.nnarrow = 0;
+  q.plane_w.clear();
+  q.plane_b.clear();
+  q.plane_sums.clear();
+  q.swar_slots = false;
+  q.plane_sig.clear();
   if (!shape.fast || shape.tier != 1 || shape.g1 < 2 || shape.g1 > 4 || getenv("EVQGPU_NO_NARROW")) return;
-  auto take = [&](int w, int col) {
-    if (q.state_narrow[w] >= 0) return;
-    q.state_narrow[w] = q.nnarrow++;
+  const CodegenEnv env = row_env(shape);
+  int budget = 56;   // u32 accumulator registers per thread
+  if (const char* e = getenv("EVQGPU_PLANE_BUDGET")) budget = atoi(e);
+  auto need_packed = [&](int col) {
+    for (int c : q.narrow_col)
+      if (c == col) return;
     q.narrow_col.push_back(col);
   };
-  take(0, -1);
+  auto operand = [&](std::vector<evqgpu_query::PlaneOperand>& list, const evqgpu_query::PlaneOperand& o) -> int {
+    for (size_t i = 0; i < list.size(); ++i)
+      if (list[i].expr && o.expr && list[i].expr->signature() == o.expr->signature()) return (int) i;
+    list.push_back(o);
+    return (int) list.size() - 1;
+  };
+  auto planes_of = [&](const Expr* e) -> int {
+    if (is_packed_byte_column(e, shape)) return 1;
+    const uint32_t b = expr_value_bits(e, env);
+    return (int) ((b + 7) / 8);
+  };
+  {   // the rows counter
+    evqgpu_query::PlaneSum ps;
+    ps.word = 0;
+    ps.plane0 = q.nnarrow;
+    q.nnarrow += 1;
+    q.state_narrow[0] = 0;
+    q.plane_sums.push_back(ps);
+  }
   for (const auto& item : q.select) {
-    if (!item.agg || item.state0 <= 0) continue;
+    if (!item.agg || item.state0 <= 0 || q.state_narrow[item.state0] >= 0) continue;
     if (q.state_keys[item.state0].compare(0, 4, "sum:") != 0) continue;
+    const FnInfo& fi = item.agg->info();
+    if (fi.args.empty() || fi.args[0] != EVQ_UINT64) continue;
     const Expr* arg = item.agg->args[0].get();
-    if (arg->op != EVQ_X_INPUT || arg->col >= shape.cols.size()) continue;
-    const ColSig& c = shape.cols[arg->col];
-    if (c.kind == EVQ_KIND_LEB128 && c.leb_len == 1 && !c.nullable && c.sql_type != EVQ_BOOL) take(item.state0, (int) arg->col);
+    if (expr_may_raise(arg)) continue;
+    // candidates (W, B): the whole argument, or the two ways to split a top-level product
+    struct Cand { const Expr* w; const Expr* b; };
+    std::vector<Cand> cands = {{arg, nullptr}};
+    if (arg->op == EVQ_X_CALL && arg->info().fn == Fn::MUL && arg->args.size() == 2) {
+      cands.push_back({arg->args[0].get(), arg->args[1].get()});
+      cands.push_back({arg->args[1].get(), arg->args[0].get()});
+    }
+    const Cand* best = nullptr;
+    int best_planes = 0;
+    for (const auto& c : cands) {
+      if (expr_value_max(c.w, env) > 0xffffffffull) continue;
+      if (c.b && expr_value_max(c.b, env) > 255) continue;
+      const int np = planes_of(c.w);
+      if (!best || np < best_planes) { best = &c; best_planes = np; }
+    }
+    if (!best || (q.nnarrow + best_planes) * shape.g1 > budget) continue;
+    evqgpu_query::PlaneOperand w;
+    w.expr = best->w;
+    w.nplanes = best_planes;
+    if (is_packed_byte_column(best->w, shape)) { w.packed_col = (int) best->w->col; need_packed(w.packed_col); }
+    evqgpu_query::PlaneSum ps;
+    ps.word = item.state0;
+    ps.w = operand(q.plane_w, w);
+    ps.nplanes = best_planes;
+    if (best->b) {
+      evqgpu_query::PlaneOperand b;
+      b.expr = best->b;
+      if (is_packed_byte_column(best->b, shape)) {
+        b.packed_col = (int) best->b->col;
+      } else if (best->b->op == EVQ_X_CALL && best->b->args.size() == 2 &&
+                 (best->b->info().fn == Fn::ADD || best->b->info().fn == Fn::SUB)) {
+        // literal +- 1-byte column, decided per byte without carries or borrows (the value range says so): done on the
+        // packed bytes of 4 rows at once
+        const Expr* x = best->b->args[0].get();
+        const Expr* y = best->b->args[1].get();
+        const bool add = best->b->info().fn == Fn::ADD;
+        if (x->op == EVQ_X_LITERAL && x->type == EVQ_UINT64 && x->imm <= 255 && is_packed_byte_column(y, shape) &&
+            (add || expr_value_max(y, env) <= x->imm)) {
+          b.packed_col = (int) y->col; b.swar = add ? 2 : 1; b.swar_lit = x->imm;
+        } else if (add && y->op == EVQ_X_LITERAL && y->type == EVQ_UINT64 && y->imm <= 255 && is_packed_byte_column(x, shape)) {
+          b.packed_col = (int) x->col; b.swar = 2; b.swar_lit = y->imm;
+        }
+      }
+      if (b.packed_col >= 0) need_packed(b.packed_col);
+      ps.b = operand(q.plane_b, b);
+    }
+    ps.plane0 = q.nnarrow;
+    q.nnarrow += best_planes;
+    q.state_narrow[item.state0] = (int) q.plane_sums.size();
+    q.plane_sums.push_back(ps);
+  }
+  // dense slots on the packed key bytes: every key a bare 1-byte column whose range the statistics bound inside the slots
+  {
+    bool ok = !q.group.empty() && shape.dense.slots <= 4;
+    for (size_t i = 0; ok && i < q.group.size(); ++i) {
+      const DenseMap& dm = shape.dense;
+      const bool may_null = dm.key_null_idx[i] != ~0ull;
+      ok = is_packed_byte_column(q.group[i].get(), shape) && !may_null && dm.key_min[i] == 0 &&
+           expr_value_max(q.group[i].get(), env) <= dm.key_range[i] - 1;
+    }
+    if (ok && !getenv("EVQGPU_NO_SWAR_SLOTS")) {
+      q.swar_slots = true;
+      for (const auto& g : q.group) need_packed((int) g->col);
+    }
   }
   // re-number the words that stay in shared memory
   q.nstate_smem = 0;
@@ -157,6 +260,12 @@ void layout_narrow(evqgpu_query& q, const KernelShape& shape) {
     q.state_smem[i] = -1;
     if (q.state_carry_of[i] < 0 && q.state_narrow[i] < 0) q.state_smem[i] = q.nstate_smem++;
   }
+  std::ostringstream sg;
+  sg << "S" << (int) q.swar_slots << ";";
+  for (const auto& ps : q.plane_sums)
+    sg << ps.word << ":" << (ps.w >= 0 ? q.plane_w[ps.w].expr->signature() : std::string("1")) << "*"
+       << (ps.b >= 0 ? q.plane_b[ps.b].expr->signature() : std::string("1")) << "/" << ps.nplanes << ";";
+  q.plane_sig = sg.str();
 }
 
 // Upper bound on the bit length of a uint64-valued expression, from the column statistics of the scanned tables
@@ -539,24 +648,101 @@ static std::string gen_row_functions(const evqgpu_query& q, const KernelShape& s
           gen_flush_word(w, "sacc[EVQ_SIDX(g, " + std::to_string(q.state_smem[w]) + ")]", "dense_state + (u64) g * " + std::to_string(nstate));
       os << "}\n";
       if (q.nnarrow > 0) {
-        // byte-wide aggregates: u32 registers per (word, group), fed 4 rows at a time.  `selector` holds one nibble per
-        // row of the quad: its dense slot, or 4 when the row did not pass WHERE; PRMT turns it into the 0/1 byte mask of
-        // group g, dp4a sums the column's 4 bytes under that mask.
+        // byte-plane sums (layout_narrow): u32 registers per (plane, group), fed 4 rows at a time.  `selector` holds one
+        // nibble per row of the quad: its dense slot, or >= 4 when the row did not pass WHERE; PRMT turns it into the byte
+        // mask of group g (0xff where the row belongs to it).  Sums without a byte operand use the mask itself as the
+        // signed operand -1, i.e. they accumulate the NEGATED sum (mod 2^32), which evq_narrow_flush undoes.
+        if (q.swar_slots) {
+          os << "#define EVQ_SWAR_SLOTS 1\n";
+          os << "__device__ __forceinline__ u32 evq_quad_slots(const EvqCols& cols, int j) {\n  const u32 s = 0u";
+          for (size_t i = 0; i < q.group.size(); ++i) os << " + cols.p" << q.group[i]->col << "[j] * " << shape.dense.key_stride[i] << "u";
+          os << ";   // the slot of each row in its byte (< 4: no carries)\n";
+          os << "  return __byte_perm(s | (s >> 4), 0u, 0x4420u);   // one nibble per row\n}\n";
+        }
+        // a W / B expression for row kk of quad j
+        auto quad_env = [&](int kk) {
+          CodegenEnv e = row_env(shape);
+          for (size_t i = 0; i < shape.cols.size(); ++i) {
+            if (!shape.cols[i].used) continue;
+            const std::string ref = "cols.c" + std::to_string(i) + "[4 * j + " + std::to_string(kk) + "]";
+            const bool widen = fast_ctype(shape.cols[i]) == std::string("u32") && shape.cols[i].sql_type != EVQ_BOOL;
+            e.col_value[i] = widen ? "((u64) " + ref + ")" : ref;
+          }
+          return e;
+        };
         os << "__device__ __forceinline__ void evq_accumulate_narrow(const EvqCols& cols, int j, u32 selector, u32* nacc) {\n";
-        os << "#pragma unroll\n  for (int g = 0; g < EVQ_G1; ++g) {\n    const u32 sel = __byte_perm(1u << (8 * g), 0u, selector);\n";
-        for (int w = 0; w < nstate; ++w) {
-          const int a = q.state_narrow[w];
-          if (a < 0) continue;
-          if (q.narrow_col[a] < 0) os << "    nacc[" << a << " * EVQ_G1 + g] = __dp4a(0x01010101u, sel, nacc[" << a << " * EVQ_G1 + g]);\n";
-          else os << "    nacc[" << a << " * EVQ_G1 + g] = __dp4a(cols.p" << q.narrow_col[a] << "[j], sel, nacc[" << a << " * EVQ_G1 + g]);\n";
+        os << "  u32 m[EVQ_G1];\n#pragma unroll\n  for (int g = 0; g < EVQ_G1; ++g) m[g] = __byte_perm(0xffu << (8 * g), 0u, selector);\n";
+        // byte planes of every distinct W
+        for (size_t wi = 0; wi < q.plane_w.size(); ++wi) {
+          const auto& W = q.plane_w[wi];
+          if (W.packed_col >= 0) {
+            os << "  const u32 w" << wi << "p0 = cols.p" << W.packed_col << "[j];\n";
+            continue;
+          }
+          for (int kk = 0; kk < 4; ++kk) {
+            Code c = gen_expr(W.expr, quad_env(kk));
+            os << "  const u32 w" << wi << "r" << kk << " = (u32) (" << c.value << ");\n";
+          }
+          const std::string w = "w" + std::to_string(wi);
+          if (W.nplanes == 1) {
+            os << "  const u32 " << w << "p0 = __byte_perm(__byte_perm(" << w << "r0, " << w << "r1, 0x0040u), __byte_perm(" << w << "r2, "
+               << w << "r3, 0x0040u), 0x5410u);\n";
+          } else {
+            os << "  const u32 " << w << "a = __byte_perm(" << w << "r0, " << w << "r1, 0x5140u), " << w << "b = __byte_perm(" << w << "r2, "
+               << w << "r3, 0x5140u);\n";
+            os << "  const u32 " << w << "p0 = __byte_perm(" << w << "a, " << w << "b, 0x5410u), " << w << "p1 = __byte_perm(" << w << "a, "
+               << w << "b, 0x7632u);\n";
+            if (W.nplanes > 2) {
+              os << "  const u32 " << w << "c = __byte_perm(" << w << "r0, " << w << "r1, 0x7362u), " << w << "d = __byte_perm(" << w
+                 << "r2, " << w << "r3, 0x7362u);\n";
+              os << "  const u32 " << w << "p2 = __byte_perm(" << w << "c, " << w << "d, 0x5410u);\n";
+              if (W.nplanes > 3) os << "  const u32 " << w << "p3 = __byte_perm(" << w << "c, " << w << "d, 0x7632u);\n";
+            }
+          }
+        }
+        // the 4 rows' bytes of every distinct B
+        for (size_t bi = 0; bi < q.plane_b.size(); ++bi) {
+          const auto& B = q.plane_b[bi];
+          os << "  const u32 b" << bi << " = ";
+          if (B.packed_col >= 0 && B.swar == 0) {
+            os << "cols.p" << B.packed_col << "[j];\n";
+          } else if (B.packed_col >= 0) {
+            char lit[32];
+            snprintf(lit, sizeof(lit), "0x%08xu", (unsigned) (B.swar_lit * 0x01010101u));
+            os << lit << (B.swar == 1 ? " - " : " + ") << "cols.p" << B.packed_col << "[j];\n";
+          } else {
+            std::string r[4];
+            for (int kk = 0; kk < 4; ++kk) r[kk] = "(u32) (" + gen_expr(B.expr, quad_env(kk)).value + ")";
+            os << "__byte_perm(__byte_perm(" << r[0] << ", " << r[1] << ", 0x0040u), __byte_perm(" << r[2] << ", " << r[3]
+               << ", 0x0040u), 0x5410u);\n";
+          }
+        }
+        os << "#pragma unroll\n  for (int g = 0; g < EVQ_G1; ++g) {\n";
+        for (size_t bi = 0; bi < q.plane_b.size(); ++bi) os << "    const u32 b" << bi << "m = b" << bi << " & m[g];\n";
+        for (const auto& ps : q.plane_sums) {
+          for (int pl = 0; pl < ps.nplanes; ++pl) {
+            const std::string acc = "nacc[" + std::to_string(ps.plane0 + pl) + " * EVQ_G1 + g]";
+            const std::string plane = ps.w < 0 ? std::string("0x01010101u") : "w" + std::to_string(ps.w) + "p" + std::to_string(pl);
+            if (ps.b < 0) os << "    " << acc << " = evq_dp4a_us(" << plane << ", m[g], " << acc << ");\n";
+            else os << "    " << acc << " = __dp4a(" << plane << ", b" << ps.b << "m, " << acc << ");\n";
+          }
         }
         os << "  }\n}\n";
+        // rows that passed WHERE, from the (negated) rows counters
+        os << "__device__ __forceinline__ u64 evq_narrow_rows(const u32* nacc) {\n  u64 n = 0;\n#pragma unroll\n"
+              "  for (int g = 0; g < EVQ_G1; ++g) n += (u64) (0u - nacc[g]);\n  return n;\n}\n";
         os << "__device__ __forceinline__ void evq_narrow_flush(const u32* nacc, u64* dense_state) {\n";
         for (int g = 0; g < shape.g1; ++g)
-          for (int w = 0; w < nstate; ++w)
-            if (q.state_narrow[w] >= 0)
-              gen_flush_word(w, "(u64) nacc[" + std::to_string(q.state_narrow[w] * shape.g1 + g) + "]",
-                             "dense_state + " + std::to_string((uint64_t) g * nstate));
+          for (const auto& ps : q.plane_sums) {
+            std::string v;
+            for (int pl = 0; pl < ps.nplanes; ++pl) {
+              std::string a = "nacc[" + std::to_string((ps.plane0 + pl) * shape.g1 + g) + "]";
+              if (ps.b < 0) a = "(0u - " + a + ")";
+              a = "((u64) " + a + " << " + std::to_string(8 * pl) + ")";
+              v += (pl ? " + " : "") + a;
+            }
+            gen_flush_word(ps.word, v, "dense_state + " + std::to_string((uint64_t) g * nstate));
+          }
         os << "}\n";
       }
     } else {
@@ -715,7 +901,8 @@ std::string generate_source(const evqgpu_query& q, const KernelShape& shape_in) 
      << std::max(1, q.nstate_smem) << "\n#define EVQ_NKEYS " << q.group.size() << "\n#define EVQ_NLEB "
      << shape.nleb << "\n#define EVQ_NNULL " << shape.nnull << "\n#define EVQ_HAS_PREP "
      << ((shape.nleb > 0 || shape.nnull > 0) ? 1 : 0) << "\n#define EVQ_MIN_CTAS " << shape.min_ctas << "\n#define EVQ_NGEN "
-     << shape.ngen << "\n#define EVQ_GEN_CHUNKS " << gen_chunks(shape) << "\n#define EVQ_NNARROW " << q.nnarrow << "\n";
+     << shape.ngen << "\n#define EVQ_GEN_CHUNKS " << gen_chunks(shape) << "\n#define EVQ_NNARROW " << q.nnarrow << "\n#define EVQ_NSTATE_SMEM " << q.nstate_smem << "\n";
+  if (getenv("EVQGPU_DRYRUN")) os << "#define EVQ_DRYRUN 1\n";
   os << kSrcAbi << "\n" << kSrcPrelude << "\n";
   const std::string kern = shape.fast ? kSrcScanFast : kSrcScanKernel;
   const std::string marker = "//@@EVQ_GENERATED@@";

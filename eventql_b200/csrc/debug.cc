@@ -33,6 +33,7 @@ extern "C" int evqgpu_debug_generate(const evqgpu_query_desc* desc, const evqgpu
       cs.dmax = columns[i].dlevel_max;
       cs.bits = columns[i].value_bits ? columns[i].value_bits : 64;
       cs.vmax = cs.bits >= 64 ? ~0ull : (1ull << cs.bits) - 1;
+      if (columns[i].value_max) { cs.vmax = columns[i].value_max; cs.vmin = columns[i].value_min; }
       cs.leb_len = columns[i].leb_max_len ? columns[i].leb_max_len : 10;
       cs.data_stream = s.nstreams++;
       if (cs.nullable) { cs.level_stream = s.nstreams++; cs.null_slot = s.nnull++; }

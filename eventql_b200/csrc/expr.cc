@@ -250,7 +250,7 @@ static Range expr_range(const Expr* e, const CodegenEnv& env) {
     case EVQ_X_INPUT:
       if (e->type == EVQ_BOOL) return {0, 1};
       if (e->type != EVQ_UINT64 && e->type != EVQ_TIMESTAMP64) return kAny;
-      return {0, e->col < env.col_max.size() ? env.col_max[e->col] : ~0ull};
+      return {e->col < env.col_min.size() ? env.col_min[e->col] : 0ull, e->col < env.col_max.size() ? env.col_max[e->col] : ~0ull};
     case EVQ_X_LITERAL:
       if (e->type == EVQ_BOOL) return {e->imm ? 1ull : 0ull, e->imm ? 1ull : 0ull};
       if (e->type != EVQ_UINT64 && e->type != EVQ_TIMESTAMP64) return kAny;
@@ -294,6 +294,32 @@ uint32_t expr_value_bits(const Expr* e, const CodegenEnv& env) {
 uint64_t expr_value_max(const Expr* e, const CodegenEnv& env) { return expr_range(e, env).hi; }
 
 static Code gen_expr_impl(const Expr* e, const CodegenEnv& env);
+
+// Can evaluating `e` raise (integer division / modulo by zero, math.cc:136-216)?  Such subtrees are never folded away.
+bool expr_may_raise(const Expr* e) {
+  if (e->op == EVQ_X_CALL) {
+    const Fn fn = e->info().fn;
+    if (fn == Fn::DIV || fn == Fn::MOD || fn == Fn::POW) return true;
+  }
+  for (const auto& a : e->args)
+    if (expr_may_raise(a.get())) return true;
+  return false;
+}
+
+// A comparison of two uint64-valued expressions whose value ranges (column statistics) decide it: 1 / 0, else -1.
+static int fold_compare(Fn fn, const Expr* x, const Expr* y, const CodegenEnv& env) {
+  if (env.col_max.empty() || expr_may_raise(x) || expr_may_raise(y)) return -1;
+  const Range a = expr_range(x, env), b = expr_range(y, env);
+  switch (fn) {
+    case Fn::GT: return a.lo > b.hi ? 1 : a.hi <= b.lo ? 0 : -1;
+    case Fn::GTE: return a.lo >= b.hi ? 1 : a.hi < b.lo ? 0 : -1;
+    case Fn::LT: return a.hi < b.lo ? 1 : a.lo >= b.hi ? 0 : -1;
+    case Fn::LTE: return a.hi <= b.lo ? 1 : a.lo > b.hi ? 0 : -1;
+    case Fn::EQ: return (a.hi < b.lo || a.lo > b.hi) ? 0 : (a.lo == a.hi && b.lo == b.hi && a.lo == b.lo) ? 1 : -1;
+    case Fn::NEQ: return (a.hi < b.lo || a.lo > b.hi) ? 1 : (a.lo == a.hi && b.lo == b.hi && a.lo == b.lo) ? 0 : -1;
+    default: return -1;
+  }
+}
 
 // Sub-expressions whose value provably fits 32 bits are re-typed through u32: same value, but the compiler can then use
 // 32-bit compares and 32x32->64 / 64x32 multiplies instead of full 64-bit arithmetic.
@@ -350,6 +376,11 @@ static Code gen_expr_impl(const Expr* e, const CodegenEnv& env) {
   std::vector<Code> a;
   for (const auto& x : e->args) a.push_back(gen_expr(x.get(), env));
   const int T = fi.args.empty() ? EVQ_NIL : fi.args[0];
+  if ((T == EVQ_UINT64 || T == EVQ_TIMESTAMP64) && e->args.size() == 2) {
+    // range checks the statistics of the scanned columns already answer (e.g. `price > 0` over a column whose minimum is 90000)
+    const int folded = fold_compare(fi.fn, e->args[0].get(), e->args[1].get(), env);
+    if (folded >= 0) return {folded ? "1u" : "0u", "0u"};
+  }
   auto bin = [&](const char* op) { return "((" + a[0].value + ") " + op + " (" + a[1].value + "))"; };
   std::string v;
   switch (fi.fn) {

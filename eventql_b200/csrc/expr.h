@@ -64,6 +64,8 @@ struct CodegenEnv {
   std::string err = "err";   // name of the u32 error accumulator in scope
   // upper bound of the values of input column i (column statistics); empty = unknown
   std::vector<uint64_t> col_max;
+  // lower bound of the values of input column i; empty = 0
+  std::vector<uint64_t> col_min;
 };
 
 struct Code {
@@ -74,6 +76,7 @@ struct Code {
 Code gen_expr(const Expr* e, const CodegenEnv& env);
 uint32_t expr_value_bits(const Expr* e, const CodegenEnv& env);   // bit length bound of a uint64-valued expression (64 = unknown)
 uint64_t expr_value_max(const Expr* e, const CodegenEnv& env);
+bool expr_may_raise(const Expr* e);   // integer division / modulo / pow somewhere in the tree
 // the value as raw 64-bit pattern (u64), e.g. for key tuples and aggregate state words
 std::string as_bits(const Code& c, int type);
 const char* ctype_of(int type);

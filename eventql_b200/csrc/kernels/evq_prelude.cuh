@@ -437,6 +437,13 @@ __device__ __forceinline__ u64* evq_ht_upsert(const EvqHashTable& H, const u64* 
   return evq_ht_upsert_from<NK>(H, key, fpv, slot, w0, w1, claimed_counter);
 }
 
+// unsigned bytes of a times SIGNED bytes of b (a 0xff mask byte counts as -1), added to c
+__device__ __forceinline__ u32 evq_dp4a_us(u32 a, u32 b, u32 c) {
+  u32 d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
 // ---- aggregate state updates ------------------------------------------------------------------------------------------
 // state identities: sum/count 0; min = all ones (u64) / INT64_MAX / +inf; max = 0 / INT64_MIN / -inf; "seen" counters 0
 

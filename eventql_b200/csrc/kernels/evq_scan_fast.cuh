@@ -434,6 +434,14 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
       T.rows = rem < EVQ_TILE_ROWS ? (u32) rem : EVQ_TILE_ROWS;
     }
 
+#ifdef EVQ_DRYRUN   // measurement aid (EVQGPU_DRYRUN=1): the copy pipeline alone, the consumers release every tile untouched
+    __syncwarp();
+    if (evq_lane() == 0) evq_mbar_arrive(&hdr->empty[s]);
+    continue;
+#endif
+    // rows of this thread inside the tile: all EVQ_RPT except in the table's last tile (one compare against a constant per row)
+    const u32 nvalid = T.rows >= EVQ_RPT * (tid + 1u) ? (u32) EVQ_RPT : (T.rows > EVQ_RPT * tid ? T.rows - EVQ_RPT * tid : 0u);
+
     EvqFastPrep prep;
     evq_fast_prep(T, P, scr, prep);
     EvqCols cols;
@@ -448,7 +456,7 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
     for (int k = 0; k < EVQ_RPT; ++k) {
       EvqRow row;
       evq_fast_row(cols, k, row);
-      pass_k[k] = (EVQ_RPT * tid + k < T.rows) && evq_where(row, err);
+      pass_k[k] = ((u32) k < nvalid) && evq_where(row, err);
       mine += pass_k[k] ? 1u : 0u;
     }
     u32 incl = mine;
@@ -501,7 +509,7 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
         const int k = 4 * j + kk;
         EvqRow row;
         evq_fast_row(cols, k, row);
-        pass[kk] = (EVQ_RPT * tid + k < T.rows) && evq_where(row, err);
+        pass[kk] = ((u32) k < nvalid) && evq_where(row, err);
         fpv[kk] = slot[kk] = w0[kk] = w1[kk] = 0;
         if (pass[kk]) {
           u32 ktag[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
@@ -526,21 +534,31 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
       }
     }
 #elif EVQ_TIER == 1 && EVQ_G1 > 1 && EVQ_NNARROW > 0
-    // dense tier with byte-wide aggregates: rows are handled in quads; the quad's selector (one nibble per row: dense slot,
-    // or 4 = did not pass) drives the dp4a accumulators, the remaining (wide) words take the shared-memory path per row
+    // dense tier with byte-plane sums: rows are handled in quads; the quad's selector (one nibble per row: dense slot, or
+    // >= 4 = did not pass) drives the dp4a accumulators, the remaining words (if any) take the shared-memory path per row
 #pragma unroll
     for (int j = 0; j < EVQ_RPT / 4; ++j) {
+#ifdef EVQ_SWAR_SLOTS
+      u32 selector = evq_quad_slots(cols, j);   // slots of the 4 rows from the packed key bytes
+#else
       u32 selector = 0x4444u;
+#endif
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         const int k = 4 * j + kk;
         EvqRow row;
         evq_fast_row(cols, k, row);
 #ifdef EVQ_WHERE_PURE
-        const bool pass = evq_where(row, err) & (EVQ_RPT * tid + k < T.rows);
+        const bool pass = evq_where(row, err) & ((u32) k < nvalid);
 #else
-        const bool pass = (EVQ_RPT * tid + k < T.rows) && evq_where(row, err);
+        const bool pass = ((u32) k < nvalid) && evq_where(row, err);
 #endif
+#if defined(EVQ_SWAR_SLOTS) && EVQ_NSTATE_SMEM == 0
+        selector |= pass ? 0u : (4u << (4 * kk));   // nothing else to do per row: no branch
+#elif defined(EVQ_SWAR_SLOTS)
+        if (pass) evq_accumulate_smem(row, sacc, (selector >> (4 * kk)) & 3u, tid, P.dense_state, err);
+        else selector |= 4u << (4 * kk);
+#else
         if (pass) {   // (rows passed are counted from the rows accumulators at the end)
           u64 key[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
           u32 ktag[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
@@ -552,9 +570,12 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
           if (g != ~0u) {
 #endif
             selector ^= (g ^ 4u) << (4 * kk);
+#if EVQ_NSTATE_SMEM > 0
             evq_accumulate_smem(row, sacc, g, tid, P.dense_state, err);
+#endif
           }
         }
+#endif
       }
       evq_accumulate_narrow(cols, j, selector, nacc);
     }
@@ -563,7 +584,7 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
     for (int k = 0; k < EVQ_RPT; ++k) {
       EvqRow row;
       evq_fast_row(cols, k, row);
-      const bool pass = (EVQ_RPT * tid + k < T.rows) && evq_where(row, err);
+      const bool pass = ((u32) k < nvalid) && evq_where(row, err);
 #if EVQ_TIER == 1
       if (pass) {
         ++passed;
@@ -603,8 +624,7 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
 #if EVQ_G1 > 1
   for (u32 g = 0; g < EVQ_G1; ++g) evq_state_flush_smem(sacc, g, tid, P.dense_state);
 #if EVQ_NNARROW > 0
-#pragma unroll
-  for (int g = 0; g < EVQ_G1; ++g) passed += nacc[g];   // narrow accumulator 0 is the rows counter
+  passed += evq_narrow_rows(nacc);   // plane 0 is the rows counter
   evq_narrow_flush(nacc, P.dense_state);
 #endif
 #else

@@ -49,6 +49,19 @@ static Binding bind_table(const evqgpu_query& q, evqgpu_table* t) {
   return b;
 }
 
+// The kernels are specialised on the value range of the columns (narrow arithmetic, comparisons that the range decides,
+// range checks that cannot fail).  Small bounds are kept exact; large ones are coarsened to powers of two so that tables
+// whose extremes differ a little share one kernel.
+static uint64_t stat_ceil(uint64_t vmax) {
+  if (vmax < 256) return vmax;
+  const int b = 64 - __builtin_clzll(vmax);
+  return b >= 64 ? ~0ull : (1ull << b) - 1;
+}
+static uint64_t stat_floor(uint64_t vmin) {
+  if (vmin < 256) return vmin;
+  return 1ull << (63 - __builtin_clzll(vmin));
+}
+
 static KernelShape shape_for(const evqgpu_query& q, evqgpu_table* t, const Binding& b) {
   KernelShape s;
   s.cols.resize(q.input_columns.size());
@@ -63,7 +76,8 @@ static KernelShape shape_for(const evqgpu_query& q, evqgpu_table* t, const Bindi
     cs.nullable = c.meta.dlevel_max > 0;
     cs.dmax = c.meta.dlevel_max;
     cs.bits = c.value_bits;
-    cs.vmax = c.value_max;
+    cs.vmax = stat_ceil(c.value_max);
+    cs.vmin = stat_floor(c.value_min);
     cs.leb_len = c.leb_max_len;
     cs.data_stream = s.nstreams++;
     if (cs.nullable) {
@@ -83,6 +97,7 @@ static void widen_shape(KernelShape& s, const KernelShape& o) {
   for (size_t i = 0; i < s.cols.size(); ++i) {
     s.cols[i].bits = std::max(s.cols[i].bits, o.cols[i].bits);
     s.cols[i].vmax = std::max(s.cols[i].vmax, o.cols[i].vmax);
+    s.cols[i].vmin = std::min(s.cols[i].vmin, o.cols[i].vmin);
     s.cols[i].leb_len = std::max(s.cols[i].leb_len, o.cols[i].leb_len);
   }
 }
@@ -367,7 +382,9 @@ static void fit_shape(evqgpu_query& q, KernelShape& s, std::vector<TablePlan>& p
       // as many CTAs per SM as shared memory allows (latency hiding for the decode phases), within the register budget
       // the launch bounds leave per thread: 2 x 288 threads or 4 x 160 threads
       const int by_smem = (int) ((227 * 1024) / (worst + 1024));
-      const int cap = s.ncons <= 128 ? 6 : 2;
+      // (the byte-plane accumulators of the dense tier are registers: fewer CTAs, more registers per thread)
+      const int nacc = q.nnarrow * s.g1;
+      const int cap = s.ncons <= 128 ? (nacc > 36 ? 4 : nacc > 16 ? 5 : 6) : 2;
       s.min_ctas = std::max(1, std::min(by_smem, cap));
       if (const char* e = getenv("EVQGPU_MAX_CTAS")) s.min_ctas = std::max(1, std::min(s.min_ctas, atoi(e)));
       return;
@@ -635,8 +652,8 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
              (int) s.use_subidx, q.nnarrow);
     sig += buf;
     for (const auto& c : s.cols) {
-      snprintf(buf, sizeof(buf), "%d.%u.%u.%d.%u.%u.%u.%d.%d.%d.%llu;", (int) c.used, c.sql_type, c.kind, (int) c.nullable, c.dmax, c.bits,
-               c.leb_len, c.gen_slot, c.sub_stream, c.data_stream, (unsigned long long) c.vmax);
+      snprintf(buf, sizeof(buf), "%d.%u.%u.%d.%u.%u.%u.%d.%d.%d.%llu.%llu;", (int) c.used, c.sql_type, c.kind, (int) c.nullable, c.dmax, c.bits,
+               c.leb_len, c.gen_slot, c.sub_stream, c.data_stream, (unsigned long long) c.vmax, (unsigned long long) c.vmin);
       sig += buf;
     }
     for (size_t i = 0; i < nk; ++i) {
@@ -646,6 +663,7 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
     }
     for (size_t i = 0; i < q.state_keys.size(); ++i) sig += q.state_keys[i] + "#" + std::to_string(q.state_narrow[i]) + ";";
     for (int c : q.narrow_col) sig += "p" + std::to_string(c);
+    sig += q.plane_sig;
     if (!q.module || sig != q.module_sig) {
       q.kernel_source = generate_source(q, s);
       q.module = jit_compile(ctx, q.kernel_source, {"evq_scan", "evq_init", "evq_emit"}, &ms);

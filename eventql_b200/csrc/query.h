@@ -33,7 +33,8 @@ struct ColSig {
   int data_stream = -1, level_stream = -1;
   int leb_slot = -1, null_slot = -1;
   uint32_t bits = 64;      // every value < 2^bits (max over the scanned tables)
-  uint64_t vmax = ~0ull;   // every value <= vmax (max over the scanned tables)
+  uint64_t vmax = ~0ull;   // every value <= vmax (max over the scanned tables; coarsened, see stat_ceil)
+  uint64_t vmin = 0;       // every value >= vmin (min over the scanned tables; coarsened, see stat_floor)
   uint32_t leb_len = 10;   // LEB128: longest value in bytes (max over the scanned tables)
   int gen_slot = -1;       // fast kernel: index among the LEB128 columns that may need the boundary search (leb_len >= 2)
   bool packed = false;     // fast kernel: keep the column's raw bytes (4 rows per word) for the dp4a aggregates
@@ -96,9 +97,28 @@ struct evqgpu_query {
   int nstate_smem = 0;
   // byte-wide aggregates of the fast dense kernel (rows counter, sums of 1-byte columns): accumulated with dp4a into
   // thread-private u32 registers instead of shared memory (codegen.cc: layout_narrow)
-  std::vector<int> state_narrow;    // index among the narrow accumulators, -1 otherwise
-  std::vector<int> narrow_col;      // per narrow accumulator: input column whose bytes are summed, -1 = rows counter
-  int nnarrow = 0;
+  std::vector<int> state_narrow;    // index into plane_sums, -1 otherwise
+  std::vector<int> narrow_col;      // input columns whose raw bytes (4 rows per word) the kernel keeps next to the values
+  int nnarrow = 0;                  // byte planes over all plane sums: EVQ_NNARROW * EVQ_G1 u32 accumulators per thread
+  // Byte-plane sums (codegen.cc: layout_narrow): sum(W * B) per group with W < 2^32 split into byte planes and B <= 255
+  // (or absent), accumulated 4 rows at a time with dp4a: sum = SUM_p 256^p * dp4a(plane_p(W), B & mask_of_group)
+  struct PlaneOperand {
+    const evq::Expr* expr = nullptr;   // null: the constant 1 (rows counter)
+    int packed_col = -1;               // >= 0: bare 1-byte LEB128 column (its raw bytes are the one plane / the byte operand)
+    int nplanes = 1;
+    int swar = 0;                      // byte operand lit - col (1), lit + col (2) on the packed bytes of packed_col
+    uint64_t swar_lit = 0;
+  };
+  struct PlaneSum {
+    int word = 0;                      // state word
+    int w = -1, b = -1;                // indexes into plane_w / plane_b (-1: constant 1)
+    int nplanes = 1;
+    int plane0 = 0;                    // first plane: accumulators nacc[(plane0 + p) * G1 + g]
+  };
+  std::vector<PlaneOperand> plane_w, plane_b;
+  std::vector<PlaneSum> plane_sums;
+  bool swar_slots = false;             // dense slots of 4 rows computed on the packed key bytes
+  std::string plane_sig;               // text form of the above for the kernel signature
   std::string merge_checked_layout;  // state layout all ranks were last verified to share
   uint64_t expected_groups = 0;
   std::vector<bool> col_used;

@@ -139,24 +139,86 @@ __global__ void k_leb_chunk_counts(const uint4* __restrict__ data, u64 nbytes, u
   }
 }
 
-// column statistic of PLAIN64 streams: the largest value
-__global__ void k_max_reduce64(const u64* __restrict__ v, u64 n, unsigned long long* __restrict__ out) {
-  u64 acc = 0;
-  for (u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64) gridDim.x * blockDim.x) acc = max(acc, v[i]);
-  for (int o = 16; o > 0; o >>= 1) acc = max(acc, __shfl_xor_sync(0xffffffffu, acc, o));
-  if ((threadIdx.x & 31) == 0 && acc) atomicMax(out, acc);
+// ---- column statistics: exact minimum and maximum of the values (zone-map style; the scan kernels are specialised on them)
+// out[0] = max, out[1] = ~min (both start at 0, both merged with atomicMax)
+
+// PLAIN64 / PLAIN32 streams
+template <typename T>
+__global__ void k_minmax_plain(const T* __restrict__ v, u64 n, unsigned long long* __restrict__ out) {
+  u64 mx = 0, mn = ~0ull;
+  for (u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64) gridDim.x * blockDim.x) {
+    const u64 x = (u64) v[i];
+    mx = max(mx, x);
+    mn = min(mn, x);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(out, mx);
+    atomicMax(out + 1, ~mn);
+  }
 }
 
-// column statistic of LEB128 streams whose values are all one byte long: the largest byte
-__global__ void k_max_reduce8(const uint4* __restrict__ v, u64 n16, unsigned int* __restrict__ out) {
-  u32 acc = 0;
+// LEB128 streams whose values are all one byte long: value i is byte i, n = number of values
+__global__ void k_minmax_bytes(const uint4* __restrict__ v, u64 n, unsigned long long* __restrict__ out) {
+  u32 mx = 0, mn = 0xffffffffu;
+  const u64 n16 = n >> 4;
   for (u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (u64) gridDim.x * blockDim.x) {
     const uint4 q = v[i];
-    acc = __vmaxu4(acc, __vmaxu4(__vmaxu4(q.x, q.y), __vmaxu4(q.z, q.w)));
+    mx = __vmaxu4(mx, __vmaxu4(__vmaxu4(q.x, q.y), __vmaxu4(q.z, q.w)));
+    mn = __vminu4(mn, __vminu4(__vminu4(q.x, q.y), __vminu4(q.z, q.w)));
   }
-  acc = max(max(acc & 0xffu, (acc >> 8) & 0xffu), max((acc >> 16) & 0xffu, acc >> 24));
-  for (int o = 16; o > 0; o >>= 1) acc = max(acc, __shfl_xor_sync(0xffffffffu, acc, o));
-  if ((threadIdx.x & 31) == 0 && acc) atomicMax(out, acc);
+  mx = max(max(mx & 0xffu, (mx >> 8) & 0xffu), max((mx >> 16) & 0xffu, mx >> 24));
+  mn = min(min(mn & 0xffu, (mn >> 8) & 0xffu), min((mn >> 16) & 0xffu, mn >> 24));
+  if (blockIdx.x == 0 && threadIdx.x == 0) {   // the last, partial 16 bytes
+    const u8* b = (const u8*) v;
+    for (u64 i = n16 << 4; i < n; ++i) {
+      mx = max(mx, (u32) b[i]);
+      mn = min(mn, (u32) b[i]);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(out, (unsigned long long) mx);
+    atomicMax(out + 1, ~(unsigned long long) mn);
+  }
+}
+
+// variable-length LEB128 streams with a sub-index: one thread decodes the 8 values behind one sub-index entry
+__global__ void k_minmax_leb(const u8* __restrict__ data, const u64* __restrict__ off_index, const u16* __restrict__ sub,
+                             u32 num_tiles, u64 num_rows, unsigned long long* __restrict__ out) {
+  const u64 idx = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  const u64 tile = idx / (EVQ_TILE_ROWS / 8);
+  const u32 g = (u32) (idx % (EVQ_TILE_ROWS / 8));
+  u64 mx = 0, mn = ~0ull;
+  const u64 first = tile * EVQ_TILE_ROWS + 8ull * g;
+  if (tile < num_tiles && first < num_rows) {
+    const u32 nv = (u32) min((u64) 8, num_rows - first);
+    const u8* p = data + off_index[tile] + sub[idx];
+    for (u32 i = 0; i < nv; ++i) {
+      u64 x = 0;
+      for (u32 sh = 0; sh < 70; sh += 7) {
+        const u8 b = *p++;
+        x |= (u64) (b & 0x7fu) << sh;          // (the 10th byte contributes its low bit only: shifts >= 64 - 7 drop the rest)
+        if (!(b & 0x80u)) break;
+      }
+      mx = max(mx, x);
+      mn = min(mn, x);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  }
+  if ((threadIdx.x & 31) == 0 && mn <= mx) {
+    atomicMax(out, mx);
+    atomicMax(out + 1, ~mn);
+  }
 }
 
 // off_index[t] = byte offset at which value number boundary(t) starts, boundary(t) = val_index[t] or t*TILE
@@ -319,6 +381,19 @@ void table_finish_column(evqgpu_table* t, Column& c) {
 
   DevBuf maxspan;
   maxspan.alloc(sizeof(unsigned int));
+  c.value_min = 0;
+  // exact value range of the column (k_minmax_*): {max, ~min} on the device, read back once the pass has run
+  DevBuf minmax;
+  minmax.alloc(16);
+  auto read_minmax = [&](bool have_values) {
+    u64 mm[2] = {0, 0};
+    EVQ_CUDA(cudaMemcpyAsync(mm, minmax.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (!have_values) return;
+    c.value_max = mm[0];
+    c.value_min = ~mm[1] <= mm[0] ? ~mm[1] : 0;
+    c.value_bits = mm[0] ? 64 - (uint32_t) __builtin_clzll(mm[0]) : 1;
+  };
 
   // ---- optional column: present values per tile -> val_index
   const bool nullable = c.meta.dlevel_max > 0;
@@ -377,18 +452,13 @@ void table_finish_column(evqgpu_table* t, Column& c) {
       c.data_bits = w * 8;
       c.value_bits = w * 8;
       c.value_max = w == 8 ? ~0ull : 0xffffffffull;
-      if (w == 8 && nv && c.sql_type != EVQ_FLOAT64) {
-        DevBuf acc;
-        acc.alloc(8);
-        EVQ_CUDA(cudaMemsetAsync(acc.p, 0, 8, ctx->stream));
-        k_max_reduce64<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(c.data.buf.as<u64>(), nv, acc.as<unsigned long long>());
+      if (nv && c.sql_type != EVQ_FLOAT64) {
+        EVQ_CUDA(cudaMemsetAsync(minmax.p, 0, 16, ctx->stream));
+        if (w == 8) k_minmax_plain<u64><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(c.data.buf.as<u64>(), nv, minmax.as<unsigned long long>());
+        else k_minmax_plain<u32><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(c.data.buf.as<u32>(), nv, minmax.as<unsigned long long>());
         EVQ_CUDA(cudaGetLastError());
         ctx->kernel_launches++;
-        u64 ored = 0;
-        EVQ_CUDA(cudaMemcpyAsync(&ored, acc.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
-        c.value_bits = ored ? 64 - (uint32_t) __builtin_clzll(ored) : 1;
-        c.value_max = ored;
+        read_minmax(true);
       }
       if (nullable) c.data_tile_cap = span_from_index(c.val_index.as<u64>(), w, 0, 0);
       else c.data_tile_cap = EVQ_TILE_ROWS * w + 32;
@@ -430,16 +500,13 @@ void table_finish_column(evqgpu_table* t, Column& c) {
         while (c.leb_max_len < 10 && (runs >> (c.leb_max_len - 1)) & 1u) ++c.leb_max_len;
         c.value_bits = std::min<uint32_t>(64, 7 * c.leb_max_len);
         c.value_max = c.value_bits >= 64 ? ~0ull : (1ull << c.value_bits) - 1;
-        if (c.leb_max_len == 1 && c.data.nbytes) {
-          // all values are single bytes (zero padded stream): the exact maximum is one more cheap pass
-          EVQ_CUDA(cudaMemsetAsync(maxspan.p, 0, sizeof(unsigned int), ctx->stream));
-          k_max_reduce8<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(c.data.buf.as<uint4>(), (c.data.nbytes + 15) / 16, maxspan.as<unsigned int>());
+        if (c.leb_max_len == 1 && nv && c.data.nbytes >= nv) {
+          // all values are single bytes: value i is byte i, the exact range is one more cheap pass
+          EVQ_CUDA(cudaMemsetAsync(minmax.p, 0, 16, ctx->stream));
+          k_minmax_bytes<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(c.data.buf.as<uint4>(), nv, minmax.as<unsigned long long>());
           EVQ_CUDA(cudaGetLastError());
           ctx->kernel_launches++;
-          unsigned int mx = 0;
-          EVQ_CUDA(cudaMemcpyAsync(&mx, maxspan.p, sizeof(mx), cudaMemcpyDeviceToHost, ctx->stream));
-          EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
-          c.value_max = mx;
+          read_minmax(true);
         }
       }
       exclusive_scan_u64(ctx, counts.as<u64>(), base.as<u64>(), nchunks + 1);
@@ -469,10 +536,20 @@ void table_finish_column(evqgpu_table* t, Column& c) {
             c.data.buf.as<u8>(), c.off_index.as<u64>(), ntiles, c.sub_index.as<u16>());
         EVQ_CUDA(cudaGetLastError());
         ctx->kernel_launches++;
+        // ... which also make the exact value range one cheap pass (8 values per thread)
+        EVQ_CUDA(cudaMemsetAsync(minmax.p, 0, 16, ctx->stream));
+        const uint64_t groups = (uint64_t) ntiles * (EVQ_TILE_ROWS / 8);
+        k_minmax_leb<<<(unsigned) ((groups + 255) / 256), 256, 0, ctx->stream>>>(
+            c.data.buf.as<u8>(), c.off_index.as<u64>(), c.sub_index.as<u16>(), ntiles, t->num_rows, minmax.as<unsigned long long>());
+        EVQ_CUDA(cudaGetLastError());
+        ctx->kernel_launches++;
+        read_minmax(nv > 0);
       }
       break;
     }
   }
+  // NULLs read as value 0 wherever the tag is ignored
+  if (nullable && c.num_values < t->num_rows) c.value_min = 0;
   c.loaded = true;
 }
 
@@ -593,6 +670,8 @@ int evqgpu_table_column_info(const evqgpu_table* tbl, uint32_t idx, evqgpu_colum
     out->num_values = c.num_values;
     out->value_bits = c.value_bits;
     out->leb_max_len = c.leb_max_len;
+    out->value_min = c.value_min;
+    out->value_max = c.value_max;
   });
 }
 

@@ -42,7 +42,8 @@ struct Column {
   uint32_t level_bits = 0;
   uint32_t value_bits = 64;    // statistic: every value of the column is < 2^value_bits (computed when the column is loaded)
   uint32_t leb_max_len = 10;   // LEB128: the longest value in bytes
-  uint64_t value_max = ~0ull;  // statistic: upper bound of every value (exact for 1-byte LEB128 and PLAIN64 columns)
+  uint64_t value_max = ~0ull;  // statistic: largest value (exact for plain columns, 1-byte LEB128 and sub-indexed LEB128 columns; a bound otherwise)
+  uint64_t value_min = 0;      // statistic: smallest value (exact for the same columns, 0 otherwise; 0 when NULLs are present)
   uint32_t data_tile_cap = 0;  // max bytes one tile copy of the data stream can need (multiple of 16)
   uint32_t level_tile_cap = 0;
 };

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define EVQGPU_ABI_VERSION 1
+#define EVQGPU_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define EVQGPU_API __attribute__((visibility("default")))
@@ -153,6 +153,9 @@ typedef struct evqgpu_column_info {
   uint64_t num_values;      /* non-NULL values (known once loaded) */
   uint32_t value_bits;      /* statistic: every value < 2^value_bits (known once loaded) */
   uint32_t leb_max_len;     /* statistic: longest LEB128 value in bytes (known once loaded) */
+  uint64_t value_min;       /* statistic: value range of the non-NULL values (exact where the loader can decode the
+                               column in one pass, else [0, 2^value_bits - 1]); value_min is 0 when NULLs are present */
+  uint64_t value_max;
 } evqgpu_column_info;
 
 /* Parse header + page index of a cstable file image (v0.1.0 and v0.2.0).  Host only: nothing
@@ -344,6 +347,9 @@ typedef struct evqgpu_debug_column {
   uint32_t dlevel_max; /* 0 = required */
   uint32_t value_bits;   /* column statistic: every value < 2^value_bits; 0 = unknown (64) */
   uint32_t leb_max_len;  /* column statistic: longest LEB128 value in bytes; 0 = unknown (10) */
+  uint32_t reserved;
+  uint64_t value_min;    /* column statistics: value range; value_max 0 = unknown (2^value_bits - 1) */
+  uint64_t value_max;
 } evqgpu_debug_column;
 
 /* tier: 1 = dense / single group (dense_slots groups), 2 = global hash table; ignored for scan-only plans.

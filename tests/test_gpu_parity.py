@@ -108,20 +108,66 @@ def test_decode_and_aggregate_ragged_sizes(gpu_ctx, nrows, null_every, tmp_path)
     tbl.close()
 
 
-def test_column_statistics(gpu_ctx):
-    """value_bits / leb_max_len (computed when a column is loaded) bound every value: the fast kernel's static types"""
-    spec = T.lineitem_spec() + [dict(name="wide", logical_type=P.COL_UNSIGNED_INT, encoding=P.ENC_UINT64_PLAIN, seed=77, lo=0, span=1 << 40),
+@pytest.mark.parametrize("nrows", [300_000, 12_345, 7])
+def test_column_statistics(gpu_ctx, nrows):
+    """value_bits / leb_max_len / value_min / value_max (computed when a column is loaded): the fast kernel's static types,
+    the comparisons it may fold and the range checks it may drop all rest on them, so they are checked value for value"""
+    spec = T.lineitem_spec() + [dict(name="wide", logical_type=P.COL_UNSIGNED_INT, encoding=P.ENC_UINT64_PLAIN, seed=77, lo=5, span=1 << 40),
+                                dict(name="narrow", logical_type=P.COL_UNSIGNED_INT, encoding=P.ENC_UINT32_PLAIN, seed=78, lo=1000, span=70000),
                                 dict(name="big", logical_type=P.COL_UNSIGNED_INT, encoding=P.ENC_UINT64_LEB128, seed=9, lo=0,
-                                     span=(1 << 64) - 1, transform=1)]
-    tbl = gpu_ctx.synthesize(300_000, spec)
+                                     span=(1 << 64) - 1, transform=1),
+                                dict(name="opt", logical_type=P.COL_UNSIGNED_INT, encoding=P.ENC_UINT64_LEB128, seed=10, lo=3, span=100,
+                                     null_every=5)]
+    tbl = gpu_ctx.synthesize(nrows, spec)
     info = {c["name"]: c for c in tbl.columns()}
     assert info["flag"]["leb_max_len"] == 1 and info["quantity"]["leb_max_len"] == 1 and info["shipdate"]["leb_max_len"] == 2
-    assert info["price"]["leb_max_len"] == 4 and info["price"]["value_bits"] == 28
-    assert info["wide"]["value_bits"] == 40
-    assert info["big"]["leb_max_len"] == 10 and info["big"]["value_bits"] == 64
+    if nrows > 1000:
+        assert info["price"]["leb_max_len"] == 4 and info["price"]["value_bits"] == 24
+        assert info["wide"]["value_bits"] == 40
+        assert info["big"]["leb_max_len"] == 10 and info["big"]["value_bits"] == 64
     for s in spec:
-        v, _ = T.synth_values(s, 300_000)
-        assert int(v.max()) < (1 << info[s["name"]]["value_bits"]) or info[s["name"]]["value_bits"] == 64
+        v, nulls = T.synth_values(s, nrows)
+        i = info[s["name"]]
+        assert int(v.max()) < (1 << i["value_bits"]) or i["value_bits"] == 64
+        if s["name"] == "opt":      # NULLs read as 0 (SURVEY H7): the minimum must cover them
+            assert i["value_min"] == 0 and i["value_max"] >= int(v.max())
+        else:
+            assert (i["value_min"], i["value_max"]) == (int(v.min()), int(v.max())), s["name"]
+    tbl.close()
+
+
+def test_predicates_decided_by_statistics(gpu_ctx, tmp_path):
+    """Comparisons that the value range of a column decides are folded at kernel-generation time; the result must not change"""
+    spec = T.lineitem_spec()
+    n = 50_000
+    tbl = gpu_ctx.synthesize(n, spec)
+    f = str(tmp_path / "t.cst")
+    tbl.write_file(f)
+    ref = O.read_cstable(f)
+    c, names = T.cols_of(spec)
+
+    def q(where):
+        return P.QueryPlan(names, [c["flag"], P.call("count", P.lit(1)), P.call("sum", c["price"]), P.call("max", c["quantity"])],
+                           where=where, group=[c["flag"]])
+
+    wheres = [
+        c["price"] > 89999,                                   # always true (the minimum is >= 90000)
+        c["price"] > 90000,                                   # not decided by the (coarsened) range
+        c["price"] < 65536,                                   # always false -> no groups
+        (c["quantity"] >= 1) & (c["quantity"] <= 50),         # both true
+        (c["quantity"] > 50) | c["discount"].eq(11),          # both false
+        c["tax"].neq(9),                                      # always true
+        (P.lit(100) - c["discount"]) >= 90,                   # range arithmetic: always true
+        (c["price"] * c["quantity"]) > (1 << 40),             # always false
+        c["shipdate"] <= 10471,                               # undecided
+        (c["price"] / (c["quantity"] - c["quantity"])) >= 0,  # "always true" but raises: must not be folded away
+    ]
+    for w in wheres[:-1]:
+        plan = q(w)
+        got, _ = run_gpu(gpu_ctx, [tbl], plan)
+        compare(got, O.run_query([ref], plan).rows(), False)
+    with pytest.raises(capi.EvqError):
+        run_gpu(gpu_ctx, [tbl], q(wheres[-1]))
     tbl.close()
 
 
