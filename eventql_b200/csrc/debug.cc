@@ -75,7 +75,8 @@ extern "C" int evqgpu_debug_generate(const evqgpu_query_desc* desc, const evqgpu
       layout_states(q, s);
       layout_narrow(q, s);
       s.ncons = s.fast ? 128 : 256;   // what fit_shape picks first
-      s.nstages = 3;
+      s.nstages = s.fast ? 2 : 3;
+      s.kt = s.fast ? 2 : 1;
       s.min_ctas = s.fast ? 4 : 2;
       std::string src = generate_source(q, s);
       if (compile) {

@@ -169,8 +169,8 @@ __device__ __forceinline__ u32 evq_fixed_mask(u32 len) { return len >= 4u ? 0x7f
 // L == 1: value i is byte i
 template <int S>
 __device__ __forceinline__ void evq_fast_ld_leb1(const EvqTile& T, const EvqScanParams& P, u32 (&v)[EVQ_RPT]) {
-  // every value is one byte: byte offset == row index, so a tile starts at a multiple of 1024 (delta == 0, word aligned)
-  const u32 off = P.streams[S].smem_off + evq_fast_first(T, S);
+  // every value is one byte: byte offset == row index, so a tile starts at a multiple of 1024 (delta is word aligned)
+  const u32 off = P.streams[S].smem_off + T.desc[S].delta + evq_fast_first(T, S);
   u32 x[EVQ_RPT / 4];
   if (EVQ_RPT == 8) evq_stage_v2(T, off, x[0], x[EVQ_RPT / 4 - 1]);
   else x[0] = evq_stage_word(T, off);
@@ -184,7 +184,7 @@ __device__ __forceinline__ void evq_fast_ld_leb1(const EvqTile& T, const EvqScan
 // same, also keeping the raw bytes (4 rows per word) for the dp4a aggregates
 template <int S>
 __device__ __forceinline__ void evq_fast_ld_leb1p(const EvqTile& T, const EvqScanParams& P, u32 (&v)[EVQ_RPT], u32 (&packed)[EVQ_RPT / 4]) {
-  const u32 off = P.streams[S].smem_off + evq_fast_first(T, S);
+  const u32 off = P.streams[S].smem_off + T.desc[S].delta + evq_fast_first(T, S);
   if (EVQ_RPT == 8) evq_stage_v2(T, off, packed[0], packed[EVQ_RPT / 4 - 1]);
   else packed[0] = evq_stage_word(T, off);
 #pragma unroll
@@ -347,7 +347,7 @@ __device__ __forceinline__ void evq_fast_ld_bitpack(const EvqTile& T, const EvqS
 struct EvqSmemHeader {
   u64 full[4];
   u64 empty[4];
-  EvqStreamDesc desc[4][EVQ_NSTREAMS > 0 ? EVQ_NSTREAMS : 1];
+  EvqStreamDesc desc[4][EVQ_KT][EVQ_NSTREAMS > 0 ? EVQ_NSTREAMS : 1];
 };
 
 #define EVQ_HDR_BYTES ((sizeof(EvqSmemHeader) + 127) & ~127)
@@ -375,27 +375,30 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
   }
   __syncthreads();
 
-  const u32 first_tile = blockIdx.x;
-  const u32 tile_step = gridDim.x;
+  // a CTA walks groups of EVQ_KT consecutive row tiles (one pipeline stage each)
+  const u32 first_group = blockIdx.x;
+  const u32 group_step = gridDim.x;
+  const u32 num_groups = (P.num_tiles + EVQ_KT - 1u) / EVQ_KT;
 
   if (tid >= EVQ_NCONS) {
-    // ===================== producer warp: one TMA bulk copy per column stream and tile =====================
-    // lane i owns stream i; its descriptor lives in registers, and the row-tile index of the next tile is read while
-    // the warp still waits for that tile's stage to be released
+    // ===================== producer warp: one TMA bulk copy per column stream and tile group =====================
+    // lane i owns stream i; its descriptor lives in registers, and the row-tile index of the next group is read while
+    // the warp still waits for that group's stage to be released
     const u32 lane = evq_lane();
     const bool active = lane < P.num_streams;
     EvqStream S;
     S.base = 0; S.off_index = 0; S.val_index = 0; S.nbytes = 0; S.kind = 0; S.bits = 0; S.smem_off = 0; S.smem_cap = 0;
     if (active) S = P.streams[lane];
-    EvqCopyPlan cp;
-    evq_producer_plan(P, S, active, first_tile, cp);
+    EvqCopyPlanK cp;
+    evq_producer_plan_k(P, S, active, first_group, num_groups, cp);
     u32 it = 0;
-    for (u32 tile = first_tile; tile < P.num_tiles; tile += tile_step, ++it) {
+    for (u32 group = first_group; group < num_groups; group += group_step, ++it) {
       const u32 s = it % EVQ_NSTAGES;
       const u32 round = it / EVQ_NSTAGES;
       if (round > 0) evq_mbar_wait(&hdr->empty[s], (round - 1) & 1u);
-      evq_producer_commit(S, active, cp, stages + (size_t) s * stage_bytes, hdr->desc[s], &hdr->full[s]);
-      evq_producer_plan(P, S, active, tile + tile_step, cp);
+      evq_producer_commit_k(S, active, cp, stages + (size_t) s * stage_bytes, &hdr->desc[s][0][0], EVQ_NSTREAMS > 0 ? EVQ_NSTREAMS : 1,
+                            &hdr->full[s]);
+      evq_producer_plan_k(P, S, active, group + group_step, num_groups, cp);
     }
     return;
   }
@@ -422,23 +425,23 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
 #endif
 
   u32 it = 0;
-  for (u32 tile = first_tile; tile < P.num_tiles; tile += tile_step, ++it) {
+  for (u32 group = first_group; group < num_groups; group += group_step, ++it) {
     const u32 s = it % EVQ_NSTAGES;
     evq_mbar_wait(&hdr->full[s], (it / EVQ_NSTAGES) & 1u);
     T.stage = stages + (size_t) s * stage_bytes;
     T.stage_sa = evq_smem_u32(T.stage);
-    T.desc = hdr->desc[s];
+#ifndef EVQ_DRYRUN   // (EVQGPU_DRYRUN=1, a measurement aid: the copy pipeline alone, the consumers release every stage untouched)
+#pragma unroll 1
+   for (u32 sub = 0; sub < EVQ_KT; ++sub) {
+    const u32 tile = group * EVQ_KT + sub;
+    if (tile >= P.num_tiles) break;
+    T.desc = hdr->desc[s][sub];
     T.row0 = (u64) tile * EVQ_TILE_ROWS;
     {
       const u64 rem = P.num_rows - T.row0;
       T.rows = rem < EVQ_TILE_ROWS ? (u32) rem : EVQ_TILE_ROWS;
     }
 
-#ifdef EVQ_DRYRUN   // measurement aid (EVQGPU_DRYRUN=1): the copy pipeline alone, the consumers release every tile untouched
-    __syncwarp();
-    if (evq_lane() == 0) evq_mbar_arrive(&hdr->empty[s]);
-    continue;
-#endif
     // rows of this thread inside the tile: all EVQ_RPT except in the table's last tile (one compare against a constant per row)
     const u32 nvalid = T.rows >= EVQ_RPT * (tid + 1u) ? (u32) EVQ_RPT : (T.rows > EVQ_RPT * tid ? T.rows - EVQ_RPT * tid : 0u);
 
@@ -615,6 +618,8 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
     }
 #endif
 
+   }
+#endif
     __syncwarp();
     if (evq_lane() == 0) evq_mbar_arrive(&hdr->empty[s]);
   }

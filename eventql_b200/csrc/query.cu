@@ -151,9 +151,10 @@ static StageLayout stage_layout(const evqgpu_query& q, evqgpu_table* t, const Bi
       L.smem_cap[stream] = cap;
       off += cap;
     };
-    place(cs.data_stream, c.data_tile_cap);
+    // (kt consecutive tiles are contiguous in a required column's stream: at most kt times the largest tile)
+    place(cs.data_stream, c.data_tile_cap * (uint32_t) s.kt);
     if (cs.nullable) place(cs.level_stream, c.level_tile_cap);
-    if (cs.sub_stream >= 0) place(cs.sub_stream, (EVQ_TILE_ROWS / 8) * 2);
+    if (cs.sub_stream >= 0) place(cs.sub_stream, (EVQ_TILE_ROWS / 8) * 2 * (uint32_t) s.kt);
   }
   L.stage_bytes = (uint32_t) round_up(off + 128, 128);
   (void) q;
@@ -172,7 +173,7 @@ static size_t scratch_bytes(const KernelShape& s) {
 }
 
 static size_t header_bytes(const KernelShape& s) {
-  const size_t raw = 8 * 4 + 8 * 4 + (s.fast ? 0 : 4 * 4) + 16 * 4 * std::max(1, s.nstreams);
+  const size_t raw = 8 * 4 + 8 * 4 + (s.fast ? 0 : 4 * 4) + 16 * 4 * (s.fast ? s.kt : 1) * std::max(1, s.nstreams);
   return round_up(raw, 128);
 }
 
@@ -359,7 +360,12 @@ static uint64_t algorithmic_bytes(const evqgpu_query& q, const std::vector<Table
 // choose thread count / stages so the CTA fits; returns dynamic smem bytes of the largest table
 static void fit_shape(evqgpu_query& q, KernelShape& s, std::vector<TablePlan>& plans) {
   const size_t limit = (size_t) q.ctx->smem_optin;
-  for (int attempt = 0; attempt < 4; ++attempt) {
+  // fast kernel: 2 row tiles per stage first (half as many, twice as large bulk copies), if that costs no resident CTA
+  int kt_first = s.fast ? 2 : 1;
+  if (const char* e = getenv("EVQGPU_KT")) kt_first = s.fast ? std::max(1, std::min(4, atoi(e))) : 1;
+  const int nattempts = kt_first > 1 ? 8 : 4;
+  for (int attempt = 0; attempt < nattempts; ++attempt) {
+    s.kt = (kt_first > 1 && attempt < 4) ? kt_first : 1;
     s.ncons = (attempt & 1) ? 128 : 256;
     s.nstages = (attempt & 2) ? 2 : 3;
     if (s.fast) {
@@ -385,6 +391,7 @@ static void fit_shape(evqgpu_query& q, KernelShape& s, std::vector<TablePlan>& p
       // (the byte-plane accumulators of the dense tier are registers: fewer CTAs, more registers per thread)
       const int nacc = q.nnarrow * s.g1;
       const int cap = s.ncons <= 128 ? (nacc > 36 ? 4 : nacc > 16 ? 5 : 6) : 2;
+      if (s.kt > 1 && by_smem < cap && !getenv("EVQGPU_KT")) { attempt |= 3; continue; }   // larger stages would cost residency: one tile per stage
       s.min_ctas = std::max(1, std::min(by_smem, cap));
       if (const char* e = getenv("EVQGPU_MAX_CTAS")) s.min_ctas = std::max(1, std::min(s.min_ctas, atoi(e)));
       return;
@@ -408,7 +415,11 @@ static void run_scan(evqgpu_query& q, const KernelShape& s, std::vector<TablePla
     tile_row_base += p.table->num_tiles;
     u32 stage_bytes = p.layout.stage_bytes;
     const int ctas_per_sm = std::max<int>(1, std::min<size_t>(s.min_ctas, (227 * 1024) / (p.smem + 1024)));
-    const unsigned grid = (unsigned) std::min<uint64_t>(p.table->num_tiles, (uint64_t) ctx->sm_count * ctas_per_sm);
+    const uint64_t groups = (p.table->num_tiles + s.kt - 1) / s.kt;
+    uint64_t grid64 = std::min<uint64_t>(groups, (uint64_t) ctx->sm_count * ctas_per_sm);
+    // the u32 byte-plane accumulators of a thread take at most 8 * 255 * 255 per row tile: bound the tiles per CTA
+    if (q.nnarrow > 0) grid64 = std::max<uint64_t>(grid64, (p.table->num_tiles + 7999) / 8000);
+    const unsigned grid = (unsigned) grid64;
     void* args[] = {&P, &stage_bytes};
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ctx->profiling) {
@@ -648,8 +659,8 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
   {
     std::string sig;
     char buf[160];
-    snprintf(buf, sizeof(buf), "t%d g%d n%d s%d c%d f%d x%d N%d|", s.tier, s.g1, s.ncons, s.nstages, s.min_ctas, (int) s.fast,
-             (int) s.use_subidx, q.nnarrow);
+    snprintf(buf, sizeof(buf), "t%d g%d n%d s%d c%d f%d x%d N%d K%d|", s.tier, s.g1, s.ncons, s.nstages, s.min_ctas, (int) s.fast,
+             (int) s.use_subidx, q.nnarrow, s.kt);
     sig += buf;
     for (const auto& c : s.cols) {
       snprintf(buf, sizeof(buf), "%d.%u.%u.%d.%u.%u.%u.%d.%d.%d.%llu.%llu;", (int) c.used, c.sql_type, c.kind, (int) c.nullable, c.dmax, c.bits,

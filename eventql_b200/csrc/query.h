@@ -53,6 +53,7 @@ struct KernelShape {
   int g1 = 1;          // dense slots (power of two >= groups) for tier 1
   int ncons = 256;     // consumer threads
   int nstages = 3;
+  int kt = 1;          // fast kernel: consecutive row tiles per pipeline stage (one bulk copy per stream and stage)
   int min_ctas = 1;
   int nstreams = 0, nleb = 0, nnull = 0;
   bool fast = false;   // all referenced columns are required: kernels/evq_scan_fast.cuh (4 consecutive rows per thread)
