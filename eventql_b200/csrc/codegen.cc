@@ -511,15 +511,19 @@ static void gen_fast_layout(std::ostringstream& os, const KernelShape& shape) {
         {
           // where this thread's 8 values start: from the column's sub-index (staged with the tile), or searched by evq_fast_prep
           std::string general, start;
-          if (c.sub_stream >= 0) {
+          if (c.leb_uniform) {   // every value has leb_len bytes: the fixed-stride paths only
+            general = "false";
+            start = "0u";
+          } else if (c.sub_stream >= 0) {
             general = "evq_fast_general<" + S + ", " + std::to_string(c.leb_len) + ">(T)";
             start = "evq_fast_substart<" + std::to_string(c.sub_stream) + ">(T, P)";
           } else {
             general = "prep.general[" + std::to_string(c.gen_slot) + "]";
             start = "prep.start[" + std::to_string(c.gen_slot) + "]";
           }
-          os << "    evq_fast_ld_leb" << (c.leb_len <= 4 ? "32" : "64") << "<" << S << ", 0, " << c.leb_len << ">(T, P, " << general << ", "
-             << start << ", raw);\n";
+          // second template argument: 2 = two sub-index entry points packed in `start`, 1 = one searched entry point
+          os << "    evq_fast_ld_leb" << (c.leb_len <= 4 ? "32" : "64") << "<" << S << ", " << (c.sub_stream >= 0 ? 2 : 1) << ", " << c.leb_len
+             << ">(T, P, " << general << ", " << start << ", raw);\n";
         }
         break;
     }

@@ -20,7 +20,9 @@ typedef double f64;
 #define EVQ_KIND_BITPACK 2
 #define EVQ_KIND_LEB128 3
 #define EVQ_KIND_LEVEL 4
-#define EVQ_KIND_SUBIDX 5   // per-tile table of decode entry points (u16 x 128), not column data
+#define EVQ_KIND_SUBIDX 5   // per-tile table of decode entry points (u16 per EVQ_SUB_GRAN values), not column data
+#define EVQ_SUB_GRAN 4     // the sub-index of a variable-length LEB128 column records the start of every 4th value
+#define EVQ_SUB_ENTRIES (EVQ_TILE_ROWS / EVQ_SUB_GRAN)
 
 #define EVQ_ERR_DIV_ZERO 1u
 #define EVQ_ERR_MOD_ZERO 2u

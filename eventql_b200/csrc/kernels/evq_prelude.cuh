@@ -170,8 +170,8 @@ __device__ __forceinline__ void evq_producer_plan(const EvqScanParams& P, const 
     start = blk0 * 16 * S.bits;
     end = blk1 * 16 * S.bits;
   } else if (S.kind == EVQ_KIND_SUBIDX) {
-    start = (u64) tile * (EVQ_TILE_ROWS / 8) * 2;
-    end = start + (EVQ_TILE_ROWS / 8) * 2;
+    start = (u64) tile * EVQ_SUB_ENTRIES * 2;
+    end = start + EVQ_SUB_ENTRIES * 2;
   } else {
     u64 v0 = row0, v1 = row0 + rows;
     if (S.val_index) {
@@ -243,7 +243,7 @@ __device__ __forceinline__ u64 evq_tile_start(const EvqScanParams& P, const EvqS
     case EVQ_KIND_PLAIN64: return row * 8;
     case EVQ_KIND_PLAIN32: return row * 4;
     case EVQ_KIND_BITPACK: return ((row + 127) >> 7) * 16 * S.bits;   // tiles start on 128-value blocks; the end rounds up
-    case EVQ_KIND_SUBIDX: return (u64) tile * (EVQ_TILE_ROWS / 8) * 2;
+    case EVQ_KIND_SUBIDX: return (u64) tile * EVQ_SUB_ENTRIES * 2;
     default: return S.off_index[tile];
   }
 }

@@ -50,17 +50,20 @@ __device__ __forceinline__ void evq_fast_prep_a(const EvqTile& T, const EvqScanP
   const EvqStreamDesc d = T.desc[S];
   general = d.nbytes != (u32) L * d.nvals;   // the same for every thread of the CTA
   if (!general) return;
-  const u8* region = T.stage + P.streams[S].smem_off;
-  const u32 tb = d.delta + d.nbytes;
+  // chunks are counted from the 16-byte block the tile's payload starts in (with several tiles per stage the payload of
+  // a tile starts anywhere inside the stream's region)
+  const u8* region = T.stage + P.streams[S].smem_off + (d.delta & ~15u);
+  const u32 dl = d.delta & 15u;
+  const u32 tb = dl + d.nbytes;
   const u32 nchunks = (tb + 15u) >> 4;
   const u32 per = (nchunks + EVQ_NCONS - 1) / EVQ_NCONS;
   const u32 c0 = T.ctid * per;
   const u32 c1 = c0 + per < nchunks ? c0 + per : nchunks;
   // the first two masks stay in registers (L <= 4: at most 2 chunks per thread with 128 consumers, 1 with 256)
-  const u32 m0 = c0 < c1 ? evq_leb_chunk_mask(region, c0, d.delta, tb) : 0u;
-  const u32 m1 = c0 + 1u < c1 ? evq_leb_chunk_mask(region, c0 + 1u, d.delta, tb) : 0u;
+  const u32 m0 = c0 < c1 ? evq_leb_chunk_mask(region, c0, dl, tb) : 0u;
+  const u32 m1 = c0 + 1u < c1 ? evq_leb_chunk_mask(region, c0 + 1u, dl, tb) : 0u;
   u32 count = __popc(m0) + __popc(m1);
-  for (u32 c = c0 + 2u; c < c1; ++c) count += __popc(evq_leb_chunk_mask(region, c, d.delta, tb));
+  for (u32 c = c0 + 2u; c < c1; ++c) count += __popc(evq_leb_chunk_mask(region, c, dl, tb));
   const u32 lane = evq_lane();
   u32 incl = count;
 #pragma unroll
@@ -75,7 +78,7 @@ __device__ __forceinline__ void evq_fast_prep_a(const EvqTile& T, const EvqScanP
   if (c0 + 1u < c1) scr->chunk[G][c0 + 1u] = (before << 16) | m1;
   before += __popc(m1);
   for (u32 c = c0 + 2u; c < c1; ++c) {
-    const u32 m = evq_leb_chunk_mask(region, c, d.delta, tb);
+    const u32 m = evq_leb_chunk_mask(region, c, dl, tb);
     scr->chunk[G][c] = (before << 16) | m;
     before += __popc(m);
   }
@@ -91,7 +94,8 @@ __device__ __forceinline__ u32 evq_fast_prep_b(const EvqTile& T, const EvqScanPa
   u32 wt[EVQ_NWARPS];
 #pragma unroll
   for (int i = 0; i < EVQ_NWARPS - 1; ++i) wt[i] = scr->wtot[G][i];
-  const u32 tb = d.delta + d.nbytes;
+  const u32 dl = d.delta & 15u;
+  const u32 tb = dl + d.nbytes;
   const u32 nchunks = (tb + 15u) >> 4;
   const u32 per = (nchunks + EVQ_NCONS - 1) / EVQ_NCONS;
   const u32 span = 32u * per;                      // chunks per warp
@@ -112,7 +116,7 @@ __device__ __forceinline__ u32 evq_fast_prep_b(const EvqTile& T, const EvqScanPa
   while (lo + 1u < nchunks && b + __popc(e & 0xffffu) <= r) { ++lo; b = before(lo, e); }
   u32 m = e & 0xffffu;
   for (u32 k = r - b; k > 0u; --k) m &= m - 1u;
-  return 16u * lo + (u32) __ffs(m) - d.delta;      // (__ffs - 1) is the terminator's byte; the value starts behind it
+  return 16u * lo + (u32) __ffs(m) - dl;           // (__ffs - 1) is the terminator's byte; the value starts behind it
 }
 
 // with a sub-index (Column::sub_index, staged with the tile as its own stream) nothing has to be searched
@@ -121,9 +125,10 @@ __device__ __forceinline__ bool evq_fast_general(const EvqTile& T) {
   return T.desc[S].nbytes != (u32) L * T.desc[S].nvals;
 }
 
+// EVQ_RPT == 8, EVQ_SUB_GRAN == 4: two entries per thread (low half: value 8t, high half: value 8t + 4) in one word
 template <int X>
 __device__ __forceinline__ u32 evq_fast_substart(const EvqTile& T, const EvqScanParams& P) {
-  return (u32) ((const u16*) (T.stage + P.streams[X].smem_off + T.desc[X].delta))[T.ctid];   // EVQ_RPT == 8: one entry per thread
+  return ((const u32*) (T.stage + P.streams[X].smem_off + T.desc[X].delta))[T.ctid];
 }
 
 // ---- per-thread decode of 4 consecutive values -------------------------------------------------------------------------
@@ -234,15 +239,20 @@ __device__ __forceinline__ void evq_fast_ld_leb32(const EvqTile& T, const EvqSca
       }
     }
   } else {
-    u32 p = pay + start;
+    // G == 2: `start` packs two entry points from the sub-index (value 0 and value EVQ_RPT / 2 of the thread), decoded as
+    // two independent chains; G == 1: one entry point (searched by evq_fast_prep), one chain over all values
+    u32 p[2] = {pay + (G == 2 ? (start & 0xffffu) : start), pay + (start >> 16)};
 #pragma unroll
-    for (int i = 0; i < EVQ_RPT; ++i) {
-      const u32 x = evq_stage_u32(T, p);
-      const u32 tm = ~x & 0x80808080u;           // terminator bits of the window
-      const u32 msk = tm ^ (tm - 1u);            // every bit up to and including the first of them
-      const u32 y = x & msk & 0x7f7f7f7fu;
-      v[i] = L == 2 ? evq_leb_pack2(y) : evq_fast_pack4(y);
-      p += __popc(msk) >> 3;
+    for (int i = 0; i < EVQ_RPT / G; ++i) {
+#pragma unroll
+      for (int h = 0; h < G; ++h) {
+        const u32 x = evq_stage_u32(T, p[h]);
+        const u32 tm = ~x & 0x80808080u;           // terminator bits of the window
+        const u32 msk = tm ^ (tm - 1u);            // every bit up to and including the first of them
+        const u32 y = x & msk & 0x7f7f7f7fu;
+        v[h * (EVQ_RPT / 2) + i] = L == 2 ? evq_leb_pack2(y) : evq_fast_pack4(y);
+        p[h] += __popc(msk) >> 3;
+      }
     }
   }
 }
@@ -254,7 +264,7 @@ __device__ __forceinline__ void evq_fast_ld_leb64(const EvqTile& T, const EvqSca
   const u8* pay = T.stage + P.streams[S].smem_off + T.desc[S].delta;
   const u8* p;
   if (!general) p = pay + (u32) L * evq_fast_first(T, S);
-  else p = pay + start;
+  else p = pay + (G == 2 ? (start & 0xffffu) : start);   // (one chain: the second sub-index entry is not needed)
 #pragma unroll
   for (int i = 0; i < EVQ_RPT; ++i) {
     u32 lo, hi;

@@ -79,6 +79,7 @@ static KernelShape shape_for(const evqgpu_query& q, evqgpu_table* t, const Bindi
     cs.vmax = stat_ceil(c.value_max);
     cs.vmin = stat_floor(c.value_min);
     cs.leb_len = c.leb_max_len;
+    cs.leb_uniform = c.data_kind == EVQ_KIND_LEB128 && c.leb_uniform && !getenv("EVQGPU_NO_UNIFORM");
     cs.data_stream = s.nstreams++;
     if (cs.nullable) {
       cs.level_stream = s.nstreams++;
@@ -98,6 +99,7 @@ static void widen_shape(KernelShape& s, const KernelShape& o) {
     s.cols[i].bits = std::max(s.cols[i].bits, o.cols[i].bits);
     s.cols[i].vmax = std::max(s.cols[i].vmax, o.cols[i].vmax);
     s.cols[i].vmin = std::min(s.cols[i].vmin, o.cols[i].vmin);
+    s.cols[i].leb_uniform = s.cols[i].leb_uniform && o.cols[i].leb_uniform && s.cols[i].leb_len == o.cols[i].leb_len;
     s.cols[i].leb_len = std::max(s.cols[i].leb_len, o.cols[i].leb_len);
   }
 }
@@ -109,7 +111,7 @@ static void finish_shape(KernelShape& s, bool have_subidx) {
   for (auto& c : s.cols) {
     c.gen_slot = -1;
     c.sub_stream = -1;
-    if (!(s.fast && c.used && c.kind == EVQ_KIND_LEB128 && c.leb_len >= 2)) continue;
+    if (!(s.fast && c.used && c.kind == EVQ_KIND_LEB128 && c.leb_len >= 2) || c.leb_uniform) continue;
     if (s.use_subidx) c.sub_stream = s.nstreams++;
     else c.gen_slot = s.ngen++;
   }
@@ -154,7 +156,7 @@ static StageLayout stage_layout(const evqgpu_query& q, evqgpu_table* t, const Bi
     // (kt consecutive tiles are contiguous in a required column's stream: at most kt times the largest tile)
     place(cs.data_stream, c.data_tile_cap * (uint32_t) s.kt);
     if (cs.nullable) place(cs.level_stream, c.level_tile_cap);
-    if (cs.sub_stream >= 0) place(cs.sub_stream, (EVQ_TILE_ROWS / 8) * 2 * (uint32_t) s.kt);
+    if (cs.sub_stream >= 0) place(cs.sub_stream, EVQ_SUB_ENTRIES * 2 * (uint32_t) s.kt);
   }
   L.stage_bytes = (uint32_t) round_up(off + 128, 128);
   (void) q;
@@ -298,7 +300,7 @@ static KernelShape shape_of_plans(const evqgpu_query& q, const std::vector<Table
     for (size_t i = 0; i < s.cols.size(); ++i) {
       if (p.binding.col_index[i] < 0) continue;
       const Column& c = p.table->cols[p.binding.col_index[i]];
-      if (c.data_kind == EVQ_KIND_LEB128 && s.cols[i].leb_len >= 2 && !c.sub_index.p) have_subidx = false;
+      if (c.data_kind == EVQ_KIND_LEB128 && s.cols[i].leb_len >= 2 && !s.cols[i].leb_uniform && !c.sub_index.p) have_subidx = false;
     }
   finish_shape(s, have_subidx);
   return s;
@@ -663,8 +665,8 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
              (int) s.use_subidx, q.nnarrow, s.kt);
     sig += buf;
     for (const auto& c : s.cols) {
-      snprintf(buf, sizeof(buf), "%d.%u.%u.%d.%u.%u.%u.%d.%d.%d.%llu.%llu;", (int) c.used, c.sql_type, c.kind, (int) c.nullable, c.dmax, c.bits,
-               c.leb_len, c.gen_slot, c.sub_stream, c.data_stream, (unsigned long long) c.vmax, (unsigned long long) c.vmin);
+      snprintf(buf, sizeof(buf), "%d.%u.%u.%d.%u.%u.%u%s.%d.%d.%d.%llu.%llu;", (int) c.used, c.sql_type, c.kind, (int) c.nullable, c.dmax, c.bits,
+               c.leb_len, c.leb_uniform ? "u" : "", c.gen_slot, c.sub_stream, c.data_stream, (unsigned long long) c.vmax, (unsigned long long) c.vmin);
       sig += buf;
     }
     for (size_t i = 0; i < nk; ++i) {

@@ -36,6 +36,7 @@ struct ColSig {
   uint64_t vmax = ~0ull;   // every value <= vmax (max over the scanned tables; coarsened, see stat_ceil)
   uint64_t vmin = 0;       // every value >= vmin (min over the scanned tables; coarsened, see stat_floor)
   uint32_t leb_len = 10;   // LEB128: longest value in bytes (max over the scanned tables)
+  bool leb_uniform = false;   // LEB128: every value of every scanned table has exactly leb_len bytes
   int gen_slot = -1;       // fast kernel: index among the LEB128 columns that may need the boundary search (leb_len >= 2)
   bool packed = false;     // fast kernel: keep the column's raw bytes (4 rows per word) for the dp4a aggregates
   int sub_stream = -1;     // fast kernel: stream of the column's sub-index (entry points of every 8th value), -1 = none

@@ -190,7 +190,8 @@ __global__ void k_minmax_bytes(const uint4* __restrict__ v, u64 n, unsigned long
 }
 
 // variable-length LEB128 streams with a sub-index: one thread decodes the 8 values behind one sub-index entry
-__global__ void k_minmax_leb(const u8* __restrict__ data, const u64* __restrict__ off_index, const u16* __restrict__ sub,
+// (sub == nullptr: every value is `ulen` bytes long)
+__global__ void k_minmax_leb(const u8* __restrict__ data, const u64* __restrict__ off_index, const u16* __restrict__ sub, u32 ulen,
                              u32 num_tiles, u64 num_rows, unsigned long long* __restrict__ out) {
   const u64 idx = (u64) blockIdx.x * blockDim.x + threadIdx.x;
   const u64 tile = idx / (EVQ_TILE_ROWS / 8);
@@ -199,7 +200,7 @@ __global__ void k_minmax_leb(const u8* __restrict__ data, const u64* __restrict_
   const u64 first = tile * EVQ_TILE_ROWS + 8ull * g;
   if (tile < num_tiles && first < num_rows) {
     const u32 nv = (u32) min((u64) 8, num_rows - first);
-    const u8* p = data + off_index[tile] + sub[idx];
+    const u8* p = data + off_index[tile] + (sub ? (u32) sub[tile * EVQ_SUB_ENTRIES + g * (8 / EVQ_SUB_GRAN)] : 8u * g * ulen);
     for (u32 i = 0; i < nv; ++i) {
       u64 x = 0;
       for (u32 sh = 0; sh < 70; sh += 7) {
@@ -259,9 +260,9 @@ __global__ void k_leb_select(const u8* __restrict__ data, u64 nbytes, const u64*
   off_index[t] = nbytes;   // fewer values than expected: the scan kernel never reads past nbytes
 }
 
-// sub_index[t][g] = byte offset, from the tile's first byte, at which value 8g of tile t starts.  One warp per tile walks
+// sub_index[t][g] = byte offset, from the tile's first byte, at which value EVQ_SUB_GRAN * g of tile t starts.  One warp per tile walks
 // the tile's bytes in 16-byte chunks (32 chunks per step), numbers the terminator bytes with a warp scan and records the
-// byte behind every 8th one.
+// byte behind every EVQ_SUB_GRAN-th one.
 __global__ void k_leb_sub_index(const u8* __restrict__ data, const u64* __restrict__ off_index, u32 num_tiles, u16* __restrict__ sub) {
   const u32 tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const u32 lane = threadIdx.x & 31;
@@ -271,7 +272,7 @@ __global__ void k_leb_sub_index(const u8* __restrict__ data, const u64* __restri
   const u32 delta = (u32) (start - al);
   const u32 tb = (u32) (end - al);                 // bytes [delta, tb) of the aligned window are the tile
   const u32 nchunks = (tb + 15u) >> 4;
-  u16* out = sub + (u64) tile * (EVQ_TILE_ROWS / 8);
+  u16* out = sub + (u64) tile * EVQ_SUB_ENTRIES;
   if (lane == 0) out[0] = 0;
   u32 running = 0;
   for (u32 base = 0; base < nchunks; base += 32) {
@@ -297,9 +298,9 @@ __global__ void k_leb_sub_index(const u8* __restrict__ data, const u64* __restri
     while (m) {
       const u32 k = __ffs(m) - 1u;
       m &= m - 1u;
-      if ((j & 7u) == 7u) {
-        const u32 g = (j + 1u) >> 3;
-        if (g < EVQ_TILE_ROWS / 8) out[g] = (u16) (16u * c + k + 1u - delta);
+      if ((j & (EVQ_SUB_GRAN - 1u)) == EVQ_SUB_GRAN - 1u) {
+        const u32 g = (j + 1u) / EVQ_SUB_GRAN;
+        if (g < EVQ_SUB_ENTRIES) out[g] = (u16) (16u * c + k + 1u - delta);
       }
       ++j;
     }
@@ -528,19 +529,24 @@ void table_finish_column(evqgpu_table* t, Column& c) {
       c.data_payload_bytes = used;
       c.data_bits = 0;
       c.data_tile_cap = span_from_index(c.off_index.as<u64>(), 1, 0, 0);
+      c.leb_uniform = nv > 0 && used == (u64) c.leb_max_len * nv;
       if (c.leb_max_len >= 2 && !nullable && ntiles) {
-        // where the values of the column differ in length: starts of every 8th value (the fast kernel's decode entry points)
-        c.sub_index.alloc((uint64_t) ntiles * (EVQ_TILE_ROWS / 8) * 2 + 256);
-        EVQ_CUDA(cudaMemsetAsync(c.sub_index.p, 0, c.sub_index.bytes, ctx->stream));
-        k_leb_sub_index<<<(unsigned) (((uint64_t) ntiles * 32 + 255) / 256), 256, 0, ctx->stream>>>(
-            c.data.buf.as<u8>(), c.off_index.as<u64>(), ntiles, c.sub_index.as<u16>());
-        EVQ_CUDA(cudaGetLastError());
-        ctx->kernel_launches++;
+        if (!c.leb_uniform) {
+          // where the values of the column differ in length: starts of every EVQ_SUB_GRAN-th value (the fast kernel's decode
+          // entry points)
+          c.sub_index.alloc((uint64_t) ntiles * EVQ_SUB_ENTRIES * 2 + 256);
+          EVQ_CUDA(cudaMemsetAsync(c.sub_index.p, 0, c.sub_index.bytes, ctx->stream));
+          k_leb_sub_index<<<(unsigned) (((uint64_t) ntiles * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+              c.data.buf.as<u8>(), c.off_index.as<u64>(), ntiles, c.sub_index.as<u16>());
+          EVQ_CUDA(cudaGetLastError());
+          ctx->kernel_launches++;
+        }
         // ... which also make the exact value range one cheap pass (8 values per thread)
         EVQ_CUDA(cudaMemsetAsync(minmax.p, 0, 16, ctx->stream));
         const uint64_t groups = (uint64_t) ntiles * (EVQ_TILE_ROWS / 8);
         k_minmax_leb<<<(unsigned) ((groups + 255) / 256), 256, 0, ctx->stream>>>(
-            c.data.buf.as<u8>(), c.off_index.as<u64>(), c.sub_index.as<u16>(), ntiles, t->num_rows, minmax.as<unsigned long long>());
+            c.data.buf.as<u8>(), c.off_index.as<u64>(), c.leb_uniform ? nullptr : c.sub_index.as<u16>(), c.leb_max_len, ntiles,
+            t->num_rows, minmax.as<unsigned long long>());
         EVQ_CUDA(cudaGetLastError());
         ctx->kernel_launches++;
         read_minmax(nv > 0);

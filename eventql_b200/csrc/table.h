@@ -6,9 +6,9 @@
 //   dlevel  : same for the DLEVEL pages of optional columns (bit-packed, libsimdcomp vertical layout)
 //   val_index[t] : number of non-NULL values before row tile t        (optional columns)   u64[ntiles+1]
 //   off_index[t] : byte offset of the first value of row tile t       (LEB128 columns)     u64[ntiles+1]
-//   sub_index[t][g] : byte offset inside tile t of its value 8g        (LEB128 columns whose values differ in length)
-//                     u16[ntiles][128] = 0.25 B per row; lets the fast scan kernel start its per-thread sequential decode
-//                     without searching value boundaries
+//   sub_index[t][g] : byte offset inside tile t of its value 4g        (LEB128 columns whose values differ in length)
+//                     u16[ntiles][256] = 0.5 B per row; lets the fast scan kernel start two independent 4-value decode
+//                     chains per thread without searching value boundaries
 // A row tile is EVQ_TILE_ROWS = 1024 records.
 #pragma once
 #include <string>
@@ -33,7 +33,7 @@ struct Column {
   bool scannable = false;      // flat, numeric
   DeviceStream data, dlevel;
   DevBuf off_index, val_index;
-  DevBuf sub_index;            // variable-length LEB128 columns: u16[ntiles][128] byte offset (from the tile's first byte) of every 8th value
+  DevBuf sub_index;            // variable-length LEB128 columns: u16[ntiles][256] byte offset (from the tile's first byte) of every 4th value
   uint64_t num_values = 0;
   uint64_t data_payload_bytes = 0;    // algorithmic bytes of the DATA stream
   uint64_t level_payload_bytes = 0;
@@ -42,6 +42,7 @@ struct Column {
   uint32_t level_bits = 0;
   uint32_t value_bits = 64;    // statistic: every value of the column is < 2^value_bits (computed when the column is loaded)
   uint32_t leb_max_len = 10;   // LEB128: the longest value in bytes
+  bool leb_uniform = false;    // LEB128: every value is leb_max_len bytes long (value i starts at byte i * leb_max_len: no sub-index)
   uint64_t value_max = ~0ull;  // statistic: largest value (exact for plain columns, 1-byte LEB128 and sub-indexed LEB128 columns; a bound otherwise)
   uint64_t value_min = 0;      // statistic: smallest value (exact for the same columns, 0 otherwise; 0 when NULLs are present)
   uint32_t data_tile_cap = 0;  // max bytes one tile copy of the data stream can need (multiple of 16)

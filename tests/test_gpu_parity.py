@@ -208,6 +208,37 @@ def test_partitions_are_scanned_as_one_table(gpu_ctx, tmp_path):
         t.close()
 
 
+@pytest.mark.parametrize("sizes", [(30_000, 5_000), (2_047, 1_025, 1), (1_024, 3_000)])
+def test_partitions_with_different_length_profiles(gpu_ctx, tmp_path, sizes):
+    """A LEB128 column whose values all have one length carries no sub-index; another partition of the same query where
+    the lengths differ does.  The kernel specialised for the set of partitions must decode both (odd tile counts exercise
+    the last, half-filled pipeline stage of the several-tiles-per-stage layout)."""
+    def spec(lo, span):
+        return [dict(name="k", logical_type=P.COL_UNSIGNED_INT, encoding=P.ENC_UINT64_LEB128, seed=5, lo=0, span=3),
+                dict(name="x", logical_type=P.COL_UNSIGNED_INT, encoding=P.ENC_UINT64_LEB128, seed=6, lo=lo, span=span),
+                dict(name="y", logical_type=P.COL_UNSIGNED_INT, encoding=P.ENC_UINT64_LEB128, seed=7, lo=100_000, span=3_000_000)]
+    profiles = [(200, 800), (0, 1000), (16384, 100)]      # all 2 bytes / 1-2 bytes / all 3 bytes
+    tables, files = [], []
+    for i, n in enumerate(sizes):
+        sp = spec(*profiles[i % len(profiles)])
+        t = gpu_ctx.synthesize(n, sp, row_offset=10_000 * i)
+        f = str(tmp_path / ("p%d.cst" % i))
+        t.write_file(f)
+        tables.append(t)
+        files.append(O.read_cstable(f))
+    c, names = T.cols_of(spec(0, 1))
+    plan = P.QueryPlan(names, [c["k"], P.call("count", P.lit(1)), P.call("sum", c["x"]), P.call("sum", c["x"] * c["k"]),
+                               P.call("max", c["y"]), P.call("sum", c["y"])], where=c["x"] < 900_000, group=[c["k"]])
+    for subset in ([0], [1] if len(tables) > 1 else [0], list(range(len(tables)))):
+        got, _ = run_gpu(gpu_ctx, [tables[i] for i in subset], plan)
+        compare(got, O.run_query([files[i] for i in subset], plan).rows(), False)
+    scan = P.QueryPlan(names, [c["x"], c["y"]], where=c["k"].eq(1), flags=0)
+    got, _ = run_gpu(gpu_ctx, tables, scan)
+    compare(got, O.run_query(files, scan).rows(), True)
+    for t in tables:
+        t.close()
+
+
 def test_device_generator_matches_numpy(gpu_ctx):
     """The synthetic tables of bench.py are generated on the device; pin the generator to tests/common.py:synth_values
     (same splitmix64 definition) through the CUDA decode path, for every encoding, with a row offset."""
