@@ -71,7 +71,7 @@ SYMBOLS = [
     "evqgpu_host_free", "evqgpu_host_register", "evqgpu_host_unregister", "evqgpu_ctx_stream", "evqgpu_ctx_synchronize",
     "evqgpu_ctx_set_profiling", "evqgpu_ctx_kernel_launches",
     "evqgpu_table_open", "evqgpu_table_create", "evqgpu_table_add_column", "evqgpu_table_add_stream",
-    "evqgpu_table_destroy", "evqgpu_table_num_rows", "evqgpu_table_num_columns", "evqgpu_table_column_info",
+    "evqgpu_table_set_filter", "evqgpu_table_destroy", "evqgpu_table_num_rows", "evqgpu_table_num_columns", "evqgpu_table_column_info",
     "evqgpu_table_find_column", "evqgpu_table_load_columns", "evqgpu_table_read_stream", "evqgpu_table_decode_column",
     "evqgpu_table_write_file", "evqgpu_table_synthesize", "evqgpu_function_lookup", "evqgpu_function_symbol",
     "evqgpu_function_is_aggregate", "evqgpu_query_create", "evqgpu_query_destroy", "evqgpu_query_num_columns",
@@ -110,6 +110,7 @@ def lib() -> C.CDLL:
     L.evqgpu_table_create.argtypes = [vp, u64, C.POINTER(vp)]
     L.evqgpu_table_add_column.argtypes = [vp, cp, u32, u32, u32, u32]
     L.evqgpu_table_add_stream.argtypes = [vp, cp, u32, vp, u64, u32, u32]
+    L.evqgpu_table_set_filter.argtypes = [vp, vp, u64, u32]
     L.evqgpu_table_destroy.argtypes = [vp]
     L.evqgpu_table_destroy.restype = None
     L.evqgpu_table_num_rows.argtypes = [vp]
@@ -353,6 +354,17 @@ class Table:
     def add_stream(self, column: str, kind: int, data: np.ndarray, bitpack_max: int = 0):
         data = np.ascontiguousarray(data, dtype=np.uint8)
         check(lib().evqgpu_table_add_stream(self._h, column.encode(), kind, data.ctypes.data_as(C.c_void_p), data.nbytes, bitpack_max, 0))
+
+    def set_filter(self, keep: Optional[np.ndarray]):
+        """FastCSTableScan::setFilter: one bool per row (True = keep), ANDed with WHERE; None removes the filter."""
+        if keep is None:
+            check(lib().evqgpu_table_set_filter(self._h, None, 0, 0))
+            return
+        keep = np.asarray(keep, dtype=bool)
+        bits = np.packbits(keep, bitorder="little")
+        if bits.size == 0:
+            bits = np.zeros(1, dtype=np.uint8)
+        check(lib().evqgpu_table_set_filter(self._h, bits.ctypes.data_as(C.c_void_p), int(keep.size), 0))
 
     def read_stream(self, column: str, kind: int = P.STREAM_DATA):
         n = C.c_uint64(0)

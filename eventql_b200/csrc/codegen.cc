@@ -908,6 +908,7 @@ std::string generate_source(const evqgpu_query& q, const KernelShape& shape_in) 
      << shape.ngen << "\n#define EVQ_GEN_CHUNKS " << gen_chunks(shape) << "\n#define EVQ_NNARROW " << q.nnarrow << "\n#define EVQ_NSTATE_SMEM " << q.nstate_smem << "\n";
   if (getenv("EVQGPU_DRYRUN")) os << "#define EVQ_DRYRUN 1\n";
   if (shape.fast) os << "#define EVQ_KT " << shape.kt << "\n";
+  if (shape.filter_stream >= 0) os << "#define EVQ_FILTER_STREAM " << shape.filter_stream << "\n";
   os << kSrcAbi << "\n" << kSrcPrelude << "\n";
   const std::string kern = shape.fast ? kSrcScanFast : kSrcScanKernel;
   const std::string marker = "//@@EVQ_GENERATED@@";

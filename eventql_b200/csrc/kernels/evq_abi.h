@@ -21,6 +21,7 @@ typedef double f64;
 #define EVQ_KIND_LEB128 3
 #define EVQ_KIND_LEVEL 4
 #define EVQ_KIND_SUBIDX 5   // per-tile table of decode entry points (u16 per EVQ_SUB_GRAN values), not column data
+#define EVQ_KIND_FILTER 6   // external row filter of the table: 1 bit per row (128 bytes per row tile)
 #define EVQ_SUB_GRAN 4     // the sub-index of a variable-length LEB128 column records the start of every 4th value
 #define EVQ_SUB_ENTRIES (EVQ_TILE_ROWS / EVQ_SUB_GRAN)
 

@@ -102,6 +102,9 @@ __device__ __forceinline__ void evq_producer_issue(const EvqScanParams& P, u32 t
       const u64 blk0 = row0 >> 7, blk1 = (row0 + rows + 127) >> 7;
       start = blk0 * 16 * S.bits;
       end = blk1 * 16 * S.bits;
+    } else if (S.kind == EVQ_KIND_FILTER) {
+      start = (u64) tile * (EVQ_TILE_ROWS / 8);
+      end = start + (EVQ_TILE_ROWS / 8);
     } else {
       u64 v0 = row0, v1 = row0 + rows;
       if (S.val_index) {
@@ -172,6 +175,9 @@ __device__ __forceinline__ void evq_producer_plan(const EvqScanParams& P, const 
   } else if (S.kind == EVQ_KIND_SUBIDX) {
     start = (u64) tile * EVQ_SUB_ENTRIES * 2;
     end = start + EVQ_SUB_ENTRIES * 2;
+  } else if (S.kind == EVQ_KIND_FILTER) {
+    start = (u64) tile * (EVQ_TILE_ROWS / 8);
+    end = start + (EVQ_TILE_ROWS / 8);
   } else {
     u64 v0 = row0, v1 = row0 + rows;
     if (S.val_index) {
@@ -244,6 +250,7 @@ __device__ __forceinline__ u64 evq_tile_start(const EvqScanParams& P, const EvqS
     case EVQ_KIND_PLAIN32: return row * 4;
     case EVQ_KIND_BITPACK: return ((row + 127) >> 7) * 16 * S.bits;   // tiles start on 128-value blocks; the end rounds up
     case EVQ_KIND_SUBIDX: return (u64) tile * EVQ_SUB_ENTRIES * 2;
+    case EVQ_KIND_FILTER: return (u64) tile * (EVQ_TILE_ROWS / 8);
     default: return S.off_index[tile];
   }
 }
@@ -295,6 +302,13 @@ __device__ __forceinline__ void evq_producer_commit_k(const EvqStream& S, bool a
   __syncwarp();
   if (cp.bytes) evq_bulk_g2s(stage + S.smem_off, cp.src, cp.bytes, full_bar);
 }
+
+// external row filter (FastCSTableScan::setFilter, CSTableScan.cc:826-833): bit r of the tile's 128 filter bytes
+#ifdef EVQ_FILTER_STREAM
+__device__ __forceinline__ u32 evq_filter_byte(const EvqTile& T, const EvqScanParams& P, u32 byte_index) {
+  return (u32) (T.stage + P.streams[EVQ_FILTER_STREAM].smem_off + T.desc[EVQ_FILTER_STREAM].delta)[byte_index];
+}
+#endif
 
 // ---- decoders over the staged tile ------------------------------------------------------------------------------------
 

@@ -455,6 +455,14 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
     // rows of this thread inside the tile: all EVQ_RPT except in the table's last tile (one compare against a constant per row)
     const u32 nvalid = T.rows >= EVQ_RPT * (tid + 1u) ? (u32) EVQ_RPT : (T.rows > EVQ_RPT * tid ? T.rows - EVQ_RPT * tid : 0u);
 
+#ifdef EVQ_FILTER_STREAM
+    // the table's external row filter, ANDed with WHERE (which still runs on every row: CSTableScan.cc:826-833)
+    const u32 keep = EVQ_RPT == 8 ? evq_filter_byte(T, P, tid) : (evq_filter_byte(T, P, tid >> 1) >> (4u * (tid & 1u))) & 15u;
+#define EVQ_ROW_KEPT(k) (((keep >> (k)) & 1u) != 0u)
+#else
+#define EVQ_ROW_KEPT(k) true
+#endif
+
     EvqFastPrep prep;
     evq_fast_prep(T, P, scr, prep);
     EvqCols cols;
@@ -469,7 +477,7 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
     for (int k = 0; k < EVQ_RPT; ++k) {
       EvqRow row;
       evq_fast_row(cols, k, row);
-      pass_k[k] = ((u32) k < nvalid) && evq_where(row, err);
+      pass_k[k] = ((u32) k < nvalid) && evq_where(row, err) && EVQ_ROW_KEPT(k);
       mine += pass_k[k] ? 1u : 0u;
     }
     u32 incl = mine;
@@ -522,7 +530,7 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
         const int k = 4 * j + kk;
         EvqRow row;
         evq_fast_row(cols, k, row);
-        pass[kk] = ((u32) k < nvalid) && evq_where(row, err);
+        pass[kk] = ((u32) k < nvalid) && evq_where(row, err) && EVQ_ROW_KEPT(k);
         fpv[kk] = slot[kk] = w0[kk] = w1[kk] = 0;
         if (pass[kk]) {
           u32 ktag[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
@@ -562,9 +570,9 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
         EvqRow row;
         evq_fast_row(cols, k, row);
 #ifdef EVQ_WHERE_PURE
-        const bool pass = evq_where(row, err) & ((u32) k < nvalid);
+        const bool pass = evq_where(row, err) & ((u32) k < nvalid) & EVQ_ROW_KEPT(k);
 #else
-        const bool pass = ((u32) k < nvalid) && evq_where(row, err);
+        const bool pass = ((u32) k < nvalid) && evq_where(row, err) && EVQ_ROW_KEPT(k);
 #endif
 #if defined(EVQ_SWAR_SLOTS) && EVQ_NSTATE_SMEM == 0
         selector |= pass ? 0u : (4u << (4 * kk));   // nothing else to do per row: no branch
@@ -597,7 +605,7 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
     for (int k = 0; k < EVQ_RPT; ++k) {
       EvqRow row;
       evq_fast_row(cols, k, row);
-      const bool pass = ((u32) k < nvalid) && evq_where(row, err);
+      const bool pass = ((u32) k < nvalid) && evq_where(row, err) && EVQ_ROW_KEPT(k);
 #if EVQ_TIER == 1
       if (pass) {
         ++passed;

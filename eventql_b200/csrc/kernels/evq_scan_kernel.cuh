@@ -280,6 +280,9 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
       evq_load_row(T, P, scr, prep, valid ? r : 0u, row);
       bool pass = false;
       if (valid) pass = evq_where(row, err);
+#ifdef EVQ_FILTER_STREAM   // the table's external row filter, ANDed with WHERE (CSTableScan.cc:826-833)
+      pass = pass && ((evq_filter_byte(T, P, r >> 3) >> (r & 7u)) & 1u) != 0u;
+#endif
 #if EVQ_TIER == 1
       if (pass) {
         ++passed;

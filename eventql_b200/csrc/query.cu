@@ -158,6 +158,11 @@ static StageLayout stage_layout(const evqgpu_query& q, evqgpu_table* t, const Bi
     if (cs.nullable) place(cs.level_stream, c.level_tile_cap);
     if (cs.sub_stream >= 0) place(cs.sub_stream, EVQ_SUB_ENTRIES * 2 * (uint32_t) s.kt);
   }
+  if (s.filter_stream >= 0) {
+    L.smem_off[s.filter_stream] = off;
+    L.smem_cap[s.filter_stream] = (EVQ_TILE_ROWS / 8) * (uint32_t) s.kt;
+    off += L.smem_cap[s.filter_stream];
+  }
   L.stage_bytes = (uint32_t) round_up(off + 128, 128);
   (void) q;
   return L;
@@ -303,6 +308,20 @@ static KernelShape shape_of_plans(const evqgpu_query& q, const std::vector<Table
       if (c.data_kind == EVQ_KIND_LEB128 && s.cols[i].leb_len >= 2 && !s.cols[i].leb_uniform && !c.sub_index.p) have_subidx = false;
     }
   finish_shape(s, have_subidx);
+  // external row filters (FastCSTableScan::setFilter): one more stream; a partition without one keeps all its rows
+  bool any_filter = false;
+  for (const auto& p : plans) any_filter = any_filter || p.table->has_filter;
+  if (any_filter) {
+    if (s.nstreams >= EVQ_MAX_STREAMS) fail(EVQGPU_ERR_UNSUPPORTED, "no stream left for the row filter");
+    s.filter_stream = s.nstreams++;
+    for (const auto& p : plans) {
+      evqgpu_table* t = p.table;
+      if (t->has_filter || t->filter.p) continue;
+      use_device(t->ctx);
+      t->filter.alloc(round_up((uint64_t) t->num_tiles * (EVQ_TILE_ROWS / 8), 256) + 256);
+      EVQ_CUDA(cudaMemsetAsync(t->filter.p, 0xff, t->filter.bytes, t->ctx->stream));
+    }
+  }
   return s;
 }
 
@@ -345,6 +364,17 @@ static void fill_streams(EvqScanParams& P, evqgpu_table* t, const Binding& b, co
       l.smem_off = L.smem_off[cs.level_stream];
       l.smem_cap = L.smem_cap[cs.level_stream];
     }
+  }
+  if (s.filter_stream >= 0) {
+    EvqStream& f = P.streams[s.filter_stream];
+    f.base = t->filter.as<u8>();
+    f.off_index = nullptr;
+    f.val_index = nullptr;
+    f.nbytes = t->filter.bytes;
+    f.kind = EVQ_KIND_FILTER;
+    f.bits = 1;
+    f.smem_off = L.smem_off[s.filter_stream];
+    f.smem_cap = L.smem_cap[s.filter_stream];
   }
 }
 
@@ -662,7 +692,7 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
     std::string sig;
     char buf[160];
     snprintf(buf, sizeof(buf), "t%d g%d n%d s%d c%d f%d x%d N%d K%d|", s.tier, s.g1, s.ncons, s.nstages, s.min_ctas, (int) s.fast,
-             (int) s.use_subidx, q.nnarrow, s.kt);
+             (int) s.use_subidx, q.nnarrow, s.kt * 100 + s.filter_stream + 1);
     sig += buf;
     for (const auto& c : s.cols) {
       snprintf(buf, sizeof(buf), "%d.%u.%u.%d.%u.%u.%u%s.%d.%d.%d.%llu.%llu;", (int) c.used, c.sql_type, c.kind, (int) c.nullable, c.dmax, c.bits,

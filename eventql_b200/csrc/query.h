@@ -59,6 +59,7 @@ struct KernelShape {
   int nstreams = 0, nleb = 0, nnull = 0;
   bool fast = false;   // all referenced columns are required: kernels/evq_scan_fast.cuh (4 consecutive rows per thread)
   int ngen = 0;        // fast kernel: LEB128 columns with leb_len >= 2 whose value boundaries are searched in the kernel
+  int filter_stream = -1;    // stream of the tables' external row filter (FastCSTableScan::setFilter), -1 = none
   bool use_subidx = false;   // fast kernel: variable-length columns take their decode entry points from Column::sub_index
   DenseMap dense;      // tier 1 with g1 > 1: the key -> slot map is baked into the kernel text as constants
 };

@@ -326,6 +326,8 @@ __global__ void k_max_span(const u64* __restrict__ idx, u32 num_tiles, u32 scale
   atomicMax(out, span);
 }
 
+__global__ void k_mask_last_byte(u8* p, u32 keep_bits) { *p &= (u8) ((1u << keep_bits) - 1u); }
+
 // ---- host side -----------------------------------------------------------------------------------------------------
 
 static void exclusive_scan_u64(evqgpu_ctx* ctx, const u64* in, u64* out, uint64_t n) {
@@ -646,6 +648,35 @@ int evqgpu_table_add_stream(evqgpu_table* tbl, const char* column, uint32_t kind
       if (!c.scannable) fail(EVQGPU_ERR_UNSUPPORTED, "column '%s' is outside the flat numeric scan path", column);
       table_finish_column(tbl, c);
     }
+  });
+}
+
+int evqgpu_table_set_filter(evqgpu_table* tbl, const void* bits, uint64_t nrows, uint32_t flags) {
+  return guarded([&] {
+    if (!tbl) fail(EVQGPU_ERR_ARG, "evqgpu_table_set_filter: null table");
+    use_device(tbl->ctx);
+    if (!bits) {
+      tbl->filter.release();
+      tbl->has_filter = false;
+      return;
+    }
+    if (nrows != tbl->num_rows)
+      fail(EVQGPU_ERR_ARG, "evqgpu_table_set_filter: the filter has %llu rows, the table %llu", (unsigned long long) nrows,
+           (unsigned long long) tbl->num_rows);
+    // one 128-byte line per row tile, zero padded: rows behind the end are dropped anyway
+    const uint64_t alloc = round_up((uint64_t) tbl->num_tiles * (EVQ_TILE_ROWS / 8), 256) + 256;
+    tbl->filter.alloc(alloc);
+    EVQ_CUDA(cudaMemsetAsync(tbl->filter.p, 0, tbl->filter.bytes, tbl->ctx->stream));
+    const uint64_t nbytes = (nrows + 7) / 8;
+    if (nbytes)
+      EVQ_CUDA(cudaMemcpyAsync(tbl->filter.p, bits, nbytes, (flags & EVQGPU_STREAM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                               tbl->ctx->stream));
+    if (nrows % 8) {   // clear the bits behind the last row in the last byte
+      k_mask_last_byte<<<1, 1, 0, tbl->ctx->stream>>>(tbl->filter.as<u8>() + nbytes - 1, (u32) (nrows % 8));
+      EVQ_CUDA(cudaGetLastError());
+    }
+    EVQ_CUDA(cudaStreamSynchronize(tbl->ctx->stream));   // the caller's buffer may go away
+    tbl->has_filter = true;
   });
 }
 

@@ -60,6 +60,8 @@ struct evqgpu_table {
   uint32_t num_tiles = 0;
   std::vector<evq::Column> cols;
   bool from_file = false;
+  evq::DevBuf filter;        // external row filter (FastCSTableScan::setFilter): 1 bit per row, LSB first, zero padded
+  bool has_filter = false;
   uint64_t uid = 0;   // unique per table object (pointers can be reused after destroy)
 
   int find(const char* name) const {

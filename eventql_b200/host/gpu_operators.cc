@@ -145,8 +145,21 @@ SType GpuQueryExpression::getColumnType(size_t idx) const { return (SType) evqgp
 GpuCSTableScan::GpuCSTableScan(GpuContext* gpu, std::shared_ptr<SequentialScanNode> stmt, const std::string& cstable_filename)
     : GpuQueryExpression(gpu, {cstable_filename}), stmt_(std::move(stmt)) {}
 
+void GpuCSTableScan::setFilter(std::vector<bool>&& filter) {
+  filter_ = std::move(filter);
+  filter_enabled_ = true;
+}
+
 ReturnCode GpuCSTableScan::execute() {
   try {
+    if (filter_enabled_) {
+      // packed LSB first, as evqgpu_table_set_filter takes it
+      std::vector<uint8_t> bits((filter_.size() + 7) / 8 + 1, 0);
+      for (size_t i = 0; i < filter_.size(); ++i)
+        if (filter_[i]) bits[i >> 3] |= (uint8_t) (1u << (i & 7));
+      evqgpu_table* t = gpu_->openTable(filenames_[0]);
+      if (evqgpu_table_set_filter(t, bits.data(), filter_.size(), 0) != EVQGPU_OK) return ReturnCode::error("ERUNTIME", lastError());
+    }
     const std::vector<std::string> cols = stmt_->selectedColumns();
     std::vector<const char*> names;
     for (const auto& c : cols) names.push_back(c.c_str());
@@ -164,7 +177,10 @@ ReturnCode GpuCSTableScan::execute() {
     d.where = where.view();
     d.num_select = (uint32_t) selv.size();
     d.select = selv.data();
-    return run(d);
+    const ReturnCode rc = run(d);
+    // the filter belongs to this scan, the resident table is shared
+    if (filter_enabled_) evqgpu_table_set_filter(gpu_->openTable(filenames_[0]), nullptr, 0, 0);
+    return rc;
   } catch (const std::exception& e) {
     return ReturnCode::error("ERUNTIME", e.what());
   }

@@ -67,8 +67,12 @@ class GpuCSTableScan : public GpuQueryExpression {
 public:
   GpuCSTableScan(GpuContext* gpu, std::shared_ptr<csql::SequentialScanNode> stmt, const std::string& cstable_filename);
   csql::ReturnCode execute() override;
+  // FastCSTableScan::setFilter (sql/CSTableScan.h:36-41): the LSM visibility bitmap of the segment, ANDed with WHERE
+  void setFilter(std::vector<bool>&& filter);
 private:
   std::shared_ptr<csql::SequentialScanNode> stmt_;
+  std::vector<bool> filter_;
+  bool filter_enabled_ = false;
 };
 
 // GroupByExpression whose input is a sequential scan of cstable partitions: scan + filter + aggregate in one device pass

@@ -173,6 +173,13 @@ EVQGPU_API int evqgpu_table_add_column(evqgpu_table* tbl, const char* name, uint
 EVQGPU_API int evqgpu_table_add_stream(evqgpu_table* tbl, const char* column, uint32_t kind, const void* ptr,
                                        uint64_t nbytes, uint32_t bitpack_max, uint32_t flags);
 
+/* External row filter of a table: FastCSTableScan::setFilter (sql/CSTableScan.h:36-41, CSTableScan.cc:1006-1009), the
+ * LSM visibility bitmap of a partition segment.  `bits` holds one bit per row, LSB first (row i = bit i%8 of byte i/8,
+ * 1 = keep); the scan evaluates WHERE on every row and then drops the rows whose bit is 0 (CSTableScan.cc:826-833).
+ * ptr may be a host pointer or - with EVQGPU_STREAM_DEVICE - a device pointer; it is copied.  bits == NULL removes the
+ * filter.  nrows must equal the table's row count. */
+EVQGPU_API int evqgpu_table_set_filter(evqgpu_table* tbl, const void* bits, uint64_t nrows, uint32_t flags);
+
 EVQGPU_API void evqgpu_table_destroy(evqgpu_table* tbl);
 
 EVQGPU_API uint64_t evqgpu_table_num_rows(const evqgpu_table* tbl);
