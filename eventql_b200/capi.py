@@ -60,6 +60,10 @@ class QueryStats(C.Structure):
                 ("jit_ms", C.c_float), ("scan_ms", C.c_float), ("scan_launches", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class SortSpec(C.Structure):
+    _fields_ = [("column", C.c_uint32), ("descending", C.c_uint32)]
+
+
 class DebugColumn(C.Structure):
     _fields_ = [("sql_type", C.c_uint32), ("encoding", C.c_uint32), ("dlevel_max", C.c_uint32), ("value_bits", C.c_uint32),
                 ("leb_max_len", C.c_uint32), ("reserved", C.c_uint32), ("value_min", C.c_uint64), ("value_max", C.c_uint64)]
@@ -76,7 +80,7 @@ SYMBOLS = [
     "evqgpu_table_write_file", "evqgpu_table_synthesize", "evqgpu_function_lookup", "evqgpu_function_symbol",
     "evqgpu_function_is_aggregate", "evqgpu_query_create", "evqgpu_query_destroy", "evqgpu_query_num_columns",
     "evqgpu_query_column_type", "evqgpu_query_execute", "evqgpu_query_enqueue", "evqgpu_query_finish",
-    "evqgpu_query_num_rows", "evqgpu_query_fetch", "evqgpu_query_get_stats", "evqgpu_query_kernel_source",
+    "evqgpu_query_num_rows", "evqgpu_query_fetch", "evqgpu_query_order_by", "evqgpu_query_limit", "evqgpu_query_get_stats", "evqgpu_query_kernel_source",
     "evqgpu_comm_unique_id", "evqgpu_comm_init", "evqgpu_comm_destroy", "evqgpu_query_merge", "evqgpu_debug_generate",
 ]
 
@@ -140,6 +144,8 @@ def lib() -> C.CDLL:
     L.evqgpu_query_finish.argtypes = [vp]
     L.evqgpu_query_num_rows.argtypes = [vp, C.POINTER(u64)]
     L.evqgpu_query_fetch.argtypes = [vp, u64, u64, C.POINTER(vp), C.POINTER(u64)]
+    L.evqgpu_query_order_by.argtypes = [vp, C.POINTER(SortSpec), u32]
+    L.evqgpu_query_limit.argtypes = [vp, u64, u64]
     L.evqgpu_query_get_stats.argtypes = [vp, C.POINTER(QueryStats)]
     L.evqgpu_query_kernel_source.argtypes = [vp]
     L.evqgpu_query_kernel_source.restype = cp
@@ -445,6 +451,15 @@ class Query:
         got = C.c_uint64(0)
         check(lib().evqgpu_query_fetch(self._h, row0, max_rows, ptrs, C.byref(got)))
         return [b[: got.value * w].tobytes() for b, w in zip(bufs, widths)]
+
+    def order_by(self, specs: Sequence[tuple]):
+        """OrderByExpression over the result: [(result column, descending)], most significant first."""
+        arr = (SortSpec * max(1, len(specs)))(*[SortSpec(int(c), 1 if d else 0) for c, d in specs])
+        check(lib().evqgpu_query_order_by(self._h, arr, len(specs)))
+
+    def limit(self, limit: int, offset: int = 0):
+        """LimitExpression: keep result rows [offset, offset + limit)."""
+        check(lib().evqgpu_query_limit(self._h, int(limit), int(offset)))
 
     def rows(self) -> List[tuple]:
         """Rows as python tuples (None = NULL): convenience for order-insensitive comparisons in tests."""

@@ -8,9 +8,15 @@
 //   evqgpu_sql q6    <lineitem .cst>...               Q6-style global aggregate (C2)
 //   evqgpu_sql count <file.cst> <column>              select count(1), sum(c), min(c), max(c), mean(c) ... where c > 0
 //   evqgpu_sql scan  <file.cst> <column>              select <column> from t        (FastCSTableScan alone)
+//   evqgpu_sql scanf <file.cst> <column> <m>          the same with setFilter(row % m == 0)   (LSM visibility filter)
+//   evqgpu_sql top   <file.cst> <column> <limit> <offset>
+//                                                     select c, count(1), sum(c) from t where c >= 0 group by c
+//                                                     order by c desc limit <limit> offset <offset>
+//                                                     (LimitExpression over OrderByExpression over the fused GROUP BY)
 //
 // Output: one line per row, ';' separated (uint64 decimal, float64 %.17g, bool true|false, NULL).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "gpu_operators.h"
 
@@ -122,6 +128,35 @@ int main(int argc, char** argv) {
       auto node = std::make_shared<GroupByNode>(gsel, std::vector<ExprRef>{}, scan);
       auto te = provider.buildGroupByExpression(node);
       return pull(te.get());
+    }
+    if (mode == "scanf" && argc >= 5) {
+      GpuTableProvider provider(&gpu, "t", {argv[2]});
+      std::vector<std::pair<std::string, SType>> in = {{argv[3], U}};
+      auto scan = std::make_shared<SequentialScanNode>("t", in, std::vector<SelectRef>{sel(col(0))}, nullptr);
+      auto te = provider.buildSequentialScan(scan);
+      auto* gs = dynamic_cast<GpuCSTableScan*>(te.get());
+      if (!gs) { fprintf(stderr, "provider declined the plan\n"); return 1; }
+      const uint64_t m = strtoull(argv[4], nullptr, 10);
+      const uint64_t nrows = evqgpu_table_num_rows(gpu.openTable(argv[2]));
+      std::vector<bool> keep(nrows);
+      for (uint64_t i = 0; i < nrows; ++i) keep[i] = m && i % m == 0;
+      gs->setFilter(std::move(keep));
+      return pull(te.get());
+    }
+    if (mode == "top" && argc >= 6) {
+      GpuTableProvider provider(&gpu, "t", {argv[2]});
+      std::vector<std::pair<std::string, SType>> in = {{argv[3], U}};
+      auto scan = std::make_shared<SequentialScanNode>("t", in, std::vector<SelectRef>{sel(col(0))}, cmp("gte", col(0), u(0)));
+      std::vector<SelectRef> gsel = {sel(col(0)), sel(count1()), sel(agg("sum", col(0)))};
+      auto node = std::make_shared<GroupByNode>(gsel, std::vector<ExprRef>{col(0)}, scan);
+      auto te = provider.buildGroupByExpression(node);
+      auto* gq = dynamic_cast<GpuQueryExpression*>(te.get());
+      if (!gq) { fprintf(stderr, "provider declined the plan\n"); return 1; }
+      te.release();
+      std::unique_ptr<GpuQueryExpression> input(gq);
+      std::unique_ptr<TableExpression> ordered(new GpuOrderByExpression({{0, true}}, std::move(input)));
+      GpuLimitExpression limited(strtoull(argv[4], nullptr, 10), strtoull(argv[5], nullptr, 10), std::move(ordered), gq);
+      return pull(&limited);
     }
     fprintf(stderr, "bad arguments\n");
     return 2;

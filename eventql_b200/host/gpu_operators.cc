@@ -121,6 +121,40 @@ ReturnCode GpuQueryExpression::run(const evqgpu_query_desc& desc) {
   }
 }
 
+ReturnCode GpuQueryExpression::refresh() {
+  if (!query_) return ReturnCode::error("ERUNTIME", "refresh before execute");
+  if (evqgpu_query_num_rows(query_, &num_rows_) != EVQGPU_OK) return ReturnCode::error("ERUNTIME", lastError());
+  cursor_ = 0;
+  return ReturnCode::success();
+}
+
+// ---- ORDER BY / LIMIT over a device-resident result ----------------------------------------------------------------------
+
+GpuOrderByExpression::GpuOrderByExpression(std::vector<GpuSortSpec> sort_specs, std::unique_ptr<GpuQueryExpression> input)
+    : sort_specs_(std::move(sort_specs)), input_(std::move(input)) {
+  if (sort_specs_.empty()) throw std::runtime_error("can't execute ORDER BY: no sort specs");   // orderby.cc:52-54
+}
+
+ReturnCode GpuOrderByExpression::execute() {
+  ReturnCode rc = input_->execute();
+  if (!rc.isSuccess()) return rc;
+  std::vector<evqgpu_sort_spec> specs;
+  for (const auto& s : sort_specs_) specs.push_back({(uint32_t) s.column, s.descending ? 1u : 0u});
+  if (evqgpu_query_order_by(input_->handle(), specs.data(), (uint32_t) specs.size()) != EVQGPU_OK)
+    return ReturnCode::error("ERUNTIME", lastError());
+  return input_->refresh();
+}
+
+GpuLimitExpression::GpuLimitExpression(size_t limit, size_t offset, std::unique_ptr<TableExpression> input, GpuQueryExpression* query)
+    : limit_(limit), offset_(offset), input_(std::move(input)), query_(query) {}
+
+ReturnCode GpuLimitExpression::execute() {
+  ReturnCode rc = input_->execute();
+  if (!rc.isSuccess()) return rc;
+  if (evqgpu_query_limit(query_->handle(), limit_, offset_) != EVQGPU_OK) return ReturnCode::error("ERUNTIME", lastError());
+  return query_->refresh();
+}
+
 ReturnCode GpuQueryExpression::nextBatch(SVector* columns, size_t* len) {
   *len = 0;
   if (!query_) return ReturnCode::error("ERUNTIME", "nextBatch before execute");

@@ -52,6 +52,9 @@ public:
   size_t getColumnCount() const override;
   csql::SType getColumnType(size_t idx) const override;
   static const size_t kOutputBatchSize = 1024;   // sql/CSTableScan.h:142, groupby.h:36
+  // for the operators stacked on top (ORDER BY / LIMIT run on the device-resident result)
+  evqgpu_query* handle() const { return query_; }
+  csql::ReturnCode refresh();   // re-read the row count after the result was reordered / cut; rewinds the cursor
 protected:
   GpuQueryExpression(GpuContext* gpu, std::vector<std::string> filenames) : gpu_(gpu), filenames_(std::move(filenames)) {}
   csql::ReturnCode run(const evqgpu_query_desc& desc);
@@ -82,6 +85,38 @@ public:
   csql::ReturnCode execute() override;
 private:
   std::shared_ptr<csql::GroupByNode> node_;
+};
+
+// OrderByExpression (sql/statements/select/orderby.h:34-66, orderby.cc:58-160) over a device-resident result: the sort
+// expressions are columns of the input (the planner appends hidden select items for anything else); execute() sorts on the
+// device (evqgpu_query_order_by), nextBatch() streams the input's rows in the new order.
+struct GpuSortSpec { size_t column; bool descending; };
+class GpuOrderByExpression : public csql::TableExpression {
+public:
+  GpuOrderByExpression(std::vector<GpuSortSpec> sort_specs, std::unique_ptr<GpuQueryExpression> input);
+  csql::ReturnCode execute() override;
+  csql::ReturnCode nextBatch(csql::SVector* columns, size_t* len) override { return input_->nextBatch(columns, len); }
+  size_t getColumnCount() const override { return input_->getColumnCount(); }
+  csql::SType getColumnType(size_t idx) const override { return input_->getColumnType(idx); }
+  GpuQueryExpression* input() const { return input_.get(); }
+private:
+  std::vector<GpuSortSpec> sort_specs_;
+  std::unique_ptr<GpuQueryExpression> input_;
+};
+
+// LimitExpression (sql/statements/select/limit.h, limit.cc:43-112): rows [offset, offset + limit) of its input, which is
+// either a device query or an ORDER BY over one
+class GpuLimitExpression : public csql::TableExpression {
+public:
+  GpuLimitExpression(size_t limit, size_t offset, std::unique_ptr<csql::TableExpression> input, GpuQueryExpression* query);
+  csql::ReturnCode execute() override;
+  csql::ReturnCode nextBatch(csql::SVector* columns, size_t* len) override { return input_->nextBatch(columns, len); }
+  size_t getColumnCount() const override { return input_->getColumnCount(); }
+  csql::SType getColumnType(size_t idx) const override { return input_->getColumnType(idx); }
+private:
+  size_t limit_, offset_;
+  std::unique_ptr<csql::TableExpression> input_;
+  GpuQueryExpression* query_;   // the device query underneath input_ (owned by it)
 };
 
 // CSTableScanProvider: table name -> cstable file(s)

@@ -309,6 +309,22 @@ EVQGPU_API int evqgpu_query_num_rows(evqgpu_query* q, uint64_t* out);
 EVQGPU_API int evqgpu_query_fetch(evqgpu_query* q, uint64_t row0, uint64_t max_rows, void* const* columns,
                                   uint64_t* nrows_out);
 
+/* ORDER BY over the result rows of an executed (and, for multi-rank jobs, merged) query, on the device:
+ * csql::OrderByExpression (sql/statements/select/orderby.cc:58-160) with sort expressions that are columns of the
+ * result (what the planner hands the operator: it appends hidden select items for anything else).  Values compare like
+ * the reference's typed `cmp` functions (unsigned / signed / double / bool; NULL tags are ignored, a NULL sorts as its
+ * value bits 0).  Rows with equal sort keys keep their previous order (the reference's std::sort leaves it unspecified).
+ * Later fetches see the new order. */
+typedef struct evqgpu_sort_spec {
+  uint32_t column;       /* result column */
+  uint32_t descending;   /* 0 = ASC */
+} evqgpu_sort_spec;
+EVQGPU_API int evqgpu_query_order_by(evqgpu_query* q, const evqgpu_sort_spec* specs, uint32_t nspecs);
+
+/* LIMIT / OFFSET: csql::LimitExpression (sql/statements/select/limit.cc:43-112): keep result rows
+ * [offset, offset + limit). */
+EVQGPU_API int evqgpu_query_limit(evqgpu_query* q, uint64_t limit, uint64_t offset);
+
 /* Statistics of the last execute. */
 typedef struct evqgpu_query_stats {
   uint64_t rows_scanned;

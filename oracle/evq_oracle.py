@@ -672,6 +672,33 @@ class Result:
         return pack_svector(self.columns[idx])
 
 
+def order_by(res: Result, specs: Sequence[Tuple[int, bool]]) -> Result:
+    """OrderByExpression::execute (sql/statements/select/orderby.cc:58-160): sort the rows with one typed `cmp` per
+    sort spec (values only: the pure cmp functions drop NULL tags, SURVEY H7, so a NULL compares as its value bits 0).
+    specs = [(result column, descending)], most significant first.  Rows with equal keys keep their order here; the
+    reference's std::sort leaves it unspecified."""
+    if not specs:
+        raise OracleError("can't execute ORDER BY: no sort specs")
+    idx = list(range(res.num_rows))
+    for col, desc in reversed(list(specs)):
+        v = res.columns[col]
+        vals = v.values.tolist()
+        if v.type == P.FLOAT64:
+            vals = [0.0 if x == 0.0 else x for x in vals]      # -0.0 == +0.0
+        idx.sort(key=lambda i: vals[i], reverse=bool(desc))   # python's sort is stable, also with reverse=True
+    take = np.asarray(idx, dtype=np.int64)
+    cols = [Vec(v.type, v.values[take], v.tags[take]) for v in res.columns]
+    return Result(res.types, cols, res.num_rows, res.rows_scanned, res.rows_passed)
+
+
+def limit(res: Result, count: int, offset: int = 0) -> Result:
+    """LimitExpression::nextBatch (sql/statements/select/limit.cc:43-112): rows [offset, offset + count)."""
+    lo = min(offset, res.num_rows)
+    hi = min(lo + count, res.num_rows)
+    cols = [Vec(v.type, v.values[lo:hi], v.tags[lo:hi]) for v in res.columns]
+    return Result(res.types, cols, hi - lo, res.rows_scanned, res.rows_passed)
+
+
 def pack_svector(v: Vec) -> bytes:
     """Packed SVector bytes (sql/svalue.cc:533-549): numeric [8 B value][1 B tag], BOOL [1 B][1 B tag]."""
     n = len(v.tags)

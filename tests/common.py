@@ -292,6 +292,39 @@ def golden_cases():
     return out
 
 
+def orderby_cases():
+    """ORDER BY / LIMIT over the mixed golden table: [(case, sql, plan without ORDER BY / LIMIT, sort specs
+    [(result column, descending)], limit or None, offset, number of select columns)].  The sort keys are total orders
+    (the reference's std::sort is not stable) and every referenced column also appears in WHERE (SURVEY H5)."""
+    spec = GOLDEN_TABLES["mixed"][0]()
+    c, names = cols_of(spec)
+    cnt = P.call("count", P.lit(1))
+    out = []
+    gb = P.QueryPlan(names, [c["b"], cnt, P.call("sum", c["c"])], where=(c["b"] >= 0) & (c["c"] >= 0), group=[c["b"]])
+    base = "select b, count(1), sum(c) from t where b >= 0 and c >= 0 group by b"
+    out.append(("ob_uint_asc_limit", base + " order by b limit 5;", gb, [(0, False)], 5, 0, 3))
+    out.append(("ob_uint_desc_limit_offset", base + " order by b desc limit 4 offset 2;", gb, [(0, True)], 4, 2, 3))
+    out.append(("ob_uint_all", base + " order by b;", gb, [(0, False)], None, 0, 3))
+    k0, k1 = c["b"] % 7, c["d"] % 3
+    two = P.QueryPlan(names, [k0, k1, cnt, P.call("sum", c["f"])], where=(c["b"] >= 0) & (c["f"] >= 0.0) & (c["d"] >= 0), group=[k0, k1])
+    out.append(("ob_two_keys", "select b % 7, d % 3, count(1), sum(f) from t where b >= 0 and f >= 0.0 and d >= 0 group by b % 7, d % 3 "
+                "order by b % 7 desc, d % 3 asc;", two, [(0, True), (1, False)], None, 0, 4))
+    fl = P.QueryPlan(names, [c["b"], P.call("sum", c["f"])], where=(c["f"] >= 0.0) & (c["b"] >= 0), group=[c["b"]])
+    out.append(("ob_float_desc", "select b, sum(f) as s from t where f >= 0.0 and b >= 0 group by b order by s desc limit 3;", fl,
+                [(1, True)], 3, 0, 2))
+    sk = P.call("to_int64", c["b"]) - 50
+    si = P.QueryPlan(names, [sk, cnt], where=c["b"] >= 0, group=[sk])
+    out.append(("ob_int64", "select to_int64(b) - 50, count(1) from t where b >= 0 group by to_int64(b) - 50 order by to_int64(b) - 50 "
+                "limit 4;", si, [(0, False)], 4, 0, 2))
+    sc = P.QueryPlan(names, [c["a"], c["d"]], where=(c["b"] < 2) & (c["a"] >= 0) & (c["d"] >= 0), flags=0)
+    out.append(("ob_scan_desc", "select a, d from t where b < 2 and a >= 0 and d >= 0 order by a desc limit 5;", sc, [(0, True)], 5, 0, 2))
+    ts = P.QueryPlan(names, [c["t"], c["b"]], where=(c["b"] < 1) & (c["t"] > 0), flags=0)
+    out.append(("ob_timestamp", "select t, b from t where b < 1 and t > 0 order by t limit 3;", ts, [(0, False)], 3, 0, 2))
+    lm = P.QueryPlan(names, [c["a"], c["b"]], where=(c["b"] < 5) & (c["a"] >= 0), flags=0)
+    out.append(("limit_scan_offset", "select a, b from t where b < 5 and a >= 0 limit 7 offset 3;", lm, [], 7, 3, 2))
+    return out
+
+
 def rows_digest(rows, types, ordered):
     """sha256 over the exact (non-float) columns of the rows; GROUP BY results are sorted first."""
     import hashlib

@@ -83,3 +83,26 @@ def test_scan_and_aggregates_on_the_reference_fixture(native_lib):
     assert rc == 0, err
     g = T.golden()["c1_global"]
     T.check_against_golden("c1_global", _parse(lines, g["types"]), ordered=False)
+
+
+@pytest.mark.gpu
+def test_order_by_limit_and_row_filter_operators(native_lib):
+    """GpuLimitExpression over GpuOrderByExpression over the fused GROUP BY, and GpuCSTableScan::setFilter, on the
+    reference's fixture: against the 213 golden `time` values of test/sql/00001"""
+    fx = os.path.join(GOLD, "testtbl.cst")
+    times = [int(l) for l in open(os.path.join(GOLD, "sql_00001.result.txt")).read().split("\n")[1:] if l.strip()]
+    groups = {}
+    for x in times:
+        c, s = groups.get(x, (0, 0))
+        groups[x] = (c + 1, s + x)
+    want = [(k, groups[k][0], groups[k][1]) for k in sorted(groups, reverse=True)]
+    rc, lines, err = run_sql("top", fx, "time", "7", "3")
+    assert rc == 0, (lines, err)
+    assert _parse(lines, ["uint64"] * 3) == want[3:10]
+    rc, lines, err = run_sql("top", fx, "time", "100000", "0")
+    assert rc == 0 and _parse(lines, ["uint64"] * 3) == want
+    rc, lines, err = run_sql("scanf", fx, "time", "3")
+    assert rc == 0, (lines, err)
+    assert [int(l) for l in lines] == times[::3]
+    rc, lines, err = run_sql("scanf", fx, "time", "0")      # nothing visible
+    assert rc == 0 and lines == []
