@@ -82,17 +82,21 @@ void layout_states(evqgpu_query& q, const KernelShape& shape) {
   q.state_ops.clear();
   q.state_keys.clear();
   q.state_carry_of.clear();
+  q.state_global.clear();
+  q.distinct_args.clear();
+  q.distinct_word.clear();
   auto word = [&](const std::string& key, int op, int carry_of = -1) -> int {
     for (size_t i = 0; i < q.state_keys.size(); ++i)
       if (q.state_keys[i] == key) return (int) i;
     q.state_keys.push_back(key);
     q.state_ops.push_back(op);
     q.state_carry_of.push_back(carry_of);
+    q.state_global.push_back(carry_of >= 0);
     return (int) q.state_keys.size() - 1;
   };
   word("rows", OP_ADD_U64);
   for (auto& item : q.select) {
-    item.state0 = item.state_seen = item.state_carry = -1;
+    item.state0 = item.state_seen = item.state_carry = item.distinct = -1;
     if (!item.agg) continue;
     const FnInfo& fi = item.agg->info();
     const Expr* arg = item.agg->args.empty() ? nullptr : item.agg->args[0].get();
@@ -101,6 +105,23 @@ void layout_states(evqgpu_query& q, const KernelShape& shape) {
     const bool never_null = arg && tag_is_static_zero(arg, shape);
     switch (fi.fn) {
       case Fn::COUNT: item.state0 = 0; break;
+      case Fn::COUNT_DISTINCT: {
+        // count_distinct_uint64 (aggregate.cc:80-137) keeps a std::set of the values per group.  Here one global hash set
+        // of (group, value) pairs per distinct argument (EvqScanParams::dt); the thread that inserts a pair - and only that
+        // one - adds 1 to the group's "cd:" word, which lives in global memory only.
+        item.state0 = word("cd:" + sig, OP_ADD_U64);
+        q.state_global[item.state0] = true;
+        for (size_t d = 0; d < q.distinct_word.size(); ++d)
+          if (q.distinct_word[d] == item.state0) item.distinct = (int) d;
+        if (item.distinct < 0) {
+          if (q.distinct_args.size() >= EVQ_MAX_DISTINCT)
+            fail(EVQGPU_ERR_UNSUPPORTED, "more than %d count_distinct aggregates in one query", EVQ_MAX_DISTINCT);
+          item.distinct = (int) q.distinct_args.size();
+          q.distinct_args.push_back(arg);
+          q.distinct_word.push_back(item.state0);
+        }
+        break;
+      }
       case Fn::SUM:
         item.state0 = ty == EVQ_FLOAT64 ? word("fsum:" + sig, OP_ADD_F64) : word("sum:" + sig, OP_ADD_U64);
         break;
@@ -125,7 +146,7 @@ void layout_states(evqgpu_query& q, const KernelShape& shape) {
   q.state_smem.assign(q.state_ops.size(), -1);
   q.nstate_smem = 0;
   for (size_t i = 0; i < q.state_ops.size(); ++i)
-    if (q.state_carry_of[i] < 0) q.state_smem[i] = q.nstate_smem++;
+    if (!q.state_global[i]) q.state_smem[i] = q.nstate_smem++;
   q.state_narrow.assign(q.state_ops.size(), -1);
   q.narrow_col.clear();
   q.nnarrow = 0;
@@ -249,7 +270,7 @@ void layout_narrow(evqgpu_query& q, const KernelShape& shape) {
       ok = is_packed_byte_column(q.group[i].get(), shape) && !may_null && dm.key_min[i] == 0 &&
            expr_value_max(q.group[i].get(), env) <= dm.key_range[i] - 1;
     }
-    if (ok && !getenv("EVQGPU_NO_SWAR_SLOTS")) {
+    if (ok && q.distinct_args.empty() && !getenv("EVQGPU_NO_SWAR_SLOTS")) {   // (count_distinct needs the slot per row)
       q.swar_slots = true;
       for (const auto& g : q.group) need_packed((int) g->col);
     }
@@ -258,7 +279,7 @@ void layout_narrow(evqgpu_query& q, const KernelShape& shape) {
   q.nstate_smem = 0;
   for (size_t i = 0; i < q.state_ops.size(); ++i) {
     q.state_smem[i] = -1;
-    if (q.state_carry_of[i] < 0 && q.state_narrow[i] < 0) q.state_smem[i] = q.nstate_smem++;
+    if (!q.state_global[i] && q.state_narrow[i] < 0) q.state_smem[i] = q.nstate_smem++;
   }
   std::ostringstream sg;
   sg << "S" << (int) q.swar_slots << ";";
@@ -323,6 +344,7 @@ static void gen_updates(std::ostringstream& os, const evqgpu_query& q, const Ker
     if (!item.agg) continue;
     const FnInfo& fi = item.agg->info();
     const Expr* arg = item.agg->args.empty() ? nullptr : item.agg->args[0].get();
+    if (fi.fn == Fn::COUNT_DISTINCT) continue;   // evq_accumulate_distinct
     if (fi.fn == Fn::COUNT) {
       // count(nil): the argument is evaluated for its side effects only (aggregate.cc:35-38, conversion.cc:29-90)
       if (arg && arg->op != EVQ_X_LITERAL && !(arg->op == EVQ_X_CALL && arg->args.size() == 1 && arg->args[0]->op == EVQ_X_LITERAL)) {
@@ -579,6 +601,18 @@ static std::string gen_row_functions(const evqgpu_query& q, const KernelShape& s
     if (c.tag != "0u") os << "  if (ktag[" << i << "]) key[" << i << "] = 0ull;\n";
   }
   os << "}\n";
+
+  // ---- count_distinct: insert (group, value) into the set of the argument; the inserting thread counts it
+  if (!q.distinct_args.empty() && (q.flags & EVQGPU_QUERY_GROUPBY)) {
+    os << "#define EVQ_NDISTINCT " << q.distinct_args.size() << "\n";
+    os << "__device__ __forceinline__ void evq_accumulate_distinct(const EvqRow& row, u64 gid, u64* state, const EvqScanParams& P, u32& err) {\n";
+    for (size_t d = 0; d < q.distinct_args.size(); ++d) {
+      Code c = gen_expr(q.distinct_args[d], env);
+      os << "  {\n    u64 k2[2] = {gid, " << as_bits(c, EVQ_UINT64) << "};\n    const u32 t2[2] = {0u, 0u};\n";
+      os << "    if (!evq_ht_upsert<2>(P.dt[" << d << "], k2, t2, state + " << q.distinct_word[d] << ")) err |= EVQ_ERR_TABLE_FULL;\n  }\n";
+    }
+    os << "}\n";
+  }
 
   // ---- dense tier: group key tuple -> accumulator slot, with the key bounds of this execution as constants
   if (shape.tier == 1 && shape.g1 > 1) {
@@ -861,6 +895,7 @@ static std::string gen_group_kernels(const evqgpu_query& q, const KernelShape& s
       std::string val;
       switch (fi.fn) {
         case Fn::COUNT: val = "st[0]"; break;                                       // count_get (aggregate.cc:40-42)
+        case Fn::COUNT_DISTINCT: val = s0; break;                                   // count_distinct_uint64_get
         case Fn::SUM: val = from_bits(s0, fi.ret); break;                           // sum_*_get
         case Fn::MIN:
         case Fn::MAX: val = "(" + s1 + " ? " + from_bits(s0, fi.ret) + " : " + from_bits("0ull", fi.ret) + ")"; break;
@@ -905,7 +940,8 @@ std::string generate_source(const evqgpu_query& q, const KernelShape& shape_in) 
      << std::max(1, q.nstate_smem) << "\n#define EVQ_NKEYS " << q.group.size() << "\n#define EVQ_NLEB "
      << shape.nleb << "\n#define EVQ_NNULL " << shape.nnull << "\n#define EVQ_HAS_PREP "
      << ((shape.nleb > 0 || shape.nnull > 0) ? 1 : 0) << "\n#define EVQ_MIN_CTAS " << shape.min_ctas << "\n#define EVQ_NGEN "
-     << shape.ngen << "\n#define EVQ_GEN_CHUNKS " << gen_chunks(shape) << "\n#define EVQ_NNARROW " << q.nnarrow << "\n#define EVQ_NSTATE_SMEM " << q.nstate_smem << "\n";
+     << shape.ngen << "\n#define EVQ_GEN_CHUNKS " << gen_chunks(shape) << "\n#define EVQ_NNARROW " << q.nnarrow << "\n#define EVQ_NSTATE_SMEM " << q.nstate_smem << "\n#define EVQ_NSTATE_ALL "
+     << std::max<size_t>(1, q.state_ops.size()) << "\n";
   if (getenv("EVQGPU_DRYRUN")) os << "#define EVQ_DRYRUN 1\n";
   if (shape.fast) os << "#define EVQ_KT " << shape.kt << "\n";
   if (shape.filter_stream >= 0) os << "#define EVQ_FILTER_STREAM " << shape.filter_stream << "\n";

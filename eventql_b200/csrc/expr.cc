@@ -28,6 +28,7 @@ const std::vector<FnInfo>& function_table() {
     reg("sum", Fn::SUM, I, {I}, true);
     reg("sum", Fn::SUM, U, {U}, true);
     reg("sum", Fn::SUM, F, {F}, true);
+    reg("count_distinct", Fn::COUNT_DISTINCT, U, {U}, true);   // sql/defaults.cc:50, aggregate.cc:80-137
     for (int ty : {U, I, F}) {
       reg("min", Fn::MIN, ty, {ty}, true);
       reg("max", Fn::MAX, ty, {ty}, true);

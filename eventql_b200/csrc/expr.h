@@ -15,7 +15,7 @@ enum class Fn {
   ADD, SUB, MUL, DIV, MOD, POW,
   TO_NIL, TO_INT64, TO_TIMESTAMP64, FROM_TIMESTAMP, DATE_TRUNC,
   // aggregates (sql/expressions/aggregate.cc + oracle/ref_tools/ext_aggregates.cc)
-  COUNT, SUM, MIN, MAX, MEAN
+  COUNT, SUM, MIN, MAX, MEAN, COUNT_DISTINCT
 };
 
 struct FnInfo {

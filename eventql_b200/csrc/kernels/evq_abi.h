@@ -33,6 +33,7 @@ typedef double f64;
 
 #define EVQ_MAX_STREAMS 32
 #define EVQ_MAX_KEYS 8
+#define EVQ_MAX_DISTINCT 4   // count_distinct aggregates per query
 
 // ---- kernel parameter blocks ----------------------------------------------------------------------------------
 
@@ -69,6 +70,7 @@ struct EvqScanParams {
   // aggregation state
   u64* dense_state;                 // tier 1: [G1][NSTATE] merged across CTAs with atomics
   EvqHashTable ht;                  // tier 2
+  EvqHashTable dt[EVQ_MAX_DISTINCT]; // count_distinct: sets of (group, value) pairs, one table per distinct argument
   u64 key_min[EVQ_MAX_KEYS];        // tier 1 dense slot = sum((key - min) * stride), NULL -> null_idx * stride
   u64 key_stride[EVQ_MAX_KEYS];
   u64 key_null_idx[EVQ_MAX_KEYS];

@@ -182,6 +182,13 @@ struct EvqSmemHeader {
 // evq_accumulate_*, evq_state_*, evq_project) are pasted at the next line by csrc/query.cc.
 //@@EVQ_GENERATED@@
 
+// count_distinct (generated only when the query has such aggregates): per passing row, after its group is known
+#ifdef EVQ_NDISTINCT
+#define EVQ_DISTINCT_ROW(row, gid, state) evq_accumulate_distinct(row, gid, state, P, err)
+#else
+#define EVQ_DISTINCT_ROW(row, gid, state) ((void) 0)
+#endif
+
 extern "C" __global__ void __launch_bounds__(EVQ_NTHREADS, EVQ_MIN_CTAS)
 evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
   extern __shared__ __align__(128) u8 evq_smem[];
@@ -291,9 +298,13 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
         u32 ktag[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
         evq_keys(row, key, ktag, err);
         const u32 g = evq_dense_slot(key, ktag, err);
-        if (g != ~0u) evq_accumulate_smem(row, sacc, g, tid, P.dense_state, err);
+        if (g != ~0u) {
+          evq_accumulate_smem(row, sacc, g, tid, P.dense_state, err);
+          EVQ_DISTINCT_ROW(row, (u64) g, P.dense_state + (u64) g * EVQ_NSTATE_ALL);
+        }
 #else
         evq_accumulate_regs(row, racc, P.dense_state, err);
+        EVQ_DISTINCT_ROW(row, 0ull, P.dense_state);
 #endif
       }
 #elif EVQ_TIER == 2
@@ -307,6 +318,7 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
           err |= EVQ_ERR_TABLE_FULL;
         } else {
           evq_accumulate_global(row, sp + 1 + EVQ_NKEYS, err);
+          EVQ_DISTINCT_ROW(row, (u64) sp, sp + 1 + EVQ_NKEYS);
         }
       }
 #else

@@ -761,6 +761,21 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
     launch(ctx, q.module->kernels.at("evq_init"), dim3((unsigned) ((ip.slots + 255) / 256)), dim3(256), 0, args);
     q.stats.kernel_launches++;
   }
+  // count_distinct: one empty (group, value) set per distinct argument; grown x4 with the group table when it fills up
+  if (!q.distinct_args.empty()) {
+    if ((q.flags & EVQGPU_QUERY_PARTIAL) && ctx->nranks > 1)
+      fail(EVQGPU_ERR_UNSUPPORTED, "count_distinct keeps value sets per group: partial results are not merged across ranks");
+    if (q.dt_cap == 0) q.dt_cap = next_pow2(std::max<uint64_t>(1ull << 20, std::min<uint64_t>(total_rows, 1ull << 24) * 2));
+    q.dt_slots.resize(q.distinct_args.size());
+    for (size_t d = 0; d < q.distinct_args.size(); ++d) {
+      ensure(q.dt_slots[d], q.dt_cap * 8 * 4);
+      EVQ_CUDA(cudaMemsetAsync(q.dt_slots[d].p, 0, q.dt_cap * 8 * 4, ctx->stream));
+      base.dt[d].slots = q.dt_slots[d].as<u64>();
+      base.dt[d].cap = q.dt_cap;
+      base.dt[d].stride = 4;      // fingerprint, group id, value, pad: one 32-byte sector
+      base.dt[d].nkeys = 2;
+    }
+  }
 
   run_scan(q, s, plans, base);
 
@@ -871,6 +886,10 @@ void finish_query(evqgpu_query& q) {
       // grow the group table and run again (resize policy: double until it fits)
       if (q.ht_cap >= (1ull << 31)) fail(EVQGPU_ERR_NOMEM, "group table exceeds 2^31 slots");
       q.ht_cap *= 4;
+      if (!q.distinct_args.empty()) {
+        if (q.dt_cap >= (1ull << 33)) fail(EVQGPU_ERR_NOMEM, "count_distinct set exceeds 2^33 slots");
+        q.dt_cap *= 4;
+      }
       std::vector<evqgpu_table*> tables = q.tables;
       const uint64_t hint = q.ht_cap;
       (void) hint;

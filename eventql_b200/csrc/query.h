@@ -21,6 +21,7 @@ struct SelectItem {
   int state0 = -1;             // count: rows word; sum: the sum; min/max: the extremum; mean: the sum (u64 low word or f64)
   int state_seen = -1;         // min/max/mean: number of non-NULL arguments (the rows word when the argument cannot be NULL)
   int state_carry = -1;        // mean over a uint64 argument: wraps of the 64-bit sum word (exact 128-bit integer sum)
+  int distinct = -1;           // count_distinct: index into evqgpu_query::distinct_args
 };
 
 // how one input column is laid out on the device (part of the kernel's specialisation key)
@@ -100,6 +101,11 @@ struct evqgpu_query {
   int nstate_smem = 0;
   // byte-wide aggregates of the fast dense kernel (rows counter, sums of 1-byte columns): accumulated with dp4a into
   // thread-private u32 registers instead of shared memory (codegen.cc: layout_narrow)
+  std::vector<bool> state_global;   // words updated in global memory only (carry words, count_distinct counters)
+  std::vector<const evq::Expr*> distinct_args;   // count_distinct: the distinct arguments (one (group, value) set each)
+  std::vector<int> distinct_word;   // ... and the state word that counts the set's members per group
+  std::vector<evq::DevBuf> dt_slots;
+  uint64_t dt_cap = 0;
   std::vector<int> state_narrow;    // index into plane_sums, -1 otherwise
   std::vector<int> narrow_col;      // input columns whose raw bytes (4 rows per word) the kernel keeps next to the values
   int nnarrow = 0;                  // byte planes over all plane sums: EVQ_NNARROW * EVQ_G1 u32 accumulators per thread

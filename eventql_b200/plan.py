@@ -125,6 +125,7 @@ def _registry():
     reg("count", [NIL], UINT64, agg=True)
     reg("sum", [INT64], INT64, agg=True)
     reg("sum", [UINT64], UINT64, agg=True)
+    reg("count_distinct", [UINT64], UINT64, agg=True)      # sql/defaults.cc:50, aggregate.cc:80-137
     reg("logical_and", [BOOL, BOOL], BOOL)
     reg("logical_or", [BOOL, BOOL], BOOL)
     reg("neg", [BOOL], BOOL)

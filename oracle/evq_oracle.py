@@ -845,6 +845,10 @@ def _aggregate(name: str, rtype: int, arg: Optional[Vec], starts: np.ndarray, m:
             seen = np.add.reduceat(present.astype(np.uint64), starts) > 0
             r = np.where(seen, r, np.zeros(1, dtype=v.dtype))
             return Vec(rtype, r.astype(v.dtype), zt)
+        if name == "count_distinct":                      # aggregate.cc:80-137: std::set of the VALUES (a NULL is its value 0)
+            ends = np.append(starts, m)
+            r = np.array([len(np.unique(arg.values[ends[i]:ends[i + 1]])) for i in range(ng)], dtype=np.uint64)
+            return Vec(P.UINT64, r, zt)
         if name == "mean":                                # ext_aggregates.cc Mean: sum(double)/n over non-NULL
             v = np.where(present, arg.values.astype(np.float64), 0.0)
             s = np.add.reduceat(v, starts)

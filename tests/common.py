@@ -215,6 +215,17 @@ def semantic_queries(spec):
         [cnt, P.call("sum", P.call("sub", P.call("to_int64", c["b"]), P.lit(50))),
          P.call("min", P.call("sub", P.call("to_int64", c["b"]), P.lit(50))),
          P.call("max", P.call("sub", P.call("to_int64", c["b"]), P.lit(50)))], where=c["b"] >= 0)
+    # count_distinct_uint64 (aggregate.cc:80-137): std::set of the values per group, a NULL counts as its value 0
+    cd = lambda e: P.call("count_distinct", e)
+    add("distinct_global", "select count_distinct(b), count(1) from t where b >= 0;", [cd(c["b"]), cnt], where=c["b"] >= 0)
+    add("distinct_null_groups", "select k, count_distinct(b), count_distinct(a), count(1), sum(b) from t where b >= 0 and k >= 0 and a >= 0 group by k;",
+        [c["k"], cd(c["b"]), cd(c["a"]), cnt, P.call("sum", c["b"])], where=(c["b"] >= 0) & (c["k"] >= 0) & (c["a"] >= 0), group=[c["k"]])
+    add("distinct_many_groups", "select d, count_distinct(c), count(1) from t where d >= 0 and c >= 0 group by d;",
+        [c["d"], cd(c["c"]), cnt], where=(c["d"] >= 0) & (c["c"] >= 0), group=[c["d"]])
+    add("distinct_required_hash", "select b, count_distinct(c % 50), count_distinct(b), sum(c) from t where b >= 0 and c >= 0 group by b;",
+        [c["b"], cd(c["c"] % 50), cd(c["b"]), P.call("sum", c["c"])], where=(c["b"] >= 0) & (c["c"] >= 0), group=[c["b"]])
+    add("distinct_required_dense", "select b % 3, count_distinct(c % 50), sum(b), count(1) from t where b >= 0 and c >= 0 group by b % 3;",
+        [c["b"] % 3, cd(c["c"] % 50), P.call("sum", c["b"]), cnt], where=(c["b"] >= 0) & (c["c"] >= 0), group=[c["b"] % 3])
     # scan-only plans (FastCSTableScan alone): filtered projection keeps table order
     add("scan_project", "select a, d, f, bo, c + d from t where b < 5;",
         [c["a"], c["d"], c["f"], c["bo"], c["c"] + c["d"]], where=c["b"] < 5, flags=0)

@@ -353,6 +353,26 @@ def test_order_by_large_result_properties(gpu_ctx):
     tbl.close()
 
 
+def test_count_distinct_set_grows(gpu_ctx):
+    """count_distinct over 40 M rows of almost-all-distinct values: the (group, value) set starts at 32 M slots, fills up,
+    is grown x4 and the query re-run; result == numpy's unique count per group"""
+    n = 40_000_000
+    spec = [dict(name="g", logical_type=P.COL_UNSIGNED_INT, encoding=P.ENC_UINT64_LEB128, seed=31, lo=0, span=3),
+            dict(name="x", logical_type=P.COL_UNSIGNED_INT, encoding=P.ENC_UINT64_PLAIN, seed=32, lo=0, span=1 << 26)]
+    tbl = gpu_ctx.synthesize(n, spec)
+    c, names = T.cols_of(spec)
+    plan = P.QueryPlan(names, [c["g"], P.call("count_distinct", c["x"]), P.call("count", P.lit(1))], where=c["x"] >= 0, group=[c["g"]])
+    got, stats = run_gpu(gpu_ctx, [tbl], plan)
+    g, _ = T.synth_values(spec[0], n)
+    x, _ = T.synth_values(spec[1], n)
+    want = []
+    for k in range(3):
+        m = g == k
+        want.append((k, int(np.unique(x[m]).size), int(m.sum())))
+    assert sorted(got) == want
+    tbl.close()
+
+
 def test_device_generator_matches_numpy(gpu_ctx):
     """The synthetic tables of bench.py are generated on the device; pin the generator to tests/common.py:synth_values
     (same splitmix64 definition) through the CUDA decode path, for every encoding, with a row offset."""
