@@ -544,8 +544,13 @@ static void gen_fast_layout(std::ostringstream& os, const KernelShape& shape) {
             start = "prep.start[" + std::to_string(c.gen_slot) + "]";
           }
           // second template argument: 2 = two sub-index entry points packed in `start`, 1 = one searched entry point
-          os << "    evq_fast_ld_leb" << (c.leb_len <= 4 ? "32" : "64") << "<" << S << ", " << (c.sub_stream >= 0 ? 2 : 1) << ", " << c.leb_len
-             << ">(T, P, " << general << ", " << start << ", raw);\n";
+          // (leb32 only) fourth: the fewest bytes a value of the column can have, from its minimum
+          uint32_t lmin = 1;
+          for (uint64_t m = c.vmin >> 7; m; m >>= 7) ++lmin;
+          lmin = std::min(lmin, c.leb_len);
+          os << "    evq_fast_ld_leb" << (c.leb_len <= 4 ? "32" : "64") << "<" << S << ", " << (c.sub_stream >= 0 ? 2 : 1) << ", " << c.leb_len;
+          if (c.leb_len <= 4) os << ", " << lmin;
+          os << ">(T, P, " << general << ", " << start << ", raw);\n";
         }
         break;
     }

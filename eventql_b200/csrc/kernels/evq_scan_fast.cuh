@@ -199,8 +199,15 @@ __device__ __forceinline__ void evq_fast_ld_leb1p(const EvqTile& T, const EvqSca
   }
 }
 
-// 2 <= L <= 4: 32-bit window
-template <int S, int G, int L>
+// 4 bytes at the shared-window byte address a (the stages are 128-byte aligned: the shift is the same as for an offset)
+__device__ __forceinline__ u32 evq_sa_u32(u32 a) {
+  u32 w0, w1;
+  asm volatile("ld.shared.u32 %0, [%2];\n\tld.shared.u32 %1, [%2+4];" : "=r"(w0), "=r"(w1) : "r"(a & ~3u));
+  return __funnelshift_r(w0, w1, a << 3);
+}
+
+// 2 <= L <= 4: 32-bit window.  LMIN: no value of the column is shorter than LMIN bytes (from the column's minimum).
+template <int S, int G, int L, int LMIN>
 __device__ __forceinline__ void evq_fast_ld_leb32(const EvqTile& T, const EvqScanParams& P, bool general, u32 start,
                                                   u32 (&v)[EVQ_RPT]) {
   const u32 pay = P.streams[S].smem_off + T.desc[S].delta;
@@ -241,17 +248,25 @@ __device__ __forceinline__ void evq_fast_ld_leb32(const EvqTile& T, const EvqSca
   } else {
     // G == 2: `start` packs two entry points from the sub-index (value 0 and value EVQ_RPT / 2 of the thread), decoded as
     // two independent chains; G == 1: one entry point (searched by evq_fast_prep), one chain over all values
-    u32 p[2] = {pay + (G == 2 ? (start & 0xffffu) : start), pay + (start >> 16)};
+    u32 p[2] = {T.stage_sa + pay + (G == 2 ? (start & 0xffffu) : start), T.stage_sa + pay + (start >> 16)};
 #pragma unroll
     for (int i = 0; i < EVQ_RPT / G; ++i) {
 #pragma unroll
       for (int h = 0; h < G; ++h) {
-        const u32 x = evq_stage_u32(T, p[h]);
-        const u32 tm = ~x & 0x80808080u;           // terminator bits of the window
-        const u32 msk = tm ^ (tm - 1u);            // every bit up to and including the first of them
-        const u32 y = x & msk & 0x7f7f7f7fu;
+        const u32 x = evq_sa_u32(p[h]);
+        u32 y;
+        if (LMIN == L - 1) {
+          // every value has L - 1 or L bytes: the continuation bit of byte L - 2 says which
+          const u32 cont = (x >> (8 * (L - 1) - 1)) & 1u;
+          y = x & (evq_fixed_mask(L - 1) + cont * (0x7fu << (8 * (L - 1))));
+          p[h] += (u32) (L - 1) + cont;
+        } else {
+          const u32 tm = ~x & 0x80808080u;           // terminator bits of the window
+          const u32 msk = tm ^ (tm - 1u);            // every bit up to and including the first of them
+          y = x & msk & 0x7f7f7f7fu;
+          p[h] += __popc(msk) >> 3;
+        }
         v[h * (EVQ_RPT / 2) + i] = L == 2 ? evq_leb_pack2(y) : evq_fast_pack4(y);
-        p[h] += __popc(msk) >> 3;
       }
     }
   }
