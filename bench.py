@@ -61,6 +61,9 @@ def workload(name):
         from eventql_b200 import plan as P
         return dict(spec=lambda p: T.lineitem_spec(P.ENC_UINT64_PLAIN), query=lambda s: T.q1(s), alias="lineitem", rows=125_000_000, parts=2,
                     desc="C3 (PLAIN twin): the same Q1 over lineitem stored UINT64_PLAIN (56 B/row)")
+    if name == "c3_q1_null":
+        return dict(spec=lambda p: T.lineitem_spec(null_every=7), query=lambda s: T.q1(s), alias="lineitem", rows=10_000_000, parts=2,
+                    desc="C3 (nullable twin, SURVEY 8d): Q1 over lineitem with optional price / tax / flag (NULL every 7th row): general kernel")
     if name == "c2_q6":
         return dict(spec=lambda p: T.lineitem_spec(), query=lambda s: T.q6(s), alias="lineitem", rows=100_000_000, parts=1,
                     desc="C2: TPC-H-Q6-style selective filter + global SUM, 100 M-row lineitem UINT64_LEB128")

@@ -619,6 +619,21 @@ static std::string gen_row_functions(const evqgpu_query& q, const KernelShape& s
     os << "}\n";
   }
 
+  // ---- direct-addressed group array (tier 2 without a hash table): key tuple -> slot from the key bounds, which are
+  // kernel PARAMETERS here (one kernel for every table set); a key outside the bounds is an internal error
+  if (shape.tier == 2 && shape.dense_global) {
+    os << "#define EVQ_DENSE_GLOBAL 1\n";
+    os << "__device__ __forceinline__ u64 evq_dense_slot_rt(const u64* key, const u32* ktag, const EvqScanParams& P, u32& err) {\n"
+          "  u64 slot = 0;\n  bool ok = true;\n";
+    for (size_t i = 0; i < q.group.size(); ++i) {
+      os << "  {\n    const u64 d = key[" << i << "] - P.key_min[" << i << "];\n";
+      os << "    const bool isnull = ktag[" << i << "] != 0u;\n";
+      os << "    ok = ok && (isnull ? P.key_null_idx[" << i << "] != ~0ull : d <= P.key_span[" << i << "]);\n";
+      os << "    slot += (isnull ? P.key_null_idx[" << i << "] : d) * P.key_stride[" << i << "];\n  }\n";
+    }
+    os << "  if (!ok) {\n    err |= EVQ_ERR_SLOT_RANGE;\n    return ~0ull;\n  }\n  return slot;\n}\n";
+  }
+
   // ---- dense tier: group key tuple -> accumulator slot, with the key bounds of this execution as constants
   if (shape.tier == 1 && shape.g1 > 1) {
     bool all_proven = true;
@@ -848,7 +863,7 @@ static std::string gen_group_kernels(const evqgpu_query& q, const KernelShape& s
   os << "struct EvqInitParams { u64* dense_state; EvqHashTable ht; u64 slots; };\n";
   os << "extern \"C\" __global__ void evq_init(const __grid_constant__ EvqInitParams I) {\n";
   os << "  const u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x;\n  if (i >= I.slots) return;\n";
-  if (shape.tier == 1) {
+  if (shape.tier == 1 || shape.dense_global) {
     for (int s = 0; s < nstate; ++s)
       os << "  I.dense_state[i * " << nstate << " + " << s << "] = evq_state_identity<" << q.state_ops[s] << ">();\n";
   } else {
@@ -865,7 +880,7 @@ static std::string gen_group_kernels(const evqgpu_query& q, const KernelShape& s
   os << "  const u64 slot = (u64) blockIdx.x * blockDim.x + threadIdx.x;\n  if (slot >= E.slots) return;\n";
   os << "  u64 st[" << std::max(1, nstate) << "];\n  u64 key[" << std::max(1, nk) << "];\n  u32 ktag[" << std::max(1, nk) << "];\n";
   os << "  u32 err = 0;\n";
-  if (shape.tier == 1) {
+  if (shape.tier == 1 || shape.dense_global) {
     for (int s = 0; s < nstate; ++s) os << "  st[" << s << "] = E.dense_state[slot * " << nstate << " + " << s << "];\n";
     os << "  if (st[0] == 0) return;\n";   // no row reached this group: it does not exist
     for (int i = 0; i < nk; ++i) {

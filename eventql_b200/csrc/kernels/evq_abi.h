@@ -74,6 +74,7 @@ struct EvqScanParams {
   u64 key_min[EVQ_MAX_KEYS];        // tier 1 dense slot = sum((key - min) * stride), NULL -> null_idx * stride
   u64 key_stride[EVQ_MAX_KEYS];
   u64 key_null_idx[EVQ_MAX_KEYS];
+  u64 key_span[EVQ_MAX_KEYS];       // largest non-NULL index of key i (direct-addressed group array: checked at run time)
   u64 dense_slots;                  // number of valid dense slots (<= EVQ_G1)
   // scan-only output
   u64* tile_counts;                 // pass 1: rows passing WHERE per tile

@@ -483,7 +483,10 @@ __device__ __forceinline__ u64* evq_ht_upsert_from(const EvqHashTable& H, const 
                                                   u64* claimed_counter) {
   const u64 mask = H.cap - 1;
   bool first = true;
-  for (u64 probes = 0; probes <= mask; ++probes) {
+  // a probe sequence this long means the table is (locally) full: report it, the host grows the table and runs again
+  // (walking a full table to its end would take cap probes for every remaining row)
+  const u64 limit = mask < 4096ull ? mask : 4096ull;
+  for (u64 probes = 0; probes <= limit; ++probes) {
     u64* s = H.slots + slot * H.stride;
     u64 cur = first ? w0 : evq_ld_l2(s);
     if (cur == 0) {

@@ -538,6 +538,27 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
       }
     }
 #endif
+#elif EVQ_TIER == 2 && defined(EVQ_DENSE_GLOBAL)
+    // direct-addressed group array: the slot follows from the key bounds, the aggregates are atomics at L2 (the array of a
+    // few million groups stays L2-resident: no DRAM traffic besides the column streams)
+#pragma unroll
+    for (int k = 0; k < EVQ_RPT; ++k) {
+      EvqRow row;
+      evq_fast_row(cols, k, row);
+      const bool pass = ((u32) k < nvalid) && evq_where(row, err) && EVQ_ROW_KEPT(k);
+      if (pass) {
+        u64 key[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
+        u32 ktag[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
+        evq_keys(row, key, ktag, err);
+        const u64 g = evq_dense_slot_rt(key, ktag, P, err);
+        if (g != ~0ull) {
+          ++passed;
+          u64* st = P.dense_state + g * EVQ_NSTATE_ALL;
+          evq_accumulate_global(row, st, err);
+          EVQ_DISTINCT_ROW(row, g, st);
+        }
+      }
+    }
 #elif EVQ_TIER == 2
     // hash tier: the group table lives in HBM, every probe is a DRAM round trip.  Rows are handled in quads: first the
     // home slots of all 4 rows are computed and their first probes issued, then the rows are resolved and their

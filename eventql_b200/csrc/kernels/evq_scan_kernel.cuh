@@ -307,6 +307,19 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
         EVQ_DISTINCT_ROW(row, 0ull, P.dense_state);
 #endif
       }
+#elif EVQ_TIER == 2 && defined(EVQ_DENSE_GLOBAL)
+      if (pass) {   // direct-addressed group array (see evq_scan_fast.cuh)
+        u64 key[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
+        u32 ktag[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
+        evq_keys(row, key, ktag, err);
+        const u64 g = evq_dense_slot_rt(key, ktag, P, err);
+        if (g != ~0ull) {
+          ++passed;
+          u64* st = P.dense_state + g * EVQ_NSTATE_ALL;
+          evq_accumulate_global(row, st, err);
+          EVQ_DISTINCT_ROW(row, g, st);
+        }
+      }
 #elif EVQ_TIER == 2
       if (pass) {
         ++passed;

@@ -607,7 +607,7 @@ static bool compute_dense_map(evqgpu_query& q, std::vector<evqgpu_table*>& table
     const uint64_t mn = bounds[BW * i + 1], mx = bounds[BW * i + 2];
     // signed and unsigned keys alike: (key - min) as an unsigned difference
     const uint64_t span = mx - mn;
-    if (span > 1000000) return false;
+    if (span > (1ull << 24) - 2) return false;
     dm.key_min[i] = mn;
     // one extra index for NULL keys, only when the expression can carry a NULL tag at all
     const bool may_null = bounds[BW * i + 3] != 0;
@@ -617,7 +617,7 @@ static bool compute_dense_map(evqgpu_query& q, std::vector<evqgpu_table*>& table
   uint64_t slots = 1;
   for (size_t i = nk; i-- > 0;) {
     dm.key_stride[i] = slots;
-    if (dm.key_range[i] > 4096 || slots * dm.key_range[i] > 4096) return false;
+    if (dm.key_range[i] > (1ull << 24) || slots * dm.key_range[i] > (1ull << 24)) return false;
     slots *= dm.key_range[i];
   }
   dm.slots = slots;
@@ -629,7 +629,7 @@ static bool compute_dense_map(evqgpu_query& q, std::vector<evqgpu_table*>& table
 void emit_results(evqgpu_query& q) {
   evqgpu_ctx* ctx = q.ctx;
   const uint64_t emit_slots = q.emit.slots;
-  const uint64_t out_cap = q.shape.tier == 1 ? emit_slots : std::min<uint64_t>(emit_slots, std::max<uint64_t>(q.emit_total_rows, 1));
+  const uint64_t out_cap = (q.shape.tier == 1 || q.shape.dense_global) ? std::min<uint64_t>(emit_slots, std::max<uint64_t>(q.emit_total_rows, 64)) : std::min<uint64_t>(emit_slots, std::max<uint64_t>(q.emit_total_rows, 1));
   q.out_cols.resize(q.select.size());
   for (size_t i = 0; i < q.select.size(); ++i)
     ensure(q.out_cols[i], out_cap * (q.select[i].expr->type == EVQ_BOOL ? 2 : 9) + 16);
@@ -664,26 +664,34 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
     if (q.dense_cache_valid && uids == q.dense_cache_uids) {
       dense = q.dense_cache_ok;
       dm = q.dense;
-    } else if (q.expected_groups == 0 || q.expected_groups <= 64) {
+    } else if (q.expected_groups <= (1ull << 24)) {   // (0 = unknown)
       dense = compute_dense_map(q, tables, dm);
       q.dense_cache_valid = true;
       q.dense_cache_ok = dense;
       q.dense_cache_uids = uids;
     }
+    bool dense_global = false;
     if (dense) {
       s.g1 = g1_for(dm.slots);
       // thread-private accumulators must fit next to the pipeline stages
       const size_t acc = (size_t) s.g1 * q.nstate_smem * (s.fast ? 256 : 128) * 8;
-      if (s.g1 > 64 || acc > 96 * 1024) dense = false;
+      if (dm.slots > 64 || acc > 96 * 1024) {
+        dense = false;
+        // too many groups for thread-private state, but the key tuples span a small box: a direct-addressed group
+        // array in global memory (no keys, no probing), which stays L2-resident up to a few million groups.  A
+        // multi-rank job keeps the hash tier: its merge moves groups, not boxes.
+        dense_global = dm.slots * q.state_ops.size() * 8 <= (1ull << 30) && !((q.flags & EVQGPU_QUERY_PARTIAL) && ctx->nranks > 1) &&
+                       !getenv("EVQGPU_NO_DENSE_GLOBAL");
+      }
     }
-    if (!dense) { s.tier = 2; s.g1 = 1; }
+    if (!dense) { s.tier = 2; s.g1 = 1; s.dense_global = dense_global; }
   }
-  if (s.tier == 1 && s.g1 > 1) s.dense = dm;
+  if ((s.tier == 1 && s.g1 > 1) || s.dense_global) s.dense = dm;
   layout_narrow(q, s);
   fit_shape(q, s, plans);
   q.shape = s;
   q.dense = dm;
-  q.stats.strategy = (uint32_t) s.tier;
+  q.stats.strategy = s.dense_global ? 1u : (uint32_t) s.tier;
 
   // ---- kernel text: everything the generated text depends on is summarised in a short signature, so that a repeated
   // execution (the common case: same plan, same partitions) skips spelling and hashing ~300 KB of source
@@ -692,14 +700,14 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
     std::string sig;
     char buf[160];
     snprintf(buf, sizeof(buf), "t%d g%d n%d s%d c%d f%d x%d N%d K%d|", s.tier, s.g1, s.ncons, s.nstages, s.min_ctas, (int) s.fast,
-             (int) s.use_subidx, q.nnarrow, s.kt * 100 + s.filter_stream + 1);
+             (int) s.use_subidx, q.nnarrow, s.kt * 1000 + (s.filter_stream + 1) * 10 + (int) s.dense_global);
     sig += buf;
     for (const auto& c : s.cols) {
       snprintf(buf, sizeof(buf), "%d.%u.%u.%d.%u.%u.%u%s.%d.%d.%d.%llu.%llu;", (int) c.used, c.sql_type, c.kind, (int) c.nullable, c.dmax, c.bits,
                c.leb_len, c.leb_uniform ? "u" : "", c.gen_slot, c.sub_stream, c.data_stream, (unsigned long long) c.vmax, (unsigned long long) c.vmin);
       sig += buf;
     }
-    for (size_t i = 0; i < nk; ++i) {
+    for (size_t i = 0; i < nk && !s.dense_global; ++i) {   // (the direct-addressed array takes its bounds as parameters)
       snprintf(buf, sizeof(buf), "k%llu.%llu.%llu.%llu;", (unsigned long long) s.dense.key_min[i], (unsigned long long) s.dense.key_stride[i],
                (unsigned long long) s.dense.key_null_idx[i], (unsigned long long) s.dense.key_range[i]);
       sig += buf;
@@ -726,19 +734,20 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
   InitParams ip;
   memset(&ip, 0, sizeof(ip));
   uint64_t emit_slots = 0;
-  if (s.tier == 1) {
-    const uint64_t slots = s.g1 > 1 ? (uint64_t) s.g1 : 1;
+  if (s.tier == 1 || s.dense_global) {
+    const uint64_t slots = s.dense_global ? dm.slots : s.g1 > 1 ? (uint64_t) s.g1 : 1;
     ensure(q.dense_state, slots * nstate * 8);
     base.dense_state = q.dense_state.as<u64>();
-    base.dense_slots = s.g1 > 1 ? dm.slots : 1;
+    base.dense_slots = (s.g1 > 1 || s.dense_global) ? dm.slots : 1;
     for (size_t i = 0; i < nk; ++i) {
       base.key_min[i] = dm.key_min[i];
       base.key_stride[i] = dm.key_stride[i];
       base.key_null_idx[i] = dm.key_null_idx[i];
+      base.key_span[i] = dm.key_range[i] - (dm.key_null_idx[i] != ~0ull ? 2 : 1);
     }
     ip.dense_state = base.dense_state;
     ip.slots = slots;
-    emit_slots = s.g1 > 1 ? dm.slots : 1;
+    emit_slots = (s.g1 > 1 || s.dense_global) ? dm.slots : 1;
   } else {
     uint64_t want = q.ht_cap;
     if (want == 0) {
@@ -765,7 +774,10 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
   if (!q.distinct_args.empty()) {
     if ((q.flags & EVQGPU_QUERY_PARTIAL) && ctx->nranks > 1)
       fail(EVQGPU_ERR_UNSUPPORTED, "count_distinct keeps value sets per group: partial results are not merged across ranks");
-    if (q.dt_cap == 0) q.dt_cap = next_pow2(std::max<uint64_t>(1ull << 20, std::min<uint64_t>(total_rows, 1ull << 24) * 2));
+    if (q.dt_cap == 0) {
+      q.dt_cap = next_pow2(std::max<uint64_t>(1ull << 20, std::min<uint64_t>(total_rows, 1ull << 24) * 2));
+      if (const char* e = getenv("EVQGPU_DT_CAP")) q.dt_cap = next_pow2(std::max<uint64_t>(1024, strtoull(e, nullptr, 10)));   // (tests: force growth)
+    }
     q.dt_slots.resize(q.distinct_args.size());
     for (size_t d = 0; d < q.distinct_args.size(); ++d) {
       ensure(q.dt_slots[d], q.dt_cap * 8 * 4);

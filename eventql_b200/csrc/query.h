@@ -58,6 +58,8 @@ struct KernelShape {
   int kt = 1;          // fast kernel: consecutive row tiles per pipeline stage (one bulk copy per stream and stage)
   int min_ctas = 1;
   int nstreams = 0, nleb = 0, nnull = 0;
+  bool dense_global = false;   // tier 2 without a hash table: the groups are a direct-addressed array (key bounds known), updated
+                               // with atomics at L2 - for key ranges beyond the thread-private dense tier
   bool fast = false;   // all referenced columns are required: kernels/evq_scan_fast.cuh (4 consecutive rows per thread)
   int ngen = 0;        // fast kernel: LEB128 columns with leb_len >= 2 whose value boundaries are searched in the kernel
   int filter_stream = -1;    // stream of the tables' external row filter (FastCSTableScan::setFilter), -1 = none

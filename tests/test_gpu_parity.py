@@ -353,15 +353,16 @@ def test_order_by_large_result_properties(gpu_ctx):
     tbl.close()
 
 
-def test_count_distinct_set_grows(gpu_ctx):
-    """count_distinct over 40 M rows of almost-all-distinct values: the (group, value) set starts at 32 M slots, fills up,
-    is grown x4 and the query re-run; result == numpy's unique count per group"""
-    n = 40_000_000
+def test_count_distinct_set_grows(gpu_ctx, monkeypatch):
+    """count_distinct whose (group, value) set starts too small (forced to 4096 slots): it fills up, is grown x4 until the
+    pairs fit and the query re-run; result == numpy's unique count per group"""
+    n = 300_000
     spec = [dict(name="g", logical_type=P.COL_UNSIGNED_INT, encoding=P.ENC_UINT64_LEB128, seed=31, lo=0, span=3),
             dict(name="x", logical_type=P.COL_UNSIGNED_INT, encoding=P.ENC_UINT64_PLAIN, seed=32, lo=0, span=1 << 26)]
     tbl = gpu_ctx.synthesize(n, spec)
     c, names = T.cols_of(spec)
     plan = P.QueryPlan(names, [c["g"], P.call("count_distinct", c["x"]), P.call("count", P.lit(1))], where=c["x"] >= 0, group=[c["g"]])
+    monkeypatch.setenv("EVQGPU_DT_CAP", "4096")
     got, stats = run_gpu(gpu_ctx, [tbl], plan)
     g, _ = T.synth_values(spec[0], n)
     x, _ = T.synth_values(spec[1], n)
@@ -565,11 +566,18 @@ def test_timeseries_partition_properties(gpu_ctx):
     _sql, plan = T.q_timeseries(T.readings_spec(0), expected_groups=1_440_000)
     per = [run_gpu(gpu_ctx, [p], plan)[0] for p in parts]
     both, stats = run_gpu(gpu_ctx, parts, plan)
-    assert stats["strategy"] == 2
+    assert stats["strategy"] == 1            # 2 x 1440 x 1000 key box: the direct-addressed group array, not the hash table
     assert len(both) == len(per[0]) + len(per[1])
     assert sorted(both) == sorted(per[0] + per[1])
     assert sum(r[2] for r in both) == 2 * n
     day0 = 1_438_041_600_000_000 // 60_000_000
     assert all(day0 <= r[0] < day0 + 1440 for r in per[0]) and all(day0 + 1440 <= r[0] < day0 + 2880 for r in per[1])
+    # the hash tier must give the same groups
+    os.environ["EVQGPU_NO_DENSE_GLOBAL"] = "1"
+    try:
+        hashed, hstats = run_gpu(gpu_ctx, parts, plan)
+    finally:
+        del os.environ["EVQGPU_NO_DENSE_GLOBAL"]
+    assert hstats["strategy"] == 2 and sorted(hashed) == sorted(both)
     for p in parts:
         p.close()
