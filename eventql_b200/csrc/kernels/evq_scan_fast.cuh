@@ -272,11 +272,46 @@ __device__ __forceinline__ void evq_fast_ld_leb32(const EvqTile& T, const EvqSca
   }
 }
 
+// The thread's 64 contiguous, 16-byte aligned bytes (8 values of 8 bytes; EVQ_RPT == 8) without bank conflicts: at a
+// 64-byte lane stride four 128-bit loads at the same offset collide 4-way inside every quarter warp (lanes t and t + 2
+// start at the same bank), per-value 64-bit loads 8- to 16-way.  Lane t therefore reads its four 16-byte pieces in the
+// rotated order (j + t / 2) & 3 - the 8 lanes of a quarter warp then cover all 32 banks - and rotates them back in
+// registers (two rounds of selects).
+__device__ __forceinline__ void evq_stage_64bytes(const EvqTile& T, u32 off, u32 (&w)[16]) {
+  const u32 r = (T.ctid >> 1) & 3u;
+  u32 c[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) evq_stage_v4(T, off + 16u * ((j + r) & 3u), c[j][0], c[j][1], c[j][2], c[j][3]);
+  // c[j] = piece (j + r) & 3; piece k = c[(k - r) & 3]
+  const bool r1 = (r & 1u) != 0u, r2 = (r & 2u) != 0u;
+  u32 e[4][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) e[k][i] = r1 ? c[(k + 3) & 3][i] : c[k][i];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[4 * k + i] = r2 ? e[(k + 2) & 3][i] : e[k][i];
+}
+
 // 5 <= L <= 10: 64-bit window (+ 2 bytes for 9- and 10-byte values)
 template <int S, int G, int L>
 __device__ __forceinline__ void evq_fast_ld_leb64(const EvqTile& T, const EvqScanParams& P, bool general, u32 start,
                                                   u64 (&v)[EVQ_RPT]) {
   const u8* pay = T.stage + P.streams[S].smem_off + T.desc[S].delta;
+  if (L == 8 && EVQ_RPT == 8 && !general) {
+    // every value has 8 bytes: the thread's 8 values are 64 contiguous bytes
+    const u32 off = P.streams[S].smem_off + T.desc[S].delta + 8u * evq_fast_first(T, S);
+    if ((off & 15u) == 0u) {
+      u32 w[16];
+      evq_stage_64bytes(T, off, w);
+#pragma unroll
+      for (int i = 0; i < EVQ_RPT; ++i)
+        v[i] = (u64) evq_leb_pack4(w[2 * i] & 0x7f7f7f7fu) | ((u64) evq_leb_pack4(w[2 * i + 1] & 0x7f7f7f7fu) << 28);
+      return;
+    }
+  }
   const u8* p;
   if (!general) p = pay + (u32) L * evq_fast_first(T, S);
   else p = pay + (G == 2 ? (start & 0xffffu) : start);   // (one chain: the second sub-index entry is not needed)
@@ -311,7 +346,12 @@ __device__ __forceinline__ void evq_fast_ld_leb64(const EvqTile& T, const EvqSca
 template <int S>
 __device__ __forceinline__ void evq_fast_ld_plain64(const EvqTile& T, const EvqScanParams& P, u64 (&v)[EVQ_RPT]) {
   const u32 off = P.streams[S].smem_off + T.desc[S].delta + 8u * evq_fast_first(T, S);
-  if ((off & 15u) == 0u) {   // 16-byte vector loads (two values each)
+  if (EVQ_RPT == 8 && (off & 15u) == 0u) {   // 64 contiguous bytes per thread, bank-conflict free
+    u32 w[16];
+    evq_stage_64bytes(T, off, w);
+#pragma unroll
+    for (int i = 0; i < EVQ_RPT; ++i) v[i] = (u64) w[2 * i] | ((u64) w[2 * i + 1] << 32);
+  } else if ((off & 15u) == 0u) {   // 16-byte vector loads (two values each)
 #pragma unroll
     for (int i = 0; i < EVQ_RPT; i += 2) {
       u32 a, b, c, d;
@@ -330,7 +370,12 @@ __device__ __forceinline__ void evq_fast_ld_plain64(const EvqTile& T, const EvqS
 template <int S>
 __device__ __forceinline__ void evq_fast_ld_plain64_lo(const EvqTile& T, const EvqScanParams& P, u32 (&v)[EVQ_RPT]) {
   const u32 off = P.streams[S].smem_off + T.desc[S].delta + 8u * evq_fast_first(T, S);
-  if ((off & 15u) == 0u) {
+  if (EVQ_RPT == 8 && (off & 15u) == 0u) {
+    u32 w[16];
+    evq_stage_64bytes(T, off, w);
+#pragma unroll
+    for (int i = 0; i < EVQ_RPT; ++i) v[i] = w[2 * i];
+  } else if ((off & 15u) == 0u) {
 #pragma unroll
     for (int i = 0; i < EVQ_RPT; i += 2) {
       u32 b, d;
