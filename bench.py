@@ -484,7 +484,8 @@ def evq_arm(args):
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": wl["desc"], "sql": sql, "rows_per_gpu": total_rows_rank, "partitions_per_gpu": parts,
                        "rows_per_partition": rows, "total_rows": total_rows, "groups": len(result_rows),
-                       "strategy": {0: "scan-only", 1: "dense (registers/shared memory)", 2: "global hash table"}[stats["strategy"]],
+                       "strategy": {0: "scan-only", 1: "dense (registers/shared memory)", 2: "global hash table",
+                                    3: "direct-addressed group array (L2 atomics)"}[stats["strategy"]],
                        "l2": "inputs (%.1f GB per GPU) are larger than L2; no flush" % (algo_bytes_rank / 1e9),
                        "merge": "none (1 GPU)" if world == 1 else "NCCL over NVLink inside every step",
                        "jit_ms_first_query": first_stats["jit_ms"]},

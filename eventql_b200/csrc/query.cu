@@ -691,7 +691,7 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
   fit_shape(q, s, plans);
   q.shape = s;
   q.dense = dm;
-  q.stats.strategy = s.dense_global ? 1u : (uint32_t) s.tier;
+  q.stats.strategy = s.dense_global ? 3u : (uint32_t) s.tier;
 
   // ---- kernel text: everything the generated text depends on is summarised in a short signature, so that a repeated
   // execution (the common case: same plan, same partitions) skips spelling and hashing ~300 KB of source

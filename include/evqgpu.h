@@ -332,7 +332,8 @@ typedef struct evqgpu_query_stats {
   uint64_t algorithmic_bytes;    /* payload bytes of the referenced streams */
   uint64_t num_groups;
   uint32_t kernel_launches;      /* device kernels launched by the last execute */
-  uint32_t strategy;             /* 0 scan-only, 1 register/shared-memory low-cardinality, 2 global hash table */
+  uint32_t strategy;             /* 0 scan-only, 1 register/shared-memory low-cardinality, 2 global hash table,
+                                    3 direct-addressed group array in global memory (key tuples spanning a small box) */
   float jit_ms;                  /* NVRTC time spent by evqgpu_query_create (0 when cached) */
   float scan_ms;                 /* summed device time of the scan kernel launches since the last finish
                                     (only with evqgpu_ctx_set_profiling) */

@@ -566,7 +566,7 @@ def test_timeseries_partition_properties(gpu_ctx):
     _sql, plan = T.q_timeseries(T.readings_spec(0), expected_groups=1_440_000)
     per = [run_gpu(gpu_ctx, [p], plan)[0] for p in parts]
     both, stats = run_gpu(gpu_ctx, parts, plan)
-    assert stats["strategy"] == 1            # 2 x 1440 x 1000 key box: the direct-addressed group array, not the hash table
+    assert stats["strategy"] == 3            # 2 x 1440 x 1000 key box: the direct-addressed group array, not the hash table
     assert len(both) == len(per[0]) + len(per[1])
     assert sorted(both) == sorted(per[0] + per[1])
     assert sum(r[2] for r in both) == 2 * n
