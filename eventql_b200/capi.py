@@ -80,7 +80,7 @@ SYMBOLS = [
     "evqgpu_table_write_file", "evqgpu_table_synthesize", "evqgpu_function_lookup", "evqgpu_function_symbol",
     "evqgpu_function_is_aggregate", "evqgpu_query_create", "evqgpu_query_destroy", "evqgpu_query_num_columns",
     "evqgpu_query_column_type", "evqgpu_query_execute", "evqgpu_query_enqueue", "evqgpu_query_finish",
-    "evqgpu_query_num_rows", "evqgpu_query_fetch", "evqgpu_query_order_by", "evqgpu_query_limit", "evqgpu_query_get_stats", "evqgpu_query_kernel_source",
+    "evqgpu_query_num_rows", "evqgpu_query_fetch", "evqgpu_query_order_by", "evqgpu_query_limit", "evqgpu_query_fetch_partial", "evqgpu_query_get_stats", "evqgpu_query_kernel_source",
     "evqgpu_comm_unique_id", "evqgpu_comm_init", "evqgpu_comm_destroy", "evqgpu_query_merge", "evqgpu_debug_generate",
 ]
 
@@ -146,6 +146,7 @@ def lib() -> C.CDLL:
     L.evqgpu_query_fetch.argtypes = [vp, u64, u64, C.POINTER(vp), C.POINTER(u64)]
     L.evqgpu_query_order_by.argtypes = [vp, C.POINTER(SortSpec), u32]
     L.evqgpu_query_limit.argtypes = [vp, u64, u64]
+    L.evqgpu_query_fetch_partial.argtypes = [vp, u64, u64, vp, vp, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
     L.evqgpu_query_get_stats.argtypes = [vp, C.POINTER(QueryStats)]
     L.evqgpu_query_kernel_source.argtypes = [vp]
     L.evqgpu_query_kernel_source.restype = cp
@@ -451,6 +452,20 @@ class Query:
         got = C.c_uint64(0)
         check(lib().evqgpu_query_fetch(self._h, row0, max_rows, ptrs, C.byref(got)))
         return [b[: got.value * w].tobytes() for b, w in zip(bufs, widths)]
+
+    def fetch_partial(self) -> List[tuple]:
+        """The groups as PartialGroupByExpression rows: [(20-byte SHA-1 group key, saved states)] (plan flag QUERY_WIRE)."""
+        n = self.num_rows
+        keys = np.zeros(max(1, n) * 20, dtype=np.uint8)
+        offs = (C.c_uint64 * (n + 1))()
+        got = C.c_uint64(0)
+        need = C.c_uint64(0)
+        check(lib().evqgpu_query_fetch_partial(self._h, 0, n, keys.ctypes.data_as(C.c_void_p), None, 0, offs, C.byref(got), C.byref(need)))
+        data = np.zeros(max(1, need.value), dtype=np.uint8)
+        check(lib().evqgpu_query_fetch_partial(self._h, 0, n, keys.ctypes.data_as(C.c_void_p), data.ctypes.data_as(C.c_void_p), data.nbytes,
+                                               offs, C.byref(got), C.byref(need)))
+        kb, db = keys.tobytes(), data.tobytes()
+        return [(kb[20 * i: 20 * i + 20], db[offs[i]: offs[i + 1]]) for i in range(got.value)]
 
     def order_by(self, specs: Sequence[tuple]):
         """OrderByExpression over the result: [(result column, descending)], most significant first."""

@@ -875,7 +875,7 @@ static std::string gen_group_kernels(const evqgpu_query& q, const KernelShape& s
 
   os << "struct EvqEmitParams { const u64* dense_state; EvqHashTable ht; u64 key_min[EVQ_MAX_KEYS]; u64 key_stride[EVQ_MAX_KEYS]; "
         "u64 key_null_idx[EVQ_MAX_KEYS]; u64 key_range[EVQ_MAX_KEYS]; u64 slots; u64* out_count; u64 out_capacity; "
-        "u8* out_cols[EVQ_MAX_STREAMS]; };\n";
+        "u8* out_cols[EVQ_MAX_STREAMS]; u8* out_sha; u64* out_state; };\n";
   os << "extern \"C\" __global__ void evq_emit(const __grid_constant__ EvqEmitParams E) {\n";
   os << "  const u64 slot = (u64) blockIdx.x * blockDim.x + threadIdx.x;\n  if (slot >= E.slots) return;\n";
   os << "  u64 st[" << std::max(1, nstate) << "];\n  u64 key[" << std::max(1, nk) << "];\n  u32 ktag[" << std::max(1, nk) << "];\n";
@@ -936,6 +936,19 @@ static std::string gen_group_kernels(const evqgpu_query& q, const KernelShape& s
       os << "  evq_store_packed2(E.out_cols[" << i << "] + out_row * 2, " << as_bits(c, ty) << ", " << c.tag << ");\n";
     else
       os << "  evq_store_packed9(E.out_cols[" << i << "] + out_row * 9, " << as_bits(c, ty) << ", " << c.tag << ");\n";
+  }
+  if (q.flags & EVQGPU_QUERY_WIRE) {
+    // PartialGroupByExpression rows: the group key is the SHA-1 of the group expressions' packed stack bytes, last
+    // expression first (groupby.cc:112-135: [8 B value][1 B tag], BOOL [1 B][1 B]); the states travel raw
+    os << "  {\n    u8 msg[" << std::max(1, 9 * nk) << "];\n    u32 len = 0;\n";
+    for (int i = nk; i-- > 0;) {
+      if (q.group[i]->type == EVQ_BOOL)
+        os << "    msg[len++] = (u8) (key[" << i << "] != 0ull);\n    msg[len++] = (u8) ktag[" << i << "];\n";
+      else
+        os << "    for (int b = 0; b < 8; ++b) msg[len++] = (u8) (key[" << i << "] >> (8 * b));\n    msg[len++] = (u8) ktag[" << i << "];\n";
+    }
+    os << "    evq_sha1(msg, len, E.out_sha + out_row * 20);\n  }\n";
+    for (int s = 0; s < nstate; ++s) os << "  E.out_state[out_row * " << nstate << " + " << s << "] = st[" << s << "];\n";
   }
   os << "  (void) err;\n}\n";
   return os.str();

@@ -608,6 +608,44 @@ __device__ __forceinline__ void evq_state_atomic(u64* addr, u64 v) {
   }
 }
 
+// SHA-1 (FIPS 180-4) of a short message (< 120 bytes: at most two blocks): the group key of the partial-aggregation wire
+// format (util/SHA1.cc is what the reference calls)
+__device__ __forceinline__ u32 evq_rotl(u32 x, int n) { return (x << n) | (x >> (32 - n)); }
+__device__ void evq_sha1(const u8* msg, u32 len, u8* out) {
+  u32 h0 = 0x67452301u, h1 = 0xefcdab89u, h2 = 0x98badcfeu, h3 = 0x10325476u, h4 = 0xc3d2e1f0u;
+  const u32 nblocks = len < 56u ? 1u : 2u;
+  for (u32 blk = 0; blk < nblocks; ++blk) {
+    u32 w[80];
+    for (u32 i = 0; i < 16; ++i) {
+      u32 word = 0;
+      for (u32 b = 0; b < 4; ++b) {
+        const u32 pos = blk * 64u + i * 4u + b;
+        u32 byte = 0;
+        if (pos < len) byte = msg[pos];
+        else if (pos == len) byte = 0x80u;
+        word = (word << 8) | byte;
+      }
+      w[i] = word;
+    }
+    if (blk == nblocks - 1u) { w[14] = 0u; w[15] = len * 8u; }
+    for (u32 i = 16; i < 80; ++i) w[i] = evq_rotl(w[i - 3] ^ w[i - 8] ^ w[i - 14] ^ w[i - 16], 1);
+    u32 a = h0, b = h1, c = h2, d = h3, e = h4;
+    for (u32 i = 0; i < 80; ++i) {
+      u32 f, k;
+      if (i < 20) { f = (b & c) | (~b & d); k = 0x5a827999u; }
+      else if (i < 40) { f = b ^ c ^ d; k = 0x6ed9eba1u; }
+      else if (i < 60) { f = (b & c) | (b & d) | (c & d); k = 0x8f1bbcdcu; }
+      else { f = b ^ c ^ d; k = 0xca62c1d6u; }
+      const u32 t = evq_rotl(a, 5) + f + e + k + w[i];
+      e = d; d = c; c = evq_rotl(b, 30); b = a; a = t;
+    }
+    h0 += a; h1 += b; h2 += c; h3 += d; h4 += e;
+  }
+  const u32 h[5] = {h0, h1, h2, h3, h4};
+  for (u32 i = 0; i < 5; ++i)
+    for (u32 b = 0; b < 4; ++b) out[4 * i + b] = (u8) (h[i] >> (24 - 8 * b));
+}
+
 // ---- expression helpers (semantics of sql/expressions/math.cc, boolean.cc, conversion.cc) ------------------------------
 
 __device__ __forceinline__ u64 evq_div_u64(u64 a, u64 b, u32& err) {

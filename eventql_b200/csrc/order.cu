@@ -83,6 +83,7 @@ static void rewrite_rows(evqgpu_query& q, const u32* perm, uint64_t first, uint6
   }
   q.num_rows_out = n;
   q.out_capacity = n;
+  q.reordered = true;
 }
 
 }  // namespace evq

@@ -639,6 +639,12 @@ void emit_results(evqgpu_query& q) {
   ep.out_count = q.out_count.as<u64>();
   ep.out_capacity = out_cap;
   for (size_t i = 0; i < q.select.size(); ++i) ep.out_cols[i] = q.out_cols[i].as<u8>();
+  if (q.flags & EVQGPU_QUERY_WIRE) {
+    ensure(q.out_sha, out_cap * 20 + 16);
+    ensure(q.out_state, out_cap * std::max<size_t>(1, q.state_ops.size()) * 8 + 16);
+    ep.out_sha = q.out_sha.as<u8>();
+    ep.out_state = q.out_state.as<u64>();
+  }
   void* args[] = {&ep};
   launch(ctx, q.module->kernels.at("evq_emit"), dim3((unsigned) ((emit_slots + 255) / 256)), dim3(256), 0, args);
   q.stats.kernel_launches++;
@@ -804,6 +810,7 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
     q.emit.key_range[i] = dm.key_range[i];
   }
   q.emit.slots = emit_slots;
+  q.reordered = false;
   q.emitted = false;
   if (!((q.flags & EVQGPU_QUERY_PARTIAL) && ctx->nranks > 1)) emit_results(q);
   (void) sync;

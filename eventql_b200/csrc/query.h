@@ -79,6 +79,8 @@ struct EmitParams {
   u64* out_count;
   u64 out_capacity;
   u8* out_cols[EVQ_MAX_STREAMS];
+  u8* out_sha;            // EVQGPU_QUERY_WIRE: 20-byte SHA-1 of every group's key tuple bytes (groupby.cc:129-135)
+  u64* out_state;         // EVQGPU_QUERY_WIRE: the raw aggregate state words of every group [rows][nstate]
 };
 
 struct InitParams {
@@ -138,6 +140,8 @@ struct evqgpu_query {
   evq::DevBuf merge_recv, merge_send, merge_slots, merge_counts;
   evq::DevBuf dense_state, ht_slots, status, counters, out_count, tile_counts, tile_base;
   std::vector<evq::DevBuf> out_cols;
+  evq::DevBuf out_sha, out_state;   // EVQGPU_QUERY_WIRE (PartialGroupByExpression rows)
+  bool reordered = false;           // ORDER BY / LIMIT rewrote the result rows (the per-group side buffers no longer line up)
   uint64_t out_capacity = 0;
   uint64_t ht_cap = 0;
 

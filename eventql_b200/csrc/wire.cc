@@ -1,0 +1,114 @@
+// wire.cc - evqgpu_query_fetch_partial: the groups of an aggregate plan as the rows the reference's
+// PartialGroupByExpression::nextBatch produces (sql/statements/select/groupby.cc:411-445), i.e. what a shard of a cluster
+// query sends to GroupByMergeExpression (groupby.cc:553-615) and writes to its query cache (groupby.cc:379-405).
+//
+// The device side (evq_emit with EVQGPU_QUERY_WIRE, csrc/codegen.cc) leaves three things per group in HBM: the packed
+// result columns, the SHA-1 of the key tuple and the raw aggregate state words.  Here they are copied to the host and
+// spelled in the reference's serialisation: varuints (util/io/outputstream.cc appendVarUInt) for count / sum, the raw
+// structs of the extension aggregates (oracle/ref_tools/ext_aggregates.cc), SValue::encode (svalue.cc:306-309) for items
+// that are not aggregates.
+#include <string.h>
+
+#include <vector>
+
+#include "query.h"
+
+namespace evq {
+void finish_query(evqgpu_query& q);
+
+static void put_varuint(std::vector<uint8_t>& out, uint64_t v) {   // OutputStream::appendVarUInt: LEB128
+  do {
+    uint8_t b = v & 0x7f;
+    v >>= 7;
+    if (v) b |= 0x80;
+    out.push_back(b);
+  } while (v);
+}
+
+static void put_raw(std::vector<uint8_t>& out, const void* p, size_t n) {
+  const uint8_t* b = (const uint8_t*) p;
+  out.insert(out.end(), b, b + n);
+}
+
+}  // namespace evq
+
+using namespace evq;
+
+extern "C" int evqgpu_query_fetch_partial(evqgpu_query* q, uint64_t row0, uint64_t max_rows, void* keys, void* data, uint64_t data_cap,
+                                          uint64_t* data_offsets, uint64_t* nrows_out, uint64_t* data_bytes_out) {
+  return guarded([&] {
+    if (!q || !keys || !data_offsets || !nrows_out || !data_bytes_out) fail(EVQGPU_ERR_ARG, "evqgpu_query_fetch_partial: null argument");
+    if (!(q->flags & EVQGPU_QUERY_WIRE) || !(q->flags & EVQGPU_QUERY_GROUPBY))
+      fail(EVQGPU_ERR_ARG, "evqgpu_query_fetch_partial: the plan was not created with EVQGPU_QUERY_GROUPBY | EVQGPU_QUERY_WIRE");
+    if (q->pending) finish_query(*q);
+    if (!q->emitted) fail(EVQGPU_ERR_ARG, "evqgpu_query_fetch_partial: the partial results of a multi-rank job are merged, not fetched");
+    if (q->reordered) fail(EVQGPU_ERR_ARG, "evqgpu_query_fetch_partial after ORDER BY / LIMIT: the key hashes no longer match the rows");
+    for (const auto& item : q->select)
+      if (item.agg && item.agg->info().fn == Fn::COUNT_DISTINCT)
+        fail(EVQGPU_ERR_UNSUPPORTED, "count_distinct keeps no value sets: its partial state cannot be serialised");
+    use_device(q->ctx);
+    uint64_t n = 0;
+    if (row0 < q->num_rows_out) n = std::min<uint64_t>(max_rows, q->num_rows_out - row0);
+    *nrows_out = n;
+    data_offsets[0] = 0;
+    *data_bytes_out = 0;
+    if (n == 0) return;
+    const size_t nstate = std::max<size_t>(1, q->state_ops.size());
+    std::vector<uint64_t> st(n * nstate);
+    std::vector<std::vector<uint8_t>> cols(q->select.size());
+    cudaStream_t s = q->ctx->stream;
+    EVQ_CUDA(cudaMemcpyAsync(keys, q->out_sha.as<u8>() + row0 * 20, n * 20, cudaMemcpyDeviceToHost, s));
+    EVQ_CUDA(cudaMemcpyAsync(st.data(), q->out_state.as<u64>() + row0 * nstate, n * nstate * 8, cudaMemcpyDeviceToHost, s));
+    for (size_t i = 0; i < q->select.size(); ++i) {
+      if (q->select[i].agg) continue;
+      const uint64_t w = q->select[i].expr->type == EVQ_BOOL ? 2 : 9;
+      cols[i].resize(n * w);
+      EVQ_CUDA(cudaMemcpyAsync(cols[i].data(), q->out_cols[i].as<u8>() + row0 * w, n * w, cudaMemcpyDeviceToHost, s));
+    }
+    EVQ_CUDA(cudaStreamSynchronize(s));
+    std::vector<uint8_t> out;
+    out.reserve(n * 32);
+    for (uint64_t r = 0; r < n; ++r) {
+      const uint64_t* g = &st[r * nstate];
+      for (size_t i = 0; i < q->select.size(); ++i) {
+        const SelectItem& item = q->select[i];
+        if (!item.agg) {   // SValue::encode: type, length, packed value
+          const uint64_t w = item.expr->type == EVQ_BOOL ? 2 : 9;
+          out.push_back((uint8_t) item.expr->type);
+          put_varuint(out, w);
+          put_raw(out, &cols[i][r * w], w);
+          continue;
+        }
+        const FnInfo& fi = item.agg->info();
+        const uint64_t s0 = item.state0 >= 0 ? g[item.state0] : 0;
+        const uint64_t seen = item.state_seen >= 0 ? g[item.state_seen] : 0;
+        switch (fi.fn) {
+          case Fn::COUNT: put_varuint(out, g[0]); break;                               // count_save
+          case Fn::SUM:
+            if (fi.ret == EVQ_FLOAT64) put_raw(out, &s0, 8);                           // SumF64::save
+            else put_varuint(out, s0);                                                 // sum_uint64_save / sum_int64_save
+            break;
+          case Fn::MIN:
+          case Fn::MAX: {                                                              // MinMaxState {value, seen}
+            const uint64_t have = seen ? 1 : 0, v = have ? s0 : 0;
+            put_raw(out, &v, 8);
+            put_raw(out, &have, 8);
+            break;
+          }
+          case Fn::MEAN: {                                                             // MeanState {double sum, n}
+            double sum;
+            if (item.state_carry >= 0) sum = (double) g[item.state_carry] * 18446744073709551616.0 + (double) s0;
+            else memcpy(&sum, &s0, 8);
+            put_raw(out, &sum, 8);
+            put_raw(out, &seen, 8);
+            break;
+          }
+          default: fail(EVQGPU_ERR_UNSUPPORTED, "aggregate %s has no partial state format", fi.symbol.c_str());
+        }
+      }
+      data_offsets[r + 1] = out.size();
+    }
+    *data_bytes_out = out.size();
+    if (data && out.size() <= data_cap) memcpy(data, out.data(), out.size());
+  });
+}

@@ -9,6 +9,8 @@
 //   evqgpu_sql count <file.cst> <column>              select count(1), sum(c), min(c), max(c), mean(c) ... where c > 0
 //   evqgpu_sql scan  <file.cst> <column>              select <column> from t        (FastCSTableScan alone)
 //   evqgpu_sql scanf <file.cst> <column> <m>          the same with setFilter(row % m == 0)   (LSM visibility filter)
+//   evqgpu_sql partial <file.cst> <column>            select c, count(1), sum(c) from t where c >= 0 group by c   as
+//                                                     PartialGroupByExpression rows: hex key ; hex saved states
 //   evqgpu_sql top   <file.cst> <column> <limit> <offset>
 //                                                     select c, count(1), sum(c) from t where c >= 0 group by c
 //                                                     order by c desc limit <limit> offset <offset>
@@ -142,6 +144,38 @@ int main(int argc, char** argv) {
       for (uint64_t i = 0; i < nrows; ++i) keep[i] = m && i % m == 0;
       gs->setFilter(std::move(keep));
       return pull(te.get());
+    }
+    if (mode == "partial" && argc >= 4) {
+      std::vector<std::pair<std::string, SType>> in = {{argv[3], U}};
+      auto scan = std::make_shared<SequentialScanNode>("t", in, std::vector<SelectRef>{sel(col(0))}, cmp("gte", col(0), u(0)));
+      std::vector<SelectRef> gsel = {sel(col(0)), sel(count1()), sel(agg("sum", col(0)))};
+      auto node = std::make_shared<GroupByNode>(gsel, std::vector<ExprRef>{col(0)}, scan);
+      GpuPartialGroupByExpression te(&gpu, node, {argv[2]});
+      ReturnCode rc = te.execute();
+      if (!rc.isSuccess()) { printf("ERROR!\n%s\n", rc.getMessage().c_str()); return 1; }
+      std::vector<SVector> cols;
+      cols.emplace_back(SType::STRING);
+      cols.emplace_back(SType::STRING);
+      for (;;) {
+        for (auto& c : cols) c.clear();
+        size_t n = 0;
+        rc = te.nextBatch(cols.data(), &n);
+        if (!rc.isSuccess()) { printf("ERROR!\n%s\n", rc.getMessage().c_str()); return 1; }
+        if (n == 0) break;
+        const uint8_t* p[2] = {(const uint8_t*) cols[0].getData(), (const uint8_t*) cols[1].getData()};
+        for (size_t r = 0; r < n; ++r) {
+          std::string line;
+          for (int c = 0; c < 2; ++c) {
+            uint32_t len; memcpy(&len, p[c], 4);
+            char buf[4];
+            for (uint32_t i = 0; i < len; ++i) { snprintf(buf, sizeof(buf), "%02x", p[c][4 + i]); line += buf; }
+            p[c] += 4 + len + 1;
+            if (c == 0) line += ";";
+          }
+          puts(line.c_str());
+        }
+      }
+      return 0;
     }
     if (mode == "top" && argc >= 6) {
       GpuTableProvider provider(&gpu, "t", {argv[2]});

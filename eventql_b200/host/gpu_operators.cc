@@ -244,7 +244,7 @@ ReturnCode GpuGroupByExpression::execute() {
     evqgpu_query_desc d;
     memset(&d, 0, sizeof(d));
     d.struct_size = sizeof(d);
-    d.flags = EVQGPU_QUERY_GROUPBY | (node_->isPartialAggregation() ? EVQGPU_QUERY_PARTIAL : 0);
+    d.flags = EVQGPU_QUERY_GROUPBY | (node_->isPartialAggregation() ? EVQGPU_QUERY_PARTIAL : 0) | extra_flags_;
     d.num_input_columns = (uint32_t) names.size();
     d.input_columns = names.data();
     d.where = where.view();
@@ -256,6 +256,43 @@ ReturnCode GpuGroupByExpression::execute() {
   } catch (const std::exception& e) {
     return ReturnCode::error("ERUNTIME", e.what());
   }
+}
+
+// ---- PartialGroupByExpression rows ----------------------------------------------------------------------------------------
+
+GpuPartialGroupByExpression::GpuPartialGroupByExpression(GpuContext* gpu, std::shared_ptr<GroupByNode> node,
+                                                         std::vector<std::string> partition_files)
+    : GpuGroupByExpression(gpu, std::move(node), std::move(partition_files)) {
+  extra_flags_ = EVQGPU_QUERY_WIRE;
+}
+
+ReturnCode GpuPartialGroupByExpression::nextBatch(SVector* columns, size_t* len) {
+  *len = 0;
+  if (!query_) return ReturnCode::error("ERUNTIME", "nextBatch before execute");
+  if (cursor_ >= num_rows_) return ReturnCode::success();
+  std::vector<uint8_t> keys(kOutputBatchSize * 20), data(kOutputBatchSize * 64);
+  std::vector<uint64_t> offs(kOutputBatchSize + 1);
+  uint64_t got = 0, need = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    if (evqgpu_query_fetch_partial(query_, cursor_, kOutputBatchSize, keys.data(), data.data(), data.size(), offs.data(), &got, &need) != EVQGPU_OK)
+      return ReturnCode::error("ERUNTIME", lastError());
+    if (need <= data.size()) break;
+    data.resize(need);
+  }
+  for (uint64_t r = 0; r < got; ++r) {   // copyString (svalue.cc:1097-1102): [u32 length][bytes][tag]
+    const uint8_t tag = 0;
+    uint32_t n = 20;
+    columns[0].append(&n, 4);
+    columns[0].append(&keys[r * 20], 20);
+    columns[0].append(&tag, 1);
+    n = (uint32_t) (offs[r + 1] - offs[r]);
+    columns[1].append(&n, 4);
+    columns[1].append(&data[offs[r]], n);
+    columns[1].append(&tag, 1);
+  }
+  cursor_ += got;
+  *len = (size_t) got;
+  return ReturnCode::success();
 }
 
 // ---- provider / scheduler hooks ----------------------------------------------------------------------------------------

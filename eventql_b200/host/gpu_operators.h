@@ -83,8 +83,20 @@ class GpuGroupByExpression : public GpuQueryExpression {
 public:
   GpuGroupByExpression(GpuContext* gpu, std::shared_ptr<csql::GroupByNode> node, std::vector<std::string> partition_files);
   csql::ReturnCode execute() override;
-private:
+protected:
   std::shared_ptr<csql::GroupByNode> node_;
+  uint32_t extra_flags_ = 0;
+};
+
+// PartialGroupByExpression (sql/statements/select/groupby.h:66-100, groupby.cc:223-472): the shard side of a cluster
+// GROUP BY.  Same fused device pass, but the rows are (STRING 20-byte SHA-1 group key, STRING saved states) - what
+// GroupByMergeExpression (groupby.cc:553-615) on a coordinator, CPU or GPU, loads and merges.
+class GpuPartialGroupByExpression : public GpuGroupByExpression {
+public:
+  GpuPartialGroupByExpression(GpuContext* gpu, std::shared_ptr<csql::GroupByNode> node, std::vector<std::string> partition_files);
+  csql::ReturnCode nextBatch(csql::SVector* columns, size_t* len) override;
+  size_t getColumnCount() const override { return 2; }
+  csql::SType getColumnType(size_t) const override { return csql::SType::STRING; }
 };
 
 // OrderByExpression (sql/statements/select/orderby.h:34-66, orderby.cc:58-160) over a device-resident result: the sort

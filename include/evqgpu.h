@@ -269,6 +269,8 @@ EVQGPU_API int evqgpu_function_is_aggregate(int function_id);
 
 #define EVQGPU_QUERY_GROUPBY 1u       /* aggregate plan: select items are GroupByNode select expressions */
 #define EVQGPU_QUERY_PARTIAL 2u       /* results stay as mergeable partials until evqgpu_query_merge */
+#define EVQGPU_QUERY_WIRE 4u          /* aggregate plan whose groups are fetched in the reference's partial-aggregation row format
+                                         (evqgpu_query_fetch_partial): group key hashes and raw states are kept besides the rows */
 
 typedef struct evqgpu_query_desc {
   uint32_t struct_size;                 /* sizeof(evqgpu_query_desc) */
@@ -308,6 +310,21 @@ EVQGPU_API int evqgpu_query_num_rows(evqgpu_query* q, uint64_t* out);
  * Group order is unspecified, like the reference's. */
 EVQGPU_API int evqgpu_query_fetch(evqgpu_query* q, uint64_t row0, uint64_t max_rows, void* const* columns,
                                   uint64_t* nrows_out);
+
+/* The groups of an executed EVQGPU_QUERY_WIRE plan as the rows csql::PartialGroupByExpression::nextBatch produces
+ * (sql/statements/select/groupby.cc:411-445) - what a shard of a cluster query returns to GroupByMergeExpression
+ * (groupby.cc:553-615) and stores in its query cache:
+ *   keys:  20 bytes per group, SHA-1 of the group expressions' packed values and tags, last expression first
+ *          (groupby.cc:112-135);
+ *   data:  per group the select items in order - an aggregate item as its function's saved state (count / sum: varuint,
+ *          aggregate.cc:52-58, 200-206; the extension aggregates min / max {value, seen}, mean {double sum, count},
+ *          sum<float64> raw, oracle/ref_tools/ext_aggregates.cc), any other item as SValue::encode (svalue.cc:306-309:
+ *          type byte, length, packed value);  data_offsets[i] .. data_offsets[i + 1] is group i's slice.
+ * Groups [row0, row0 + max_rows); *nrows_out = groups written, *data_bytes_out = bytes needed (nothing is written when
+ * data_cap is too small).  count_distinct keeps no value sets and is refused. */
+EVQGPU_API int evqgpu_query_fetch_partial(evqgpu_query* q, uint64_t row0, uint64_t max_rows, void* keys, void* data,
+                                          uint64_t data_cap, uint64_t* data_offsets, uint64_t* nrows_out,
+                                          uint64_t* data_bytes_out);
 
 /* ORDER BY over the result rows of an executed (and, for multi-rank jobs, merged) query, on the device:
  * csql::OrderByExpression (sql/statements/select/orderby.cc:58-160) with sort expressions that are columns of the

@@ -822,6 +822,108 @@ def run_query_on(inputs: Sequence[Vec], n: int, plan: P.QueryPlan, row_filter: O
     return Result(types, out_cols, ng, n, m)
 
 
+def _varuint(v: int) -> bytes:
+    """OutputStream::appendVarUInt (util/io/outputstream.cc): unsigned LEB128."""
+    out = bytearray()
+    v &= (1 << 64) - 1
+    while True:
+        b = v & 0x7F
+        v >>= 7
+        if v:
+            out.append(b | 0x80)
+        else:
+            out.append(b)
+            return bytes(out)
+
+
+def run_partial_query(tables: Sequence[CSTableFile], plan: P.QueryPlan) -> List[Tuple[bytes, bytes]]:
+    """PartialGroupByExpression (sql/statements/select/groupby.cc:223-472), the shard side of a cluster GROUP BY: one row per
+    group, (key, data).  key = SHA-1 of the group expressions' packed stack bytes, last expression first (groupby.cc:112-135:
+    [8 B value][1 B tag], BOOL [1 B][1 B]).  data = the select items in order: an aggregate item as its function's saved
+    state (count / sum_uint64 / sum_int64: varuint, aggregate.cc:52-58, 200-206; min / max {value, seen}, mean {double sum,
+    n}, sum<float64> raw: oracle/ref_tools/ext_aggregates.cc), any other item as SValue::encode (svalue.cc:306-309)."""
+    import hashlib
+    import struct
+    if not plan.is_groupby:
+        raise OracleError("partial aggregation needs an aggregate plan")
+    inputs, n = load_inputs(tables, plan.input_columns)
+    if plan.where is not None:
+        keep = eval_expr(plan.where, inputs, n).values.astype(bool)
+    else:
+        keep = np.ones(n, dtype=bool)
+    sel = np.flatnonzero(keep)
+    m = len(sel)
+    if m == 0:
+        return []
+    finputs = [_take(v, sel) for v in inputs]
+    keys = [eval_expr(g, finputs, m) for g in plan.group]
+    if keys:
+        sort_cols = []
+        for k in keys:
+            sort_cols.append(k.tags)
+            sort_cols.append(k.bits64())
+        order = np.lexsort(sort_cols[::-1])
+        boundary = np.zeros(m, dtype=bool)
+        boundary[0] = True
+        for c in sort_cols:
+            cs = c[order]
+            boundary[1:] |= cs[1:] != cs[:-1]
+        starts = np.flatnonzero(boundary)
+    else:
+        order = np.arange(m)
+        starts = np.array([0])
+    ng = len(starts)
+    sinputs = [_take(v, order) for v in finputs]
+    gkeys = [_take(_take(k, order), starts) for k in keys]
+
+    def packed(v: Vec, i: int) -> bytes:
+        if v.type == P.BOOL:
+            return bytes([1 if v.values[i] else 0, int(v.tags[i])])
+        return struct.pack("<Q", int(v.bits64()[i])) + bytes([int(v.tags[i])])
+
+    items = []                                   # per select item: list of ng byte strings
+    counts = np.diff(np.append(starts, m)).astype(np.uint64)
+    for s in plan.select:
+        agg = P.find_aggregate(s)
+        if agg is None:
+            col = _take(eval_expr(s, sinputs, m), starts)
+            enc = []
+            for i in range(ng):
+                b = packed(col, i)
+                enc.append(bytes([col.type]) + _varuint(len(b)) + b)
+            items.append(enc)
+            continue
+        name = agg.name
+        if name == "count":
+            items.append([_varuint(int(c)) for c in counts])
+            continue
+        if name == "count_distinct":
+            raise OracleError("count_distinct: the value sets are not restated here")
+        arg = eval_expr(agg.args[0], sinputs, m)
+        present = (arg.tags & 1) == 0
+        npres = np.add.reduceat(present.astype(np.uint64), starts)
+        res = _aggregate(name, agg.type, arg, starts, m)
+        if name == "sum":
+            if agg.type == P.FLOAT64:
+                items.append([struct.pack("<d", float(x)) for x in res.values])
+            else:
+                items.append([_varuint(int(x)) for x in res.bits64()])
+        elif name in ("min", "max"):
+            bits = res.bits64()
+            items.append([struct.pack("<QQ", int(bits[i]) if npres[i] else 0, 1 if npres[i] else 0) for i in range(ng)])
+        elif name == "mean":
+            with np.errstate(all="ignore"):
+                sums = np.add.reduceat(np.where(present, arg.values.astype(np.float64), 0.0), starts)
+            items.append([struct.pack("<dQ", float(sums[i]), int(npres[i])) for i in range(ng)])
+        else:
+            raise OracleError("unknown aggregate %s" % name)
+    out = []
+    for i in range(ng):
+        kb = b"".join(packed(k, i) for k in reversed(gkeys))
+        out.append((hashlib.sha1(kb).digest(), b"".join(it[i] for it in items)))
+    return out
+
+
 def _aggregate(name: str, rtype: int, arg: Optional[Vec], starts: np.ndarray, m: int) -> Vec:
     ng = len(starts)
     zt = np.zeros(ng, dtype=np.uint8)

@@ -27,6 +27,12 @@
 #include <eventql/sql/result_cursor.h>
 #include <eventql/sql/query_plan.h>
 #include <eventql/sql/svalue.h>
+#include <eventql/sql/scheduler.h>
+#include <eventql/sql/transaction.h>
+#include <eventql/sql/runtime/compiler.h>
+#include <eventql/sql/qtree/GroupByNode.h>
+#include <eventql/sql/statements/select/groupby.h>
+#include <eventql/util/SHA1.h>
 #include <eventql/io/cstable/cstable_writer.h>
 #include <eventql/io/cstable/cstable_reader.h>
 #include <eventql/io/cstable/TableSchema.h>
@@ -39,7 +45,7 @@ void registerExtensionAggregates(csql::SymbolTable* sym);
 static int usage() {
   fprintf(stderr,
       "usage:\n"
-      "  evqlref sql [-t name=file.cst]... [-n reps] [-x] -q 'SQL'\n"
+      "  evqlref sql [-t name=file.cst]... [-n reps] [-x] [-P] -q 'SQL'\n"
       "      -x  do NOT register the extension aggregates (min/max/mean/sum<float64>)\n"
       "  evqlref write <out.cst> <v1|v2> <nrows> <name>:<uint|datetime|float|bool>:<encoding>:<optional 0|1>:<datafile>[:<nullfile>] ...\n"
       "      datafile = nrows x 8 B little-endian (u64 / double bits / 0|1); nullfile = nrows x 1 B (1 = NULL)\n"
@@ -86,11 +92,48 @@ static std::string fmtValue(csql::SType type, const void* data) {
   return "?";
 }
 
+// `sql -P`: every GROUP BY of the plan runs as the reference's PartialGroupByExpression (the shard side of a cluster query,
+// sql/statements/select/groupby.cc:223-472) instead of GroupByExpression; its rows are (20-byte group key, saved states),
+// printed as hex.  This is what a shard puts on the wire and into the query cache.
+class PartialScheduler : public csql::DefaultScheduler {
+protected:
+  ScopedPtr<csql::TableExpression> buildGroupByExpression(
+      csql::Transaction* txn,
+      csql::ExecutionContext* execution_context,
+      RefPtr<csql::GroupByNode> node) override {
+    Vector<csql::ValueExpression> select_expressions;
+    Vector<csql::ValueExpression> group_expressions;
+    for (const auto& slnode : node->selectList()) {
+      select_expressions.emplace_back(txn->getCompiler()->buildValueExpression(txn, slnode->expression()));
+    }
+    for (const auto& e : node->groupExpressions()) {
+      group_expressions.emplace_back(txn->getCompiler()->buildValueExpression(txn, e));
+    }
+    return mkScoped(
+        new csql::PartialGroupByExpression(
+            txn,
+            std::move(select_expressions),
+            std::move(group_expressions),
+            SHA1::compute(std::string("evqlref")),
+            buildTableExpression(txn, execution_context, node->inputTable().asInstanceOf<csql::TableExpressionNode>())));
+  }
+};
+
+static std::string hexString(const void* data) {
+  const uint8_t* p = (const uint8_t*) data;
+  uint32_t len; memcpy(&len, p, 4);
+  static const char* digits = "0123456789abcdef";
+  std::string out;
+  for (uint32_t i = 0; i < len; ++i) { out += digits[p[4 + i] >> 4]; out += digits[p[4 + i] & 15]; }
+  return out;
+}
+
 static int cmdSql(int argc, char** argv) {
   std::vector<std::pair<std::string, std::string>> tables;
   std::string query;
   int reps = 1;
   bool ext = true;
+  bool partial = false;
   for (int i = 0; i < argc; ++i) {
     std::string a = argv[i];
     if (a == "-t" && i + 1 < argc) {
@@ -104,6 +147,8 @@ static int cmdSql(int argc, char** argv) {
       reps = atoi(argv[++i]);
     } else if (a == "-x") {
       ext = false;
+    } else if (a == "-P") {
+      partial = true;
     } else {
       return usage();
     }
@@ -113,6 +158,9 @@ static int cmdSql(int argc, char** argv) {
   auto runtime = csql::Runtime::getDefaultRuntime();
   if (ext) {
     evqlref::registerExtensionAggregates(runtime->symbols());
+  }
+  if (partial) {
+    runtime->setScheduler(mkScoped<csql::Scheduler>(new PartialScheduler()));
   }
 
   for (int rep = 0; rep < reps; ++rep) {
@@ -146,7 +194,8 @@ static int cmdSql(int argc, char** argv) {
           std::string line;
           for (size_t i = 0; i < ncols; ++i) {
             if (i) line += ";";
-            line += fmtValue(cursor->getColumnType(i), cursor->getColumnData(i));
+            if (partial && cursor->getColumnType(i) == csql::SType::STRING) line += hexString(cursor->getColumnData(i));
+            else line += fmtValue(cursor->getColumnType(i), cursor->getColumnData(i));
           }
           puts(line.c_str());
         }

@@ -336,6 +336,97 @@ def orderby_cases():
     return out
 
 
+def partial_cases():
+    """Partial aggregation (PartialGroupByExpression rows) over the mixed golden table: [(case, sql, plan)]; the plans carry
+    QUERY_WIRE.  Every referenced column also appears in WHERE."""
+    spec = GOLDEN_TABLES["mixed"][0]()
+    c, names = cols_of(spec)
+    cnt = P.call("count", P.lit(1))
+    W = P.QUERY_GROUPBY | P.QUERY_WIRE
+    out = []
+    out.append(("pa_null_key", "select k, count(1), sum(b) from t where b >= 0 and k >= 0 group by k;",
+                P.QueryPlan(names, [c["k"], cnt, P.call("sum", c["b"])], where=(c["b"] >= 0) & (c["k"] >= 0), group=[c["k"]], flags=W)))
+    k0, k1 = c["b"] % 3, c["d"] % 2
+    out.append(("pa_two_keys_all_aggs",
+                "select b % 3, d % 2, count(1), sum(c), min(c), max(c), mean(c), sum(f), min(f), mean(f) from t "
+                "where b >= 0 and c >= 0 and d >= 0 and f >= 0.0 group by b % 3, d % 2;",
+                P.QueryPlan(names, [k0, k1, cnt, P.call("sum", c["c"]), P.call("min", c["c"]), P.call("max", c["c"]), P.call("mean", c["c"]),
+                                    P.call("sum", c["f"]), P.call("min", c["f"]), P.call("mean", c["f"])],
+                            where=(c["b"] >= 0) & (c["c"] >= 0) & (c["d"] >= 0) & (c["f"] >= 0.0), group=[k0, k1], flags=W)))
+    out.append(("pa_global", "select count(1), sum(b) from t where b >= 0;",
+                P.QueryPlan(names, [cnt, P.call("sum", c["b"])], where=c["b"] >= 0, flags=W)))
+    out.append(("pa_bool_key", "select bo, count(1), max(a) from t where b >= 0 and a >= 0 group by bo;",
+                P.QueryPlan(names, [c["bo"], cnt, P.call("max", c["a"])], where=(c["b"] >= 0) & (c["a"] >= 0), group=[c["bo"]], flags=W)))
+    sk = P.call("to_int64", c["b"]) - 50
+    out.append(("pa_int64_key", "select to_int64(b) - 50, count(1), sum(to_int64(b) - 50) from t where b < 9 group by to_int64(b) - 50;",
+                P.QueryPlan(names, [sk, cnt, P.call("sum", sk)], where=c["b"] < 9, group=[sk], flags=W)))
+    out.append(("pa_many_groups_key_not_selected", "select count(1), sum(c), mean(b) from t where d >= 0 and c >= 0 and b >= 0 group by d;",
+                P.QueryPlan(names, [cnt, P.call("sum", c["c"]), P.call("mean", c["b"])], where=(c["d"] >= 0) & (c["c"] >= 0) & (c["b"] >= 0),
+                            group=[c["d"]], flags=W)))
+    return out
+
+
+def parse_partial_data(plan, data: bytes):
+    """The saved states of one PartialGroupByExpression row as python values (floats stay floats: they are compared with the
+    1e-9 tolerance, the summation order differs), following the select items of the plan."""
+    import struct
+    pos = 0
+
+    def varuint():
+        nonlocal pos
+        v, sh = 0, 0
+        while True:
+            b = data[pos]
+            pos += 1
+            v |= (b & 0x7F) << sh
+            sh += 7
+            if not b & 0x80:
+                return v
+
+    out = []
+    for s in plan.select:
+        agg = P.find_aggregate(s)
+        if agg is None:
+            t = data[pos]
+            pos += 1
+            n = varuint()
+            raw = data[pos: pos + n]
+            pos += n
+            out.append((t, raw.hex()))
+        elif agg.name in ("count",) or (agg.name == "sum" and agg.type != P.FLOAT64):
+            out.append(varuint())
+        elif agg.name == "sum":
+            out.append(struct.unpack_from("<d", data, pos)[0])
+            pos += 8
+        elif agg.name in ("min", "max"):
+            v, seen = struct.unpack_from("<QQ", data, pos)
+            pos += 16
+            out.append(struct.unpack("<d", struct.pack("<Q", v))[0] if agg.type == P.FLOAT64 else v)
+            out.append(seen)
+        elif agg.name == "mean":
+            sm, n = struct.unpack_from("<dQ", data, pos)
+            pos += 16
+            out.append(sm)
+            out.append(n)
+        else:
+            raise ValueError(agg.name)
+    assert pos == len(data), (pos, len(data))
+    return tuple(out)
+
+
+def partial_rows_equal(plan, got, want):
+    """[(key, data)] against [(key, data)] as sets of groups: keys exact, states exact except floats (1e-9 relative)."""
+    a = sorted((k.hex(),) + parse_partial_data(plan, d) for k, d in got)
+    b = sorted((k.hex(),) + parse_partial_data(plan, d) for k, d in want)
+    if [r[0] for r in a] != [r[0] for r in b]:
+        return False, "group keys differ (%d vs %d groups)" % (len(a), len(b))
+    for ra, rb in zip(a, b):
+        ok, why = rows_equal([ra[1:]], [rb[1:]])
+        if not ok:
+            return False, "group %s: %s" % (ra[0], why)
+    return True, ""
+
+
 def rows_digest(rows, types, ordered):
     """sha256 over the exact (non-float) columns of the rows; GROUP BY results are sorted first."""
     import hashlib

@@ -1,0 +1,49 @@
+#!/usr/bin/env python3
+"""Golden vectors for the partial-aggregation row format (tests/common.py:partial_cases): the (group key, saved states)
+rows the unmodified reference engine's PartialGroupByExpression returns (oracle/_ref/evqlref sql -P, which installs a
+DefaultScheduler subclass whose buildGroupByExpression builds the partial operator) on the reference-written `mixed`
+table.  Asserts while generating that the oracle's restatement reproduces them (keys and integer states exact, float
+states 1e-9).  Build container only; output committed as tests/golden/ref_partial.json.
+
+Usage: python tests/golden/make_golden_partial.py
+"""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import make_golden as G  # noqa: E402
+from oracle import evq_oracle as O  # noqa: E402
+from tests import common as T  # noqa: E402
+
+
+def main():
+    tmp = tempfile.mkdtemp(prefix="evqpartial")
+    mk, nrows = T.GOLDEN_TABLES["mixed"]
+    rp = os.path.join(tmp, "mixed.ref.cst")
+    G.ref_write(rp, mk(), nrows, tmp=tmp)
+    f = O.read_cstable(rp)
+    out = {"generator": "tests/golden/make_golden_partial.py", "reference": "17ai/eventql v0.5.0 (oracle/_ref/evqlref sql -P)", "cases": {}}
+    for name, sql, plan in T.partial_cases():
+        r = subprocess.run([G.EVQLREF, "sql", "-P", "-t", "t=" + rp, "-q", sql], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        lines = [ln for ln in r.stdout.split("\n") if ln]
+        assert r.returncode == 0 and lines[0].startswith("#") and "ERROR!" not in lines, (name, r.stdout[:400], r.stderr[-400:])
+        rows = sorted(ln.split(";") for ln in lines[1:])
+        want = [(bytes.fromhex(k), bytes.fromhex(d)) for k, d in rows]
+        ok, why = T.partial_rows_equal(plan, O.run_partial_query([f], plan), want)
+        assert ok, (name, why)
+        out["cases"][name] = {"sql": sql, "rows": rows}
+        print("case %-36s groups=%d ok" % (name, len(rows)))
+    with open(os.path.join(HERE, "ref_partial.json"), "w") as fh:
+        json.dump(out, fh, indent=0, separators=(",", ":"))
+    print("wrote", os.path.join(HERE, "ref_partial.json"))
+
+
+if __name__ == "__main__":
+    main()

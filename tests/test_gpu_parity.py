@@ -374,6 +374,54 @@ def test_count_distinct_set_grows(gpu_ctx, monkeypatch):
     tbl.close()
 
 
+@pytest.mark.parametrize("case", T.partial_cases(), ids=[c[0] for c in T.partial_cases()])
+def test_partial_rows_equal_reference_engine(gpu_ctx, case):
+    """evqgpu_query_fetch_partial: the groups in the reference's partial-aggregation row format (SHA-1 of the key tuple
+    computed in the emit kernel + saved states) against the rows of the reference's PartialGroupByExpression
+    (tests/golden/ref_partial.json) and the oracle; the ordinary rows of the same execution stay available"""
+    import json
+    name, _sql, plan = case
+    with open(os.path.join(GOLD, "ref_partial.json")) as fh:
+        g = json.load(fh)["cases"][name]
+    want = [(bytes.fromhex(k), bytes.fromhex(d)) for k, d in g["rows"]]
+    path = T.golden_table_path("mixed")
+    tbl = gpu_ctx.open_table_file(path)
+    q = gpu_ctx.query(plan)
+    try:
+        q.execute([tbl])
+        got = q.fetch_partial()
+        rows = q.rows()
+    finally:
+        q.close()
+        tbl.close()
+    ok, why = T.partial_rows_equal(plan, got, want)
+    assert ok, why
+    f = O.read_cstable(path)
+    ok, why = T.partial_rows_equal(plan, got, O.run_partial_query([f], plan))
+    assert ok, why
+    compare(rows, O.run_query([f], plan).rows(), False)
+
+
+def test_partial_rows_need_the_wire_flag(gpu_ctx):
+    spec = T.lineitem_spec()
+    tbl = gpu_ctx.synthesize(5000, spec)
+    _sql, plan = T.q1(spec)
+    q = gpu_ctx.query(plan)
+    q.execute([tbl])
+    with pytest.raises(capi.EvqError):
+        q.fetch_partial()
+    q.close()
+    plan.flags |= P.QUERY_WIRE
+    q = gpu_ctx.query(plan)
+    q.execute([tbl])
+    assert len(q.fetch_partial()) == 4
+    q.order_by([(0, True)])
+    with pytest.raises(capi.EvqError):
+        q.fetch_partial()          # the key hashes no longer line up with the reordered rows
+    q.close()
+    tbl.close()
+
+
 def test_device_generator_matches_numpy(gpu_ctx):
     """The synthetic tables of bench.py are generated on the device; pin the generator to tests/common.py:synth_values
     (same splitmix64 definition) through the CUDA decode path, for every encoding, with a row offset."""

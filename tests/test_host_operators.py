@@ -106,3 +106,22 @@ def test_order_by_limit_and_row_filter_operators(native_lib):
     assert [int(l) for l in lines] == times[::3]
     rc, lines, err = run_sql("scanf", fx, "time", "0")      # nothing visible
     assert rc == 0 and lines == []
+
+
+@pytest.mark.gpu
+def test_partial_groupby_operator_rows(native_lib):
+    """GpuPartialGroupByExpression on the reference's fixture: (SHA-1 group key, saved states) rows == the oracle's
+    restatement of PartialGroupByExpression, which tests/golden/ref_partial.json pins to the reference engine"""
+    from eventql_b200 import plan as P
+    from oracle import evq_oracle as O
+    fx = os.path.join(GOLD, "testtbl.cst")
+    rc, lines, err = run_sql("partial", fx, "time")
+    assert rc == 0, (lines, err)
+    got = [tuple(bytes.fromhex(x) for x in l.split(";")) for l in lines]
+    t = P.Col(0, P.UINT64)
+    plan = P.QueryPlan(["time"], [t, P.call("count", P.lit(1)), P.call("sum", t)], where=t >= 0, group=[t],
+                       flags=P.QUERY_GROUPBY | P.QUERY_WIRE)
+    want = O.run_partial_query([O.read_cstable(fx)], plan)
+    assert len(got) == 213
+    ok, why = T.partial_rows_equal(plan, got, want)
+    assert ok, why
