@@ -476,10 +476,15 @@ static void gen_general_layout(std::ostringstream& os, const KernelShape& shape)
 static void gen_fast_layout(std::ostringstream& os, const KernelShape& shape) {
   const size_t ncols = shape.cols.size();
   os << "struct EvqRow {\n";
-  for (size_t i = 0; i < ncols; ++i)
-    if (shape.cols[i].used) os << "  " << fast_ctype(shape.cols[i]) << " c" << i << ";\n";
+  for (size_t i = 0; i < ncols; ++i) {
+    if (!shape.cols[i].used) continue;
+    os << "  " << fast_ctype(shape.cols[i]) << " c" << i << ";\n";
+    if (shape.cols[i].nullable) os << "  u32 t" << i << ";\n";   // STag: 1 = NULL
+  }
   os << "  u32 _unused;\n};\n";
   os << "struct EvqCols {\n";
+  for (size_t i = 0; i < ncols; ++i)
+    if (shape.cols[i].used && shape.cols[i].nullable) os << "  u32 n" << i << ", r" << i << ";\n";   // presence bits of the thread's rows, ordinal of its first value
   for (size_t i = 0; i < ncols; ++i)
     if (shape.cols[i].used) os << "  " << fast_ctype(shape.cols[i]) << " c" << i << "[EVQ_RPT];\n";
   for (size_t i = 0; i < ncols; ++i)
@@ -509,6 +514,24 @@ static void gen_fast_layout(std::ostringstream& os, const KernelShape& shape) {
   }
   os << "}\n";
 
+  // ---- optional columns: presence bits of the thread's rows + ordinal of its first value (one barrier per tile)
+  os << "__device__ __forceinline__ void evq_fast_nulls(const EvqTile& T, const EvqScanParams& P, EvqFastScratch* scr, u32 buf, u32 nvalid, EvqCols& cols) {\n";
+  if (shape.nnull > 0) {
+    for (size_t i = 0; i < ncols; ++i) {
+      const ColSig& c = shape.cols[i];
+      if (!c.used || !c.nullable) continue;
+      os << "  cols.n" << i << " = evq_fast_presence<" << c.level_stream << ">(T, P) & ((1u << nvalid) - 1u);\n";
+      os << "  cols.r" << i << " = evq_fast_null_scan(cols.n" << i << ", scr, buf, " << c.null_slot << ", T.ctid);\n";
+    }
+    os << "  evq_cons_sync();\n";
+    for (size_t i = 0; i < ncols; ++i) {
+      const ColSig& c = shape.cols[i];
+      if (!c.used || !c.nullable) continue;
+      os << "  cols.r" << i << " = evq_fast_null_rank(cols.r" << i << ", scr, buf, " << c.null_slot << ", T.ctid);\n";
+    }
+  }
+  os << "}\n";
+
   // ---- FastCSTableScan::fetchColumn* (sql/CSTableScan.cc:860-968) for the thread's 4 rows
   os << "__device__ __forceinline__ void evq_fast_decode(const EvqTile& T, const EvqScanParams& P, const EvqFastScratch* scr, const EvqFastPrep& prep, EvqCols& cols) {\n";
   for (size_t i = 0; i < ncols; ++i) {
@@ -517,6 +540,35 @@ static void gen_fast_layout(std::ostringstream& os, const KernelShape& shape) {
     const std::string S = std::to_string(c.data_stream);
     const std::string ct = fast_ctype(c);
     const bool narrow = ct == "u32";
+    if (c.nullable) {
+      // NULL: value 0, tag STAG_NULL (CSTableScan.cc:877-890); only the present values are in the data stream
+      const std::string pbr = "cols.n" + std::to_string(i) + ", cols.r" + std::to_string(i);
+      std::string raw_tn = "u32";
+      os << "  {\n";
+      switch (c.kind) {
+        case EVQ_KIND_PLAIN64: raw_tn = "u64"; os << "    u64 raw[EVQ_RPT];\n    evq_fast_ldn_plain64<" << S << ">(T, P, " << pbr << ", raw);\n"; break;
+        case EVQ_KIND_PLAIN32: os << "    u32 raw[EVQ_RPT];\n    evq_fast_ldn_plain32<" << S << ">(T, P, " << pbr << ", raw);\n"; break;
+        case EVQ_KIND_BITPACK: os << "    u32 raw[EVQ_RPT];\n    evq_fast_ldn_bitpack<" << S << ">(T, P, " << pbr << ", raw);\n"; break;
+        default:
+          if (c.leb_len <= 1) {
+            os << "    u32 raw[EVQ_RPT];\n    evq_fast_ldn_leb1<" << S << ">(T, P, " << pbr << ", raw);\n";
+          } else {
+            raw_tn = "u64";
+            os << "    u64 raw[EVQ_RPT];\n    evq_fast_ldn_leb<" << S << ", " << (c.leb_uniform ? -1 : c.sub_stream) << ", " << c.leb_len << ">(T, P, " << pbr
+               << ", raw);\n";
+          }
+          break;
+      }
+      std::string conv;
+      switch (c.sql_type) {
+        case EVQ_FLOAT64: conv = "evq_f64(raw[k])"; break;
+        case EVQ_BOOL: conv = "(u32) (raw[k] > 0)"; break;
+        default: conv = std::string("(") + ct + ") raw[k]"; break;
+      }
+      os << "#pragma unroll\n    for (int k = 0; k < EVQ_RPT; ++k) cols.c" << i << "[k] = " << conv << ";\n  }\n";
+      (void) raw_tn;
+      continue;
+    }
     const std::string raw_t = (c.kind == EVQ_KIND_PLAIN64 && !(narrow && c.sql_type != EVQ_BOOL && c.sql_type != EVQ_FLOAT64)) || (c.kind == EVQ_KIND_LEB128 && c.leb_len > 4) ? "u64" : "u32";
     os << "  {\n    " << raw_t << " raw[EVQ_RPT];\n";
     switch (c.kind) {
@@ -564,8 +616,11 @@ static void gen_fast_layout(std::ostringstream& os, const KernelShape& shape) {
   }
   os << "}\n";
   os << "__device__ __forceinline__ void evq_fast_row(const EvqCols& cols, int k, EvqRow& row) {\n";
-  for (size_t i = 0; i < ncols; ++i)
-    if (shape.cols[i].used) os << "  row.c" << i << " = cols.c" << i << "[k];\n";
+  for (size_t i = 0; i < ncols; ++i) {
+    if (!shape.cols[i].used) continue;
+    os << "  row.c" << i << " = cols.c" << i << "[k];\n";
+    if (shape.cols[i].nullable) os << "  row.t" << i << " = ((cols.n" << i << " >> k) & 1u) ^ 1u;\n";
+  }
   os << "}\n";
 }
 

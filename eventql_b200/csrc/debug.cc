@@ -39,7 +39,10 @@ extern "C" int evqgpu_debug_generate(const evqgpu_query_desc* desc, const evqgpu
       if (cs.nullable) { cs.level_stream = s.nstreams++; cs.null_slot = s.nnull++; }
       if (cs.kind == EVQ_KIND_LEB128) cs.leb_slot = s.nleb++;
     }
-    s.fast = s.nnull == 0;
+    s.fast = !getenv("EVQGPU_NO_FAST_NULL");
+    for (const auto& c : s.cols)
+      if (c.used && c.nullable && c.dmax != 1) s.fast = false;
+    if (s.nnull > 0 && getenv("EVQGPU_NO_SUBIDX")) s.fast = false;
     s.use_subidx = s.fast && !getenv("EVQGPU_NO_SUBIDX");
     for (auto& c : s.cols) {
       c.gen_slot = -1;

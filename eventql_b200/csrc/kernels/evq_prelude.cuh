@@ -241,14 +241,21 @@ struct EvqCopyPlanK {
   EvqStreamDesc desc[EVQ_KT];
 };
 
-// byte offset at which row tile `tile` (<= num_tiles: the end) starts in the stream of a required column
-__device__ __forceinline__ u64 evq_tile_start(const EvqScanParams& P, const EvqStream& S, u32 tile) {
+// ordinal of the first VALUE of row tile `tile` (<= num_tiles: the end) in a data stream: the row for required columns,
+// the number of non-NULL values before the tile for optional ones
+__device__ __forceinline__ u64 evq_tile_first_value(const EvqScanParams& P, const EvqStream& S, u32 tile) {
+  if (S.val_index) return S.val_index[tile];
   const u64 rows = (u64) tile * EVQ_TILE_ROWS;
-  const u64 row = rows < P.num_rows ? rows : P.num_rows;
+  return rows < P.num_rows ? rows : P.num_rows;
+}
+
+// byte offset of value ordinal v in the stream (BITPACK: of the 128-value block that holds it; `end`: of the block behind)
+__device__ __forceinline__ u64 evq_value_offset(const EvqStream& S, u32 tile, u64 v, bool end) {
   switch (S.kind) {
-    case EVQ_KIND_PLAIN64: return row * 8;
-    case EVQ_KIND_PLAIN32: return row * 4;
-    case EVQ_KIND_BITPACK: return ((row + 127) >> 7) * 16 * S.bits;   // tiles start on 128-value blocks; the end rounds up
+    case EVQ_KIND_PLAIN64: return v * 8;
+    case EVQ_KIND_PLAIN32: return v * 4;
+    case EVQ_KIND_BITPACK:
+    case EVQ_KIND_LEVEL: return ((end ? v + 127 : v) >> 7) * 16 * S.bits;
     case EVQ_KIND_SUBIDX: return (u64) tile * EVQ_SUB_ENTRIES * 2;
     case EVQ_KIND_FILTER: return (u64) tile * (EVQ_TILE_ROWS / 8);
     default: return S.off_index[tile];
@@ -261,14 +268,21 @@ __device__ __forceinline__ void evq_producer_plan_k(const EvqScanParams& P, cons
   cp.bytes = 0;
   if (!active || group >= num_groups) return;
   const u32 t0 = group * EVQ_KT;
-  u64 start[EVQ_KT + 1];
+  u64 val[EVQ_KT + 1], start[EVQ_KT + 1];
 #pragma unroll
   for (int i = 0; i <= EVQ_KT; ++i) {
     const u32 t = t0 + i < P.num_tiles ? t0 + i : P.num_tiles;
-    start[i] = evq_tile_start(P, S, t);
+    if (S.kind == EVQ_KIND_LEVEL) {   // level streams are row-indexed
+      const u64 rows = (u64) t * EVQ_TILE_ROWS;
+      val[i] = rows < P.num_rows ? rows : P.num_rows;
+    } else {
+      val[i] = evq_tile_first_value(P, S, t);
+    }
+    start[i] = evq_value_offset(S, t, val[i], false);
   }
+  const u64 end = evq_value_offset(S, t0 + EVQ_KT < P.num_tiles ? t0 + EVQ_KT : P.num_tiles, val[EVQ_KT], true);
   const u64 al = start[0] & ~15ull;
-  u32 bytes = start[EVQ_KT] > start[0] ? (u32) (((start[EVQ_KT] - al) + 15) & ~15ull) : 0u;
+  u32 bytes = end > start[0] ? (u32) (((end - al) + 15) & ~15ull) : 0u;
   if (bytes > S.smem_cap) {   // the host sized the stage from the tile index: cannot happen unless that is wrong
     atomicOr(P.status, EVQ_ERR_STAGE_OVERFLOW);
     bytes = S.smem_cap & ~15u;
@@ -277,12 +291,10 @@ __device__ __forceinline__ void evq_producer_plan_k(const EvqScanParams& P, cons
   cp.bytes = bytes;
 #pragma unroll
   for (int i = 0; i < EVQ_KT; ++i) {
-    const u64 row0 = (u64) (t0 + i) * EVQ_TILE_ROWS;
-    const u64 rem = row0 < P.num_rows ? P.num_rows - row0 : 0ull;
     cp.desc[i].delta = (u32) (start[i] - al);
     cp.desc[i].nbytes = (u32) (start[i + 1] - start[i]);
-    cp.desc[i].nvals = rem < EVQ_TILE_ROWS ? (u32) rem : EVQ_TILE_ROWS;
-    cp.desc[i].skew = 0;
+    cp.desc[i].nvals = (u32) (val[i + 1] - val[i]);
+    cp.desc[i].skew = S.kind == EVQ_KIND_BITPACK ? (u32) (val[i] & 127ull) : 0u;
   }
 }
 

@@ -35,6 +35,7 @@ struct EvqFastScratch {
   u32 wtot[EVQ_NGEN > 0 ? EVQ_NGEN : 1][EVQ_NWARPS];          // terminators per consumer warp (boundary search)
   u32 chunk[EVQ_NGEN > 0 ? EVQ_NGEN : 1][EVQ_GEN_CHUNKS];     // per chunk: terminators before it in its warp << 16 | terminator mask
   u32 scan[EVQ_NWARPS];                                       // scan-only plans: pass counts per warp
+  u32 nullw[2][EVQ_NNULL > 0 ? EVQ_NNULL : 1][EVQ_NWARPS];    // optional columns: present values per consumer warp (two tiles in flight)
 };
 
 // ---- boundary search of a variable-length LEB128 column ------------------------------------------------------------------
@@ -412,6 +413,132 @@ __device__ __forceinline__ void evq_fast_ld_bitpack(const EvqTile& T, const EvqS
   for (int i = 0; i < EVQ_RPT; ++i) v[i] = evq_unpack_vertical(words, d.skew + i0 + i, bits);
 }
 
+// ---- optional columns (one definition-level bit per row) ------------------------------------------------------------------
+// Only the present values are in the data stream (ColumnWriter.cc:92-100): thread t needs (a) which of its 8 rows are
+// present and (b) the ordinal, inside the tile, of its first present value = present rows of the threads before it.
+
+// presence bits of rows 8t .. 8t+7 (bit k = row 8t + k) from the tile's 1-bit level blocks (libsimdcomp vertical layout:
+// value i of a 128-block is bit i / 4 of the block's word i % 4; 8t is a multiple of 8, so the thread's rows are bits
+// b0 and b0 + 1 of the four words of one block)
+template <int LS>
+__device__ __forceinline__ u32 evq_fast_presence(const EvqTile& T, const EvqScanParams& P) {
+  const u32 i0 = EVQ_RPT * T.ctid;
+  const u32 off = P.streams[LS].smem_off + T.desc[LS].delta + (i0 >> 7) * 16u;
+  u32 w0, w1, w2, w3;
+  evq_stage_v4(T, off, w0, w1, w2, w3);
+  const u32 b0 = (i0 & 127u) >> 2;
+  const u32 x0 = w0 >> b0, x1 = w1 >> b0, x2 = w2 >> b0, x3 = w3 >> b0;
+  u32 pb = (x0 & 1u) | ((x1 & 1u) << 1) | ((x2 & 1u) << 2) | ((x3 & 1u) << 3);
+  if (EVQ_RPT == 8) pb |= ((x0 & 2u) << 3) | ((x1 & 2u) << 4) | ((x2 & 2u) << 5) | ((x3 & 2u) << 6);
+  return pb;
+}
+
+// ordinal of the thread's first present value among the tile's values of the column: warp scan of the per-thread counts,
+// warp totals through shared memory (`buf` alternates between consecutive tiles, so one barrier per tile suffices)
+__device__ __forceinline__ u32 evq_fast_null_scan(u32 pb, EvqFastScratch* scr, u32 buf, int slot, u32 tid) {
+  const u32 cnt = __popc(pb);
+  u32 incl = cnt;
+  const u32 lane = evq_lane();
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const u32 n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (u32) o) incl += n;
+  }
+  if (lane == 31) scr->nullw[buf][slot][tid >> 5] = incl;
+  return incl - cnt;
+}
+__device__ __forceinline__ u32 evq_fast_null_rank(u32 excl, const EvqFastScratch* scr, u32 buf, int slot, u32 tid) {
+  u32 r = excl;
+#pragma unroll
+  for (int w = 0; w < EVQ_NWARPS; ++w) r += (u32) w < (tid >> 5) ? scr->nullw[buf][slot][w] : 0u;
+  return r;
+}
+
+// index, among the thread's present values, of row k's value
+__device__ __forceinline__ u32 evq_pidx(u32 pb, int k) { return __popc(pb & ((1u << k) - 1u)); }
+
+// 1-byte LEB128, optional: the value with ordinal r is byte r of the tile's payload
+template <int S>
+__device__ __forceinline__ void evq_fast_ldn_leb1(const EvqTile& T, const EvqScanParams& P, u32 pb, u32 rank, u32 (&v)[EVQ_RPT]) {
+  u32 lo, hi;
+  evq_lds_unaligned64(T.stage + P.streams[S].smem_off + T.desc[S].delta + rank, lo, hi);
+#pragma unroll
+  for (int k = 0; k < EVQ_RPT; ++k) v[k] = ((pb >> k) & 1u) ? (__byte_perm(lo, hi, evq_pidx(pb, k)) & 0xffu) : 0u;
+}
+
+template <int S>
+__device__ __forceinline__ void evq_fast_ldn_plain64(const EvqTile& T, const EvqScanParams& P, u32 pb, u32 rank, u64 (&v)[EVQ_RPT]) {
+  const u64* p = (const u64*) (T.stage + P.streams[S].smem_off + T.desc[S].delta) + rank;
+#pragma unroll
+  for (int k = 0; k < EVQ_RPT; ++k) v[k] = ((pb >> k) & 1u) ? p[evq_pidx(pb, k)] : 0ull;
+}
+
+template <int S>
+__device__ __forceinline__ void evq_fast_ldn_plain32(const EvqTile& T, const EvqScanParams& P, u32 pb, u32 rank, u32 (&v)[EVQ_RPT]) {
+  const u32* p = (const u32*) (T.stage + P.streams[S].smem_off + T.desc[S].delta) + rank;
+#pragma unroll
+  for (int k = 0; k < EVQ_RPT; ++k) v[k] = ((pb >> k) & 1u) ? p[evq_pidx(pb, k)] : 0u;
+}
+
+template <int S>
+__device__ __forceinline__ void evq_fast_ldn_bitpack(const EvqTile& T, const EvqScanParams& P, u32 pb, u32 rank, u32 (&v)[EVQ_RPT]) {
+  const EvqStreamDesc& d = T.desc[S];
+  const u32* words = (const u32*) (T.stage + P.streams[S].smem_off + d.delta);
+  const u32 bits = P.streams[S].bits;
+#pragma unroll
+  for (int k = 0; k < EVQ_RPT; ++k) v[k] = ((pb >> k) & 1u) ? evq_unpack_vertical(words, d.skew + rank + evq_pidx(pb, k), bits) : 0u;
+}
+
+// LEB128 of 2..10 bytes, optional.  X = stream of the column's sub-index (u16 per EVQ_SUB_GRAN values of the tile), or -1
+// when every value has L bytes.  The thread enters at the sub-index entry in front of its first value, skips the
+// values in between and then decodes one value per present row.
+template <int S, int X, int L>
+__device__ __forceinline__ void evq_fast_ldn_leb(const EvqTile& T, const EvqScanParams& P, u32 pb, u32 rank, u64 (&v)[EVQ_RPT]) {
+  const u8* pay = T.stage + P.streams[S].smem_off + T.desc[S].delta;
+  const bool uniform = X < 0 || T.desc[S].nbytes == (u32) L * T.desc[S].nvals;
+  const u8* p;
+  u32 skip = 0;
+  if (uniform) {
+    p = pay + (u32) L * rank;
+  } else {
+    const u32 e = rank / EVQ_SUB_GRAN < EVQ_SUB_ENTRIES ? rank / EVQ_SUB_GRAN : EVQ_SUB_ENTRIES - 1u;   // (rank == nvals == 1024: nothing to decode)
+    p = pay + ((const u16*) (T.stage + P.streams[X < 0 ? 0 : X].smem_off + T.desc[X < 0 ? 0 : X].delta))[e];
+    skip = rank - e * EVQ_SUB_GRAN;
+  }
+#pragma unroll
+  for (int k = -(int) (EVQ_SUB_GRAN - 1); k < EVQ_RPT; ++k) {
+    // k < 0: one of the up to EVQ_SUB_GRAN - 1 values between the entry point and the thread's first value
+    const bool take = k < 0 ? (u32) (-k) <= skip : ((pb >> k) & 1u) != 0u;
+    u64 val = 0;
+    if (take) {
+      u32 lo, hi;
+      evq_lds_unaligned64(p, lo, hi);
+      u32 len;
+      if (uniform) {
+        len = L;
+      } else {
+        const u32 tl = ~lo & 0x80808080u, th = ~hi & 0x80808080u;
+        if (tl) len = (32u - __clz(tl & (0u - tl))) >> 3;
+        else if (L > 4 && th) len = 4u + ((32u - __clz(th & (0u - th))) >> 3);
+        else len = L <= 4 ? 4u : (L > 9 && (p[8] & 0x80u)) ? 10u : 9u;
+      }
+      if (k >= 0) {
+        if (len <= 4u) {
+          val = evq_leb_pack4(lo & evq_fixed_mask(len));
+        } else {
+          val = (u64) evq_leb_pack4(lo & 0x7f7f7f7fu) | ((u64) evq_leb_pack4(hi & evq_fixed_mask(len - 4u)) << 28);
+          if (L > 8 && len > 8u) {
+            val |= ((u64) (p[8] & 0x7fu)) << 56;
+            if (L > 9 && len > 9u) val |= ((u64) (p[9] & 0x7fu)) << 63;
+          }
+        }
+      }
+      p += len;
+    }
+    if (k >= 0) v[k] = val;
+  }
+}
+
 // ---- the kernel ------------------------------------------------------------------------------------------------------
 
 struct EvqSmemHeader {
@@ -501,6 +628,9 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
 #endif
 #endif
 
+#if EVQ_NNULL > 0
+  u32 nullbuf = 0;
+#endif
   u32 it = 0;
   for (u32 group = first_group; group < num_groups; group += group_step, ++it) {
     const u32 s = it % EVQ_NSTAGES;
@@ -533,6 +663,10 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
     EvqFastPrep prep;
     evq_fast_prep(T, P, scr, prep);
     EvqCols cols;
+#if EVQ_NNULL > 0
+    evq_fast_nulls(T, P, scr, nullbuf, nvalid, cols);
+    nullbuf ^= 1u;
+#endif
     evq_fast_decode(T, P, scr, prep, cols);
 
 #if EVQ_TIER == 0 || EVQ_TIER == 3

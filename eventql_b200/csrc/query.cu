@@ -84,7 +84,8 @@ static KernelShape shape_for(const evqgpu_query& q, evqgpu_table* t, const Bindi
     if (cs.nullable) {
       cs.level_stream = s.nstreams++;
       cs.null_slot = s.nnull++;
-      s.fast = false;
+      // flat optional columns (one definition level bit per row) also run the fast layout
+      if (c.meta.dlevel_max != 1 || c.level_bits != 1 || getenv("EVQGPU_NO_FAST_NULL")) s.fast = false;
     }
     if (cs.kind == EVQ_KIND_LEB128) cs.leb_slot = s.nleb++;
   }
@@ -107,6 +108,7 @@ static void widen_shape(KernelShape& s, const KernelShape& o) {
 static void finish_shape(KernelShape& s, bool have_subidx) {
   if (getenv("EVQGPU_NO_FAST")) s.fast = false;
   s.use_subidx = s.fast && have_subidx && !getenv("EVQGPU_NO_SUBIDX");
+  if (s.nnull > 0 && !s.use_subidx) s.fast = false;   // the in-kernel boundary search covers required columns only
   s.ngen = 0;
   for (auto& c : s.cols) {
     c.gen_slot = -1;
@@ -155,7 +157,7 @@ static StageLayout stage_layout(const evqgpu_query& q, evqgpu_table* t, const Bi
     };
     // (kt consecutive tiles are contiguous in a required column's stream: at most kt times the largest tile)
     place(cs.data_stream, c.data_tile_cap * (uint32_t) s.kt);
-    if (cs.nullable) place(cs.level_stream, c.level_tile_cap);
+    if (cs.nullable) place(cs.level_stream, c.level_tile_cap * (uint32_t) s.kt);
     if (cs.sub_stream >= 0) place(cs.sub_stream, EVQ_SUB_ENTRIES * 2 * (uint32_t) s.kt);
   }
   if (s.filter_stream >= 0) {
@@ -172,7 +174,7 @@ static size_t scratch_bytes(const KernelShape& s) {
   const size_t nwarps = s.ncons / 32;
   if (s.fast) {   // EvqFastScratch
     const size_t ngen = std::max(1, s.ngen);
-    return round_up(4 * ngen * nwarps + 4 * ngen * (size_t) gen_chunks(s) + 4 * nwarps, 128) + 128;
+    return round_up(4 * ngen * nwarps + 4 * ngen * (size_t) gen_chunks(s) + 4 * nwarps + 8 * std::max(1, s.nnull) * nwarps, 128) + 128;
   }
   const size_t one = 4 * std::max(1, s.nleb) * nwarps + 4 * std::max(1, s.nnull) * (EVQ_TILE_ROWS / 32) +
                      2 * std::max(1, s.nleb) * EVQ_TILE_ROWS + 4 * nwarps;
@@ -680,7 +682,7 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
     if (dense) {
       s.g1 = g1_for(dm.slots);
       // thread-private accumulators must fit next to the pipeline stages
-      const size_t acc = (size_t) s.g1 * q.nstate_smem * (s.fast ? 256 : 128) * 8;
+      const size_t acc = (size_t) s.g1 * q.nstate_smem * 128 * 8;   // (both kernels can run 128 consumer threads)
       if (dm.slots > 64 || acc > 96 * 1024) {
         dense = false;
         // too many groups for thread-private state, but the key tuples span a small box: a direct-addressed group

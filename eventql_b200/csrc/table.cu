@@ -532,7 +532,7 @@ void table_finish_column(evqgpu_table* t, Column& c) {
       c.data_bits = 0;
       c.data_tile_cap = span_from_index(c.off_index.as<u64>(), 1, 0, 0);
       c.leb_uniform = nv > 0 && used == (u64) c.leb_max_len * nv;
-      if (c.leb_max_len >= 2 && !nullable && ntiles) {
+      if (c.leb_max_len >= 2 && ntiles) {
         if (!c.leb_uniform) {
           // where the values of the column differ in length: starts of every EVQ_SUB_GRAN-th value (the fast kernel's decode
           // entry points)
@@ -543,6 +543,7 @@ void table_finish_column(evqgpu_table* t, Column& c) {
           EVQ_CUDA(cudaGetLastError());
           ctx->kernel_launches++;
         }
+        if (nullable) break;   // (the value-range pass below walks row-indexed groups: required columns only)
         // ... which also make the exact value range one cheap pass (8 values per thread)
         EVQ_CUDA(cudaMemsetAsync(minmax.p, 0, 16, ctx->stream));
         const uint64_t groups = (uint64_t) ntiles * (EVQ_TILE_ROWS / 8);

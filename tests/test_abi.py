@@ -115,9 +115,11 @@ def test_kernel_text_compiles_for_sm100a(native_lib, case):
         tier, slots = 0, 0
     src, cubin_bytes = capi.debug_generate(plan, _cols(spec, case != "q1_nostats"), tier=tier, dense_slots=slots, compile=True)
     assert "evq_scan" in src and cubin_bytes > 1000
-    # required columns take the fast kernel (4 consecutive rows per thread), optional ones the general kernel
+    # required and flat optional columns take the fast kernel (consecutive rows per thread); optional ones read their
+    # presence bits from the level stream
     nullable = any(s.get("null_every") for s in spec)
-    assert ("evq_fast_decode" in src) == (not nullable)
+    assert "evq_fast_decode" in src
+    assert ("cols.n" in src and "evq_fast_presence<" in src.split("void evq_fast_nulls(", 1)[1].split("evq_fast_decode(", 1)[0]) == nullable
     # the TMA bulk copy + mbarrier pipeline is part of every variant
     assert "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes" in src
 
