@@ -309,7 +309,7 @@ __device__ __forceinline__ void evq_fast_ld_leb64(const EvqTile& T, const EvqSca
       evq_stage_64bytes(T, off, w);
 #pragma unroll
       for (int i = 0; i < EVQ_RPT; ++i)
-        v[i] = (u64) evq_leb_pack4(w[2 * i] & 0x7f7f7f7fu) | ((u64) evq_leb_pack4(w[2 * i + 1] & 0x7f7f7f7fu) << 28);
+        v[i] = (u64) evq_fast_pack4(w[2 * i] & 0x7f7f7f7fu) | ((u64) evq_fast_pack4(w[2 * i + 1] & 0x7f7f7f7fu) << 28);
       return;
     }
   }

@@ -1,5 +1,5 @@
 """Average evq_scan launch time of a workload (CUDA events around every launch), for knob sweeps:
-  EVQGPU_NSTAGES=3 python scripts/launch_time.py [c3_q1|c2_q6|...] [partitions] [reps]"""
+  EVQGPU_NSTAGES=3 python scripts/launch_time.py [c3_q1|c2_q6|...] [partitions] [reps] [rows per partition]"""
 import os
 import sys
 
@@ -10,6 +10,8 @@ from eventql_b200 import capi
 wl = bench.workload(sys.argv[1] if len(sys.argv) > 1 else "c3_q1")
 parts = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 10
+if len(sys.argv) > 4:
+    wl["rows"] = int(sys.argv[4])
 ctx = capi.Context(0)
 tables = [ctx.synthesize(wl["rows"], wl["spec"](p), row_offset=p * wl["rows"]) for p in range(parts)]
 sql, plan = wl["query"](wl["spec"](0))
