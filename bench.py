@@ -37,7 +37,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="evq", choices=["evq", "reference"])
-    ap.add_argument("--workload", default="c3_q1", choices=["c3_q1", "c3_q1_plain", "c2_q6", "c4_highcard", "c5_timeseries"])
+    ap.add_argument("--workload", default="c3_q1", choices=["c3_q1", "c3_q1_plain", "c3_q1_null", "c2_q6", "c4_highcard", "c5_timeseries"])
     ap.add_argument("--rows-per-partition", type=int, default=0, help="0 = the workload's default")
     ap.add_argument("--partitions-per-gpu", type=int, default=0, help="0 = the workload's default")
     ap.add_argument("--e2e-steps", type=int, default=2)
