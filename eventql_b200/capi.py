@@ -64,6 +64,15 @@ class SortSpec(C.Structure):
     _fields_ = [("column", C.c_uint32), ("descending", C.c_uint32)]
 
 
+class LsmSegment(C.Structure):
+    _fields_ = [("table", C.c_void_p), ("skiplist", C.c_void_p), ("flags", C.c_uint32), ("reserved", C.c_uint32),
+                ("visible_rows", C.c_uint64)]
+
+
+LSM_SKIP_COLUMN = 1
+LSM_NO_FILTER = 2
+
+
 class DebugColumn(C.Structure):
     _fields_ = [("sql_type", C.c_uint32), ("encoding", C.c_uint32), ("dlevel_max", C.c_uint32), ("value_bits", C.c_uint32),
                 ("leb_max_len", C.c_uint32), ("reserved", C.c_uint32), ("value_min", C.c_uint64), ("value_max", C.c_uint64)]
@@ -82,6 +91,7 @@ SYMBOLS = [
     "evqgpu_query_column_type", "evqgpu_query_execute", "evqgpu_query_enqueue", "evqgpu_query_finish",
     "evqgpu_query_num_rows", "evqgpu_query_fetch", "evqgpu_query_order_by", "evqgpu_query_limit", "evqgpu_query_fetch_partial", "evqgpu_query_get_stats", "evqgpu_query_kernel_source",
     "evqgpu_comm_unique_id", "evqgpu_comm_init", "evqgpu_comm_destroy", "evqgpu_query_merge", "evqgpu_debug_generate",
+    "evqgpu_table_decode_string_column", "evqgpu_table_get_filter", "evqgpu_lsm_build_filters",
 ]
 
 _lib = None
@@ -127,6 +137,9 @@ def lib() -> C.CDLL:
     L.evqgpu_table_read_stream.argtypes = [vp, cp, u32, vp, u64, C.POINTER(u64), C.POINTER(u32)]
     L.evqgpu_table_decode_column.argtypes = [vp, cp, u64, u64, vp, u64]
     L.evqgpu_table_write_file.argtypes = [vp, cp]
+    L.evqgpu_table_decode_string_column.argtypes = [vp, cp, u64, u64, vp, u64, C.POINTER(u64)]
+    L.evqgpu_table_get_filter.argtypes = [vp, vp, u64, C.POINTER(C.c_int)]
+    L.evqgpu_lsm_build_filters.argtypes = [vp, C.POINTER(LsmSegment), u32]
     L.evqgpu_table_synthesize.argtypes = [vp, u64, u64, C.POINTER(SynthColumn), u32, C.POINTER(vp)]
     L.evqgpu_function_lookup.argtypes = [cp]
     L.evqgpu_function_symbol.argtypes = [C.c_int]
@@ -301,6 +314,24 @@ class Context:
     def query(self, plan: P.QueryPlan) -> "Query":
         return Query(self, plan)
 
+    def lsm_build_filters(self, segments) -> List[int]:
+        """PartitionCursor's visibility filters (server/sql/partition_cursor.cc:157-194) for the segments of one
+        partition, in the cursor's order.  segments: (Table, skiplist bools or None, use_skip_column, needs_filter).
+        Installs each table's row filter; returns the visible rows per segment."""
+        arr = (LsmSegment * max(1, len(segments)))()
+        keep = []
+        for i, (tbl, skiplist, use_skip_column, needs_filter) in enumerate(segments):
+            arr[i].table = tbl._h
+            arr[i].flags = (LSM_SKIP_COLUMN if use_skip_column else 0) | (0 if needs_filter else LSM_NO_FILTER)
+            if skiplist is not None:
+                bits = np.packbits(np.asarray(skiplist, dtype=bool), bitorder="little")
+                if bits.size == 0:
+                    bits = np.zeros(1, dtype=np.uint8)
+                keep.append(bits)
+                arr[i].skiplist = bits.ctypes.data_as(C.c_void_p)
+        check(lib().evqgpu_lsm_build_filters(self._h, arr, len(segments)))
+        return [int(arr[i].visible_rows) for i in range(len(segments))]
+
     def host_alloc(self, nbytes: int) -> np.ndarray:
         """Pinned host buffer as a numpy uint8 array (freed when the context closes... or never: tests only)."""
         p = C.c_void_p()
@@ -390,6 +421,27 @@ class Table:
         out = np.zeros(max(1, nrows * w), dtype=np.uint8)
         check(lib().evqgpu_table_decode_column(self._h, name.encode(), row0, nrows, out.ctypes.data_as(C.c_void_p), out.nbytes))
         return out[: nrows * w].tobytes()
+
+    def decode_string_column(self, name: str, row0: int = 0, nrows: Optional[int] = None) -> bytes:
+        """FastCSTableScan::fetchColumnString: the packed STRING SVector of rows [row0, row0 + nrows)."""
+        if nrows is None:
+            nrows = self.num_rows - row0
+        need = C.c_uint64(0)
+        check(lib().evqgpu_table_decode_string_column(self._h, name.encode(), row0, nrows, None, 0, C.byref(need)))
+        out = np.zeros(max(1, need.value), dtype=np.uint8)
+        check(lib().evqgpu_table_decode_string_column(self._h, name.encode(), row0, nrows, out.ctypes.data_as(C.c_void_p), out.nbytes,
+                                                      C.byref(need)))
+        return out[: need.value].tobytes()
+
+    def get_filter(self) -> Optional[np.ndarray]:
+        """The table's external row filter as one bool per row, None when it has none."""
+        has = C.c_int(0)
+        n = self.num_rows
+        bits = np.zeros(max(1, (n + 7) // 8), dtype=np.uint8)
+        check(lib().evqgpu_table_get_filter(self._h, bits.ctypes.data_as(C.c_void_p), bits.nbytes, C.byref(has)))
+        if not has.value:
+            return None
+        return np.unpackbits(bits, bitorder="little")[:n].astype(bool)
 
     def write_file(self, path: str):
         check(lib().evqgpu_table_write_file(self._h, path.encode()))

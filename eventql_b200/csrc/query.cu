@@ -43,6 +43,9 @@ static Binding bind_table(const evqgpu_query& q, evqgpu_table* t) {
     if (!q.col_used[i]) continue;
     const int ci = t->find(q.input_columns[i].c_str());
     if (ci < 0) fail(EVQGPU_ERR_ARG, "column not found: %s", q.input_columns[i].c_str());
+    if (!t->cols[ci].scannable)
+      fail(EVQGPU_ERR_UNSUPPORTED, "column '%s' (logical type %u, encoding %u, rlevel_max %u) is outside the flat numeric scan path",
+           q.input_columns[i].c_str(), t->cols[ci].meta.logical_type, t->cols[ci].meta.encoding, t->cols[ci].meta.rlevel_max);
     if (!t->cols[ci].loaded) table_load_column(t, t->cols[ci]);
     b.col_index[i] = ci;
   }

@@ -40,6 +40,11 @@ void table_init_columns(evqgpu_table* t) {
       case EVQ_ENC_UINT32_BITPACKED:
       case EVQ_ENC_BOOLEAN_BITPACKED: c.data_kind = EVQ_KIND_BITPACK; break;
       case EVQ_ENC_UINT64_LEB128: c.data_kind = EVQ_KIND_LEB128; break;
+      case EVQ_ENC_STRING_PLAIN:
+        c.scannable = false;
+        c.data_kind = EVQ_KIND_STRING_HOST;
+        c.is_string = c.sql_type == EVQ_STRING && c.meta.rlevel_max == 0;
+        break;
       default: c.scannable = false; break;
     }
   }
@@ -359,6 +364,31 @@ static void upload_stream(evqgpu_table* t, DeviceStream& ds, const StreamLayout&
 
 void table_load_column(evqgpu_table* t, Column& c) {
   if (c.loaded) return;
+  if (c.is_string) {
+    // flat STRING_PLAIN column: the stream goes to the device like any other; the value index is built from the host
+    // image of the stream (length prefixes are a sequential chain - strings.cu)
+    if (!t->from_file) fail(EVQGPU_ERR_ARG, "column '%s' has no streams", c.meta.name.c_str());
+    use_device(t->ctx);
+    StreamLayout dl = stream_layout(t->meta, c.meta, EVQ_STREAM_DATA, t->file, t->file_bytes);
+    upload_stream(t, c.data, dl);
+    if (c.meta.dlevel_max > 0) {
+      StreamLayout ll = stream_layout(t->meta, c.meta, EVQ_STREAM_DLEVEL, t->file, t->file_bytes);
+      upload_stream(t, c.dlevel, ll);
+      if (t->meta.version == 1) c.dlevel.bitpack_max = c.meta.dlevel_max;
+    }
+    if (dl.extents.size() == 1) {
+      table_finish_string_column(t, c, t->file + dl.extents[0].file_offset, dl.total);
+    } else {
+      std::vector<uint8_t> logical(dl.total);
+      uint64_t dst = 0;
+      for (const auto& e : dl.extents) {
+        memcpy(logical.data() + dst, t->file + e.file_offset, e.nbytes);
+        dst += e.nbytes;
+      }
+      table_finish_string_column(t, c, logical.data(), dl.total);
+    }
+    return;
+  }
   if (!c.scannable)
     fail(EVQGPU_ERR_UNSUPPORTED, "column '%s' (logical type %u, encoding %u, rlevel_max %u) is outside the flat numeric scan path",
          c.meta.name.c_str(), c.meta.logical_type, c.meta.encoding, c.meta.rlevel_max);
@@ -645,7 +675,13 @@ int evqgpu_table_add_stream(evqgpu_table* tbl, const char* column, uint32_t kind
                                (flags & EVQGPU_STREAM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                                tbl->ctx->stream));
     const bool ready = c.data.present && (c.meta.dlevel_max == 0 || c.dlevel.present);
-    if (ready) {
+    if (ready && c.is_string) {
+      std::vector<uint8_t> logical(c.data.nbytes);
+      if (c.data.nbytes)
+        EVQ_CUDA(cudaMemcpyAsync(logical.data(), c.data.buf.p, c.data.nbytes, cudaMemcpyDeviceToHost, tbl->ctx->stream));
+      EVQ_CUDA(cudaStreamSynchronize(tbl->ctx->stream));
+      table_finish_string_column(tbl, c, logical.data(), c.data.nbytes);
+    } else if (ready) {
       if (!c.scannable) fail(EVQGPU_ERR_UNSUPPORTED, "column '%s' is outside the flat numeric scan path", column);
       table_finish_column(tbl, c);
     }

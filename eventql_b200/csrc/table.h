@@ -9,6 +9,10 @@
 //   sub_index[t][g] : byte offset inside tile t of its value 4g        (LEB128 columns whose values differ in length)
 //                     u16[ntiles][256] = 0.5 B per row; lets the fast scan kernel start two independent 4-value decode
 //                     chains per thread without searching value boundaries
+// Flat STRING_PLAIN columns (strings.cu) keep the data stream plus a value index built when the column is loaded:
+//   str_start[v] : byte offset of the payload of value v (behind its length prefix)   u64[nvalues]
+//   str_len[v]   : its length                                                         u32[nvalues]
+//   row_value[r] : value ordinal of record r, 0xffffffff = NULL                       u32[nrows]  (optional columns)
 // A row tile is EVQ_TILE_ROWS = 1024 records.
 #pragma once
 #include <string>
@@ -47,7 +51,12 @@ struct Column {
   uint64_t value_min = 0;      // statistic: smallest value (exact for the same columns, 0 otherwise; 0 when NULLs are present)
   uint32_t data_tile_cap = 0;  // max bytes one tile copy of the data stream can need (multiple of 16)
   uint32_t level_tile_cap = 0;
+  // flat string columns
+  bool is_string = false;
+  DevBuf str_start, str_len, row_value;
 };
+
+#define EVQ_KIND_STRING_HOST 255u   // Column::data_kind of string columns (host side only: the scan kernels never see them)
 
 }  // namespace evq
 
@@ -76,4 +85,6 @@ uint32_t sql_type_of(const ColumnMeta& m);
 void table_init_columns(evqgpu_table* t);
 void table_load_column(evqgpu_table* t, Column& c);
 void table_finish_column(evqgpu_table* t, Column& c);   // indexes + tile caps after the streams are on the device
+// strings.cu: value index of a string column whose streams are on the device; `host_stream` is the logical DATA stream
+void table_finish_string_column(evqgpu_table* t, Column& c, const uint8_t* host_stream, uint64_t nbytes);
 }  // namespace evq

@@ -18,6 +18,7 @@ from typing import List, Optional, Sequence, Tuple, Union
 NIL, UINT64, INT64, FLOAT64, BOOL, STRING, TIMESTAMP64 = range(7)
 TYPE_NAMES = ["nil", "uint64", "int64", "float64", "bool", "string", "timestamp64"]
 TYPE_BY_NAME = {n: i for i, n in enumerate(TYPE_NAMES)}
+STAG_NULL = 1   # csql::STag (sql/svalue.h:51-56)
 
 # evqgpu_insn.op
 X_CALL, X_LITERAL, X_INPUT, X_IF = 1, 3, 4, 6

@@ -31,6 +31,10 @@
  *                                        output in the packed SVector encoding of sql/svalue.cc:533-549
  *   evqgpu_query_merge                   sql/statements/select/groupby.cc:528-637 (GroupByMergeExpression)
  *   evqgpu_function_lookup               sql/runtime/symboltable.cc:33-39,162-175 (symbol strings)
+ *   evqgpu_table_decode_string_column    io/cstable/columns/column_reader_string.cc + page_reader_lenencstring.cc:37-62
+ *                                        (StringColumnReader::readString), sql/CSTableScan.cc:970-995 (fetchColumnString)
+ *   evqgpu_lsm_build_filters             server/sql/partition_cursor.cc:157-194,216-218 (the visibility filter loop of
+ *                                        PartitionCursor::openNextTable and its setFilter call)
  */
 #ifndef EVQGPU_H
 #define EVQGPU_H
@@ -42,7 +46,7 @@
 extern "C" {
 #endif
 
-#define EVQGPU_ABI_VERSION 2
+#define EVQGPU_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define EVQGPU_API __attribute__((visibility("default")))
@@ -189,7 +193,8 @@ EVQGPU_API int evqgpu_table_find_column(const evqgpu_table* tbl, const char* nam
 
 /* Make the named columns resident: host->device copy of their pages (async DMA when the file
  * image is pinned), then the device-side row-tile index and min/max statistics.  Idempotent.
- * names == NULL loads every flat, non-string column. */
+ * names == NULL loads every flat, non-string column; a flat STRING_PLAIN column is loaded when it is named (stream + the
+ * value index {start, length} + the record -> value map of optional columns). */
 EVQGPU_API int evqgpu_table_load_columns(evqgpu_table* tbl, const char* const* names, uint32_t n);
 
 /* Device -> host copy of one logical stream (tests, cstable export). nbytes_out may exceed cap:
@@ -202,6 +207,42 @@ EVQGPU_API int evqgpu_table_read_stream(evqgpu_table* tbl, const char* column, u
  * FastCSTableScan::fetchColumn* (sql/CSTableScan.cc:860-968) on its own, used by the decode parity tests. */
 EVQGPU_API int evqgpu_table_decode_column(evqgpu_table* tbl, const char* column, uint64_t row0, uint64_t nrows,
                                           void* dst, uint64_t cap);
+
+/* Decode rows [row0, row0 + nrows) of a flat STRING_PLAIN column (v0.2.0 `varuint length + bytes` values that may straddle
+ * pages, v0.1.0 `u32 length + bytes`) on the device into the packed STRING SVector FastCSTableScan::fetchColumnString
+ * builds (sql/CSTableScan.cc:970-995, sql/svalue.cc:533-549): present -> [u32 length][bytes][tag 0], NULL -> [u32 0][tag
+ * EVQ_STAG_NULL].  *nbytes_out = bytes needed; nothing is copied when dst == NULL or cap is smaller. */
+EVQGPU_API int evqgpu_table_decode_string_column(evqgpu_table* tbl, const char* column, uint64_t row0, uint64_t nrows,
+                                                 void* dst, uint64_t cap, uint64_t* nbytes_out);
+
+/* Read back the table's external row filter (1 bit per row, LSB first; (num_rows + 7) / 8 bytes).  *has_filter_out = 0
+ * when the table has none (nothing is copied). */
+EVQGPU_API int evqgpu_table_get_filter(evqgpu_table* tbl, void* bits, uint64_t cap_bytes, int* has_filter_out);
+
+/* ------------------------------------------------------------------------------------------
+ * LSM visibility: the row filters of a partition's segments, built on the device
+ * ---------------------------------------------------------------------------------------- */
+
+/* One table PartitionCursor::openNextTable visits (server/sql/partition_cursor.cc:82-155).  Segments are passed in the
+ * cursor's order: head arena, compacting arena, then the partition's LSM tables newest first. */
+#define EVQGPU_LSM_SKIP_COLUMN 1u   /* tbl->has_skiplist(): rows whose __lsm_skip column is true are dropped */
+#define EVQGPU_LSM_NO_FILTER 2u     /* the cursor's needs_filter == false (partition_cursor.cc:149-155): every row stays
+                                       visible, the segment's ids are not recorded, any filter of the table is removed */
+typedef struct evqgpu_lsm_segment {
+  evqgpu_table* table;      /* needs the reference's bookkeeping columns (db/partition_arena.cc:41-45): __lsm_id (string, 20
+                               bytes per value), __lsm_is_update and, with EVQGPU_LSM_SKIP_COLUMN, __lsm_skip (booleans) */
+  const void* skiplist;     /* arena skiplist (PartitionArena::SkiplistReader): host pointer, 1 bit per row, LSB first,
+                               1 = skip; overrides the column; NULL = none */
+  uint32_t flags;           /* EVQGPU_LSM_* */
+  uint32_t reserved;
+  uint64_t visible_rows;    /* out: rows the segment's filter keeps */
+} evqgpu_lsm_segment;
+
+/* Build and install (as with evqgpu_table_set_filter) the row filter of every segment: a row is dropped if it is skipped
+ * or if an earlier row - of an earlier segment, or earlier in its own - was a visible update with the same __lsm_id
+ * (partition_cursor.cc:157-194).  An id that is not 20 bytes long fails with EVQGPU_ERR_RUNTIME ("invalid SHA1Hash",
+ * util/SHA1.cc:79-85).  All segments must belong to `ctx`. */
+EVQGPU_API int evqgpu_lsm_build_filters(evqgpu_ctx* ctx, evqgpu_lsm_segment* segs, uint32_t nsegs);
 
 /* Write the table as a v0.2.0 cstable file (the layout of io/cstable/cstable_writer.cc:267-293). */
 EVQGPU_API int evqgpu_table_write_file(evqgpu_table* tbl, const char* path);

@@ -363,6 +363,119 @@ def decode_column(f: CSTableFile, name: str) -> DecodedColumn:
     return DecodedColumn(out, present, st)
 
 
+def decode_string_column(f: CSTableFile, name: str) -> List[Optional[bytes]]:
+    """One string (or None for NULL) per record of a flat STRING_PLAIN column, the way FastCSTableScan::fetchColumnString
+    consumes it (sql/CSTableScan.cc:970-995): StringColumnReader::readString reads a value only where the definition level
+    equals dlevel_max (columns/column_reader_string.cc).  v0.2.0 values are `varuint length + bytes` and may straddle pages
+    (columns/page_reader_lenencstring.cc:37-62); v0.1.0 values are `u32 length + bytes` (columns/v1/StringColumnReader.cc:94-113)."""
+    col = f.columns[name]
+    if col.storage_type != P.ENC_STRING_PLAIN:
+        raise OracleError("invalid storage type for string column '%s'" % name)
+    if col.rlevel_max > 0:
+        raise OracleError("repeated column %s: FastCSTableScan reads one entry per record (unsupported)" % name)
+    n = f.num_rows
+    if f.version == 2:
+        if col.dlevel_max > 0:
+            dstream, dmaxv = f.stream(col, P.STREAM_DLEVEL)
+            present = bitunpack_vertical(dstream, n, bits(dmaxv)) == np.uint64(col.dlevel_max)
+        else:
+            present = np.ones(n, dtype=bool)
+        data = f.stream(col, P.STREAM_DATA)[0].tobytes()
+    else:
+        body = f.data[col.body_offset: col.body_offset + col.body_size]
+        _num_vals, rsize, dsize, datasize = struct.unpack_from("<QQQQ", body, 0)
+        dl_stream = np.frombuffer(body[32 + rsize: 32 + rsize + dsize], dtype=np.uint8)
+        present = bitunpack_vertical(dl_stream, n, bits(col.dlevel_max)) == np.uint64(col.dlevel_max)
+        data = body[32 + rsize + dsize: 32 + rsize + dsize + datasize]
+    out: List[Optional[bytes]] = []
+    pos = 0
+    for i in range(n):
+        if not present[i]:
+            out.append(None)
+            continue
+        if f.version == 2:
+            if pos >= len(data):
+                raise OracleError("end of column reached")
+            ln, pos = read_varuint(data, pos)
+        else:
+            if pos + 4 > len(data):
+                raise OracleError("end of column reached")
+            ln = struct.unpack_from("<I", data, pos)[0]
+            pos += 4
+        if pos + ln > len(data):
+            raise OracleError("end of column reached")
+        out.append(data[pos:pos + ln])
+        pos += ln
+    return out
+
+
+def pack_svector_strings(vals: Sequence[Optional[bytes]]) -> bytes:
+    """The packed STRING SVector FastCSTableScan::fetchColumnString builds (sql/CSTableScan.cc:970-995, svalue.cc:533-549):
+    present -> [u32 length][bytes][tag 0]; NULL -> [u32 0][tag STAG_NULL]."""
+    out = bytearray()
+    for v in vals:
+        if v is None:
+            out += struct.pack("<I", 0) + bytes([P.STAG_NULL])
+        else:
+            out += struct.pack("<I", len(v)) + v + b"\0"
+    return bytes(out)
+
+
+def unpack_svector_strings(buf: bytes, n: int) -> List[Optional[bytes]]:
+    out: List[Optional[bytes]] = []
+    pos = 0
+    for _ in range(n):
+        ln = struct.unpack_from("<I", buf, pos)[0]
+        tag = buf[pos + 4 + ln]
+        out.append(None if (tag & P.STAG_NULL) else bytes(buf[pos + 4: pos + 4 + ln]))
+        pos += 5 + ln
+    if pos != len(buf):
+        raise OracleError("trailing bytes in a string SVector")
+    return out
+
+
+@dataclass
+class LsmSegment:
+    """One table PartitionCursor::openNextTable visits (server/sql/partition_cursor.cc:82-155), in its order: head arena,
+    compacting arena, then the on-disk LSM tables newest first."""
+    table: CSTableFile
+    skiplist: Optional[np.ndarray] = None   # arena skiplist (PartitionArena::SkiplistReader), one bool per row
+    use_skip_column: bool = False           # tbl->has_skiplist(): read the __lsm_skip column
+    needs_filter: bool = True               # partition_cursor.cc:149-155
+
+
+def lsm_visibility(segments: Sequence[LsmSegment]) -> List[Optional[np.ndarray]]:
+    """The row filters PartitionCursor::openNextTable hands to setFilter (server/sql/partition_cursor.cc:157-194, :216-218):
+    a row is dropped if it is skipped or if a row seen earlier (in an earlier table, or earlier in this one) was an update
+    with the same __lsm_id; visible update rows add their id to the set.  None = no filter (needs_filter == false: the
+    table's ids are not recorded either).  PARITY UNPINNED against the reference (the cursor needs a live partition
+    snapshot); the string and boolean column decode underneath it is pinned."""
+    id_set = set()
+    out: List[Optional[np.ndarray]] = []
+    for seg in segments:
+        n = seg.table.num_rows
+        if not seg.needs_filter:
+            out.append(None)
+            continue
+        ids = decode_string_column(seg.table, "__lsm_id")
+        upd = decode_column(seg.table, "__lsm_is_update").values != 0
+        skipcol = decode_column(seg.table, "__lsm_skip").values != 0 if seg.use_skip_column else np.zeros(n, dtype=bool)
+        flt = np.ones(n, dtype=bool)
+        for i in range(n):
+            ident = ids[i] if ids[i] is not None else b""
+            if len(ident) != 20:                         # SHA1Hash(const void*, size_t): util/SHA1.cc:79-85
+                raise OracleError("invalid SHA1Hash")
+            skip = bool(skipcol[i])
+            if seg.skiplist is not None:
+                skip = bool(seg.skiplist[i])
+            if skip or ident in id_set:
+                flt[i] = False
+            elif upd[i]:
+                id_set.add(ident)
+        out.append(flt)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # cstable writer, v0.2.0 (io/cstable/cstable_writer.cc:267-293, cstable.cc:138-198, page_manager.cc:45-75)
 # ------------------------------------------------------------------------------------------------
@@ -375,6 +488,7 @@ class WriteColumn:
     values: np.ndarray                    # uint64 raw bits per record
     nulls: Optional[np.ndarray] = None    # bool per record -> optional column (dlevel_max = 1)
     bitpack_max: int = 0xFFFFFFFF         # column_writer_uint.cc:57-63: data pages always use the default max
+    strings: Optional[Sequence[bytes]] = None   # STRING_PLAIN columns: one byte string per record (ignored where NULL)
 
 
 def _paginate(payload: np.ndarray, bitpacked: bool, maxv: int) -> List[bytes]:
@@ -428,7 +542,8 @@ def write_cstable(path: str, num_rows: int, columns: Sequence[WriteColumn], inte
         name = c.name.encode()
         hdr += write_varuint(c.logical_type) + write_varuint(c.encoding) + write_varuint(cid)
         hdr += write_varuint(len(name)) + name + write_varuint(0) + write_varuint(1 if optional else 0)
-        vals = np.asarray(c.values, dtype=np.uint64)
+        is_string = c.encoding == P.ENC_STRING_PLAIN
+        vals = np.zeros(num_rows, dtype=np.uint64) if is_string else np.asarray(c.values, dtype=np.uint64)
         assert len(vals) == num_rows
         level_bytes = 0
         if optional:
@@ -442,7 +557,16 @@ def write_cstable(path: str, num_rows: int, columns: Sequence[WriteColumn], inte
         maxv = 1 if c.encoding == P.ENC_BOOLEAN_BITPACKED else c.bitpack_max
         if c.encoding == P.ENC_BOOLEAN_BITPACKED:
             vals = (vals > 0).astype(np.uint64)
-        pay = encode_data(c.encoding, vals, maxv)
+        if is_string:
+            # columns/page_writer_lenencstring.cc:36-48: varuint length + bytes, values run across page boundaries
+            keep = np.ones(num_rows, dtype=bool) if not optional else ~np.asarray(c.nulls, dtype=bool)
+            blob = bytearray()
+            for i in range(num_rows):
+                if keep[i]:
+                    blob += write_varuint(len(c.strings[i])) + c.strings[i]
+            pay = np.frombuffer(bytes(blob), dtype=np.uint8)
+        else:
+            pay = encode_data(c.encoding, vals, maxv)
         streams.append((P.STREAM_DATA, cid, _paginate(pay, bitpacked, maxv)))
         sidecar[c.name] = {"data_bytes": int(len(pay)), "level_bytes": int(level_bytes), "num_values": int(len(vals))}
     pad = (-len(hdr)) % SECTOR

@@ -45,11 +45,13 @@ void registerExtensionAggregates(csql::SymbolTable* sym);
 static int usage() {
   fprintf(stderr,
       "usage:\n"
-      "  evqlref sql [-t name=file.cst]... [-n reps] [-x] [-P] -q 'SQL'\n"
+      "  evqlref sql [-t name=file.cst]... [-n reps] [-x] [-P] [-H] -q 'SQL'\n"
+      "      -H  print string values as x<hex> (NULL stays NULL)\n"
       "      -x  do NOT register the extension aggregates (min/max/mean/sum<float64>)\n"
-      "  evqlref write <out.cst> <v1|v2> <nrows> <name>:<uint|datetime|float|bool>:<encoding>:<optional 0|1>:<datafile>[:<nullfile>] ...\n"
+      "  evqlref write <out.cst> <v1|v2> <nrows> <name>:<uint|datetime|float|bool|string>:<encoding>:<optional 0|1>:<datafile>[:<nullfile>] ...\n"
       "      datafile = nrows x 8 B little-endian (u64 / double bits / 0|1); nullfile = nrows x 1 B (1 = NULL)\n"
-      "      encoding = leb128 | uint64 | uint32 | bitpacked | ieee754 | boolean\n"
+      "                 string columns: nrows x ([u32 length][bytes]) (an entry is read for NULL rows too)\n"
+      "      encoding = leb128 | uint64 | uint32 | bitpacked | ieee754 | boolean | string\n"
       "  evqlref info <file.cst>\n");
   return 2;
 }
@@ -134,6 +136,7 @@ static int cmdSql(int argc, char** argv) {
   int reps = 1;
   bool ext = true;
   bool partial = false;
+  bool hexstr = false;
   for (int i = 0; i < argc; ++i) {
     std::string a = argv[i];
     if (a == "-t" && i + 1 < argc) {
@@ -149,6 +152,8 @@ static int cmdSql(int argc, char** argv) {
       ext = false;
     } else if (a == "-P") {
       partial = true;
+    } else if (a == "-H") {
+      hexstr = true;
     } else {
       return usage();
     }
@@ -195,6 +200,11 @@ static int cmdSql(int argc, char** argv) {
           for (size_t i = 0; i < ncols; ++i) {
             if (i) line += ";";
             if (partial && cursor->getColumnType(i) == csql::SType::STRING) line += hexString(cursor->getColumnData(i));
+            else if (hexstr && cursor->getColumnType(i) == csql::SType::STRING) {
+              const uint8_t* sp = (const uint8_t*) cursor->getColumnData(i);
+              uint32_t slen; memcpy(&slen, sp, 4);
+              line += (sp[4 + slen] & csql::STAG_NULL) ? std::string("NULL") : "x" + hexString(sp);
+            }
             else line += fmtValue(cursor->getColumnType(i), cursor->getColumnData(i));
           }
           puts(line.c_str());
@@ -241,6 +251,7 @@ static cstable::ColumnEncoding parseEnc(const std::string& e) {
   if (e == "bitpacked") return cstable::ColumnEncoding::UINT32_BITPACKED;
   if (e == "ieee754") return cstable::ColumnEncoding::FLOAT_IEEE754;
   if (e == "boolean") return cstable::ColumnEncoding::BOOLEAN_BITPACKED;
+  if (e == "string") return cstable::ColumnEncoding::STRING_PLAIN;
   fprintf(stderr, "bad encoding %s\n", e.c_str());
   exit(2);
 }
@@ -267,6 +278,7 @@ static int cmdWrite(int argc, char** argv) {
     else if (c.type == "datetime") t = cstable::ColumnType::DATETIME;
     else if (c.type == "float") t = cstable::ColumnType::FLOAT;
     else if (c.type == "bool") t = cstable::ColumnType::BOOLEAN;
+    else if (c.type == "string") t = cstable::ColumnType::STRING;
     else return usage();
     schema.addColumn(c.name, t, parseEnc(c.enc), false, c.optional);
   }
@@ -287,6 +299,22 @@ static int cmdWrite(int argc, char** argv) {
       if (!nf) { perror(c.nullfile.c_str()); return 1; }
     }
     uint64_t dmax = c.optional ? 1 : 0;
+    if (c.type == "string") {
+      std::string val;
+      for (size_t i = 0; i < nrows; ++i) {
+        uint32_t len = 0;
+        if (fread(&len, 4, 1, df) != 1) { fprintf(stderr, "short read %s\n", c.datafile.c_str()); return 1; }
+        val.resize(len);
+        if (len && fread(&val[0], 1, len, df) != len) { fprintf(stderr, "short read %s\n", c.datafile.c_str()); return 1; }
+        uint8_t isnull = 0;
+        if (nf && fread(&isnull, 1, 1, nf) != 1) { fprintf(stderr, "short read %s\n", c.nullfile.c_str()); return 1; }
+        if (isnull) cw->writeNull(0, 0);
+        else cw->writeString(0, dmax, val);
+      }
+      fclose(df);
+      if (nf) fclose(nf);
+      continue;
+    }
     const size_t CH = 1 << 16;
     std::vector<uint64_t> buf(CH);
     std::vector<uint8_t> nbuf(CH);

@@ -497,3 +497,85 @@ def all_golden_cases():
     out = [(name, tname, plan, not plan.is_groupby) for name, tname, _alias, _sql, plan in golden_cases()]
     out += [(name, "testtbl.cst", plan, not plan.is_groupby) for name, _sql, plan in testtbl_queries()]
     return out
+
+
+# ---- string columns (SURVEY §8 a4 / a9 readString, fetchColumnString) and LSM segments (§8 f2) ----
+_VOCAB = [b"google.de", b"googleadservices.com", b"facebook", b"newsletter", b"DE-Special-post", b"", b"x", b"\x00\xff;\n",
+          b"GA2-DE-Search-Brand", b"a" * 127, b"b" * 128, b"c" * 129, "grüße".encode()]
+
+
+def synth_strings(seed: int, num_rows: int, null_every: int = 0):
+    """(list of bytes, nulls bool).  Lengths cover 0, 1, the 1 -> 2 byte varuint boundary (127 / 128), a few values of
+    ~100 KB (3-byte length prefixes; with 512 KiB pages several values straddle a page boundary) and embedded NUL /
+    separator bytes."""
+    rows = np.arange(num_rows, dtype=np.uint64)
+    r = splitmix64(np.uint64(seed) + rows)
+    out = []
+    for i in range(num_rows):
+        x = int(r[i])
+        w = _VOCAB[x % len(_VOCAB)]
+        if i % 397 == 396:
+            v = (w + b"|" + str(i).encode()) * (100_000 // (len(w) + 6))
+        elif x % 7 == 0:
+            v = w + b"-" + str(x % 1000).encode()
+        else:
+            v = w
+        out.append(v)
+    nulls = ((rows % np.uint64(null_every)) == np.uint64(null_every - 1)) if null_every else np.zeros(num_rows, dtype=bool)
+    return out, nulls
+
+
+STRINGS_ROWS = 2500
+
+
+def strings_table_columns(num_rows: int = STRINGS_ROWS):
+    """name -> (kind, values, nulls) of the string fixture table (tests/golden/ref_strings_v{1,2}.cst.gz)."""
+    import hashlib
+    k, _ = synth_values(dict(seed=41, lo=0, span=1000), num_rows)
+    s_req, _ = synth_strings(42, num_rows)
+    s_opt, nulls = synth_strings(43, num_rows, null_every=3)
+    ids = [hashlib.sha1(b"row-%d" % (int(x) % 600)).digest() for x in k]
+    return [("k", "uint", k, None), ("s_req", "string", s_req, None), ("s_opt", "string", s_opt, nulls), ("id", "string", ids, None)]
+
+
+def write_strings_table(path: str, num_rows: int = STRINGS_ROWS):
+    """The string fixture table written by the ORACLE's writer (test infrastructure)."""
+    from oracle import evq_oracle as O
+    cols = []
+    for name, kind, vals, nulls in strings_table_columns(num_rows):
+        if kind == "string":
+            cols.append(O.WriteColumn(name, P.COL_STRING, P.ENC_STRING_PLAIN, None, nulls, strings=vals))
+        else:
+            cols.append(O.WriteColumn(name, P.COL_UNSIGNED_INT, P.ENC_UINT64_LEB128, vals, nulls))
+    return O.write_cstable(path, num_rows, cols)
+
+
+def lsm_segment_columns(seg: int, num_rows: int, key_space: int = 400, seed: int = 77):
+    """Columns of one synthetic partition segment: the reference's bookkeeping columns (db/partition_arena.cc:41-45:
+    __lsm_is_update, __lsm_skip, __lsm_id = 20 raw bytes, __lsm_version, __lsm_sequence; all required) plus a payload
+    column.  Ids repeat inside a segment and across segments."""
+    import hashlib
+    rows = np.arange(num_rows, dtype=np.uint64)
+    r = splitmix64(np.uint64(seed + 1000 * seg) + rows)
+    key = r % np.uint64(key_space)
+    ids = [hashlib.sha1(b"id-%d" % int(x)).digest() for x in key]
+    is_update = ((r >> np.uint64(20)) % np.uint64(3) == 0).astype(np.uint64)
+    skip = ((r >> np.uint64(30)) % np.uint64(10) == 0).astype(np.uint64)
+    version = (r >> np.uint64(40)) % np.uint64(1000)
+    seq = rows + np.uint64(1 + 100000 * seg)
+    v = (r >> np.uint64(8)) % np.uint64(5000)
+    return dict(ids=ids, is_update=is_update, skip=skip, version=version, seq=seq, v=v, key=key)
+
+
+def write_lsm_segment(path: str, seg: int, num_rows: int, **kw):
+    from oracle import evq_oracle as O
+    c = lsm_segment_columns(seg, num_rows, **kw)
+    cols = [O.WriteColumn("__lsm_is_update", P.COL_BOOLEAN, P.ENC_BOOLEAN_BITPACKED, c["is_update"]),
+            O.WriteColumn("__lsm_skip", P.COL_BOOLEAN, P.ENC_BOOLEAN_BITPACKED, c["skip"]),
+            O.WriteColumn("__lsm_id", P.COL_STRING, P.ENC_STRING_PLAIN, None, strings=c["ids"]),
+            O.WriteColumn("__lsm_version", P.COL_UNSIGNED_INT, P.ENC_UINT64_LEB128, c["version"]),
+            O.WriteColumn("__lsm_sequence", P.COL_UNSIGNED_INT, P.ENC_UINT64_LEB128, c["seq"]),
+            O.WriteColumn("key", P.COL_UNSIGNED_INT, P.ENC_UINT64_LEB128, c["key"]),
+            O.WriteColumn("v", P.COL_UNSIGNED_INT, P.ENC_UINT64_LEB128, c["v"])]
+    O.write_cstable(path, num_rows, cols)
+    return c

@@ -489,10 +489,14 @@ def test_errors_are_loud(gpu_ctx, tmp_path):
     with pytest.raises(capi.EvqError):            # not a cstable
         gpu_ctx.open_table(np.zeros(1000, dtype=np.uint8))
     tbl.close()
-    # string columns are outside the numeric device path: loud, not silently skipped
+    # repeated columns and queries over string columns are outside the device scan path: loud, not silently skipped
+    # (flat string columns load and decode: tests/test_strings_lsm.py)
     t2 = gpu_ctx.open_table_file(os.path.join(GOLD, "testtbl.cst"))
     with pytest.raises(capi.EvqError) as ei:
-        t2.load(["session_id"])
+        t2.load(["event.search_query.query_string"])
+    assert ei.value.status == 2
+    with pytest.raises(capi.EvqError) as ei:
+        run_gpu(gpu_ctx, [t2], P.QueryPlan(["session_id"], [P.call("count", P.lit(1))], where=P.Col(0, P.UINT64) > 0))
     assert ei.value.status == 2
     t2.close()
 
