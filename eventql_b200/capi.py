@@ -65,12 +65,15 @@ class SortSpec(C.Structure):
 
 
 class LsmSegment(C.Structure):
-    _fields_ = [("table", C.c_void_p), ("skiplist", C.c_void_p), ("flags", C.c_uint32), ("reserved", C.c_uint32),
+    _fields_ = [("table", C.c_void_p), ("skiplist", C.c_void_p), ("flags", C.c_uint32), ("filtered", C.c_uint32),
                 ("visible_rows", C.c_uint64)]
 
 
 LSM_SKIP_COLUMN = 1
 LSM_NO_FILTER = 2
+LSM_HAS_UPDATES = 4
+LSM_OLDEST = 8
+LSM_AUTO = 16
 
 
 class DebugColumn(C.Structure):
@@ -316,13 +319,21 @@ class Context:
 
     def lsm_build_filters(self, segments) -> List[int]:
         """PartitionCursor's visibility filters (server/sql/partition_cursor.cc:157-194) for the segments of one
-        partition, in the cursor's order.  segments: (Table, skiplist bools or None, use_skip_column, needs_filter).
-        Installs each table's row filter; returns the visible rows per segment."""
+        partition, in the cursor's order.  segments: (Table, skiplist bools or None, use_skip_column, needs_filter[,
+        has_updates, oldest]); needs_filter None = the cursor's own rule (LSM_AUTO with has_updates / oldest).
+        Installs each table's row filter; returns the visible rows per segment (self.lsm_filtered: which got a filter)."""
         arr = (LsmSegment * max(1, len(segments)))()
         keep = []
-        for i, (tbl, skiplist, use_skip_column, needs_filter) in enumerate(segments):
+        for i, seg in enumerate(segments):
+            tbl, skiplist, use_skip_column, needs_filter = seg[:4]
+            has_updates, oldest = (seg[4], seg[5]) if len(seg) > 4 else (False, False)
             arr[i].table = tbl._h
-            arr[i].flags = (LSM_SKIP_COLUMN if use_skip_column else 0) | (0 if needs_filter else LSM_NO_FILTER)
+            fl = LSM_SKIP_COLUMN if use_skip_column else 0
+            if needs_filter is None:
+                fl |= LSM_AUTO | (LSM_HAS_UPDATES if has_updates else 0) | (LSM_OLDEST if oldest else 0)
+            elif not needs_filter:
+                fl |= LSM_NO_FILTER
+            arr[i].flags = fl
             if skiplist is not None:
                 bits = np.packbits(np.asarray(skiplist, dtype=bool), bitorder="little")
                 if bits.size == 0:
@@ -330,6 +341,7 @@ class Context:
                 keep.append(bits)
                 arr[i].skiplist = bits.ctypes.data_as(C.c_void_p)
         check(lib().evqgpu_lsm_build_filters(self._h, arr, len(segments)))
+        self.lsm_filtered = [bool(arr[i].filtered) for i in range(len(segments))]
         return [int(arr[i].visible_rows) for i in range(len(segments))]
 
     def host_alloc(self, nbytes: int) -> np.ndarray:

@@ -200,9 +200,20 @@ __device__ __forceinline__ u64 mix64(u64 x) {
 }
 
 __global__ void k_lsm_gather(LsmSegmentArgs a, u32* __restrict__ ids, u64* __restrict__ keys, u32* __restrict__ ords,
-                             u8* __restrict__ flags, u32* __restrict__ status) {
+                             u8* __restrict__ flags, u32* __restrict__ status, unsigned long long* __restrict__ live_updates) {
   const u64 r = (u64) blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= a.num_rows) return;
+  const bool in_range = r < a.num_rows;
+  // rows that would record their id (update, not skipped): counted per segment for the cursor's needs_filter rule
+  bool live = false;
+  if (in_range) {
+    live = a.upd_bits && vertical_get(a.upd_words, a.upd_bits, r) > 0;
+    bool sk = a.skip_words && a.skip_bits && vertical_get(a.skip_words, a.skip_bits, r) > 0;
+    if (a.skiplist) sk = (a.skiplist[r >> 3] >> (r & 7)) & 1;
+    live = live && !sk;
+  }
+  const u32 nlive = __popc(__ballot_sync(0xffffffffu, live));
+  if ((threadIdx.x & 31) == 0 && nlive) atomicAdd(live_updates, (unsigned long long) nlive);
+  if (!in_range) return;
   const u64 g = a.base + r;
   const u32 v = a.id_row_value ? a.id_row_value[r] : (u32) r;
   u32 w[5] = {0, 0, 0, 0, 0};
@@ -335,10 +346,11 @@ int evqgpu_lsm_build_filters(evqgpu_ctx* ctx, evqgpu_lsm_segment* segs, uint32_t
       if (!segs[i].table) fail(EVQGPU_ERR_ARG, "evqgpu_lsm_build_filters: segment %u has no table", i);
       if (segs[i].table->ctx != ctx) fail(EVQGPU_ERR_ARG, "evqgpu_lsm_build_filters: segment %u lives on another context", i);
       segs[i].visible_rows = segs[i].table->num_rows;
+      segs[i].filtered = 0;
       if (!(segs[i].flags & EVQGPU_LSM_NO_FILTER)) total += segs[i].table->num_rows;
     }
     if (total >= 0xffffffffull) fail(EVQGPU_ERR_UNSUPPORTED, "visibility filter over more than 2^32 - 1 rows");
-    DevBuf ids, keys_a, keys_b, ords_a, ords_b, flags, visible, status, tmp;
+    DevBuf ids, keys_a, keys_b, ords_a, ords_b, flags, visible, status, live, errs, tmp;
     ids.alloc(total * 20);
     keys_a.alloc(total * 8);
     keys_b.alloc(total * 8);
@@ -346,13 +358,20 @@ int evqgpu_lsm_build_filters(evqgpu_ctx* ctx, evqgpu_lsm_segment* segs, uint32_t
     ords_b.alloc(total * 4);
     flags.alloc(total);
     visible.alloc(total);
-    status.alloc(16);   // [0] error bits (u32), [8] visible-row counter (u64)
+    status.alloc(16);   // [8] visible-row counter (u64)
+    live.alloc((uint64_t) (nsegs + 1) * 8);   // per segment: rows that record their id (update, not skipped)
+    errs.alloc((uint64_t) (nsegs + 1) * 4);   // per segment: error bits
     EVQ_CUDA(cudaMemsetAsync(status.p, 0, 16, ctx->stream));
+    EVQ_CUDA(cudaMemsetAsync(errs.p, 0, (uint64_t) (nsegs + 1) * 4, ctx->stream));
+    EVQ_CUDA(cudaMemsetAsync(live.p, 0, (uint64_t) (nsegs + 1) * 8, ctx->stream));
     std::vector<DevBuf> skiplists(nsegs);
+    std::vector<uint64_t> bases(nsegs, 0);
     uint64_t base = 0;
     for (uint32_t i = 0; i < nsegs; ++i) {
       evqgpu_table* t = segs[i].table;
-      if ((segs[i].flags & EVQGPU_LSM_NO_FILTER) || t->num_rows == 0) continue;
+      if (segs[i].flags & EVQGPU_LSM_NO_FILTER) continue;
+      bases[i] = base;
+      if (t->num_rows == 0) continue;
       Column& id = string_column(t, "__lsm_id");
       Column& upd = lsm_bool_column(t, "__lsm_is_update");
       LsmSegmentArgs a;
@@ -377,11 +396,39 @@ int evqgpu_lsm_build_filters(evqgpu_ctx* ctx, evqgpu_lsm_segment* segs, uint32_t
       a.num_rows = t->num_rows;
       a.base = base;
       k_lsm_gather<<<(unsigned) ((t->num_rows + 255) / 256), 256, 0, ctx->stream>>>(a, ids.as<u32>(), keys_a.as<u64>(), ords_a.as<u32>(),
-                                                                                  flags.as<u8>(), status.as<u32>());
+                                                                                  flags.as<u8>(), errs.as<u32>() + i,
+                                                                                  live.as<unsigned long long>() + i);
       EVQ_CUDA(cudaGetLastError());
       ctx->kernel_launches++;
       base += t->num_rows;
     }
+    // which segments the cursor filters (partition_cursor.cc:139-155): with EVQGPU_LSM_AUTO a table without a skiplist is
+    // scanned unfiltered - and records no ids - when no id was recorded before it and it is the partition's oldest table or
+    // has no updates.  "No id recorded yet" == no filtered segment before it holds a non-skipped update row.
+    std::vector<uint64_t> live_h(nsegs + 1, 0);
+    std::vector<u32> errs_h(nsegs + 1, 0);
+    EVQ_CUDA(cudaMemcpyAsync(live_h.data(), live.p, (uint64_t) (nsegs + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    EVQ_CUDA(cudaMemcpyAsync(errs_h.data(), errs.p, (uint64_t) (nsegs + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<char> filtered(nsegs, 0);
+    bool id_set_empty = true;
+    for (uint32_t i = 0; i < nsegs; ++i) {
+      const uint32_t f = segs[i].flags;
+      if (f & EVQGPU_LSM_NO_FILTER) continue;
+      bool needs = true;
+      if (f & EVQGPU_LSM_AUTO) {
+        const bool has_skiplist = (f & EVQGPU_LSM_SKIP_COLUMN) || segs[i].skiplist;
+        if (!has_skiplist && (f & EVQGPU_LSM_OLDEST) && id_set_empty) needs = false;
+        if (!has_skiplist && !(f & EVQGPU_LSM_HAS_UPDATES) && id_set_empty) needs = false;
+      }
+      filtered[i] = needs;
+      if (needs && live_h[i] > 0) id_set_empty = false;
+      if (!needs && segs[i].table->num_rows)   // its rows take no part: as if skipped
+        EVQ_CUDA(cudaMemsetAsync(flags.as<u8>() + bases[i], LSM_SKIP, segs[i].table->num_rows, ctx->stream));
+    }
+    // the reference converts every id it reads; the ids of a segment it does not filter are never read
+    for (uint32_t i = 0; i < nsegs; ++i)
+      if (filtered[i] && (errs_h[i] & LSM_ERR_ID_LENGTH)) fail(EVQGPU_ERR_RUNTIME, "invalid SHA1Hash");
     if (total) {
       size_t tmp_bytes = 0;
       EVQ_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_a.as<u64>(), keys_b.as<u64>(), ords_a.as<u32>(), ords_b.as<u32>(),
@@ -395,14 +442,9 @@ int evqgpu_lsm_build_filters(evqgpu_ctx* ctx, evqgpu_lsm_segment* segs, uint32_t
       EVQ_CUDA(cudaGetLastError());
       ctx->kernel_launches++;
     }
-    u32 err = 0;
-    EVQ_CUDA(cudaMemcpyAsync(&err, status.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (err & LSM_ERR_ID_LENGTH) fail(EVQGPU_ERR_RUNTIME, "invalid SHA1Hash");
-    base = 0;
     for (uint32_t i = 0; i < nsegs; ++i) {
       evqgpu_table* t = segs[i].table;
-      if (segs[i].flags & EVQGPU_LSM_NO_FILTER) {   // partition_cursor.cc:216-218: no setFilter call
+      if (!filtered[i]) {   // partition_cursor.cc:216-218: no setFilter call
         t->filter.release();
         t->has_filter = false;
         continue;
@@ -413,16 +455,16 @@ int evqgpu_lsm_build_filters(evqgpu_ctx* ctx, evqgpu_lsm_segment* segs, uint32_t
       if (t->num_rows) {
         EVQ_CUDA(cudaMemsetAsync((u8*) status.p + 8, 0, 8, ctx->stream));
         const uint64_t nb = (t->num_rows + 7) / 8;
-        k_lsm_pack<<<(unsigned) ((nb + 255) / 256), 256, 0, ctx->stream>>>(visible.as<u8>(), base, t->num_rows, t->filter.as<u8>(),
+        k_lsm_pack<<<(unsigned) ((nb + 255) / 256), 256, 0, ctx->stream>>>(visible.as<u8>(), bases[i], t->num_rows, t->filter.as<u8>(),
                                                                          (unsigned long long*) ((u8*) status.p + 8));
         EVQ_CUDA(cudaGetLastError());
         ctx->kernel_launches++;
         EVQ_CUDA(cudaMemcpyAsync(&cnt, (u8*) status.p + 8, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
       }
+      EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
       segs[i].visible_rows = cnt;
+      segs[i].filtered = 1;
       t->has_filter = true;
-      base += t->num_rows;
     }
   });
 }

@@ -177,6 +177,40 @@ int main(int argc, char** argv) {
       }
       return 0;
     }
+    if (mode == "partition" && argc >= 4) {
+      // evqgpu_sql partition <column> <seg.cst>[:flags]...   flags: a = arena (skiplist: every 7th row), s = has_skiplist,
+      // u = has_updates; segments in the cursor's order.  `select <column> from t where <column> >= 0` through
+      // GpuPartitionCursor (PartitionCursor::nextBatch, server/sql/partition_cursor.cc:56-80)
+      std::vector<std::pair<std::string, SType>> in = {{argv[2], U}};
+      auto scan = std::make_shared<SequentialScanNode>("t", in, std::vector<SelectRef>{sel(col(0))}, cmp("gte", col(0), u(0)));
+      std::vector<GpuPartitionSegment> segs;
+      for (int i = 3; i < argc; ++i) {
+        std::string a = argv[i];
+        GpuPartitionSegment sg;
+        const size_t c = a.rfind(':');
+        std::string fl;
+        if (c != std::string::npos && a.find('/', c) == std::string::npos) { fl = a.substr(c + 1); a = a.substr(0, c); }
+        sg.cstable_filename = a;
+        sg.is_arena = fl.find('a') != std::string::npos;
+        sg.has_skiplist = fl.find('s') != std::string::npos;
+        sg.has_updates = fl.find('u') != std::string::npos;
+        if (sg.is_arena) {
+          const uint64_t n = evqgpu_table_num_rows(gpu.openTable(a));
+          sg.arena_skiplist.resize(n);
+          for (uint64_t r = 0; r < n; ++r) sg.arena_skiplist[r] = r % 7 == 3;
+        }
+        segs.push_back(std::move(sg));
+      }
+      GpuPartitionCursor cursor(&gpu, scan, segs);
+      const int rc = pull(&cursor);
+      if (rc == 0) {
+        std::string line = "#visible";
+        for (size_t i = 0; i < segs.size(); ++i)
+          line += " " + std::to_string(cursor.visibleRows()[i]) + (cursor.filtered()[i] ? "f" : "u");
+        fprintf(stderr, "%s\n", line.c_str());
+      }
+      return rc;
+    }
     if (mode == "top" && argc >= 6) {
       GpuTableProvider provider(&gpu, "t", {argv[2]});
       std::vector<std::pair<std::string, SType>> in = {{argv[3], U}};

@@ -128,6 +128,72 @@ ReturnCode GpuQueryExpression::refresh() {
   return ReturnCode::success();
 }
 
+// ---- PartitionCursor: the segments of one partition behind their visibility filters -------------------------------------
+
+GpuPartitionCursor::GpuPartitionCursor(GpuContext* gpu, std::shared_ptr<SequentialScanNode> stmt, std::vector<GpuPartitionSegment> segments)
+    : GpuQueryExpression(gpu, {}), stmt_(std::move(stmt)), segments_(std::move(segments)) {
+  for (const auto& s : segments_) filenames_.push_back(s.cstable_filename);
+}
+
+ReturnCode GpuPartitionCursor::execute() {
+  try {
+    // (1) the filters (partition_cursor.cc:157-194), all segments in one device pass
+    std::vector<evqgpu_lsm_segment> segs(segments_.size());
+    std::vector<std::vector<uint8_t>> skipbits(segments_.size());
+    int oldest = -1;
+    for (size_t i = 0; i < segments_.size(); ++i)
+      if (!segments_[i].is_arena) oldest = (int) i;
+    for (size_t i = 0; i < segments_.size(); ++i) {
+      const GpuPartitionSegment& s = segments_[i];
+      memset(&segs[i], 0, sizeof(segs[i]));
+      segs[i].table = gpu_->openTable(s.cstable_filename);
+      if (s.is_arena) {
+        // arenas are always filtered, rows are skipped by the arena's skiplist (partition_cursor.cc:92-127, :181-183)
+        const uint64_t n = evqgpu_table_num_rows(segs[i].table);
+        if (s.arena_skiplist.size() != n) return ReturnCode::error("ERUNTIME", "arena skiplist does not match the arena's row count");
+        skipbits[i].assign((n + 7) / 8 + 1, 0);
+        for (uint64_t r = 0; r < n; ++r)
+          if (s.arena_skiplist[r]) skipbits[i][r >> 3] |= (uint8_t) (1u << (r & 7));
+        segs[i].skiplist = skipbits[i].data();
+      } else {
+        segs[i].flags = EVQGPU_LSM_AUTO | (s.has_skiplist ? EVQGPU_LSM_SKIP_COLUMN : 0u) | (s.has_updates ? EVQGPU_LSM_HAS_UPDATES : 0u) |
+                        ((int) i == oldest ? EVQGPU_LSM_OLDEST : 0u);
+      }
+    }
+    if (evqgpu_lsm_build_filters(gpu_->handle(), segs.data(), (uint32_t) segs.size()) != EVQGPU_OK)
+      return ReturnCode::error("ERUNTIME", lastError());
+    visible_rows_.clear();
+    filtered_.clear();
+    for (const auto& s : segs) {
+      visible_rows_.push_back(s.visible_rows);
+      filtered_.push_back(s.filtered != 0);
+    }
+    // (2) one scan over the segments in the cursor's order (FastCSTableScan per segment in the reference, :196-203)
+    const std::vector<std::string> cols = stmt_->selectedColumns();
+    std::vector<const char*> names;
+    for (const auto& c : cols) names.push_back(c.c_str());
+    Program where = translate(stmt_->whereExpression());
+    std::vector<Program> sel;
+    for (const auto& s : stmt_->selectList()) sel.push_back(translate(s->expression()));
+    std::vector<evqgpu_expr> selv;
+    for (const auto& p : sel) selv.push_back(p.view());
+    evqgpu_query_desc d;
+    memset(&d, 0, sizeof(d));
+    d.struct_size = sizeof(d);
+    d.num_input_columns = (uint32_t) names.size();
+    d.input_columns = names.data();
+    d.where = where.view();
+    d.num_select = (uint32_t) selv.size();
+    d.select = selv.data();
+    const ReturnCode rc = run(d);
+    // the filters belong to this cursor's snapshot, the resident tables are shared
+    for (auto& s : segs) evqgpu_table_set_filter(s.table, nullptr, 0, 0);
+    return rc;
+  } catch (const std::exception& e) {
+    return ReturnCode::error("ERUNTIME", e.what());
+  }
+}
+
 // ---- ORDER BY / LIMIT over a device-resident result ----------------------------------------------------------------------
 
 GpuOrderByExpression::GpuOrderByExpression(std::vector<GpuSortSpec> sort_specs, std::unique_ptr<GpuQueryExpression> input)

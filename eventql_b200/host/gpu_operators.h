@@ -4,6 +4,7 @@
 //   evql_b200::GpuCSTableScan          csql::FastCSTableScan        sql/CSTableScan.h:126-189, CSTableScan.cc:691-995
 //   evql_b200::GpuGroupByExpression    csql::GroupByExpression over a FastCSTableScan input, fused into one device pass
 //                                      sql/statements/select/groupby.h:34-66, groupby.cc:69-220
+//   evql_b200::GpuPartitionCursor      eventql::PartitionCursor      server/sql/partition_cursor.cc:56-225 (visibility filters)
 //   evql_b200::GpuTableProvider        csql::CSTableScanProvider     sql/CSTableScanProvider.cc:38-113
 //   evql_b200::buildGroupByExpression  what a DefaultScheduler subclass returns from its virtual buildGroupByExpression
 //                                      (sql/scheduler.cc:153-182), cf. eventql::Scheduler (server/sql/scheduler.cc:55-77)
@@ -76,6 +77,34 @@ private:
   std::shared_ptr<csql::SequentialScanNode> stmt_;
   std::vector<bool> filter_;
   bool filter_enabled_ = false;
+};
+
+// eventql::PartitionCursor (server/sql/partition_cursor.h:38-70, partition_cursor.cc:56-225): the scan of ONE partition,
+// i.e. of its segments - head arena, compacting arena, then the on-disk LSM tables newest first - each behind its
+// visibility filter.  The reference opens the segments one after the other and builds every filter with a row loop over
+// __lsm_id / __lsm_is_update / __lsm_skip and a std::set<SHA1Hash>; here the filters of all segments are built in one device
+// pass (evqgpu_lsm_build_filters) and the segments are scanned as one table, in the cursor's order.
+struct GpuPartitionSegment {
+  std::string cstable_filename;
+  bool is_arena = false;             // head / compacting arena: always filtered, skiplist from the arena
+  std::vector<bool> arena_skiplist;  // PartitionArena::SkiplistReader, one flag per row (arena segments)
+  bool has_skiplist = false;         // LSMTableRef::has_skiplist: the table carries a __lsm_skip column
+  bool has_updates = false;          // LSMTableRef::has_updates
+};
+class GpuPartitionCursor : public GpuQueryExpression {
+public:
+  // segments in scan order (partition_cursor.cc:92-140): arenas first, then lsm_tables() from the back; the last
+  // non-arena segment is the partition's oldest table (tblidx == 0)
+  GpuPartitionCursor(GpuContext* gpu, std::shared_ptr<csql::SequentialScanNode> stmt, std::vector<GpuPartitionSegment> segments);
+  csql::ReturnCode execute() override;
+  // rows each segment's filter kept / whether it was filtered at all (needs_filter, partition_cursor.cc:149-155)
+  const std::vector<uint64_t>& visibleRows() const { return visible_rows_; }
+  const std::vector<bool>& filtered() const { return filtered_; }
+private:
+  std::shared_ptr<csql::SequentialScanNode> stmt_;
+  std::vector<GpuPartitionSegment> segments_;
+  std::vector<uint64_t> visible_rows_;
+  std::vector<bool> filtered_;
 };
 
 // GroupByExpression whose input is a sequential scan of cstable partitions: scan + filter + aggregate in one device pass

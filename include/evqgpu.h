@@ -228,14 +228,19 @@ EVQGPU_API int evqgpu_table_get_filter(evqgpu_table* tbl, void* bits, uint64_t c
 #define EVQGPU_LSM_SKIP_COLUMN 1u   /* tbl->has_skiplist(): rows whose __lsm_skip column is true are dropped */
 #define EVQGPU_LSM_NO_FILTER 2u     /* the cursor's needs_filter == false (partition_cursor.cc:149-155): every row stays
                                        visible, the segment's ids are not recorded, any filter of the table is removed */
+#define EVQGPU_LSM_HAS_UPDATES 4u   /* LSMTableRef::has_updates of an on-disk table */
+#define EVQGPU_LSM_OLDEST 8u        /* the partition's oldest on-disk table (tblidx == 0, visited last) */
+#define EVQGPU_LSM_AUTO 16u         /* decide needs_filter by the cursor's own rule (partition_cursor.cc:149-155): a table
+                                       without a skiplist is scanned unfiltered when no id has been recorded before it and it
+                                       is the oldest table or has no updates */
 typedef struct evqgpu_lsm_segment {
   evqgpu_table* table;      /* needs the reference's bookkeeping columns (db/partition_arena.cc:41-45): __lsm_id (string, 20
                                bytes per value), __lsm_is_update and, with EVQGPU_LSM_SKIP_COLUMN, __lsm_skip (booleans) */
   const void* skiplist;     /* arena skiplist (PartitionArena::SkiplistReader): host pointer, 1 bit per row, LSB first,
                                1 = skip; overrides the column; NULL = none */
   uint32_t flags;           /* EVQGPU_LSM_* */
-  uint32_t reserved;
-  uint64_t visible_rows;    /* out: rows the segment's filter keeps */
+  uint32_t filtered;        /* out: 1 = a filter was installed, 0 = the segment is scanned unfiltered */
+  uint64_t visible_rows;    /* out: rows the segment's filter keeps (all rows when unfiltered) */
 } evqgpu_lsm_segment;
 
 /* Build and install (as with evqgpu_table_set_filter) the row filter of every segment: a row is dropped if it is skipped

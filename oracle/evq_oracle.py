@@ -441,7 +441,9 @@ class LsmSegment:
     table: CSTableFile
     skiplist: Optional[np.ndarray] = None   # arena skiplist (PartitionArena::SkiplistReader), one bool per row
     use_skip_column: bool = False           # tbl->has_skiplist(): read the __lsm_skip column
-    needs_filter: bool = True               # partition_cursor.cc:149-155
+    needs_filter: Optional[bool] = True     # None: the cursor's rule for on-disk tables (partition_cursor.cc:149-155)
+    has_updates: bool = False               # LSMTableRef::has_updates
+    oldest: bool = False                    # tblidx == 0
 
 
 def lsm_visibility(segments: Sequence[LsmSegment]) -> List[Optional[np.ndarray]]:
@@ -454,7 +456,15 @@ def lsm_visibility(segments: Sequence[LsmSegment]) -> List[Optional[np.ndarray]]
     out: List[Optional[np.ndarray]] = []
     for seg in segments:
         n = seg.table.num_rows
-        if not seg.needs_filter:
+        needs = seg.needs_filter
+        if needs is None:                                # partition_cursor.cc:139-155
+            needs = True
+            has_skiplist = seg.use_skip_column or seg.skiplist is not None
+            if not has_skiplist and seg.oldest and not id_set:
+                needs = False
+            if not has_skiplist and not seg.has_updates and not id_set:
+                needs = False
+        if not needs:
             out.append(None)
             continue
         ids = decode_string_column(seg.table, "__lsm_id")

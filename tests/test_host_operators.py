@@ -125,3 +125,35 @@ def test_partial_groupby_operator_rows(native_lib):
     assert len(got) == 213
     ok, why = T.partial_rows_equal(plan, got, want)
     assert ok, why
+
+
+@pytest.mark.gpu
+def test_partition_cursor_operator(native_lib, tmp_path):
+    """GpuPartitionCursor (eventql::PartitionCursor, server/sql/partition_cursor.cc:56-225): an arena with a skiplist, then
+    on-disk tables newest first with the cursor's own needs_filter rule; the rows it returns, in order, are the visible rows
+    of the oracle's restatement of the filter loop."""
+    import numpy as np
+    from eventql_b200 import plan as P
+    from oracle import evq_oracle as O
+    sizes = [1500, 2100, 1200, 800]
+    files, cols = [], []
+    for i, n in enumerate(sizes):
+        p = str(tmp_path / ("seg%d.cst" % i))
+        cols.append(T.write_lsm_segment(p, i, n, key_space=350))
+        files.append(p)
+    flags = ["a", "su", "u", ""]          # arena; has_skiplist + has_updates; has_updates; oldest table, no updates flag
+    rc, lines, err = run_sql("partition", "v", *["%s:%s" % (f, fl) if fl else f for f, fl in zip(files, flags)])
+    assert rc == 0, (lines, err)
+    arena_skip = (np.arange(sizes[0]) % 7) == 3
+    segs = [O.LsmSegment(O.read_cstable(files[0]), arena_skip, False, True),
+            O.LsmSegment(O.read_cstable(files[1]), None, True, None, True, False),
+            O.LsmSegment(O.read_cstable(files[2]), None, False, None, True, False),
+            O.LsmSegment(O.read_cstable(files[3]), None, False, None, False, True)]
+    vis = O.lsm_visibility(segs)
+    want = []
+    for i in range(4):
+        keep = np.ones(sizes[i], dtype=bool) if vis[i] is None else vis[i]
+        want += [int(x) for x in cols[i]["v"][keep]]
+    assert [int(l) for l in lines] == want
+    summary = [l for l in err.split("\n") if l.startswith("#visible")][0].split()[1:]
+    assert summary == ["%d%s" % (sizes[i] if vis[i] is None else int(vis[i].sum()), "u" if vis[i] is None else "f") for i in range(4)]
