@@ -94,7 +94,7 @@ SYMBOLS = [
     "evqgpu_query_column_type", "evqgpu_query_execute", "evqgpu_query_enqueue", "evqgpu_query_finish",
     "evqgpu_query_num_rows", "evqgpu_query_fetch", "evqgpu_query_order_by", "evqgpu_query_limit", "evqgpu_query_fetch_partial", "evqgpu_query_get_stats", "evqgpu_query_kernel_source",
     "evqgpu_comm_unique_id", "evqgpu_comm_init", "evqgpu_comm_destroy", "evqgpu_query_merge", "evqgpu_debug_generate",
-    "evqgpu_table_decode_string_column", "evqgpu_table_get_filter", "evqgpu_lsm_build_filters",
+    "evqgpu_table_decode_string_column", "evqgpu_table_get_filter", "evqgpu_lsm_build_filters", "evqgpu_query_fetch_strings",
 ]
 
 _lib = None
@@ -160,6 +160,7 @@ def lib() -> C.CDLL:
     L.evqgpu_query_finish.argtypes = [vp]
     L.evqgpu_query_num_rows.argtypes = [vp, C.POINTER(u64)]
     L.evqgpu_query_fetch.argtypes = [vp, u64, u64, C.POINTER(vp), C.POINTER(u64)]
+    L.evqgpu_query_fetch_strings.argtypes = [vp, u32, u64, u64, vp, u64, C.POINTER(u64), C.POINTER(u64)]
     L.evqgpu_query_order_by.argtypes = [vp, C.POINTER(SortSpec), u32]
     L.evqgpu_query_limit.argtypes = [vp, u64, u64]
     L.evqgpu_query_fetch_partial.argtypes = [vp, u64, u64, vp, vp, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
@@ -517,6 +518,17 @@ class Query:
         check(lib().evqgpu_query_fetch(self._h, row0, max_rows, ptrs, C.byref(got)))
         return [b[: got.value * w].tobytes() for b, w in zip(bufs, widths)]
 
+    def fetch_strings(self, column: int, row0: int = 0, max_rows: Optional[int] = None) -> bytes:
+        """A string result column as packed STRING SVector elements ([u32 length][bytes][tag])."""
+        if max_rows is None:
+            max_rows = self.num_rows - row0
+        got, need = C.c_uint64(0), C.c_uint64(0)
+        check(lib().evqgpu_query_fetch_strings(self._h, column, row0, max_rows, None, 0, C.byref(got), C.byref(need)))
+        buf = np.zeros(max(1, need.value), dtype=np.uint8)
+        check(lib().evqgpu_query_fetch_strings(self._h, column, row0, max_rows, buf.ctypes.data_as(C.c_void_p), buf.nbytes,
+                                               C.byref(got), C.byref(need)))
+        return buf[: need.value].tobytes()
+
     def fetch_partial(self) -> List[tuple]:
         """The groups as PartialGroupByExpression rows: [(20-byte SHA-1 group key, saved states)] (plan flag QUERY_WIRE)."""
         n = self.num_rows
@@ -545,9 +557,18 @@ class Query:
         cols = self.fetch_packed()
         n = len(cols[0]) // (2 if self.types[0] == P.BOOL else 9) if cols else 0
         out_cols = []
-        for raw, t in zip(cols, self.types):
+        for ci, (raw, t) in enumerate(zip(cols, self.types)):
             a = np.frombuffer(raw, dtype=np.uint8)
-            if t == P.BOOL:
+            if t == P.STRING:
+                # fetch_packed holds the dictionary codes; the values come from evqgpu_query_fetch_strings
+                buf = self.fetch_strings(ci)
+                vals, pos = [], 0
+                for _ in range(n):
+                    ln = int.from_bytes(buf[pos:pos + 4], "little")
+                    vals.append(None if buf[pos + 4 + ln] & 1 else buf[pos + 4:pos + 4 + ln])
+                    pos += 5 + ln
+                assert pos == len(buf)
+            elif t == P.BOOL:
                 a = a.reshape(n, 2)
                 vals = [None if tag & 1 else bool(v) for v, tag in zip(a[:, 0].tolist(), a[:, 1].tolist())]
             else:

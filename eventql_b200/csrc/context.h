@@ -4,6 +4,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <unordered_map>
 #include <vector>
 #include "util.h"
 
@@ -26,6 +27,10 @@ struct evqgpu_ctx {
   void* pinned_scratch = nullptr;   // 4 KiB pinned
   uint64_t kernel_launches = 0;     // total kernels launched through this context
   bool profiling = false;           // bracket scan kernel launches with events (evqgpu_ctx_set_profiling)
+  // string dictionary of the context (strings.cu): every distinct value of a string column a query touches, and every
+  // string literal, gets a dense code; code 0 is the empty string (what a NULL string compares as, boolean.cc:235-257)
+  std::unordered_map<std::string, uint32_t> string_codes;
+  std::vector<std::string> code_strings;
 };
 
 namespace evq {

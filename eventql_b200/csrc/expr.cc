@@ -38,7 +38,7 @@ const std::vector<FnInfo>& function_table() {
     reg("logical_or", Fn::LOGICAL_OR, B, {B, B});
     reg("neg", Fn::NEG, B, {B});
     for (int ty : {U, I, F, T}) reg("cmp", Fn::CMP, I, {ty, ty});
-    for (int ty : {U, I, F, B, T}) {
+    for (int ty : {U, I, F, B, S, T}) {   // string eq / neq: lowered to dictionary codes at intake (query.cu: lower_strings)
       reg("eq", Fn::EQ, B, {ty, ty});
       reg("neq", Fn::NEQ, B, {ty, ty});
     }

@@ -304,6 +304,8 @@ void merge_query(evqgpu_query& q) {
   }
   if (!(q.flags & EVQGPU_QUERY_PARTIAL))
     fail(EVQGPU_ERR_ARG, "evqgpu_query_merge: the plan was not created with EVQGPU_QUERY_PARTIAL");
+  if (q.string_keys)   // dictionary codes are per context: the ranks' codes for one string differ
+    fail(EVQGPU_ERR_UNSUPPORTED, "evqgpu_query_merge: string GROUP BY keys cannot be merged across ranks");
   // the state layout depends on which columns are optional: all ranks must have arrived at the same one
   {
     std::string sig = std::to_string(q.shape.tier) + "/" + std::to_string(q.shape.g1) + "/";

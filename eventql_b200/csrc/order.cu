@@ -100,6 +100,9 @@ int evqgpu_query_order_by(evqgpu_query* q, const evqgpu_sort_spec* specs, uint32
     for (uint32_t i = 0; i < nspecs; ++i)
       if (specs[i].column >= q->select.size())
         fail(EVQGPU_ERR_ARG, "evqgpu_query_order_by: sort column %u of %zu", specs[i].column, q->select.size());
+    for (uint32_t i = 0; i < nspecs; ++i)
+      if (q->select[specs[i].column].is_string)   // the device column holds dictionary codes, which carry no order
+        fail(EVQGPU_ERR_UNSUPPORTED, "evqgpu_query_order_by: ORDER BY a string column");
     const uint64_t n = q->num_rows_out;
     if (n >= (1ull << 32)) fail(EVQGPU_ERR_UNSUPPORTED, "ORDER BY over more than 2^32 result rows");
     if (n < 2) return;

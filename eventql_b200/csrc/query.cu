@@ -33,21 +33,30 @@ static void ensure(DevBuf& b, uint64_t bytes) {
 
 // ---- binding of the plan's input columns to one table -------------------------------------------------------------
 struct Binding {
-  std::vector<int> col_index;   // plan input column -> table column (or -1 when unused)
+  std::vector<int> col_index;          // plan input column -> table column (or -1 when unused)
+  std::vector<const Column*> cols;     // ... and the column the kernels read: the table's own, or the code column of a string column
 };
 
 static Binding bind_table(const evqgpu_query& q, evqgpu_table* t) {
   Binding b;
   b.col_index.assign(q.input_columns.size(), -1);
+  b.cols.assign(q.input_columns.size(), nullptr);
   for (size_t i = 0; i < q.input_columns.size(); ++i) {
     if (!q.col_used[i]) continue;
     const int ci = t->find(q.input_columns[i].c_str());
     if (ci < 0) fail(EVQGPU_ERR_ARG, "column not found: %s", q.input_columns[i].c_str());
+    b.col_index[i] = ci;
+    if (q.col_is_string[i]) {
+      if (!t->cols[ci].is_string)
+        fail(EVQGPU_ERR_ARG, "column '%s' is used as a string but is not a flat string column", q.input_columns[i].c_str());
+      b.cols[i] = ensure_code_column(t, t->cols[ci]);
+      continue;
+    }
     if (!t->cols[ci].scannable)
       fail(EVQGPU_ERR_UNSUPPORTED, "column '%s' (logical type %u, encoding %u, rlevel_max %u) is outside the flat numeric scan path",
            q.input_columns[i].c_str(), t->cols[ci].meta.logical_type, t->cols[ci].meta.encoding, t->cols[ci].meta.rlevel_max);
     if (!t->cols[ci].loaded) table_load_column(t, t->cols[ci]);
-    b.col_index[i] = ci;
+    b.cols[i] = &t->cols[ci];
   }
   return b;
 }
@@ -71,7 +80,7 @@ static KernelShape shape_for(const evqgpu_query& q, evqgpu_table* t, const Bindi
   s.fast = true;
   for (size_t i = 0; i < q.input_columns.size(); ++i) {
     if (b.col_index[i] < 0) continue;
-    const Column& c = t->cols[b.col_index[i]];
+    const Column& c = *b.cols[i];
     ColSig& cs = s.cols[i];
     cs.used = true;
     cs.sql_type = c.sql_type;
@@ -149,7 +158,7 @@ static StageLayout stage_layout(const evqgpu_query& q, evqgpu_table* t, const Bi
   for (size_t i = 0; i < s.cols.size(); ++i) {
     const ColSig& cs = s.cols[i];
     if (!cs.used) continue;
-    const Column& c = t->cols[b.col_index[i]];
+    const Column& c = *b.cols[i];
     auto place = [&](int stream, uint32_t cap) {
       // regions are packed at TMA granularity (16 bytes); decoders may read a few values past a payload (short last
       // tile), which lands in the next region or in the tail pad of the stage
@@ -210,12 +219,55 @@ static void check_scalar_item(const evqgpu_query& q, const Expr* e) {
 
 namespace evq {
 
+// String support (strings.cu): eq / neq between string columns and string literals, and bare string columns as GROUP BY
+// expressions / select items, are rewritten to the columns' dictionary codes (evqgpu_ctx::string_codes; NULL reads as code
+// 0 = "", which is what eq_string sees for a NULL, boolean.cc:235-257).  Everything else typed STRING is refused.
+static void lower_string_leaf(evqgpu_query* q, Expr* a) {
+  if (a->op == EVQ_X_INPUT) {
+    if (a->col >= q->col_is_string.size()) fail(EVQGPU_ERR_ARG, "expression references input column %u of %zu", a->col, q->col_is_string.size());
+    q->col_is_string[a->col] = true;
+  } else if (a->op == EVQ_X_LITERAL) {
+    if (!q->ctx) fail(EVQGPU_ERR_UNSUPPORTED, "string literals need a context (dictionary codes)");
+    a->imm = string_code(q->ctx, a->str);
+    a->str.clear();
+  } else {
+    fail(EVQGPU_ERR_UNSUPPORTED, "string expressions other than columns and literals are outside the device path");
+  }
+  a->type = EVQ_UINT64;
+}
+
+static void lower_strings(evqgpu_query* q, Expr* e) {
+  if (!e) return;
+  if (e->op == EVQ_X_CALL && (e->info().fn == Fn::EQ || e->info().fn == Fn::NEQ) && e->info().args[0] == EVQ_STRING) {
+    lower_string_leaf(q, e->args[0].get());
+    lower_string_leaf(q, e->args[1].get());
+    e->fn = function_lookup(e->info().fn == Fn::EQ ? "eq#bool/uint64;uint64;" : "neq#bool/uint64;uint64;");
+    return;
+  }
+  if (e->op == EVQ_X_CALL && e->info().fn == Fn::DATE_TRUNC) {   // its window literal stays a string
+    lower_strings(q, e->args[1].get());
+    return;
+  }
+  if (e->type == EVQ_STRING)
+    fail(EVQGPU_ERR_UNSUPPORTED, "string values are outside the device path except in eq / neq with columns and literals and as bare GROUP BY / select columns");
+  for (auto& a : e->args) lower_strings(q, a.get());
+}
+
+// a bare string column as a GROUP BY expression or select item
+static bool lower_bare_string_column(evqgpu_query* q, Expr* e) {
+  if (!e || e->op != EVQ_X_INPUT || e->type != EVQ_STRING) return false;
+  lower_string_leaf(q, e);
+  return true;
+}
+
 void query_intake(evqgpu_query* q, const evqgpu_query_desc* desc) {
   if (desc->struct_size != sizeof(evqgpu_query_desc)) fail(EVQGPU_ERR_ARG, "evqgpu_query_desc: struct_size mismatch");
   q->flags = desc->flags;
   q->expected_groups = desc->expected_groups;
   for (uint32_t i = 0; i < desc->num_input_columns; ++i) q->input_columns.push_back(desc->input_columns[i]);
+  q->col_is_string.assign(q->input_columns.size(), false);
   q->where = parse_program(desc->where);
+  lower_strings(q, q->where.get());
   if (q->where && q->where->type != EVQ_BOOL) fail(EVQGPU_ERR_ARG, "WHERE expression must be of type bool");
   if (q->where && find_aggregate(q->where.get())) fail(EVQGPU_ERR_ARG, "aggregate call in WHERE");
   if (desc->num_group > EVQ_MAX_KEYS) fail(EVQGPU_ERR_UNSUPPORTED, "at most %d GROUP BY expressions", EVQ_MAX_KEYS);
@@ -225,6 +277,13 @@ void query_intake(evqgpu_query* q, const evqgpu_query_desc* desc) {
     ExprPtr g = parse_program(desc->group[i]);
     if (!g) fail(EVQGPU_ERR_ARG, "empty GROUP BY expression");
     if (find_aggregate(g.get())) fail(EVQGPU_ERR_ARG, "aggregate call in GROUP BY");
+    if (lower_bare_string_column(q, g.get())) {
+      if (q->flags & EVQGPU_QUERY_WIRE)
+        fail(EVQGPU_ERR_UNSUPPORTED, "string GROUP BY keys in the partial-aggregation row format (the key hash covers the string bytes)");
+      q->string_keys = true;
+    } else {
+      lower_strings(q, g.get());
+    }
     if (g->type == EVQ_STRING || g->type == EVQ_NIL) fail(EVQGPU_ERR_UNSUPPORTED, "GROUP BY key type is outside the numeric device path");
     q->group.push_back(std::move(g));
   }
@@ -233,6 +292,8 @@ void query_intake(evqgpu_query* q, const evqgpu_query_desc* desc) {
     SelectItem item;
     item.expr = parse_program(desc->select[i]);
     if (!item.expr) fail(EVQGPU_ERR_ARG, "empty select expression");
+    item.is_string = lower_bare_string_column(q, item.expr.get());
+    if (!item.is_string) lower_strings(q, item.expr.get());
     if (item.expr->type == EVQ_STRING || item.expr->type == EVQ_NIL)
       fail(EVQGPU_ERR_UNSUPPORTED, "select item %u: result type is outside the numeric device path", i);
     item.agg = find_aggregate(item.expr.get());
@@ -281,7 +342,8 @@ void evqgpu_query_destroy(evqgpu_query* q) {
 
 uint32_t evqgpu_query_num_columns(const evqgpu_query* q) { return q ? (uint32_t) q->select.size() : 0; }
 uint32_t evqgpu_query_column_type(const evqgpu_query* q, uint32_t idx) {
-  return (q && idx < q->select.size()) ? (uint32_t) q->select[idx].expr->type : 0;
+  if (!q || idx >= q->select.size()) return 0;
+  return q->select[idx].is_string ? (uint32_t) EVQ_STRING : (uint32_t) q->select[idx].expr->type;
 }
 
 }  // extern "C"
@@ -309,7 +371,7 @@ static KernelShape shape_of_plans(const evqgpu_query& q, const std::vector<Table
   for (const auto& p : plans)
     for (size_t i = 0; i < s.cols.size(); ++i) {
       if (p.binding.col_index[i] < 0) continue;
-      const Column& c = p.table->cols[p.binding.col_index[i]];
+      const Column& c = *p.binding.cols[i];
       if (c.data_kind == EVQ_KIND_LEB128 && s.cols[i].leb_len >= 2 && !s.cols[i].leb_uniform && !c.sub_index.p) have_subidx = false;
     }
   finish_shape(s, have_subidx);
@@ -337,7 +399,7 @@ static void fill_streams(EvqScanParams& P, evqgpu_table* t, const Binding& b, co
   for (size_t i = 0; i < s.cols.size(); ++i) {
     const ColSig& cs = s.cols[i];
     if (!cs.used) continue;
-    const Column& c = t->cols[b.col_index[i]];
+    const Column& c = *b.cols[i];
     EvqStream& d = P.streams[cs.data_stream];
     d.base = c.data.buf.as<u8>();
     d.off_index = c.data_kind == EVQ_KIND_LEB128 ? c.off_index.as<u64>() : nullptr;
@@ -388,7 +450,7 @@ static uint64_t algorithmic_bytes(const evqgpu_query& q, const std::vector<Table
   for (const auto& p : plans)
     for (size_t i = 0; i < q.input_columns.size(); ++i)
       if (p.binding.col_index[i] >= 0) {
-        const Column& c = p.table->cols[p.binding.col_index[i]];
+        const Column& c = *p.binding.cols[i];
         n += c.data_payload_bytes + c.level_payload_bytes;
       }
   return n;
@@ -998,6 +1060,47 @@ int evqgpu_query_fetch(evqgpu_query* q, uint64_t row0, uint64_t max_rows, void* 
     }
     if (n) EVQ_CUDA(cudaStreamSynchronize(q->ctx->stream));
     *nrows_out = n;
+  });
+}
+
+int evqgpu_query_fetch_strings(evqgpu_query* q, uint32_t column, uint64_t row0, uint64_t max_rows, void* dst, uint64_t cap,
+                               uint64_t* nrows_out, uint64_t* nbytes_out) {
+  return guarded([&] {
+    if (!q || !nrows_out || !nbytes_out) fail(EVQGPU_ERR_ARG, "evqgpu_query_fetch_strings: null argument");
+    if (column >= q->select.size() || !q->select[column].is_string)
+      fail(EVQGPU_ERR_ARG, "evqgpu_query_fetch_strings: result column %u is not a string column", column);
+    if (q->pending) finish_query(*q);
+    use_device(q->ctx);
+    uint64_t n = 0;
+    if (row0 < q->num_rows_out) n = std::min<uint64_t>(max_rows, q->num_rows_out - row0);
+    *nrows_out = n;
+    *nbytes_out = 0;
+    if (!n) return;
+    // the device result holds [code u64][tag]; the values come from the context's dictionary (result rows only)
+    std::vector<uint8_t> packed(n * 9);
+    EVQ_CUDA(cudaMemcpyAsync(packed.data(), q->out_cols[column].as<u8>() + row0 * 9, n * 9, cudaMemcpyDeviceToHost, q->ctx->stream));
+    EVQ_CUDA(cudaStreamSynchronize(q->ctx->stream));
+    const auto& dict = q->ctx->code_strings;
+    uint64_t total = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+      uint64_t code;
+      memcpy(&code, &packed[i * 9], 8);
+      if (code >= dict.size()) fail(EVQGPU_ERR_RUNTIME, "string code %llu outside the dictionary", (unsigned long long) code);
+      total += 5 + ((packed[i * 9 + 8] & EVQ_STAG_NULL) ? 0 : dict[code].size());
+    }
+    *nbytes_out = total;
+    if (!dst || cap < total) { *nrows_out = 0; return; }
+    uint8_t* o = (uint8_t*) dst;
+    for (uint64_t i = 0; i < n; ++i) {   // the packed STRING element: [u32 length][bytes][tag] (svalue.cc:533-549)
+      uint64_t code;
+      memcpy(&code, &packed[i * 9], 8);
+      const bool null = packed[i * 9 + 8] & EVQ_STAG_NULL;
+      const uint32_t len = null ? 0u : (uint32_t) dict[code].size();
+      memcpy(o, &len, 4);
+      if (len) memcpy(o + 4, dict[code].data(), len);
+      o[4 + len] = null ? EVQ_STAG_NULL : 0;
+      o += 5 + len;
+    }
   });
 }
 

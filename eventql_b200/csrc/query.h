@@ -22,6 +22,7 @@ struct SelectItem {
   int state_seen = -1;         // min/max/mean: number of non-NULL arguments (the rows word when the argument cannot be NULL)
   int state_carry = -1;        // mean over a uint64 argument: wraps of the 64-bit sum word (exact 128-bit integer sum)
   int distinct = -1;           // count_distinct: index into evqgpu_query::distinct_args
+  bool is_string = false;      // a bare string column: the device column holds dictionary codes, fetched with evqgpu_query_fetch_strings
 };
 
 // how one input column is laid out on the device (part of the kernel's specialisation key)
@@ -135,6 +136,8 @@ struct evqgpu_query {
   std::string merge_checked_layout;  // state layout all ranks were last verified to share
   uint64_t expected_groups = 0;
   std::vector<bool> col_used;
+  std::vector<bool> col_is_string;   // plan input columns read as dictionary codes of a string column (strings.cu)
+  bool string_keys = false;          // a GROUP BY expression is a string column
 
   // device state, reused across executions
   evq::DevBuf merge_recv, merge_send, merge_slots, merge_counts;

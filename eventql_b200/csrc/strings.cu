@@ -150,6 +150,75 @@ void table_finish_string_column(evqgpu_table* t, Column& c, const uint8_t* host,
   c.loaded = true;
 }
 
+// ---- dictionary codes: string predicates and string group keys ---------------------------------------------------------
+// eq / neq between string columns and literals, and GROUP BY / select of a bare string column, run in the scan kernels on
+// dense codes: equality of codes <=> equality of bytes because every table of a context shares one dictionary.  The codes
+// are assigned by a host pass over the column's values when the first query needs them (a hash-map lookup per value, once
+// per column); the shadow column then goes through the same index / statistics pass as any UINT32_PLAIN column, so the
+// kernels see narrow keys with an exact range (a handful of distinct flags -> the dense register tier).
+
+uint32_t string_code(evqgpu_ctx* ctx, const std::string& s) {
+  if (ctx->code_strings.empty()) {
+    ctx->code_strings.push_back(std::string());
+    ctx->string_codes.emplace(std::string(), 0u);
+  }
+  auto it = ctx->string_codes.find(s);
+  if (it != ctx->string_codes.end()) return it->second;
+  if (ctx->code_strings.size() >= 0xfffffff0ull) fail(EVQGPU_ERR_UNSUPPORTED, "string dictionary of the context is full");
+  const uint32_t code = (uint32_t) ctx->code_strings.size();
+  ctx->code_strings.push_back(s);
+  ctx->string_codes.emplace(s, code);
+  return code;
+}
+
+const Column* ensure_code_column(evqgpu_table* t, Column& c) {
+  if (c.code_col) return c.code_col.get();
+  if (!c.is_string) fail(EVQGPU_ERR_ARG, "column '%s' is not a string column", c.meta.name.c_str());
+  if (!c.loaded) table_load_column(t, c);
+  evqgpu_ctx* ctx = t->ctx;
+  use_device(ctx);
+  const uint64_t nv = c.num_values;
+  std::vector<uint8_t> data(c.data_payload_bytes);
+  std::vector<uint64_t> start(nv);
+  std::vector<uint32_t> len(nv), codes(nv);
+  if (!data.empty()) EVQ_CUDA(cudaMemcpyAsync(data.data(), c.data.buf.p, data.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  if (nv) {
+    EVQ_CUDA(cudaMemcpyAsync(start.data(), c.str_start.p, nv * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    EVQ_CUDA(cudaMemcpyAsync(len.data(), c.str_len.p, nv * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::string key;
+  for (uint64_t i = 0; i < nv; ++i) {
+    key.assign((const char*) data.data() + start[i], len[i]);
+    codes[i] = string_code(ctx, key);
+  }
+  std::unique_ptr<Column> sh(new Column());
+  sh->meta = c.meta;
+  sh->meta.logical_type = EVQ_COL_UNSIGNED_INT;
+  sh->meta.encoding = EVQ_ENC_UINT32_PLAIN;
+  sh->sql_type = EVQ_UINT64;
+  sh->scannable = true;
+  sh->data_kind = EVQ_KIND_PLAIN32;
+  sh->data.present = true;
+  sh->data.nbytes = nv * 4;
+  const uint64_t alloc = round_up(nv * 4, 256) + 256;
+  sh->data.buf.alloc(alloc);
+  const uint64_t tail0 = (nv * 4) & ~255ull;
+  EVQ_CUDA(cudaMemsetAsync((uint8_t*) sh->data.buf.p + tail0, 0, alloc - tail0, ctx->stream));
+  if (nv) EVQ_CUDA(cudaMemcpyAsync(sh->data.buf.p, codes.data(), nv * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (c.meta.dlevel_max > 0) {
+    sh->dlevel.present = c.dlevel.present;
+    sh->dlevel.nbytes = c.dlevel.nbytes;
+    sh->dlevel.bitpack_max = c.dlevel.bitpack_max;
+    sh->dlevel.buf.alloc(c.dlevel.buf.bytes);
+    EVQ_CUDA(cudaMemcpyAsync(sh->dlevel.buf.p, c.dlevel.buf.p, c.dlevel.buf.bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  EVQ_CUDA(cudaStreamSynchronize(ctx->stream));   // `codes` goes away
+  table_finish_column(t, *sh);
+  c.code_col = std::move(sh);
+  return c.code_col.get();
+}
+
 static Column& string_column(evqgpu_table* tbl, const char* name) {
   const int ci = tbl->find(name);
   if (ci < 0) fail(EVQGPU_ERR_ARG, "column not found: %s", name);

@@ -15,6 +15,7 @@
 //   row_value[r] : value ordinal of record r, 0xffffffff = NULL                       u32[nrows]  (optional columns)
 // A row tile is EVQ_TILE_ROWS = 1024 records.
 #pragma once
+#include <memory>
 #include <string>
 #include <vector>
 #include "context.h"
@@ -54,6 +55,9 @@ struct Column {
   // flat string columns
   bool is_string = false;
   DevBuf str_start, str_len, row_value;
+  // ... and, once a query compares or groups by the column, its values as dictionary codes (evqgpu_ctx::string_codes): a
+  // UINT32_PLAIN shadow column with the same definition levels, which is what the scan kernels read
+  std::unique_ptr<Column> code_col;
 };
 
 #define EVQ_KIND_STRING_HOST 255u   // Column::data_kind of string columns (host side only: the scan kernels never see them)
@@ -87,4 +91,6 @@ void table_load_column(evqgpu_table* t, Column& c);
 void table_finish_column(evqgpu_table* t, Column& c);   // indexes + tile caps after the streams are on the device
 // strings.cu: value index of a string column whose streams are on the device; `host_stream` is the logical DATA stream
 void table_finish_string_column(evqgpu_table* t, Column& c, const uint8_t* host_stream, uint64_t nbytes);
+uint32_t string_code(evqgpu_ctx* ctx, const std::string& s);        // code of a string in the context's dictionary (inserted if new)
+const Column* ensure_code_column(evqgpu_table* t, Column& c);       // the dictionary-coded shadow of a loaded string column
 }  // namespace evq

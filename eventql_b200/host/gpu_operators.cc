@@ -230,8 +230,19 @@ ReturnCode GpuQueryExpression::nextBatch(SVector* columns, size_t* len) {
   uint64_t got = 0;
   if (evqgpu_query_fetch(query_, cursor_, kOutputBatchSize, ptrs.data(), &got) != EVQGPU_OK)
     return ReturnCode::error("ERUNTIME", lastError());
-  for (size_t i = 0; i < staging_.size(); ++i)
+  for (size_t i = 0; i < staging_.size(); ++i) {
+    if (getColumnType(i) == SType::STRING) {   // a string group key / projected string column: [u32 length][bytes][tag] elements
+      uint64_t rows = 0, bytes = 0;
+      if (evqgpu_query_fetch_strings(query_, (uint32_t) i, cursor_, got, nullptr, 0, &rows, &bytes) != EVQGPU_OK)
+        return ReturnCode::error("ERUNTIME", lastError());
+      std::vector<uint8_t> buf(bytes + 1);
+      if (evqgpu_query_fetch_strings(query_, (uint32_t) i, cursor_, got, buf.data(), bytes, &rows, &bytes) != EVQGPU_OK)
+        return ReturnCode::error("ERUNTIME", lastError());
+      columns[i].append(buf.data(), bytes);
+      continue;
+    }
     columns[i].append(staging_[i].data(), got * sql_sizeof_fixed(getColumnType(i)));   // already in the packed SVector encoding
+  }
   cursor_ += got;
   *len = (size_t) got;
   return ReturnCode::success();

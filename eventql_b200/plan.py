@@ -134,10 +134,11 @@ def _registry():
     for t in (UINT64, INT64, FLOAT64, TIMESTAMP64):
         reg("cmp", [t, t], INT64)
     for name in ("eq", "neq"):
-        for t in (UINT64, INT64, FLOAT64, BOOL, TIMESTAMP64):
+        for t in (UINT64, INT64, FLOAT64, BOOL, STRING, TIMESTAMP64):   # sql/defaults.cc:65-76
             reg(name, [t, t], BOOL, conv=False)
     for name in ("lt", "lte", "gt", "gte"):
-        for t in (UINT64, INT64, FLOAT64, TIMESTAMP64):
+        for t in (UINT64, INT64, FLOAT64, STRING, TIMESTAMP64):         # sql/defaults.cc:77-96
+
             # boolean.cc:415-430: lt_int64 is the one comparison that allows argument conversion
             reg(name, [t, t], BOOL, conv=(name == "lt" and t == INT64))
     for t in (UINT64, INT64, FLOAT64, BOOL, TIMESTAMP64):

@@ -357,6 +357,17 @@ EVQGPU_API int evqgpu_query_num_rows(evqgpu_query* q, uint64_t* out);
 EVQGPU_API int evqgpu_query_fetch(evqgpu_query* q, uint64_t row0, uint64_t max_rows, void* const* columns,
                                   uint64_t* nrows_out);
 
+/* String result columns (evqgpu_query_column_type == EVQ_STRING: a bare string column as GROUP BY key or select item).  The
+ * device result - and evqgpu_query_fetch - holds the column as [dictionary code u64][tag]; this call returns rows
+ * [row0, row0 + max_rows) as packed STRING elements, [u32 length][bytes][tag] (sql/svalue.cc:533-549; NULL = length 0 + tag
+ * EVQ_STAG_NULL).  *nbytes_out = bytes needed; when dst == NULL or cap is smaller nothing is written and *nrows_out = 0.
+ *
+ * String support of a plan (no CPU fallback for the rest - EVQGPU_ERR_UNSUPPORTED): eq / neq between string columns and
+ * string literals (expressions/boolean.cc:235-257, 355-377: the NULL tag is dropped, a NULL compares as ""), bare string
+ * columns as GROUP BY expressions and select items.  They run on dictionary codes shared by all tables of a context. */
+EVQGPU_API int evqgpu_query_fetch_strings(evqgpu_query* q, uint32_t column, uint64_t row0, uint64_t max_rows, void* dst,
+                                          uint64_t cap, uint64_t* nrows_out, uint64_t* nbytes_out);
+
 /* The groups of an executed EVQGPU_QUERY_WIRE plan as the rows csql::PartialGroupByExpression::nextBatch produces
  * (sql/statements/select/groupby.cc:411-445) - what a shard of a cluster query returns to GroupByMergeExpression
  * (groupby.cc:553-615) and stores in its query cache:

@@ -630,6 +630,10 @@ class Vec:
     tags: np.ndarray       # uint8
 
     def bits64(self) -> np.ndarray:
+        if self.type == P.STRING:
+            # group identity of a string key is its bytes (groupby.cc:112-135 hashes them); any injective id will do
+            _, inv = np.unique(self.values, return_inverse=True)
+            return inv.astype(np.uint64)
         if self.type == P.FLOAT64:
             return self.values.view(np.uint64)
         if self.type == P.INT64:
@@ -695,7 +699,10 @@ def eval_expr(e: P.Expr, inputs: Sequence[Vec], n: int, active: Optional[np.ndar
         return Vec(e.type, v.values, v.tags)                      # X_INPUT keeps the tag (vm.cc:138-142)
     if isinstance(e, P.Lit):
         if e.type == P.STRING:
-            return Vec(P.STRING, np.array([e.value] * 1, dtype=object), np.zeros(1, dtype=np.uint8))
+            val = e.value.encode() if isinstance(e.value, str) else bytes(e.value)
+            arr = np.empty(n, dtype=object)
+            arr[:] = [val] * n
+            return Vec(P.STRING, arr, np.zeros(n, dtype=np.uint8))
         if e.type == P.NIL:
             return Vec(P.NIL, np.zeros(n, dtype=np.uint64), np.ones(n, dtype=np.uint8))
         return _const(e.type, e.value, n)
@@ -721,8 +728,8 @@ def eval_expr(e: P.Expr, inputs: Sequence[Vec], n: int, active: Optional[np.ndar
     zt = np.zeros(n, dtype=np.uint8)                               # pure functions push tag 0 (svalue.cc:950-958)
     T = argt[0] if argt else P.NIL
     dt = _NP_OF.get(T, np.uint64)
-    x = a[0].values.astype(dt, copy=False) if a else None
-    y = a[1].values.astype(dt, copy=False) if len(a) > 1 else None
+    x = a[0].values.astype(dt, copy=False) if a and T != P.STRING else None
+    y = a[1].values.astype(dt, copy=False) if len(a) > 1 and T != P.STRING else None
     with np.errstate(all="ignore"):
         if name == "logical_and":
             return Vec(P.BOOL, x.astype(bool) & y.astype(bool), zt)
@@ -730,6 +737,12 @@ def eval_expr(e: P.Expr, inputs: Sequence[Vec], n: int, active: Optional[np.ndar
             return Vec(P.BOOL, x.astype(bool) | y.astype(bool), zt)
         if name == "neg":
             return Vec(P.BOOL, ~x.astype(bool), zt)
+        if T == P.STRING and name in ("eq", "neq", "lt", "lte", "gt", "gte"):
+            # boolean.cc:235-257 ...: length + memcmp on the popped strings; the tag is dropped, so a NULL compares as ""
+            import operator
+            op = {"eq": operator.eq, "neq": operator.ne, "lt": operator.lt, "lte": operator.le, "gt": operator.gt,
+                  "gte": operator.ge}[name]
+            return Vec(P.BOOL, np.fromiter((op(p, q) for p, q in zip(a[0].values, a[1].values)), dtype=bool, count=n), zt)
         if name in ("eq", "neq", "lt", "lte", "gt", "gte"):
             r = {"eq": np.equal, "neq": np.not_equal, "lt": np.less, "lte": np.less_equal,
                  "gt": np.greater, "gte": np.greater_equal}[name](x, y)
@@ -867,12 +880,23 @@ def load_inputs(tables: Sequence[CSTableFile], names: Sequence[str]) -> Tuple[Li
         for t in tables:
             if name not in t.columns:
                 raise OracleError("column not found: %s" % name)
+            if t.columns[name].logical_type == P.COL_STRING:
+                sv = decode_string_column(t, name)           # fetchColumnString: NULL -> length 0 + STAG_NULL
+                arr = np.empty(len(sv), dtype=object)
+                arr[:] = [b"" if x is None else x for x in sv]
+                st = P.STRING
+                parts_v.append(arr)
+                parts_t.append(np.array([1 if x is None else 0 for x in sv], dtype=np.uint8))
+                continue
             d = decode_column(t, name)
             st = d.sql_type
             parts_v.append(d.values)
             parts_t.append(np.where(d.present, 0, 1).astype(np.uint8))
         raw = np.concatenate(parts_v) if parts_v else np.zeros(0, dtype=np.uint64)
         tags = np.concatenate(parts_t) if parts_t else np.zeros(0, dtype=np.uint8)
+        if st == P.STRING:
+            vecs.append(Vec(st, raw, tags))
+            continue
         if st == P.FLOAT64:
             vals = raw.view(np.float64)
         elif st == P.BOOL:
@@ -884,8 +908,6 @@ def load_inputs(tables: Sequence[CSTableFile], names: Sequence[str]) -> Tuple[Li
 
 
 def _take(v: Vec, idx) -> Vec:
-    if v.type == P.STRING:
-        return v
     return Vec(v.type, v.values[idx], v.tags[idx])
 
 

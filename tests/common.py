@@ -579,3 +579,60 @@ def write_lsm_segment(path: str, seg: int, num_rows: int, **kw):
             O.WriteColumn("v", P.COL_UNSIGNED_INT, P.ENC_UINT64_LEB128, c["v"])]
     O.write_cstable(path, num_rows, cols)
     return c
+
+
+def string_query_cases():
+    """[(name, sql for the reference planner, plan, ordered)] over the string fixture table (strings_table_columns):
+    eq / neq between string columns and literals (NULL compares as "", boolean.cc:235-257), string GROUP BY keys (NULL and ""
+    are different groups: the key bytes include the tag, groupby.cc:112-135), a projected string column."""
+    names = ["k", "s_req", "s_opt"]
+    k, s_req, s_opt = P.Col(0, P.UINT64), P.Col(1, P.STRING), P.Col(2, P.STRING)
+    cnt = P.call("count", P.lit(1))
+    Q = []
+
+    def add(name, sql, select, where=None, group=(), flags=P.QUERY_GROUPBY, ordered=False):
+        Q.append((name, sql, P.QueryPlan(names, list(select), where=where, group=list(group), flags=flags), ordered))
+
+    add("str_eq_lit", "select count(1), sum(k) from t where s_opt = 'google.de' and k >= 0;",
+        [cnt, P.call("sum", k)], where=s_opt.eq(P.lit("google.de")) & (k >= 0))
+    add("str_lit_eq_col", "select count(1), sum(k) from t where 'facebook' = s_req and k >= 0;",
+        [cnt, P.call("sum", k)], where=P.lit("facebook").eq(s_req) & (k >= 0))
+    add("str_eq_empty_matches_null", "select count(1), sum(k) from t where s_opt = '' and k >= 0;",
+        [cnt, P.call("sum", k)], where=s_opt.eq(P.lit("")) & (k >= 0))
+    add("str_neq_cols", "select count(1), sum(k) from t where s_opt != s_req and k >= 0;",
+        [cnt, P.call("sum", k)], where=s_opt.neq(s_req) & (k >= 0))
+    add("str_eq_cols", "select count(1), min(k), max(k) from t where s_opt = s_req and k >= 0;",
+        [cnt, P.call("min", k), P.call("max", k)], where=s_opt.eq(s_req) & (k >= 0))
+    add("str_eq_unknown_literal", "select count(1), sum(k) from t where s_req = 'no such value' and k >= 0;",
+        [cnt, P.call("sum", k)], where=s_req.eq(P.lit("no such value")) & (k >= 0))
+    add("str_neq_unknown_literal", "select count(1), sum(k) from t where s_req != 'another unknown value' and k >= 0;",
+        [cnt, P.call("sum", k)], where=s_req.neq(P.lit("another unknown value")) & (k >= 0))
+    add("str_group_nullable", "select s_opt, count(1), sum(k) from t where k < 500 group by s_opt;",
+        [s_opt, cnt, P.call("sum", k)], where=k < 500, group=[s_opt])
+    add("str_group_two_keys", "select s_req, s_opt, count(1), max(k) from t where k >= 0 and s_req != 'x' group by s_req, s_opt;",
+        [s_req, s_opt, cnt, P.call("max", k)], where=(k >= 0) & s_req.neq(P.lit("x")), group=[s_req, s_opt])
+    add("str_group_mixed_key", "select s_req, k / 500, count(1) from t where k >= 0 group by s_req, k / 500;",
+        [s_req, k / 500, cnt], where=k >= 0, group=[s_req, k / 500])
+    add("str_scan_projection", "select s_opt, k, s_req from t where s_req = 'facebook' or s_opt = 'x';",
+        [s_opt, k, s_req], where=s_req.eq(P.lit("facebook")) | s_opt.eq(P.lit("x")), flags=0, ordered=True)
+    return Q
+
+
+def parse_string_query_rows(rows, types):
+    """Golden rows of ref_strings.json 'queries' -> tuples: numbers as int, strings as their digest text, NULL as None."""
+    out = []
+    for r in rows:
+        vals = []
+        for s, t in zip(r, types):
+            if s == "NULL":
+                vals.append(None)
+            elif t == "string":
+                vals.append(s)
+            elif t == "float64":
+                vals.append(float(s))
+            elif t == "bool":
+                vals.append(s == "true")
+            else:
+                vals.append(int(s))
+        out.append(tuple(vals))
+    return out

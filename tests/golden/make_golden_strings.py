@@ -120,6 +120,35 @@ def main():
         assert O.decode_string_column(f, name) == got, name
         cols[name] = [digest(v) for v in got]
     out["tables"]["testtbl"] = {"rows": f.num_rows, "columns": cols}
+    # queries over string columns: rows of the reference engine (strings as digests), the oracle must agree
+    out["queries"] = {}
+    rp = os.path.join(tmp, "strings_v2.cst")
+    f = O.read_cstable(rp)
+    for name, sql, plan, ordered in T.string_query_cases():
+        r = subprocess.run([EVQLREF, "sql", "-H", "-t", "t=" + rp, "-q", sql], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        lines = r.stdout.decode().split("\n")
+        assert r.returncode == 0 and lines[0].startswith("#"), (name, lines[:3])
+        types = [h.rsplit(":", 1)[1] for h in lines[0][1:].split(";")]
+        rows = []
+        for ln in lines[1:]:
+            if ln == "":
+                continue
+            row = []
+            for v, t in zip(ln.split(";"), types):
+                if t == "string":
+                    row.append("NULL" if v == "NULL" else digest(bytes.fromhex(v[1:])))
+                else:
+                    row.append(v)
+            rows.append(row)
+        out["queries"][name] = {"sql": sql, "types": types, "rows": rows}
+        want = T.parse_string_query_rows(rows, types)
+        got = [tuple(digest(v) if isinstance(v, bytes) else v for v in row) for row in O.run_query([f], plan).rows()]
+        if ordered:
+            assert got == want, (name, got[:3], want[:3])
+        else:
+            ok, why = T.rows_equal(got, want)
+            assert ok, (name, why)
+        print("query %-28s %d rows" % (name, len(rows)))
     with open(os.path.join(HERE, "ref_strings.json"), "w") as fo:
         json.dump(out, fo, indent=0, sort_keys=True)
     print("wrote ref_strings.json")
