@@ -128,9 +128,9 @@ ExprPtr parse_program(const evqgpu_expr& prog) {
         e->imm = in.imm;
         if (in.type == EVQ_STRING) {
           const uint32_t off = (uint32_t) (in.imm >> 32), len = (uint32_t) in.imm;
-          if (!prog.strings || (uint64_t) off + len > prog.strings_len)
+          if (len && (!prog.strings || (uint64_t) off + len > prog.strings_len))
             fail(EVQGPU_ERR_ARG, "expression: string literal out of range");
-          e->str.assign(prog.strings + off, len);
+          if (len) e->str.assign(prog.strings + off, len);
         }
         break;
       case EVQ_X_CALL: {
