@@ -56,13 +56,22 @@ static int pull(TableExpression* te) {
     rc = te->nextBatch(cols.data(), &n);
     if (!rc.isSuccess()) { printf("ERROR!\n%s\n", rc.getMessage().c_str()); return 1; }
     if (n == 0) break;
+    std::vector<const uint8_t*> scur(nc);   // cursors into the variable-length STRING columns
+    for (size_t i = 0; i < nc; ++i) scur[i] = (const uint8_t*) cols[i].getData();
     for (size_t r = 0; r < n; ++r) {
       std::string line;
       for (size_t i = 0; i < nc; ++i) {
         const SType t = te->getColumnType(i);
-        const uint8_t* p = (const uint8_t*) cols[i].getData() + r * sql_sizeof_fixed(t);
         char buf[64];
         if (i) line += ";";
+        if (t == SType::STRING) {   // [u32 length][bytes][tag] (svalue.cc:533-549), printed like evqlref -H
+          uint32_t len; memcpy(&len, scur[i], 4);
+          if (scur[i][4 + len] & STAG_NULL) line += "NULL";
+          else { line += "x"; for (uint32_t b = 0; b < len; ++b) { snprintf(buf, sizeof(buf), "%02x", scur[i][4 + b]); line += buf; } }
+          scur[i] += 5 + len;
+          continue;
+        }
+        const uint8_t* p = (const uint8_t*) cols[i].getData() + r * sql_sizeof_fixed(t);
         if (t == SType::BOOL) { line += (p[1] & STAG_NULL) ? "NULL" : (p[0] ? "true" : "false"); continue; }
         if (p[8] & STAG_NULL) { line += "NULL"; continue; }
         uint64_t v; memcpy(&v, p, 8);
@@ -176,6 +185,24 @@ int main(int argc, char** argv) {
         }
       }
       return 0;
+    }
+    if (mode == "strgroup" && argc >= 5) {
+      // evqgpu_sql strgroup <file.cst> <string column> <numeric column>:
+      //   select <s>, count(1), sum(<n>) from t where <n> >= 0 and <s> != 'x' group by <s>
+      GpuTableProvider provider(&gpu, "t", {argv[2]});
+      const SType S = SType::STRING;
+      std::vector<std::pair<std::string, SType>> in = {{argv[4], U}, {argv[3], S}};
+      ExprRef lit = LiteralExpressionNode::string("x");
+      ExprRef scol = col(1, S);
+      ExprRef where = land(cmp("gte", col(0), u(0)), call("neq", SType::BOOL, {scol, lit}));
+      auto scan = std::make_shared<SequentialScanNode>("t", in, std::vector<SelectRef>{sel(scol), sel(col(0))}, where);
+      // GroupByNode space: 0 = the string column, 1 = the numeric column
+      ExprRef gkey = col(0, S);
+      std::vector<SelectRef> gsel = {sel(gkey), sel(count1()), sel(agg("sum", col(1)))};
+      auto node = std::make_shared<GroupByNode>(gsel, std::vector<ExprRef>{gkey}, scan);
+      auto te = provider.buildGroupByExpression(node);
+      if (!te) { fprintf(stderr, "provider declined the plan\n"); return 1; }
+      return pull(te.get());
     }
     if (mode == "partition" && argc >= 4) {
       // evqgpu_sql partition <column> <seg.cst>[:flags]...   flags: a = arena (skiplist: every 7th row), s = has_skiplist,

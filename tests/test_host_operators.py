@@ -157,3 +157,28 @@ def test_partition_cursor_operator(native_lib, tmp_path):
     assert [int(l) for l in lines] == want
     summary = [l for l in err.split("\n") if l.startswith("#visible")][0].split()[1:]
     assert summary == ["%d%s" % (sizes[i] if vis[i] is None else int(vis[i].sum()), "u" if vis[i] is None else "f") for i in range(4)]
+
+
+@pytest.mark.gpu
+def test_string_group_key_through_the_host_operators(native_lib):
+    """A string GROUP BY key and a string predicate through GpuGroupByExpression: nextBatch appends the packed STRING
+    elements ([u32 length][bytes][tag]) the reference's operators exchange; rows equal the oracle's."""
+    import gzip
+    import tempfile
+    from eventql_b200 import plan as P
+    from oracle import evq_oracle as O
+    raw = gzip.open(os.path.join(GOLD, "ref_strings_v2.cst.gz")).read()
+    with tempfile.NamedTemporaryFile(suffix=".cst") as tf:
+        tf.write(raw)
+        tf.flush()
+        rc, lines, err = run_sql("strgroup", tf.name, "s_opt", "k")
+    assert rc == 0, (lines, err)
+    got = []
+    for l in lines:
+        s, c, v = l.split(";")
+        got.append((None if s == "NULL" else bytes.fromhex(s[1:]), int(c), int(v)))
+    k, s_opt = P.Col(0, P.UINT64), P.Col(1, P.STRING)
+    plan = P.QueryPlan(["k", "s_opt"], [s_opt, P.call("count", P.lit(1)), P.call("sum", k)],
+                       where=(k >= 0) & s_opt.neq(P.lit("x")), group=[s_opt])
+    ok, why = T.rows_equal(got, O.run_query([O.parse_cstable(raw)], plan).rows())
+    assert ok, why
