@@ -615,6 +615,7 @@ static bool compute_dense_map(evqgpu_query& q, std::vector<evqgpu_table*>& table
   evqgpu_query* bq = nullptr;
   if (evqgpu_query_create(q.ctx, &d, &bq) != EVQGPU_OK) return false;
   std::unique_ptr<evqgpu_query, void (*)(evqgpu_query*)> guard(bq, evqgpu_query_destroy);
+  bq->col_is_string = q.col_is_string;   // the re-serialised key expressions already read string columns as dictionary codes
   if (evqgpu_query_execute(bq, tables.data(), (uint32_t) tables.size()) != EVQGPU_OK) return false;
   q.stats.kernel_launches += bq->stats.kernel_launches;
   q.jit_ms_total += bq->jit_ms_total;
