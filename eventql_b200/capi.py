@@ -95,6 +95,7 @@ SYMBOLS = [
     "evqgpu_query_num_rows", "evqgpu_query_fetch", "evqgpu_query_order_by", "evqgpu_query_limit", "evqgpu_query_fetch_partial", "evqgpu_query_get_stats", "evqgpu_query_kernel_source",
     "evqgpu_comm_unique_id", "evqgpu_comm_init", "evqgpu_comm_destroy", "evqgpu_query_merge", "evqgpu_debug_generate",
     "evqgpu_table_decode_string_column", "evqgpu_table_get_filter", "evqgpu_lsm_build_filters", "evqgpu_query_fetch_strings",
+    "evqgpu_partial_cache_encode", "evqgpu_partial_cache_filename", "evqgpu_query_store_cache",
 ]
 
 _lib = None
@@ -161,6 +162,9 @@ def lib() -> C.CDLL:
     L.evqgpu_query_num_rows.argtypes = [vp, C.POINTER(u64)]
     L.evqgpu_query_fetch.argtypes = [vp, u64, u64, C.POINTER(vp), C.POINTER(u64)]
     L.evqgpu_query_fetch_strings.argtypes = [vp, u32, u64, u64, vp, u64, C.POINTER(u64), C.POINTER(u64)]
+    L.evqgpu_partial_cache_encode.argtypes = [vp, vp, C.POINTER(u64), u64, vp, u64, C.POINTER(u64)]
+    L.evqgpu_partial_cache_filename.argtypes = [vp, vp, C.c_char_p, u64]
+    L.evqgpu_query_store_cache.argtypes = [vp, cp]
     L.evqgpu_query_order_by.argtypes = [vp, C.POINTER(SortSpec), u32]
     L.evqgpu_query_limit.argtypes = [vp, u64, u64]
     L.evqgpu_query_fetch_partial.argtypes = [vp, u64, u64, vp, vp, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
@@ -175,6 +179,32 @@ def lib() -> C.CDLL:
                                         C.POINTER(u64)]
     _lib = L
     return L
+
+
+def partial_cache_encode(rows) -> bytes:
+    """[(20-byte group key, saved states)] -> the .qc query cache entry of PartialGroupByExpression (groupby.cc:411-432)."""
+    n = len(rows)
+    keys = b"".join(k for k, _ in rows)
+    data = b"".join(d for _, d in rows)
+    offs = (C.c_uint64 * (n + 1))()
+    pos = 0
+    for i, (_, d) in enumerate(rows):
+        offs[i] = pos
+        pos += len(d)
+    offs[n] = pos
+    need = C.c_uint64(0)
+    kb = C.create_string_buffer(keys, max(1, len(keys)))
+    db = C.create_string_buffer(data, max(1, len(data)))
+    check(lib().evqgpu_partial_cache_encode(kb, db, offs, n, None, 0, C.byref(need)))
+    out = C.create_string_buffer(max(1, need.value))
+    check(lib().evqgpu_partial_cache_encode(kb, db, offs, n, out, need.value, C.byref(need)))
+    return out.raw[: need.value]
+
+
+def partial_cache_filename(input_cache_key: bytes, expression_fingerprint: bytes) -> str:
+    out = C.create_string_buffer(44)
+    check(lib().evqgpu_partial_cache_filename(input_cache_key, expression_fingerprint, out, 44))
+    return out.value.decode()
 
 
 def check(rc: int) -> None:
@@ -542,6 +572,10 @@ class Query:
                                                offs, C.byref(got), C.byref(need)))
         kb, db = keys.tobytes(), data.tobytes()
         return [(kb[20 * i: 20 * i + 20], db[offs[i]: offs[i + 1]]) for i in range(got.value)]
+
+    def store_cache(self, path: str):
+        """The groups as the query cache entry the reference's partial operator stores (.qc file)."""
+        check(lib().evqgpu_query_store_cache(self._h, path.encode()))
 
     def order_by(self, specs: Sequence[tuple]):
         """OrderByExpression over the result: [(result column, descending)], most significant first."""

@@ -7,8 +7,10 @@
 // spelled in the reference's serialisation: varuints (util/io/outputstream.cc appendVarUInt) for count / sum, the raw
 // structs of the extension aggregates (oracle/ref_tools/ext_aggregates.cc), SValue::encode (svalue.cc:306-309) for items
 // that are not aggregates.
+#include <stdio.h>
 #include <string.h>
 
+#include <string>
 #include <vector>
 
 #include "query.h"
@@ -110,5 +112,88 @@ extern "C" int evqgpu_query_fetch_partial(evqgpu_query* q, uint64_t row0, uint64
     }
     *data_bytes_out = out.size();
     if (data && out.size() <= data_cap) memcpy(data, out.data(), out.size());
+  });
+}
+
+// ---- the query cache entry of a partial aggregation -------------------------------------------------------------------
+// PartialGroupByExpression::execute stores its groups under QueryCache (sql/runtime/query_cache.cc:58-75) as
+//   u8 0x01 | u64 number of groups | per group: 20-byte group key | the saved states of the select items
+// (sql/statements/select/groupby.cc:411-432; read back by :262-292) in the file <cache dir>/<key>.qc, where
+//   key = SHA1(hex(input cache key) + hex(expression fingerprint))            (groupby.cc:474-483, util/SHA1.cc:87-89).
+// The per-group bytes are exactly the `data` slices evqgpu_query_fetch_partial produces.
+
+extern "C" int evqgpu_partial_cache_encode(const void* keys, const void* data, const uint64_t* data_offsets, uint64_t ngroups,
+                                           void* dst, uint64_t cap, uint64_t* nbytes_out) {
+  return guarded([&] {
+    if (!nbytes_out || (ngroups && (!keys || !data_offsets))) fail(EVQGPU_ERR_ARG, "evqgpu_partial_cache_encode: null argument");
+    uint64_t need = 9 + 20 * ngroups;
+    for (uint64_t i = 0; i < ngroups; ++i) {
+      if (data_offsets[i + 1] < data_offsets[i]) fail(EVQGPU_ERR_ARG, "evqgpu_partial_cache_encode: data offsets must ascend");
+      need += data_offsets[i + 1] - data_offsets[i];
+    }
+    *nbytes_out = need;
+    if (!dst || cap < need) return;
+    if (ngroups && !data && data_offsets[ngroups] != data_offsets[0]) fail(EVQGPU_ERR_ARG, "evqgpu_partial_cache_encode: null data");
+    uint8_t* o = (uint8_t*) dst;
+    *o++ = 0x01;
+    memcpy(o, &ngroups, 8);
+    o += 8;
+    for (uint64_t i = 0; i < ngroups; ++i) {
+      memcpy(o, (const uint8_t*) keys + 20 * i, 20);
+      o += 20;
+      const uint64_t n = data_offsets[i + 1] - data_offsets[i];
+      if (n) memcpy(o, (const uint8_t*) data + data_offsets[i], n);
+      o += n;
+    }
+  });
+}
+
+extern "C" int evqgpu_partial_cache_filename(const void* input_cache_key, const void* expression_fingerprint, char* out, uint64_t cap) {
+  return guarded([&] {
+    if (!input_cache_key || !expression_fingerprint || !out || cap < 44) fail(EVQGPU_ERR_ARG, "evqgpu_partial_cache_filename: bad argument");
+    static const char* digits = "0123456789abcdef";
+    char text[80];
+    const uint8_t* parts[2] = {(const uint8_t*) input_cache_key, (const uint8_t*) expression_fingerprint};
+    for (int p = 0; p < 2; ++p)
+      for (int i = 0; i < 20; ++i) {
+        text[40 * p + 2 * i] = digits[parts[p][i] >> 4];
+        text[40 * p + 2 * i + 1] = digits[parts[p][i] & 15];
+      }
+    uint8_t h[20];
+    sha1((const uint8_t*) text, 80, h);
+    for (int i = 0; i < 20; ++i) {
+      out[2 * i] = digits[h[i] >> 4];
+      out[2 * i + 1] = digits[h[i] & 15];
+    }
+    memcpy(out + 40, ".qc", 4);
+  });
+}
+
+extern "C" int evqgpu_query_store_cache(evqgpu_query* q, const char* path) {
+  return guarded([&] {
+    if (!q || !path) fail(EVQGPU_ERR_ARG, "evqgpu_query_store_cache: null argument");
+    uint64_t n = 0;
+    if (evqgpu_query_num_rows(q, &n) != EVQGPU_OK) throw Error{EVQGPU_ERR_RUNTIME, last_error()};
+    std::vector<uint8_t> keys(20 * n + 1);
+    std::vector<uint64_t> offs(n + 1, 0);
+    uint64_t got = 0, need = 0;
+    int rc = evqgpu_query_fetch_partial(q, 0, n, keys.data(), nullptr, 0, offs.data(), &got, &need);
+    if (rc != EVQGPU_OK) throw Error{rc, last_error()};
+    std::vector<uint8_t> data(need + 1);
+    rc = evqgpu_query_fetch_partial(q, 0, n, keys.data(), data.data(), need, offs.data(), &got, &need);
+    if (rc != EVQGPU_OK) throw Error{rc, last_error()};
+    if (got != n) fail(EVQGPU_ERR_RUNTIME, "evqgpu_query_store_cache: fetched %llu of %llu groups", (unsigned long long) got, (unsigned long long) n);
+    uint64_t bytes = 0;
+    evqgpu_partial_cache_encode(keys.data(), data.data(), offs.data(), n, nullptr, 0, &bytes);
+    std::vector<uint8_t> entry(bytes);
+    rc = evqgpu_partial_cache_encode(keys.data(), data.data(), offs.data(), n, entry.data(), bytes, &bytes);
+    if (rc != EVQGPU_OK) throw Error{rc, last_error()};
+    // QueryCache::storeEntry: write beside the target, then rename (query_cache.cc:64-74)
+    const std::string tmp = std::string(path) + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) fail(EVQGPU_ERR_ARG, "evqgpu_query_store_cache: cannot create %s", tmp.c_str());
+    const bool ok = fwrite(entry.data(), 1, entry.size(), f) == entry.size();
+    if (fclose(f) != 0 || !ok) { remove(tmp.c_str()); fail(EVQGPU_ERR_RUNTIME, "evqgpu_query_store_cache: short write to %s", tmp.c_str()); }
+    if (rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); fail(EVQGPU_ERR_RUNTIME, "evqgpu_query_store_cache: cannot rename to %s", path); }
   });
 }

@@ -383,6 +383,20 @@ EVQGPU_API int evqgpu_query_fetch_partial(evqgpu_query* q, uint64_t row0, uint64
                                           uint64_t data_cap, uint64_t* data_offsets, uint64_t* nrows_out,
                                           uint64_t* data_bytes_out);
 
+/* The query cache entry PartialGroupByExpression::execute stores for its groups (sql/statements/select/groupby.cc:411-432,
+ * read back by :262-292; sql/runtime/query_cache.cc:58-75):  u8 0x01 | u64 number of groups | per group: 20-byte group key |
+ * saved states of the select items - the keys / data slices evqgpu_query_fetch_partial returns.  Pure host function.
+ * *nbytes_out = bytes needed; nothing is written when dst == NULL or cap is smaller. */
+EVQGPU_API int evqgpu_partial_cache_encode(const void* keys, const void* data, const uint64_t* data_offsets, uint64_t ngroups,
+                                           void* dst, uint64_t cap, uint64_t* nbytes_out);
+/* File name of the entry inside the cache directory: hex(SHA1(hex(input cache key) + hex(expression fingerprint))) + ".qc"
+ * (groupby.cc:474-483, query_cache.cc:45,64); both keys are 20 bytes, out receives 44 bytes incl. the NUL. */
+EVQGPU_API int evqgpu_partial_cache_filename(const void* input_cache_key, const void* expression_fingerprint, char* out,
+                                             uint64_t cap);
+/* Write the groups of an executed EVQGPU_QUERY_WIRE plan as such an entry to `path` (temporary file + rename, like
+ * QueryCache::storeEntry). */
+EVQGPU_API int evqgpu_query_store_cache(evqgpu_query* q, const char* path);
+
 /* ORDER BY over the result rows of an executed (and, for multi-rank jobs, merged) query, on the device:
  * csql::OrderByExpression (sql/statements/select/orderby.cc:58-160) with sort expressions that are columns of the
  * result (what the planner hands the operator: it appends hidden select items for anything else).  Values compare like

@@ -23,6 +23,7 @@
 #include <vector>
 #include <eventql/sql/runtime/defaultruntime.h>
 #include <eventql/sql/runtime/runtime.h>
+#include <eventql/sql/runtime/query_cache.h>
 #include <eventql/sql/CSTableScanProvider.h>
 #include <eventql/sql/result_cursor.h>
 #include <eventql/sql/query_plan.h>
@@ -47,6 +48,7 @@ static int usage() {
       "usage:\n"
       "  evqlref sql [-t name=file.cst]... [-n reps] [-x] [-P] [-H] -q 'SQL'\n"
       "      -H  print string values as x<hex> (NULL stays NULL)\n"
+      "      -C <dir>  with -P: install the reference's QueryCache on <dir>; the partial operator stores its .qc file there\n"
       "      -x  do NOT register the extension aggregates (min/max/mean/sum<float64>)\n"
       "  evqlref write <out.cst> <v1|v2> <nrows> <name>:<uint|datetime|float|bool|string>:<encoding>:<optional 0|1>:<datafile>[:<nullfile>] ...\n"
       "      datafile = nrows x 8 B little-endian (u64 / double bits / 0|1); nullfile = nrows x 1 B (1 = NULL)\n"
@@ -97,6 +99,24 @@ static std::string fmtValue(csql::SType type, const void* data) {
 // `sql -P`: every GROUP BY of the plan runs as the reference's PartialGroupByExpression (the shard side of a cluster query,
 // sql/statements/select/groupby.cc:223-472) instead of GroupByExpression; its rows are (20-byte group key, saved states),
 // printed as hex.  This is what a shard puts on the wire and into the query cache.
+// `sql -P -C <dir>`: the reference's own query cache (sql/runtime/query_cache.cc) is installed and the partial operator's
+// input is given a cache key (in the server eventql::TableScan::getCacheKey supplies one, server/sql/table_scan.cc:173;
+// FastCSTableScan has none), so that PartialGroupByExpression::execute stores its `.qc` file (groupby.cc:411-432).
+class CacheKeyedExpression : public csql::TableExpression {
+public:
+  CacheKeyedExpression(ScopedPtr<csql::TableExpression> input, SHA1Hash key) : input_(std::move(input)), key_(key) {}
+  ReturnCode execute() override { return input_->execute(); }
+  ReturnCode nextBatch(csql::SVector* columns, size_t* len) override { return input_->nextBatch(columns, len); }
+  size_t getColumnCount() const override { return input_->getColumnCount(); }
+  csql::SType getColumnType(size_t idx) const override { return input_->getColumnType(idx); }
+  Option<SHA1Hash> getCacheKey() const override { return Some(key_); }
+private:
+  ScopedPtr<csql::TableExpression> input_;
+  SHA1Hash key_;
+};
+
+static bool g_cache_keyed = false;
+
 class PartialScheduler : public csql::DefaultScheduler {
 protected:
   ScopedPtr<csql::TableExpression> buildGroupByExpression(
@@ -117,7 +137,11 @@ protected:
             std::move(select_expressions),
             std::move(group_expressions),
             SHA1::compute(std::string("evqlref")),
-            buildTableExpression(txn, execution_context, node->inputTable().asInstanceOf<csql::TableExpressionNode>())));
+            g_cache_keyed
+                ? ScopedPtr<csql::TableExpression>(new CacheKeyedExpression(
+                      buildTableExpression(txn, execution_context, node->inputTable().asInstanceOf<csql::TableExpressionNode>()),
+                      SHA1::compute(std::string("evqlref-input"))))
+                : buildTableExpression(txn, execution_context, node->inputTable().asInstanceOf<csql::TableExpressionNode>())));
   }
 };
 
@@ -137,6 +161,7 @@ static int cmdSql(int argc, char** argv) {
   bool ext = true;
   bool partial = false;
   bool hexstr = false;
+  std::string cache_dir;
   for (int i = 0; i < argc; ++i) {
     std::string a = argv[i];
     if (a == "-t" && i + 1 < argc) {
@@ -154,6 +179,8 @@ static int cmdSql(int argc, char** argv) {
       partial = true;
     } else if (a == "-H") {
       hexstr = true;
+    } else if (a == "-C" && i + 1 < argc) {
+      cache_dir = argv[++i];
     } else {
       return usage();
     }
@@ -166,6 +193,11 @@ static int cmdSql(int argc, char** argv) {
   }
   if (partial) {
     runtime->setScheduler(mkScoped<csql::Scheduler>(new PartialScheduler()));
+  }
+  if (!cache_dir.empty()) {
+    g_cache_keyed = true;
+    // store on the first execution: cache_store_minhits = 0
+    runtime->setQueryCache(new csql::QueryCache(cache_dir, csql::QueryCache::kDefaultAssocCacheSize, 0));
   }
 
   for (int rep = 0; rep < reps; ++rep) {

@@ -31,14 +31,19 @@ def main():
     f = O.read_cstable(rp)
     out = {"generator": "tests/golden/make_golden_partial.py", "reference": "17ai/eventql v0.5.0 (oracle/_ref/evqlref sql -P)", "cases": {}}
     for name, sql, plan in T.partial_cases():
-        r = subprocess.run([G.EVQLREF, "sql", "-P", "-t", "t=" + rp, "-q", sql], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        cdir = tempfile.mkdtemp(prefix="evqqc")
+        r = subprocess.run([G.EVQLREF, "sql", "-P", "-C", cdir, "-t", "t=" + rp, "-q", sql], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
         lines = [ln for ln in r.stdout.split("\n") if ln]
         assert r.returncode == 0 and lines[0].startswith("#") and "ERROR!" not in lines, (name, r.stdout[:400], r.stderr[-400:])
         rows = sorted(ln.split(";") for ln in lines[1:])
         want = [(bytes.fromhex(k), bytes.fromhex(d)) for k, d in rows]
         ok, why = T.partial_rows_equal(plan, O.run_partial_query([f], plan), want)
         assert ok, (name, why)
-        out["cases"][name] = {"sql": sql, "rows": rows}
+        # the query cache entry the reference's own PartialGroupByExpression::execute stored (groupby.cc:411-432)
+        qcs = [x for x in os.listdir(cdir) if x.endswith(".qc")]
+        assert len(qcs) == 1, qcs
+        qc = open(os.path.join(cdir, qcs[0]), "rb").read()
+        out["cases"][name] = {"sql": sql, "rows": rows, "qc_file": qcs[0], "qc": qc.hex()}
         print("case %-36s groups=%d ok" % (name, len(rows)))
     with open(os.path.join(HERE, "ref_partial.json"), "w") as fh:
         json.dump(out, fh, indent=0, separators=(",", ":"))

@@ -166,3 +166,32 @@ def test_product_never_imports_oracle():
                 assert "import oracle" not in text and "from oracle" not in text and "oracle/" not in text.replace(
                     "oracle/ref_tools/ext_aggregates.cc", ""), os.path.join(dirpath, f)
     assert "oracle" not in open(HEADER).read().replace("oracle/ref_tools/ext_aggregates.cc", "")
+
+
+def test_partial_cache_entry_equals_the_reference_file(native_lib):
+    """The query cache entry of a partial aggregation (sql/statements/select/groupby.cc:411-432, query_cache.cc:58-75):
+    tests/golden/ref_partial.json holds, per case, the .qc file the reference's own PartialGroupByExpression::execute stored
+    (make_golden_partial.py, evqlref sql -P -C) next to its rows.  Encoding the reference's rows, in the file's group
+    order, reproduces the file byte for byte; the file name is the reference's cache key."""
+    import hashlib
+    import json
+    import os
+    with open(os.path.join(T.ROOT, "tests", "golden", "ref_partial.json")) as fh:
+        cases = json.load(fh)["cases"]
+    for name, g in cases.items():
+        qc = bytes.fromhex(g["qc"])
+        rows = {bytes.fromhex(k): bytes.fromhex(d) for k, d in g["rows"]}
+        assert qc[0] == 1 and int.from_bytes(qc[1:9], "little") == len(rows), name
+        ordered, pos = [], 9
+        while pos < len(qc):                      # the groups in the file's (hash map) order
+            key = qc[pos:pos + 20]
+            data = rows[key]
+            assert qc[pos + 20:pos + 20 + len(data)] == data, name
+            ordered.append((key, data))
+            pos += 20 + len(data)
+        assert len(ordered) == len(rows), name
+        assert capi.partial_cache_encode(ordered) == qc, name
+        # evqlref keys its scan with SHA1("evqlref-input") and the operator with SHA1("evqlref") (oracle/ref_tools/evqlref.cc)
+        fn = capi.partial_cache_filename(hashlib.sha1(b"evqlref-input").digest(), hashlib.sha1(b"evqlref").digest())
+        assert fn == g["qc_file"], name
+    assert capi.partial_cache_encode([]) == bytes([1]) + bytes(8)

@@ -387,15 +387,24 @@ def test_partial_rows_equal_reference_engine(gpu_ctx, case):
     path = T.golden_table_path("mixed")
     tbl = gpu_ctx.open_table_file(path)
     q = gpu_ctx.query(plan)
+    import tempfile
     try:
         q.execute([tbl])
         got = q.fetch_partial()
         rows = q.rows()
+        # ... and as the query cache entry the reference's partial operator stores (groupby.cc:411-432)
+        with tempfile.TemporaryDirectory() as d:
+            qc_path = os.path.join(d, g["qc_file"])
+            q.store_cache(qc_path)
+            qc = open(qc_path, "rb").read()
+            assert os.listdir(d) == [g["qc_file"]]
     finally:
         q.close()
         tbl.close()
     ok, why = T.partial_rows_equal(plan, got, want)
     assert ok, why
+    assert qc == capi.partial_cache_encode(got)
+    assert qc[0] == 1 and int.from_bytes(qc[1:9], "little") == len(want) and len(qc) == len(bytes.fromhex(g["qc"]))
     f = O.read_cstable(path)
     ok, why = T.partial_rows_equal(plan, got, O.run_partial_query([f], plan))
     assert ok, why
