@@ -96,6 +96,7 @@ SYMBOLS = [
     "evqgpu_comm_unique_id", "evqgpu_comm_init", "evqgpu_comm_destroy", "evqgpu_query_merge", "evqgpu_debug_generate",
     "evqgpu_table_decode_string_column", "evqgpu_table_get_filter", "evqgpu_lsm_build_filters", "evqgpu_query_fetch_strings",
     "evqgpu_partial_cache_encode", "evqgpu_partial_cache_filename", "evqgpu_query_store_cache",
+    "evqgpu_partial_frames_encode",
 ]
 
 _lib = None
@@ -163,6 +164,7 @@ def lib() -> C.CDLL:
     L.evqgpu_query_fetch.argtypes = [vp, u64, u64, C.POINTER(vp), C.POINTER(u64)]
     L.evqgpu_query_fetch_strings.argtypes = [vp, u32, u64, u64, vp, u64, C.POINTER(u64), C.POINTER(u64)]
     L.evqgpu_partial_cache_encode.argtypes = [vp, vp, C.POINTER(u64), u64, vp, u64, C.POINTER(u64)]
+    L.evqgpu_partial_frames_encode.argtypes = [vp, vp, C.POINTER(u64), u64, u64, vp, u64, C.POINTER(u64), C.POINTER(u64)]
     L.evqgpu_partial_cache_filename.argtypes = [vp, vp, C.c_char_p, u64]
     L.evqgpu_query_store_cache.argtypes = [vp, cp]
     L.evqgpu_query_order_by.argtypes = [vp, C.POINTER(SortSpec), u32]
@@ -198,6 +200,26 @@ def partial_cache_encode(rows) -> bytes:
     check(lib().evqgpu_partial_cache_encode(kb, db, offs, n, None, 0, C.byref(need)))
     out = C.create_string_buffer(max(1, need.value))
     check(lib().evqgpu_partial_cache_encode(kb, db, offs, n, out, need.value, C.byref(need)))
+    return out.raw[: need.value]
+
+
+def partial_frames_encode(rows, soft_max_body: int = 0) -> bytes:
+    """[(20-byte group key, saved states)] -> the QUERY_PARTIALAGGR_RESULT frames of a shard's answer, back to back."""
+    n = len(rows)
+    keys = b"".join(k for k, _ in rows)
+    data = b"".join(d for _, d in rows)
+    offs = (C.c_uint64 * (n + 1))()
+    pos = 0
+    for i, (_, d) in enumerate(rows):
+        offs[i] = pos
+        pos += len(d)
+    offs[n] = pos
+    need, frames = C.c_uint64(0), C.c_uint64(0)
+    kb = C.create_string_buffer(keys, max(1, len(keys)))
+    db = C.create_string_buffer(data, max(1, len(data)))
+    check(lib().evqgpu_partial_frames_encode(kb, db, offs, n, soft_max_body, None, 0, C.byref(need), C.byref(frames)))
+    out = C.create_string_buffer(max(1, need.value))
+    check(lib().evqgpu_partial_frames_encode(kb, db, offs, n, soft_max_body, out, need.value, C.byref(need), C.byref(frames)))
     return out.raw[: need.value]
 
 

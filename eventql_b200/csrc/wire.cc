@@ -197,3 +197,53 @@ extern "C" int evqgpu_query_store_cache(evqgpu_query* q, const char* path) {
     if (rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); fail(EVQGPU_ERR_RUNTIME, "evqgpu_query_store_cache: cannot rename to %s", path); }
   });
 }
+
+// ---- QUERY_PARTIALAGGR_RESULT frames ------------------------------------------------------------------------------------
+// What a shard answers a coordinator's QUERY_PARTIALAGGR with (transport/native/ops/query_partialaggr.cc:83-124): frames of
+//   8-byte header: u16 opcode 0x0102 | u16 flags (EVQL_ENDOFREQUEST = 1 on the last) | u32 payload length, big endian
+//                  (TCPConnection::writeFrameHeaderAsync, transport/native/connection_tcp.cc:238-251)
+//   payload:       varuint flags (0) | varuint number of rows | body  (QueryPartialAggrResultFrame::writeTo,
+//                  transport/native/frames/query_partialaggr_result.cc:56-60)
+//   body:          per row the 20-byte group key and the saved states, back to back (appendString writes raw bytes)
+// A frame is closed once its body exceeds the soft maximum (8 MiB in the reference); if that happens on the last row an
+// empty frame carries the end-of-request flag, as the reference's loop does.
+extern "C" int evqgpu_partial_frames_encode(const void* keys, const void* data, const uint64_t* data_offsets, uint64_t ngroups,
+                                            uint64_t soft_max_body, void* dst, uint64_t cap, uint64_t* nbytes_out,
+                                            uint64_t* nframes_out) {
+  return guarded([&] {
+    if (!nbytes_out || (ngroups && (!keys || !data_offsets))) fail(EVQGPU_ERR_ARG, "evqgpu_partial_frames_encode: null argument");
+    if (soft_max_body == 0) soft_max_body = 8ull << 20;
+    std::vector<uint8_t> out;
+    uint64_t frames = 0, i = 0;
+    for (bool eof = false; !eof;) {
+      std::vector<uint8_t> body;
+      uint64_t num_rows = 0;
+      while ((eof = (i >= ngroups)) == false) {
+        ++num_rows;
+        put_raw(body, (const uint8_t*) keys + 20 * i, 20);
+        if (data_offsets[i + 1] < data_offsets[i]) fail(EVQGPU_ERR_ARG, "evqgpu_partial_frames_encode: data offsets must ascend");
+        if (data_offsets[i + 1] > data_offsets[i]) {
+          if (!data) fail(EVQGPU_ERR_ARG, "evqgpu_partial_frames_encode: null data");
+          put_raw(body, (const uint8_t*) data + data_offsets[i], data_offsets[i + 1] - data_offsets[i]);
+        }
+        ++i;
+        if (body.size() > soft_max_body) break;
+      }
+      std::vector<uint8_t> payload;
+      put_varuint(payload, 0);
+      put_varuint(payload, num_rows);
+      payload.insert(payload.end(), body.begin(), body.end());
+      if (payload.size() > 0xffffffffull) fail(EVQGPU_ERR_UNSUPPORTED, "evqgpu_partial_frames_encode: frame payload over 4 GiB");
+      const uint16_t opcode = 0x0102, flags = eof ? 1 : 0;
+      const uint32_t len = (uint32_t) payload.size();
+      const uint8_t hdr[8] = {(uint8_t) (opcode >> 8), (uint8_t) opcode, (uint8_t) (flags >> 8), (uint8_t) flags,
+                              (uint8_t) (len >> 24), (uint8_t) (len >> 16), (uint8_t) (len >> 8), (uint8_t) len};
+      put_raw(out, hdr, 8);
+      out.insert(out.end(), payload.begin(), payload.end());
+      ++frames;
+    }
+    *nbytes_out = out.size();
+    if (nframes_out) *nframes_out = frames;
+    if (dst && cap >= out.size()) memcpy(dst, out.data(), out.size());
+  });
+}

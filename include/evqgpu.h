@@ -397,6 +397,15 @@ EVQGPU_API int evqgpu_partial_cache_filename(const void* input_cache_key, const 
  * QueryCache::storeEntry). */
 EVQGPU_API int evqgpu_query_store_cache(evqgpu_query* q, const char* path);
 
+/* The QUERY_PARTIALAGGR_RESULT frames a shard answers a coordinator with (transport/native/ops/query_partialaggr.cc:83-124):
+ * per frame an 8-byte big-endian header {u16 opcode 0x0102, u16 flags (1 = end of request on the last), u32 payload length}
+ * (transport/native/connection_tcp.cc:238-251) and the payload varuint 0 | varuint rows | per row 20-byte key + saved states
+ * (frames/query_partialaggr_result.cc:56-60).  A frame closes once its body exceeds soft_max_body (0 = the reference's
+ * 8 MiB).  Pure host function over evqgpu_query_fetch_partial's output; all frames are written back to back. */
+EVQGPU_API int evqgpu_partial_frames_encode(const void* keys, const void* data, const uint64_t* data_offsets, uint64_t ngroups,
+                                            uint64_t soft_max_body, void* dst, uint64_t cap, uint64_t* nbytes_out,
+                                            uint64_t* nframes_out);
+
 /* ORDER BY over the result rows of an executed (and, for multi-rank jobs, merged) query, on the device:
  * csql::OrderByExpression (sql/statements/select/orderby.cc:58-160) with sort expressions that are columns of the
  * result (what the planner hands the operator: it appends hidden select items for anything else).  Values compare like

@@ -24,6 +24,9 @@
 #include <eventql/sql/runtime/defaultruntime.h>
 #include <eventql/sql/runtime/runtime.h>
 #include <eventql/sql/runtime/query_cache.h>
+#include <eventql/transport/native/frames/query_partialaggr_result.h>
+#include <eventql/util/io/outputstream.h>
+#include <arpa/inet.h>
 #include <eventql/sql/CSTableScanProvider.h>
 #include <eventql/sql/result_cursor.h>
 #include <eventql/sql/query_plan.h>
@@ -48,6 +51,9 @@ static int usage() {
       "usage:\n"
       "  evqlref sql [-t name=file.cst]... [-n reps] [-x] [-P] [-H] -q 'SQL'\n"
       "      -H  print string values as x<hex> (NULL stays NULL)\n"
+      "      -F <file> [-M <soft max bytes>]  with -P: instead of printing, write the QUERY_PARTIALAGGR_RESULT frames the server op\n"
+      "                sends for the result (loop of transport/native/ops/query_partialaggr.cc:83-124 over the reference's\n"
+      "                QueryPartialAggrResultFrame; 8-byte headers as TCPConnection::writeFrameHeaderAsync writes them)\n"
       "      -C <dir>  with -P: install the reference's QueryCache on <dir>; the partial operator stores its .qc file there\n"
       "      -x  do NOT register the extension aggregates (min/max/mean/sum<float64>)\n"
       "  evqlref write <out.cst> <v1|v2> <nrows> <name>:<uint|datetime|float|bool|string>:<encoding>:<optional 0|1>:<datafile>[:<nullfile>] ...\n"
@@ -162,6 +168,8 @@ static int cmdSql(int argc, char** argv) {
   bool partial = false;
   bool hexstr = false;
   std::string cache_dir;
+  std::string frames_file;
+  size_t frame_soft_max = 1024 * 1024 * 8;   // kPartialAggrResponseSoftMaxSize (transport/native/ops/query_partialaggr.cc:39)
   for (int i = 0; i < argc; ++i) {
     std::string a = argv[i];
     if (a == "-t" && i + 1 < argc) {
@@ -181,6 +189,10 @@ static int cmdSql(int argc, char** argv) {
       hexstr = true;
     } else if (a == "-C" && i + 1 < argc) {
       cache_dir = argv[++i];
+    } else if (a == "-F" && i + 1 < argc) {
+      frames_file = argv[++i];
+    } else if (a == "-M" && i + 1 < argc) {
+      frame_soft_max = strtoull(argv[++i], NULL, 10);
     } else {
       return usage();
     }
@@ -226,7 +238,38 @@ static int cmdSql(int argc, char** argv) {
         puts(hdr.c_str());
       }
       size_t nrows = 0;
-      while (cursor->isValid()) {
+      if (!frames_file.empty()) {
+        // the result loop of performOperation_QUERY_PARTIALAGGR (transport/native/ops/query_partialaggr.cc:83-124), with the
+        // connection replaced by a file
+        FILE* ff = fopen(frames_file.c_str(), "wb");
+        if (!ff) { perror(frames_file.c_str()); return 1; }
+        for (bool eof = false; !eof; ) {
+          eventql::native_transport::QueryPartialAggrResultFrame result_frame;
+          auto os = StringOutputStream::fromString(&result_frame.getBody());
+          size_t num_rows = 0;
+          while ((eof = !cursor->isValid()) == false) {
+            ++num_rows;
+            ++nrows;
+            os->appendString(cursor->getColumnString(0));
+            os->appendString(cursor->getColumnString(1));
+            auto rc = cursor->next();
+            if (!rc.isSuccess()) { fprintf(stdout, "ERROR!\n%s\n", rc.getMessage().c_str()); return 1; }
+            if (result_frame.getBody().size() > frame_soft_max) break;
+          }
+          result_frame.setNumRows(num_rows);
+          std::string payload;
+          auto payload_os = StringOutputStream::fromString(&payload);
+          result_frame.writeTo(payload_os.get());
+          // TCPConnection::writeFrameHeaderAsync (transport/native/connection_tcp.cc:238-251)
+          uint16_t opcode_n = htons(EVQL_OP_QUERY_PARTIALAGGR_RESULT);
+          uint16_t flags_n = htons(eof ? EVQL_ENDOFREQUEST : 0);
+          uint32_t len_n = htonl(payload.size());
+          fwrite(&opcode_n, 2, 1, ff); fwrite(&flags_n, 2, 1, ff); fwrite(&len_n, 4, 1, ff);
+          fwrite(payload.data(), 1, payload.size(), ff);
+        }
+        fclose(ff);
+      }
+      while (frames_file.empty() && cursor->isValid()) {
         if (print) {
           std::string line;
           for (size_t i = 0; i < ncols; ++i) {

@@ -43,7 +43,16 @@ def main():
         qcs = [x for x in os.listdir(cdir) if x.endswith(".qc")]
         assert len(qcs) == 1, qcs
         qc = open(os.path.join(cdir, qcs[0]), "rb").read()
-        out["cases"][name] = {"sql": sql, "rows": rows, "qc_file": qcs[0], "qc": qc.hex()}
+        # ... and the QUERY_PARTIALAGGR_RESULT frames of the same result, with the reference's 8 MiB soft maximum and with a
+        # small one that splits the result (evqlref sql -P -F: the server op's loop over the reference's frame class)
+        frames = {}
+        for soft_max in (0, 4096):
+            ff = os.path.join(cdir, "frames.bin")
+            fr = subprocess.run([G.EVQLREF, "sql", "-P", "-F", ff, "-t", "t=" + rp, "-q", sql] + (["-M", str(soft_max)] if soft_max else []),
+                                stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+            assert fr.returncode == 0, fr.stdout[-300:]
+            frames[str(soft_max)] = open(ff, "rb").read().hex()
+        out["cases"][name] = {"sql": sql, "rows": rows, "qc_file": qcs[0], "qc": qc.hex(), "frames": frames}
         print("case %-36s groups=%d ok" % (name, len(rows)))
     with open(os.path.join(HERE, "ref_partial.json"), "w") as fh:
         json.dump(out, fh, indent=0, separators=(",", ":"))
