@@ -450,8 +450,9 @@ def lsm_visibility(segments: Sequence[LsmSegment]) -> List[Optional[np.ndarray]]
     """The row filters PartitionCursor::openNextTable hands to setFilter (server/sql/partition_cursor.cc:157-194, :216-218):
     a row is dropped if it is skipped or if a row seen earlier (in an earlier table, or earlier in this one) was an update
     with the same __lsm_id; visible update rows add their id to the set.  None = no filter (needs_filter == false: the
-    table's ids are not recorded either).  PARITY UNPINNED against the reference (the cursor needs a live partition
-    snapshot); the string and boolean column decode underneath it is pinned."""
+    table's ids are not recorded either).  Pinned: tests/golden/ref_lsm.json holds the rows the reference's own
+    PartitionCursor returns over partitions of on-disk tables (oracle/ref_tools/evqlref.cc `sql -S`); only the arena
+    skiplist override has no reference run behind it."""
     id_set = set()
     out: List[Optional[np.ndarray]] = []
     for seg in segments:

@@ -25,6 +25,10 @@
 #include <eventql/sql/runtime/runtime.h>
 #include <eventql/sql/runtime/query_cache.h>
 #include <eventql/transport/native/frames/query_partialaggr_result.h>
+#include <eventql/server/sql/partition_cursor.h>
+#include <eventql/db/partition_snapshot.h>
+#include <eventql/db/database.h>
+#include <eventql/db/file_tracker.h>
 #include <eventql/util/io/outputstream.h>
 #include <arpa/inet.h>
 #include <eventql/sql/CSTableScanProvider.h>
@@ -54,6 +58,8 @@ static int usage() {
       "      -F <file> [-M <soft max bytes>]  with -P: instead of printing, write the QUERY_PARTIALAGGR_RESULT frames the server op\n"
       "                sends for the result (loop of transport/native/ops/query_partialaggr.cc:83-124 over the reference's\n"
       "                QueryPartialAggrResultFrame; 8-byte headers as TCPConnection::writeFrameHeaderAsync writes them)\n"
+      "      -S <dir>:<name>[:su],<name>[:su],...  table `t` = one partition scanned by the reference's PartitionCursor; its LSM\n"
+      "                tables are <dir>/<name>.cst, newest first; s = has_skiplist, u = has_updates\n"
       "      -C <dir>  with -P: install the reference's QueryCache on <dir>; the partial operator stores its .qc file there\n"
       "      -x  do NOT register the extension aggregates (min/max/mean/sum<float64>)\n"
       "  evqlref write <out.cst> <v1|v2> <nrows> <name>:<uint|datetime|float|bool|string>:<encoding>:<optional 0|1>:<datafile>[:<nullfile>] ...\n"
@@ -123,6 +129,52 @@ private:
 
 static bool g_cache_keyed = false;
 
+// `sql -S <dir>:<newest>[:flags],...`: table `t` is ONE partition whose on-disk LSM tables are the listed cstable files
+// (<dir>/<name>.cst; flags s = has_skiplist, u = has_updates), newest first - the order the reference's PartitionCursor
+// visits them (server/sql/partition_cursor.cc:128-155 walks PartitionState::lsm_tables back to front).  The scan of `t` is
+// the reference's own eventql::PartitionCursor over a hand-built PartitionSnapshot (no arenas), i.e. its visibility filter
+// loop (partition_cursor.cc:157-194) + one FastCSTableScan per table.
+class PartitionProvider : public csql::TableProvider {
+public:
+  PartitionProvider(const std::string& dir, const std::vector<std::string>& newest_first) :
+      schema_provider_("t", dir + "/" + newest_first[0].substr(0, newest_first[0].find(':')) + ".cst") {
+    eventql::PartitionState state;
+    state.set_partition_key(std::string(20, '\0'));
+    // the snapshot counts references on its files through DatabaseContext::file_tracker (db/partition_snapshot.cc:59-68)
+    memset(&dbctx_, 0, sizeof(dbctx_));
+    file_tracker_.reset(new eventql::FileTracker(dir));
+    dbctx_.file_tracker = file_tracker_.get();
+    // lsm_tables: oldest first
+    for (size_t i = newest_first.size(); i-- > 0; ) {
+      std::string name = newest_first[i], flags;
+      auto c = name.find(':');
+      if (c != std::string::npos) { flags = name.substr(c + 1); name = name.substr(0, c); }
+      auto* ref = state.add_lsm_tables();
+      ref->set_filename(name);
+      ref->set_first_sequence(1);
+      ref->set_last_sequence(1);
+      ref->set_has_skiplist(flags.find('s') != std::string::npos);
+      ref->set_has_updates(flags.find('u') != std::string::npos);
+    }
+    snap_ = new eventql::PartitionSnapshot(state, dir, "", &dbctx_, 0);
+  }
+  Option<ScopedPtr<csql::TableExpression>> buildSequentialScan(
+      csql::Transaction* txn,
+      csql::ExecutionContext* execution_context,
+      RefPtr<csql::SequentialScanNode> seqscan) const override {
+    if (seqscan->tableName() != "t") return None<ScopedPtr<csql::TableExpression>>();
+    return Option<ScopedPtr<csql::TableExpression>>(ScopedPtr<csql::TableExpression>(
+        new eventql::PartitionCursor(txn, execution_context, nullptr, snap_, seqscan)));
+  }
+  void listTables(Function<void (const csql::TableInfo& table)> fn) const override { schema_provider_.listTables(fn); }
+  Option<csql::TableInfo> describe(const String& table_name) const override { return schema_provider_.describe(table_name); }
+private:
+  csql::CSTableScanProvider schema_provider_;
+  eventql::DatabaseContext dbctx_;
+  ScopedPtr<eventql::FileTracker> file_tracker_;
+  RefPtr<eventql::PartitionSnapshot> snap_;
+};
+
 class PartialScheduler : public csql::DefaultScheduler {
 protected:
   ScopedPtr<csql::TableExpression> buildGroupByExpression(
@@ -160,6 +212,8 @@ static std::string hexString(const void* data) {
   return out;
 }
 
+static std::vector<std::string> split(const std::string& s, char c);
+
 static int cmdSql(int argc, char** argv) {
   std::vector<std::pair<std::string, std::string>> tables;
   std::string query;
@@ -169,6 +223,7 @@ static int cmdSql(int argc, char** argv) {
   bool hexstr = false;
   std::string cache_dir;
   std::string frames_file;
+  std::string partition_spec;
   size_t frame_soft_max = 1024 * 1024 * 8;   // kPartialAggrResponseSoftMaxSize (transport/native/ops/query_partialaggr.cc:39)
   for (int i = 0; i < argc; ++i) {
     std::string a = argv[i];
@@ -189,6 +244,8 @@ static int cmdSql(int argc, char** argv) {
       hexstr = true;
     } else if (a == "-C" && i + 1 < argc) {
       cache_dir = argv[++i];
+    } else if (a == "-S" && i + 1 < argc) {
+      partition_spec = argv[++i];
     } else if (a == "-F" && i + 1 < argc) {
       frames_file = argv[++i];
     } else if (a == "-M" && i + 1 < argc) {
@@ -218,6 +275,11 @@ static int cmdSql(int argc, char** argv) {
       auto repo = mkScoped(new csql::TableRepository());
       for (const auto& t : tables) {
         repo->addProvider(new csql::CSTableScanProvider(t.first, t.second));
+      }
+      if (!partition_spec.empty()) {
+        auto colon = partition_spec.find(':');
+        if (colon == std::string::npos) return usage();
+        repo->addProvider(new PartitionProvider(partition_spec.substr(0, colon), split(partition_spec.substr(colon + 1), ',')));
       }
       txn->setTableProvider(std::move(repo));
 

@@ -636,3 +636,22 @@ def parse_string_query_rows(rows, types):
                 vals.append(int(s))
         out.append(tuple(vals))
     return out
+
+
+# ---- LSM partitions scanned by the reference's own PartitionCursor (tests/golden/ref_lsm.json) ----
+LSM_SIZES = [900, 1500, 700]
+LSM_KEY_SPACE = 300
+# name -> per on-disk table, newest first: (has_skiplist, has_updates); the last one is the partition's oldest table
+LSM_CASES = {
+    "skiplist_then_updates": [(True, True), (False, True), (False, False)],
+    "first_unfiltered": [(False, False), (False, True), (False, True)],
+    "nothing_filtered": [(False, False), (False, False), (False, True)],
+    "all_skiplists": [(True, False), (True, False), (True, False)],
+    "updates_everywhere": [(False, True), (False, True), (False, True)],
+}
+
+
+def lsm_case_segments(case: str):
+    """[(use_skip_column, has_updates, oldest)] of LSM_CASES[case], the arguments of O.LsmSegment / Context.lsm_build_filters."""
+    meta = LSM_CASES[case]
+    return [(m[0], m[1], i == len(meta) - 1) for i, m in enumerate(meta)]

@@ -182,3 +182,22 @@ def test_string_group_key_through_the_host_operators(native_lib):
                        where=(k >= 0) & s_opt.neq(P.lit("x")), group=[s_opt])
     ok, why = T.rows_equal(got, O.run_query([O.parse_cstable(raw)], plan).rows())
     assert ok, why
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", list(T.LSM_CASES))
+def test_partition_cursor_operator_equals_reference_partition_cursor(native_lib, tmp_path, case):
+    """GpuPartitionCursor pulled through execute / nextBatch returns the rows of the reference's eventql::PartitionCursor
+    (tests/golden/ref_lsm.json), in order."""
+    import json
+    g = json.load(open(os.path.join(GOLD, "ref_lsm.json")))["cases"][case]
+    args = []
+    for i, n in enumerate(T.LSM_SIZES):
+        p = str(tmp_path / ("seg%d.cst" % i))
+        T.write_lsm_segment(p, i, n, key_space=T.LSM_KEY_SPACE)
+        m = T.LSM_CASES[case][i]
+        fl = ("s" if m[0] else "") + ("u" if m[1] else "")
+        args.append(p + (":" + fl if fl else ""))
+    rc, lines, err = run_sql("partition", "v", *args)
+    assert rc == 0, (lines, err)
+    assert [int(l) for l in lines] == g["rows"]
