@@ -51,6 +51,52 @@ def _worker(rank, world, port, case, out):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     nparts, rows = 5, 20_000
+    if case == "lsm":
+        # Partitions of an evqld table: each is a set of segments whose visibility filter (PartitionCursor, partition_cursor.cc:
+        # 157-194) spans all of them, so a partition - not a segment - is the unit a rank owns.  Every rank filters and aggregates
+        # its partitions; the merged partials equal the result over all visible rows of all partitions.
+        import tempfile
+        nparts, nseg, seg_rows = 3, 3, 1200
+        d = tempfile.mkdtemp(prefix="evqlsm%d_" % rank)
+        key, v = P.Col(0, P.UINT64), P.Col(1, P.UINT64)
+        plan = P.QueryPlan(["key", "v"], [key % 7, P.call("count", P.lit(1)), P.call("sum", v), P.call("min", v), P.call("max", v)],
+                           where=v >= 0, group=[key % 7])
+
+        def partition(p):
+            files, filt = [], []
+            segs = []
+            for sgi in range(nseg):
+                path = os.path.join(d, "p%d_s%d.cst" % (p, sgi))
+                T.write_lsm_segment(path, 10 * p + sgi, seg_rows, key_space=250)
+                f = O.read_cstable(path)
+                files.append(f)
+                segs.append(O.LsmSegment(f, None, sgi == 0, True))
+            for f, keep in zip(files, O.lsm_visibility(segs)):
+                filt.append(np.ones(f.num_rows, dtype=bool) if keep is None else keep)
+            return files, filt
+
+        def run(parts):
+            files, filt = [], []
+            for p in parts:
+                a, b = partition(p)
+                files += a
+                filt += b
+            if not files:
+                return []
+            return O.run_query(files, plan, row_filter=np.concatenate(filt)).rows()
+
+        partial = run(sharding.assign_partitions(nparts, rank, world))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, partial)
+        merged = sharding.merge_partial_rows(gathered, 1, ["sum", "sum", "min", "max"])
+        whole = run(list(range(nparts)))
+        ok, why = T.rows_equal(merged, whole)
+        flag = torch.tensor([1 if ok else 0])
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            out.put((bool(flag.item()), why, len(whole)))
+        dist.destroy_process_group()
+        return
     if case == "q1":
         spec = T.lineitem_spec(null_every=7)
         _sql, plan = T.q1(spec, means=False)
@@ -87,7 +133,7 @@ def _worker(rank, world, port, case, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", ["q1", "highcard"])
+@pytest.mark.parametrize("case", ["q1", "highcard", "lsm"])
 def test_partial_aggregates_merge_to_the_whole_table_result(case):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
