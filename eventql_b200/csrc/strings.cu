@@ -21,6 +21,11 @@
 //       resolve  a row is hidden iff an entry before it in its hash run has the same id bytes and is a non-skipped update
 //       pack     1 bit per row into the table's filter stream (the layout evqgpu_table_set_filter produces)
 //     Exact: hash collisions only make runs longer, ids are compared byte for byte.
+//
+// (3) String predicates and string GROUP BY keys.  eq / neq between string columns and literals
+//     (sql/expressions/boolean.cc:235-257, 355-377) and bare string columns as keys / select items run in the scan kernels on
+//     dictionary codes: a UINT32_PLAIN shadow column per string column, codes from one dictionary per context (section
+//     "dictionary codes" below; the rewrite of the plan is query.cu: lower_strings).
 #include "table.h"
 #include <cub/cub.cuh>
 #include <string.h>
