@@ -162,6 +162,13 @@ int main(int argc, char** argv) {
       GpuPartialGroupByExpression te(&gpu, node, {argv[2]});
       ReturnCode rc = te.execute();
       if (!rc.isSuccess()) { printf("ERROR!\n%s\n", rc.getMessage().c_str()); return 1; }
+      if (argc >= 5) {   // evqgpu_sql partial <file> <column> <cache dir>: also store the query cache entry (keys of all 0x11 / 0x22 bytes)
+        uint8_t in_key[20], fp[20];
+        memset(in_key, 0x11, 20);
+        memset(fp, 0x22, 20);
+        rc = te.storeCacheEntry(argv[4], in_key, fp);
+        if (!rc.isSuccess()) { printf("ERROR!\n%s\n", rc.getMessage().c_str()); return 1; }
+      }
       std::vector<SVector> cols;
       cols.emplace_back(SType::STRING);
       cols.emplace_back(SType::STRING);

@@ -372,6 +372,17 @@ ReturnCode GpuPartialGroupByExpression::nextBatch(SVector* columns, size_t* len)
   return ReturnCode::success();
 }
 
+ReturnCode GpuPartialGroupByExpression::storeCacheEntry(const std::string& cache_dir, const uint8_t input_cache_key[20],
+                                                        const uint8_t expression_fingerprint[20]) {
+  if (!query_) return ReturnCode::error("ERUNTIME", "storeCacheEntry before execute");
+  char name[44];
+  if (evqgpu_partial_cache_filename(input_cache_key, expression_fingerprint, name, sizeof(name)) != EVQGPU_OK)
+    return ReturnCode::error("ERUNTIME", lastError());
+  const std::string path = cache_dir + "/" + name;
+  if (evqgpu_query_store_cache(query_, path.c_str()) != EVQGPU_OK) return ReturnCode::error("ERUNTIME", lastError());
+  return ReturnCode::success();
+}
+
 // ---- provider / scheduler hooks ----------------------------------------------------------------------------------------
 
 std::unique_ptr<TableExpression> GpuTableProvider::buildSequentialScan(std::shared_ptr<SequentialScanNode> seqscan) const {

@@ -126,6 +126,10 @@ public:
   csql::ReturnCode nextBatch(csql::SVector* columns, size_t* len) override;
   size_t getColumnCount() const override { return 2; }
   csql::SType getColumnType(size_t) const override { return csql::SType::STRING; }
+  // The "store cache" step of PartialGroupByExpression::execute (groupby.cc:411-432): write the groups as the query cache
+  // entry <cache_dir>/<SHA1(hex(input key) + hex(fingerprint))>.qc (groupby.cc:474-483, runtime/query_cache.cc:58-75).  Both
+  // keys are 20-byte SHA-1 values (the input's getCacheKey() and the operator's expression fingerprint).  Call after execute().
+  csql::ReturnCode storeCacheEntry(const std::string& cache_dir, const uint8_t input_cache_key[20], const uint8_t expression_fingerprint[20]);
 };
 
 // OrderByExpression (sql/statements/select/orderby.h:34-66, orderby.cc:58-160) over a device-resident result: the sort

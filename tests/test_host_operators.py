@@ -125,6 +125,17 @@ def test_partial_groupby_operator_rows(native_lib):
     assert len(got) == 213
     ok, why = T.partial_rows_equal(plan, got, want)
     assert ok, why
+    # ... and the operator's "store cache" step: the query cache entry under the reference's file name, the same groups
+    import hashlib
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        rc, lines2, err = run_sql("partial", fx, "time", d)
+        assert rc == 0, (lines2, err)
+        name = hashlib.sha1((("11" * 20) + ("22" * 20)).encode()).hexdigest() + ".qc"
+        assert os.listdir(d) == [name]
+        qc = open(os.path.join(d, name), "rb").read()
+    rows2 = [tuple(bytes.fromhex(x) for x in l.split(";")) for l in lines2]
+    assert qc == capi.partial_cache_encode(rows2)
 
 
 @pytest.mark.gpu
