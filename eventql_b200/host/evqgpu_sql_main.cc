@@ -90,6 +90,33 @@ int main(int argc, char** argv) {
   if (argc < 3) { fprintf(stderr, "usage: evqgpu_sql q1|q6|count|scan <file.cst>... [column]\n"); return 2; }
   const std::string mode = argv[1];
   try {
+    if (mode == "translate") {
+      // evqgpu_sql translate q6|strings|ifexpr: print the postfix evqgpu_insn program translate() emits for a WHERE expression
+      // (no device needed) - "op type nargs arg imm" per instruction, then the string pool as hex
+      const SType U = SType::UINT64, S = SType::STRING;
+      ExprRef e;
+      const std::string which = argv[2];
+      if (which == "q6") {
+        e = land(land(land(land(land(cmp("gte", col(0), u(8766)), cmp("lt", col(0), u(9131))), cmp("gte", col(1), u(5))),
+                           cmp("lte", col(1), u(7))), cmp("lt", col(2), u(24))), cmp("gt", col(3), u(0)));
+      } else if (which == "strings") {
+        e = land(cmp("eq", col(1, S), LiteralExpressionNode::string("google.de")), cmp("neq", LiteralExpressionNode::string(""), col(2, S)));
+      } else if (which == "ifexpr") {
+        e = cmp("gt", ExprRef(new IfExpressionNode(cmp("lt", col(0), u(50)), arith("mul", col(1), u(3)), col(2))), u(7));
+      } else {
+        fprintf(stderr, "translate: unknown expression\n");
+        return 2;
+      }
+      (void) U;
+      const Program p = translate(e);
+      for (const auto& in : p.code)
+        printf("%u %u %u %u %llu\n", (unsigned) in.op, (unsigned) in.type, (unsigned) in.nargs, (unsigned) in.arg, (unsigned long long) in.imm);
+      std::string hex;
+      char buf[4];
+      for (unsigned char ch : p.strings) { snprintf(buf, sizeof(buf), "%02x", ch); hex += buf; }
+      printf("strings %s\n", hex.c_str());
+      return 0;
+    }
     GpuContext gpu(0);
     const SType U = SType::UINT64;
     if (mode == "q1" || mode == "q6") {

@@ -212,3 +212,25 @@ def test_partition_cursor_operator_equals_reference_partition_cursor(native_lib,
     rc, lines, err = run_sql("partition", "v", *args)
     assert rc == 0, (lines, err)
     assert [int(l) for l in lines] == g["rows"]
+
+
+@pytest.mark.parametrize("which", ["q6", "strings", "ifexpr"])
+def test_host_translate_emits_the_same_program_as_the_plan_module(native_lib, which):
+    """evql_b200::translate (qtree -> postfix evqgpu_insn program) against eventql_b200.plan.flatten for the same expression:
+    same opcodes, types, argument counts, function ids (evqgpu_function_lookup of the reference's symbol strings), literal
+    bits and string pool.  No device needed."""
+    from eventql_b200 import plan as P
+    U, S = P.UINT64, P.STRING
+    c = lambda i, t=U: P.Col(i, t)
+    if which == "q6":
+        e = ((c(0) >= 8766) & (c(0) < 9131) & (c(1) >= 5) & (c(1) <= 7) & (c(2) < 24) & (c(3) > 0))
+    elif which == "strings":
+        e = c(1, S).eq(P.lit("google.de")) & P.lit("").neq(c(2, S))
+    else:
+        e = P.If(c(0) < 50, c(1) * 3, c(2)) > 7
+    prog = P.flatten(e, lambda sym: native_lib.evqgpu_function_lookup(sym.encode()))
+    rc, lines, err = run_sql("translate", which)
+    assert rc == 0, err
+    got = [tuple(int(x) for x in l.split()) for l in lines[:-1]]
+    assert got == [tuple(i) for i in prog.insns]
+    assert lines[-1].split()[1:] == ([prog.strings.hex()] if prog.strings else [])
