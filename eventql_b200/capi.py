@@ -96,7 +96,7 @@ SYMBOLS = [
     "evqgpu_comm_unique_id", "evqgpu_comm_init", "evqgpu_comm_destroy", "evqgpu_query_merge", "evqgpu_debug_generate",
     "evqgpu_table_decode_string_column", "evqgpu_table_get_filter", "evqgpu_lsm_build_filters", "evqgpu_query_fetch_strings",
     "evqgpu_partial_cache_encode", "evqgpu_partial_cache_filename", "evqgpu_query_store_cache",
-    "evqgpu_partial_frames_encode",
+    "evqgpu_partial_frames_encode", "evqgpu_partial_rows_split", "evqgpu_partial_cache_decode", "evqgpu_partial_frames_decode",
 ]
 
 _lib = None
@@ -165,6 +165,10 @@ def lib() -> C.CDLL:
     L.evqgpu_query_fetch_strings.argtypes = [vp, u32, u64, u64, vp, u64, C.POINTER(u64), C.POINTER(u64)]
     L.evqgpu_partial_cache_encode.argtypes = [vp, vp, C.POINTER(u64), u64, vp, u64, C.POINTER(u64)]
     L.evqgpu_partial_frames_encode.argtypes = [vp, vp, C.POINTER(u64), u64, u64, vp, u64, C.POINTER(u64), C.POINTER(u64)]
+    L.evqgpu_partial_rows_split.argtypes = [C.POINTER(QueryDesc), vp, u64, C.POINTER(u64), u64, C.POINTER(u64)]
+    L.evqgpu_partial_cache_decode.argtypes = [C.POINTER(QueryDesc), vp, u64, C.POINTER(u64), u64, C.POINTER(u64)]
+    L.evqgpu_partial_frames_decode.argtypes = [C.POINTER(QueryDesc), vp, u64, C.POINTER(u64), u64, C.POINTER(u64), C.POINTER(u64),
+                                               C.POINTER(C.c_int)]
     L.evqgpu_partial_cache_filename.argtypes = [vp, vp, C.c_char_p, u64]
     L.evqgpu_query_store_cache.argtypes = [vp, cp]
     L.evqgpu_query_order_by.argtypes = [vp, C.POINTER(SortSpec), u32]
@@ -221,6 +225,35 @@ def partial_frames_encode(rows, soft_max_body: int = 0) -> bytes:
     out = C.create_string_buffer(max(1, need.value))
     check(lib().evqgpu_partial_frames_encode(kb, db, offs, n, soft_max_body, out, need.value, C.byref(need), C.byref(frames)))
     return out.raw[: need.value]
+
+
+def _split(fn, plan: P.QueryPlan, buf: bytes, pairs: bool = False, extra=()):
+    pc = _PlanC(plan)
+    raw = C.create_string_buffer(buf, max(1, len(buf)))
+    n = C.c_uint64(0)
+    check(fn(C.byref(pc.desc), raw, len(buf), None, 0, C.byref(n), *extra))
+    offs = (C.c_uint64 * ((2 * n.value if pairs else n.value + 1) + 1))()
+    check(fn(C.byref(pc.desc), raw, len(buf), offs, n.value, C.byref(n), *extra))
+    if pairs:
+        return [(buf[offs[2 * i]: offs[2 * i] + 20], buf[offs[2 * i] + 20: offs[2 * i + 1]]) for i in range(n.value)]
+    return [(buf[offs[i]: offs[i] + 20], buf[offs[i] + 20: offs[i + 1]]) for i in range(n.value)]
+
+
+def partial_rows_split(plan: P.QueryPlan, body: bytes):
+    """`20-byte key | saved states` rows back to back -> [(key, states)], walked with the plan (GroupByMergeExpression's read loop)."""
+    return _split(lib().evqgpu_partial_rows_split, plan, body)
+
+
+def partial_cache_decode(plan: P.QueryPlan, entry: bytes):
+    """A .qc query cache entry -> [(key, states)]."""
+    return _split(lib().evqgpu_partial_cache_decode, plan, entry)
+
+
+def partial_frames_decode(plan: P.QueryPlan, frames: bytes):
+    """QUERY_PARTIALAGGR_RESULT frames back to back -> ([(key, states)], number of frames, end-of-request seen)."""
+    nframes, eor = C.c_uint64(0), C.c_int(0)
+    rows = _split(lib().evqgpu_partial_frames_decode, plan, frames, pairs=True, extra=(C.byref(nframes), C.byref(eor)))
+    return rows, nframes.value, bool(eor.value)
 
 
 def partial_cache_filename(input_cache_key: bytes, expression_fingerprint: bytes) -> str:

@@ -247,3 +247,145 @@ extern "C" int evqgpu_partial_frames_encode(const void* keys, const void* data, 
     if (dst && cap >= out.size()) memcpy(dst, out.data(), out.size());
   });
 }
+
+// ---- reading partial rows back (the coordinator's side of the formats above) --------------------------------------------
+// GroupByMergeExpression (groupby.cc:553-615) and the cache load of PartialGroupByExpression (groupby.cc:262-292) walk a
+// body of `20-byte key | saved states` rows by loading every select item's state in turn (VM::loadInstanceState /
+// SValue::decode): the length of a row is only known from the plan.  evqgpu_partial_rows_split does that walk for a plan
+// description and returns where every row starts; the containers (.qc entry, result frames) are unwrapped by the two
+// functions below it.  Pure host functions: parsing only, no aggregation happens here.
+namespace evq {
+void query_intake(evqgpu_query* q, const evqgpu_query_desc* desc);
+
+static uint64_t get_varuint(const uint8_t* p, uint64_t n, uint64_t& pos) {
+  uint64_t v = 0;
+  for (int k = 0;; ++k) {
+    if (pos >= n) fail(EVQGPU_ERR_FORMAT, "partial rows: truncated varuint");
+    const uint8_t b = p[pos++];
+    if (k < 10) v |= (uint64_t) (b & 0x7f) << (7 * k);
+    if (!(b & 0x80)) return v;
+  }
+}
+
+// length of one row's saved states starting at p[pos]
+static void skip_states(const evqgpu_query& q, const uint8_t* p, uint64_t n, uint64_t& pos) {
+  for (const auto& item : q.select) {
+    if (!item.agg) {   // SValue::encode (svalue.cc:306-309): type byte, varuint length, packed value
+      if (pos >= n) fail(EVQGPU_ERR_FORMAT, "partial rows: truncated value");
+      ++pos;
+      const uint64_t len = get_varuint(p, n, pos);
+      if (len > n - pos) fail(EVQGPU_ERR_FORMAT, "partial rows: truncated value");
+      pos += len;
+      continue;
+    }
+    const FnInfo& fi = item.agg->info();
+    uint64_t fixed = 0;
+    switch (fi.fn) {
+      case Fn::COUNT: get_varuint(p, n, pos); break;
+      case Fn::SUM:
+        if (fi.ret == EVQ_FLOAT64) fixed = 8;
+        else get_varuint(p, n, pos);
+        break;
+      case Fn::MIN:
+      case Fn::MAX:
+      case Fn::MEAN: fixed = 16; break;
+      default: fail(EVQGPU_ERR_UNSUPPORTED, "aggregate %s has no partial state format", fi.symbol.c_str());
+    }
+    if (fixed > n - pos) fail(EVQGPU_ERR_FORMAT, "partial rows: truncated state");
+    pos += fixed;
+  }
+}
+
+static void split_rows(const evqgpu_query& q, const uint8_t* body, uint64_t n, uint64_t base, uint64_t expect_rows, bool exact,
+                       std::vector<uint64_t>& starts) {
+  uint64_t pos = 0, rows = 0;
+  while (pos < n && (!exact || rows < expect_rows)) {
+    if (n - pos < 20) fail(EVQGPU_ERR_FORMAT, "partial rows: truncated group key");
+    starts.push_back(base + pos);
+    pos += 20;
+    skip_states(q, body, n, pos);
+    ++rows;
+  }
+  if (exact && (rows != expect_rows || pos != n))
+    fail(EVQGPU_ERR_FORMAT, "partial rows: %llu rows announced, %llu found (%llu of %llu bytes used)", (unsigned long long) expect_rows,
+         (unsigned long long) rows, (unsigned long long) pos, (unsigned long long) n);
+}
+
+static void copy_out(const std::vector<uint64_t>& starts, uint64_t end, uint64_t* row_offsets, uint64_t cap_rows, uint64_t* nrows_out) {
+  *nrows_out = starts.size();
+  if (!row_offsets || cap_rows < starts.size()) return;
+  for (size_t i = 0; i < starts.size(); ++i) row_offsets[i] = starts[i];
+  row_offsets[starts.size()] = end;
+}
+}  // namespace evq
+
+extern "C" int evqgpu_partial_rows_split(const evqgpu_query_desc* desc, const void* body, uint64_t nbytes, uint64_t* row_offsets,
+                                         uint64_t cap_rows, uint64_t* nrows_out) {
+  return guarded([&] {
+    if (!desc || (!body && nbytes) || !nrows_out) fail(EVQGPU_ERR_ARG, "evqgpu_partial_rows_split: null argument");
+    evqgpu_query q;
+    query_intake(&q, desc);
+    std::vector<uint64_t> starts;
+    split_rows(q, (const uint8_t*) body, nbytes, 0, 0, false, starts);
+    copy_out(starts, nbytes, row_offsets, cap_rows, nrows_out);
+  });
+}
+
+extern "C" int evqgpu_partial_cache_decode(const evqgpu_query_desc* desc, const void* entry, uint64_t nbytes, uint64_t* row_offsets,
+                                           uint64_t cap_rows, uint64_t* nrows_out) {
+  return guarded([&] {
+    if (!desc || !entry || !nrows_out) fail(EVQGPU_ERR_ARG, "evqgpu_partial_cache_decode: null argument");
+    const uint8_t* p = (const uint8_t*) entry;
+    if (nbytes < 9 || p[0] != 0x01) fail(EVQGPU_ERR_FORMAT, "not a partial aggregation cache entry");
+    uint64_t ngroups;
+    memcpy(&ngroups, p + 1, 8);
+    evqgpu_query q;
+    query_intake(&q, desc);
+    std::vector<uint64_t> starts;
+    split_rows(q, p + 9, nbytes - 9, 9, ngroups, true, starts);
+    copy_out(starts, nbytes, row_offsets, cap_rows, nrows_out);
+  });
+}
+
+extern "C" int evqgpu_partial_frames_decode(const evqgpu_query_desc* desc, const void* frames, uint64_t nbytes, uint64_t* row_offsets,
+                                            uint64_t cap_rows, uint64_t* nrows_out, uint64_t* nframes_out, int* end_of_request_out) {
+  return guarded([&] {
+    if (!desc || (!frames && nbytes) || !nrows_out) fail(EVQGPU_ERR_ARG, "evqgpu_partial_frames_decode: null argument");
+    const uint8_t* p = (const uint8_t*) frames;
+    evqgpu_query q;
+    query_intake(&q, desc);
+    // rows of consecutive frames are not adjacent in the buffer: every row gets its own [start, end) pair
+    std::vector<uint64_t> starts, ends;
+    uint64_t pos = 0, nframes = 0;
+    int eor = 0;
+    while (pos < nbytes) {
+      if (nbytes - pos < 8) fail(EVQGPU_ERR_FORMAT, "partial result frames: truncated header");
+      const uint32_t opcode = (uint32_t) p[pos] << 8 | p[pos + 1], flags = (uint32_t) p[pos + 2] << 8 | p[pos + 3];
+      const uint64_t len = (uint64_t) p[pos + 4] << 24 | (uint64_t) p[pos + 5] << 16 | (uint64_t) p[pos + 6] << 8 | p[pos + 7];
+      if (opcode != 0x0102) fail(EVQGPU_ERR_FORMAT, "partial result frames: opcode 0x%04x", opcode);
+      if (eor) fail(EVQGPU_ERR_FORMAT, "partial result frames: data behind the end-of-request frame");
+      pos += 8;
+      if (len > nbytes - pos) fail(EVQGPU_ERR_FORMAT, "partial result frames: truncated payload");
+      uint64_t q0 = pos;
+      get_varuint(p, pos + len, q0);                      // frame flags
+      const uint64_t rows = get_varuint(p, pos + len, q0);
+      std::vector<uint64_t> s;
+      split_rows(q, p + q0, pos + len - q0, q0, rows, true, s);
+      for (size_t i = 0; i < s.size(); ++i) {
+        starts.push_back(s[i]);
+        ends.push_back(i + 1 < s.size() ? s[i + 1] : pos + len);
+      }
+      eor = (flags & 1) ? 1 : 0;
+      pos += len;
+      ++nframes;
+    }
+    *nrows_out = starts.size();
+    if (nframes_out) *nframes_out = nframes;
+    if (end_of_request_out) *end_of_request_out = eor;
+    if (row_offsets && cap_rows >= starts.size())
+      for (size_t i = 0; i < starts.size(); ++i) {
+        row_offsets[2 * i] = starts[i];
+        row_offsets[2 * i + 1] = ends[i];
+      }
+  });
+}

@@ -406,6 +406,26 @@ EVQGPU_API int evqgpu_partial_frames_encode(const void* keys, const void* data, 
                                             uint64_t soft_max_body, void* dst, uint64_t cap, uint64_t* nbytes_out,
                                             uint64_t* nframes_out);
 
+/* Reading partial rows back - the coordinator's side (GroupByMergeExpression, groupby.cc:553-615; the cache load of the
+ * partial operator, groupby.cc:262-292).  A body of `20-byte key | saved states` rows can only be walked with the plan: the
+ * functions parse `desc` (the partial GROUP BY plan the shard ran) and report where the rows are.  Pure host functions,
+ * parsing only.
+ *   evqgpu_partial_rows_split    body = rows back to back; row_offsets[0 .. n] receives the row starts and the end
+ *                                (row i = [row_offsets[i], row_offsets[i + 1]): 20 bytes key, the rest saved states)
+ *   evqgpu_partial_cache_decode  a .qc entry (header checked against the rows found); offsets are into `entry`
+ *   evqgpu_partial_frames_decode QUERY_PARTIALAGGR_RESULT frames back to back (every frame's row count checked);
+ *                                row_offsets[2 i], [2 i + 1] = start and end of row i in `frames` (rows of different
+ *                                frames are not adjacent); *end_of_request_out = 1 when the last frame carried the flag
+ * *nrows_out = rows found; nothing is written when row_offsets == NULL or cap_rows is smaller.  EVQGPU_ERR_FORMAT on
+ * truncated or inconsistent input. */
+EVQGPU_API int evqgpu_partial_rows_split(const evqgpu_query_desc* desc, const void* body, uint64_t nbytes, uint64_t* row_offsets,
+                                         uint64_t cap_rows, uint64_t* nrows_out);
+EVQGPU_API int evqgpu_partial_cache_decode(const evqgpu_query_desc* desc, const void* entry, uint64_t nbytes, uint64_t* row_offsets,
+                                           uint64_t cap_rows, uint64_t* nrows_out);
+EVQGPU_API int evqgpu_partial_frames_decode(const evqgpu_query_desc* desc, const void* frames, uint64_t nbytes,
+                                            uint64_t* row_offsets, uint64_t cap_rows, uint64_t* nrows_out, uint64_t* nframes_out,
+                                            int* end_of_request_out);
+
 /* ORDER BY over the result rows of an executed (and, for multi-rank jobs, merged) query, on the device:
  * csql::OrderByExpression (sql/statements/select/orderby.cc:58-160) with sort expressions that are columns of the
  * result (what the planner hands the operator: it appends hidden select items for anything else).  Values compare like

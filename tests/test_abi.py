@@ -239,3 +239,32 @@ def test_partial_result_frames_equal_the_reference(native_lib):
     assert split_seen
     # no groups: one empty frame that ends the request
     assert capi.partial_frames_encode([]) == bytes([1, 2, 0, 1, 0, 0, 0, 2, 0, 0])
+
+
+def test_partial_rows_are_read_back_with_the_plan(native_lib):
+    """The coordinator's side of the partial-aggregation formats: the .qc entries and result frames the REFERENCE produced
+    (ref_partial.json) are split into (key, saved states) rows by walking them with the plan, like GroupByMergeExpression /
+    the cache load do (groupby.cc:553-615, :262-292); the rows are the reference's rows.  Truncated input is refused."""
+    import json
+    import os
+    with open(os.path.join(T.ROOT, "tests", "golden", "ref_partial.json")) as fh:
+        cases = json.load(fh)["cases"]
+    plans = {name: plan for name, _sql, plan in T.partial_cases()}
+    for name, g in cases.items():
+        want = sorted((bytes.fromhex(k), bytes.fromhex(d)) for k, d in g["rows"])
+        qc = bytes.fromhex(g["qc"])
+        assert sorted(capi.partial_cache_decode(plans[name], qc)) == want, name
+        assert sorted(capi.partial_rows_split(plans[name], qc[9:])) == want, name
+        for soft_max, hexed in g["frames"].items():
+            rows, nframes, eor = capi.partial_frames_decode(plans[name], bytes.fromhex(hexed))
+            assert sorted(rows) == want and eor and nframes >= 1, (name, soft_max)
+        # round trip through our own encoders
+        assert capi.partial_cache_decode(plans[name], capi.partial_cache_encode(want)) == want
+        rows, nframes, eor = capi.partial_frames_decode(plans[name], capi.partial_frames_encode(want, 512))
+        assert rows == want and eor
+        if len(qc) > 40:
+            with pytest.raises(capi.EvqError) as ei:
+                capi.partial_cache_decode(plans[name], qc[:-3])
+            assert ei.value.status == 5
+            with pytest.raises(capi.EvqError):
+                capi.partial_cache_decode(plans[name], bytes([2]) + qc[1:])
