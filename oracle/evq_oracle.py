@@ -9,7 +9,11 @@ Parity status: PINNED.  tests/test_oracle_pinning.py checks this restatement aga
     copied to tests/golden/ together with the fixture test/sql_testdata/testtbl.cst,
   * the known answers written down in io/cstable/cstable_test.cc:74-240,483-521,587-755,
   * outputs of the reference itself (oracle/_ref/evqlref, built from /root/reference by
-    oracle/build_ref.py) committed as tests/golden/ref_*.json by tests/golden/make_golden.py.
+    oracle/build_ref.py) committed as tests/golden/ref_*.json by tests/golden/make_golden*.py: query rows
+    (ref_results.json), ORDER BY / LIMIT rows in order (ref_orderby.json), PartialGroupByExpression rows with the
+    reference's own .qc cache entries and result frames (ref_partial.json), string columns and string queries on
+    reference-written tables (ref_strings.json, tests/test_strings_lsm.py), and the rows of the reference's own
+    eventql::PartitionCursor over LSM partitions for the visibility filter (ref_lsm.json).
 
 Everything below follows the reference file:line cited next to it (paths relative to
 /root/reference/src/eventql/).  Integer work is bit-exact (numpy uint64/int64 wrap like C);
