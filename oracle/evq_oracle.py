@@ -1085,6 +1085,129 @@ def run_partial_query(tables: Sequence[CSTableFile], plan: P.QueryPlan) -> List[
     return out
 
 
+def _read_varuint_at(data: bytes, pos: int) -> Tuple[int, int]:
+    v, sh = 0, 0
+    while True:
+        b = data[pos]
+        pos += 1
+        v |= (b & 0x7F) << sh
+        sh += 7
+        if not b & 0x80:
+            return v, pos
+
+
+def parse_partial_states(plan: P.QueryPlan, data: bytes) -> List[tuple]:
+    """The saved states of one partial-aggregation row, one entry per select item, as VM::loadInstanceState / SValue::decode
+    read them (groupby.cc:262-292, 590-600): ("value", type, packed bytes) | ("count", n) | ("sum", raw 64-bit or float) |
+    ("minmax", raw 64-bit value, seen) | ("mean", float sum, n)."""
+    out, pos = [], 0
+    for s in plan.select:
+        agg = P.find_aggregate(s)
+        if agg is None:
+            t = data[pos]
+            n, pos = _read_varuint_at(data, pos + 1)
+            out.append(("value", t, data[pos:pos + n]))
+            pos += n
+        elif agg.name == "count":
+            v, pos = _read_varuint_at(data, pos)
+            out.append(("count", v))
+        elif agg.name == "sum" and agg.type != P.FLOAT64:
+            v, pos = _read_varuint_at(data, pos)
+            out.append(("sum", v))
+        elif agg.name == "sum":
+            out.append(("sum", struct.unpack_from("<d", data, pos)[0]))
+            pos += 8
+        elif agg.name in ("min", "max"):
+            v, seen = struct.unpack_from("<QQ", data, pos)
+            out.append(("minmax", v, seen))
+            pos += 16
+        elif agg.name == "mean":
+            sm, n = struct.unpack_from("<dQ", data, pos)
+            out.append(("mean", sm, n))
+            pos += 16
+        else:
+            raise OracleError("aggregate %s has no partial state format" % agg.name)
+    if pos != len(data):
+        raise OracleError("invalid partialaggr result encoding")
+    return out
+
+
+def merge_partial_rows(plan: P.QueryPlan, row_lists: Sequence[Sequence[Tuple[bytes, bytes]]]) -> List[tuple]:
+    """GroupByMergeExpression (sql/statements/select/groupby.cc:553-615 execute, :617-660 nextBatch): the coordinator loads
+    the shards' (group key, saved states) rows, merges the states of equal keys with the aggregates' merge functions
+    (count / sum: += aggregate.cc:48-50, 196-198; min / max: over the seen ones, mean: sums and counts add,
+    sum<float64>: += - oracle/ref_tools/ext_aggregates.cc) - a non-aggregate item is overwritten by every row that carries
+    it (SValue::decode) - and evaluates every select item's `get` side per group.  Returns rows as python tuples (None = NULL)."""
+    M64 = (1 << 64) - 1
+    groups: Dict[bytes, list] = {}
+    for rows in row_lists:
+        for key, data in rows:
+            st = [list(x) for x in parse_partial_states(plan, data)]
+            cur = groups.get(key)
+            if cur is None:
+                groups[key] = st
+                continue
+            for i, (s, a, b) in enumerate(zip(plan.select, cur, st)):
+                kind = a[0]
+                if kind == "value":
+                    cur[i] = b
+                elif kind == "count":
+                    a[1] = (a[1] + b[1]) & M64
+                elif kind == "sum":
+                    a[1] = (a[1] + b[1]) & M64 if isinstance(a[1], int) else a[1] + b[1]
+                elif kind == "mean":
+                    a[1] += b[1]
+                    a[2] = (a[2] + b[2]) & M64
+                elif kind == "minmax":
+                    if not b[2]:
+                        continue
+                    agg = P.find_aggregate(s)
+                    dt = {P.INT64: "<q", P.FLOAT64: "<d"}.get(agg.type, "<Q")
+                    va = struct.unpack(dt, struct.pack("<Q", a[1]))[0]
+                    vb = struct.unpack(dt, struct.pack("<Q", b[1]))[0]
+                    if not a[2] or (vb > va if agg.name == "max" else vb < va):
+                        a[1] = b[1]
+                    a[2] = 1
+    out = []
+    zt = np.zeros(1, dtype=np.uint8)
+    for key, st in groups.items():
+        row = []
+        for s, a in zip(plan.select, st):
+            agg = P.find_aggregate(s)
+            if agg is None:
+                t, raw = a[1], a[2]
+                if t == P.BOOL:
+                    row.append(None if raw[1] & 1 else bool(raw[0]))
+                else:
+                    bits_ = struct.unpack_from("<Q", raw, 0)[0]
+                    if raw[8] & 1:
+                        row.append(None)
+                    elif t == P.FLOAT64:
+                        row.append(struct.unpack("<d", struct.pack("<Q", bits_))[0])
+                    elif t == P.INT64:
+                        row.append(struct.unpack("<q", struct.pack("<Q", bits_))[0])
+                    else:
+                        row.append(bits_)
+                continue
+            if a[0] == "count":
+                res = Vec(P.UINT64, np.array([a[1]], dtype=np.uint64), zt)
+            elif a[0] == "sum":
+                if agg.type == P.FLOAT64:
+                    res = Vec(P.FLOAT64, np.array([a[1]], dtype=np.float64), zt)
+                else:
+                    res = Vec(agg.type, np.array([a[1]], dtype=np.uint64).view(_NP_OF[agg.type]), zt)
+            elif a[0] == "minmax":
+                res = Vec(agg.type, np.array([a[1]], dtype=np.uint64).view(_NP_OF[agg.type]), zt)     # MinMax::get: the value (0 if none seen)
+            else:
+                with np.errstate(all="ignore"):
+                    res = Vec(P.FLOAT64, np.array([a[1]], dtype=np.float64) / np.float64(a[2]), zt)   # Mean::get: sum / n
+            v = res if s is agg else eval_expr(s, [], 1, None, (agg, res))
+            val = v.values.tolist()[0]
+            row.append(None if int(v.tags[0]) & 1 else val)
+        out.append(tuple(row))
+    return out
+
+
 def _aggregate(name: str, rtype: int, arg: Optional[Vec], starts: np.ndarray, m: int) -> Vec:
     ng = len(starts)
     zt = np.zeros(ng, dtype=np.uint8)

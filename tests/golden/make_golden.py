@@ -41,10 +41,10 @@ ENC_NAMES = {P.ENC_UINT64_LEB128: "leb128", P.ENC_UINT64_PLAIN: "uint64", P.ENC_
 TYPE_NAMES = {P.COL_UNSIGNED_INT: "uint", P.COL_DATETIME: "datetime", P.COL_FLOAT: "float", P.COL_BOOLEAN: "bool"}
 
 
-def ref_write(path, spec, nrows, version="v2", tmp="/tmp"):
+def ref_write(path, spec, nrows, version="v2", tmp="/tmp", row_offset=0):
     args = [EVQLREF, "write", path, version, str(nrows)]
     for s in spec:
-        v, nulls = T.synth_values(s, nrows)
+        v, nulls = T.synth_values(s, nrows, row_offset)
         df = os.path.join(tmp, "col_%s.bin" % s["name"])
         v.astype("<u8").tofile(df)
         a = "%s:%s:%s:%d:%s" % (s["name"], TYPE_NAMES[s.get("logical_type", P.COL_UNSIGNED_INT)], ENC_NAMES[s["encoding"]],

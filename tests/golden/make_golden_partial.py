@@ -29,6 +29,13 @@ def main():
     rp = os.path.join(tmp, "mixed.ref.cst")
     G.ref_write(rp, mk(), nrows, tmp=tmp)
     f = O.read_cstable(rp)
+    # a second partition (the rows behind the first one's) and the table that holds both: what two shards return, merged like
+    # GroupByMergeExpression does, must be what the reference answers on the whole table
+    nrows_b = 1700
+    rp_b = os.path.join(tmp, "mixed_b.ref.cst")
+    rp_all = os.path.join(tmp, "mixed_all.ref.cst")
+    G.ref_write(rp_b, mk(), nrows_b, tmp=tmp, row_offset=nrows)
+    G.ref_write(rp_all, mk(), nrows + nrows_b, tmp=tmp)
     out = {"generator": "tests/golden/make_golden_partial.py", "reference": "17ai/eventql v0.5.0 (oracle/_ref/evqlref sql -P)", "cases": {}}
     for name, sql, plan in T.partial_cases():
         cdir = tempfile.mkdtemp(prefix="evqqc")
@@ -52,7 +59,15 @@ def main():
                                 stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
             assert fr.returncode == 0, fr.stdout[-300:]
             frames[str(soft_max)] = open(ff, "rb").read().hex()
-        out["cases"][name] = {"sql": sql, "rows": rows, "qc_file": qcs[0], "qc": qc.hex(), "frames": frames}
+        rb = subprocess.run([G.EVQLREF, "sql", "-P", "-t", "t=" + rp_b, "-q", sql], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        rows_b = sorted(ln.split(";") for ln in rb.stdout.split("\n")[1:] if ln)
+        types, whole = G.ref_sql([("t", rp_all)], sql)
+        assert types != "error", (name, whole)
+        merged = O.merge_partial_rows(plan, [want, [(bytes.fromhex(k), bytes.fromhex(d)) for k, d in rows_b]])
+        ok, why = T.rows_equal(merged, T.parse_ref_rows(whole, types))
+        assert ok, (name, "merge of the two partitions' partial rows vs the reference on the whole table", why)
+        out["cases"][name] = {"sql": sql, "rows": rows, "qc_file": qcs[0], "qc": qc.hex(), "frames": frames,
+                              "merge": {"partition_b_rows": nrows_b, "rows_b": rows_b, "types": types, "whole_table_rows": whole}}
         print("case %-36s groups=%d ok" % (name, len(rows)))
     with open(os.path.join(HERE, "ref_partial.json"), "w") as fh:
         json.dump(out, fh, indent=0, separators=(",", ":"))
