@@ -1,0 +1,222 @@
+"""The drop-in, proven against the reference's REAL classes.
+
+`eventql_b200/evqgpu_refsql` is the reference's own Runtime - tokenizer, parser, QueryPlanBuilder, QueryPlan, ResultCursor,
+compiled from /root/reference by oracle/build_ref.py - with eventql_b200/host/refbind/gpu_binding.{h,cc} plugged in
+through the reference's two extension points: `GpuScheduler : csql::DefaultScheduler` via Runtime::setScheduler and
+`GpuCSTableScanProvider : csql::TableProvider` via TableRepository::addProvider.  Every golden SQL string goes in as
+TEXT; what comes out of ResultCursor must be the rows the unmodified reference engine returned for the same text
+(tests/golden/ref_*.json).  Nothing in the plan is built by hand: implicit to_<type> wrapping, folded constants,
+first-reference column order and hidden ORDER BY columns are whatever the reference's planner produces.
+
+The binary is built where the reference tree exists (eventql_b200/host/refbind/build.py, from __graft_entry__.build())
+and travels to the GPU box; the CPU test only checks that it links, loads libevqgpu.so and refuses to run without a
+device.
+"""
+import gzip
+import hashlib
+import json
+import os
+import subprocess
+
+import pytest
+
+from tests import common as T
+
+EXE = os.path.join(T.ROOT, "eventql_b200", "evqgpu_refsql")
+GOLD = os.path.join(T.ROOT, "tests", "golden")
+
+needs_binary = pytest.mark.skipif(not os.path.exists(EXE), reason="evqgpu_refsql is built only where the reference tree is present")
+
+
+def run_sql(tables, sql, extra=()):
+    """-> ('error', message) | (types, rows as lists of strings, GPUPLAN dict)"""
+    args = [EXE, "sql"]
+    for alias, paths in tables:
+        args += ["-t", "%s=%s" % (alias, ",".join(paths if isinstance(paths, (list, tuple)) else [paths]))]
+    args += list(extra) + ["-q", sql]
+    r = subprocess.run(args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+    out = r.stdout.decode("latin-1")
+    lines = out.split("\n")
+    if "ERROR!" in lines:
+        i = lines.index("ERROR!")
+        return "error", lines[i + 1] if i + 1 < len(lines) else ""
+    assert r.returncode == 0, (sql, r.stderr.decode()[-2000:])
+    assert lines[0].startswith("#"), lines[:3]
+    types = [h.rsplit(":", 1)[1] for h in lines[0][1:].split(";")]
+    rows = [ln.split(";") for ln in lines[1:] if ln != ""]
+    plan = {}
+    for ln in r.stderr.decode().splitlines():
+        if ln.startswith("GPUPLAN"):
+            plan = {k: int(v) for k, v in (kv.split("=") for kv in ln.split()[1:])}
+    return types, rows, plan
+
+
+@needs_binary
+def test_binding_links_against_the_reference_and_refuses_to_run_without_a_device():
+    """CPU: the binary exists, resolves libevqgpu.so next to it, and (without a GPU) fails loudly instead of falling back."""
+    import torch
+    r = subprocess.run(["ldd", EXE], stdout=subprocess.PIPE, text=True)
+    assert "libevqgpu.so" in r.stdout and "not found" not in r.stdout
+    if torch.cuda.is_available():
+        pytest.skip("a device is present: covered by the gpu tests")
+    res = run_sql([("testtable", os.path.join(GOLD, "testtbl.cst"))], "select count(1) from testtable;")
+    assert res[0] == "error" and "no host execution mode" in res[1]
+
+
+def _compare(name, got_types, got_rows, g, ordered):
+    assert got_types == g["types"], (name, got_types, g["types"])
+    want_rows = g["rows"]
+    if "sha256" in g:
+        got = T.parse_ref_rows(got_rows, got_types)
+        T.check_against_golden(name, got, ordered)
+        return
+    got = T.parse_string_query_rows(got_rows, got_types)
+    want = T.parse_string_query_rows(want_rows, g["types"])
+    if ordered:
+        assert len(got) == len(want), name
+        for i, (a, b) in enumerate(zip(got, want)):
+            ok, why = T.rows_equal([a], [b])
+            assert ok, "%s row %d: %s" % (name, i, why)
+    else:
+        ok, why = T.rows_equal(got, want)
+        assert ok, "%s: %s" % (name, why)
+
+
+_CASES = [(name, tname, alias, sql, not plan.is_groupby) for name, tname, alias, sql, plan in T.golden_cases()]
+_CASES += [(name, "testtbl.cst", "testtable", sql, not plan.is_groupby) for name, sql, plan in T.testtbl_queries()]
+
+
+@needs_binary
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,tname,alias,sql,ordered", _CASES, ids=[c[0] for c in _CASES])
+def test_sql_text_through_the_reference_planner_into_the_gpu_operators(case, tname, alias, sql, ordered):
+    g = T.golden()[case]
+    assert g["sql"] == sql
+    res = run_sql([(alias, T.golden_table_path(tname))], sql)
+    if "error" in g:
+        assert res[0] == "error" and g["error"] in res[1], res
+        return
+    assert res[0] != "error", res
+    types, rows, plan = res
+    _compare(case, types, rows, g, ordered)
+    # aggregate plans were fused onto the device by GpuScheduler::buildGroupByExpression; the operator protocol ran
+    if not ordered:
+        assert plan.get("fused_groupbys", 0) >= 1, plan
+    assert plan.get("heartbeats", 0) >= 1, plan
+
+
+_OB = T.orderby_cases()
+
+
+@needs_binary
+@pytest.mark.gpu
+@pytest.mark.parametrize("host_sort", [False, True], ids=["device_sort", "reference_orderby_over_gpu_groupby"])
+@pytest.mark.parametrize("case", _OB, ids=[c[0] for c in _OB])
+def test_order_by_limit_text_through_the_reference_planner(case, host_sort, monkeypatch):
+    """ORDER BY / LIMIT: once sorted on the device (GpuScheduler::buildOrderByExpression), once by the reference's own
+    OrderByExpression / LimitExpression pulling batches from the GPU operator (the upstream operators call the same two
+    methods) - rows in order, as the reference returned them."""
+    name, sql = case[0], case[1]
+    with open(os.path.join(GOLD, "ref_orderby.json")) as fh:
+        g = json.load(fh)["cases"][name]
+    assert g["sql"] == sql
+    if host_sort:
+        monkeypatch.setenv("EVQGPU_HOST_ORDERBY", "1")
+    res = run_sql([("t", T.golden_table_path("mixed"))], sql)
+    assert res[0] != "error", res
+    types, rows, plan = res
+    _compare(name, types, rows, g, True)
+    assert plan.get("fused_groupbys", 0) >= 1 or "group by" not in sql
+    if not host_sort and " order by " in sql:
+        assert plan.get("device_sorts", 0) >= 1, plan
+
+
+_SQ = T.string_query_cases()
+
+
+def _digest(v):
+    if v == "NULL":
+        return v
+    b = bytes.fromhex(v[1:])
+    return "x" + b.hex() if len(b) <= 48 else "sha1:%s:%d" % (hashlib.sha1(b).hexdigest(), len(b))
+
+
+@needs_binary
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,sql,plan,ordered", _SQ, ids=[c[0] for c in _SQ])
+def test_string_queries_text_through_the_reference_planner(name, sql, plan, ordered, tmp_path):
+    g = json.load(open(os.path.join(GOLD, "ref_strings.json")))["queries"][name]
+    p = str(tmp_path / "ref_strings_v2.cst")
+    with open(p, "wb") as fh:
+        fh.write(gzip.open(os.path.join(GOLD, "ref_strings_v2.cst.gz")).read())
+    res = run_sql([("t", p)], sql, extra=["-H"])
+    assert res[0] != "error", res
+    types, rows, _plan = res
+    rows = [[_digest(v) if t == "string" else v for v, t in zip(r, types)] for r in rows]
+    _compare(name, types, rows, g, ordered)
+
+
+_PA = T.partial_cases()
+
+
+@needs_binary
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", _PA, ids=[c[0] for c in _PA])
+def test_partial_group_by_rows_through_the_reference_planner(case):
+    """isPartialAggregation(): the shard side of a cluster GROUP BY - rows (20-byte SHA-1 group key, saved states) as the
+    reference's PartialGroupByExpression produces them for the same SQL text (tests/golden/ref_partial.json)."""
+    name, sql = case[0], case[1]
+    g = json.load(open(os.path.join(GOLD, "ref_partial.json")))["cases"][name]
+    assert g["sql"] == sql
+    res = run_sql([("t", T.golden_table_path("mixed"))], sql, extra=["-P"])
+    assert res[0] != "error", res
+    _types, rows, plan = res
+    assert sorted(map(tuple, rows)) == sorted(map(tuple, g["rows"]))
+    assert plan.get("fused_groupbys", 0) >= 1
+
+
+@needs_binary
+@pytest.mark.gpu
+def test_subquery_pass_through_is_fused(tmp_path):
+    """The H5 workaround form: GROUP BY over a SubqueryNode over a sequential scan (sql/statements/select/subquery.cc:57-120
+    is a pure projection + filter) is fused into the same device pass; equal to the direct form's golden rows."""
+    g = T.golden()["q1_lineitem_leb"]
+    path = T.golden_table_path("lineitem_leb")
+    sql = ("select flag, status, count(1), sum(quantity), sum(price), sum(price * (100 - discount)), "
+           "sum(price * (100 - discount) * (100 + tax)), sum(discount), mean(quantity), mean(price), mean(discount) "
+           "from (select flag, status, quantity, price, discount, tax, shipdate from lineitem where shipdate <= 10471) "
+           "where quantity > 0 and price > 0 and discount >= 0 and tax >= 0 group by flag, status;")
+    res = run_sql([("lineitem", path)], sql)
+    assert res[0] != "error", res
+    types, rows, plan = res
+    assert plan.get("fused_groupbys", 0) == 1, plan
+    got = T.parse_ref_rows(rows, types)
+    want = T.parse_ref_rows(g["rows"], g["types"])
+    if len(types) == len(g["types"]):
+        ok, why = T.rows_equal(got, want)
+        assert ok, why
+    else:   # the direct golden case has another select list: compare the shared leading columns
+        n = min(len(types), len(g["types"]))
+        ok, why = T.rows_equal([r[:n] for r in got], [r[:n] for r in want])
+        assert ok, why
+
+
+@needs_binary
+@pytest.mark.gpu
+def test_partitions_of_one_table_through_the_provider(tmp_path):
+    """A table served from several partition files: GROUP BY is one device pass over all of them."""
+    spec = T.lineitem_spec()
+    files = []
+    for i in range(3):
+        p = str(tmp_path / ("p%d.cst" % i))
+        T.write_table(p, spec, 30_000 + 1000 * i, row_offset=i * 50_000)
+        files.append(p)
+    sql, _plan = T.q1(spec)
+    whole = run_sql([("lineitem", files)], sql)
+    assert whole[0] != "error", whole
+    parts = [run_sql([("lineitem", [f])], sql) for f in files]
+    cnt = {}
+    for _t, rows, _p in parts:
+        for r in rows:
+            cnt[(r[0], r[1])] = cnt.get((r[0], r[1]), 0) + int(r[2])
+    assert {(r[0], r[1]): int(r[2]) for r in whole[1]} == cnt
