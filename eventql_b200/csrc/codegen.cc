@@ -142,6 +142,32 @@ void layout_states(evqgpu_query& q, const KernelShape& shape) {
       default: fail(EVQGPU_ERR_UNSUPPORTED, "aggregate %s", fi.symbol.c_str());
     }
   }
+  // first-row items: a pair of adjacent words [ordinal | tag][value], global memory only, 16-byte aligned in both state
+  // layouts: word w of a hash slot sits at slot + 1 + nkeys + w (slots are 32-byte aligned), word w of a dense slot at
+  // base + g * nstate + w with an even nstate and a base offset by (1 + nkeys) & 1 words (query.cu) - so (1 + nkeys + w) even
+  if (q.has_first) {
+    const size_t nk = q.group.size();
+    int npad = 0;
+    auto pad = [&]() {
+      word("pad:" + std::to_string(npad++), OP_ADD_U64);
+      q.state_global.back() = true;
+    };
+    for (auto& item : q.select) {
+      item.state_first = -1;
+      if (!item.first) continue;
+      const std::string sig = item.expr->signature();
+      bool found = false;
+      for (size_t i = 0; i < q.state_keys.size(); ++i)
+        if (q.state_keys[i] == "first_ord:" + sig) { item.state_first = (int) i; found = true; }
+      if (found) continue;
+      if ((1 + nk + q.state_keys.size()) & 1) pad();
+      item.state_first = word("first_ord:" + sig, OP_FIRST_ORD);
+      q.state_global.back() = true;
+      word("first_val:" + sig, OP_FIRST_VAL);
+      q.state_global.back() = true;
+    }
+    if (q.state_keys.size() & 1) pad();
+  }
   // carry words are touched once in 2^64 / value rows: they live in the global state only, never in thread-private storage
   q.state_smem.assign(q.state_ops.size(), -1);
   q.nstate_smem = 0;
@@ -176,6 +202,7 @@ void layout_narrow(evqgpu_query& q, const KernelShape& shape) {
   q.swar_slots = false;
   q.plane_sig.clear();
   if (!shape.fast || shape.tier != 1 || shape.g1 < 2 || shape.g1 > 4 || getenv("EVQGPU_NO_NARROW")) return;
+  if (q.has_first) return;   // first-row items are updated per row (evq_first_update): the per-row accumulate call stays
   const CodegenEnv env = row_env(shape);
   int budget = 56;   // u32 accumulator registers per thread
   if (const char* e = getenv("EVQGPU_PLANE_BUDGET")) budget = atoi(e);
@@ -341,6 +368,13 @@ static void gen_updates(std::ostringstream& os, const evqgpu_query& q, const Ker
   if (!done[0]) os << "  EVQ_UPD(0, " << OP_ADD_U64 << ", 1ull);\n";   // rows per group
   done[0] = true;
   for (const auto& item : q.select) {
+    if (item.first && item.state_first >= 0 && !done[item.state_first]) {
+      // the value of the group's first row (groupby.cc:161-172): smallest row ordinal wins, one 128-bit CAS
+      done[item.state_first] = true;
+      Code c = gen_expr(item.expr.get(), env);
+      os << "  {\n    const u64 t = (u64) ((" << c.tag << ") != 0u);\n    const u64 v = t ? 0ull : " << as_bits(c, item.expr->type) << ";\n";
+      os << "    evq_first_update(EVQ_GPTR(" << item.state_first << "), (row.ord << 1) | t, v);\n  }\n";
+    }
     if (!item.agg) continue;
     const FnInfo& fi = item.agg->info();
     const Expr* arg = item.agg->args.empty() ? nullptr : item.agg->args[0].get();
@@ -396,7 +430,7 @@ static void gen_general_layout(std::ostringstream& os, const KernelShape& shape)
   os << "struct EvqRow {\n";
   for (size_t i = 0; i < ncols; ++i)
     if (shape.cols[i].used) os << "  " << col_ctype(shape.cols[i].sql_type) << " c" << i << "; u32 t" << i << ";\n";
-  os << "  u32 _unused;\n};\n";
+  os << "  u64 ord;\n  u32 _unused;\n};\n";
   os << "struct EvqPrep {\n  EvqLebState leb[" << std::max(1, shape.nleb) << "];\n  u32 lebcount[" << std::max(1, shape.nleb)
      << "];\n  u32 nullpfx[" << std::max(1, shape.nnull) << "];\n};\n";
 
@@ -429,6 +463,7 @@ static void gen_general_layout(std::ostringstream& os, const KernelShape& shape)
 
   // ---- row decode: FastCSTableScan::fetchColumn* (sql/CSTableScan.cc:860-968) for one row
   os << "__device__ __forceinline__ void evq_load_row(const EvqTile& T, const EvqScanParams& P, const EvqScratch* scr, const EvqPrep& prep, u32 r, EvqRow& row) {\n";
+  os << "  row.ord = P.ord_base + P.tile_row_base * EVQ_TILE_ROWS + T.row0 + r;\n";   // table order over the partitions of the query
   for (size_t i = 0; i < ncols; ++i) {
     const ColSig& c = shape.cols[i];
     if (!c.used) continue;
@@ -481,8 +516,8 @@ static void gen_fast_layout(std::ostringstream& os, const KernelShape& shape) {
     os << "  " << fast_ctype(shape.cols[i]) << " c" << i << ";\n";
     if (shape.cols[i].nullable) os << "  u32 t" << i << ";\n";   // STag: 1 = NULL
   }
-  os << "  u32 _unused;\n};\n";
-  os << "struct EvqCols {\n";
+  os << "  u64 ord;\n  u32 _unused;\n};\n";
+  os << "struct EvqCols {\n  u64 ord0;\n";
   for (size_t i = 0; i < ncols; ++i)
     if (shape.cols[i].used && shape.cols[i].nullable) os << "  u32 n" << i << ", r" << i << ";\n";   // presence bits of the thread's rows, ordinal of its first value
   for (size_t i = 0; i < ncols; ++i)
@@ -615,7 +650,7 @@ static void gen_fast_layout(std::ostringstream& os, const KernelShape& shape) {
     os << "#pragma unroll\n    for (int k = 0; k < EVQ_RPT; ++k) cols.c" << i << "[k] = " << conv << ";\n  }\n";
   }
   os << "}\n";
-  os << "__device__ __forceinline__ void evq_fast_row(const EvqCols& cols, int k, EvqRow& row) {\n";
+  os << "__device__ __forceinline__ void evq_fast_row(const EvqCols& cols, int k, EvqRow& row) {\n  row.ord = cols.ord0 + k;\n";
   for (size_t i = 0; i < ncols; ++i) {
     if (!shape.cols[i].used) continue;
     os << "  row.c" << i << " = cols.c" << i << "[k];\n";
@@ -751,10 +786,11 @@ static std::string gen_row_functions(const evqgpu_query& q, const KernelShape& s
       os << "#define EVQ_UPD(st, op, v) _acc[EVQ_SM_##st * EVQ_NCONS] = evq_state_combine<op>(_acc[EVQ_SM_##st * EVQ_NCONS], (v))\n";
       os << "#define EVQ_UPD_C(st, cw, v) { const u64 _o = _acc[EVQ_SM_##st * EVQ_NCONS]; const u64 _n = _o + (v); "
             "_acc[EVQ_SM_##st * EVQ_NCONS] = _n; if (_n < _o) atomicAdd(dense_state + (u64) g * " << nstate << " + (cw), 1ull); }\n";
+      os << "#define EVQ_GPTR(st) (dense_state + (u64) g * " << nstate << " + (st))\n";
       os << "__device__ __forceinline__ void evq_accumulate_smem(const EvqRow& row, u64* sacc, u32 g, u32 tid, u64* dense_state, u32& err) {\n";
       os << "  u64* _acc = sacc + g * " << nsm << "u * EVQ_NCONS + tid;\n";
       gen_updates(os, q, shape);
-      os << "}\n#undef EVQ_UPD\n#undef EVQ_UPD_C\n";
+      os << "}\n#undef EVQ_UPD\n#undef EVQ_UPD_C\n#undef EVQ_GPTR\n";
       os << "__device__ __forceinline__ void evq_state_flush_smem(u64* sacc, u32 g, u32 tid, u64* dense_state) {\n";
       for (int w = 0; w < nstate; ++w)
         if (q.state_smem[w] >= 0)
@@ -867,9 +903,10 @@ static std::string gen_row_functions(const evqgpu_query& q, const KernelShape& s
       os << "#define EVQ_UPD(st, op, v) acc[EVQ_SM_##st] = evq_state_combine<op>(acc[EVQ_SM_##st], (v))\n";
       os << "#define EVQ_UPD_C(st, cw, v) { const u64 _o = acc[EVQ_SM_##st]; const u64 _n = _o + (v); acc[EVQ_SM_##st] = _n; "
             "if (_n < _o) atomicAdd(dense_state + (cw), 1ull); }\n";
+      os << "#define EVQ_GPTR(st) (dense_state + (st))\n";
       os << "__device__ __forceinline__ void evq_accumulate_regs(const EvqRow& row, u64* acc, u64* dense_state, u32& err) {\n";
       gen_updates(os, q, shape);
-      os << "}\n#undef EVQ_UPD\n#undef EVQ_UPD_C\n";
+      os << "}\n#undef EVQ_UPD\n#undef EVQ_UPD_C\n#undef EVQ_GPTR\n";
       os << "__device__ __forceinline__ void evq_state_flush_regs(u64* acc, u64* dense_state) {\n";
       for (int w = 0; w < nstate; ++w)
         if (q.state_smem[w] >= 0) gen_flush_word(w, "acc[" + std::to_string(q.state_smem[w]) + "]", "dense_state");
@@ -880,9 +917,10 @@ static std::string gen_row_functions(const evqgpu_query& q, const KernelShape& s
     os << "#define EVQ_UPD(st, op, v) evq_state_atomic<op>(state + (st), (v))\n";
     os << "#define EVQ_UPD_C(st, cw, v) { const u64 _v = (v); const u64 _o = atomicAdd(state + (st), _v); "
           "if (_o + _v < _v) atomicAdd(state + (cw), 1ull); }\n";
+    os << "#define EVQ_GPTR(st) (state + (st))\n";
     os << "__device__ __forceinline__ void evq_accumulate_global(const EvqRow& row, u64* state, u32& err) {\n";
     gen_updates(os, q, shape);
-    os << "}\n#undef EVQ_UPD\n#undef EVQ_UPD_C\n";
+    os << "}\n#undef EVQ_UPD\n#undef EVQ_UPD_C\n#undef EVQ_GPTR\n";
   } else if (shape.tier == 3) {
     // scan-only projection: select list evaluated on the rows that pass, packed SVector elements in table order
     os << "__device__ __forceinline__ void evq_project(const EvqRow& row, const EvqScanParams& P, u64 out_row, u32& err) {\n";
@@ -985,8 +1023,14 @@ static std::string gen_group_kernels(const evqgpu_query& q, const KernelShape& s
       }
       e2.subst.push_back({item.agg->signature(), {val, "0u"}});
     }
-    Code c = gen_expr(item.expr.get(), e2);
     const int ty = item.expr->type;
+    if (item.first) {   // the boxed value of the group's first row (groupby.cc:161-172, :213-215)
+      const std::string v = "st[" + std::to_string(item.state_first + 1) + "]", t = "(u32) (st[" + std::to_string(item.state_first) + "] & 1ull)";
+      if (ty == EVQ_BOOL) os << "  evq_store_packed2(E.out_cols[" << i << "] + out_row * 2, " << v << ", " << t << ");\n";
+      else os << "  evq_store_packed9(E.out_cols[" << i << "] + out_row * 9, " << v << ", " << t << ");\n";
+      continue;
+    }
+    Code c = gen_expr(item.expr.get(), e2);
     if (ty == EVQ_BOOL)
       os << "  evq_store_packed2(E.out_cols[" << i << "] + out_row * 2, " << as_bits(c, ty) << ", " << c.tag << ");\n";
     else

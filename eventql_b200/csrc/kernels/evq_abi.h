@@ -84,6 +84,7 @@ struct EvqScanParams {
   u32* status;                      // [0] error bits, [1] unused
   u64* counters;                    // [0] rows passed, [1] groups claimed (tier 2)
   u64 tile_row_base;                // first tile index of this table inside tile_counts
+  u64 ord_base;                     // added to a row's ordinal (tile index * 1024 + row in tile): rank-major order of a multi-rank job
 };
 
 

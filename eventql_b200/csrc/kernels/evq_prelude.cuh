@@ -578,11 +578,17 @@ __device__ __forceinline__ void evq_atomic_max_f64(u64* addr, f64 v) {
 #define EVQ_OP_MAX_I64 5
 #define EVQ_OP_MIN_F64 6
 #define EVQ_OP_MAX_F64 7
+// "first row wins" for a non-aggregate select item that is not a function of the GROUP BY key (groupby.cc:161-172: the
+// reference evaluates and boxes it for the group's FIRST row only).  A pair of adjacent, 16-byte aligned state words:
+// [row ordinal << 1 | NULL tag] (the smallest wins) and [value bits of that row], updated with ONE 128-bit CAS.
+#define EVQ_OP_FIRST_ORD 8
+#define EVQ_OP_FIRST_VAL 9
 
 template <int OP>
 __device__ __forceinline__ u64 evq_state_identity() {
   switch (OP) {
     case EVQ_OP_MIN_U64: return ~0ull;
+    case EVQ_OP_FIRST_ORD: return ~0ull;
     case EVQ_OP_MIN_I64: return 0x7fffffffffffffffull;
     case EVQ_OP_MAX_I64: return 0x8000000000000000ull;
     case EVQ_OP_MIN_F64: return 0x7ff0000000000000ull;
@@ -617,6 +623,22 @@ __device__ __forceinline__ void evq_state_atomic(u64* addr, u64 v) {
     case EVQ_OP_MAX_I64: atomicMax((i64*) addr, (i64) v); break;
     case EVQ_OP_MIN_F64: evq_atomic_min_f64(addr, __longlong_as_double((i64) v)); break;
     default: evq_atomic_max_f64(addr, __longlong_as_double((i64) v)); break;
+  }
+}
+
+// keep the (ordinal|tag, value) pair with the smallest first word (global memory, 16-byte aligned)
+__device__ __forceinline__ void evq_first_update(u64* pair, u64 ordtag, u64 value) {
+  u64 cur = *(volatile u64*) pair;
+  if (ordtag >= cur) return;   // the common case after the group's first rows: one (L2-resident) load
+  u64 curv = *(volatile u64*) (pair + 1);
+  for (;;) {
+    u64 olo, ohi;
+    asm volatile("{\n\t.reg .b128 c, n, o;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 n, {%4, %5};\n\t"
+                 "atom.global.relaxed.gpu.cas.b128 o, [%6], c, n;\n\tmov.b128 {%0, %1}, o;\n\t}"
+                 : "=l"(olo), "=l"(ohi) : "l"(cur), "l"(curv), "l"(ordtag), "l"(value), "l"(pair) : "memory");
+    if ((olo == cur && ohi == curv) || ordtag >= olo) return;
+    cur = olo;
+    curv = ohi;
   }
 }
 

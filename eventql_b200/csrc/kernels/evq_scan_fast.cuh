@@ -663,6 +663,7 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
     EvqFastPrep prep;
     evq_fast_prep(T, P, scr, prep);
     EvqCols cols;
+    cols.ord0 = P.ord_base + (P.tile_row_base + tile) * (u64) EVQ_TILE_ROWS + EVQ_RPT * tid;   // (dead unless a first-row item reads row.ord)
 #if EVQ_NNULL > 0
     evq_fast_nulls(T, P, scr, nullbuf, nvalid, cols);
     nullbuf ^= 1u;

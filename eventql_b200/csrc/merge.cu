@@ -33,6 +33,7 @@ struct MergeOps {
 __device__ __forceinline__ u64 merge_identity(int op) {
   switch (op) {
     case EVQ_OP_MIN_U64: return evq_state_identity<EVQ_OP_MIN_U64>();
+    case EVQ_OP_FIRST_ORD: return ~0ull;
     case EVQ_OP_MIN_I64: return evq_state_identity<EVQ_OP_MIN_I64>();
     case EVQ_OP_MAX_I64: return evq_state_identity<EVQ_OP_MAX_I64>();
     case EVQ_OP_MIN_F64: return evq_state_identity<EVQ_OP_MIN_F64>();
@@ -74,6 +75,17 @@ __global__ void k_merge_dense(u64* __restrict__ state, const u64* __restrict__ g
   if (i >= nwords) return;
   const int w = (int) (i % mo.nstate);
   const int op = mo.ops[w];
+  if (op == EVQ_OP_FIRST_ORD || op == EVQ_OP_FIRST_VAL) {
+    // first-row pair: the (ordinal | tag, value) of the rank whose ordinal word is smallest (ordinals are rank-major)
+    const u64 oi = op == EVQ_OP_FIRST_ORD ? i : i - 1;
+    u64 best = gathered[oi], val = gathered[oi + 1];
+    for (int r = 1; r < nranks; ++r) {
+      const u64 o = gathered[(u64) r * nwords + oi];
+      if (o < best) { best = o; val = gathered[(u64) r * nwords + oi + 1]; }
+    }
+    state[i] = op == EVQ_OP_FIRST_ORD ? best : val;
+    return;
+  }
   u64 acc = gathered[i];
   for (int r = 1; r < nranks; ++r) acc = merge_combine(op, acc, gathered[(u64) r * nwords + i]);
   if (mo.carry_of[w] >= 0) {
@@ -155,6 +167,11 @@ __global__ void k_merge_insert(EvqHashTable H, MergeOps mo, const u64* __restric
     u64* state = sp + 1 + NK;
     for (int s = 0; s < mo.nstate; ++s) {
       const u64 v = src[NK + 1 + s];
+      if (mo.ops[s] == EVQ_OP_FIRST_VAL) continue;
+      if (mo.ops[s] == EVQ_OP_FIRST_ORD) {
+        if (v != ~0ull) evq_first_update(state + s, v, src[NK + 1 + s + 1]);
+        continue;
+      }
       if (mo.carry_at[s] >= 0) {
         if (v) {
           const u64 old = atomicAdd(state + s, v);
@@ -194,8 +211,8 @@ static void merge_dense(evqgpu_query& q) {
   const uint64_t slots = q.shape.g1 > 1 ? (uint64_t) q.shape.g1 : 1;
   const uint64_t nwords = slots * mo.nstate;
   if (q.merge_recv.bytes < nwords * 8 * ctx->nranks) q.merge_recv.alloc(nwords * 8 * ctx->nranks);
-  comm_all_gather(ctx, q.dense_state.p, q.merge_recv.p, nwords * 8);
-  k_merge_dense<<<(unsigned) ((nwords + 127) / 128), 128, 0, ctx->stream>>>(q.dense_state.as<u64>(), q.merge_recv.as<u64>(),
+  comm_all_gather(ctx, q.dense_base, q.merge_recv.p, nwords * 8);
+  k_merge_dense<<<(unsigned) ((nwords + 127) / 128), 128, 0, ctx->stream>>>(q.dense_base, q.merge_recv.as<u64>(),
                                                                            ctx->nranks, nwords, mo);
   EVQ_CUDA(cudaGetLastError());
   ctx->kernel_launches++;

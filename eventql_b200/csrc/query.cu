@@ -207,14 +207,20 @@ static size_t acc_bytes(const evqgpu_query& q, const KernelShape& s) {
 
 // ---- plan intake -----------------------------------------------------------------------------------------------------
 
-static void check_scalar_item(const evqgpu_query& q, const Expr* e) {
-  // non-aggregate select items must be functions of the GROUP BY key (the reference takes the group's first row,
-  // groupby.cc:161-172, which is only deterministic in that case); verified by trying to generate the emit code
+static bool is_function_of_keys(const evqgpu_query& q, const Expr* e) {
+  // a non-aggregate select item that is a function of the GROUP BY key is evaluated from the stored key at emit time;
+  // anything else takes the value of the group's first row (groupby.cc:161-172).  Decided by trying to generate the emit code.
   CodegenEnv env;
   env.col_value.assign(q.input_columns.size(), "");
   env.col_tag.assign(q.input_columns.size(), "");
   for (size_t i = 0; i < q.group.size(); ++i) env.subst.push_back({q.group[i]->signature(), {"k", "t"}});
-  (void) gen_expr(e, env);
+  try {
+    (void) gen_expr(e, env);
+  } catch (const Error& err) {
+    if (err.status == EVQGPU_ERR_UNSUPPORTED) return false;
+    throw;
+  }
+  return true;
 }
 
 namespace evq {
@@ -304,8 +310,12 @@ void query_intake(evqgpu_query* q, const evqgpu_query_desc* desc) {
     q->select.push_back(std::move(item));
   }
   if (groupby)
-    for (const auto& item : q->select)
-      if (!item.agg) check_scalar_item(*q, item.expr.get());
+    for (auto& item : q->select)
+      if (!item.agg && !is_function_of_keys(*q, item.expr.get())) {
+        if (item.is_string) fail(EVQGPU_ERR_UNSUPPORTED, "a string select item of an aggregate plan must be a GROUP BY key");
+        item.first = true;
+        q->has_first = true;
+      }
   // which input columns does the device actually have to read
   q->col_used.assign(q->input_columns.size(), false);
   collect_columns(q->where.get(), q->col_used);
@@ -313,6 +323,7 @@ void query_intake(evqgpu_query* q, const evqgpu_query_desc* desc) {
   for (const auto& item : q->select) {
     if (!groupby) collect_columns(item.expr.get(), q->col_used);
     else if (item.agg) for (const auto& a : item.agg->args) collect_columns(a.get(), q->col_used);
+    else if (item.first) collect_columns(item.expr.get(), q->col_used);
   }
 }
 
@@ -803,6 +814,7 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
   memset(&base, 0, sizeof(base));
   base.status = q.status.as<u32>();
   base.counters = q.counters.as<u64>();
+  base.ord_base = (u64) ctx->rank << 44;   // rank-major row ordinals (first-row items of a multi-rank job)
   EVQ_CUDA(cudaMemsetAsync(q.status.p, 0, 16, ctx->stream));
   EVQ_CUDA(cudaMemsetAsync(q.counters.p, 0, 32, ctx->stream));
   InitParams ip;
@@ -810,8 +822,10 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
   uint64_t emit_slots = 0;
   if (s.tier == 1 || s.dense_global) {
     const uint64_t slots = s.dense_global ? dm.slots : s.g1 > 1 ? (uint64_t) s.g1 : 1;
-    ensure(q.dense_state, slots * nstate * 8);
-    base.dense_state = q.dense_state.as<u64>();
+    ensure(q.dense_state, slots * nstate * 8 + 16);
+    // first-row pairs must be 16-byte aligned in both tiers: their word index w has (1 + nk + w) even (layout_states)
+    q.dense_base = q.dense_state.as<u64>() + ((q.has_first && ((1 + nk) & 1)) ? 1 : 0);
+    base.dense_state = q.dense_base;
     base.dense_slots = (s.g1 > 1 || s.dense_global) ? dm.slots : 1;
     for (size_t i = 0; i < nk; ++i) {
       base.key_min[i] = dm.key_min[i];

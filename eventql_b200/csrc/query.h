@@ -12,7 +12,8 @@
 namespace evq {
 
 // state-word op codes (kernels/evq_prelude.cuh EVQ_OP_*)
-enum { OP_ADD_U64 = 0, OP_ADD_F64 = 1, OP_MIN_U64 = 2, OP_MAX_U64 = 3, OP_MIN_I64 = 4, OP_MAX_I64 = 5, OP_MIN_F64 = 6, OP_MAX_F64 = 7 };
+enum { OP_ADD_U64 = 0, OP_ADD_F64 = 1, OP_MIN_U64 = 2, OP_MAX_U64 = 3, OP_MIN_I64 = 4, OP_MAX_I64 = 5, OP_MIN_F64 = 6, OP_MAX_F64 = 7,
+       OP_FIRST_ORD = 8, OP_FIRST_VAL = 9 };
 
 struct SelectItem {
   ExprPtr expr;
@@ -23,6 +24,11 @@ struct SelectItem {
   int state_carry = -1;        // mean over a uint64 argument: wraps of the 64-bit sum word (exact 128-bit integer sum)
   int distinct = -1;           // count_distinct: index into evqgpu_query::distinct_args
   bool is_string = false;      // a bare string column: the device column holds dictionary codes, fetched with evqgpu_query_fetch_strings
+  // a non-aggregate item that is NOT a function of the GROUP BY key (e.g. the hidden columns the planner appends for
+  // `ORDER BY <expression>`): the reference boxes its value for the group's first row (groupby.cc:161-172); here the pair
+  // of state words state_first (row ordinal | tag, smallest wins) and state_first + 1 (value bits of that row)
+  bool first = false;
+  int state_first = -1;
 };
 
 // how one input column is laid out on the device (part of the kernel's specialisation key)
@@ -138,6 +144,8 @@ struct evqgpu_query {
   std::vector<bool> col_used;
   std::vector<bool> col_is_string;   // plan input columns read as dictionary codes of a string column (strings.cu)
   bool string_keys = false;          // a GROUP BY expression is a string column
+  bool has_first = false;            // some select item takes the value of its group's first row (SelectItem::first)
+  u64* dense_base = nullptr;         // dense_state, offset by one word where that makes the first-row pairs 16-byte aligned
 
   // device state, reused across executions
   evq::DevBuf merge_recv, merge_send, merge_slots, merge_counts;

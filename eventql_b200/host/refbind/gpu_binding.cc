@@ -186,7 +186,11 @@ ReturnCode GpuTableExpression::run(const evqgpu_query_desc& desc) {
   if (evqgpu_query_num_rows(query_, &num_rows_) != EVQGPU_OK) return ReturnCode::error("ERUNTIME", lastError());
   cursor_ = 0;
   completed_ = false;
-  staging_.assign(evqgpu_query_num_columns(query_), std::vector<uint8_t>(kOutputBatchSize * 9));
+  if (evqgpu_query_num_columns(query_) != types_.size()) return ReturnCode::error("ERUNTIME", "device query and plan disagree on the column count");
+  for (size_t i = 0; i < types_.size(); ++i)
+    if ((SType) evqgpu_query_column_type(query_, (uint32_t) i) != types_[i])
+      return ReturnCode::error("ERUNTIME", "device query and plan disagree on the type of column %d", (int) i);
+  staging_.assign(types_.size(), std::vector<uint8_t>(kOutputBatchSize * 9));
   return ReturnCode::success();
 }
 
@@ -236,8 +240,10 @@ ReturnCode GpuTableExpression::nextBatch(SVector* columns, size_t* len) {
   return ReturnCode::success();
 }
 
-size_t GpuTableExpression::getColumnCount() const { return query_ ? evqgpu_query_num_columns(query_) : 0; }
-SType GpuTableExpression::getColumnType(size_t idx) const { return (SType) evqgpu_query_column_type(query_, (uint32_t) idx); }
+// (ResultCursor and the operators above size their buffers from these BEFORE execute(), result_cursor.cc:34-43: the types
+// come from the plan, not from the device query)
+size_t GpuTableExpression::getColumnCount() const { return types_.size(); }
+SType GpuTableExpression::getColumnType(size_t idx) const { return types_.at(idx); }
 
 // the identity of the inputs (path, inode, size, mtime of every file) + the plan: what eventql::TableScan::getCacheKey
 // supplies in the server (server/sql/table_scan.cc:173); lets PartialGroupByExpression use its query cache (groupby.cc:255-295)
@@ -254,7 +260,6 @@ public:
   Impl(Transaction* txn, ExecutionContext* ectx, RefPtr<GpuDevice> gpu, RefPtr<SequentialScanNode> stmt, const String& file)
       : GpuTableExpression(txn, ectx, gpu, Vector<String>{file}), stmt_(stmt), filter_enabled_(false) {
     plan_text_ = stmt_->toString();
-    // (the column types must be known before execute(): ResultCursor and the operators above size their buffers from them)
     for (const auto& s : stmt_->selectList()) types_.push_back(s->expression()->getReturnType());
   }
   ReturnCode execute() override {
@@ -290,10 +295,7 @@ public:
     if (filter_enabled_) evqgpu_table_set_filter(t, nullptr, 0, 0);   // the filter belongs to this scan, the resident table is shared
     return rc;
   }
-  size_t getColumnCount() const override { return types_.size(); }
-  SType getColumnType(size_t idx) const override { return types_[idx]; }
   RefPtr<SequentialScanNode> stmt_;
-  std::vector<SType> types_;
   std::vector<bool> filter_;
   bool filter_enabled_;
 };
@@ -322,6 +324,7 @@ GpuGroupByExpression::GpuGroupByExpression(Transaction* txn, ExecutionContext* e
     : GpuTableExpression(txn, ectx, gpu, std::move(partition_files)), node_(node), scan_(scan), through_(through),
       extra_flags_(extra_flags) {
   plan_text_ = node_->toString();
+  for (const auto& s : node_->selectList()) types_.push_back(s->expression()->getReturnType());
 }
 
 // e with every column reference replaced through `column_map`, spelled as a postfix program over the scan's input columns

@@ -83,7 +83,6 @@ public:
   Option<SHA1Hash> getCacheKey() const override;
   evqgpu_query* handle() const { return query_; }
   ReturnCode refresh();   // after ORDER BY / LIMIT rewrote the device result
-  // result columns beyond this count are hidden (ORDER BY helper columns are cut by the operators above)
 protected:
   GpuTableExpression(csql::Transaction* txn, csql::ExecutionContext* ectx, RefPtr<GpuDevice> gpu, Vector<String> files);
   ReturnCode run(const evqgpu_query_desc& desc);
@@ -92,6 +91,7 @@ protected:
   RefPtr<GpuDevice> gpu_;
   Vector<String> filenames_;
   String plan_text_;        // qtree text: part of the cache key
+  std::vector<csql::SType> types_;   // result column types, known from the plan before execute()
   evqgpu_query* query_;
   uint64_t cursor_, num_rows_;
   bool completed_;

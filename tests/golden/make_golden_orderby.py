@@ -31,7 +31,9 @@ def main():
     out = {"generator": "tests/golden/make_golden_orderby.py", "reference": "17ai/eventql v0.5.0 (oracle/_ref/evqlref)", "cases": {}}
     for name, sql, plan, specs, limit, offset, ncols in T.orderby_cases():
         types, rows = G.ref_sql([("t", rp)], sql)
-        # the planner appends hidden select items for the sort expressions: keep the query's own columns
+        # the planner appends hidden select items for the sort expressions (their values: the group's first row,
+        # groupby.cc:161-172): stored as "full_*" for the binding test, the query's own columns as "types" / "rows"
+        full_types, full_rows = types, rows
         types, rows = types[:ncols], [r[:ncols] for r in rows]
         want = T.parse_ref_rows(rows, types)
         res = O.run_query([f], plan)
@@ -44,7 +46,7 @@ def main():
         for g, w in zip(got, want):
             ok, why = T.rows_equal([g], [w])
             assert ok, (name, why)
-        out["cases"][name] = {"sql": sql, "types": types, "rows": rows}
+        out["cases"][name] = {"sql": sql, "types": types, "rows": rows, "full_types": full_types, "full_rows": full_rows}
         print("case %-28s rows=%d ok" % (name, len(rows)))
     with open(os.path.join(HERE, "ref_orderby.json"), "w") as fh:
         json.dump(out, fh, indent=0, separators=(",", ":"))

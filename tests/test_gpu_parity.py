@@ -322,6 +322,53 @@ def test_order_by_limit_equals_reference_engine(gpu_ctx, case):
     compare(got, res.rows(), True)
 
 
+@pytest.mark.parametrize("shape", ["dense", "hash", "global", "wire"])
+def test_first_row_items(gpu_ctx, tmp_path, shape):
+    """Non-aggregate select items that are NOT functions of the GROUP BY key - what the reference's planner appends as hidden
+    columns for `ORDER BY <expression>` - take the value (and NULL tag) of the group's FIRST row in table order
+    (groupby.cc:161-172): one 128-bit CAS on (row ordinal | tag, value) per improving row.  Every tier, optional columns,
+    two partitions (table order = partition order)."""
+    spec = T.mixed_spec()
+    c, names = T.cols_of(spec)
+    cnt = P.call("count", P.lit(1))
+    files = []
+    for i, n in enumerate((33_000, 21_000)):
+        p = str(tmp_path / ("m%d.cst" % i))
+        T.write_table(p, spec, n, row_offset=i * 40_000)
+        files.append(p)
+    if shape == "dense":
+        k0, k1 = c["b"] % 7, c["d"] % 3
+        plan = P.QueryPlan(names, [k0, k1, cnt, P.call("sum", c["c"]), c["b"], c["d"], c["a"] + 1, c["f"], c["bo"]],
+                           where=(c["b"] >= 0), group=[k0, k1])
+    elif shape == "global":
+        plan = P.QueryPlan(names, [cnt, c["a"], c["k"], c["t"]], where=(c["b"] >= 3))
+    elif shape == "wire":
+        plan = P.QueryPlan(names, [c["b"] % 5, cnt, c["a"], c["d"]], where=(c["b"] >= 0), group=[c["b"] % 5], flags=P.QUERY_GROUPBY | P.QUERY_WIRE)
+    else:
+        plan = P.QueryPlan(names, [c["c"] % 5003, cnt, P.call("max", c["b"]), c["a"], c["big"], c["k"]], where=(c["b"] >= 0),
+                           group=[c["c"] % 5003], expected_groups=1 << 25)
+    tables = [gpu_ctx.open_table_file(p) for p in files]
+    try:
+        q = gpu_ctx.query(plan)
+        try:
+            q.execute(tables)
+            got = q.rows()
+            st = q.stats()
+            part = q.fetch_partial() if shape == "wire" else None
+        finally:
+            q.close()
+        fs = [O.read_cstable(p) for p in files]
+        want = O.run_query(fs, plan).rows()
+        compare(got, want, False)
+        assert st["strategy"] == {"dense": 1, "global": 1, "wire": 1, "hash": 2}[shape]
+        if part is not None:
+            ok, why = T.partial_rows_equal(plan, part, O.run_partial_query(fs, plan))
+            assert ok, why
+    finally:
+        for t in tables:
+            t.close()
+
+
 def test_order_by_large_result_properties(gpu_ctx):
     """ORDER BY over a 2 M-group result (hash tier): sortedness, stability across equal keys, permutation of the unsorted
     rows, LIMIT / OFFSET windows; multi-key and descending orders against numpy's lexsort."""
