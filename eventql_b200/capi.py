@@ -57,7 +57,7 @@ class SynthColumn(C.Structure):
 class QueryStats(C.Structure):
     _fields_ = [("rows_scanned", C.c_uint64), ("rows_passed", C.c_uint64), ("algorithmic_bytes", C.c_uint64),
                 ("num_groups", C.c_uint64), ("kernel_launches", C.c_uint32), ("strategy", C.c_uint32),
-                ("jit_ms", C.c_float), ("scan_ms", C.c_float), ("scan_launches", C.c_uint32), ("reserved", C.c_uint32)]
+                ("jit_ms", C.c_float), ("scan_ms", C.c_float), ("scan_launches", C.c_uint32), ("jit_disk_hits", C.c_uint32)]
 
 
 class SortSpec(C.Structure):
@@ -91,7 +91,7 @@ SYMBOLS = [
     "evqgpu_table_find_column", "evqgpu_table_load_columns", "evqgpu_table_read_stream", "evqgpu_table_decode_column",
     "evqgpu_table_write_file", "evqgpu_table_synthesize", "evqgpu_function_lookup", "evqgpu_function_symbol",
     "evqgpu_function_is_aggregate", "evqgpu_query_create", "evqgpu_query_destroy", "evqgpu_query_num_columns",
-    "evqgpu_query_column_type", "evqgpu_query_execute", "evqgpu_query_enqueue", "evqgpu_query_finish",
+    "evqgpu_query_column_type", "evqgpu_query_prepare", "evqgpu_query_execute", "evqgpu_query_enqueue", "evqgpu_query_finish",
     "evqgpu_query_num_rows", "evqgpu_query_fetch", "evqgpu_query_order_by", "evqgpu_query_limit", "evqgpu_query_fetch_partial", "evqgpu_query_get_stats", "evqgpu_query_kernel_source",
     "evqgpu_comm_unique_id", "evqgpu_comm_init", "evqgpu_comm_destroy", "evqgpu_query_merge", "evqgpu_debug_generate",
     "evqgpu_table_decode_string_column", "evqgpu_table_get_filter", "evqgpu_lsm_build_filters", "evqgpu_query_fetch_strings",
@@ -159,6 +159,7 @@ def lib() -> C.CDLL:
     L.evqgpu_query_column_type.restype = u32
     L.evqgpu_query_execute.argtypes = [vp, C.POINTER(vp), u32]
     L.evqgpu_query_enqueue.argtypes = [vp, C.POINTER(vp), u32]
+    L.evqgpu_query_prepare.argtypes = [vp, C.POINTER(vp), u32]
     L.evqgpu_query_finish.argtypes = [vp]
     L.evqgpu_query_num_rows.argtypes = [vp, C.POINTER(u64)]
     L.evqgpu_query_fetch.argtypes = [vp, u64, u64, C.POINTER(vp), C.POINTER(u64)]
@@ -572,6 +573,12 @@ class Query:
 
     def execute(self, tables: Sequence[Table]):
         check(lib().evqgpu_query_execute(self._h, self._tables(tables), len(tables)))
+        return self
+
+    def prepare(self, tables: Sequence[Table]):
+        """Multi-rank jobs: COLLECTIVE - every rank calls it before enqueue() whenever its table set changes (execute() does
+        it implicitly); the ranks agree on slot assignment and state layout, a local failure fails all ranks."""
+        check(lib().evqgpu_query_prepare(self._h, self._tables(tables), len(tables)))
         return self
 
     def enqueue(self, tables: Sequence[Table]):

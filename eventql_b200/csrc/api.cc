@@ -34,6 +34,7 @@ int evqgpu_ctx_create(int device, uint64_t flags, evqgpu_ctx** out) {
     if (prop.major < 10)
       fail(EVQGPU_ERR_UNSUPPORTED, "device %d is sm_%d%d; the kernels are written for sm_100a (B200)", device, prop.major, prop.minor);
     EVQ_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->pool = pool_create();
     EVQ_CUDA(cudaMallocHost(&ctx->pinned_scratch, 4096));
     *out = ctx.release();
   });
@@ -46,7 +47,8 @@ void evqgpu_ctx_destroy(evqgpu_ctx* ctx) {
   cudaSetDevice(ctx->device);
   evqgpu_comm_destroy(ctx);
   ctx->jit_cache.clear();
-  evq::pool_trim(ctx->device);
+  evq::pool_trim(ctx->pool);   // blocks still held by live tables / queries return to the (shared) pool object and go with it
+  evq::set_current_ctx(nullptr);
   if (ctx->pinned_scratch) cudaFreeHost(ctx->pinned_scratch);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;

@@ -10,6 +10,7 @@
 
 namespace evq {
 struct JitModule;
+struct Pool;   // device memory blocks cached for reuse (util.cc)
 }
 
 struct evqgpu_ctx {
@@ -31,30 +32,42 @@ struct evqgpu_ctx {
   // string literal, gets a dense code; code 0 is the empty string (what a NULL string compares as, boolean.cc:235-257)
   std::unordered_map<std::string, uint32_t> string_codes;
   std::vector<std::string> code_strings;
+  // device memory pool of THIS context.  All work of a context is ordered on its one stream, so a block freed by the
+  // context and handed out again to the same context is reused in stream order; blocks never move between contexts
+  // (two contexts on one device have two streams: a shared pool would hand a block to the other stream while kernels of
+  // the first still use it).
+  std::shared_ptr<evq::Pool> pool;
 };
 
 namespace evq {
 
-inline void use_device(const evqgpu_ctx* ctx) { EVQ_CUDA(cudaSetDevice(ctx->device)); }
+// the context whose entry point runs on this thread: device allocations are served from its pool
+void set_current_ctx(const evqgpu_ctx* ctx);
+inline void use_device(const evqgpu_ctx* ctx) {
+  EVQ_CUDA(cudaSetDevice(ctx->device));
+  set_current_ctx(ctx);
+}
 
-// Device memory goes through a small per-device pool: loading a column allocates ~8 buffers (stream, indexes, scan
+// Device memory goes through a small per-CONTEXT pool: loading a column allocates ~8 buffers (stream, indexes, scan
 // scratch) and cudaMalloc / cudaFree of hundreds of MB cost about a millisecond each (cudaFree also synchronises the
-// device), which dominated the per-column load time.  Blocks are reused by best fit (within 25 % slack); the pool is
-// trimmed when it holds more than 24 GiB or when the last context of the device goes away.
-void* pool_alloc(uint64_t bytes, uint64_t* granted);
-void pool_free(void* p, uint64_t granted);
-void pool_trim(int device);
+// device), which dominated the per-column load time.  Blocks are reused by best fit (within 25 % slack); a pool is
+// trimmed when it holds more than 24 GiB and released with its context.  A block returns to the pool it came from.
+std::shared_ptr<Pool> pool_create();
+void* pool_alloc(uint64_t bytes, uint64_t* granted, std::shared_ptr<Pool>* owner);
+void pool_free(const std::shared_ptr<Pool>& owner, void* p, uint64_t granted);
+void pool_trim(const std::shared_ptr<Pool>& pool);
 
 // device allocation that frees itself
 struct DevBuf {
   void* p = nullptr;
   uint64_t bytes = 0;
+  std::shared_ptr<Pool> owner;   // the pool the block came from (null: plain cudaMalloc, no context was current)
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+  DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes), owner(std::move(o.owner)) { o.p = nullptr; o.bytes = 0; }
   DevBuf& operator=(DevBuf&& o) noexcept {
-    if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; }
+    if (this != &o) { release(); p = o.p; bytes = o.bytes; owner = std::move(o.owner); o.p = nullptr; o.bytes = 0; }
     return *this;
   }
   ~DevBuf() { release(); }
@@ -62,13 +75,14 @@ struct DevBuf {
     release();
     if (n == 0) n = 16;
     uint64_t granted = 0;
-    p = pool_alloc(n, &granted);
+    p = pool_alloc(n, &granted, &owner);
     bytes = granted;
   }
   void release() {
-    if (p) pool_free(p, bytes);
+    if (p) pool_free(owner, p, bytes);
     p = nullptr;
     bytes = 0;
+    owner.reset();
   }
   template <typename T> T* as() const { return (T*) p; }
 };

@@ -16,6 +16,7 @@ struct JitModule {
   std::map<std::string, cudaKernel_t> kernels;
   std::string source;
   float compile_ms = 0;
+  bool from_disk = false;   // the cubin came from the on-disk cache (jit.cc), NVRTC did not run
   ~JitModule();
 };
 

@@ -271,19 +271,26 @@ static void merge_hash(evqgpu_query& q) {
   EVQ_CUDA(cudaGetLastError());
   // 4. all-to-all over NVLink
   comm_all_to_all(ctx, sendbuf.p, send_off.data(), send_bytes.data(), recvbuf.p, recv_off.data(), recv_bytes.data());
-  // 5. owner-side merge into a fresh table
-  const uint64_t cap = next_pow2_(std::max<uint64_t>(1024, recv_total * 2));
+  // 5. owner-side merge into a fresh table.  The merged table has its own status word: a full MERGE table (a probe run
+  // longer than the bound) is grown and refilled from the received records here - it must never be mistaken for a full
+  // scan table, whose remedy (re-running the local scan) would leave the records un-merged.
+  uint64_t cap = std::max(q.merge_cap, next_pow2_(std::max<uint64_t>(1024, recv_total * 2)));
   DevBuf& slots = q.merge_slots;
-  if (slots.bytes < cap * 8 * H.stride) slots.alloc(cap * 8 * H.stride);
+  if (q.merge_status.bytes < 16) q.merge_status.alloc(16);
   EvqHashTable M = H;
-  M.slots = slots.as<u64>();
-  M.cap = cap;
-  k_merge_init<<<(unsigned) ((cap + 255) / 256), 256, 0, ctx->stream>>>(M, mo);
-  EVQ_CUDA(cudaGetLastError());
-  EVQ_CUDA(cudaMemsetAsync(q.counters.as<u64>() + 1, 0, 8, ctx->stream));
-  if (recv_total) {
+  for (;;) {
+    if (slots.bytes < cap * 8 * H.stride) slots.alloc(cap * 8 * H.stride);
+    M.slots = slots.as<u64>();
+    M.cap = cap;
+    k_merge_init<<<(unsigned) ((cap + 255) / 256), 256, 0, ctx->stream>>>(M, mo);
+    EVQ_CUDA(cudaGetLastError());
+    EVQ_CUDA(cudaMemsetAsync(q.counters.as<u64>() + 1, 0, 8, ctx->stream));
+    EVQ_CUDA(cudaMemsetAsync(q.merge_status.p, 0, 16, ctx->stream));
+    ctx->kernel_launches += 1;
+    q.stats.kernel_launches += 1;
+    if (!recv_total) break;
     u64* cnt = q.counters.as<u64>();
-    u32* st = q.status.as<u32>();
+    u32* st = q.merge_status.as<u32>();
     const u64* recs = recvbuf.as<u64>();
     switch (mo.nkeys) {
       case 0: launch_insert<0>(ctx, M, mo, recs, recv_total, cnt, st); break;
@@ -297,9 +304,18 @@ static void merge_hash(evqgpu_query& q) {
       default: launch_insert<8>(ctx, M, mo, recs, recv_total, cnt, st); break;
     }
     EVQ_CUDA(cudaGetLastError());
+    ctx->kernel_launches += 1;
+    q.stats.kernel_launches += 1;
+    u32 mst = 0;
+    EVQ_CUDA(cudaMemcpyAsync(&mst, q.merge_status.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (!(mst & EVQ_ERR_TABLE_FULL)) break;
+    if (cap >= (1ull << 31)) fail(EVQGPU_ERR_NOMEM, "merged group table exceeds 2^31 slots");
+    cap *= 4;
   }
-  ctx->kernel_launches += 4;
-  q.stats.kernel_launches += 4;
+  q.merge_cap = cap;
+  ctx->kernel_launches += 2;
+  q.stats.kernel_launches += 2;
   // results are emitted from the merged table; the local table stays allocated for the next execution
   q.emit.ht = M;
   q.emit.slots = cap;
@@ -323,20 +339,8 @@ void merge_query(evqgpu_query& q) {
     fail(EVQGPU_ERR_ARG, "evqgpu_query_merge: the plan was not created with EVQGPU_QUERY_PARTIAL");
   if (q.string_keys)   // dictionary codes are per context: the ranks' codes for one string differ
     fail(EVQGPU_ERR_UNSUPPORTED, "evqgpu_query_merge: string GROUP BY keys cannot be merged across ranks");
-  // the state layout depends on which columns are optional: all ranks must have arrived at the same one
-  {
-    std::string sig = std::to_string(q.shape.tier) + "/" + std::to_string(q.shape.g1) + "/";
-    for (size_t i = 0; i < q.state_keys.size(); ++i) sig += q.state_keys[i] + "#" + std::to_string(q.state_ops[i]) + ";";
-    if (sig != q.merge_checked_layout) {
-      uint64_t h = 1469598103934665603ull;
-      for (unsigned char ch : sig) h = (h ^ ch) * 1099511628211ull;
-      std::vector<uint64_t> all = comm_all_gather_host(q.ctx, std::vector<uint64_t>{h});
-      for (uint64_t o : all)
-        if (o != h) fail(EVQGPU_ERR_ARG, "evqgpu_query_merge: ranks disagree on the aggregate state layout (partitions differ in "
-                         "which columns are optional, or in the number of groups strategy)");
-      q.merge_checked_layout = sig;
-    }
-  }
+  // (the ranks agreed on the aggregation strategy, the slot assignment and the state layout in evqgpu_query_prepare,
+  // one unconditional collective; nothing here decides per rank whether to enter a collective)
   if (q.shape.tier == 1) merge_dense(q);
   else merge_hash(q);
   q.merged = true;

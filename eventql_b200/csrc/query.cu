@@ -566,11 +566,17 @@ static bool key_dense_capable(const Expr* g) {
 
 // Bounds pre-pass: min/max of every GROUP BY expression over the tables, computed with the scan kernel itself
 // (a single-group aggregate query), so that a handful of groups can be mapped to dense accumulator slots.
-static bool compute_dense_map(evqgpu_query& q, std::vector<evqgpu_table*>& tables, DenseMap& dm) {
+// local_key_bounds fills, per key, {valid, min, max, may be NULL}; false = the keys are not dense-capable at all.
+static const size_t kBW = 4;
+
+// -> 1 bounds known, 0 the key types rule the dense tiers out (a property of the plan), -1 the pre-pass failed HERE
+// (e.g. a key expression divides by zero on this rank's rows)
+static int local_key_bounds(evqgpu_query& q, std::vector<evqgpu_table*>& tables, std::vector<uint64_t>& bounds) {
   const size_t nk = q.group.size();
+  bounds.assign(kBW * nk, 0);
   for (const auto& g : q.group)
-    if (!key_dense_capable(g.get())) return false;
-  // plan: select min(k0), max(k0), count_null(k0)... -> min/max + "has NULL" via a second pair on the tag
+    if (!key_dense_capable(g.get())) return 0;
+  // plan: select min(k0), max(k0), ... ("has NULL" follows from the nullability of the key's columns)
   std::vector<std::vector<evqgpu_insn>> codes;
   std::vector<evqgpu_expr> sel;
   std::vector<const char*> names;
@@ -613,7 +619,6 @@ static bool compute_dense_map(evqgpu_query& q, std::vector<evqgpu_table*>& table
       codes.push_back(std::move(code));
     }
   }
-  // count of rows (to detect NULL keys we compare "seen" with rows: a tagged bare column skips NULLs in min/max)
   for (auto& c : codes) sel.push_back({c.data(), (uint32_t) c.size(), nullptr, 0});
   evqgpu_query_desc d;
   memset(&d, 0, sizeof(d));
@@ -624,72 +629,75 @@ static bool compute_dense_map(evqgpu_query& q, std::vector<evqgpu_table*>& table
   d.num_select = (uint32_t) sel.size();
   d.select = sel.data();
   evqgpu_query* bq = nullptr;
-  if (evqgpu_query_create(q.ctx, &d, &bq) != EVQGPU_OK) return false;
+  if (evqgpu_query_create(q.ctx, &d, &bq) != EVQGPU_OK) return -1;
   std::unique_ptr<evqgpu_query, void (*)(evqgpu_query*)> guard(bq, evqgpu_query_destroy);
   bq->col_is_string = q.col_is_string;   // the re-serialised key expressions already read string columns as dictionary codes
-  if (evqgpu_query_execute(bq, tables.data(), (uint32_t) tables.size()) != EVQGPU_OK) return false;
+  if (evqgpu_query_execute(bq, tables.data(), (uint32_t) tables.size()) != EVQGPU_OK) return -1;
   q.stats.kernel_launches += bq->stats.kernel_launches;
   q.jit_ms_total += bq->jit_ms_total;
   uint64_t nrows = 0;
   evqgpu_query_num_rows(bq, &nrows);
-  // local bounds per key: {valid, min, max, may be NULL}
   std::vector<bool> nullable_cols(q.input_columns.size(), false);
   for (auto* t : tables)
     for (size_t i = 0; i < q.input_columns.size(); ++i) {
       const int ci = t->find(q.input_columns[i].c_str());
       if (ci >= 0 && t->cols[ci].meta.dlevel_max > 0) nullable_cols[i] = true;
     }
-  const size_t BW = 4;
-  std::vector<uint64_t> bounds(BW * nk, 0);
   // only a bare column reference keeps its NULL tag as a key: one extra slot index then
-  for (size_t i = 0; i < nk; ++i) bounds[BW * i + 3] = key_may_be_null(q.group[i].get(), nullable_cols) ? 1 : 0;
-  std::vector<bool> is_signed(nk, false);
-  for (size_t i = 0; i < nk; ++i) is_signed[i] = q.group[i]->type != EVQ_UINT64;   // int64 / bool / timestamp64 went through int64
+  for (size_t i = 0; i < nk; ++i) bounds[kBW * i + 3] = key_may_be_null(q.group[i].get(), nullable_cols) ? 1 : 0;
   if (nrows != 0) {
     std::vector<std::vector<uint8_t>> bufs(sel.size(), std::vector<uint8_t>(9));
     std::vector<void*> ptrs;
     for (auto& b : bufs) ptrs.push_back(b.data());
     uint64_t got = 0;
-    if (evqgpu_query_fetch(bq, 0, 1, ptrs.data(), &got) != EVQGPU_OK || got != 1) return false;
+    if (evqgpu_query_fetch(bq, 0, 1, ptrs.data(), &got) != EVQGPU_OK || got != 1) return -1;
     for (size_t i = 0; i < nk; ++i) {
-      bounds[BW * i] = 1;
-      memcpy(&bounds[BW * i + 1], bufs[2 * i].data(), 8);
-      memcpy(&bounds[BW * i + 2], bufs[2 * i + 1].data(), 8);
+      bounds[kBW * i] = 1;
+      memcpy(&bounds[kBW * i + 1], bufs[2 * i].data(), 8);
+      memcpy(&bounds[kBW * i + 2], bufs[2 * i + 1].data(), 8);
     }
   }
-  // every rank must arrive at the same slot assignment: combine the bounds of all ranks (SURVEY 8e "canonical slot assignment")
-  if (q.ctx->nccl_comm && q.ctx->nranks > 1) {
-    std::vector<uint64_t> all = comm_all_gather_host(q.ctx, bounds);
-    for (size_t i = 0; i < nk; ++i) {
-      uint64_t valid = 0, mn = 0, mx = 0, may_null = 0;
-      for (int r = 0; r < q.ctx->nranks; ++r) {
-        const uint64_t* b = &all[(size_t) r * bounds.size() + BW * i];
-        may_null |= b[3];
-        if (!b[0]) continue;
-        if (!valid) { valid = 1; mn = b[1]; mx = b[2]; continue; }
-        if (is_signed[i]) {
-          if ((int64_t) b[1] < (int64_t) mn) mn = b[1];
-          if ((int64_t) b[2] > (int64_t) mx) mx = b[2];
-        } else {
-          if (b[1] < mn) mn = b[1];
-          if (b[2] > mx) mx = b[2];
-        }
-      }
-      bounds[BW * i] = valid; bounds[BW * i + 1] = mn; bounds[BW * i + 2] = mx; bounds[BW * i + 3] = may_null;
-    }
-  }
+  return 1;
+}
+
+// the bounds of several ranks -> the bounds of the whole job (SURVEY 8e "canonical slot assignment")
+static void combine_key_bounds(const evqgpu_query& q, const std::vector<std::vector<uint64_t>>& per_rank, std::vector<uint64_t>& bounds) {
+  const size_t nk = q.group.size();
+  bounds.assign(kBW * nk, 0);
   for (size_t i = 0; i < nk; ++i) {
-    if (!bounds[BW * i]) {   // no row anywhere: any mapping works
+    const bool is_signed = q.group[i]->type != EVQ_UINT64;   // int64 / bool / timestamp64 went through int64
+    uint64_t valid = 0, mn = 0, mx = 0, may_null = 0;
+    for (const auto& rb : per_rank) {
+      const uint64_t* b = &rb[kBW * i];
+      may_null |= b[3];
+      if (!b[0]) continue;
+      if (!valid) { valid = 1; mn = b[1]; mx = b[2]; continue; }
+      if (is_signed) {
+        if ((int64_t) b[1] < (int64_t) mn) mn = b[1];
+        if ((int64_t) b[2] > (int64_t) mx) mx = b[2];
+      } else {
+        if (b[1] < mn) mn = b[1];
+        if (b[2] > mx) mx = b[2];
+      }
+    }
+    bounds[kBW * i] = valid; bounds[kBW * i + 1] = mn; bounds[kBW * i + 2] = mx; bounds[kBW * i + 3] = may_null;
+  }
+}
+
+static bool dense_map_from_bounds(const evqgpu_query& q, const std::vector<uint64_t>& bounds, DenseMap& dm) {
+  const size_t nk = q.group.size();
+  for (size_t i = 0; i < nk; ++i) {
+    if (!bounds[kBW * i]) {   // no row anywhere: any mapping works
       dm.key_min[i] = 0; dm.key_range[i] = 2; dm.key_null_idx[i] = 1;
       continue;
     }
-    const uint64_t mn = bounds[BW * i + 1], mx = bounds[BW * i + 2];
+    const uint64_t mn = bounds[kBW * i + 1], mx = bounds[kBW * i + 2];
     // signed and unsigned keys alike: (key - min) as an unsigned difference
     const uint64_t span = mx - mn;
     if (span > (1ull << 24) - 2) return false;
     dm.key_min[i] = mn;
     // one extra index for NULL keys, only when the expression can carry a NULL tag at all
-    const bool may_null = bounds[BW * i + 3] != 0;
+    const bool may_null = bounds[kBW * i + 3] != 0;
     dm.key_range[i] = span + (may_null ? 2 : 1);
     dm.key_null_idx[i] = may_null ? span + 1 : ~0ull;
   }
@@ -701,6 +709,16 @@ static bool compute_dense_map(evqgpu_query& q, std::vector<evqgpu_table*>& table
   }
   dm.slots = slots;
   return true;
+}
+
+static bool is_multi_rank_partial(const evqgpu_query& q) {
+  return (q.flags & EVQGPU_QUERY_PARTIAL) && (q.flags & EVQGPU_QUERY_GROUPBY) && q.ctx->nccl_comm && q.ctx->nranks > 1;
+}
+
+static uint64_t fnv1a(const std::string& s) {
+  uint64_t h = 1469598103934665603ull;
+  for (unsigned char ch : s) h = (h ^ ch) * 1099511628211ull;
+  return h;
 }
 
 // GroupByExpression::nextBatch (groupby.cc:187-220) for all groups at once: the emit kernel evaluates every select
@@ -730,8 +748,88 @@ void emit_results(evqgpu_query& q) {
   q.emitted = true;
 }
 
+static std::string layout_signature(const evqgpu_query& q) {
+  std::string sig;
+  for (size_t i = 0; i < q.state_keys.size(); ++i) sig += q.state_keys[i] + "#" + std::to_string(q.state_ops[i]) + ";";
+  return sig;
+}
+
+// evqgpu_query_prepare: everything the ranks of a multi-rank job must agree on BEFORE the scan, in ONE unconditional
+// collective (an all-gather every rank enters no matter what happened locally):
+//   * did anything fail locally (binding the tables, the key-bounds pre-pass)?  -> the call fails on every rank
+//   * the aggregate state layout (depends on which columns are optional in the rank's partitions)
+//   * the key bounds -> the canonical key -> slot assignment of the dense tiers
+// evqgpu_query_enqueue / _merge then run without any data-dependent decision about entering a collective.
+void prepare_query(evqgpu_query& q, std::vector<evqgpu_table*>& tv) {
+  if (!is_multi_rank_partial(q)) return;   // nothing to agree on
+  evqgpu_ctx* ctx = q.ctx;
+  const size_t nk = q.group.size();
+  std::vector<uint64_t> uids;
+  for (auto* t : tv) uids.push_back(t ? t->uid : 0);
+  uint64_t failed = 0, capable = 0, layout = 0;
+  std::vector<uint64_t> bounds(kBW * nk, 0);
+  std::string msg;
+  try {
+    std::vector<TablePlan> plans;
+    for (auto* t : tv) {
+      if (!t) fail(EVQGPU_ERR_ARG, "null table");
+      if (t->ctx != q.ctx) fail(EVQGPU_ERR_ARG, "table belongs to another context");
+      TablePlan p;
+      p.table = t;
+      p.binding = bind_table(q, t);
+      plans.push_back(std::move(p));
+    }
+    if (plans.empty()) fail(EVQGPU_ERR_ARG, "evqgpu_query_prepare: no tables");
+    KernelShape s = shape_of_plans(q, plans);
+    layout_states(q, s);
+    layout = fnv1a(layout_signature(q));
+    if (nk > 0 && q.expected_groups <= (1ull << 24)) {
+      const int rc = local_key_bounds(q, tv, bounds);
+      if (rc < 0) fail(EVQGPU_ERR_RUNTIME, "key bounds pre-pass failed: %s", last_error());
+      capable = (uint64_t) rc;
+    }
+  } catch (const Error& e) {
+    failed = 1;
+    msg = e.msg;
+  }
+  std::vector<uint64_t> mine = {failed, capable, layout};
+  mine.insert(mine.end(), bounds.begin(), bounds.end());
+  const std::vector<uint64_t> all = comm_all_gather_host(ctx, mine);   // every rank, every time
+  const size_t W = mine.size();
+  for (int r = 0; r < ctx->nranks; ++r)
+    if (all[(size_t) r * W])
+      fail(EVQGPU_ERR_RUNTIME, "evqgpu_query_prepare: rank %d failed%s%s", r, r == ctx->rank ? ": " : "", r == ctx->rank ? msg.c_str() : "");
+  for (int r = 0; r < ctx->nranks; ++r)
+    if (all[(size_t) r * W + 2] != layout)
+      fail(EVQGPU_ERR_ARG, "evqgpu_query_prepare: ranks disagree on the aggregate state layout (partitions differ in which columns are optional)");
+  bool dense = nk > 0;
+  std::vector<std::vector<uint64_t>> per_rank;
+  for (int r = 0; r < ctx->nranks; ++r) {
+    dense = dense && all[(size_t) r * W + 1] == 1;
+    per_rank.emplace_back(all.begin() + (size_t) r * W + 3, all.begin() + (size_t) (r + 1) * W);
+  }
+  DenseMap dm;
+  if (dense) {
+    combine_key_bounds(q, per_rank, bounds);
+    dense = dense_map_from_bounds(q, bounds, dm);
+  }
+  q.dense_cache_valid = true;
+  q.dense_cache_ok = dense;
+  q.dense_cache_map = dm;
+  q.dense_cache_uids = uids;
+  q.prepared = true;
+  q.prepared_uids = uids;
+}
+
 static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std::vector<evqgpu_table*>& tables, bool sync) {
   evqgpu_ctx* ctx = q.ctx;
+  if (is_multi_rank_partial(q)) {
+    std::vector<uint64_t> uids;
+    for (auto* t : tables) uids.push_back(t->uid);
+    if (!q.prepared || uids != q.prepared_uids)
+      fail(EVQGPU_ERR_ARG, "multi-rank job: call evqgpu_query_prepare (on every rank) for this set of tables before "
+                           "evqgpu_query_enqueue; evqgpu_query_execute does it implicitly");
+  }
   KernelShape s = shape_of_plans(q, plans);
   layout_states(q, s);
   uint64_t total_rows = 0;
@@ -748,11 +846,14 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
     for (auto* t : tables) uids.push_back(t->uid);
     if (q.dense_cache_valid && uids == q.dense_cache_uids) {
       dense = q.dense_cache_ok;
-      dm = q.dense;
+      dm = q.dense_cache_map;
     } else if (q.expected_groups <= (1ull << 24)) {   // (0 = unknown)
-      dense = compute_dense_map(q, tables, dm);
+      // (a multi-rank partial plan never gets here: evqgpu_query_prepare agreed on the map, see prepare_query)
+      std::vector<uint64_t> bounds;
+      dense = local_key_bounds(q, tables, bounds) == 1 && dense_map_from_bounds(q, bounds, dm);
       q.dense_cache_valid = true;
       q.dense_cache_ok = dense;
+      q.dense_cache_map = dm;
       q.dense_cache_uids = uids;
     }
     bool dense_global = false;
@@ -804,6 +905,7 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
       q.kernel_source = generate_source(q, s);
       q.module = jit_compile(ctx, q.kernel_source, {"evq_scan", "evq_init", "evq_emit"}, &ms);
       q.module_sig = sig;
+      if (ms > 0 && q.module->from_disk) q.stats.jit_disk_hits++;
     }
   }
   q.jit_ms_total += ms;
@@ -994,7 +1096,9 @@ void finish_query(evqgpu_query& q) {
       std::vector<evqgpu_table*> tables = q.tables;
       const uint64_t hint = q.ht_cap;
       (void) hint;
-      int rc = evqgpu_query_execute(&q, tables.data(), (uint32_t) tables.size());
+      // (enqueue + finish, not execute: the retry is local to this rank and must not enter a collective)
+      int rc = evqgpu_query_enqueue(&q, tables.data(), (uint32_t) tables.size());
+      if (rc == EVQGPU_OK) rc = evqgpu_query_finish(&q);
       if (rc != EVQGPU_OK) throw Error{rc, last_error()};
       return;
     }
@@ -1047,8 +1151,20 @@ int evqgpu_query_finish(evqgpu_query* q) {
   });
 }
 
+int evqgpu_query_prepare(evqgpu_query* q, evqgpu_table* const* tables, uint32_t ntables) {
+  return guarded([&] {
+    if (!q || (!tables && ntables)) fail(EVQGPU_ERR_ARG, "evqgpu_query_prepare: null argument");
+    use_device(q->ctx);
+    std::vector<evqgpu_table*> tv(tables, tables + ntables);
+    prepare_query(*q, tv);
+  });
+}
+
 int evqgpu_query_execute(evqgpu_query* q, evqgpu_table* const* tables, uint32_t ntables) {
-  int rc = evqgpu_query_enqueue(q, tables, ntables);
+  // in a multi-rank job execute is collective: the ranks agree on slot assignment and state layout first
+  int rc = evqgpu_query_prepare(q, tables, ntables);
+  if (rc != EVQGPU_OK) return rc;
+  rc = evqgpu_query_enqueue(q, tables, ntables);
   if (rc != EVQGPU_OK) return rc;
   return evqgpu_query_finish(q);
 }

@@ -148,7 +148,8 @@ struct evqgpu_query {
   u64* dense_base = nullptr;         // dense_state, offset by one word where that makes the first-row pairs 16-byte aligned
 
   // device state, reused across executions
-  evq::DevBuf merge_recv, merge_send, merge_slots, merge_counts;
+  evq::DevBuf merge_recv, merge_send, merge_slots, merge_counts, merge_status;
+  uint64_t merge_cap = 0;           // capacity the merged table last needed (kept across executions)
   evq::DevBuf dense_state, ht_slots, status, counters, out_count, tile_counts, tile_base;
   std::vector<evq::DevBuf> out_cols;
   evq::DevBuf out_sha, out_state;   // EVQGPU_QUERY_WIRE (PartialGroupByExpression rows)
@@ -160,6 +161,9 @@ struct evqgpu_query {
   evq::KernelShape shape;
   evq::DenseMap dense;
   bool dense_cache_valid = false, dense_cache_ok = false;
+  evq::DenseMap dense_cache_map;            // (q.dense is the map of the LAST execution, which may have fallen back to the hash tier)
+  bool prepared = false;                    // multi-rank: evqgpu_query_prepare agreed on slot assignment + layout ...
+  std::vector<uint64_t> prepared_uids;      // ... for this set of tables
   std::vector<uint64_t> dense_cache_uids;   // bounds of the GROUP BY expressions are cached per set of (immutable) tables
   std::shared_ptr<evq::JitModule> module;
   std::string module_sig;   // what `module` was specialised for (group-by plans)
@@ -186,6 +190,7 @@ void layout_states(evqgpu_query& q, const KernelShape& shape);
 void layout_narrow(evqgpu_query& q, const KernelShape& shape);   // after tier / g1 are known
 int gen_chunks(const KernelShape& shape);
 // query.cu
+void prepare_query(evqgpu_query& q, std::vector<evqgpu_table*>& tables);
 void emit_results(evqgpu_query& q);
 void finish_query(evqgpu_query& q);
 // merge.cu

@@ -35,14 +35,19 @@ void fail(int status, const char* fmt, ...) {
 
 namespace evq {
 
-namespace {
 struct Pool {
+  std::mutex mu;
   std::multimap<uint64_t, void*> free_blocks;   // size -> block
   uint64_t held = 0;
+  int device = 0;
+  ~Pool() {
+    for (auto& b : free_blocks) cudaFree(b.second);
+  }
 };
-std::mutex g_pool_mu;
-std::map<int, Pool> g_pools;
+
+namespace {
 const uint64_t kPoolLimit = 24ull << 30;
+thread_local const evqgpu_ctx* g_current_ctx = nullptr;
 
 uint64_t pool_round(uint64_t n) {
   if (n <= (1u << 20)) return (n + 511) & ~511ull;
@@ -50,27 +55,34 @@ uint64_t pool_round(uint64_t n) {
 }
 }  // namespace
 
-void* pool_alloc(uint64_t bytes, uint64_t* granted) {
-  int dev = 0;
-  cudaGetDevice(&dev);
+void set_current_ctx(const evqgpu_ctx* ctx) { g_current_ctx = ctx; }
+
+std::shared_ptr<Pool> pool_create() {
+  auto p = std::make_shared<Pool>();
+  cudaGetDevice(&p->device);
+  return p;
+}
+
+void* pool_alloc(uint64_t bytes, uint64_t* granted, std::shared_ptr<Pool>* owner) {
   const uint64_t want = pool_round(bytes);
-  {
-    std::lock_guard<std::mutex> lk(g_pool_mu);
-    Pool& P = g_pools[dev];
-    auto it = P.free_blocks.lower_bound(want);
-    if (it != P.free_blocks.end() && it->first <= want + want / 4) {
+  std::shared_ptr<Pool> P = g_current_ctx ? g_current_ctx->pool : nullptr;
+  *owner = P;
+  if (P) {
+    std::lock_guard<std::mutex> lk(P->mu);
+    auto it = P->free_blocks.lower_bound(want);
+    if (it != P->free_blocks.end() && it->first <= want + want / 4) {
       void* p = it->second;
       *granted = it->first;
-      P.held -= it->first;
-      P.free_blocks.erase(it);
+      P->held -= it->first;
+      P->free_blocks.erase(it);
       return p;
     }
   }
   void* p = nullptr;
   cudaError_t e = cudaMalloc(&p, want);
-  if (e != cudaSuccess) {   // give the cached blocks back and try once more
+  if (e != cudaSuccess && P) {   // give the cached blocks back and try once more
     cudaGetLastError();
-    pool_trim(dev);
+    pool_trim(P);
     e = cudaMalloc(&p, want);
   }
   if (e != cudaSuccess) {
@@ -81,29 +93,30 @@ void* pool_alloc(uint64_t bytes, uint64_t* granted) {
   return p;
 }
 
-void pool_free(void* p, uint64_t granted) {
-  int dev = 0;
-  cudaGetDevice(&dev);
+void pool_free(const std::shared_ptr<Pool>& owner, void* p, uint64_t granted) {
+  if (!owner) {
+    cudaFree(p);
+    return;
+  }
   bool trim = false;
   {
-    std::lock_guard<std::mutex> lk(g_pool_mu);
-    Pool& P = g_pools[dev];
-    P.free_blocks.emplace(granted, p);
-    P.held += granted;
-    trim = P.held > kPoolLimit;
+    std::lock_guard<std::mutex> lk(owner->mu);
+    owner->free_blocks.emplace(granted, p);
+    owner->held += granted;
+    trim = owner->held > kPoolLimit;
   }
-  if (trim) pool_trim(dev);
+  if (trim) pool_trim(owner);
 }
 
-void pool_trim(int device) {
+void pool_trim(const std::shared_ptr<Pool>& pool) {
+  if (!pool) return;
   std::multimap<uint64_t, void*> blocks;
   {
-    std::lock_guard<std::mutex> lk(g_pool_mu);
-    Pool& P = g_pools[device];
-    blocks.swap(P.free_blocks);
-    P.held = 0;
+    std::lock_guard<std::mutex> lk(pool->mu);
+    blocks.swap(pool->free_blocks);
+    pool->held = 0;
   }
-  for (auto& b : blocks) cudaFree(b.second);
+  for (auto& b : blocks) cudaFree(b.second);   // (cudaFree synchronises the device: nothing still reads the blocks)
 }
 
 }  // namespace evq

@@ -1,8 +1,8 @@
 // gpu_binding.h - the GPU path bound to the reference's REAL classes.
 //
-// This header is compiled against the reference's own headers (-I /root/reference/src, as oracle/build_ref.py sets the
-// include paths up); it is what a maintainer of the reference adds to the tree.  Nothing here is a
-// restatement: every base class is the reference's.
+// This header is compiled against the reference's own headers (-I /root/reference/src and the include paths of its build,
+// tests/refbind/build_refsql.py); it is what a maintainer of the reference adds to the tree.  Nothing
+// here is a restatement: every base class is the reference's.
 //
 //   evql_b200::refbind::GpuScheduler            : csql::DefaultScheduler      sql/scheduler.h:84-171 - overrides the virtual
 //                                                 protected buildGroupByExpression / buildOrderByExpression / buildLimit

@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define EVQGPU_ABI_VERSION 3
+#define EVQGPU_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define EVQGPU_API __attribute__((visibility("default")))
@@ -342,6 +342,17 @@ EVQGPU_API uint32_t evqgpu_query_column_type(const evqgpu_query* q, uint32_t idx
  * the context stream; the call returns once the result row count is known. */
 EVQGPU_API int evqgpu_query_execute(evqgpu_query* q, evqgpu_table* const* tables, uint32_t ntables);
 
+/* Multi-rank jobs (evqgpu_comm_init with nranks > 1) and EVQGPU_QUERY_PARTIAL aggregate plans: a COLLECTIVE call.  Every
+ * rank calls it - in the same order relative to its other collective calls (prepare, merge) - whenever the set of tables it
+ * is about to scan changes.  In one all-gather that every rank enters no matter what happened locally, the ranks agree
+ * on what must be identical everywhere before the scan: the aggregation strategy, the key -> slot assignment of the dense
+ * tiers (from the key bounds of all ranks) and the aggregate state layout.  A rank whose local part failed
+ * (a missing column, a key expression that divides by zero) still takes part, and the call then fails on EVERY rank.
+ * evqgpu_query_execute calls it implicitly on every execution - so execute is itself collective in a multi-rank job -
+ * while evqgpu_query_enqueue and evqgpu_query_merge never decide per rank whether to enter a collective: enqueue requires a
+ * preceding prepare for exactly these tables and fails with EVQGPU_ERR_ARG otherwise.  Everywhere else: a no-op. */
+EVQGPU_API int evqgpu_query_prepare(evqgpu_query* q, evqgpu_table* const* tables, uint32_t ntables);
+
 /* Same, but only enqueues the device work (no host synchronisation); finish with
  * evqgpu_query_finish.  Lets a caller time the device portion with CUDA events on
  * evqgpu_ctx_stream(). */
@@ -451,11 +462,12 @@ typedef struct evqgpu_query_stats {
   uint32_t kernel_launches;      /* device kernels launched by the last execute */
   uint32_t strategy;             /* 0 scan-only, 1 register/shared-memory low-cardinality, 2 global hash table,
                                     3 direct-addressed group array in global memory (key tuples spanning a small box) */
-  float jit_ms;                  /* NVRTC time spent by evqgpu_query_create (0 when cached) */
+  float jit_ms;                  /* time spent making the specialised kernel loadable in the last execute: NVRTC, or reading the
+                                    cubin from the on-disk cache ($EVQGPU_CACHE_DIR, default ~/.cache/evqgpu); 0 = already loaded */
   float scan_ms;                 /* summed device time of the scan kernel launches since the last finish
                                     (only with evqgpu_ctx_set_profiling) */
   uint32_t scan_launches;        /* number of scan kernel launches scan_ms covers */
-  uint32_t reserved;
+  uint32_t jit_disk_hits;        /* kernels of the last execute that came from the on-disk cubin cache instead of NVRTC */
 } evqgpu_query_stats;
 EVQGPU_API int evqgpu_query_get_stats(evqgpu_query* q, evqgpu_query_stats* out);
 

@@ -42,7 +42,57 @@ def main():
     cases.append(("minmax_float_dense", spec, P.QueryPlan(names, [c["bo"], P.call("count", P.lit(1)), P.call("sum", c["f"]), P.call("min", c["f"]),
                                                                  P.call("max", c["a"]), P.call("mean", c["big"]), P.call("sum", c["big"])],
                                                           where=c["b"] >= 0, group=[c["bo"]])))
+    # first-row items (non-aggregate, not a function of the key): the pair with the smallest rank-major row ordinal wins the merge
+    spec = T.mixed_spec()
+    c, names = T.cols_of(spec)
+    cases.append(("first_row_dense", spec, P.QueryPlan(names, [c["b"] % 3, P.call("count", P.lit(1)), c["a"], c["d"]], where=c["b"] >= 0,
+                                                       group=[c["b"] % 3])))
+    cases.append(("first_row_hash", spec, P.QueryPlan(names, [c["c"] % 5003, P.call("count", P.lit(1)), c["a"], c["k"]], where=c["b"] >= 0,
+                                                      group=[c["c"] % 5003], expected_groups=1 << 25)))
     failures = []
+
+    # ---- collectives are never entered on a per-rank decision (evqgpu_query_prepare)
+    spec = T.mixed_spec()
+    c, names = T.cols_of(spec)
+    # (1) enqueue without a prepare for these tables fails loudly instead of entering a collective alone
+    tbl = ctx.synthesize(20_000, [s for s in spec if not (s["encoding"] == P.ENC_UINT32_BITPACKED and s.get("null_every"))], row_offset=rank * 20_000)
+    q = ctx.query(P.QueryPlan(names, [c["b"] % 3, P.call("count", P.lit(1))], where=c["b"] >= 0, group=[c["b"] % 3],
+                              flags=P.QUERY_GROUPBY | P.QUERY_PARTIAL))
+    try:
+        q.enqueue([tbl])
+        failures.append("enqueue without prepare did not fail")
+    except capi.EvqError as e:
+        if "evqgpu_query_prepare" not in e.message:
+            failures.append("enqueue without prepare: " + e.message)
+    q.prepare([tbl])
+    q.enqueue([tbl])
+    q.merge()
+    if sum(r[1] for r in q.rows()) != 20_000 * world:
+        failures.append("prepare + enqueue + merge: wrong row count")
+    q.close()
+    tbl.close()
+    # (2) a key expression that divides by zero on ONE rank only: that rank still takes part in the agreement and the
+    # execution fails on EVERY rank (nobody is left waiting in a collective)
+    bad = [dict(s) for s in spec if not (s["encoding"] == P.ENC_UINT32_BITPACKED and s.get("null_every"))]
+    for s in bad:
+        if s["name"] == "b":
+            s["lo"] = 0 if rank == 1 % world else 1
+    tbl = ctx.synthesize(20_000, bad, row_offset=rank * 20_000)
+    q = ctx.query(P.QueryPlan(names, [P.lit(1000) / c["b"], P.call("count", P.lit(1))], where=c["d"] >= 0, group=[P.lit(1000) / c["b"]],
+                              flags=P.QUERY_GROUPBY | P.QUERY_PARTIAL))
+    try:
+        q.execute([tbl])
+        failures.append("rank %d: a failure on rank %d went unnoticed" % (rank, 1 % world))
+    except capi.EvqError as e:
+        if "rank %d failed" % (1 % world) not in e.message:
+            failures.append("rank %d: unexpected message %r" % (rank, e.message))
+    q.close()
+    tbl.close()
+    nf = torch.tensor([len(failures)], device="cuda")
+    dist.all_reduce(nf)
+    if rank == 0:
+        print("collective agreement checks: %s" % ("ok" if int(nf.item()) == 0 else failures), flush=True)
+
     for name, spec, plan in cases:
         ts = name == "timeseries"
         mine = sharding.assign_partitions(nparts, rank, world)
@@ -79,7 +129,7 @@ def main():
         for t in tables:
             t.close()
     flag = torch.tensor([len(failures)], device="cuda")
-    dist.broadcast(flag, 0)
+    dist.all_reduce(flag)
     ctx.close()
     dist.destroy_process_group()
     sys.exit(1 if int(flag.item()) else 0)

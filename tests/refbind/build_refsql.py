@@ -1,4 +1,5 @@
-"""Compile the reference binding (gpu_binding.{h,cc}) against the reference's REAL headers and link the test runner
+"""TEST TARGET.  Compile the reference binding (eventql_b200/host/refbind/gpu_binding.{h,cc}) against the reference's REAL
+headers and link the test runner
 eventql_b200/evqgpu_refsql = reference Runtime (parser, planner, ResultCursor: oracle/_ref/build/libevqlref.a) +
 GpuScheduler + GpuCSTableScanProvider + libevqgpu.so.
 
@@ -6,15 +7,15 @@ Only possible where the reference tree and its compiled objects exist (this cont
 oracle/_ref/build from oracle/build_ref.py).  The linked binary is git-ignored but travels to the GPU box with the
 snapshot, like libevqgpu.so.  No reference source is copied; include paths point into /root/reference.
 
-Usage: python -m eventql_b200.host.refbind.build [--ref /root/reference]
+Usage: python -m tests.refbind.build_refsql [--ref /root/reference]
 """
 import os
 import subprocess
 import sys
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-PKG = os.path.dirname(os.path.dirname(HERE))
-ROOT = os.path.dirname(PKG)
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+PKG = os.path.join(ROOT, "eventql_b200")
+HERE = os.path.join(PKG, "host", "refbind")   # the binding sources (product); this script and the runner's main are test code
 REFBUILD = os.path.join(ROOT, "oracle", "_ref", "build")
 OUT = os.path.join(PKG, "evqgpu_refsql")
 

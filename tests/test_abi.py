@@ -139,10 +139,17 @@ def test_unsupported_plans_fail_loudly(native_lib):
     with pytest.raises(capi.EvqError) as ei:
         capi.debug_generate(plan, _cols(spec), compile=False)
     assert ei.value.status == 1
-    # scalar select item that is not a function of the group key (reference: first row wins, non-deterministic)
+
+
+def test_first_row_select_item_compiles_with_one_128_bit_cas(native_lib):
+    """A scalar select item that is not a function of the group key takes the value of the group's first row
+    (groupby.cc:161-172): (row ordinal | tag, value) pairs updated with atom.cas.b128, in the dense and the hash tier."""
+    spec = T.lineitem_spec()
+    c, names = T.cols_of(spec)
     plan = P.QueryPlan(names, [c["price"], P.call("count", P.lit(1))], group=[c["flag"]])
-    with pytest.raises(capi.EvqError):
-        capi.debug_generate(plan, _cols(spec), compile=False)
+    for tier, slots in ((1, 2), (2, 0)):
+        src, cubin_bytes = capi.debug_generate(plan, _cols(spec), tier=tier, dense_slots=slots, compile=True)
+        assert "evq_first_update(EVQ_GPTR(" in src and "atom.global.relaxed.gpu.cas.b128" in src and cubin_bytes > 1000
 
 
 def test_context_without_device_raises(native_lib):

@@ -8,7 +8,7 @@ TEXT; what comes out of ResultCursor must be the rows the unmodified reference e
 (tests/golden/ref_*.json).  Nothing in the plan is built by hand: implicit to_<type> wrapping, folded constants,
 first-reference column order and hidden ORDER BY columns are whatever the reference's planner produces.
 
-The binary is built where the reference tree exists (eventql_b200/host/refbind/build.py, from __graft_entry__.build())
+The binary is built where the reference tree exists (tests/refbind/build_refsql.py, from __graft_entry__.build())
 and travels to the GPU box; the CPU test only checks that it links, loads libevqgpu.so and refuses to run without a
 device.
 """
