@@ -1069,8 +1069,9 @@ void finish_query(evqgpu_query& q) {
   EVQ_CUDA(cudaMemcpyAsync(&host.out_count, q.out_count.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
   EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
   q.pending = false;
-  q.stats.scan_ms = 0;
-  q.stats.scan_launches = (uint32_t) q.prof_events.size();
+  // (accumulated over the finishes of one execution: the hash merge finishes the scan before it ships the table and
+  // once more after the merged groups are emitted)
+  q.stats.scan_launches += (uint32_t) q.prof_events.size();
   for (auto& e : q.prof_events) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, e.first, e.second) == cudaSuccess) q.stats.scan_ms += ms;
