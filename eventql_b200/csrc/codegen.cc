@@ -969,12 +969,13 @@ static std::string gen_group_kernels(const evqgpu_query& q, const KernelShape& s
   os << "struct EvqEmitParams { const u64* dense_state; EvqHashTable ht; u64 key_min[EVQ_MAX_KEYS]; u64 key_stride[EVQ_MAX_KEYS]; "
         "u64 key_null_idx[EVQ_MAX_KEYS]; u64 key_range[EVQ_MAX_KEYS]; u64 slots; u64* out_count; u64 out_capacity; "
         "u8* out_cols[EVQ_MAX_STREAMS]; u8* out_sha; u64* out_state; };\n";
-  os << "extern \"C\" __global__ void evq_emit(const __grid_constant__ EvqEmitParams E) {\n";
-  os << "  const u64 slot = (u64) blockIdx.x * blockDim.x + threadIdx.x;\n  if (slot >= E.slots) return;\n";
+  // one group -> one result row.  `dstate`: the dense state array the group's words are read from (the tail kernel passes
+  // the merged copy in shared memory); unused by the hash tier, which reads its slot
+  os << "__device__ __forceinline__ void evq_emit_group(const EvqEmitParams& E, const u64 slot, const u64* dstate) {\n";
   os << "  u64 st[" << std::max(1, nstate) << "];\n  u64 key[" << std::max(1, nk) << "];\n  u32 ktag[" << std::max(1, nk) << "];\n";
   os << "  u32 err = 0;\n";
   if (shape.tier == 1 || shape.dense_global) {
-    for (int s = 0; s < nstate; ++s) os << "  st[" << s << "] = E.dense_state[slot * " << nstate << " + " << s << "];\n";
+    for (int s = 0; s < nstate; ++s) os << "  st[" << s << "] = dstate[slot * " << nstate << " + " << s << "];\n";
     os << "  if (st[0] == 0) return;\n";   // no row reached this group: it does not exist
     for (int i = 0; i < nk; ++i) {
       os << "  {\n    const u64 idx = (slot / E.key_stride[" << i << "]) % E.key_range[" << i << "];\n";
@@ -1050,6 +1051,74 @@ static std::string gen_group_kernels(const evqgpu_query& q, const KernelShape& s
     for (int s = 0; s < nstate; ++s) os << "  E.out_state[out_row * " << nstate << " + " << s << "] = st[" << s << "];\n";
   }
   os << "  (void) err;\n}\n";
+  os << "extern \"C\" __global__ void evq_emit(const __grid_constant__ EvqEmitParams E) {\n";
+  os << "  const u64 slot = (u64) blockIdx.x * blockDim.x + threadIdx.x;\n  if (slot >= E.slots) return;\n";
+  os << "  evq_emit_group(E, slot, E.dense_state);\n}\n";
+
+  // ---- the tail of a dense-tier execution: ONE kernel (one CTA) behind the scan launches that
+  //   (1) multi-rank: pushes this rank's state words into every peer's exchange buffer over NVLink (P2P stores), raises its
+  //       flag there, waits for the peers' flags and combines all ranks' words in rank order (GroupByMergeExpression,
+  //       groupby.cc:553-615; deterministic also for double sums) - the all-gather, the merge kernel and the emit kernel in one
+  //   (2) emits the result rows (GroupByExpression::nextBatch)
+  //   (3) publishes status / counters / row count in the query's result block and re-arms the state (identities, zeroed
+  //       counters) for the next execution, which then needs no init kernel and no memsets
+  if (shape.tier == 1 && !shape.dense_global) {
+    const int slots = shape.g1 > 1 ? shape.g1 : 1;
+    const int nwords = slots * nstate;
+    os << "struct EvqTailParams { EvqEmitParams E; u64* dense_state; u64* ctl; u32 nranks; u32 rank; u64 epoch; u64* xbuf_local; "
+          "u64* flags_local; u64* xbuf_peer[16]; u64* flags_peer[16]; u64* merged_out; };\n";
+    os << "#define EVQ_TAIL_WORDS " << nwords << "\n#define EVQ_XSLOT_WORDS 8192\n";
+    os << "extern \"C\" __global__ void __launch_bounds__(256, 1) evq_tail(const __grid_constant__ EvqTailParams T) {\n";
+    os << "  __shared__ u64 m[EVQ_TAIL_WORDS];\n  __shared__ u64 nrows;\n  __shared__ u32 timed_out;\n";
+    os << "  const u32 tid = threadIdx.x;\n  if (tid == 0) { nrows = 0; timed_out = 0; }\n";
+    os << "  const u64 par = T.epoch & 1ull;\n";
+    os << "  if (T.nranks > 1) {\n";
+    os << "    for (u32 i = tid; i < EVQ_TAIL_WORDS; i += 256) {\n      const u64 v = T.dense_state[i];\n"
+          "      for (u32 r = 0; r < T.nranks; ++r)\n        if (r != T.rank) T.xbuf_peer[r][(par * 16 + T.rank) * EVQ_XSLOT_WORDS + i] = v;\n    }\n";
+    os << "    __threadfence_system();\n    __syncthreads();\n";
+    os << "    if (tid < T.nranks && tid != T.rank) {\n"
+          "      asm volatile(\"st.release.sys.global.u64 [%0], %1;\" :: \"l\"(T.flags_peer[tid] + T.rank), \"l\"(T.epoch) : \"memory\");\n"
+          "      const long long t0 = clock64();\n      u64 seen = 0;\n"
+          "      for (;;) {\n        asm volatile(\"ld.acquire.sys.global.u64 %0, [%1];\" : \"=l\"(seen) : \"l\"(T.flags_local + tid) : \"memory\");\n"
+          "        if (seen >= T.epoch) break;\n"
+          "        if (clock64() - t0 > 40000000000ll) { timed_out = 1; break; }\n        __nanosleep(64);\n      }\n    }\n";
+    os << "    __syncthreads();\n  }\n";
+    // combine in rank order
+    os << "  for (u32 i = tid; i < EVQ_TAIL_WORDS; i += 256) {\n    const u32 w = i % " << nstate << "u;\n    u64 acc = 0;\n    switch (w) {\n";
+    for (int w = 0; w < nstate; ++w) {
+      const int op = q.state_ops[w];
+      os << "      case " << w << ": {\n";
+      if (op == OP_FIRST_ORD || op == OP_FIRST_VAL) {
+        const int d = op == OP_FIRST_ORD ? 0 : 1;
+        os << "        const u32 oi = i - " << d << "u;\n        u64 best = ~0ull, val = 0;\n"
+              "        for (u32 r = 0; r < T.nranks; ++r) {\n"
+              "          const u64* src = r == T.rank ? T.dense_state : (const u64*) (T.xbuf_local + (par * 16 + r) * EVQ_XSLOT_WORDS);\n"
+              "          const u64 o = __ldcv(src + oi);\n          if (o < best) { best = o; val = __ldcv(src + oi + 1); }\n        }\n"
+              "        acc = " << (d ? "val" : "best") << ";\n";
+      } else {
+        const int carry_of = q.state_carry_of[w];
+        os << "        acc = evq_state_identity<" << op << ">();\n";
+        if (carry_of >= 0) os << "        u64 lo = 0;\n";
+        os << "        for (u32 r = 0; r < T.nranks; ++r) {\n"
+              "          const u64* src = r == T.rank ? T.dense_state : (const u64*) (T.xbuf_local + (par * 16 + r) * EVQ_XSLOT_WORDS);\n"
+              "          acc = evq_state_combine<" << op << ">(acc, __ldcv(src + i));\n";
+        if (carry_of >= 0)   // add the wraps of re-summing the partner word in the same rank order
+          os << "          { const u64 n = __ldcv(src + i - " << w - carry_of << "u); lo += n; acc += lo < n ? 1ull : 0ull; }\n";
+        os << "        }\n";
+      }
+      os << "        break;\n      }\n";
+    }
+    os << "    }\n    m[i] = acc;\n  }\n  __syncthreads();\n";
+    os << "  {\n    EvqEmitParams E = T.E;\n    E.out_count = &nrows;\n    for (u64 slot = tid; slot < E.slots; slot += 256) evq_emit_group(E, slot, m);\n  }\n";
+    os << "  __syncthreads();\n";
+    // publish + re-arm
+    os << "  for (u32 i = tid; i < EVQ_TAIL_WORDS; i += 256) {\n    if (T.merged_out) T.merged_out[i] = m[i];\n    switch (i % " << nstate << "u) {\n";
+    for (int w = 0; w < nstate; ++w) os << "      case " << w << ": T.dense_state[i] = evq_state_identity<" << q.state_ops[w] << ">(); break;\n";
+    os << "    }\n  }\n";
+    os << "  if (tid == 0) {\n    u64* c = T.ctl;\n    if (timed_out) ((u32*) c)[0] |= EVQ_ERR_PEER_TIMEOUT;\n"
+          "    for (int j = 0; j < 6; ++j) { c[8 + j] = c[j]; c[j] = 0ull; }\n    c[8 + 6] = nrows;\n    c[8 + 7] += 1ull;\n  }\n";
+    os << "}\n";
+  }
   return os.str();
 }
 

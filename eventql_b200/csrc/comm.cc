@@ -67,6 +67,75 @@ Nccl& nccl() {
 
 }  // namespace
 
+namespace {
+
+// Peer-mapped exchange buffers for the fused merge tail (query.cu launch_tail, codegen.cc evq_tail): every rank exports
+// one small cudaMalloc'ed buffer with CUDA IPC and maps all peers' buffers (NVLink P2P inside the box).  Whether the
+// fused path is used is decided HERE, collectively: every rank reports whether its part worked, and the path is on only
+// if it worked everywhere - otherwise all ranks keep the NCCL all-gather merge.
+void p2p_setup(evqgpu_ctx* ctx) {
+  ctx->p2p_ok = false;
+  uint64_t ok = getenv("EVQGPU_NO_P2P") ? 0 : 1;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (ok && ctx->nranks > 16) ok = 0;
+  if (ok) {
+    if (cudaMalloc(&ctx->p2p_local, EVQ_P2P_BYTES) != cudaSuccess || cudaMemset(ctx->p2p_local, 0, EVQ_P2P_BYTES) != cudaSuccess ||
+        cudaDeviceSynchronize() != cudaSuccess || cudaIpcGetMemHandle(&mine, ctx->p2p_local) != cudaSuccess) {
+      cudaGetLastError();
+      ok = 0;
+    }
+  }
+  std::vector<uint64_t> msg(9, 0);
+  msg[0] = ok;
+  memcpy(&msg[1], &mine, 64);
+  const std::vector<uint64_t> all = comm_all_gather_host(ctx, msg);   // (also orders every rank's memset before any peer's first write)
+  bool all_ok = true;
+  for (int r = 0; r < ctx->nranks; ++r) all_ok = all_ok && all[(size_t) r * 9] == 1;
+  uint64_t opened = all_ok ? 1 : 0;
+  if (all_ok) {
+    for (int r = 0; r < ctx->nranks && opened; ++r) {
+      if (r == ctx->rank) { ctx->p2p_peer[r] = ctx->p2p_local; continue; }
+      cudaIpcMemHandle_t h;
+      memcpy(&h, &all[(size_t) r * 9 + 1], 64);
+      if (cudaIpcOpenMemHandle(&ctx->p2p_peer[r], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->p2p_peer[r] = nullptr;
+        opened = 0;
+      }
+    }
+  }
+  const std::vector<uint64_t> all2 = comm_all_gather_host(ctx, std::vector<uint64_t>{opened});
+  bool everywhere = true;
+  for (uint64_t o : all2) everywhere = everywhere && o == 1;
+  if (!everywhere) {
+    for (int r = 0; r < ctx->nranks; ++r)
+      if (r != ctx->rank && ctx->p2p_peer[r]) cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
+    memset(ctx->p2p_peer, 0, sizeof(ctx->p2p_peer));
+    if (ctx->p2p_local) cudaFree(ctx->p2p_local);
+    ctx->p2p_local = nullptr;
+    cudaGetLastError();
+    return;
+  }
+  ctx->p2p_ok = true;
+  ctx->p2p_epoch = 0;
+}
+
+void p2p_teardown(evqgpu_ctx* ctx) {
+  if (!ctx->p2p_local) return;
+  cudaDeviceSynchronize();
+  for (int r = 0; r < ctx->nranks; ++r)
+    if (r != ctx->rank && ctx->p2p_peer[r]) cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
+  memset(ctx->p2p_peer, 0, sizeof(ctx->p2p_peer));
+  cudaFree(ctx->p2p_local);
+  ctx->p2p_local = nullptr;
+  ctx->p2p_ok = false;
+  cudaGetLastError();
+}
+
+}  // namespace
+
 extern "C" {
 
 int evqgpu_comm_unique_id(void* id_out) {
@@ -91,12 +160,14 @@ int evqgpu_comm_init(evqgpu_ctx* ctx, const void* id, int rank, int nranks) {
     ctx->nccl_comm = comm;
     ctx->rank = rank;
     ctx->nranks = nranks;
+    if (nranks > 1) p2p_setup(ctx);
   });
 }
 
 int evqgpu_comm_destroy(evqgpu_ctx* ctx) {
   return guarded([&] {
     if (!ctx || !ctx->nccl_comm) return;
+    p2p_teardown(ctx);
     nccl().CommDestroy((ncclComm_t) ctx->nccl_comm);
     ctx->nccl_comm = nullptr;
     ctx->nranks = 1;

@@ -24,6 +24,13 @@ struct evqgpu_ctx {
   // NCCL (loaded lazily with dlopen, see comm.cc)
   void* nccl_comm = nullptr;
   int rank = 0, nranks = 1;
+  // peer-to-peer exchange buffers for the fused merge tail of the dense tier (comm.cc: p2p_setup): every rank owns
+  // [2 parities][16 ranks][64 KiB] of state slots + one flag word per source rank, mapped into all peers with CUDA IPC
+  // over NVLink.  p2p_ok is agreed on by all ranks (all or none); without it the merge takes the NCCL all-gather path.
+  bool p2p_ok = false;
+  void* p2p_local = nullptr;          // this rank's buffer (cudaMalloc, exported)
+  void* p2p_peer[16] = {nullptr};     // the peers' buffers as mapped here (p2p_peer[rank] == p2p_local)
+  uint64_t p2p_epoch = 0;             // merges done through the buffers; the same on all ranks (merges are collective)
   // scratch for small device->host reads
   void* pinned_scratch = nullptr;   // 4 KiB pinned
   uint64_t kernel_launches = 0;     // total kernels launched through this context

@@ -30,6 +30,7 @@ typedef double f64;
 #define EVQ_ERR_TABLE_FULL 4u
 #define EVQ_ERR_SLOT_RANGE 8u
 #define EVQ_ERR_STAGE_OVERFLOW 16u
+#define EVQ_ERR_PEER_TIMEOUT 32u   // the fused merge tail waited in vain for a peer rank's state
 
 #define EVQ_MAX_STREAMS 32
 #define EVQ_MAX_KEYS 8

@@ -207,6 +207,13 @@ static MergeOps merge_ops_of(const evqgpu_query& q) {
 
 static void merge_dense(evqgpu_query& q) {
   evqgpu_ctx* ctx = q.ctx;
+  // the fused path: ONE kernel pushes this rank's few KB of state into the peers' buffers over NVLink, waits for theirs,
+  // combines in rank order, emits and re-arms (query.cu launch_tail) - no NCCL call, no separate merge / emit kernels
+  if (q.use_tail && ctx->p2p_ok && !getenv("EVQGPU_NO_P2P")) {
+    launch_tail(q, true);
+    q.pending = true;   // row count is read by the next finish
+    return;
+  }
   const MergeOps mo = merge_ops_of(q);
   const uint64_t slots = q.shape.g1 > 1 ? (uint64_t) q.shape.g1 : 1;
   const uint64_t nwords = slots * mo.nstate;
@@ -217,7 +224,8 @@ static void merge_dense(evqgpu_query& q) {
   EVQ_CUDA(cudaGetLastError());
   ctx->kernel_launches++;
   q.stats.kernel_launches++;
-  emit_results(q);
+  if (q.use_tail) launch_tail(q, false);   // (the merged words are in place: emit + re-arm)
+  else emit_results(q);
   q.pending = true;   // row count is read by the next finish
 }
 
@@ -331,7 +339,11 @@ void merge_query(evqgpu_query& q) {
   if (q.merged) return;
   use_device(q.ctx);
   if (q.ctx->nranks <= 1 || !q.ctx->nccl_comm) {
-    if (!q.emitted) emit_results(q), q.pending = true;
+    if (!q.emitted) {
+      if (q.use_tail) launch_tail(q, false);
+      else emit_results(q);
+      q.pending = true;
+    }
     q.merged = true;
     return;
   }

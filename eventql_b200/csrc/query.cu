@@ -748,6 +748,52 @@ void emit_results(evqgpu_query& q) {
   q.emitted = true;
 }
 
+// the tail of a dense-tier execution (codegen.cc evq_tail): with `merge` the ranks' state words are exchanged through the
+// peer-mapped buffers of comm.cc and combined in rank order; then emit, publish, re-arm
+void launch_tail(evqgpu_query& q, bool merge) {
+  evqgpu_ctx* ctx = q.ctx;
+  const uint64_t emit_slots = q.emit.slots;
+  const uint64_t out_cap = std::min<uint64_t>(emit_slots, std::max<uint64_t>(q.emit_total_rows, 64));
+  q.out_cols.resize(q.select.size());
+  for (size_t i = 0; i < q.select.size(); ++i)
+    ensure(q.out_cols[i], out_cap * (q.select[i].expr->type == EVQ_BOOL ? 2 : 9) + 16);
+  q.out_capacity = out_cap;
+  TailParams tp;
+  memset(&tp, 0, sizeof(tp));
+  tp.E = q.emit;
+  tp.E.out_capacity = out_cap;
+  for (size_t i = 0; i < q.select.size(); ++i) tp.E.out_cols[i] = q.out_cols[i].as<u8>();
+  if (q.flags & EVQGPU_QUERY_WIRE) {
+    ensure(q.out_sha, out_cap * 20 + 16);
+    ensure(q.out_state, out_cap * std::max<size_t>(1, q.state_ops.size()) * 8 + 16);
+    tp.E.out_sha = q.out_sha.as<u8>();
+    tp.E.out_state = q.out_state.as<u64>();
+  }
+  tp.dense_state = q.dense_base;
+  tp.ctl = q.ctl.as<u64>();
+  tp.nranks = 1;
+  tp.rank = 0;
+  if (merge) {
+    if (!ctx->p2p_ok) fail(EVQGPU_ERR_RUNTIME, "internal error: fused merge without peer-mapped buffers");
+    tp.nranks = (u32) ctx->nranks;
+    tp.rank = (u32) ctx->rank;
+    tp.epoch = ++ctx->p2p_epoch;
+    tp.xbuf_local = (u64*) ctx->p2p_local;
+    tp.flags_local = (u64*) ((uint8_t*) ctx->p2p_local + EVQ_P2P_FLAGS_OFFSET);
+    for (int r = 0; r < ctx->nranks; ++r) {
+      tp.xbuf_peer[r] = (u64*) ctx->p2p_peer[r];
+      tp.flags_peer[r] = (u64*) ((uint8_t*) ctx->p2p_peer[r] + EVQ_P2P_FLAGS_OFFSET);
+    }
+  }
+  void* args[] = {&tp};
+  launch(ctx, q.module->kernels.at("evq_tail"), dim3(1), dim3(256), 0, args);
+  q.stats.kernel_launches++;
+  q.emitted = true;
+  q.tail_done = true;
+  q.armed = true;
+  q.armed_sig = q.module_sig;
+}
+
 static std::string layout_signature(const evqgpu_query& q) {
   std::string sig;
   for (size_t i = 0; i < q.state_keys.size(); ++i) sig += q.state_keys[i] + "#" + std::to_string(q.state_ops[i]) + ";";
@@ -903,7 +949,9 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
     sig += q.plane_sig;
     if (!q.module || sig != q.module_sig) {
       q.kernel_source = generate_source(q, s);
-      q.module = jit_compile(ctx, q.kernel_source, {"evq_scan", "evq_init", "evq_emit"}, &ms);
+      std::vector<std::string> names = {"evq_scan", "evq_init", "evq_emit"};
+      if (s.tier == 1 && !s.dense_global) names.push_back("evq_tail");
+      q.module = jit_compile(ctx, q.kernel_source, names, &ms);
       q.module_sig = sig;
       if (ms > 0 && q.module->from_disk) q.stats.jit_disk_hits++;
     }
@@ -914,17 +962,33 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
   const size_t nstate = q.state_ops.size();
   EvqScanParams base;
   memset(&base, 0, sizeof(base));
-  base.status = q.status.as<u32>();
-  base.counters = q.counters.as<u64>();
   base.ord_base = (u64) ctx->rank << 44;   // rank-major row ordinals (first-row items of a multi-rank job)
-  EVQ_CUDA(cudaMemsetAsync(q.status.p, 0, 16, ctx->stream));
-  EVQ_CUDA(cudaMemsetAsync(q.counters.p, 0, 32, ctx->stream));
+  // dense tier: the execution ends in ONE tail kernel (merge over NVLink + emit + re-arm, codegen.cc evq_tail) that leaves
+  // the state words at their identities and the control block zeroed, so that the next execution of the same kernel
+  // starts without an init kernel and without memsets: a step is the scan launches + the tail
+  const bool tail = s.tier == 1 && !s.dense_global && q.distinct_args.empty() && !getenv("EVQGPU_NO_TAIL");
+  q.use_tail = tail;
+  q.tail_done = false;
+  bool armed = false;
+  if (tail) {
+    if (!q.ctl.p) { q.ctl.alloc(128); q.armed = false; }
+    base.status = q.ctl.as<u32>();
+    base.counters = q.ctl.as<u64>() + 2;
+    armed = q.armed && q.armed_sig == q.module_sig && !getenv("EVQGPU_NO_REARM");
+    if (!armed) EVQ_CUDA(cudaMemsetAsync(q.ctl.p, 0, 128, ctx->stream));
+  } else {
+    base.status = q.status.as<u32>();
+    base.counters = q.counters.as<u64>();
+    EVQ_CUDA(cudaMemsetAsync(q.status.p, 0, 16, ctx->stream));
+    EVQ_CUDA(cudaMemsetAsync(q.counters.p, 0, 32, ctx->stream));
+  }
+  q.armed = false;   // (until this execution's tail has been enqueued)
   InitParams ip;
   memset(&ip, 0, sizeof(ip));
   uint64_t emit_slots = 0;
   if (s.tier == 1 || s.dense_global) {
     const uint64_t slots = s.dense_global ? dm.slots : s.g1 > 1 ? (uint64_t) s.g1 : 1;
-    ensure(q.dense_state, slots * nstate * 8 + 16);
+    if (q.dense_state.bytes < slots * nstate * 8 + 16) { q.dense_state.alloc(slots * nstate * 8 + 16); armed = false; }
     // first-row pairs must be 16-byte aligned in both tiers: their word index w has (1 + nk + w) even (layout_states)
     q.dense_base = q.dense_state.as<u64>() + ((q.has_first && ((1 + nk) & 1)) ? 1 : 0);
     base.dense_state = q.dense_base;
@@ -955,7 +1019,7 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
     ip.slots = want;
     emit_slots = want;
   }
-  {
+  if (!armed) {
     void* args[] = {&ip};
     launch(ctx, q.module->kernels.at("evq_init"), dim3((unsigned) ((ip.slots + 255) / 256)), dim3(256), 0, args);
     q.stats.kernel_launches++;
@@ -996,7 +1060,10 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
   q.emit.slots = emit_slots;
   q.reordered = false;
   q.emitted = false;
-  if (!((q.flags & EVQGPU_QUERY_PARTIAL) && ctx->nranks > 1)) emit_results(q);
+  if (!((q.flags & EVQGPU_QUERY_PARTIAL) && ctx->nranks > 1)) {
+    if (tail) launch_tail(q, false);
+    else emit_results(q);
+  }
   (void) sync;
 }
 
@@ -1064,10 +1131,22 @@ void finish_query(evqgpu_query& q) {
   evqgpu_ctx* ctx = q.ctx;
   use_device(ctx);
   struct { u32 status[4]; u64 counters[4]; u64 out_count; } host;
-  EVQ_CUDA(cudaMemcpyAsync(host.status, q.status.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
-  EVQ_CUDA(cudaMemcpyAsync(host.counters, q.counters.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
-  EVQ_CUDA(cudaMemcpyAsync(&host.out_count, q.out_count.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (q.use_tail && (q.flags & EVQGPU_QUERY_GROUPBY)) {
+    // dense tier: one control block.  After the tail: the values it published ([8..14]); before it (a partial plan whose
+    // merge has not been called yet): the live words, no rows yet
+    u64 c[16];
+    EVQ_CUDA(cudaMemcpyAsync(c, q.ctl.p, 128, cudaMemcpyDeviceToHost, ctx->stream));
+    EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    const u64* src = q.tail_done ? c + 8 : c;
+    memcpy(host.status, src, 16);
+    memcpy(host.counters, src + 2, 32);
+    host.out_count = q.tail_done ? c[14] : 0;
+  } else {
+    EVQ_CUDA(cudaMemcpyAsync(host.status, q.status.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    EVQ_CUDA(cudaMemcpyAsync(host.counters, q.counters.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    EVQ_CUDA(cudaMemcpyAsync(&host.out_count, q.out_count.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
   q.pending = false;
   // (accumulated over the finishes of one execution: the hash merge finishes the scan before it ships the table and
   // once more after the merged groups are emitted)
@@ -1085,6 +1164,7 @@ void finish_query(evqgpu_query& q) {
   if (err & EVQ_ERR_MOD_ZERO) fail(EVQGPU_ERR_RUNTIME, "modulo by zero");
   if (err & EVQ_ERR_STAGE_OVERFLOW) fail(EVQGPU_ERR_RUNTIME, "internal error: row tile larger than its pipeline stage");
   if (err & EVQ_ERR_SLOT_RANGE) fail(EVQGPU_ERR_RUNTIME, "internal error: group key outside the dense slot range");
+  if (err & EVQ_ERR_PEER_TIMEOUT) fail(EVQGPU_ERR_RUNTIME, "merge: a peer rank did not deliver its partial aggregates (did every rank call evqgpu_query_merge?)");
   if (q.flags & EVQGPU_QUERY_GROUPBY) {
     if (err & EVQ_ERR_TABLE_FULL) {
       // grow the group table and run again (resize policy: double until it fits)

@@ -90,6 +90,23 @@ struct EmitParams {
   u64* out_state;         // EVQGPU_QUERY_WIRE: the raw aggregate state words of every group [rows][nstate]
 };
 
+// parameter block of the tail kernel of a dense-tier execution (mirrors the generated struct EvqTailParams)
+#define EVQ_P2P_XSLOT_WORDS 8192
+#define EVQ_P2P_FLAGS_OFFSET (2ull * 16 * EVQ_P2P_XSLOT_WORDS * 8)   // bytes: the flag words sit behind the state slots
+#define EVQ_P2P_BYTES (EVQ_P2P_FLAGS_OFFSET + 4096)
+struct TailParams {
+  EmitParams E;
+  u64* dense_state;
+  u64* ctl;            // [0..5] live status / counters (zeroed by the tail), [8..13] their values of this execution, [14] rows, [15] tails run
+  u32 nranks, rank;
+  u64 epoch;
+  u64* xbuf_local;
+  u64* flags_local;
+  u64* xbuf_peer[16];
+  u64* flags_peer[16];
+  u64* merged_out;     // EVQGPU_QUERY_WIRE / debugging: the merged state words, or null
+};
+
 struct InitParams {
   u64* dense_state;
   EvqHashTable ht;
@@ -151,6 +168,13 @@ struct evqgpu_query {
   evq::DevBuf merge_recv, merge_send, merge_slots, merge_counts, merge_status;
   uint64_t merge_cap = 0;           // capacity the merged table last needed (kept across executions)
   evq::DevBuf dense_state, ht_slots, status, counters, out_count, tile_counts, tile_base;
+  // dense tier: status / counters / row count live in one control block that the tail kernel publishes and re-arms
+  evq::DevBuf ctl;
+  bool use_tail = false;            // the last execution ends in evq_tail (dense tier without count_distinct)
+  bool armed = false;               // the state words and the control block are known to be identities / zero: the tail of
+                                    // the previous execution re-armed them and nothing has touched them since
+  std::string armed_sig;            // ... for the kernel of this signature (the state layout)
+  bool tail_done = false;
   std::vector<evq::DevBuf> out_cols;
   evq::DevBuf out_sha, out_state;   // EVQGPU_QUERY_WIRE (PartialGroupByExpression rows)
   bool reordered = false;           // ORDER BY / LIMIT rewrote the result rows (the per-group side buffers no longer line up)
@@ -192,6 +216,7 @@ int gen_chunks(const KernelShape& shape);
 // query.cu
 void prepare_query(evqgpu_query& q, std::vector<evqgpu_table*>& tables);
 void emit_results(evqgpu_query& q);
+void launch_tail(evqgpu_query& q, bool merge);
 void finish_query(evqgpu_query& q);
 // merge.cu
 void merge_query(evqgpu_query& q);
