@@ -188,8 +188,10 @@ void layout_states(evqgpu_query& q, const KernelShape& shape) {
 static bool is_packed_byte_column(const Expr* e, const KernelShape& shape) {
   if (e->op != EVQ_X_INPUT || e->col >= shape.cols.size()) return false;
   const ColSig& c = shape.cols[e->col];
-  return c.used && c.kind == EVQ_KIND_LEB128 && c.leb_len == 1 && !c.nullable && c.sql_type != EVQ_BOOL && c.sql_type != EVQ_FLOAT64 &&
-         c.sql_type != EVQ_INT64;
+  // (optional columns too, in the fast layout: their packed bytes hold 0 where the row is NULL, which is what every
+  // consumer of the value sees)
+  return c.used && c.kind == EVQ_KIND_LEB128 && c.leb_len == 1 && (!c.nullable || c.dmax == 1) && c.sql_type != EVQ_BOOL &&
+         c.sql_type != EVQ_FLOAT64 && c.sql_type != EVQ_INT64;
 }
 
 void layout_narrow(evqgpu_query& q, const KernelShape& shape) {
@@ -201,10 +203,19 @@ void layout_narrow(evqgpu_query& q, const KernelShape& shape) {
   q.plane_sums.clear();
   q.swar_slots = false;
   q.plane_sig.clear();
-  if (!shape.fast || shape.tier != 1 || shape.g1 < 2 || shape.g1 > 4 || getenv("EVQGPU_NO_NARROW")) return;
+  q.plane_groups = 0;
+  if (!shape.fast || shape.tier != 1 || shape.g1 < 2 || shape.dense.slots > 7 || getenv("EVQGPU_NO_NARROW")) return;
   if (q.has_first) return;   // first-row items are updated per row (evq_first_update): the per-row accumulate call stays
+  // up to 4 slots: a power of two of groups (the 0xff << 8g masks of one register); 5..7 slots (a NULL-able key: flag x
+  // status with a NULL flag = 6): exactly that many, the masks come from a register pair
+  int ng = shape.g1;
+  if (shape.g1 > 4) {
+    if (shape.g1 != 8 || shape.dense.slots < 5 || getenv("EVQGPU_NO_NARROW8")) return;
+    ng = (int) shape.dense.slots;
+  }
+  q.plane_groups = ng;
   const CodegenEnv env = row_env(shape);
-  int budget = 56;   // u32 accumulator registers per thread
+  int budget = ng <= 4 ? 56 : 92;   // u32 accumulator registers per thread
   if (const char* e = getenv("EVQGPU_PLANE_BUDGET")) budget = atoi(e);
   auto need_packed = [&](int col) {
     for (int c : q.narrow_col)
@@ -252,7 +263,7 @@ void layout_narrow(evqgpu_query& q, const KernelShape& shape) {
       const int np = planes_of(c.w);
       if (!best || np < best_planes) { best = &c; best_planes = np; }
     }
-    if (!best || (q.nnarrow + best_planes) * shape.g1 > budget) continue;
+    if (!best || (q.nnarrow + best_planes) * ng > budget) continue;
     evqgpu_query::PlaneOperand w;
     w.expr = best->w;
     w.nplanes = best_planes;
@@ -288,14 +299,51 @@ void layout_narrow(evqgpu_query& q, const KernelShape& shape) {
     q.state_narrow[item.state0] = (int) q.plane_sums.size();
     q.plane_sums.push_back(ps);
   }
+  // "seen" counters (non-NULL arguments of min / max / mean) of a bare optional column: W = 1, B = the column's presence byte
+  for (const auto& item : q.select) {
+    if (!item.agg || item.state_seen <= 0 || q.state_narrow[item.state_seen] >= 0 || item.agg->args.empty()) continue;
+    const Expr* arg = item.agg->args[0].get();
+    if (arg->op != EVQ_X_INPUT || arg->col >= shape.cols.size()) continue;
+    const ColSig& c = shape.cols[arg->col];
+    if (!c.used || !c.nullable || c.dmax != 1) continue;
+    if ((q.nnarrow + 1) * ng > budget) continue;
+    evqgpu_query::PlaneOperand b;
+    b.expr = arg;
+    b.presence_col = (int) arg->col;
+    evqgpu_query::PlaneSum ps;
+    ps.word = item.state_seen;
+    ps.w = -1;
+    ps.b = -1;
+    for (size_t i = 0; i < q.plane_b.size(); ++i)
+      if (q.plane_b[i].presence_col == b.presence_col) ps.b = (int) i;
+    if (ps.b < 0) { q.plane_b.push_back(b); ps.b = (int) q.plane_b.size() - 1; }
+    ps.nplanes = 1;
+    ps.plane0 = q.nnarrow;
+    q.nnarrow += 1;
+    q.state_narrow[item.state_seen] = (int) q.plane_sums.size();
+    q.plane_sums.push_back(ps);
+  }
   // dense slots on the packed key bytes: every key a bare 1-byte column whose range the statistics bound inside the slots
   {
-    bool ok = !q.group.empty() && shape.dense.slots <= 4;
+    // (a NULL-able key: its packed byte is 0 where the row is NULL and the slot index of NULL is added from the presence
+    // byte - index = value + null_idx * (1 - present), bytewise without carries)
+    bool ok = !q.group.empty() && shape.dense.slots <= 7;
     for (size_t i = 0; ok && i < q.group.size(); ++i) {
       const DenseMap& dm = shape.dense;
       const bool may_null = dm.key_null_idx[i] != ~0ull;
-      ok = is_packed_byte_column(q.group[i].get(), shape) && !may_null && dm.key_min[i] == 0 &&
-           expr_value_max(q.group[i].get(), env) <= dm.key_range[i] - 1;
+      ok = is_packed_byte_column(q.group[i].get(), shape) && dm.key_min[i] == 0 &&
+           (may_null || !shape.cols[q.group[i]->col].nullable) &&
+           expr_value_max(q.group[i].get(), env) <= dm.key_range[i] - (may_null ? 2 : 1);
+      if (ok && may_null) {   // the presence bytes of the key column are needed
+        bool have = false;
+        for (const auto& b : q.plane_b) have = have || b.presence_col == (int) q.group[i]->col;
+        if (!have) {
+          evqgpu_query::PlaneOperand b;
+          b.expr = q.group[i].get();
+          b.presence_col = (int) q.group[i]->col;
+          q.plane_b.push_back(b);
+        }
+      }
     }
     if (ok && q.distinct_args.empty() && !getenv("EVQGPU_NO_SWAR_SLOTS")) {   // (count_distinct needs the slot per row)
       q.swar_slots = true;
@@ -309,10 +357,10 @@ void layout_narrow(evqgpu_query& q, const KernelShape& shape) {
     if (!q.state_global[i] && q.state_narrow[i] < 0) q.state_smem[i] = q.nstate_smem++;
   }
   std::ostringstream sg;
-  sg << "S" << (int) q.swar_slots << ";";
+  sg << "S" << (int) q.swar_slots << "G" << ng << ";";
   for (const auto& ps : q.plane_sums)
     sg << ps.word << ":" << (ps.w >= 0 ? q.plane_w[ps.w].expr->signature() : std::string("1")) << "*"
-       << (ps.b >= 0 ? q.plane_b[ps.b].expr->signature() : std::string("1")) << "/" << ps.nplanes << ";";
+       << (ps.b >= 0 ? (q.plane_b[ps.b].presence_col >= 0 ? "present:" : "") + q.plane_b[ps.b].expr->signature() : std::string("1")) << "/" << ps.nplanes << ";";
   q.plane_sig = sg.str();
 }
 
@@ -517,13 +565,15 @@ static void gen_fast_layout(std::ostringstream& os, const KernelShape& shape) {
     if (shape.cols[i].nullable) os << "  u32 t" << i << ";\n";   // STag: 1 = NULL
   }
   os << "  u64 ord;\n  u32 _unused;\n};\n";
-  os << "struct EvqCols {\n  u64 ord0;\n";
+  os << "struct EvqCols {\n  u64 ord0;\n  u32 nbuf;\n";
   for (size_t i = 0; i < ncols; ++i)
     if (shape.cols[i].used && shape.cols[i].nullable) os << "  u32 n" << i << ", r" << i << ";\n";   // presence bits of the thread's rows, ordinal of its first value
   for (size_t i = 0; i < ncols; ++i)
     if (shape.cols[i].used) os << "  " << fast_ctype(shape.cols[i]) << " c" << i << "[EVQ_RPT];\n";
   for (size_t i = 0; i < ncols; ++i)
     if (shape.cols[i].used && shape.cols[i].packed) os << "  u32 p" << i << "[EVQ_RPT / 4];\n";   // the raw bytes, 4 rows per word
+  for (size_t i = 0; i < ncols; ++i)
+    if (shape.cols[i].used && shape.cols[i].presence) os << "  u32 q" << i << "[EVQ_RPT / 4];\n";  // presence bytes (1 = not NULL), 4 rows per word
   os << "  u32 _unused;\n};\n";
   const int ngen = std::max(1, shape.ngen);
   os << "struct EvqFastPrep {\n  bool general[" << ngen << "];\n  u32 start[" << ngen << "];\n};\n";
@@ -552,17 +602,33 @@ static void gen_fast_layout(std::ostringstream& os, const KernelShape& shape) {
   // ---- optional columns: presence bits of the thread's rows + ordinal of its first value (one barrier per tile)
   os << "__device__ __forceinline__ void evq_fast_nulls(const EvqTile& T, const EvqScanParams& P, EvqFastScratch* scr, u32 buf, u32 nvalid, EvqCols& cols) {\n";
   if (shape.nnull > 0) {
-    for (size_t i = 0; i < ncols; ++i) {
+    // presence bits of the thread's rows, then ONE warp scan per three optional columns: the per-thread counts (<= 8) travel
+    // in 10-bit fields of one word (a thread's exclusive prefix is at most 8 * 127 = 1016)
+    std::vector<size_t> ncol;
+    for (size_t i = 0; i < ncols; ++i)
+      if (shape.cols[i].used && shape.cols[i].nullable) ncol.push_back(i);
+    for (size_t i : ncol)
+      os << "  cols.n" << i << " = evq_fast_presence<" << shape.cols[i].level_stream << ">(T, P) & ((1u << nvalid) - 1u);\n";
+    for (size_t p0 = 0; p0 < ncol.size(); p0 += 3) {
+      os << "  u32 pk" << p0 / 3 << " = evq_fast_null_scan(";
+      for (size_t j = p0; j < std::min(p0 + 3, ncol.size()); ++j) os << (j > p0 ? " | (" : "") << "__popc(cols.n" << ncol[j] << ")" << (j > p0 ? " << " + std::to_string(10 * (j - p0)) + ")" : "");
+      os << ", scr, buf, " << p0 / 3 << ", T.ctid);\n";
+    }
+    os << "  cols.nbuf = buf;\n";
+    for (size_t i = 0; i < ncols; ++i) {   // values of the staged columns, by value ordinal (needs no ranks)
       const ColSig& c = shape.cols[i];
-      if (!c.used || !c.nullable) continue;
-      os << "  cols.n" << i << " = evq_fast_presence<" << c.level_stream << ">(T, P) & ((1u << nvalid) - 1u);\n";
-      os << "  cols.r" << i << " = evq_fast_null_scan(cols.n" << i << ", scr, buf, " << c.null_slot << ", T.ctid);\n";
+      if (!c.used || c.nv_slot < 0) continue;
+      uint32_t lmin = 1;   // (of the values in the stream: NULL rows have none)
+      for (uint64_t m = c.vmin_present >> 7; m; m >>= 7) ++lmin;
+      lmin = std::min(lmin, c.leb_len);
+      os << "  evq_fast_stage_vals<" << c.data_stream << ", " << c.sub_stream << ", " << c.leb_len << ", " << lmin << ", " << c.nv_slot
+         << ">(T, P, scr, buf);\n";
     }
     os << "  evq_cons_sync();\n";
-    for (size_t i = 0; i < ncols; ++i) {
-      const ColSig& c = shape.cols[i];
-      if (!c.used || !c.nullable) continue;
-      os << "  cols.r" << i << " = evq_fast_null_rank(cols.r" << i << ", scr, buf, " << c.null_slot << ", T.ctid);\n";
+    for (size_t p0 = 0; p0 < ncol.size(); p0 += 3) {
+      os << "  pk" << p0 / 3 << " = evq_fast_null_rank(pk" << p0 / 3 << ", scr, buf, " << p0 / 3 << ", T.ctid);\n";
+      for (size_t j = p0; j < std::min(p0 + 3, ncol.size()); ++j)
+        os << "  cols.r" << ncol[j] << " = (pk" << p0 / 3 << " >> " << 10 * (j - p0) << ") & 1023u;\n";
     }
   }
   os << "}\n";
@@ -585,7 +651,11 @@ static void gen_fast_layout(std::ostringstream& os, const KernelShape& shape) {
         case EVQ_KIND_PLAIN32: os << "    u32 raw[EVQ_RPT];\n    evq_fast_ldn_plain32<" << S << ">(T, P, " << pbr << ", raw);\n"; break;
         case EVQ_KIND_BITPACK: os << "    u32 raw[EVQ_RPT];\n    evq_fast_ldn_bitpack<" << S << ">(T, P, " << pbr << ", raw);\n"; break;
         default:
-          if (c.leb_len <= 1) {
+          if (c.nv_slot >= 0) {
+            os << "    u32 raw[EVQ_RPT];\n    evq_fast_gather_vals<" << c.nv_slot << ">(scr, cols.nbuf, " << pbr << ", raw);\n";
+          } else if (c.leb_len <= 1 && c.packed) {
+            os << "    u32 raw[EVQ_RPT];\n    evq_fast_ldn_leb1p<" << S << ">(T, P, " << pbr << ", raw, cols.p" << i << ");\n";
+          } else if (c.leb_len <= 1) {
             os << "    u32 raw[EVQ_RPT];\n    evq_fast_ldn_leb1<" << S << ">(T, P, " << pbr << ", raw);\n";
           } else {
             raw_tn = "u64";
@@ -601,6 +671,7 @@ static void gen_fast_layout(std::ostringstream& os, const KernelShape& shape) {
         default: conv = std::string("(") + ct + ") raw[k]"; break;
       }
       os << "#pragma unroll\n    for (int k = 0; k < EVQ_RPT; ++k) cols.c" << i << "[k] = " << conv << ";\n  }\n";
+      if (c.presence) os << "  evq_presence_bytes(cols.n" << i << ", cols.q" << i << ");\n";
       (void) raw_tn;
       continue;
     }
@@ -804,8 +875,15 @@ static std::string gen_row_functions(const evqgpu_query& q, const KernelShape& s
         if (q.swar_slots) {
           os << "#define EVQ_SWAR_SLOTS 1\n";
           os << "__device__ __forceinline__ u32 evq_quad_slots(const EvqCols& cols, int j) {\n  const u32 s = 0u";
-          for (size_t i = 0; i < q.group.size(); ++i) os << " + cols.p" << q.group[i]->col << "[j] * " << shape.dense.key_stride[i] << "u";
-          os << ";   // the slot of each row in its byte (< 4: no carries)\n";
+          for (size_t i = 0; i < q.group.size(); ++i) {
+            os << " + cols.p" << q.group[i]->col << "[j] * " << shape.dense.key_stride[i] << "u";
+            if (shape.dense.key_null_idx[i] != ~0ull) {   // NULL rows (packed byte 0): + null_idx, bytewise
+              char lit[32];
+              snprintf(lit, sizeof(lit), "0x%08xu", (unsigned) (shape.dense.key_null_idx[i] * 0x01010101u));
+              os << " + (" << lit << " - cols.q" << q.group[i]->col << "[j] * " << shape.dense.key_null_idx[i] << "u) * " << shape.dense.key_stride[i] << "u";
+            }
+          }
+          os << ";   // the slot of each row in its byte (< 8: no carries)\n";
           os << "  return __byte_perm(s | (s >> 4), 0u, 0x4420u);   // one nibble per row\n}\n";
         }
         // a W / B expression for row kk of quad j
@@ -820,7 +898,8 @@ static std::string gen_row_functions(const evqgpu_query& q, const KernelShape& s
           return e;
         };
         os << "__device__ __forceinline__ void evq_accumulate_narrow(const EvqCols& cols, int j, u32 selector, u32* nacc) {\n";
-        os << "  u32 m[EVQ_G1];\n#pragma unroll\n  for (int g = 0; g < EVQ_G1; ++g) m[g] = __byte_perm(0xffu << (8 * g), 0u, selector);\n";
+        os << "  u32 m[EVQ_NG];\n#pragma unroll\n  for (int g = 0; g < EVQ_NG; ++g)\n"
+              "    m[g] = __byte_perm(g < 4 ? 0xffu << (8 * (g & 3)) : 0u, g < 4 ? 0u : 0xffu << (8 * (g & 3)), selector);\n";
         // byte planes of every distinct W
         for (size_t wi = 0; wi < q.plane_w.size(); ++wi) {
           const auto& W = q.plane_w[wi];
@@ -853,7 +932,9 @@ static std::string gen_row_functions(const evqgpu_query& q, const KernelShape& s
         for (size_t bi = 0; bi < q.plane_b.size(); ++bi) {
           const auto& B = q.plane_b[bi];
           os << "  const u32 b" << bi << " = ";
-          if (B.packed_col >= 0 && B.swar == 0) {
+          if (B.presence_col >= 0) {
+            os << "cols.q" << B.presence_col << "[j];\n";
+          } else if (B.packed_col >= 0 && B.swar == 0) {
             os << "cols.p" << B.packed_col << "[j];\n";
           } else if (B.packed_col >= 0) {
             char lit[32];
@@ -866,26 +947,27 @@ static std::string gen_row_functions(const evqgpu_query& q, const KernelShape& s
                << ", 0x0040u), 0x5410u);\n";
           }
         }
-        os << "#pragma unroll\n  for (int g = 0; g < EVQ_G1; ++g) {\n";
+        os << "#pragma unroll\n  for (int g = 0; g < EVQ_NG; ++g) {\n";
         for (size_t bi = 0; bi < q.plane_b.size(); ++bi) os << "    const u32 b" << bi << "m = b" << bi << " & m[g];\n";
         for (const auto& ps : q.plane_sums) {
           for (int pl = 0; pl < ps.nplanes; ++pl) {
-            const std::string acc = "nacc[" + std::to_string(ps.plane0 + pl) + " * EVQ_G1 + g]";
+            const std::string acc = "nacc[" + std::to_string(ps.plane0 + pl) + " * EVQ_NG + g]";
             const std::string plane = ps.w < 0 ? std::string("0x01010101u") : "w" + std::to_string(ps.w) + "p" + std::to_string(pl);
-            if (ps.b < 0) os << "    " << acc << " = evq_dp4a_us(" << plane << ", m[g], " << acc << ");\n";
+            if (ps.b >= 0 && ps.w < 0) os << "    " << acc << " = __dp4a(0x01010101u, b" << ps.b << "m, " << acc << ");\n";   // a count of B's bytes
+            else if (ps.b < 0) os << "    " << acc << " = evq_dp4a_us(" << plane << ", m[g], " << acc << ");\n";
             else os << "    " << acc << " = __dp4a(" << plane << ", b" << ps.b << "m, " << acc << ");\n";
           }
         }
         os << "  }\n}\n";
         // rows that passed WHERE, from the (negated) rows counters
         os << "__device__ __forceinline__ u64 evq_narrow_rows(const u32* nacc) {\n  u64 n = 0;\n#pragma unroll\n"
-              "  for (int g = 0; g < EVQ_G1; ++g) n += (u64) (0u - nacc[g]);\n  return n;\n}\n";
+              "  for (int g = 0; g < EVQ_NG; ++g) n += (u64) (0u - nacc[g]);\n  return n;\n}\n";
         os << "__device__ __forceinline__ void evq_narrow_flush(const u32* nacc, u64* dense_state) {\n";
-        for (int g = 0; g < shape.g1; ++g)
+        for (int g = 0; g < q.plane_groups; ++g)
           for (const auto& ps : q.plane_sums) {
             std::string v;
             for (int pl = 0; pl < ps.nplanes; ++pl) {
-              std::string a = "nacc[" + std::to_string((ps.plane0 + pl) * shape.g1 + g) + "]";
+              std::string a = "nacc[" + std::to_string((ps.plane0 + pl) * q.plane_groups + g) + "]";
               if (ps.b < 0) a = "(0u - " + a + ")";
               a = "((u64) " + a + " << " + std::to_string(8 * pl) + ")";
               v += (pl ? " + " : "") + a;
@@ -1134,6 +1216,8 @@ std::string generate_source(const evqgpu_query& q, const KernelShape& shape_in) 
   KernelShape shape = shape_in;
   for (int col : q.narrow_col)
     if (col >= 0) shape.cols[col].packed = true;
+  for (const auto& b : q.plane_b)
+    if (b.presence_col >= 0) shape.cols[b.presence_col].presence = true;
   std::ostringstream os;
   os << "// generated by eventql_b200 csrc/codegen.cc - one fused scan kernel per (plan, column layout)\n";
   os << "#define EVQ_NCONS " << shape.ncons << "\n#define EVQ_NSTAGES " << shape.nstages << "\n#define EVQ_NSTREAMS "
@@ -1141,7 +1225,7 @@ std::string generate_source(const evqgpu_query& q, const KernelShape& shape_in) 
      << std::max(1, q.nstate_smem) << "\n#define EVQ_NKEYS " << q.group.size() << "\n#define EVQ_NLEB "
      << shape.nleb << "\n#define EVQ_NNULL " << shape.nnull << "\n#define EVQ_HAS_PREP "
      << ((shape.nleb > 0 || shape.nnull > 0) ? 1 : 0) << "\n#define EVQ_MIN_CTAS " << shape.min_ctas << "\n#define EVQ_NGEN "
-     << shape.ngen << "\n#define EVQ_GEN_CHUNKS " << gen_chunks(shape) << "\n#define EVQ_NNARROW " << q.nnarrow << "\n#define EVQ_NSTATE_SMEM " << q.nstate_smem << "\n#define EVQ_NSTATE_ALL "
+     << shape.ngen << "\n#define EVQ_GEN_CHUNKS " << gen_chunks(shape) << "\n#define EVQ_NNV " << shape.nnv << "\n#define EVQ_NNARROW " << q.nnarrow << "\n#define EVQ_NG " << std::max(1, q.plane_groups) << "\n#define EVQ_NSTATE_SMEM " << q.nstate_smem << "\n#define EVQ_NSTATE_ALL "
      << std::max<size_t>(1, q.state_ops.size()) << "\n";
   if (getenv("EVQGPU_DRYRUN")) os << "#define EVQ_DRYRUN 1\n";
   if (shape.fast) os << "#define EVQ_KT " << shape.kt << "\n";

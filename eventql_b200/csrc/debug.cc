@@ -33,7 +33,8 @@ extern "C" int evqgpu_debug_generate(const evqgpu_query_desc* desc, const evqgpu
       cs.dmax = columns[i].dlevel_max;
       cs.bits = columns[i].value_bits ? columns[i].value_bits : 64;
       cs.vmax = cs.bits >= 64 ? ~0ull : (1ull << cs.bits) - 1;
-      if (columns[i].value_max) { cs.vmax = columns[i].value_max; cs.vmin = columns[i].value_min; }
+      if (columns[i].value_max) { cs.vmax = columns[i].value_max; cs.vmin = columns[i].value_min; cs.vmin_present = columns[i].value_min; }
+      if (cs.nullable) cs.vmin = 0;   // NULL rows read as 0
       cs.leb_len = columns[i].leb_max_len ? columns[i].leb_max_len : 10;
       cs.data_stream = s.nstreams++;
       if (cs.nullable) { cs.level_stream = s.nstreams++; cs.null_slot = s.nnull++; }
@@ -50,6 +51,10 @@ extern "C" int evqgpu_debug_generate(const evqgpu_query_desc* desc, const evqgpu
       if (s.use_subidx) c.sub_stream = s.nstreams++;
       else c.gen_slot = s.ngen++;
     }
+    for (auto& c : s.cols)   // as finish_shape (query.cu): optional variable-length columns of <= 4 bytes are decoded by value ordinal
+      if (s.fast && c.used && c.nullable && c.kind == EVQ_KIND_LEB128 && c.leb_len >= 2 && c.leb_len <= 4 && c.sub_stream >= 0 &&
+          !getenv("EVQGPU_NO_STAGED_NULLS"))
+        c.nv_slot = s.nnv++;
     layout_states(q, s);
     const bool groupby = q.flags & EVQGPU_QUERY_GROUPBY;
     std::vector<int> tiers;
@@ -64,23 +69,26 @@ extern "C" int evqgpu_debug_generate(const evqgpu_query_desc* desc, const evqgpu
         s.g1 = 2;
         while ((uint32_t) s.g1 < dense_slots) s.g1 <<= 1;
       }
-      if (s.tier == 1 && s.g1 > 1) {   // a plausible dense map: every key spans [0, 1], last key fastest
+      if (s.tier == 1 && s.g1 > 1) {   // a plausible dense map: every key spans [0, 1] (+ NULL for a bare optional column), last key fastest
         uint64_t stride = 1;
         for (size_t k = q.group.size(); k-- > 0;) {
+          const Expr* g = q.group[k].get();
+          const bool may_null = g->op == EVQ_X_INPUT && g->col < s.cols.size() && s.cols[g->col].nullable;
           s.dense.key_min[k] = 0;
-          s.dense.key_range[k] = 2;
-          s.dense.key_null_idx[k] = ~0ull;
+          s.dense.key_range[k] = may_null ? 3 : 2;
+          s.dense.key_null_idx[k] = may_null ? 2 : ~0ull;
           s.dense.key_stride[k] = stride;
-          stride *= 2;
+          stride *= s.dense.key_range[k];
         }
         s.dense.slots = stride;
+        while ((uint64_t) s.g1 < s.dense.slots) s.g1 <<= 1;
       }
       layout_states(q, s);
       layout_narrow(q, s);
       s.ncons = s.fast ? 128 : 256;   // what fit_shape picks first
       s.nstages = s.fast ? 2 : 3;
       s.kt = s.fast ? 2 : 1;
-      s.min_ctas = s.fast ? 4 : 2;
+      s.min_ctas = s.fast ? (q.nnarrow * std::max(1, q.plane_groups) > 60 ? 3 : 4) : 2;   // as fit_shape caps it
       std::string src = generate_source(q, s);
       if (compile) {
         std::string log;

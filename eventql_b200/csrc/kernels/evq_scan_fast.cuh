@@ -36,6 +36,10 @@ struct EvqFastScratch {
   u32 chunk[EVQ_NGEN > 0 ? EVQ_NGEN : 1][EVQ_GEN_CHUNKS];     // per chunk: terminators before it in its warp << 16 | terminator mask
   u32 scan[EVQ_NWARPS];                                       // scan-only plans: pass counts per warp
   u32 nullw[2][EVQ_NNULL > 0 ? EVQ_NNULL : 1][EVQ_NWARPS];    // optional columns: present values per consumer warp (two tiles in flight)
+#if defined(EVQ_NNV) && EVQ_NNV > 0
+  // optional variable-length columns: the tile's present values, decoded by value ordinal (two tiles in flight)
+  __align__(16) u32 nval[2][EVQ_NNV][EVQ_TILE_ROWS + 8];
+#endif
 };
 
 // ---- boundary search of a variable-length LEB128 column ------------------------------------------------------------------
@@ -435,8 +439,8 @@ __device__ __forceinline__ u32 evq_fast_presence(const EvqTile& T, const EvqScan
 
 // ordinal of the thread's first present value among the tile's values of the column: warp scan of the per-thread counts,
 // warp totals through shared memory (`buf` alternates between consecutive tiles, so one barrier per tile suffices)
-__device__ __forceinline__ u32 evq_fast_null_scan(u32 pb, EvqFastScratch* scr, u32 buf, int slot, u32 tid) {
-  const u32 cnt = __popc(pb);
+// (`cnt`: the thread's count, or the counts of up to three columns in 10-bit fields - the sums never leave their fields)
+__device__ __forceinline__ u32 evq_fast_null_scan(u32 cnt, EvqFastScratch* scr, u32 buf, int slot, u32 tid) {
   u32 incl = cnt;
   const u32 lane = evq_lane();
 #pragma unroll
@@ -457,13 +461,57 @@ __device__ __forceinline__ u32 evq_fast_null_rank(u32 excl, const EvqFastScratch
 // index, among the thread's present values, of row k's value
 __device__ __forceinline__ u32 evq_pidx(u32 pb, int k) { return __popc(pb & ((1u << k) - 1u)); }
 
-// 1-byte LEB128, optional: the value with ordinal r is byte r of the tile's payload
+// prmt.b32 with its full 4-bit selector nibbles: bit 3 replicates the sign bit of the selected byte (the __byte_perm
+// intrinsic only uses 3 bits per nibble)
+__device__ __forceinline__ u32 evq_prmt(u32 a, u32 b, u32 sel) {
+  u32 d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+
+// presence bit k -> bit 4k (8 rows -> 8 nibbles)
+__device__ __forceinline__ u32 evq_spread_nibbles(u32 pb) {
+  u32 x = pb & 0xffu;
+  x = (x | (x << 12)) & 0x000f000fu;
+  x = (x | (x << 6)) & 0x03030303u;
+  x = (x | (x << 3)) & 0x11111111u;
+  return x;
+}
+
+// presence bytes (1 = not NULL) of the thread's 8 rows, 4 rows per word: nibble k of the spread bits selects byte 0 (0x00)
+// or byte 1 (0x01) of a constant - one PRMT per 4 rows
+__device__ __forceinline__ void evq_presence_bytes(u32 pb, u32 (&q)[EVQ_RPT / 4]) {
+  const u32 x = evq_spread_nibbles(pb);
+  q[0] = __byte_perm(0x00000100u, 0u, x & 0xffffu);
+  if (EVQ_RPT == 8) q[EVQ_RPT / 4 - 1] = __byte_perm(0x00000100u, 0u, x >> 16);
+}
+
+// 1-byte LEB128, optional: the value with ordinal r is byte r of the tile's payload; the thread's (up to 8) present values
+// are the 8 bytes at `rank`.  They are scattered to the rows that are present with ONE PRMT per 4 rows: selector nibble k =
+// number of present rows below row k (exclusive prefix of the presence bits, a multiply on the nibble-spread bits); an absent
+// row sets bit 3 of its nibble, which makes PRMT replicate the sign bit of the selected byte - 0, the bytes are masked to 7
+// bits (a 1-byte LEB128 value is < 128) - so NULL rows read 0 (CSTableScan.cc:877-890).  `packed`: 4 rows per word.
 template <int S>
-__device__ __forceinline__ void evq_fast_ldn_leb1(const EvqTile& T, const EvqScanParams& P, u32 pb, u32 rank, u32 (&v)[EVQ_RPT]) {
+__device__ __forceinline__ void evq_fast_ldn_leb1p(const EvqTile& T, const EvqScanParams& P, u32 pb, u32 rank, u32 (&v)[EVQ_RPT],
+                                                   u32 (&packed)[EVQ_RPT / 4]) {
   u32 lo, hi;
   evq_lds_unaligned64(T.stage + P.streams[S].smem_off + T.desc[S].delta + rank, lo, hi);
+  lo &= 0x7f7f7f7fu;
+  hi &= 0x7f7f7f7fu;
+  const u32 x = evq_spread_nibbles(pb);
+  const u32 sel = (x * 0x11111110u) | ((x ^ 0x11111111u) << 3);
+  packed[0] = evq_prmt(lo, hi, sel & 0xffffu);
+  if (EVQ_RPT == 8) packed[EVQ_RPT / 4 - 1] = evq_prmt(lo, hi, sel >> 16);
 #pragma unroll
-  for (int k = 0; k < EVQ_RPT; ++k) v[k] = ((pb >> k) & 1u) ? (__byte_perm(lo, hi, evq_pidx(pb, k)) & 0xffu) : 0u;
+  for (int j = 0; j < EVQ_RPT / 4; ++j) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[4 * j + i] = __byte_perm(packed[j], 0u, 0x4440u + i);
+  }
+}
+template <int S>
+__device__ __forceinline__ void evq_fast_ldn_leb1(const EvqTile& T, const EvqScanParams& P, u32 pb, u32 rank, u32 (&v)[EVQ_RPT]) {
+  u32 packed[EVQ_RPT / 4];
+  evq_fast_ldn_leb1p<S>(T, P, pb, rank, v, packed);
 }
 
 template <int S>
@@ -488,6 +536,35 @@ __device__ __forceinline__ void evq_fast_ldn_bitpack(const EvqTile& T, const Evq
 #pragma unroll
   for (int k = 0; k < EVQ_RPT; ++k) v[k] = ((pb >> k) & 1u) ? evq_unpack_vertical(words, d.skew + rank + evq_pidx(pb, k), bits) : 0u;
 }
+
+#if defined(EVQ_NNV) && EVQ_NNV > 0
+// Optional variable-length LEB128 column of <= 4 bytes.  Only the present values are in the data stream, so a thread's
+// rows start at a value ordinal that depends on the presence bits of all rows before them - but the VALUES can be decoded
+// without knowing that: thread t decodes the tile's value ordinals 8t .. 8t+7 exactly like a required column (two chains
+// from the column's sub-index entries) into the staging array, before the one barrier of the tile that the presence scan
+// needs anyway; behind it every row gathers its value at ordinal rank + (present rows of the thread below it).
+template <int S, int X, int L, int LMIN, int NV>
+__device__ __forceinline__ void evq_fast_stage_vals(const EvqTile& T, const EvqScanParams& P, EvqFastScratch* scr, u32 buf) {
+  if (EVQ_RPT * T.ctid >= T.desc[S].nvals) return;
+  u32 raw[EVQ_RPT];
+  evq_fast_ld_leb32<S, 2, L, LMIN>(T, P, evq_fast_general<S, L>(T), evq_fast_substart<X>(T, P), raw);
+  const u32 a = evq_smem_u32(&scr->nval[buf][NV][EVQ_RPT * T.ctid]);
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(a), "r"(raw[0]), "r"(raw[1]), "r"(raw[2]), "r"(raw[3]) : "memory");
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(a + 16u), "r"(raw[4]), "r"(raw[5]), "r"(raw[6]), "r"(raw[7]) : "memory");
+}
+template <int NV>
+__device__ __forceinline__ void evq_fast_gather_vals(const EvqFastScratch* scr, u32 buf, u32 pb, u32 rank, u32 (&v)[EVQ_RPT]) {
+  const u32 x = evq_spread_nibbles(pb);
+  const u32 excl = x * 0x11111110u;
+  const u32 a = evq_smem_u32(&scr->nval[buf][NV][rank]);
+#pragma unroll
+  for (int k = 0; k < EVQ_RPT; ++k) {
+    u32 w;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(a + 4u * ((excl >> (4 * k)) & 7u)));
+    v[k] = ((pb >> k) & 1u) ? w : 0u;
+  }
+}
+#endif
 
 // LEB128 of 2..10 bytes, optional.  X = stream of the column's sub-index (u16 per EVQ_SUB_GRAN values of the tile), or -1
 // when every value has L bytes.  The thread enters at the sub-index entry in front of its first value, skips the
@@ -618,9 +695,9 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
 #if EVQ_G1 > 1
   for (u32 g = 0; g < EVQ_G1; ++g) evq_state_init_slot(sacc, g, tid);
 #if EVQ_NNARROW > 0
-  u32 nacc[EVQ_NNARROW * EVQ_G1];
+  u32 nacc[EVQ_NNARROW * EVQ_NG];
 #pragma unroll
-  for (int i = 0; i < EVQ_NNARROW * EVQ_G1; ++i) nacc[i] = 0u;
+  for (int i = 0; i < EVQ_NNARROW * EVQ_NG; ++i) nacc[i] = 0u;
 #endif
 #else
   u64 racc[EVQ_NSTATE];
@@ -783,10 +860,12 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
     // >= 4 = did not pass) drives the dp4a accumulators, the remaining words (if any) take the shared-memory path per row
 #pragma unroll
     for (int j = 0; j < EVQ_RPT / 4; ++j) {
+      // one nibble per row: its dense slot, or EVQ_SEL_NONE = "did not pass" (a nibble no group mask answers to)
+#define EVQ_SEL_NONE (EVQ_NG > 4 ? 7u : 4u)
 #ifdef EVQ_SWAR_SLOTS
       u32 selector = evq_quad_slots(cols, j);   // slots of the 4 rows from the packed key bytes
 #else
-      u32 selector = 0x4444u;
+      u32 selector = EVQ_SEL_NONE * 0x1111u;
 #endif
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
@@ -799,10 +878,10 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
         const bool pass = ((u32) k < nvalid) && evq_where(row, err) && EVQ_ROW_KEPT(k);
 #endif
 #if defined(EVQ_SWAR_SLOTS) && EVQ_NSTATE_SMEM == 0
-        selector |= pass ? 0u : (4u << (4 * kk));   // nothing else to do per row: no branch
+        selector |= pass ? 0u : (EVQ_SEL_NONE << (4 * kk));   // nothing else to do per row: no branch
 #elif defined(EVQ_SWAR_SLOTS)
         if (pass) evq_accumulate_smem(row, sacc, (selector >> (4 * kk)) & 3u, tid, P.dense_state, err);
-        else selector |= 4u << (4 * kk);
+        else selector |= EVQ_SEL_NONE << (4 * kk);
 #else
         if (pass) {   // (rows passed are counted from the rows accumulators at the end)
           u64 key[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
@@ -814,7 +893,7 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
 #else
           if (g != ~0u) {
 #endif
-            selector ^= (g ^ 4u) << (4 * kk);
+            selector ^= (g ^ EVQ_SEL_NONE) << (4 * kk);
 #if EVQ_NSTATE_SMEM > 0
             evq_accumulate_smem(row, sacc, g, tid, P.dense_state, err);
 #endif

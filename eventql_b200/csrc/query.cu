@@ -90,6 +90,7 @@ static KernelShape shape_for(const evqgpu_query& q, evqgpu_table* t, const Bindi
     cs.bits = c.value_bits;
     cs.vmax = stat_ceil(c.value_max);
     cs.vmin = stat_floor(c.value_min);
+    cs.vmin_present = stat_floor(c.value_min_present);
     cs.leb_len = c.leb_max_len;
     cs.leb_uniform = c.data_kind == EVQ_KIND_LEB128 && c.leb_uniform && !getenv("EVQGPU_NO_UNIFORM");
     cs.data_stream = s.nstreams++;
@@ -112,6 +113,7 @@ static void widen_shape(KernelShape& s, const KernelShape& o) {
     s.cols[i].bits = std::max(s.cols[i].bits, o.cols[i].bits);
     s.cols[i].vmax = std::max(s.cols[i].vmax, o.cols[i].vmax);
     s.cols[i].vmin = std::min(s.cols[i].vmin, o.cols[i].vmin);
+    s.cols[i].vmin_present = std::min(s.cols[i].vmin_present, o.cols[i].vmin_present);
     s.cols[i].leb_uniform = s.cols[i].leb_uniform && o.cols[i].leb_uniform && s.cols[i].leb_len == o.cols[i].leb_len;
     s.cols[i].leb_len = std::max(s.cols[i].leb_len, o.cols[i].leb_len);
   }
@@ -128,6 +130,13 @@ static void finish_shape(KernelShape& s, bool have_subidx) {
     if (!(s.fast && c.used && c.kind == EVQ_KIND_LEB128 && c.leb_len >= 2) || c.leb_uniform) continue;
     if (s.use_subidx) c.sub_stream = s.nstreams++;
     else c.gen_slot = s.ngen++;
+  }
+  s.nnv = 0;
+  for (auto& c : s.cols) {
+    c.nv_slot = -1;
+    if (s.fast && c.used && c.nullable && c.kind == EVQ_KIND_LEB128 && c.leb_len >= 2 && c.leb_len <= 4 && c.sub_stream >= 0 &&
+        !getenv("EVQGPU_NO_STAGED_NULLS"))
+      c.nv_slot = s.nnv++;
   }
   if (s.nstreams > EVQ_MAX_STREAMS)
     fail(EVQGPU_ERR_UNSUPPORTED, "query reads %d column streams; the scan kernel stages at most %d", s.nstreams, EVQ_MAX_STREAMS);
@@ -186,7 +195,8 @@ static size_t scratch_bytes(const KernelShape& s) {
   const size_t nwarps = s.ncons / 32;
   if (s.fast) {   // EvqFastScratch
     const size_t ngen = std::max(1, s.ngen);
-    return round_up(4 * ngen * nwarps + 4 * ngen * (size_t) gen_chunks(s) + 4 * nwarps + 8 * std::max(1, s.nnull) * nwarps, 128) + 128;
+    return round_up(4 * ngen * nwarps + 4 * ngen * (size_t) gen_chunks(s) + 4 * nwarps + 8 * std::max(1, s.nnull) * nwarps +
+                    (size_t) s.nnv * 2 * (EVQ_TILE_ROWS + 8) * 4 + 16, 128) + 128;
   }
   const size_t one = 4 * std::max(1, s.nleb) * nwarps + 4 * std::max(1, s.nnull) * (EVQ_TILE_ROWS / 32) +
                      2 * std::max(1, s.nleb) * EVQ_TILE_ROWS + 4 * nwarps;
@@ -499,8 +509,8 @@ static void fit_shape(evqgpu_query& q, KernelShape& s, std::vector<TablePlan>& p
       // the launch bounds leave per thread: 2 x 288 threads or 4 x 160 threads
       const int by_smem = (int) ((227 * 1024) / (worst + 1024));
       // (the byte-plane accumulators of the dense tier are registers: fewer CTAs, more registers per thread)
-      const int nacc = q.nnarrow * s.g1;
-      const int cap = s.ncons <= 128 ? (nacc > 36 ? 4 : nacc > 16 ? 5 : 6) : 2;
+      const int nacc = q.nnarrow * std::max(1, q.plane_groups);
+      const int cap = s.ncons <= 128 ? (nacc > 60 ? 3 : nacc > 36 ? 4 : nacc > 16 ? 5 : 6) : 2;
       if (s.kt > 1 && by_smem < cap && !getenv("EVQGPU_KT")) { attempt |= 3; continue; }   // larger stages would cost residency: one tile per stage
       s.min_ctas = std::max(1, std::min(by_smem, cap));
       if (const char* e = getenv("EVQGPU_MAX_CTAS")) s.min_ctas = std::max(1, std::min(s.min_ctas, atoi(e)));
@@ -935,8 +945,9 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
              (int) s.use_subidx, q.nnarrow, s.kt * 1000 + (s.filter_stream + 1) * 10 + (int) s.dense_global);
     sig += buf;
     for (const auto& c : s.cols) {
-      snprintf(buf, sizeof(buf), "%d.%u.%u.%d.%u.%u.%u%s.%d.%d.%d.%llu.%llu;", (int) c.used, c.sql_type, c.kind, (int) c.nullable, c.dmax, c.bits,
-               c.leb_len, c.leb_uniform ? "u" : "", c.gen_slot, c.sub_stream, c.data_stream, (unsigned long long) c.vmax, (unsigned long long) c.vmin);
+      snprintf(buf, sizeof(buf), "%d.%u.%u.%d.%u.%u.%u%s.%d.%d.%d.%llu.%llu.%llu.%d;", (int) c.used, c.sql_type, c.kind, (int) c.nullable, c.dmax, c.bits,
+               c.leb_len, c.leb_uniform ? "u" : "", c.gen_slot, c.sub_stream, c.data_stream, (unsigned long long) c.vmax, (unsigned long long) c.vmin,
+               (unsigned long long) c.vmin_present, c.nv_slot);
       sig += buf;
     }
     for (size_t i = 0; i < nk && !s.dense_global; ++i) {   // (the direct-addressed array takes its bounds as parameters)

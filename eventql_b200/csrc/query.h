@@ -43,11 +43,15 @@ struct ColSig {
   uint32_t bits = 64;      // every value < 2^bits (max over the scanned tables)
   uint64_t vmax = ~0ull;   // every value <= vmax (max over the scanned tables; coarsened, see stat_ceil)
   uint64_t vmin = 0;       // every value >= vmin (min over the scanned tables; coarsened, see stat_floor)
+  uint64_t vmin_present = 0;   // every non-NULL value >= this (vmin is 0 as soon as NULLs are present)
   uint32_t leb_len = 10;   // LEB128: longest value in bytes (max over the scanned tables)
   bool leb_uniform = false;   // LEB128: every value of every scanned table has exactly leb_len bytes
   int gen_slot = -1;       // fast kernel: index among the LEB128 columns that may need the boundary search (leb_len >= 2)
   bool packed = false;     // fast kernel: keep the column's raw bytes (4 rows per word) for the dp4a aggregates
+  bool presence = false;   // fast kernel: keep the optional column's presence bytes (1 = not NULL, 4 rows per word): "seen" counters
   int sub_stream = -1;     // fast kernel: stream of the column's sub-index (entry points of every 8th value), -1 = none
+  int nv_slot = -1;        // fast kernel, optional variable-length LEB128 column of <= 4 bytes: its values are decoded by VALUE ordinal
+                           // (the required-column decode) into a shared staging array and gathered per row; index of that array
 };
 
 struct DenseMap {
@@ -69,6 +73,7 @@ struct KernelShape {
                                // with atomics at L2 - for key ranges beyond the thread-private dense tier
   bool fast = false;   // all referenced columns are required: kernels/evq_scan_fast.cuh (4 consecutive rows per thread)
   int ngen = 0;        // fast kernel: LEB128 columns with leb_len >= 2 whose value boundaries are searched in the kernel
+  int nnv = 0;         // fast kernel: optional columns decoded through a staging array (ColSig::nv_slot)
   int filter_stream = -1;    // stream of the tables' external row filter (FastCSTableScan::setFilter), -1 = none
   bool use_subidx = false;   // fast kernel: variable-length columns take their decode entry points from Column::sub_index
   DenseMap dense;      // tier 1 with g1 > 1: the key -> slot map is baked into the kernel text as constants
@@ -136,7 +141,9 @@ struct evqgpu_query {
   uint64_t dt_cap = 0;
   std::vector<int> state_narrow;    // index into plane_sums, -1 otherwise
   std::vector<int> narrow_col;      // input columns whose raw bytes (4 rows per word) the kernel keeps next to the values
-  int nnarrow = 0;                  // byte planes over all plane sums: EVQ_NNARROW * EVQ_G1 u32 accumulators per thread
+  int nnarrow = 0;                  // byte planes over all plane sums: EVQ_NNARROW * EVQ_NG u32 accumulators per thread
+  int plane_groups = 0;             // EVQ_NG: groups the plane accumulators are kept for (the dense slots: <= 4 as a power of two,
+                                    // 5..7 exactly - nibble 7 of the quad selector means "row did not pass")
   // Byte-plane sums (codegen.cc: layout_narrow): sum(W * B) per group with W < 2^32 split into byte planes and B <= 255
   // (or absent), accumulated 4 rows at a time with dp4a: sum = SUM_p 256^p * dp4a(plane_p(W), B & mask_of_group)
   struct PlaneOperand {
@@ -145,6 +152,8 @@ struct evqgpu_query {
     int nplanes = 1;
     int swar = 0;                      // byte operand lit - col (1), lit + col (2) on the packed bytes of packed_col
     uint64_t swar_lit = 0;
+    int presence_col = -1;             // >= 0: the byte operand is the presence (1 = not NULL) of this optional column: the
+                                       // "seen" counters of min / max / mean over it
   };
   struct PlaneSum {
     int word = 0;                      // state word

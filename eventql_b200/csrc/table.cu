@@ -196,15 +196,19 @@ __global__ void k_minmax_bytes(const uint4* __restrict__ v, u64 n, unsigned long
 
 // variable-length LEB128 streams with a sub-index: one thread decodes the 8 values behind one sub-index entry
 // (sub == nullptr: every value is `ulen` bytes long)
+// (val_index != nullptr: an optional column - the tile holds val_index[tile + 1] - val_index[tile] values, the sub-index
+// entries count VALUES of the tile)
 __global__ void k_minmax_leb(const u8* __restrict__ data, const u64* __restrict__ off_index, const u16* __restrict__ sub, u32 ulen,
-                             u32 num_tiles, u64 num_rows, unsigned long long* __restrict__ out) {
+                             u32 num_tiles, u64 num_rows, const u64* __restrict__ val_index, unsigned long long* __restrict__ out) {
   const u64 idx = (u64) blockIdx.x * blockDim.x + threadIdx.x;
   const u64 tile = idx / (EVQ_TILE_ROWS / 8);
   const u32 g = (u32) (idx % (EVQ_TILE_ROWS / 8));
   u64 mx = 0, mn = ~0ull;
-  const u64 first = tile * EVQ_TILE_ROWS + 8ull * g;
-  if (tile < num_tiles && first < num_rows) {
-    const u32 nv = (u32) min((u64) 8, num_rows - first);
+  u64 tile_vals = 0;
+  if (tile < num_tiles)
+    tile_vals = val_index ? val_index[tile + 1] - val_index[tile] : min((u64) EVQ_TILE_ROWS, num_rows - tile * EVQ_TILE_ROWS);
+  if (8ull * g < tile_vals) {
+    const u32 nv = (u32) min((u64) 8, tile_vals - 8ull * g);
     const u8* p = data + off_index[tile] + (sub ? (u32) sub[tile * EVQ_SUB_ENTRIES + g * (8 / EVQ_SUB_GRAN)] : 8u * g * ulen);
     for (u32 i = 0; i < nv; ++i) {
       u64 x = 0;
@@ -573,13 +577,12 @@ void table_finish_column(evqgpu_table* t, Column& c) {
           EVQ_CUDA(cudaGetLastError());
           ctx->kernel_launches++;
         }
-        if (nullable) break;   // (the value-range pass below walks row-indexed groups: required columns only)
-        // ... which also make the exact value range one cheap pass (8 values per thread)
+        // ... which also make the exact value range one cheap pass (8 values per thread; of an optional column: its present values)
         EVQ_CUDA(cudaMemsetAsync(minmax.p, 0, 16, ctx->stream));
         const uint64_t groups = (uint64_t) ntiles * (EVQ_TILE_ROWS / 8);
         k_minmax_leb<<<(unsigned) ((groups + 255) / 256), 256, 0, ctx->stream>>>(
             c.data.buf.as<u8>(), c.off_index.as<u64>(), c.leb_uniform ? nullptr : c.sub_index.as<u16>(), c.leb_max_len, ntiles,
-            t->num_rows, minmax.as<unsigned long long>());
+            t->num_rows, nullable ? c.val_index.as<u64>() : nullptr, minmax.as<unsigned long long>());
         EVQ_CUDA(cudaGetLastError());
         ctx->kernel_launches++;
         read_minmax(nv > 0);
@@ -588,6 +591,7 @@ void table_finish_column(evqgpu_table* t, Column& c) {
     }
   }
   // NULLs read as value 0 wherever the tag is ignored
+  c.value_min_present = c.value_min;   // over the values that are in the data stream (what a decoder of the stream meets)
   if (nullable && c.num_values < t->num_rows) c.value_min = 0;
   c.loaded = true;
 }

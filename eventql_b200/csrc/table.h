@@ -50,6 +50,7 @@ struct Column {
   bool leb_uniform = false;    // LEB128: every value is leb_max_len bytes long (value i starts at byte i * leb_max_len: no sub-index)
   uint64_t value_max = ~0ull;  // statistic: largest value (exact for plain columns, 1-byte LEB128 and sub-indexed LEB128 columns; a bound otherwise)
   uint64_t value_min = 0;      // statistic: smallest value (exact for the same columns, 0 otherwise; 0 when NULLs are present)
+  uint64_t value_min_present = 0;   // ... over the non-NULL values only: bounds the encoded length of every value in the stream
   uint32_t data_tile_cap = 0;  // max bytes one tile copy of the data stream can need (multiple of 16)
   uint32_t level_tile_cap = 0;
   // flat string columns
