@@ -283,7 +283,8 @@ def referenced_columns(plan):
     return [n for i, n in enumerate(plan.input_columns) if i in seen]
 
 
-STRATEGY = {0: "scan-only", 1: "dense (registers/shared memory)", 2: "global hash table", 3: "direct-addressed group array (L2 atomics)"}
+STRATEGY = {0: "scan-only", 1: "dense (registers/shared memory)", 2: "global hash table", 3: "direct-addressed group array (L2 atomics)",
+            4: "global hash table, partitioned aggregation (records by home slot, one L2-resident table slice at a time)"}
 
 
 class Job:

@@ -768,6 +768,46 @@ static std::string gen_row_functions(const evqgpu_query& q, const KernelShape& s
   }
   os << "}\n";
 
+  // ---- partitioned aggregation: a row that passed WHERE as a record (the columns the keys and aggregate arguments read)
+  if (shape.part_bits > 0) {
+    const size_t nrec_cols = shape.rec_cols.size();
+    bool any_null = false;
+    for (int c : shape.rec_cols) any_null = any_null || shape.cols[c].nullable;
+    os << "__device__ __forceinline__ void evq_row_store(const EvqRow& row, u64* rec) {\n";
+    std::vector<std::string> words;
+    for (int c : shape.rec_cols) {
+      const std::string ct = fast_ctype(shape.cols[c]);
+      const std::string f = "row.c" + std::to_string(c);
+      words.push_back(ct == "f64" ? "evq_bits(" + f + ")" : "(u64) " + f);
+    }
+    if (any_null) {
+      std::string t = "0ull";
+      for (size_t j = 0; j < nrec_cols; ++j)
+        if (shape.cols[shape.rec_cols[j]].nullable) t += " | ((u64) row.t" + std::to_string(shape.rec_cols[j]) + " << " + std::to_string(j) + ")";
+      words.push_back(t);
+    }
+    if (words.size() == 2) {   // one 16-byte store
+      os << "  asm volatile(\"st.global.v2.u64 [%0], {%1, %2};\" :: \"l\"(rec), \"l\"(" << words[0] << "), \"l\"(" << words[1] << ") : \"memory\");\n";
+    } else {
+      for (size_t j = 0; j < words.size(); ++j) os << "  rec[" << j << "] = " << words[j] << ";\n";
+    }
+    os << "}\n";
+    os << "__device__ __forceinline__ void evq_row_load(const u64* rec, EvqRow& row) {\n";
+    if (words.size() == 2) {
+      os << "  u64 w0, w1;\n  asm volatile(\"ld.global.cs.v2.u64 {%0, %1}, [%2];\" : \"=l\"(w0), \"=l\"(w1) : \"l\"(rec));\n  const u64 w[2] = {w0, w1};\n";
+    } else {
+      os << "  u64 w[" << words.size() << "];\n";
+      for (size_t j = 0; j < words.size(); ++j) os << "  w[" << j << "] = __ldcs(rec + " << j << ");\n";
+    }
+    for (size_t j = 0; j < nrec_cols; ++j) {
+      const int c = shape.rec_cols[j];
+      const std::string ct = fast_ctype(shape.cols[c]);
+      os << "  row.c" << c << " = " << (ct == "f64" ? "evq_f64(w[" + std::to_string(j) + "])" : "(" + ct + ") w[" + std::to_string(j) + "]") << ";\n";
+      if (shape.cols[c].nullable) os << "  row.t" << c << " = (u32) (w[" << nrec_cols << "] >> " << j << ") & 1u;\n";
+    }
+    os << "  row.ord = 0;\n}\n";
+  }
+
   // ---- count_distinct: insert (group, value) into the set of the argument; the inserting thread counts it
   if (!q.distinct_args.empty() && (q.flags & EVQGPU_QUERY_GROUPBY)) {
     os << "#define EVQ_NDISTINCT " << q.distinct_args.size() << "\n";
@@ -1137,6 +1177,39 @@ static std::string gen_group_kernels(const evqgpu_query& q, const KernelShape& s
   os << "  const u64 slot = (u64) blockIdx.x * blockDim.x + threadIdx.x;\n  if (slot >= E.slots) return;\n";
   os << "  evq_emit_group(E, slot, E.dense_state);\n}\n";
 
+  // ---- partitioned aggregation, pass 2: the records of ONE partition into the group table.  All their home slots lie in
+  // one slice of the table (the partition is the top bits of the slot index), which stays L2-resident while the partition
+  // is processed: probes hit L2 and the aggregate updates are L2 atomics - the only HBM traffic is the sequential read of
+  // the records.  Two records per thread in flight (both first probes are issued before either is resolved).
+  if (shape.tier == 2 && shape.part_bits > 0) {
+    os << "struct EvqAggParams { EvqHashTable ht; const u64* part_buf; const u32* part_cursor; u64 part_cap; u32 nparts; u32 nseg; u32* status; u64* counters; u32* bar; u32 window; u32 pad; };\n";
+    os << "extern \"C\" __global__ void __launch_bounds__(256) evq_agg_part(const __grid_constant__ EvqAggParams A) {\n";
+    os << "  u32 err = 0;\n";
+    // ONE (cooperative: all CTAs resident) launch walks the partitions in order; a CTA takes whole segments (what one
+    // pass-1 CTA appended to the partition).  The CTAs stay within `window` partitions of each other - before partition p
+    // a CTA waits until every CTA is done with partition p - window (a counter every CTA bumps once per partition) - so
+    // that at most window + 1 table slices are being worked on: they stay L2-resident, and nobody idles at a barrier.
+    os << "  for (u32 part = 0; part < A.nparts; ++part) {\n";
+    os << "    if (part >= A.window) {\n      if (threadIdx.x == 0) {\n        const u32 need = (part - A.window + 1u) * gridDim.x;\n        u32 seen;\n"
+          "        do { asm volatile(\"ld.acquire.gpu.global.u32 %0, [%1];\" : \"=r\"(seen) : \"l\"(A.bar) : \"memory\"); if (seen < need) __nanosleep(200); } while (seen < need);\n"
+          "      }\n      __syncthreads();\n    }\n";
+    os << "    for (u32 seg = blockIdx.x; seg < A.nseg; seg += gridDim.x) {\n";
+    os << "      const u32 n = A.part_cursor[(u64) part * A.nseg + seg];\n";
+    os << "      const u64* base = A.part_buf + ((u64) part * A.nseg + seg) * A.part_cap * EVQ_NREC;\n";
+    os << "      for (u32 i = threadIdx.x; i < n; i += 4u * 256u) {\n";
+    os << "        EvqRow row[4];\n        u64 key[4][EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];\n        u64 fpv[4], slot[4], w0[4], w1[4];\n        bool have[4];\n";
+    os << "#pragma unroll\n        for (int j = 0; j < 4; ++j) {\n          have[j] = i + j * 256u < n;\n          fpv[j] = slot[j] = w0[j] = w1[j] = 0;\n"
+          "          if (have[j]) evq_row_load(base + (u64) (i + j * 256u) * EVQ_NREC, row[j]);\n        }\n";
+    os << "#pragma unroll\n        for (int j = 0; j < 4; ++j) {\n          if (have[j]) {\n            u32 ktag[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];\n"
+          "            evq_keys(row[j], key[j], ktag, err);\n            evq_ht_hash<EVQ_NKEYS>(A.ht, key[j], ktag, fpv[j], slot[j]);\n"
+          "            evq_ht_prefetch(A.ht, slot[j], w0[j], w1[j]);\n          }\n        }\n";
+    os << "#pragma unroll\n        for (int j = 0; j < 4; ++j) {\n          if (have[j]) {\n"
+          "            u64* sp = evq_ht_upsert_from<EVQ_NKEYS>(A.ht, key[j], fpv[j], slot[j], w0[j], w1[j], (u64*) 0);\n"
+          "            if (!sp) err |= EVQ_ERR_TABLE_FULL;\n            else evq_accumulate_global(row[j], sp + 1 + EVQ_NKEYS, err);\n          }\n        }\n      }\n    }\n"
+          "    __syncthreads();\n    if (threadIdx.x == 0) { __threadfence(); atomicAdd(A.bar, 1u); }\n  }\n";
+    os << "  if (err) atomicOr(A.status, err);\n}\n";
+  }
+
   // ---- the tail of a dense-tier execution: ONE kernel (one CTA) behind the scan launches that
   //   (1) multi-rank: pushes this rank's state words into every peer's exchange buffer over NVLink (P2P stores), raises its
   //       flag there, waits for the peers' flags and combines all ranks' words in rank order (GroupByMergeExpression,
@@ -1227,6 +1300,11 @@ std::string generate_source(const evqgpu_query& q, const KernelShape& shape_in) 
      << ((shape.nleb > 0 || shape.nnull > 0) ? 1 : 0) << "\n#define EVQ_MIN_CTAS " << shape.min_ctas << "\n#define EVQ_NGEN "
      << shape.ngen << "\n#define EVQ_GEN_CHUNKS " << gen_chunks(shape) << "\n#define EVQ_NNV " << shape.nnv << "\n#define EVQ_NNARROW " << q.nnarrow << "\n#define EVQ_NG " << std::max(1, q.plane_groups) << "\n#define EVQ_NSTATE_SMEM " << q.nstate_smem << "\n#define EVQ_NSTATE_ALL "
      << std::max<size_t>(1, q.state_ops.size()) << "\n";
+  if (shape.part_bits > 0) {
+    bool any_null = false;
+    for (int c : shape.rec_cols) any_null = any_null || shape.cols[c].nullable;
+    os << "#define EVQ_PARTITION 1\n#define EVQ_MAX_PARTS " << (1 << shape.part_bits) << "\n#define EVQ_NREC " << shape.rec_cols.size() + (any_null ? 1 : 0) << "\n";
+  }
   if (getenv("EVQGPU_DRYRUN")) os << "#define EVQ_DRYRUN 1\n";
   if (shape.fast) os << "#define EVQ_KT " << shape.kt << "\n";
   if (shape.filter_stream >= 0) os << "#define EVQ_FILTER_STREAM " << shape.filter_stream << "\n";

@@ -64,6 +64,18 @@ extern "C" int evqgpu_debug_generate(const evqgpu_query_desc* desc, const evqgpu
     uint64_t cubin_total = 0;
     for (int t : tiers) {
       s.tier = t;
+      s.part_bits = 0;
+      s.rec_cols.clear();
+      if (t == 4) {   // the hash tier as partitioned aggregation (64 record partitions)
+        s.tier = 2;
+        s.part_bits = 6;
+        std::vector<bool> used(q.input_columns.size(), false);
+        for (const auto& g : q.group) collect_columns(g.get(), used);
+        for (const auto& item : q.select)
+          if (item.agg) for (const auto& a : item.agg->args) collect_columns(a.get(), used);
+        for (size_t i = 0; i < used.size(); ++i)
+          if (used[i]) s.rec_cols.push_back((int) i);
+      }
       s.g1 = 1;
       if (t == 1 && !q.group.empty()) {
         s.g1 = 2;

@@ -30,6 +30,7 @@ typedef double f64;
 #define EVQ_ERR_TABLE_FULL 4u
 #define EVQ_ERR_SLOT_RANGE 8u
 #define EVQ_ERR_STAGE_OVERFLOW 16u
+#define EVQ_ERR_PART_FULL 64u      // partitioned aggregation: a record partition overflowed (heavily skewed keys)
 #define EVQ_ERR_PEER_TIMEOUT 32u   // the fused merge tail waited in vain for a peer rank's state
 
 #define EVQ_MAX_STREAMS 32
@@ -83,9 +84,19 @@ struct EvqScanParams {
   u8* out_cols[EVQ_MAX_STREAMS];    // pass 2: packed SVector output per select item
   // bookkeeping
   u32* status;                      // [0] error bits, [1] unused
-  u64* counters;                    // [0] rows passed, [1] groups claimed (tier 2)
+  u64* counters;                    // [0] rows passed
   u64 tile_row_base;                // first tile index of this table inside tile_counts
   u64 ord_base;                     // added to a row's ordinal (tile index * 1024 + row in tile): rank-major order of a multi-rank job
+  // partitioned aggregation (tier 2, groups far beyond L2): pass 1 writes the rows that pass WHERE as records into
+  // 2^part_bits partitions by the top bits of their home slot; pass 2 (evq_agg_part) aggregates one partition at a time,
+  // whose slice of the group table stays L2-resident
+  // Every CTA of pass 1 owns one segment of every partition, so appending needs no global atomics and no barriers: the
+  // position inside the segment comes from a shared-memory cursor.
+  u64* part_buf;                    // [2^part_bits][gridDim.x][part_cap][EVQ_NREC] record words
+  u32* part_cursor;                 // [2^part_bits][gridDim.x] records in every segment (written when the CTA is done)
+  u64 part_cap;                     // records per segment
+  u32 part_shift;                   // partition = home slot >> part_shift
+  u32 part_bits;
 };
 
 

@@ -504,11 +504,21 @@ __device__ __forceinline__ u64* evq_ht_upsert_from(const EvqHashTable& H, const 
     if (cur == 0) {
       cur = atomicCAS(s, 0ull, fpv | 2ull);
       if (cur == 0) {
+        if (NK == 1) {
+          // one key: the final fingerprint word and the key are the slot's first 16 aligned bytes - ONE vector store
+          // publishes both (a reader that saw the claiming bit spins on the fingerprint word and then finds the key of the
+          // same store), so no memory fence is needed: with ~every warp inserting some group while the table fills, a
+          // membar per insert stalled whole warps (4.4 stalled warps per issue in pass 2 of the partitioned aggregation)
+          asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" :: "l"(s), "l"(fpv), "l"(key[0]) : "memory");
+        } else {
 #pragma unroll
-        for (int i = 0; i < NK; ++i) evq_st_l2(s + 1 + i, key[i]);
-        __threadfence();
-        evq_st_l2(s, fpv);
-        atomicAdd(claimed_counter, 1ull);
+          for (int i = 0; i < NK; ++i) evq_st_l2(s + 1 + i, key[i]);
+          __threadfence();
+          evq_st_l2(s, fpv);
+        }
+        // (count_distinct: the inserting thread counts the new member of its group's set.  The GROUP table passes no
+        // counter: one atomic on ONE address per new group serialises at L2 - 10 M new groups took ~10 ms for it alone)
+        if (claimed_counter) atomicAdd(claimed_counter, 1ull);
         return s;
       }
       first = false;   // somebody else claimed it meanwhile: its keys must be (re)read

@@ -40,6 +40,9 @@ struct EvqFastScratch {
   // optional variable-length columns: the tile's present values, decoded by value ordinal (two tiles in flight)
   __align__(16) u32 nval[2][EVQ_NNV][EVQ_TILE_ROWS + 8];
 #endif
+#ifdef EVQ_PARTITION
+  u32 pcur[EVQ_MAX_PARTS];                                    // records this CTA has appended to its segment of every partition
+#endif
 };
 
 // ---- boundary search of a variable-length LEB128 column ------------------------------------------------------------------
@@ -647,6 +650,9 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
 #endif
 
   const u32 tid = threadIdx.x;
+#ifdef EVQ_PARTITION
+  for (u32 p = tid; p < EVQ_MAX_PARTS; p += EVQ_NTHREADS) scr->pcur[p] = 0u;
+#endif
   if (tid == 0) {
     for (int s = 0; s < EVQ_NSTAGES; ++s) {
       evq_mbar_init(&hdr->full[s], 1);
@@ -707,6 +713,9 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
 
 #if EVQ_NNULL > 0
   u32 nullbuf = 0;
+#endif
+#ifdef EVQ_PARTITION
+  const u32 pcur_sa = evq_smem_u32(&scr->pcur[0]);
 #endif
   u32 it = 0;
   for (u32 group = first_group; group < num_groups; group += group_step, ++it) {
@@ -816,6 +825,30 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
         }
       }
     }
+#elif EVQ_TIER == 2 && defined(EVQ_PARTITION)
+    // partitioned aggregation, pass 1: the rows that pass WHERE become records (the columns the keys and the aggregate
+    // arguments read), appended to the partition their group's home slot falls into.  This CTA owns one segment of every
+    // partition: the position comes from a shared-memory cursor (no global atomic, no barrier), and the records of one
+    // segment land next to each other, so L2 merges the 16-byte stores into full lines before they reach HBM.
+#pragma unroll
+    for (int k = 0; k < EVQ_RPT; ++k) {
+      EvqRow row;
+      evq_fast_row(cols, k, row);
+      const bool pass = ((u32) k < nvalid) && evq_where(row, err) && EVQ_ROW_KEPT(k);
+      if (pass) {
+        ++passed;
+        u64 key[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
+        u32 ktag[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
+        u64 fpv, slot;
+        evq_keys(row, key, ktag, err);
+        evq_ht_hash<EVQ_NKEYS>(P.ht, key, ktag, fpv, slot);
+        const u32 part = (u32) (slot >> P.part_shift);
+        u32 pos;   // (an explicit shared-memory atomic: through the generic pointer it went down the global-memory path)
+        asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(pcur_sa + 4u * part) : "memory");
+        if (pos < P.part_cap) evq_row_store(row, P.part_buf + (((u64) part * gridDim.x + blockIdx.x) * P.part_cap + pos) * EVQ_NREC);
+        else err |= EVQ_ERR_PART_FULL;
+      }
+    }
 #elif EVQ_TIER == 2
     // hash tier: the group table lives in HBM, every probe is a DRAM round trip.  Rows are handled in quads: first the
     // home slots of all 4 rows are computed and their first probes issued, then the rows are resolved and their
@@ -843,7 +876,7 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
       for (int kk = 0; kk < 4; ++kk) {
         if (pass[kk]) {
           ++passed;
-          u64* sp = evq_ht_upsert_from<EVQ_NKEYS>(P.ht, key[kk], fpv[kk], slot[kk], w0[kk], w1[kk], P.counters + 1);
+          u64* sp = evq_ht_upsert_from<EVQ_NKEYS>(P.ht, key[kk], fpv[kk], slot[kk], w0[kk], w1[kk], (u64*) 0);
           if (!sp) {
             err |= EVQ_ERR_TABLE_FULL;
           } else {
@@ -933,7 +966,7 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
         u64 key[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
         u32 ktag[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
         evq_keys(row, key, ktag, err);
-        u64* sp = evq_ht_upsert<EVQ_NKEYS>(P.ht, key, ktag, P.counters + 1);
+        u64* sp = evq_ht_upsert<EVQ_NKEYS>(P.ht, key, ktag, (u64*) 0);
         if (!sp) {
           err |= EVQ_ERR_TABLE_FULL;
         } else {
@@ -952,6 +985,13 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
   }
 
   // ===================== epilogue: merge this CTA's partial state =====================
+#ifdef EVQ_PARTITION
+  evq_cons_sync();   // all appends of this CTA are counted
+  for (u32 p = tid; p < (1u << P.part_bits); p += EVQ_NCONS) {
+    const u32 n = scr->pcur[p];
+    P.part_cursor[(u64) p * gridDim.x + blockIdx.x] = n < P.part_cap ? n : (u32) P.part_cap;
+  }
+#endif
 #if EVQ_TIER == 1
 #if EVQ_G1 > 1
   for (u32 g = 0; g < EVQ_G1; ++g) evq_state_flush_smem(sacc, g, tid, P.dense_state);

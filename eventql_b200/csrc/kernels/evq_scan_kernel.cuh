@@ -326,7 +326,7 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
         u64 key[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
         u32 ktag[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
         evq_keys(row, key, ktag, err);
-        u64* sp = evq_ht_upsert<EVQ_NKEYS>(P.ht, key, ktag, P.counters + 1);
+        u64* sp = evq_ht_upsert<EVQ_NKEYS>(P.ht, key, ktag, (u64*) 0);
         if (!sp) {
           err |= EVQ_ERR_TABLE_FULL;
         } else {

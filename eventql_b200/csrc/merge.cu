@@ -159,7 +159,7 @@ __global__ void k_merge_insert(EvqHashTable H, MergeOps mo, const u64* __restric
       key[k] = src[k];
       tag[k] = (u32) ((tags >> (8 * k)) & 0xffu);
     }
-    u64* sp = evq_ht_upsert<NK>(H, key, tag, counters + 1);
+    u64* sp = evq_ht_upsert<NK>(H, key, tag, (u64*) 0);
     if (!sp) {
       atomicOr(status, EVQ_ERR_TABLE_FULL);
       continue;

@@ -11,6 +11,7 @@
 #include <string.h>
 #include <algorithm>
 #include <cmath>
+#include <functional>
 
 using namespace evq;
 
@@ -195,8 +196,9 @@ static size_t scratch_bytes(const KernelShape& s) {
   const size_t nwarps = s.ncons / 32;
   if (s.fast) {   // EvqFastScratch
     const size_t ngen = std::max(1, s.ngen);
+    const size_t parts = s.part_bits > 0 ? ((size_t) 1 << s.part_bits) : 0;
     return round_up(4 * ngen * nwarps + 4 * ngen * (size_t) gen_chunks(s) + 4 * nwarps + 8 * std::max(1, s.nnull) * nwarps +
-                    (size_t) s.nnv * 2 * (EVQ_TILE_ROWS + 8) * 4 + 16, 128) + 128;
+                    (size_t) s.nnv * 2 * (EVQ_TILE_ROWS + 8) * 4 + 16 + parts * (2 * 4 + 2 * 8) + 16, 128) + 128;
   }
   const size_t one = 4 * std::max(1, s.nleb) * nwarps + 4 * std::max(1, s.nnull) * (EVQ_TILE_ROWS / 32) +
                      2 * std::max(1, s.nleb) * EVQ_TILE_ROWS + 4 * nwarps;
@@ -520,7 +522,9 @@ static void fit_shape(evqgpu_query& q, KernelShape& s, std::vector<TablePlan>& p
   fail(EVQGPU_ERR_UNSUPPORTED, "row tile of this query does not fit shared memory (%zu columns)", q.input_columns.size());
 }
 
-static void run_scan(evqgpu_query& q, const KernelShape& s, std::vector<TablePlan>& plans, EvqScanParams base) {
+static void run_scan(evqgpu_query& q, const KernelShape& s, std::vector<TablePlan>& plans, EvqScanParams base,
+                     const std::function<void(unsigned, uint64_t, EvqScanParams&)>& before_table = nullptr,
+                     const std::function<void(unsigned)>& after_table = nullptr) {
   evqgpu_ctx* ctx = q.ctx;
   cudaKernel_t kern = q.module->kernels.at("evq_scan");
   size_t max_smem = 0;
@@ -547,12 +551,14 @@ static void run_scan(evqgpu_query& q, const KernelShape& s, std::vector<TablePla
       EVQ_CUDA(cudaEventCreate(&e1));
       EVQ_CUDA(cudaEventRecord(e0, ctx->stream));
     }
+    if (before_table) before_table(grid, p.table->num_rows, P);
     launch(ctx, kern, dim3(grid), dim3(s.ncons + 32), p.smem, args);
+    q.stats.kernel_launches++;
+    if (after_table) after_table(grid);   // (partitioned aggregation: pass 2 belongs to the table's scan - and to its timing)
     if (e0) {
       EVQ_CUDA(cudaEventRecord(e1, ctx->stream));
       q.prof_events.push_back({e0, e1});
     }
-    q.stats.kernel_launches++;
   }
 }
 
@@ -930,10 +936,41 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
   }
   if ((s.tier == 1 && s.g1 > 1) || s.dense_global) s.dense = dm;
   layout_narrow(q, s);
+  // hash tier with a group table far beyond L2: partitioned aggregation.  Pass 1 (the scan) writes the rows that pass WHERE
+  // as records into 2^part_bits partitions by the top bits of their group's home slot; pass 2 aggregates one partition at a
+  // time, whose slice of the table (~24 MB) stays L2-resident - sequential record traffic instead of a random HBM sector pair
+  // (and its write-back) per row.  A partition that overflows (heavily skewed keys, for which the direct tier is the right
+  // one anyway: hot groups live in L2) makes the query fall back to the direct tier for good.
+  uint64_t ht_want = 0, part_cap = 0;
+  if (s.tier == 2 && !s.dense_global) {
+    ht_want = q.ht_cap;
+    if (ht_want == 0) {
+      uint64_t est = q.expected_groups ? q.expected_groups : std::min<uint64_t>(total_rows, 1ull << 26);
+      ht_want = next_pow2(std::max<uint64_t>(1024, est * 2));
+    }
+    const uint32_t stride = (uint32_t) round_up(1 + nk + q.state_ops.size(), 4);
+    const uint64_t table_bytes = ht_want * 8 * stride;
+    uint64_t slice = 32ull << 20, min_bytes = 128ull << 20;
+    if (const char* e = getenv("EVQGPU_PART_SLICE_MB")) slice = std::max<uint64_t>(1, strtoull(e, nullptr, 10)) << 20;
+    if (const char* e = getenv("EVQGPU_PART_MIN_MB")) min_bytes = strtoull(e, nullptr, 10) << 20;
+    if (s.fast && table_bytes >= min_bytes && q.distinct_args.empty() && !q.has_first && !q.no_partition && nk > 0 &&
+        !getenv("EVQGPU_NO_PARTITION")) {
+      int bits = 1;
+      while ((table_bytes >> bits) > slice && bits < 8) ++bits;
+      s.part_bits = bits;
+      std::vector<bool> used(q.input_columns.size(), false);
+      for (const auto& g : q.group) collect_columns(g.get(), used);
+      for (const auto& item : q.select)
+        if (item.agg) for (const auto& a : item.agg->args) collect_columns(a.get(), used);
+      for (size_t i = 0; i < used.size(); ++i)
+        if (used[i]) s.rec_cols.push_back((int) i);
+      part_cap = 1;   // (the segment capacity follows from every table's launch grid, see below)
+    }
+  }
   fit_shape(q, s, plans);
   q.shape = s;
   q.dense = dm;
-  q.stats.strategy = s.dense_global ? 3u : (uint32_t) s.tier;
+  q.stats.strategy = s.dense_global ? 3u : s.part_bits > 0 ? 4u : (uint32_t) s.tier;
 
   // ---- kernel text: everything the generated text depends on is summarised in a short signature, so that a repeated
   // execution (the common case: same plan, same partitions) skips spelling and hashing ~300 KB of source
@@ -941,8 +978,8 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
   {
     std::string sig;
     char buf[160];
-    snprintf(buf, sizeof(buf), "t%d g%d n%d s%d c%d f%d x%d N%d K%d|", s.tier, s.g1, s.ncons, s.nstages, s.min_ctas, (int) s.fast,
-             (int) s.use_subidx, q.nnarrow, s.kt * 1000 + (s.filter_stream + 1) * 10 + (int) s.dense_global);
+    snprintf(buf, sizeof(buf), "t%d g%d n%d s%d c%d f%d x%d N%d K%d P%d|", s.tier, s.g1, s.ncons, s.nstages, s.min_ctas, (int) s.fast,
+             (int) s.use_subidx, q.nnarrow, s.kt * 1000 + (s.filter_stream + 1) * 10 + (int) s.dense_global, s.part_bits);
     sig += buf;
     for (const auto& c : s.cols) {
       snprintf(buf, sizeof(buf), "%d.%u.%u.%d.%u.%u.%u%s.%d.%d.%d.%llu.%llu.%llu.%d;", (int) c.used, c.sql_type, c.kind, (int) c.nullable, c.dmax, c.bits,
@@ -962,6 +999,7 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
       q.kernel_source = generate_source(q, s);
       std::vector<std::string> names = {"evq_scan", "evq_init", "evq_emit"};
       if (s.tier == 1 && !s.dense_global) names.push_back("evq_tail");
+      if (s.part_bits > 0) names.push_back("evq_agg_part");
       q.module = jit_compile(ctx, q.kernel_source, names, &ms);
       q.module_sig = sig;
       if (ms > 0 && q.module->from_disk) q.stats.jit_disk_hits++;
@@ -1014,11 +1052,7 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
     ip.slots = slots;
     emit_slots = (s.g1 > 1 || s.dense_global) ? dm.slots : 1;
   } else {
-    uint64_t want = q.ht_cap;
-    if (want == 0) {
-      uint64_t est = q.expected_groups ? q.expected_groups : std::min<uint64_t>(total_rows, 1ull << 26);
-      want = next_pow2(std::max<uint64_t>(1024, est * 2));
-    }
+    const uint64_t want = ht_want;
     q.ht_cap = want;
     const uint32_t stride = (uint32_t) round_up(1 + nk + nstate, 4);   // whole 32-byte sectors; 8 words = one 64-byte DRAM atom
     ensure(q.ht_slots, want * 8 * stride);
@@ -1054,7 +1088,56 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
     }
   }
 
-  run_scan(q, s, plans, base);
+  if (s.part_bits > 0) {
+    const uint64_t parts = 1ull << s.part_bits;
+    bool any_null = false;
+    for (int c : s.rec_cols) any_null = any_null || s.cols[c].nullable;
+    const uint64_t nrec = s.rec_cols.size() + (any_null ? 1 : 0);
+    base.part_bits = (u32) s.part_bits;
+    u32 lg = 0;
+    while ((1ull << lg) < base.ht.cap) ++lg;
+    base.part_shift = lg - (u32) s.part_bits;
+    cudaKernel_t agg = q.module->kernels.at("evq_agg_part");
+    uint64_t seg_cap = 0;
+    // every CTA of the table's scan owns one segment of every partition; a segment takes the CTA's share of the rows
+    // (+ 30 % and a constant: the counts are binomial around rows / (grid * partitions)); more is an overflow -> fallback
+    auto before = [&](unsigned grid, uint64_t rows, EvqScanParams& P) {
+      seg_cap = rows / ((uint64_t) grid * parts) * 13 / 10 + 64;
+      ensure(q.part_buf, parts * grid * seg_cap * nrec * 8 + 256);
+      ensure(q.part_cursor, parts * grid * 4 + 512);   // (+ the pass-2 progress counter behind the segment counts)
+      P.part_buf = q.part_buf.as<u64>();
+      P.part_cursor = q.part_cursor.as<u32>();
+      P.part_cap = seg_cap;
+    };
+    auto after = [&](unsigned grid) {
+      AggParams ap;
+      memset(&ap, 0, sizeof(ap));
+      ap.ht = base.ht;
+      ap.part_buf = q.part_buf.as<u64>();
+      ap.part_cursor = q.part_cursor.as<u32>();
+      ap.part_cap = seg_cap;
+      ap.nparts = (u32) parts;
+      ap.nseg = grid;
+      ap.status = base.status;
+      ap.counters = base.counters;
+      ap.bar = (u32*) ((uint8_t*) q.part_cursor.p + round_up(parts * grid * 4, 256));
+      ap.window = 2;
+      if (const char* e = getenv("EVQGPU_AGG_WINDOW")) ap.window = (u32) std::max(1, atoi(e));
+      EVQ_CUDA(cudaMemsetAsync(ap.bar, 0, 4, ctx->stream));
+      // all CTAs must be resident (they wait for each other): a cooperative launch of at most what the device holds
+      int per_sm = 0;
+      EVQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*) agg, 256, 0));
+      unsigned g2 = (unsigned) ctx->sm_count * (unsigned) std::max(1, std::min(per_sm, 8));
+      if (const char* e = getenv("EVQGPU_AGG_CTAS")) g2 = (unsigned) ctx->sm_count * (unsigned) std::max(1, std::min(per_sm, atoi(e)));
+      void* args[] = {&ap};
+      EVQ_CUDA(cudaLaunchCooperativeKernel((const void*) agg, dim3(std::min(g2, grid)), dim3(256), args, 0, ctx->stream));
+      ctx->kernel_launches++;
+      q.stats.kernel_launches++;
+    };
+    run_scan(q, s, plans, base, before, after);
+  } else {
+    run_scan(q, s, plans, base);
+  }
 
   // ---- emit (deferred to evqgpu_query_merge for partial plans of a multi-rank job)
   q.emit_total_rows = total_rows;
@@ -1176,6 +1259,16 @@ void finish_query(evqgpu_query& q) {
   if (err & EVQ_ERR_STAGE_OVERFLOW) fail(EVQGPU_ERR_RUNTIME, "internal error: row tile larger than its pipeline stage");
   if (err & EVQ_ERR_SLOT_RANGE) fail(EVQGPU_ERR_RUNTIME, "internal error: group key outside the dense slot range");
   if (err & EVQ_ERR_PEER_TIMEOUT) fail(EVQGPU_ERR_RUNTIME, "merge: a peer rank did not deliver its partial aggregates (did every rank call evqgpu_query_merge?)");
+  if ((q.flags & EVQGPU_QUERY_GROUPBY) && (err & EVQ_ERR_PART_FULL)) {
+    // a record partition overflowed: the keys are heavily skewed, which the direct hash tier handles well (hot groups are
+    // L2-resident anyway).  Run again without partitioning - a retry local to this rank, no collective.
+    q.no_partition = true;
+    std::vector<evqgpu_table*> tables = q.tables;
+    int rc = evqgpu_query_enqueue(&q, tables.data(), (uint32_t) tables.size());
+    if (rc == EVQGPU_OK) rc = evqgpu_query_finish(&q);
+    if (rc != EVQGPU_OK) throw Error{rc, last_error()};
+    return;
+  }
   if (q.flags & EVQGPU_QUERY_GROUPBY) {
     if (err & EVQ_ERR_TABLE_FULL) {
       // grow the group table and run again (resize policy: double until it fits)

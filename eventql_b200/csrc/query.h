@@ -74,6 +74,8 @@ struct KernelShape {
   bool fast = false;   // all referenced columns are required: kernels/evq_scan_fast.cuh (4 consecutive rows per thread)
   int ngen = 0;        // fast kernel: LEB128 columns with leb_len >= 2 whose value boundaries are searched in the kernel
   int nnv = 0;         // fast kernel: optional columns decoded through a staging array (ColSig::nv_slot)
+  int part_bits = 0;   // tier 2, fast kernel: > 0 = partitioned aggregation with 2^part_bits record partitions (query.cu)
+  std::vector<int> rec_cols;   // ... the input columns a record carries (read by the GROUP BY expressions and aggregate arguments)
   int filter_stream = -1;    // stream of the tables' external row filter (FastCSTableScan::setFilter), -1 = none
   bool use_subidx = false;   // fast kernel: variable-length columns take their decode entry points from Column::sub_index
   DenseMap dense;      // tier 1 with g1 > 1: the key -> slot map is baked into the kernel text as constants
@@ -110,6 +112,21 @@ struct TailParams {
   u64* xbuf_peer[16];
   u64* flags_peer[16];
   u64* merged_out;     // EVQGPU_QUERY_WIRE / debugging: the merged state words, or null
+};
+
+// parameter block of pass 2 of the partitioned aggregation (mirrors the generated struct EvqAggParams)
+struct AggParams {
+  EvqHashTable ht;
+  const u64* part_buf;
+  const u32* part_cursor;
+  u64 part_cap;
+  u32 nparts;
+  u32 nseg;
+  u32* status;
+  u64* counters;
+  u32* bar;       // CTAs done per partition, summed (zeroed before the launch)
+  u32 window;     // partitions a CTA may run ahead of the slowest one
+  u32 pad;
 };
 
 struct InitParams {
@@ -175,6 +192,8 @@ struct evqgpu_query {
 
   // device state, reused across executions
   evq::DevBuf merge_recv, merge_send, merge_slots, merge_counts, merge_status;
+  evq::DevBuf part_buf, part_cursor;   // partitioned aggregation: the records of pass 1 and their per-partition counts
+  bool no_partition = false;           // a partition overflowed once (skewed keys): this query keeps the direct hash tier
   uint64_t merge_cap = 0;           // capacity the merged table last needed (kept across executions)
   evq::DevBuf dense_state, ht_slots, status, counters, out_count, tile_counts, tile_base;
   // dense tier: status / counters / row count live in one control block that the tail kernel publishes and re-arms

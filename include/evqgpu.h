@@ -461,7 +461,9 @@ typedef struct evqgpu_query_stats {
   uint64_t num_groups;
   uint32_t kernel_launches;      /* device kernels launched by the last execute */
   uint32_t strategy;             /* 0 scan-only, 1 register/shared-memory low-cardinality, 2 global hash table,
-                                    3 direct-addressed group array in global memory (key tuples spanning a small box) */
+                                    3 direct-addressed group array in global memory (key tuples spanning a small box),
+                                    4 global hash table filled by partitioned aggregation (records partitioned by home slot,
+                                    one L2-resident table slice at a time) */
   float jit_ms;                  /* time spent making the specialised kernel loadable in the last execute: NVRTC, or reading the
                                     cubin from the on-disk cache ($EVQGPU_CACHE_DIR, default ~/.cache/evqgpu); 0 = already loaded */
   float scan_ms;                 /* summed device time of the scan kernel launches since the last finish
@@ -505,7 +507,8 @@ typedef struct evqgpu_debug_column {
   uint64_t value_max;
 } evqgpu_debug_column;
 
-/* tier: 1 = dense / single group (dense_slots groups), 2 = global hash table; ignored for scan-only plans.
+/* tier: 1 = dense / single group (dense_slots groups), 2 = global hash table, 4 = global hash table filled by partitioned
+ * aggregation; ignored for scan-only plans.
  * src_out (may be NULL) receives the NUL-terminated kernel text when src_cap suffices; *src_len_out its length.
  * compile != 0 runs NVRTC; *cubin_bytes_out receives the cubin size. */
 EVQGPU_API int evqgpu_debug_generate(const evqgpu_query_desc* desc, const evqgpu_debug_column* columns, uint32_t tier,

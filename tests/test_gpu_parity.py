@@ -369,6 +369,53 @@ def test_first_row_items(gpu_ctx, tmp_path, shape):
             t.close()
 
 
+@pytest.mark.parametrize("variant", ["uniform", "two_keys_nullable", "skewed_falls_back"])
+def test_partitioned_hash_aggregation(gpu_ctx, tmp_path, monkeypatch, variant):
+    """Hash tier with a group table far beyond L2: pass 1 writes the passing rows as records into partitions by the top bits of
+    their group's home slot, pass 2 aggregates one partition (one L2-resident table slice) at a time.  Forced here on small
+    tables (EVQGPU_PART_MIN_MB / _SLICE_MB); a partition that overflows (every row the same key) falls back to the direct tier."""
+    monkeypatch.setenv("EVQGPU_PART_MIN_MB", "0")
+    monkeypatch.setenv("EVQGPU_PART_SLICE_MB", "1")
+    cnt = P.call("count", P.lit(1))
+    if variant == "uniform":
+        spec = T.events_spec(5000)
+        _sql, plan = T.q_highcard(spec, expected_groups=1 << 20)
+        sizes = (70_001, 33_000)
+    else:
+        spec = T.mixed_spec()
+        c, names = T.cols_of(spec)
+        if variant == "two_keys_nullable":
+            key = c["big"] / 1_000_003   # (spans far more than a direct-addressed array takes: the hash tier)
+            plan = P.QueryPlan(names, [key, c["k"], cnt, P.call("sum", c["a"]), P.call("min", c["f"]), P.call("max", c["d"]),
+                                       P.call("mean", c["big"])], where=c["b"] >= 1, group=[key, c["k"]], expected_groups=1 << 20)
+        else:
+            key = c["big"] * (c["b"] / 99)   # 0 for 99 % of the rows, a full-range value otherwise: one partition takes nearly all records
+            plan = P.QueryPlan(names, [key, cnt, P.call("sum", c["c"])], where=c["b"] >= 0, group=[key], expected_groups=1 << 20)
+        sizes = (50_000, 21_000)
+    files = []
+    for i, n in enumerate(sizes):
+        p = str(tmp_path / ("t%d.cst" % i))
+        T.write_table(p, spec, n, row_offset=i * 100_000)
+        files.append(p)
+    tables = [gpu_ctx.open_table_file(p) for p in files]
+    try:
+        q = gpu_ctx.query(plan)
+        try:
+            for _ in range(2):
+                q.execute(tables)
+                got = q.rows()
+                st = q.stats()
+        finally:
+            q.close()
+        want = O.run_query([O.read_cstable(p) for p in files], plan).rows()
+        compare(got, want, False)
+        assert st["strategy"] == (2 if variant == "skewed_falls_back" else 4), st
+        assert st["rows_passed"] == sum(r[1 if variant != "two_keys_nullable" else 2] for r in want)
+    finally:
+        for t in tables:
+            t.close()
+
+
 def test_order_by_large_result_properties(gpu_ctx):
     """ORDER BY over a 2 M-group result (hash tier): sortedness, stability across equal keys, permutation of the unsorted
     rows, LIMIT / OFFSET windows; multi-key and descending orders against numpy's lexsort."""
@@ -650,7 +697,7 @@ def test_highcard_10m_keys_properties(gpu_ctx):
     keys = np.ascontiguousarray(np.frombuffer(cols[0], dtype=np.uint8).reshape(ng, 9)[:, :8]).view("<u8").reshape(ng)
     cnt = np.ascontiguousarray(np.frombuffer(cols[1], dtype=np.uint8).reshape(ng, 9)[:, :8]).view("<u8").reshape(ng)
     sm = np.ascontiguousarray(np.frombuffer(cols[2], dtype=np.uint8).reshape(ng, 9)[:, :8]).view("<u8").reshape(ng)
-    assert stats["strategy"] == 2
+    assert stats["strategy"] in (2, 4)   # the hash tier, filled directly or by partitioned aggregation
     assert int(cnt.sum()) == n and len(np.unique(keys)) == ng
     assert 9_990_000 < ng <= 10_000_000          # 100 M draws cover all but ~450 of the 10 M keys
     assert np.isin(keys[:100000], T.splitmix64(np.arange(10_000_000, dtype=np.uint64))).all()
@@ -686,6 +733,6 @@ def test_timeseries_partition_properties(gpu_ctx):
         hashed, hstats = run_gpu(gpu_ctx, parts, plan)
     finally:
         del os.environ["EVQGPU_NO_DENSE_GLOBAL"]
-    assert hstats["strategy"] == 2 and sorted(hashed) == sorted(both)
+    assert hstats["strategy"] in (2, 4) and sorted(hashed) == sorted(both)
     for p in parts:
         p.close()
