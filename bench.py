@@ -420,7 +420,7 @@ def run_workload(job, name, steps, warmup, rows=0, parts=0, keep_tables=False, s
     per_launch = algo / parts
     achieved = per_launch / (scan_ms / 1000.0) / 1e9 if scan_ms > 0 else None
     passed = job.sum_over_ranks(int(stats["rows_passed"]))
-    groups = len(result_rows) if (world == 1 or stats["strategy"] in (1,)) else job.sum_over_ranks(len(result_rows))
+    groups = len(result_rows) if (world == 1 or stats["strategy"] in (1, 3)) else job.sum_over_ranks(len(result_rows))
     rec = {
         "workload": wl["desc"], "sql": sql, "value": total_rows * steps / (ms / 1000.0), "unit": "rows/s", "scaling": "weak",
         "ms_per_step": ms / steps, "steps": steps, "rows_per_gpu": rows_rank, "partitions_per_gpu": parts, "rows_per_partition": rows,
@@ -428,7 +428,9 @@ def run_workload(job, name, steps, warmup, rows=0, parts=0, keep_tables=False, s
         "gbs": algo * world * steps / (ms / 1000.0) / 1e9,
         "first_execute_ms": first_ms, "jit_ms_first_query": first["jit_ms"], "jit_from_disk_cache": bool(first["jit_disk_hits"]),
         "merge": "none (1 GPU)" if world == 1 else ("NCCL over NVLink inside every step: " +
-                                                    ("all-gather of the dense state + merge kernel" if stats["strategy"] == 1 else "hash repartition (all-to-all) + owner-side insert")),
+                                                    ("dense state over peer-mapped NVLink buffers, merged + emitted by the tail kernel" if stats["strategy"] == 1 else
+                                                     "ncclAllReduce(sum) of the direct-addressed group array" if stats["strategy"] == 3 else
+                                                     "hash repartition (all-to-all) + owner-side insert")),
         "roofline": {"bound": "hbm", "kernel": "evq_scan", "achieved": achieved, "peak": job.peak, "unit": "GB/s",
                      "frac": (achieved / job.peak) if achieved else None, "traffic": None,
                      "traffic_note": "not measured in this run (needs ncu); per-kernel dram__bytes are in profiles/*ncu*.txt",

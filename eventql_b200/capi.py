@@ -97,6 +97,7 @@ SYMBOLS = [
     "evqgpu_table_decode_string_column", "evqgpu_table_get_filter", "evqgpu_lsm_build_filters", "evqgpu_query_fetch_strings",
     "evqgpu_partial_cache_encode", "evqgpu_partial_cache_filename", "evqgpu_query_store_cache",
     "evqgpu_partial_frames_encode", "evqgpu_partial_rows_split", "evqgpu_partial_cache_decode", "evqgpu_partial_frames_decode",
+    "evqgpu_query_merge_rows", "evqgpu_query_merge_finish",
 ]
 
 _lib = None
@@ -160,6 +161,8 @@ def lib() -> C.CDLL:
     L.evqgpu_query_execute.argtypes = [vp, C.POINTER(vp), u32]
     L.evqgpu_query_enqueue.argtypes = [vp, C.POINTER(vp), u32]
     L.evqgpu_query_prepare.argtypes = [vp, C.POINTER(vp), u32]
+    L.evqgpu_query_merge_rows.argtypes = [vp, vp, C.POINTER(u64), C.POINTER(u64), u64]
+    L.evqgpu_query_merge_finish.argtypes = [vp]
     L.evqgpu_query_finish.argtypes = [vp]
     L.evqgpu_query_num_rows.argtypes = [vp, C.POINTER(u64)]
     L.evqgpu_query_fetch.argtypes = [vp, u64, u64, C.POINTER(vp), C.POINTER(u64)]
@@ -573,6 +576,23 @@ class Query:
 
     def execute(self, tables: Sequence[Table]):
         check(lib().evqgpu_query_execute(self._h, self._tables(tables), len(tables)))
+        return self
+
+    def merge_rows(self, rows):
+        """Coordinator plans (QUERY_COORDINATOR): feed partial rows [(20-byte key, saved states)] a shard returned."""
+        body = b"".join(k + d for k, d in rows)
+        starts, ends, pos = [], [], 0
+        for k, d in rows:
+            starts.append(pos)
+            pos += len(k) + len(d)
+            ends.append(pos)
+        n = len(rows)
+        buf = C.create_string_buffer(body, max(1, len(body)))
+        check(lib().evqgpu_query_merge_rows(self._h, C.cast(buf, C.c_void_p), (C.c_uint64 * max(1, n))(*starts), (C.c_uint64 * max(1, n))(*ends), n))
+        return self
+
+    def merge_finish(self):
+        check(lib().evqgpu_query_merge_finish(self._h))
         return self
 
     def prepare(self, tables: Sequence[Table]):

@@ -95,7 +95,35 @@ void layout_states(evqgpu_query& q, const KernelShape& shape) {
     return (int) q.state_keys.size() - 1;
   };
   word("rows", OP_ADD_U64);
+  if (q.coordinator) {
+    // the coordinator of a cluster GROUP BY merges SAVED states (one per select item, in the reference's formats): every item
+    // has words of its own - count / sum one word, min / max {value, seen}, mean {double sum, n} - and a non-aggregate item
+    // a first-row pair (below)
+    int i = 0;
+    for (auto& item : q.select) {
+      item.state0 = item.state_seen = item.state_carry = item.distinct = -1;
+      const std::string id = std::to_string(i++);
+      if (!item.agg) continue;
+      const FnInfo& fi = item.agg->info();
+      const int ty = fi.args.empty() ? EVQ_NIL : fi.args[0];
+      switch (fi.fn) {
+        case Fn::COUNT: item.state0 = word("c" + id, OP_ADD_U64); break;
+        case Fn::SUM: item.state0 = word("s" + id, fi.ret == EVQ_FLOAT64 ? OP_ADD_F64 : OP_ADD_U64); break;
+        case Fn::MIN:
+        case Fn::MAX:
+          item.state0 = word("m" + id, minmax_op(fi.fn, ty));
+          item.state_seen = word("seen" + id, OP_ADD_U64);
+          break;
+        case Fn::MEAN:
+          item.state0 = word("fsum" + id, OP_ADD_F64);
+          item.state_seen = word("n" + id, OP_ADD_U64);
+          break;
+        default: fail(EVQGPU_ERR_UNSUPPORTED, "aggregate %s has no partial state format", fi.symbol.c_str());
+      }
+    }
+  }
   for (auto& item : q.select) {
+    if (q.coordinator) break;
     item.state0 = item.state_seen = item.state_carry = item.distinct = -1;
     if (!item.agg) continue;
     const FnInfo& fi = item.agg->info();
@@ -1130,7 +1158,7 @@ static std::string gen_group_kernels(const evqgpu_query& q, const KernelShape& s
       const std::string s1 = "st[" + std::to_string(std::max(0, item.state_seen)) + "]";
       std::string val;
       switch (fi.fn) {
-        case Fn::COUNT: val = "st[0]"; break;                                       // count_get (aggregate.cc:40-42)
+        case Fn::COUNT: val = s0; break;                                            // count_get (aggregate.cc:40-42); word 0 = rows
         case Fn::COUNT_DISTINCT: val = s0; break;                                   // count_distinct_uint64_get
         case Fn::SUM: val = from_bits(s0, fi.ret); break;                           // sum_*_get
         case Fn::MIN:
@@ -1274,6 +1302,16 @@ static std::string gen_group_kernels(const evqgpu_query& q, const KernelShape& s
           "    for (int j = 0; j < 6; ++j) { c[8 + j] = c[j]; c[j] = 0ull; }\n    c[8 + 6] = nrows;\n    c[8 + 7] += 1ull;\n  }\n";
     os << "}\n";
   }
+  return os.str();
+}
+
+std::string generate_coordinator_source(const evqgpu_query& q) {
+  KernelShape shape;
+  shape.tier = 2;
+  std::ostringstream os;
+  os << "// generated by eventql_b200 csrc/codegen.cc - emit kernel of a coordinator (GroupByMergeExpression) query\n";
+  os << "#define EVQ_NCONS 256\n#define EVQ_NKEYS " << q.group.size() << "\n";
+  os << kSrcAbi << "\n" << kSrcPrelude << "\n" << gen_group_kernels(q, shape);
   return os.str();
 }
 

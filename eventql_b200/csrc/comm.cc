@@ -175,6 +175,26 @@ int evqgpu_comm_destroy(evqgpu_ctx* ctx) {
   });
 }
 
+int evqgpu_query_merge_rows(evqgpu_query* q, const void* base, const uint64_t* row_starts, const uint64_t* row_ends, uint64_t nrows) {
+  return guarded([&] {
+    if (!q || (nrows && (!base || !row_starts || !row_ends))) fail(EVQGPU_ERR_ARG, "evqgpu_query_merge_rows: null argument");
+    if (!q->coordinator) fail(EVQGPU_ERR_ARG, "evqgpu_query_merge_rows: the plan was not created with EVQGPU_QUERY_COORDINATOR");
+    if (q->state_ops.empty()) {
+      evq::KernelShape none;
+      evq::layout_states(*q, none);
+    }
+    evq::coordinator_parse_rows(*q, (const uint8_t*) base, row_starts, row_ends, nrows);
+  });
+}
+
+int evqgpu_query_merge_finish(evqgpu_query* q) {
+  return guarded([&] {
+    if (!q) fail(EVQGPU_ERR_ARG, "evqgpu_query_merge_finish: null query");
+    if (!q->coordinator) fail(EVQGPU_ERR_ARG, "evqgpu_query_merge_finish: the plan was not created with EVQGPU_QUERY_COORDINATOR");
+    evq::coordinator_finish(*q);
+  });
+}
+
 int evqgpu_query_merge(evqgpu_query* q) {
   return guarded([&] {
     if (!q) fail(EVQGPU_ERR_ARG, "evqgpu_query_merge: null query");
@@ -189,6 +209,10 @@ namespace evq {
 // Used by merge.cu
 void comm_all_gather(evqgpu_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank) {
   EVQ_NCCL(nccl().AllGather(send, recv, bytes_per_rank, ncclUint8, (ncclComm_t) ctx->nccl_comm, ctx->stream));
+}
+
+void comm_all_reduce_sum_u64(evqgpu_ctx* ctx, void* buf, size_t nwords) {
+  EVQ_NCCL(nccl().AllReduce(buf, buf, nwords, ncclUint64, ncclSum, (ncclComm_t) ctx->nccl_comm, ctx->stream));
 }
 
 // small host-side all-gather (bounds, counts): staged through device memory because NCCL moves device buffers

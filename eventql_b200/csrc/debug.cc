@@ -15,6 +15,20 @@ extern "C" int evqgpu_debug_generate(const evqgpu_query_desc* desc, const evqgpu
     if (!desc || !columns) fail(EVQGPU_ERR_ARG, "evqgpu_debug_generate: null argument");
     evqgpu_query q;
     query_intake(&q, desc);
+    if (q.coordinator) {   // the emit kernel of a coordinator (GroupByMergeExpression) query
+      KernelShape none;
+      layout_states(q, none);
+      const std::string src = generate_coordinator_source(q);
+      uint64_t cubin_total = 0;
+      if (compile) {
+        std::string log;
+        cubin_total = jit_compile_to_cubin(src, &log).size();
+      }
+      if (src_len_out) *src_len_out = src.size();
+      if (src_out && src_cap > src.size()) memcpy(src_out, src.c_str(), src.size() + 1);
+      if (cubin_bytes_out) *cubin_bytes_out = cubin_total;
+      return;
+    }
     KernelShape s;
     s.cols.resize(q.input_columns.size());
     for (size_t i = 0; i < q.input_columns.size(); ++i) {

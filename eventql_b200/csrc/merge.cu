@@ -333,6 +333,79 @@ static void merge_hash(evqgpu_query& q) {
   finish_query(q);
 }
 
+// ---- the coordinator of a cluster GROUP BY on the device (GroupByMergeExpression, groupby.cc:528-637) ---------------------
+// The shards' rows were parsed into merge records on the host (wire.cc coordinator_parse_rows: the states are varuints,
+// which only a sequential walk can delimit); here they are merged - the same owner-side insert kernel as the cross-GPU hash
+// merge, keyed by the three words of the 20-byte SHA-1 group key - and emitted through the plan's own emit kernel.
+void coordinator_finish(evqgpu_query& q) {
+  evqgpu_ctx* ctx = q.ctx;
+  use_device(ctx);
+  if (q.state_ops.empty()) {   // (no rows were ever fed: the layout is still to be made)
+    KernelShape none;
+    layout_states(q, none);
+  }
+  const MergeOps mo = merge_ops_of(q);
+  const uint64_t rec = 4 + (uint64_t) mo.nstate;
+  const uint64_t n = q.coord_nrecords;
+  if (!q.module) {
+    float ms = 0;
+    q.kernel_source = generate_coordinator_source(q);
+    q.module = jit_compile(ctx, q.kernel_source, {"evq_emit"}, &ms);
+    q.jit_ms_total += ms;
+  }
+  if (!q.status.p) q.status.alloc(16);
+  if (!q.counters.p) q.counters.alloc(32);
+  if (!q.out_count.p) q.out_count.alloc(8);
+  EVQ_CUDA(cudaMemsetAsync(q.status.p, 0, 16, ctx->stream));
+  EVQ_CUDA(cudaMemsetAsync(q.counters.p, 0, 32, ctx->stream));
+  DevBuf& recs = q.merge_recv;
+  if (recs.bytes < std::max<uint64_t>(n, 1) * rec * 8) recs.alloc(std::max<uint64_t>(n, 1) * rec * 8);
+  if (n) EVQ_CUDA(cudaMemcpyAsync(recs.p, q.coord_records.data(), n * rec * 8, cudaMemcpyHostToDevice, ctx->stream));
+  EvqHashTable M;
+  M.stride = (u32) round_up(1 + 3 + (uint64_t) mo.nstate, 4);
+  M.nkeys = 3;
+  uint64_t cap = next_pow2_(std::max<uint64_t>(1024, n * 2));
+  if (q.merge_status.bytes < 16) q.merge_status.alloc(16);
+  for (;;) {
+    if (q.merge_slots.bytes < cap * 8 * M.stride) q.merge_slots.alloc(cap * 8 * M.stride);
+    M.slots = q.merge_slots.as<u64>();
+    M.cap = cap;
+    k_merge_init<<<(unsigned) ((cap + 255) / 256), 256, 0, ctx->stream>>>(M, mo);
+    EVQ_CUDA(cudaGetLastError());
+    EVQ_CUDA(cudaMemsetAsync(q.merge_status.p, 0, 16, ctx->stream));
+    ctx->kernel_launches++;
+    if (!n) break;
+    launch_insert<3>(ctx, M, mo, recs.as<u64>(), n, q.counters.as<u64>(), q.merge_status.as<u32>());
+    EVQ_CUDA(cudaGetLastError());
+    ctx->kernel_launches++;
+    u32 mst = 0;
+    EVQ_CUDA(cudaMemcpyAsync(&mst, q.merge_status.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (!(mst & EVQ_ERR_TABLE_FULL)) break;
+    if (cap >= (1ull << 31)) fail(EVQGPU_ERR_NOMEM, "merged group table exceeds 2^31 slots");
+    cap *= 4;
+  }
+  q.shape = KernelShape();
+  q.shape.tier = 2;
+  q.use_tail = false;
+  memset(&q.emit, 0, sizeof(q.emit));
+  q.emit.ht = M;
+  q.emit.slots = cap;
+  q.emit_total_rows = std::max<uint64_t>(n, 1);
+  q.stats = evqgpu_query_stats();
+  q.stats.strategy = 2;
+  q.stats.rows_scanned = n;
+  q.reordered = false;
+  q.tables.clear();
+  emit_results(q);
+  q.pending = true;
+  finish_query(q);
+  q.merged = true;
+  q.coord_records.clear();
+  q.coord_records.shrink_to_fit();
+  q.coord_nrecords = 0;
+}
+
 void merge_query(evqgpu_query& q) {
   if (!(q.flags & EVQGPU_QUERY_GROUPBY)) fail(EVQGPU_ERR_ARG, "evqgpu_query_merge: not an aggregate plan");
   if (q.tables.empty()) fail(EVQGPU_ERR_ARG, "evqgpu_query_merge: the query has not been executed");
@@ -353,8 +426,17 @@ void merge_query(evqgpu_query& q) {
     fail(EVQGPU_ERR_UNSUPPORTED, "evqgpu_query_merge: string GROUP BY keys cannot be merged across ranks");
   // (the ranks agreed on the aggregation strategy, the slot assignment and the state layout in evqgpu_query_prepare,
   // one unconditional collective; nothing here decides per rank whether to enter a collective)
-  if (q.shape.tier == 1) merge_dense(q);
-  else merge_hash(q);
+  if (q.shape.tier == 1) {
+    merge_dense(q);
+  } else if (q.shape.dense_global) {
+    // direct-addressed group array (the ranks agreed on the key box in evqgpu_query_prepare; every word is a wrapping
+    // 64-bit sum): one all-reduce over NVLink, in place; every rank ends with the full result
+    comm_all_reduce_sum_u64(q.ctx, q.dense_base, q.emit.slots * q.state_ops.size());
+    emit_results(q);
+    q.pending = true;
+  } else {
+    merge_hash(q);
+  }
   q.merged = true;
 }
 

@@ -321,7 +321,24 @@ void query_intake(evqgpu_query* q, const evqgpu_query_desc* desc) {
         if (find_aggregate(a.get())) fail(EVQGPU_ERR_ARG, "nested aggregate call");
     q->select.push_back(std::move(item));
   }
-  if (groupby)
+  if (desc->flags & EVQGPU_QUERY_COORDINATOR) {
+    // the coordinator of a cluster GROUP BY (GroupByMergeExpression): nothing is scanned.  Groups are identified by the 20-byte
+    // SHA-1 keys the shards send - three pseudo key words - and every non-aggregate item arrives as a value with each row
+    if (!groupby) fail(EVQGPU_ERR_ARG, "EVQGPU_QUERY_COORDINATOR needs an aggregate plan");
+    q->coordinator = true;
+    q->group.clear();
+    for (uint32_t i = 0; i < 3; ++i) {
+      evqgpu_insn in;
+      memset(&in, 0, sizeof(in));
+      in.op = EVQ_X_LITERAL;
+      in.type = EVQ_UINT64;
+      in.imm = 0x5348413100000000ull + i;   // distinct signatures that no select item can spell
+      evqgpu_expr e = {&in, 1, nullptr, 0};
+      q->group.push_back(parse_program(e));
+    }
+    for (auto& item : q->select)
+      if (!item.agg) { item.first = true; q->has_first = true; }
+  } else if (groupby)
     for (auto& item : q->select)
       if (!item.agg && !is_function_of_keys(*q, item.expr.get())) {
         if (item.is_string) fail(EVQGPU_ERR_UNSUPPORTED, "a string select item of an aggregate plan must be a GROUP BY key");
@@ -928,7 +945,13 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
         // too many groups for thread-private state, but the key tuples span a small box: a direct-addressed group
         // array in global memory (no keys, no probing), which stays L2-resident up to a few million groups.  A
         // multi-rank job keeps the hash tier: its merge moves groups, not boxes.
-        dense_global = dm.slots * q.state_ops.size() * 8 <= (1ull << 30) && !((q.flags & EVQGPU_QUERY_PARTIAL) && ctx->nranks > 1) &&
+        // In a multi-rank job the array is merged with ONE ncclAllReduce(sum) over all its words (merge.cu), which is
+        // exact when every word is a wrapping 64-bit sum / count: no min / max / double words, no carry words, no first-row pairs.
+        bool all_add = true;
+        for (size_t w = 0; w < q.state_ops.size(); ++w)
+          all_add = all_add && q.state_ops[w] == OP_ADD_U64 && q.state_carry_of[w] < 0 && q.state_keys[w].compare(0, 3, "cd:") != 0;
+        const bool multi = (q.flags & EVQGPU_QUERY_PARTIAL) && ctx->nranks > 1;
+        dense_global = dm.slots * q.state_ops.size() * 8 <= (1ull << 30) && (!multi || (all_add && !getenv("EVQGPU_NO_DENSE_GLOBAL_MERGE"))) &&
                        !getenv("EVQGPU_NO_DENSE_GLOBAL");
       }
     }
@@ -1302,6 +1325,7 @@ int evqgpu_query_enqueue(evqgpu_query* q, evqgpu_table* const* tables, uint32_t 
   return guarded([&] {
     if (!q || (!tables && ntables)) fail(EVQGPU_ERR_ARG, "evqgpu_query_enqueue: null argument");
     if (ntables == 0) fail(EVQGPU_ERR_ARG, "evqgpu_query_enqueue: no tables");
+    if (q->coordinator) fail(EVQGPU_ERR_ARG, "a coordinator query scans nothing: feed it with evqgpu_query_merge_rows");
     use_device(q->ctx);
     q->tables.assign(tables, tables + ntables);
     const uint64_t keep_cap = q->ht_cap;

@@ -188,6 +188,9 @@ struct evqgpu_query {
   std::vector<bool> col_is_string;   // plan input columns read as dictionary codes of a string column (strings.cu)
   bool string_keys = false;          // a GROUP BY expression is a string column
   bool has_first = false;            // some select item takes the value of its group's first row (SelectItem::first)
+  bool coordinator = false;          // EVQGPU_QUERY_COORDINATOR: no scan; merges shards' partial rows (merge.cu coordinator_*)
+  std::vector<uint64_t> coord_records;   // parsed rows: [3 key words][tag word][state words], kept until merge_finish
+  uint64_t coord_nrecords = 0;
   u64* dense_base = nullptr;         // dense_state, offset by one word where that makes the first-row pairs 16-byte aligned
 
   // device state, reused across executions
@@ -238,6 +241,7 @@ struct evqgpu_query {
 namespace evq {
 // codegen.cc
 std::string generate_source(const evqgpu_query& q, const KernelShape& shape);
+std::string generate_coordinator_source(const evqgpu_query& q);   // evq_emit over a table keyed by the 20-byte group keys
 void layout_states(evqgpu_query& q, const KernelShape& shape);
 void layout_narrow(evqgpu_query& q, const KernelShape& shape);   // after tier / g1 are known
 int gen_chunks(const KernelShape& shape);
@@ -248,9 +252,13 @@ void launch_tail(evqgpu_query& q, bool merge);
 void finish_query(evqgpu_query& q);
 // merge.cu
 void merge_query(evqgpu_query& q);
+void coordinator_finish(evqgpu_query& q);
+// wire.cc
+void coordinator_parse_rows(evqgpu_query& q, const uint8_t* base, const uint64_t* row_starts, const uint64_t* row_ends, uint64_t nrows);
 // comm.cc
 std::vector<uint64_t> comm_all_gather_host(evqgpu_ctx* ctx, const std::vector<uint64_t>& mine);   // [rank][mine.size()]
 void comm_all_gather(evqgpu_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank);
+void comm_all_reduce_sum_u64(evqgpu_ctx* ctx, void* buf, size_t nwords);   // in place
 void comm_all_to_all(evqgpu_ctx* ctx, const void* send, const uint64_t* send_off, const uint64_t* send_bytes, void* recv,
                      const uint64_t* recv_off, const uint64_t* recv_bytes);
 }  // namespace evq

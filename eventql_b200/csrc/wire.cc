@@ -296,6 +296,79 @@ static void skip_states(const evqgpu_query& q, const uint8_t* p, uint64_t n, uin
   }
 }
 
+// one shard row -> one merge record [3 key words][tag word][state words in the coordinator layout]: loadInstanceState of
+// every select item (groupby.cc:577-612), SValue::decode for the others (svalue.cc:311-315)
+static void parse_row(const evqgpu_query& q, const uint8_t* p, uint64_t n, uint64_t arrival, uint64_t* rec) {
+  const size_t nstate = q.state_ops.size();
+  if (n < 20) fail(EVQGPU_ERR_FORMAT, "partial rows: truncated group key");
+  rec[0] = rec[1] = rec[2] = rec[3] = 0;
+  memcpy(&rec[0], p, 8);
+  memcpy(&rec[1], p + 8, 8);
+  memcpy(&rec[2], p + 16, 4);
+  uint64_t* st = rec + 4;
+  for (size_t w = 0; w < nstate; ++w) {   // the merge kernel skips identities
+    switch (q.state_ops[w]) {
+      case OP_MIN_U64: case OP_FIRST_ORD: st[w] = ~0ull; break;
+      case OP_MIN_I64: st[w] = 0x7fffffffffffffffull; break;
+      case OP_MAX_I64: st[w] = 0x8000000000000000ull; break;
+      case OP_MIN_F64: st[w] = 0x7ff0000000000000ull; break;
+      case OP_MAX_F64: st[w] = 0xfff0000000000000ull; break;
+      default: st[w] = 0; break;
+    }
+  }
+  uint64_t pos = 20;
+  auto raw8 = [&]() -> uint64_t {
+    if (n - pos < 8) fail(EVQGPU_ERR_FORMAT, "partial rows: truncated state");
+    uint64_t v;
+    memcpy(&v, p + pos, 8);
+    pos += 8;
+    return v;
+  };
+  for (const auto& item : q.select) {
+    if (!item.agg) {
+      if (pos >= n) fail(EVQGPU_ERR_FORMAT, "partial rows: truncated value");
+      const uint8_t type = p[pos++];
+      const uint64_t len = get_varuint(p, n, pos);
+      if (len > n - pos) fail(EVQGPU_ERR_FORMAT, "partial rows: truncated value");
+      const uint64_t want = item.expr->type == EVQ_BOOL ? 2 : 9;
+      if (type != (uint8_t) item.expr->type || len != want)
+        fail(EVQGPU_ERR_FORMAT, "partial rows: a value of type %u / %llu bytes where the plan has type %u", type, (unsigned long long) len, item.expr->type);
+      uint64_t v = 0;
+      memcpy(&v, p + pos, want - 1);
+      const uint64_t tag = p[pos + want - 1] & 1u;
+      pos += len;
+      st[item.state_first] = (arrival << 1) | tag;
+      st[item.state_first + 1] = tag ? 0 : v;
+      continue;
+    }
+    const FnInfo& fi = item.agg->info();
+    switch (fi.fn) {
+      case Fn::COUNT: st[item.state0] = get_varuint(p, n, pos); break;
+      case Fn::SUM: st[item.state0] = fi.ret == EVQ_FLOAT64 ? raw8() : get_varuint(p, n, pos); break;
+      case Fn::MIN:
+      case Fn::MAX: {
+        const uint64_t v = raw8(), have = raw8();
+        if (have) { st[item.state0] = v; st[item.state_seen] = 1; }
+        break;
+      }
+      case Fn::MEAN: st[item.state0] = raw8(); st[item.state_seen] = raw8(); break;
+      default: fail(EVQGPU_ERR_UNSUPPORTED, "aggregate %s has no partial state format", fi.symbol.c_str());
+    }
+  }
+  if (pos != n) fail(EVQGPU_ERR_FORMAT, "partial rows: %llu bytes behind the last state of a row", (unsigned long long) (n - pos));
+}
+
+void coordinator_parse_rows(evqgpu_query& q, const uint8_t* base, const uint64_t* row_starts, const uint64_t* row_ends, uint64_t nrows) {
+  const size_t rec = 4 + q.state_ops.size();
+  const size_t at = q.coord_records.size();
+  q.coord_records.resize(at + nrows * rec);
+  for (uint64_t i = 0; i < nrows; ++i) {
+    if (row_ends[i] < row_starts[i]) fail(EVQGPU_ERR_ARG, "evqgpu_query_merge_rows: row %llu ends before it starts", (unsigned long long) i);
+    parse_row(q, base + row_starts[i], row_ends[i] - row_starts[i], q.coord_nrecords + i, &q.coord_records[at + i * rec]);
+  }
+  q.coord_nrecords += nrows;
+}
+
 static void split_rows(const evqgpu_query& q, const uint8_t* body, uint64_t n, uint64_t base, uint64_t expect_rows, bool exact,
                        std::vector<uint64_t>& starts) {
   uint64_t pos = 0, rows = 0;

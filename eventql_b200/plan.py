@@ -26,6 +26,7 @@ X_CALL, X_LITERAL, X_INPUT, X_IF = 1, 3, 4, 6
 QUERY_GROUPBY = 1
 QUERY_PARTIAL = 2
 QUERY_WIRE = 4        # groups are fetched as PartialGroupByExpression rows (Query.fetch_partial)
+QUERY_COORDINATOR = 8  # the coordinator side of a cluster GROUP BY: no scan, fed with shards' partial rows (Query.merge_rows)
 
 # cstable enums (io/cstable/cstable.h:112-130)
 COL_SUBRECORD, COL_BOOLEAN, COL_UNSIGNED_INT, COL_SIGNED_INT, COL_STRING, COL_FLOAT, COL_DATETIME = range(7)

@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define EVQGPU_ABI_VERSION 4
+#define EVQGPU_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define EVQGPU_API __attribute__((visibility("default")))
@@ -318,6 +318,9 @@ EVQGPU_API int evqgpu_function_is_aggregate(int function_id);
 #define EVQGPU_QUERY_WIRE 4u          /* aggregate plan whose groups are fetched in the reference's partial-aggregation row format
                                          (evqgpu_query_fetch_partial): group key hashes and raw states are kept besides the rows */
 
+#define EVQGPU_QUERY_COORDINATOR 8u   /* aggregate plan that scans nothing: the coordinator side of a cluster GROUP BY
+                                         (GroupByMergeExpression), fed with the shards' partial rows - evqgpu_query_merge_rows */
+
 typedef struct evqgpu_query_desc {
   uint32_t struct_size;                 /* sizeof(evqgpu_query_desc) */
   uint32_t flags;                       /* EVQGPU_QUERY_* */
@@ -436,6 +439,21 @@ EVQGPU_API int evqgpu_partial_cache_decode(const evqgpu_query_desc* desc, const 
 EVQGPU_API int evqgpu_partial_frames_decode(const evqgpu_query_desc* desc, const void* frames, uint64_t nbytes,
                                             uint64_t* row_offsets, uint64_t cap_rows, uint64_t* nrows_out, uint64_t* nframes_out,
                                             int* end_of_request_out);
+
+/* The coordinator's side on the device: csql::GroupByMergeExpression (sql/statements/select/groupby.cc:528-637).  `q` is created
+ * from the partial GROUP BY plan the shards ran, with EVQGPU_QUERY_GROUPBY | EVQGPU_QUERY_COORDINATOR; it scans no table.
+ * evqgpu_query_merge_rows hands it rows a shard - the reference's CPU PartialGroupByExpression or a GPU shard's
+ * evqgpu_query_fetch_partial - returned: row i is bytes [row_starts[i], row_ends[i]) of `base`, 20 bytes of SHA-1 group key +
+ * the saved states of the select items (what evqgpu_partial_rows_split / _cache_decode / _frames_decode locate; for the first
+ * two pass row_offsets and row_offsets + 1).  The states are parsed (loadInstanceState, groupby.cc:577-612; SValue::decode for
+ * non-aggregate items) and kept.  evqgpu_query_merge_finish merges them on the device - a hash table keyed by the 20-byte
+ * group key, the aggregates' merge functions as atomics (count / sum: +, min / max over the seen ones, mean: sums and counts
+ * add; a non-aggregate item: the first row's value - all rows of a group carry the same one when it is a function of the
+ * key) - and evaluates every select item's `get` side per group; the rows are then fetched like any result
+ * (evqgpu_query_num_rows / _fetch / _order_by / _limit).  count_distinct has no partial state format and is refused. */
+EVQGPU_API int evqgpu_query_merge_rows(evqgpu_query* q, const void* base, const uint64_t* row_starts, const uint64_t* row_ends,
+                                       uint64_t nrows);
+EVQGPU_API int evqgpu_query_merge_finish(evqgpu_query* q);
 
 /* ORDER BY over the result rows of an executed (and, for multi-rank jobs, merged) query, on the device:
  * csql::OrderByExpression (sql/statements/select/orderby.cc:58-160) with sort expressions that are columns of the

@@ -49,6 +49,8 @@ def main():
                                                        group=[c["b"] % 3])))
     cases.append(("first_row_hash", spec, P.QueryPlan(names, [c["c"] % 5003, P.call("count", P.lit(1)), c["a"], c["k"]], where=c["b"] >= 0,
                                                       group=[c["c"] % 5003], expected_groups=1 << 25)))
+    spec = T.readings_spec(0)
+    cases.append(("timeseries_direct_addressed", spec, T.q_timeseries(spec, expected_groups=1_440_000)[1]))
     failures = []
 
     # ---- collectives are never entered on a per-rank decision (evqgpu_query_prepare)
@@ -116,8 +118,8 @@ def main():
                 v = v.view(np.float64) if st == P.FLOAT64 else (v.astype(bool) if st == P.BOOL else v)
                 cols.append(O.Vec(st, v, np.concatenate(ns).astype(np.uint8)))
             want = O.run_query_on(cols, n, plan).rows()
-            if stats["strategy"] == 1:
-                got_sets = gathered            # dense tier: every rank ends with the full result
+            if stats["strategy"] in (1, 3):
+                got_sets = gathered            # dense tiers: every rank ends with the full result
             else:
                 got_sets = [sum(gathered, [])]  # hash tier: results stay distributed, each group on exactly one rank
             for got in got_sets:

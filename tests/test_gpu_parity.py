@@ -505,6 +505,60 @@ def test_partial_rows_equal_reference_engine(gpu_ctx, case):
     compare(rows, O.run_query([f], plan).rows(), False)
 
 
+@pytest.mark.parametrize("case", T.partial_cases(), ids=[c[0] for c in T.partial_cases()])
+def test_coordinator_merges_cpu_shard_rows_on_the_device(gpu_ctx, case):
+    """The coordinator's side (GroupByMergeExpression, groupby.cc:528-637) on the device: the partial rows the REFERENCE's CPU
+    PartialGroupByExpression returned for two partitions (tests/golden/ref_partial.json) are parsed (loadInstanceState /
+    SValue::decode), merged in a device hash table keyed by the 20-byte group keys and emitted - equal to the rows the
+    reference engine returns on the table that holds both partitions, and to the oracle's restatement of the merge.  Also a
+    mixed cluster: one shard's rows from the CPU reference, the other's from a GPU shard (evqgpu_query_fetch_partial)."""
+    import json
+    name, _sql, plan = case
+    with open(os.path.join(GOLD, "ref_partial.json")) as fh:
+        g = json.load(fh)["cases"][name]
+    rows_a = [(bytes.fromhex(k), bytes.fromhex(d)) for k, d in g["rows"]]
+    rows_b = [(bytes.fromhex(k), bytes.fromhex(d)) for k, d in g["merge"]["rows_b"]]
+    want = T.parse_ref_rows(g["merge"]["whole_table_rows"], g["merge"]["types"])
+    cplan = P.QueryPlan(plan.input_columns, plan.select, where=plan.where, group=plan.group, flags=P.QUERY_GROUPBY | P.QUERY_COORDINATOR)
+    q = gpu_ctx.query(cplan)
+    try:
+        # (the rows arrive the way a coordinator gets them: as QUERY_PARTIALAGGR_RESULT frames, located with the plan)
+        frames = capi.partial_frames_encode(rows_a, 4096)
+        located = capi.partial_frames_decode(plan, frames)
+        assert located[0] == rows_a
+        q.merge_rows(rows_a)
+        q.merge_rows(rows_b)
+        q.merge_finish()
+        got = q.rows()
+        assert q.stats()["rows_scanned"] == len(rows_a) + len(rows_b)
+        # ... and again with the same query object, shards in the other order
+        q.merge_rows(rows_b)
+        q.merge_rows(rows_a)
+        q.merge_finish()
+        again = q.rows()
+    finally:
+        q.close()
+    compare(got, want, False)
+    compare(again, want, False)
+    compare(got, O.merge_partial_rows(plan, [rows_a, rows_b]), False)
+    # mixed cluster: partition A scanned by a GPU shard, partition B's rows from the CPU reference
+    path = T.golden_table_path("mixed")
+    tbl = gpu_ctx.open_table_file(path)
+    shard = gpu_ctx.query(plan)
+    q = gpu_ctx.query(cplan)
+    try:
+        shard.execute([tbl])
+        q.merge_rows(shard.fetch_partial())
+        q.merge_rows(rows_b)
+        q.merge_finish()
+        mixed = q.rows()
+    finally:
+        q.close()
+        shard.close()
+        tbl.close()
+    compare(mixed, want, False)
+
+
 def test_partial_rows_need_the_wire_flag(gpu_ctx):
     spec = T.lineitem_spec()
     tbl = gpu_ctx.synthesize(5000, spec)
