@@ -432,6 +432,7 @@ void merge_query(evqgpu_query& q) {
     // direct-addressed group array (the ranks agreed on the key box in evqgpu_query_prepare; every word is a wrapping
     // 64-bit sum): one all-reduce over NVLink, in place; every rank ends with the full result
     comm_all_reduce_sum_u64(q.ctx, q.dense_base, q.emit.slots * q.state_ops.size());
+    q.emit_total_rows = q.emit.slots;   // (the merged groups are bounded by the box, not by THIS rank's rows)
     emit_results(q);
     q.pending = true;
   } else {
