@@ -42,7 +42,11 @@ const std::vector<FnInfo>& function_table() {
       reg("eq", Fn::EQ, B, {ty, ty});
       reg("neq", Fn::NEQ, B, {ty, ty});
     }
-    for (int ty : {U, I, F, T}) {
+    // string ordering comparisons (boolean.cc:439-710) and startswith / endswith (expressions/string.cc:52-74) between a
+    // string column and a literal: evaluated once per dictionary entry, the rows read the verdict of their value's code
+    reg("startswith", Fn::STARTSWITH, B, {S, S});
+    reg("endswith", Fn::ENDSWITH, B, {S, S});
+    for (int ty : {U, I, F, T, S}) {
       reg("lt", Fn::LT, B, {ty, ty});
       reg("lte", Fn::LTE, B, {ty, ty});
       reg("gt", Fn::GT, B, {ty, ty});

@@ -12,6 +12,7 @@ namespace evq {
 enum class Fn {
   // pure functions (sql/expressions/{boolean,math,conversion,datetime}.cc)
   LOGICAL_AND, LOGICAL_OR, NEG, CMP, EQ, NEQ, LT, LTE, GT, GTE,
+  STARTSWITH, ENDSWITH,   // (string predicates: evaluated once per dictionary entry, query.cu lower_strings)
   ADD, SUB, MUL, DIV, MOD, POW,
   TO_NIL, TO_INT64, TO_TIMESTAMP64, FROM_TIMESTAMP, DATE_TRUNC,
   // aggregates (sql/expressions/aggregate.cc + oracle/ref_tools/ext_aggregates.cc)

@@ -53,6 +53,12 @@ static Binding bind_table(const evqgpu_query& q, evqgpu_table* t) {
       b.cols[i] = ensure_code_column(t, t->cols[ci]);
       continue;
     }
+    if (i < q.col_pred.size() && q.col_pred[i] >= 0) {   // the verdict column of a string predicate over this string column
+      if (!t->cols[ci].is_string)
+        fail(EVQGPU_ERR_ARG, "column '%s' is used as a string but is not a flat string column", q.input_columns[i].c_str());
+      b.cols[i] = ensure_pred_column(t, t->cols[ci], q.string_preds[q.col_pred[i]]);
+      continue;
+    }
     if (!t->cols[ci].scannable)
       fail(EVQGPU_ERR_UNSUPPORTED, "column '%s' (logical type %u, encoding %u, rlevel_max %u) is outside the flat numeric scan path",
            q.input_columns[i].c_str(), t->cols[ci].meta.logical_type, t->cols[ci].meta.encoding, t->cols[ci].meta.rlevel_max);
@@ -254,8 +260,56 @@ static void lower_string_leaf(evqgpu_query* q, Expr* a) {
   a->type = EVQ_UINT64;
 }
 
+// fn(string column, string literal) in either order, fn an ordering comparison or startswith / endswith: the node
+// becomes a BOOL input column - the predicate's verdict column, bound per table by ensure_pred_column (strings.cu) - negated
+// when the predicate holds for "": a NULL row reads 0 and must get what the reference computes for it, predicate("")
+// (the tag is dropped, boolean.cc:441-452)
+static bool lower_string_predicate(evqgpu_query* q, Expr* e) {
+  if (e->op != EVQ_X_CALL || e->args.size() != 2) return false;
+  const Fn fn = e->info().fn;
+  if (!(fn == Fn::LT || fn == Fn::LTE || fn == Fn::GT || fn == Fn::GTE || fn == Fn::STARTSWITH || fn == Fn::ENDSWITH)) return false;
+  if (e->info().args[0] != EVQ_STRING) return false;
+  Expr* a = e->args[0].get();
+  Expr* b = e->args[1].get();
+  const bool column_first = a->op == EVQ_X_INPUT && b->op == EVQ_X_LITERAL;
+  if (!column_first && !(a->op == EVQ_X_LITERAL && b->op == EVQ_X_INPUT))
+    fail(EVQGPU_ERR_UNSUPPORTED, "string comparisons run on the device between a string column and a string literal");
+  const Expr* col = column_first ? a : b;
+  const Expr* lit = column_first ? b : a;
+  if (col->col >= q->input_columns.size()) fail(EVQGPU_ERR_ARG, "expression references input column %u of %zu", col->col, q->input_columns.size());
+  StringPredicate p;
+  p.fn = (int) fn;
+  p.column_first = column_first;
+  p.literal = lit->str;
+  p.invert = string_predicate_eval(p, std::string());
+  // a pseudo input column (same table column name, so the binding finds the string column)
+  q->string_preds.push_back(p);
+  q->input_columns.push_back(q->input_columns[col->col]);
+  q->col_is_string.push_back(false);
+  q->col_pred.resize(q->input_columns.size(), -1);
+  q->col_pred.back() = (int) q->string_preds.size() - 1;
+  const uint32_t idx = (uint32_t) q->input_columns.size() - 1;
+  // e := [neg] input(idx) : BOOL
+  std::unique_ptr<Expr> in(new Expr());
+  in->op = EVQ_X_INPUT;
+  in->type = EVQ_BOOL;
+  in->col = idx;
+  e->args.clear();
+  if (p.invert) {
+    e->fn = function_lookup("neg#bool/bool;");
+    e->args.push_back(std::move(in));
+  } else {
+    e->op = EVQ_X_INPUT;
+    e->col = idx;
+    e->fn = 0;
+  }
+  e->type = EVQ_BOOL;
+  return true;
+}
+
 static void lower_strings(evqgpu_query* q, Expr* e) {
   if (!e) return;
+  if (lower_string_predicate(q, e)) return;
   if (e->op == EVQ_X_CALL && (e->info().fn == Fn::EQ || e->info().fn == Fn::NEQ) && e->info().args[0] == EVQ_STRING) {
     lower_string_leaf(q, e->args[0].get());
     lower_string_leaf(q, e->args[1].get());

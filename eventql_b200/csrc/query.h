@@ -186,6 +186,8 @@ struct evqgpu_query {
   uint64_t expected_groups = 0;
   std::vector<bool> col_used;
   std::vector<bool> col_is_string;   // plan input columns read as dictionary codes of a string column (strings.cu)
+  std::vector<int> col_pred;         // plan input columns that are the verdict column of string_preds[i] (-1: not)
+  std::vector<evq::StringPredicate> string_preds;
   bool string_keys = false;          // a GROUP BY expression is a string column
   bool has_first = false;            // some select item takes the value of its group's first row (SelectItem::first)
   bool coordinator = false;          // EVQGPU_QUERY_COORDINATOR: no scan; merges shards' partial rows (merge.cu coordinator_*)

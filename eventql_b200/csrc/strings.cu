@@ -27,6 +27,7 @@
 //     dictionary codes: a UINT32_PLAIN shadow column per string column, codes from one dictionary per context (section
 //     "dictionary codes" below; the rewrite of the plan is query.cu: lower_strings).
 #include "table.h"
+#include "expr.h"
 #include <cub/cub.cuh>
 #include <string.h>
 #include <algorithm>
@@ -222,6 +223,82 @@ const Column* ensure_code_column(evqgpu_table* t, Column& c) {
   table_finish_column(t, *sh);
   c.code_col = std::move(sh);
   return c.code_col.get();
+}
+
+// ---- string predicates evaluated once per dictionary entry --------------------------------------------------------------
+// lt / lte / gt / gte (expressions/boolean.cc:439-710: strncmp over the shorter length, then the lengths - embedded NUL
+// bytes end the comparison like they do there) and startswith / endswith (expressions/string.cc:52-74, StringUtil) between a
+// string column and a literal.
+bool string_predicate_eval(const StringPredicate& p, const std::string& value) {
+  const std::string& left = p.column_first ? value : p.literal;
+  const std::string& right = p.column_first ? p.literal : value;
+  switch ((Fn) p.fn) {
+    case Fn::STARTSWITH: return left.size() >= right.size() && left.compare(0, right.size(), right) == 0;
+    case Fn::ENDSWITH: return left.size() >= right.size() && left.compare(left.size() - right.size(), right.size(), right) == 0;
+    default: break;
+  }
+  const int cmp = strncmp(left.c_str(), right.c_str(), std::min(left.size(), right.size()));
+  switch ((Fn) p.fn) {
+    case Fn::LT: return cmp < 0 || (cmp == 0 && left.size() < right.size());
+    case Fn::LTE: return cmp < 0 || (cmp == 0 && left.size() <= right.size());
+    case Fn::GT: return cmp > 0 || (cmp == 0 && left.size() > right.size());
+    case Fn::GTE: return cmp > 0 || (cmp == 0 && left.size() >= right.size());
+    default: fail(EVQGPU_ERR_UNSUPPORTED, "string predicate %d", p.fn);
+  }
+}
+
+__global__ void k_lut_apply(const u32* __restrict__ codes, u64 n, const u8* __restrict__ lut, u32* __restrict__ out) {
+  for (u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64) gridDim.x * blockDim.x) out[i] = lut[codes[i]];
+}
+
+// The verdict column: a UINT32_PLAIN shadow (0 / 1 per value, the string column's definition levels) that the scan reads
+// as a BOOL input.  The predicate runs on the host once per DICTIONARY entry - not per row - and a device pass maps the
+// value codes through the verdict table.
+const Column* ensure_pred_column(evqgpu_table* t, Column& c, const StringPredicate& p) {
+  const std::string key = std::to_string(p.fn) + (p.column_first ? "c" : "l") + (p.invert ? "!" : "=") + p.literal;
+  auto it = c.pred_cols.find(key);
+  if (it != c.pred_cols.end()) return it->second.get();
+  const Column* codes = ensure_code_column(t, c);
+  evqgpu_ctx* ctx = t->ctx;
+  use_device(ctx);
+  const auto& dict = ctx->code_strings;
+  std::vector<uint8_t> lut(std::max<size_t>(1, dict.size()));
+  for (size_t i = 0; i < dict.size(); ++i) lut[i] = (string_predicate_eval(p, dict[i]) != p.invert) ? 1 : 0;
+  DevBuf dlut;
+  dlut.alloc(lut.size());
+  EVQ_CUDA(cudaMemcpyAsync(dlut.p, lut.data(), lut.size(), cudaMemcpyHostToDevice, ctx->stream));
+  const uint64_t nv = codes->num_values;
+  std::unique_ptr<Column> sh(new Column());
+  sh->meta = c.meta;
+  sh->meta.logical_type = EVQ_COL_BOOLEAN;
+  sh->meta.encoding = EVQ_ENC_UINT32_PLAIN;
+  sh->sql_type = EVQ_BOOL;
+  sh->scannable = true;
+  sh->data_kind = EVQ_KIND_PLAIN32;
+  sh->data.present = true;
+  sh->data.nbytes = nv * 4;
+  const uint64_t alloc = round_up(nv * 4, 256) + 256;
+  sh->data.buf.alloc(alloc);
+  const uint64_t tail0 = (nv * 4) & ~255ull;
+  EVQ_CUDA(cudaMemsetAsync((uint8_t*) sh->data.buf.p + tail0, 0, alloc - tail0, ctx->stream));
+  if (nv) {
+    k_lut_apply<<<(unsigned) std::min<uint64_t>((nv + 255) / 256, (uint64_t) ctx->sm_count * 16), 256, 0, ctx->stream>>>(
+        codes->data.buf.as<u32>(), nv, dlut.as<u8>(), sh->data.buf.as<u32>());
+    EVQ_CUDA(cudaGetLastError());
+    ctx->kernel_launches++;
+  }
+  if (c.meta.dlevel_max > 0) {
+    sh->dlevel.present = c.dlevel.present;
+    sh->dlevel.nbytes = c.dlevel.nbytes;
+    sh->dlevel.bitpack_max = c.dlevel.bitpack_max;
+    sh->dlevel.buf.alloc(c.dlevel.buf.bytes);
+    EVQ_CUDA(cudaMemcpyAsync(sh->dlevel.buf.p, c.dlevel.buf.p, c.dlevel.buf.bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  EVQ_CUDA(cudaStreamSynchronize(ctx->stream));   // `lut` / `dlut` go away
+  table_finish_column(t, *sh);
+  const Column* out = sh.get();
+  c.pred_cols[key] = std::move(sh);
+  return out;
 }
 
 static Column& string_column(evqgpu_table* tbl, const char* name) {

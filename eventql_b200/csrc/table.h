@@ -59,6 +59,9 @@ struct Column {
   // ... and, once a query compares or groups by the column, its values as dictionary codes (evqgpu_ctx::string_codes): a
   // UINT32_PLAIN shadow column with the same definition levels, which is what the scan kernels read
   std::unique_ptr<Column> code_col;
+  // verdict columns of string predicates over this column (key: function, operand order, literal): value i = predicate of
+  // the string value i, looked up through the dictionary code (strings.cu ensure_pred_column)
+  std::map<std::string, std::unique_ptr<Column>> pred_cols;
 };
 
 #define EVQ_KIND_STRING_HOST 255u   // Column::data_kind of string columns (host side only: the scan kernels never see them)
@@ -93,5 +96,13 @@ void table_finish_column(evqgpu_table* t, Column& c);   // indexes + tile caps a
 // strings.cu: value index of a string column whose streams are on the device; `host_stream` is the logical DATA stream
 void table_finish_string_column(evqgpu_table* t, Column& c, const uint8_t* host_stream, uint64_t nbytes);
 uint32_t string_code(evqgpu_ctx* ctx, const std::string& s);        // code of a string in the context's dictionary (inserted if new)
+struct StringPredicate {
+  int fn = 0;              // evq::Fn as int: LT / LTE / GT / GTE / STARTSWITH / ENDSWITH
+  bool column_first = true;   // fn(column, literal) or fn(literal, column)
+  std::string literal;
+  bool invert = false;     // the verdict column holds NOT predicate (chosen so that a NULL row, which reads 0, gets predicate(""))
+};
+bool string_predicate_eval(const StringPredicate& p, const std::string& value);   // the reference's semantics, on the host
+const Column* ensure_pred_column(evqgpu_table* t, Column& c, const StringPredicate& p);
 const Column* ensure_code_column(evqgpu_table* t, Column& c);       // the dictionary-coded shadow of a loaded string column
 }  // namespace evq

@@ -151,6 +151,8 @@ def _registry():
     reg("from_timestamp", [INT64], TIMESTAMP64)
     reg("from_timestamp", [FLOAT64], TIMESTAMP64)
     reg("date_trunc", [STRING, TIMESTAMP64], TIMESTAMP64)
+    reg("startswith", [STRING, STRING], BOOL)                           # sql/defaults.cc:149-150, expressions/string.cc:52-74
+    reg("endswith", [STRING, STRING], BOOL)
     for name in ("add", "sub", "mul", "div", "mod", "pow"):
         for t in (UINT64, INT64, FLOAT64):
             reg(name, [t, t], t)

@@ -742,12 +742,27 @@ def eval_expr(e: P.Expr, inputs: Sequence[Vec], n: int, active: Optional[np.ndar
             return Vec(P.BOOL, x.astype(bool) | y.astype(bool), zt)
         if name == "neg":
             return Vec(P.BOOL, ~x.astype(bool), zt)
-        if T == P.STRING and name in ("eq", "neq", "lt", "lte", "gt", "gte"):
-            # boolean.cc:235-257 ...: length + memcmp on the popped strings; the tag is dropped, so a NULL compares as ""
+        if T == P.STRING and name in ("eq", "neq"):
+            # boolean.cc:235-257, 355-377: length + memcmp on the popped strings; the tag is dropped, so a NULL compares as ""
             import operator
-            op = {"eq": operator.eq, "neq": operator.ne, "lt": operator.lt, "lte": operator.le, "gt": operator.gt,
-                  "gte": operator.ge}[name]
+            op = {"eq": operator.eq, "neq": operator.ne}[name]
             return Vec(P.BOOL, np.fromiter((op(p, q) for p, q in zip(a[0].values, a[1].values)), dtype=bool, count=n), zt)
+        if T == P.STRING and name in ("lt", "lte", "gt", "gte"):
+            # boolean.cc:439-710: strncmp over the shorter length - which stops at an embedded NUL byte - then the lengths
+            def cmp3(p, q):
+                for x, y in zip(p, q):
+                    if x != y:
+                        return -1 if x < y else 1
+                    if x == 0:
+                        break
+                return 0
+            rel = {"lt": lambda c, lp, lq: c < 0 or (c == 0 and lp < lq), "lte": lambda c, lp, lq: c < 0 or (c == 0 and lp <= lq),
+                   "gt": lambda c, lp, lq: c > 0 or (c == 0 and lp > lq), "gte": lambda c, lp, lq: c > 0 or (c == 0 and lp >= lq)}[name]
+            return Vec(P.BOOL, np.fromiter((rel(cmp3(p, q), len(p), len(q)) for p, q in zip(a[0].values, a[1].values)), dtype=bool, count=n), zt)
+        if name in ("startswith", "endswith"):
+            # expressions/string.cc:52-74 (StringUtil::beginsWith / endsWith): (string, affix)
+            f = bytes.startswith if name == "startswith" else bytes.endswith
+            return Vec(P.BOOL, np.fromiter((f(p, q) for p, q in zip(a[0].values, a[1].values)), dtype=bool, count=n), zt)
         if name in ("eq", "neq", "lt", "lte", "gt", "gte"):
             r = {"eq": np.equal, "neq": np.not_equal, "lt": np.less, "lte": np.less_equal,
                  "gt": np.greater, "gte": np.greater_equal}[name](x, y)

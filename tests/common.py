@@ -613,6 +613,22 @@ def string_query_cases():
         [s_req, s_opt, cnt, P.call("max", k)], where=(k >= 0) & s_req.neq(P.lit("x")), group=[s_req, s_opt])
     add("str_group_mixed_key", "select s_req, k / 500, count(1) from t where k >= 0 group by s_req, k / 500;",
         [s_req, k / 500, cnt], where=k >= 0, group=[s_req, k / 500])
+    # ordering comparisons (strncmp over the shorter length, then the lengths; a NULL compares as "") and startswith / endswith
+    # between a string column and a literal: evaluated once per dictionary entry on the device path
+    add("str_lt_lit", "select count(1), sum(k) from t where s_req < 'google' and k >= 0;",
+        [cnt, P.call("sum", k)], where=(s_req < P.lit("google")) & (k >= 0))
+    add("str_gte_lit_nullable", "select count(1), sum(k) from t where s_opt >= 'f' and k >= 0;",
+        [cnt, P.call("sum", k)], where=(s_opt >= P.lit("f")) & (k >= 0))
+    add("str_lte_null_is_empty", "select count(1), sum(k) from t where s_opt <= 'a' and k >= 0;",
+        [cnt, P.call("sum", k)], where=(s_opt <= P.lit("a")) & (k >= 0))
+    add("str_lit_gt_col", "select count(1), min(k) from t where 'newsletter' > s_req and k >= 0;",
+        [cnt, P.call("min", k)], where=(P.lit("newsletter") > s_req) & (k >= 0))
+    add("str_startswith", "select count(1), sum(k) from t where startswith(s_req, 'google') and k >= 0;",
+        [cnt, P.call("sum", k)], where=P.call("startswith", s_req, P.lit("google")) & (k >= 0))
+    add("str_endswith_nullable_group", "select k / 500, count(1) from t where endswith(s_opt, '.com') and k >= 0 group by k / 500;",
+        [k / 500, cnt], where=P.call("endswith", s_opt, P.lit(".com")) & (k >= 0), group=[k / 500])
+    add("str_startswith_empty_matches_all", "select count(1) from t where startswith(s_opt, '') and k >= 0;",
+        [cnt], where=P.call("startswith", s_opt, P.lit("")) & (k >= 0))
     add("str_scan_projection", "select s_opt, k, s_req from t where s_req = 'facebook' or s_opt = 'x';",
         [s_opt, k, s_req], where=s_req.eq(P.lit("facebook")) | s_opt.eq(P.lit("x")), flags=0, ordered=True)
     return Q
