@@ -39,6 +39,10 @@ struct evqgpu_ctx {
   // string literal, gets a dense code; code 0 is the empty string (what a NULL string compares as, boolean.cc:235-257)
   std::unordered_map<std::string, uint32_t> string_codes;
   std::vector<std::string> code_strings;
+  // multi-rank jobs: the first dict_agreed entries are identical on all ranks (strings.cu sync_dictionary); codes behind
+  // them are provisional until the next synchronisation, which renumbers them - in the code columns registered here too
+  uint32_t dict_agreed = 0;
+  std::vector<std::pair<void*, void*>> code_columns;   // (evqgpu_table*, its string Column*) of every code column built
   // device memory pool of THIS context.  All work of a context is ordered on its one stream, so a block freed by the
   // context and handed out again to the same context is reused in stream order; blocks never move between contexts
   // (two contexts on one device have two streams: a shared pool would hand a block to the other stream while kernels of

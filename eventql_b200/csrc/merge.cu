@@ -422,8 +422,6 @@ void merge_query(evqgpu_query& q) {
   }
   if (!(q.flags & EVQGPU_QUERY_PARTIAL))
     fail(EVQGPU_ERR_ARG, "evqgpu_query_merge: the plan was not created with EVQGPU_QUERY_PARTIAL");
-  if (q.string_keys)   // dictionary codes are per context: the ranks' codes for one string differ
-    fail(EVQGPU_ERR_UNSUPPORTED, "evqgpu_query_merge: string GROUP BY keys cannot be merged across ranks");
   // (the ranks agreed on the aggregation strategy, the slot assignment and the state layout in evqgpu_query_prepare,
   // one unconditional collective; nothing here decides per rank whether to enter a collective)
   if (q.shape.tier == 1) {

@@ -253,6 +253,7 @@ static void lower_string_leaf(evqgpu_query* q, Expr* a) {
   } else if (a->op == EVQ_X_LITERAL) {
     if (!q->ctx) fail(EVQGPU_ERR_UNSUPPORTED, "string literals need a context (dictionary codes)");
     a->imm = string_code(q->ctx, a->str);
+    q->string_literals.push_back({a, a->str});   // (a multi-rank dictionary synchronisation may renumber the code)
     a->str.clear();
   } else {
     fail(EVQGPU_ERR_UNSUPPORTED, "string expressions other than columns and literals are outside the device path");
@@ -902,8 +903,8 @@ void prepare_query(evqgpu_query& q, std::vector<evqgpu_table*>& tv) {
   uint64_t failed = 0, capable = 0, layout = 0;
   std::vector<uint64_t> bounds(kBW * nk, 0);
   std::string msg;
+  std::vector<TablePlan> plans;
   try {
-    std::vector<TablePlan> plans;
     for (auto* t : tv) {
       if (!t) fail(EVQGPU_ERR_ARG, "null table");
       if (t->ctx != q.ctx) fail(EVQGPU_ERR_ARG, "table belongs to another context");
@@ -913,6 +914,26 @@ void prepare_query(evqgpu_query& q, std::vector<evqgpu_table*>& tv) {
       plans.push_back(std::move(p));
     }
     if (plans.empty()) fail(EVQGPU_ERR_ARG, "evqgpu_query_prepare: no tables");
+  } catch (const Error& e) {
+    failed = 1;
+    msg = e.msg;
+  }
+  // a plan that reads string columns as dictionary codes: the ranks' dictionaries are made identical first (collective,
+  // entered by every rank of such a plan whatever happened above), so that equal strings have equal codes everywhere -
+  // string GROUP BY keys and string predicates then merge like integers
+  bool uses_strings = !q.string_literals.empty();
+  for (bool b : q.col_is_string) uses_strings = uses_strings || b;
+  if (uses_strings) {
+    sync_dictionary(ctx);
+    for (auto& lit : q.string_literals) {
+      const uint64_t code = string_code(ctx, lit.second);
+      if (lit.first->imm != code) { lit.first->imm = code; q.module_sig.clear(); }
+    }
+  }
+  uids.clear();   // (the synchronisation gives renumbered tables a new identity)
+  for (auto* t : tv) uids.push_back(t ? t->uid : 0);
+  try {
+    if (failed) throw Error{EVQGPU_ERR_RUNTIME, msg};
     KernelShape s = shape_of_plans(q, plans);
     layout_states(q, s);
     layout = fnv1a(layout_signature(q));

@@ -186,6 +186,7 @@ struct evqgpu_query {
   uint64_t expected_groups = 0;
   std::vector<bool> col_used;
   std::vector<bool> col_is_string;   // plan input columns read as dictionary codes of a string column (strings.cu)
+  std::vector<std::pair<evq::Expr*, std::string>> string_literals;   // string literals read as dictionary codes (imm), with their text
   std::vector<int> col_pred;         // plan input columns that are the verdict column of string_preds[i] (-1: not)
   std::vector<evq::StringPredicate> string_preds;
   bool string_keys = false;          // a GROUP BY expression is a string column

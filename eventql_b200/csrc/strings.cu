@@ -222,7 +222,88 @@ const Column* ensure_code_column(evqgpu_table* t, Column& c) {
   EVQ_CUDA(cudaStreamSynchronize(ctx->stream));   // `codes` goes away
   table_finish_column(t, *sh);
   c.code_col = std::move(sh);
+  ctx->code_columns.push_back({(void*) t, (void*) &c});
   return c.code_col.get();
+}
+
+__global__ void k_remap_codes(u32* __restrict__ codes, u64 n, const u32* __restrict__ remap, u32 first) {
+  for (u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64) gridDim.x * blockDim.x) {
+    const u32 c = codes[i];
+    if (c >= first) codes[i] = remap[c - first];
+  }
+}
+
+std::vector<uint64_t> comm_all_gather_host(evqgpu_ctx* ctx, const std::vector<uint64_t>& mine);   // comm.cc
+
+bool sync_dictionary(evqgpu_ctx* ctx) {
+  if (ctx->code_strings.empty()) string_code(ctx, std::string());
+  if (ctx->dict_agreed == 0) ctx->dict_agreed = 1;   // code 0 = "" everywhere
+  const uint32_t first = ctx->dict_agreed;
+  // 1. my provisional strings, serialised [u32 length][bytes], padded to 8
+  std::vector<uint8_t> blob;
+  for (size_t i = first; i < ctx->code_strings.size(); ++i) {
+    const uint32_t len = (uint32_t) ctx->code_strings[i].size();
+    blob.insert(blob.end(), (const uint8_t*) &len, (const uint8_t*) &len + 4);
+    blob.insert(blob.end(), ctx->code_strings[i].begin(), ctx->code_strings[i].end());
+  }
+  const uint64_t my_n = ctx->code_strings.size() - first, my_bytes = blob.size();
+  const std::vector<uint64_t> sizes = comm_all_gather_host(ctx, std::vector<uint64_t>{my_n, my_bytes});
+  uint64_t max_bytes = 0, total_new = 0;
+  for (int r = 0; r < ctx->nranks; ++r) { max_bytes = std::max(max_bytes, sizes[2 * r + 1]); total_new += sizes[2 * r]; }
+  if (total_new == 0) return false;   // (every rank sees the same sizes: the same decision everywhere)
+  const size_t words = (size_t) (max_bytes + 7) / 8;
+  std::vector<uint64_t> mine(words, 0);
+  if (!blob.empty()) memcpy(mine.data(), blob.data(), blob.size());
+  const std::vector<uint64_t> all = comm_all_gather_host(ctx, mine);
+  // 2. the agreed prefix + the union of everybody's new strings in rank order
+  std::vector<std::string> provisional(ctx->code_strings.begin() + first, ctx->code_strings.end());
+  ctx->code_strings.resize(first);
+  ctx->string_codes.clear();
+  for (uint32_t i = 0; i < first; ++i) ctx->string_codes.emplace(ctx->code_strings[i], i);
+  for (int r = 0; r < ctx->nranks; ++r) {
+    const uint8_t* p = (const uint8_t*) (all.data() + (size_t) r * words);
+    uint64_t pos = 0;
+    for (uint64_t i = 0; i < sizes[2 * r]; ++i) {
+      uint32_t len;
+      memcpy(&len, p + pos, 4);
+      std::string s((const char*) p + pos + 4, len);
+      pos += 4 + len;
+      if (ctx->string_codes.find(s) == ctx->string_codes.end()) {
+        ctx->string_codes.emplace(s, (uint32_t) ctx->code_strings.size());
+        ctx->code_strings.push_back(std::move(s));
+      }
+    }
+  }
+  ctx->dict_agreed = (uint32_t) ctx->code_strings.size();
+  // 3. renumber my provisional codes where they moved
+  std::vector<uint32_t> remap(provisional.size());
+  bool changed = false;
+  for (size_t i = 0; i < provisional.size(); ++i) {
+    remap[i] = ctx->string_codes.at(provisional[i]);
+    changed = changed || remap[i] != first + i;
+  }
+  if (!changed || provisional.empty()) return changed;
+  use_device(ctx);
+  DevBuf dremap;
+  dremap.alloc(remap.size() * 4);
+  EVQ_CUDA(cudaMemcpyAsync(dremap.p, remap.data(), remap.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  for (auto& tc : ctx->code_columns) {
+    evqgpu_table* t = (evqgpu_table*) tc.first;
+    Column* c = (Column*) tc.second;
+    if (!c->code_col) continue;
+    Column& cc = *c->code_col;
+    const uint64_t nv = cc.num_values;
+    if (nv) {
+      k_remap_codes<<<(unsigned) std::min<uint64_t>((nv + 255) / 256, (uint64_t) ctx->sm_count * 16), 256, 0, ctx->stream>>>(
+          cc.data.buf.as<u32>(), nv, dremap.as<u32>(), first);
+      EVQ_CUDA(cudaGetLastError());
+      ctx->kernel_launches++;
+    }
+    table_finish_column(t, cc);   // the value range of the codes changed
+    t->uid = next_table_uid();    // (cached key bounds of queries over this table are stale)
+  }
+  EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return true;
 }
 
 // ---- string predicates evaluated once per dictionary entry --------------------------------------------------------------

@@ -25,6 +25,7 @@ uint32_t sql_type_of(const ColumnMeta& m) {   // sql/CSTableScanProvider.cc:79-1
 }
 
 static uint64_t g_next_table_uid = 1;
+uint64_t next_table_uid() { return __atomic_fetch_add(&g_next_table_uid, 1, __ATOMIC_RELAXED); }
 
 void table_init_columns(evqgpu_table* t) {
   if (t->uid == 0) t->uid = __atomic_fetch_add(&g_next_table_uid, 1, __ATOMIC_RELAXED);
@@ -724,6 +725,8 @@ int evqgpu_table_set_filter(evqgpu_table* tbl, const void* bits, uint64_t nrows,
 void evqgpu_table_destroy(evqgpu_table* tbl) {
   if (!tbl) return;
   cudaSetDevice(tbl->ctx->device);
+  auto& cc = tbl->ctx->code_columns;
+  cc.erase(std::remove_if(cc.begin(), cc.end(), [&](const std::pair<void*, void*>& e) { return e.first == (void*) tbl; }), cc.end());
   delete tbl;
 }
 

@@ -104,5 +104,10 @@ struct StringPredicate {
 };
 bool string_predicate_eval(const StringPredicate& p, const std::string& value);   // the reference's semantics, on the host
 const Column* ensure_pred_column(evqgpu_table* t, Column& c, const StringPredicate& p);
-const Column* ensure_code_column(evqgpu_table* t, Column& c);       // the dictionary-coded shadow of a loaded string column
+const Column* ensure_code_column(evqgpu_table* t, Column& c);
+// COLLECTIVE (multi-rank jobs): make the string dictionaries of all ranks identical - the ranks exchange the strings they
+// added since the last call, append their union in rank order, and renumber their provisional codes (code columns included).
+// Returns true when codes of this rank changed.
+bool sync_dictionary(evqgpu_ctx* ctx);
+uint64_t next_table_uid();       // the dictionary-coded shadow of a loaded string column
 }  // namespace evq

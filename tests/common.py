@@ -528,21 +528,22 @@ def synth_strings(seed: int, num_rows: int, null_every: int = 0):
 STRINGS_ROWS = 2500
 
 
-def strings_table_columns(num_rows: int = STRINGS_ROWS):
-    """name -> (kind, values, nulls) of the string fixture table (tests/golden/ref_strings_v{1,2}.cst.gz)."""
+def strings_table_columns(num_rows: int = STRINGS_ROWS, seed: int = 0):
+    """name -> (kind, values, nulls) of the string fixture table (tests/golden/ref_strings_v{1,2}.cst.gz are seed 0;
+    other seeds give other value sets, as the partitions of different ranks have)."""
     import hashlib
-    k, _ = synth_values(dict(seed=41, lo=0, span=1000), num_rows)
-    s_req, _ = synth_strings(42, num_rows)
-    s_opt, nulls = synth_strings(43, num_rows, null_every=3)
+    k, _ = synth_values(dict(seed=41 + seed, lo=0, span=1000), num_rows)
+    s_req, _ = synth_strings(42 + 1000 * seed, num_rows)
+    s_opt, nulls = synth_strings(43 + 1000 * seed, num_rows, null_every=3)
     ids = [hashlib.sha1(b"row-%d" % (int(x) % 600)).digest() for x in k]
     return [("k", "uint", k, None), ("s_req", "string", s_req, None), ("s_opt", "string", s_opt, nulls), ("id", "string", ids, None)]
 
 
-def write_strings_table(path: str, num_rows: int = STRINGS_ROWS):
+def write_strings_table(path: str, num_rows: int = STRINGS_ROWS, seed: int = 0):
     """The string fixture table written by the ORACLE's writer (test infrastructure)."""
     from oracle import evq_oracle as O
     cols = []
-    for name, kind, vals, nulls in strings_table_columns(num_rows):
+    for name, kind, vals, nulls in strings_table_columns(num_rows, seed):
         if kind == "string":
             cols.append(O.WriteColumn(name, P.COL_STRING, P.ENC_STRING_PLAIN, None, nulls, strings=vals))
         else:

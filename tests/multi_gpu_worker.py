@@ -95,6 +95,45 @@ def main():
     if rank == 0:
         print("collective agreement checks: %s" % ("ok" if int(nf.item()) == 0 else failures), flush=True)
 
+    # ---- string GROUP BY keys and string predicates across ranks: the ranks' dictionaries are synchronised in prepare, so
+    # equal strings have equal codes everywhere.  Every rank scans a DIFFERENT string table (different value sets, so
+    # the local dictionaries differ before the synchronisation); the merged rows == the oracle over all tables.
+    import tempfile
+    sdir = tempfile.mkdtemp(prefix="evqstr%d_" % rank)
+    sizes = [900 + 137 * r for r in range(world)]
+    spath = os.path.join(sdir, "s.cst")
+    T.write_strings_table(spath, sizes[rank], seed=1 + rank)
+    stbl = ctx.open_table_file(spath)
+    snames = ["k", "s_req", "s_opt"]
+    sk, s_req, s_opt = P.Col(0, P.UINT64), P.Col(1, P.STRING), P.Col(2, P.STRING)
+    cnt = P.call("count", P.lit(1))
+    splans = [("string_keys_dense_or_hash", P.QueryPlan(snames, [s_opt, cnt, P.call("sum", sk)], where=(sk >= 0) & s_req.neq(P.lit("x")), group=[s_opt])),
+              ("string_keys_hash", P.QueryPlan(snames, [s_req, s_opt, cnt, P.call("max", sk)], where=sk >= 0, group=[s_req, s_opt],
+                                               expected_groups=1 << 25)),
+              ("string_predicates", P.QueryPlan(snames, [cnt, P.call("sum", sk)], where=(s_req < P.lit("google")) & s_opt.neq(P.lit("facebook"))))]
+    for sname, splan in splans:
+        splan.flags |= P.QUERY_PARTIAL
+        q = ctx.query(splan)
+        q.execute([stbl])
+        q.merge()
+        part = q.rows()
+        sstrat = q.stats()["strategy"]
+        q.close()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, part)
+        allp = [None] * world
+        dist.all_gather_object(allp, open(spath, "rb").read())
+        if rank == 0:
+            files = [O.parse_cstable(b) for b in allp]
+            want = O.run_query(files, splan).rows()
+            got_sets = gathered if sstrat in (1, 3) else [sum(gathered, [])]
+            for got in got_sets:
+                ok, why = T.rows_equal(got, want)
+                if not ok:
+                    failures.append("%s: %s" % (sname, why))
+            print("case %-22s tier=%d groups=%d %s" % (sname, sstrat, len(want), "ok" if not failures else failures[-1]), flush=True)
+    stbl.close()
+
     for name, spec, plan in cases:
         ts = name == "timeseries"
         mine = sharding.assign_partitions(nparts, rank, world)
