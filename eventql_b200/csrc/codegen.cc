@@ -814,8 +814,8 @@ static std::string gen_row_functions(const evqgpu_query& q, const KernelShape& s
         if (shape.cols[shape.rec_cols[j]].nullable) t += " | ((u64) row.t" + std::to_string(shape.rec_cols[j]) + " << " + std::to_string(j) + ")";
       words.push_back(t);
     }
-    if (words.size() == 2) {   // one 16-byte store
-      os << "  asm volatile(\"st.global.v2.u64 [%0], {%1, %2};\" :: \"l\"(rec), \"l\"(" << words[0] << "), \"l\"(" << words[1] << ") : \"memory\");\n";
+    if (words.size() == 2) {   // one 16-byte store (into the tile's staging array in shared memory)
+      os << "  *(ulonglong2*) rec = make_ulonglong2(" << words[0] << ", " << words[1] << ");\n";
     } else {
       for (size_t j = 0; j < words.size(); ++j) os << "  rec[" << j << "] = " << words[j] << ";\n";
     }
@@ -1221,13 +1221,14 @@ static std::string gen_group_kernels(const evqgpu_query& q, const KernelShape& s
     os << "    if (part >= A.window) {\n      if (threadIdx.x == 0) {\n        const u32 need = (part - A.window + 1u) * gridDim.x;\n        u32 seen;\n"
           "        do { asm volatile(\"ld.acquire.gpu.global.u32 %0, [%1];\" : \"=r\"(seen) : \"l\"(A.bar) : \"memory\"); if (seen < need) __nanosleep(200); } while (seen < need);\n"
           "      }\n      __syncthreads();\n    }\n";
-    os << "    for (u32 seg = blockIdx.x; seg < A.nseg; seg += gridDim.x) {\n";
-    os << "      const u32 n = A.part_cursor[(u64) part * A.nseg + seg];\n";
-    os << "      const u64* base = A.part_buf + ((u64) part * A.nseg + seg) * A.part_cap * EVQ_NREC;\n";
-    os << "      for (u32 i = threadIdx.x; i < n; i += 4u * 256u) {\n";
+    os << "    {\n";
+    os << "      const u32 cur = A.part_cursor[part];\n      const u32 n = cur < A.part_cap ? cur : (u32) A.part_cap;\n";
+    os << "      const u64* base = A.part_buf + (u64) part * A.part_cap * EVQ_NREC;\n";
+    os << "      const u32 stride = gridDim.x * 256u;\n";
+    os << "      for (u32 i = blockIdx.x * 256u + threadIdx.x; i < n; i += 4u * stride) {\n";
     os << "        EvqRow row[4];\n        u64 key[4][EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];\n        u64 fpv[4], slot[4], w0[4], w1[4];\n        bool have[4];\n";
-    os << "#pragma unroll\n        for (int j = 0; j < 4; ++j) {\n          have[j] = i + j * 256u < n;\n          fpv[j] = slot[j] = w0[j] = w1[j] = 0;\n"
-          "          if (have[j]) evq_row_load(base + (u64) (i + j * 256u) * EVQ_NREC, row[j]);\n        }\n";
+    os << "#pragma unroll\n        for (int j = 0; j < 4; ++j) {\n          have[j] = i + j * stride < n;\n          fpv[j] = slot[j] = w0[j] = w1[j] = 0;\n"
+          "          if (have[j]) evq_row_load(base + (u64) (i + j * stride) * EVQ_NREC, row[j]);\n        }\n";
     os << "#pragma unroll\n        for (int j = 0; j < 4; ++j) {\n          if (have[j]) {\n            u32 ktag[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];\n"
           "            evq_keys(row[j], key[j], ktag, err);\n            evq_ht_hash<EVQ_NKEYS>(A.ht, key[j], ktag, fpv[j], slot[j]);\n"
           "            evq_ht_prefetch(A.ht, slot[j], w0[j], w1[j]);\n          }\n        }\n";

@@ -93,7 +93,7 @@ struct EvqScanParams {
   // Every CTA of pass 1 owns one segment of every partition, so appending needs no global atomics and no barriers: the
   // position inside the segment comes from a shared-memory cursor.
   u64* part_buf;                    // [2^part_bits][gridDim.x][part_cap][EVQ_NREC] record words
-  u32* part_cursor;                 // [2^part_bits][gridDim.x] records in every segment (written when the CTA is done)
+  u32* part_cursor;                 // [2^part_bits] records appended to every partition (runs are claimed with atomicAdd)
   u64 part_cap;                     // records per segment
   u32 part_shift;                   // partition = home slot >> part_shift
   u32 part_bits;

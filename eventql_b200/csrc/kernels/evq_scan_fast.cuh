@@ -41,7 +41,12 @@ struct EvqFastScratch {
   __align__(16) u32 nval[2][EVQ_NNV][EVQ_TILE_ROWS + 8];
 #endif
 #ifdef EVQ_PARTITION
-  u32 pcur[EVQ_MAX_PARTS];                                    // records this CTA has appended to its segment of every partition
+  __align__(16) u64 prec[EVQ_TILE_ROWS * EVQ_NREC];           // the tile's records, ordered by partition
+  u32 phist[EVQ_MAX_PARTS];                                   // records of the current tile per partition
+  u32 pscan[EVQ_MAX_PARTS];                                   // ... before the partition (where its run starts in prec)
+  u32 pbase[EVQ_MAX_PARTS];                                   // where the run goes in the partition (claimed from the global cursors)
+  u32 ptotal;
+  u8 ppart[EVQ_TILE_ROWS];                                    // the partition of every staged record
 #endif
 };
 
@@ -651,7 +656,7 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
 
   const u32 tid = threadIdx.x;
 #ifdef EVQ_PARTITION
-  for (u32 p = tid; p < EVQ_MAX_PARTS; p += EVQ_NTHREADS) scr->pcur[p] = 0u;
+  for (u32 p = tid; p < EVQ_MAX_PARTS; p += EVQ_NTHREADS) scr->phist[p] = 0u;
 #endif
   if (tid == 0) {
     for (int s = 0; s < EVQ_NSTAGES; ++s) {
@@ -715,7 +720,7 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
   u32 nullbuf = 0;
 #endif
 #ifdef EVQ_PARTITION
-  const u32 pcur_sa = evq_smem_u32(&scr->pcur[0]);
+  const u32 phist_sa = evq_smem_u32(&scr->phist[0]);
 #endif
   u32 it = 0;
   for (u32 group = first_group; group < num_groups; group += group_step, ++it) {
@@ -827,14 +832,20 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
     }
 #elif EVQ_TIER == 2 && defined(EVQ_PARTITION)
     // partitioned aggregation, pass 1: the rows that pass WHERE become records (the columns the keys and the aggregate
-    // arguments read), appended to the partition their group's home slot falls into.  This CTA owns one segment of every
-    // partition: the position comes from a shared-memory cursor (no global atomic, no barrier), and the records of one
-    // segment land next to each other, so L2 merges the 16-byte stores into full lines before they reach HBM.
+    // arguments read), appended to the partition their group's home slot falls into.  Every partition is ONE flat array.
+    // Scattered 16-byte stores cost ~3x the kernel's other work (profiles/r02_c4_pass1_experiments.txt), so the tile is
+    // ordered by partition in shared memory first:
+    //   (1) count the tile's records per partition (the count before a row is its rank inside the partition's run)
+    //   (2) one warp: exclusive scan of the counts, and ONE global atomic per partition claims the run in the partition
+    //   (3) every row's record goes to run start + rank of the staging array
+    //   (4) the staging array is copied out in order: consecutive threads write consecutive addresses of one run
+    u32 pr[EVQ_RPT];   // partition | rank << 8, ~0 = the row did not pass
 #pragma unroll
     for (int k = 0; k < EVQ_RPT; ++k) {
       EvqRow row;
       evq_fast_row(cols, k, row);
       const bool pass = ((u32) k < nvalid) && evq_where(row, err) && EVQ_ROW_KEPT(k);
+      pr[k] = ~0u;
       if (pass) {
         ++passed;
         u64 key[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
@@ -843,11 +854,74 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
         evq_keys(row, key, ktag, err);
         evq_ht_hash<EVQ_NKEYS>(P.ht, key, ktag, fpv, slot);
         const u32 part = (u32) (slot >> P.part_shift);
-        u32 pos;   // (an explicit shared-memory atomic: through the generic pointer it went down the global-memory path)
-        asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(pcur_sa + 4u * part) : "memory");
-        if (pos < P.part_cap) evq_row_store(row, P.part_buf + (((u64) part * gridDim.x + blockIdx.x) * P.part_cap + pos) * EVQ_NREC);
+        u32 rank;   // (an explicit shared-memory atomic: through the generic pointer it went down the global-memory path)
+        asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(rank) : "r"(phist_sa + 4u * part));
+        pr[k] = part | (rank << 8);
+      }
+    }
+    evq_cons_sync();
+    if (tid < 32u) {
+      constexpr u32 PER = EVQ_MAX_PARTS >= 32 ? EVQ_MAX_PARTS / 32 : 1;
+      u32 n[PER], sum = 0;
+#pragma unroll
+      for (u32 j = 0; j < PER; ++j) {
+        const u32 p = tid * PER + j;
+        n[j] = p < EVQ_MAX_PARTS ? scr->phist[p] : 0u;
+        sum += n[j];
+      }
+      u32 incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (tid >= (u32) o) incl += v;
+      }
+      u32 before = incl - sum;
+#pragma unroll
+      for (u32 j = 0; j < PER; ++j) {
+        const u32 p = tid * PER + j;
+        if (p < EVQ_MAX_PARTS) {
+          scr->phist[p] = 0u;
+          scr->pscan[p] = before;
+          scr->pbase[p] = n[j] ? atomicAdd(P.part_cursor + p, n[j]) : 0u;
+          before += n[j];
+        }
+      }
+      if (tid == 31u) scr->ptotal = incl;
+    }
+    evq_cons_sync();
+#pragma unroll
+    for (int k = 0; k < EVQ_RPT; ++k) {
+      if (pr[k] != ~0u) {
+        const u32 part = pr[k] & 255u;
+        const u32 at = scr->pscan[part] + (pr[k] >> 8);
+        EvqRow row;
+        evq_fast_row(cols, k, row);
+        evq_row_store(row, scr->prec + (size_t) at * EVQ_NREC);
+        scr->ppart[at] = (u8) part;
+      }
+    }
+    evq_cons_sync();
+    {
+      const u32 total = scr->ptotal;
+#if EVQ_NREC % 2 == 0
+      constexpr u32 U = EVQ_NREC / 2;   // 16-byte units per record
+      const ulonglong2* src = (const ulonglong2*) scr->prec;
+      for (u32 j = tid; j < total * U; j += EVQ_NCONS) {
+        const u32 i = j / U, w = j % U;
+        const u32 part = scr->ppart[i];
+        const u64 pos = (u64) scr->pbase[part] + (i - scr->pscan[part]);
+        if (pos < P.part_cap) ((ulonglong2*) (P.part_buf + ((u64) part * P.part_cap + pos) * EVQ_NREC))[w] = src[j];
         else err |= EVQ_ERR_PART_FULL;
       }
+#else
+      for (u32 j = tid; j < total * EVQ_NREC; j += EVQ_NCONS) {
+        const u32 i = j / EVQ_NREC, w = j % EVQ_NREC;
+        const u32 part = scr->ppart[i];
+        const u64 pos = (u64) scr->pbase[part] + (i - scr->pscan[part]);
+        if (pos < P.part_cap) P.part_buf[((u64) part * P.part_cap + pos) * EVQ_NREC + w] = scr->prec[j];
+        else err |= EVQ_ERR_PART_FULL;
+      }
+#endif
     }
 #elif EVQ_TIER == 2
     // hash tier: the group table lives in HBM, every probe is a DRAM round trip.  Rows are handled in quads: first the
@@ -985,13 +1059,6 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
   }
 
   // ===================== epilogue: merge this CTA's partial state =====================
-#ifdef EVQ_PARTITION
-  evq_cons_sync();   // all appends of this CTA are counted
-  for (u32 p = tid; p < (1u << P.part_bits); p += EVQ_NCONS) {
-    const u32 n = scr->pcur[p];
-    P.part_cursor[(u64) p * gridDim.x + blockIdx.x] = n < P.part_cap ? n : (u32) P.part_cap;
-  }
-#endif
 #if EVQ_TIER == 1
 #if EVQ_G1 > 1
   for (u32 g = 0; g < EVQ_G1; ++g) evq_state_flush_smem(sacc, g, tid, P.dense_state);

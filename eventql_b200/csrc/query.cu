@@ -203,8 +203,14 @@ static size_t scratch_bytes(const KernelShape& s) {
   if (s.fast) {   // EvqFastScratch
     const size_t ngen = std::max(1, s.ngen);
     const size_t parts = s.part_bits > 0 ? ((size_t) 1 << s.part_bits) : 0;
+    size_t staging = 0;   // partitioned aggregation: the tile's records ordered by partition + their partition bytes
+    if (s.part_bits > 0) {
+      bool any_null = false;
+      for (int c : s.rec_cols) any_null = any_null || s.cols[c].nullable;
+      staging = (s.rec_cols.size() + (any_null ? 1 : 0)) * 8 * EVQ_TILE_ROWS + EVQ_TILE_ROWS + 32;
+    }
     return round_up(4 * ngen * nwarps + 4 * ngen * (size_t) gen_chunks(s) + 4 * nwarps + 8 * std::max(1, s.nnull) * nwarps +
-                    (size_t) s.nnv * 2 * (EVQ_TILE_ROWS + 8) * 4 + 16 + parts * (2 * 4 + 2 * 8) + 16, 128) + 128;
+                    (size_t) s.nnv * 2 * (EVQ_TILE_ROWS + 8) * 4 + 16 + parts * (2 * 4 + 2 * 8) + 16 + staging, 128) + 128;
   }
   const size_t one = 4 * std::max(1, s.nleb) * nwarps + 4 * std::max(1, s.nnull) * (EVQ_TILE_ROWS / 32) +
                      2 * std::max(1, s.nleb) * EVQ_TILE_ROWS + 4 * nwarps;
@@ -1197,12 +1203,14 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
     base.part_shift = lg - (u32) s.part_bits;
     cudaKernel_t agg = q.module->kernels.at("evq_agg_part");
     uint64_t seg_cap = 0;
-    // every CTA of the table's scan owns one segment of every partition; a segment takes the CTA's share of the rows
-    // (+ 30 % and a constant: the counts are binomial around rows / (grid * partitions)); more is an overflow -> fallback
+    // every partition is one flat array of records; it takes its share of the table's rows (+ 5 % and a constant: the
+    // counts are binomial around rows / partitions); more is an overflow (heavily skewed keys) -> fallback
     auto before = [&](unsigned grid, uint64_t rows, EvqScanParams& P) {
-      seg_cap = rows / ((uint64_t) grid * parts) * 13 / 10 + 64;
-      ensure(q.part_buf, parts * grid * seg_cap * nrec * 8 + 256);
-      ensure(q.part_cursor, parts * grid * 4 + 512);   // (+ the pass-2 progress counter behind the segment counts)
+      (void) grid;
+      seg_cap = rows / parts * 21 / 20 + 4096;
+      ensure(q.part_buf, parts * seg_cap * nrec * 8 + 256);
+      ensure(q.part_cursor, round_up(parts * 4, 256) + 256);   // (+ the pass-2 progress counter behind the partition cursors)
+      EVQ_CUDA(cudaMemsetAsync(q.part_cursor.p, 0, round_up(parts * 4, 256) + 256, ctx->stream));
       P.part_buf = q.part_buf.as<u64>();
       P.part_cursor = q.part_cursor.as<u32>();
       P.part_cap = seg_cap;
@@ -1215,20 +1223,20 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
       ap.part_cursor = q.part_cursor.as<u32>();
       ap.part_cap = seg_cap;
       ap.nparts = (u32) parts;
-      ap.nseg = grid;
+      ap.nseg = 0;
       ap.status = base.status;
       ap.counters = base.counters;
-      ap.bar = (u32*) ((uint8_t*) q.part_cursor.p + round_up(parts * grid * 4, 256));
+      ap.bar = (u32*) ((uint8_t*) q.part_cursor.p + round_up(parts * 4, 256));
       ap.window = 2;
       if (const char* e = getenv("EVQGPU_AGG_WINDOW")) ap.window = (u32) std::max(1, atoi(e));
-      EVQ_CUDA(cudaMemsetAsync(ap.bar, 0, 4, ctx->stream));
       // all CTAs must be resident (they wait for each other): a cooperative launch of at most what the device holds
       int per_sm = 0;
       EVQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*) agg, 256, 0));
       unsigned g2 = (unsigned) ctx->sm_count * (unsigned) std::max(1, std::min(per_sm, 8));
       if (const char* e = getenv("EVQGPU_AGG_CTAS")) g2 = (unsigned) ctx->sm_count * (unsigned) std::max(1, std::min(per_sm, atoi(e)));
       void* args[] = {&ap};
-      EVQ_CUDA(cudaLaunchCooperativeKernel((const void*) agg, dim3(std::min(g2, grid)), dim3(256), args, 0, ctx->stream));
+      (void) grid;
+      EVQ_CUDA(cudaLaunchCooperativeKernel((const void*) agg, dim3(g2), dim3(256), args, 0, ctx->stream));
       ctx->kernel_launches++;
       q.stats.kernel_launches++;
     };
