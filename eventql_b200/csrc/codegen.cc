@@ -1071,6 +1071,15 @@ static std::string gen_row_functions(const evqgpu_query& q, const KernelShape& s
     os << "__device__ __forceinline__ void evq_accumulate_global(const EvqRow& row, u64* state, u32& err) {\n";
     gen_updates(os, q, shape);
     os << "}\n#undef EVQ_UPD\n#undef EVQ_UPD_C\n#undef EVQ_GPTR\n";
+    if (shape.slice_slots > 0) {   // the same on a slot of a table slice in shared memory (`state` = its shared-window address)
+      os << "#define EVQ_UPD(st, op, v) evq_state_atomic_smem<op>(state + 8u * (st), (v))\n";
+      os << "#define EVQ_UPD_C(st, cw, v) { const u64 _v = (v); const u64 _o = evq_add_ret_smem(state + 8u * (st), _v); "
+            "if (_o + _v < _v) evq_state_atomic_smem<EVQ_OP_ADD_U64>(state + 8u * (cw), 1ull); }\n";
+      os << "#define EVQ_GPTR(st) ((u64*) 0)\n";
+      os << "__device__ __forceinline__ void evq_accumulate_smem(const EvqRow& row, u32 state, u32& err) {\n";
+      gen_updates(os, q, shape);
+      os << "}\n#undef EVQ_UPD\n#undef EVQ_UPD_C\n#undef EVQ_GPTR\n";
+    }
   } else if (shape.tier == 3) {
     // scan-only projection: select list evaluated on the rows that pass, packed SVector elements in table order
     os << "__device__ __forceinline__ void evq_project(const EvqRow& row, const EvqScanParams& P, u64 out_row, u32& err) {\n";
@@ -1239,6 +1248,230 @@ static std::string gen_group_kernels(const evqgpu_query& q, const KernelShape& s
     os << "  if (err) atomicOr(A.status, err);\n}\n";
   }
 
+  // ---- partitioned aggregation with shared-memory table slices (the default form of the hash tier beyond L2).
+  // The L2-resident form above is bound by the rate of scattered L2 requests (a probe + one atomic per state word and row,
+  // profiles/README.md round 2).  Here the records are partitioned once more (evq_repart: every first-level partition into
+  // 2^sub_bits sub-partitions by the next bits of the home slot), until the table slice of one sub-partition
+  // (slice_slots slots) fits shared memory; evq_agg_smem then takes one sub-partition at a time: slice in (coalesced),
+  // records aggregated with shared-memory atomics (probing wraps inside the slice), slice out.  Per row no request
+  // leaves the SM except the sequential read of its record.
+  if (shape.tier == 2 && shape.part_bits > 0 && shape.slice_slots > 0) {
+    os << "#define EVQ_SLOT_WORDS " << 1 + nk + nstate << "\n#define EVQ_RP_TILE 2048\n";
+    os << "struct EvqRepartParams { EvqHashTable ht; const u64* in; const u32* in_cursor; u64 in_cap; u64* out; u32* out_cursor; u64 out_cap; "
+          "u32* status; u32 nparts; u32 sub_bits; u32 sub_shift; u32 pad; };\n";
+    os << R"EVQ(extern "C" __global__ void __launch_bounds__(256) evq_repart(const __grid_constant__ EvqRepartParams R) {
+  extern __shared__ __align__(128) u8 evq_smem[];
+  u64* prec = (u64*) evq_smem;                          // the tile's records ordered by sub-partition
+  u32* hist = (u32*) (prec + EVQ_RP_TILE * EVQ_NREC);   // [256] records of the tile per sub-partition
+  u32* scan = hist + 256;                               // [256] ... before the sub-partition
+  u32* base = scan + 256;                               // [256] where the run goes (claimed from the global cursors)
+  u32* wsum = base + 256;                               // [8] warp totals of the scan
+  u32* tpre = wsum + 8;                                 // [257] tiles before every first-level partition
+  u8* ppart = (u8*) (tpre + 260);                       // [EVQ_RP_TILE] the sub-partition of every staged record
+  const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const u32 hist_sa = evq_smem_u32(hist);
+  const u32 nsub = 1u << R.sub_bits;
+  u32 err = 0;
+  hist[tid] = 0u;
+  if (tid == 0) {
+    u32 t = 0;
+    for (u32 p = 0; p < R.nparts; ++p) {
+      tpre[p] = t;
+      const u32 cur = R.in_cursor[p];
+      const u32 n = cur < R.in_cap ? cur : (u32) R.in_cap;
+      t += (n + EVQ_RP_TILE - 1u) / EVQ_RP_TILE;
+    }
+    tpre[R.nparts] = t;
+  }
+  __syncthreads();
+  const u32 ntiles = tpre[R.nparts];
+  for (u32 g = blockIdx.x; g < ntiles; g += gridDim.x) {
+    u32 lo = 0, hi = R.nparts;   // the partition of tile g: last p with tpre[p] <= g
+    while (hi - lo > 1u) { const u32 mid = (lo + hi) >> 1; if (tpre[mid] <= g) lo = mid; else hi = mid; }
+    const u32 part = lo;
+    const u32 cur = R.in_cursor[part];
+    const u32 n = cur < R.in_cap ? cur : (u32) R.in_cap;
+    const u64* src = R.in + (u64) part * R.in_cap * EVQ_NREC;
+    const u32 t0 = (g - tpre[part]) * EVQ_RP_TILE;
+    EvqRow row[8];
+    u32 pr[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const u32 i = t0 + (u32) j * 256u + tid;
+      pr[j] = ~0u;
+      if (i < n) evq_row_load(src + (u64) i * EVQ_NREC, row[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const u32 i = t0 + (u32) j * 256u + tid;
+      if (i < n) {
+        u64 key[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
+        u32 ktag[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
+        u64 fpv, slot;
+        evq_keys(row[j], key, ktag, err);
+        evq_ht_hash<EVQ_NKEYS>(R.ht, key, ktag, fpv, slot);
+        const u32 sub = (u32) (slot >> R.sub_shift) & (nsub - 1u);
+        u32 rank;
+        asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(rank) : "r"(hist_sa + 4u * sub));
+        pr[j] = sub | (rank << 8);
+      }
+    }
+    __syncthreads();
+    const u32 c = hist[tid];
+    u32 incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (u32) o) incl += v;
+    }
+    if (lane == 31u) wsum[warp] = incl;
+    __syncthreads();
+    u32 before = incl - c, total = 0;
+#pragma unroll
+    for (u32 w = 0; w < 8; ++w) {
+      const u32 x = wsum[w];
+      if (w < warp) before += x;
+      total += x;
+    }
+    hist[tid] = 0u;
+    scan[tid] = before;
+    base[tid] = c ? atomicAdd(R.out_cursor + (((u64) part << R.sub_bits) | tid), c) : 0u;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (pr[j] != ~0u) {
+        const u32 sub = pr[j] & 255u;
+        const u32 at = scan[sub] + (pr[j] >> 8);
+        evq_row_store(row[j], prec + (size_t) at * EVQ_NREC);
+        ppart[at] = (u8) sub;
+      }
+    }
+    __syncthreads();
+#if EVQ_NREC % 2 == 0
+    {
+      constexpr u32 U = EVQ_NREC / 2;
+      const ulonglong2* st = (const ulonglong2*) prec;
+      for (u32 j = tid; j < total * U; j += 256u) {
+        const u32 i = j / U, w = j % U;
+        const u32 sub = ppart[i];
+        const u64 pos = (u64) base[sub] + (i - scan[sub]);
+        if (pos < R.out_cap) ((ulonglong2*) (R.out + ((((u64) part << R.sub_bits) | sub) * R.out_cap + pos) * EVQ_NREC))[w] = st[j];
+        else err |= EVQ_ERR_PART_FULL;
+      }
+    }
+#else
+    for (u32 j = tid; j < total * EVQ_NREC; j += 256u) {
+      const u32 i = j / EVQ_NREC, w = j % EVQ_NREC;
+      const u32 sub = ppart[i];
+      const u64 pos = (u64) base[sub] + (i - scan[sub]);
+      if (pos < R.out_cap) R.out[((((u64) part << R.sub_bits) | sub) * R.out_cap + pos) * EVQ_NREC + w] = prec[j];
+      else err |= EVQ_ERR_PART_FULL;
+    }
+#endif
+    __syncthreads();
+  }
+  if (err) atomicOr(R.status, err);
+}
+struct EvqAggSmemParams { EvqHashTable ht; const u64* buf; const u32* cursor; u64 cap; u32* status; u32 nsub_total; u32 slice_slots; };
+#define EVQ_AG_THREADS 1024
+// the table slice of sub-partition sp into a shared-memory buffer: asynchronous 8-byte copies (all in flight at once), one commit group
+__device__ __forceinline__ void evq_slice_load(const EvqAggSmemParams& A, u32 sp, u32 dst_sa) {
+  const u64* g = A.ht.slots + (u64) sp * A.slice_slots * A.ht.stride;
+  for (u32 i = threadIdx.x; i < A.slice_slots * EVQ_SLOT_WORDS; i += EVQ_AG_THREADS) {
+    const u64* src = g + (u64) (i / EVQ_SLOT_WORDS) * A.ht.stride + i % EVQ_SLOT_WORDS;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst_sa + 8u * i), "l"(src) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ u32 evq_next_sub(const EvqAggSmemParams& A, u32 sp) {   // the next sub-partition of this CTA that has records
+  while (sp < A.nsub_total && A.cursor[sp] == 0u) sp += gridDim.x;
+  return sp;
+}
+extern "C" __global__ void __launch_bounds__(EVQ_AG_THREADS) evq_agg_smem(const __grid_constant__ EvqAggSmemParams A) {
+  extern __shared__ __align__(128) u8 evq_smem[];
+  // two slice buffers [slice_slots][EVQ_SLOT_WORDS] (fingerprint, keys, state words): the next sub-partition's slice is
+  // copied in while the current one is aggregated
+  const u32 tab_sa0 = evq_smem_u32(evq_smem);
+  const u32 buf_bytes = A.slice_slots * (EVQ_SLOT_WORDS * 8u);
+  const u32 tid = threadIdx.x;
+  const u32 S = A.slice_slots, smask = A.slice_slots - 1u;
+  u32 err = 0;
+  u32 sp = evq_next_sub(A, blockIdx.x);
+  u32 cur_buf = 0;
+  if (sp < A.nsub_total) evq_slice_load(A, sp, tab_sa0);
+  while (sp < A.nsub_total) {
+    const u32 nsp = evq_next_sub(A, sp + gridDim.x);
+    if (nsp < A.nsub_total) {
+      evq_slice_load(A, nsp, tab_sa0 + (cur_buf ^ 1u) * buf_bytes);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const u32 tab_sa = tab_sa0 + cur_buf * buf_bytes;
+    const u32 cur = A.cursor[sp];
+    const u32 n = cur < A.cap ? cur : (u32) A.cap;
+    const u64* src = A.buf + (u64) sp * A.cap * EVQ_NREC;
+    // (the thread's next record is loaded while the current one is aggregated)
+    EvqRow nxt;
+    if (tid < n) evq_row_load(src + (u64) tid * EVQ_NREC, nxt);
+    for (u32 i = tid; i < n; i += EVQ_AG_THREADS) {
+      {
+        const EvqRow rowj = nxt;
+        if (i + EVQ_AG_THREADS < n) evq_row_load(src + (u64) (i + EVQ_AG_THREADS) * EVQ_NREC, nxt);
+        {
+          u64 key[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
+          u32 ktag[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
+          u64 fpv, slot;
+          evq_keys(rowj, key, ktag, err);
+          evq_ht_hash<EVQ_NKEYS>(A.ht, key, ktag, fpv, slot);
+          u32 l = (u32) slot & smask;
+          u32 found = 0;
+          bool have = false;
+          for (u32 probes = 0; probes < S; ++probes) {
+            const u32 sa = tab_sa + l * (EVQ_SLOT_WORDS * 8u);
+            u64 c = evq_lds64(sa);
+            if (c == 0ull) {
+              c = evq_cas_smem(sa, 0ull, fpv | 2ull);
+              if (c == 0ull) {   // claimed: keys, then the final fingerprint
+#pragma unroll
+                for (int k = 0; k < EVQ_NKEYS; ++k) evq_sts64(sa + 8u * (1u + k), key[k]);
+                __threadfence_block();
+                evq_sts64(sa, fpv);
+                found = sa;
+                have = true;
+                break;
+              }
+            }
+            if ((c | 2ull) == (fpv | 2ull)) {
+              while (c & 2ull) c = evq_lds64(sa);   // the claimant is still writing the keys
+              bool same = true;
+#pragma unroll
+              for (int k = 0; k < EVQ_NKEYS; ++k) same = same && evq_lds64(sa + 8u * (1u + k)) == key[k];
+              if (same) { found = sa; have = true; break; }
+            }
+            l = (l + 1u) & smask;
+          }
+          if (!have) err |= EVQ_ERR_TABLE_FULL;
+          else evq_accumulate_smem(rowj, found + 8u * (1u + EVQ_NKEYS), err);
+        }
+      }
+    }
+    __syncthreads();
+    {
+      u64* g = A.ht.slots + (u64) sp * S * A.ht.stride;
+      for (u32 i = tid; i < S * EVQ_SLOT_WORDS; i += EVQ_AG_THREADS)
+        g[(u64) (i / EVQ_SLOT_WORDS) * A.ht.stride + i % EVQ_SLOT_WORDS] = evq_lds64(tab_sa + 8u * i);
+    }
+    __syncthreads();
+    sp = nsp;
+    cur_buf ^= 1u;
+  }
+  if (err) atomicOr(A.status, err);
+}
+)EVQ";
+  }
+
   // ---- the tail of a dense-tier execution: ONE kernel (one CTA) behind the scan launches that
   //   (1) multi-rank: pushes this rank's state words into every peer's exchange buffer over NVLink (P2P stores), raises its
   //       flag there, waits for the peers' flags and combines all ranks' words in rank order (GroupByMergeExpression,
@@ -1343,6 +1576,7 @@ std::string generate_source(const evqgpu_query& q, const KernelShape& shape_in) 
     bool any_null = false;
     for (int c : shape.rec_cols) any_null = any_null || shape.cols[c].nullable;
     os << "#define EVQ_PARTITION 1\n#define EVQ_MAX_PARTS " << (1 << shape.part_bits) << "\n#define EVQ_NREC " << shape.rec_cols.size() + (any_null ? 1 : 0) << "\n";
+    if (shape.slice_slots > 0) os << "#define EVQ_SMEM_SLICES 1\n";
   }
   if (getenv("EVQGPU_DRYRUN")) os << "#define EVQ_DRYRUN 1\n";
   if (shape.fast) os << "#define EVQ_KT " << shape.kt << "\n";

@@ -79,10 +79,12 @@ extern "C" int evqgpu_debug_generate(const evqgpu_query_desc* desc, const evqgpu
     for (int t : tiers) {
       s.tier = t;
       s.part_bits = 0;
+      s.slice_slots = 0;
       s.rec_cols.clear();
       if (t == 4) {   // the hash tier as partitioned aggregation (64 record partitions)
         s.tier = 2;
         s.part_bits = 6;
+        s.slice_slots = 1024;   // (+ the second partitioning level and the shared-memory table slices)
         std::vector<bool> used(q.input_columns.size(), false);
         for (const auto& g : q.group) collect_columns(g.get(), used);
         for (const auto& item : q.select)

@@ -636,6 +636,70 @@ __device__ __forceinline__ void evq_state_atomic(u64* addr, u64 v) {
   }
 }
 
+// the same on a state word in shared memory (partitioned aggregation: the table slice of a partition lives in shared
+// memory while the partition's records are aggregated).  64-bit shared atomics are compare-and-swap loops in SASS.
+__device__ __forceinline__ u64 evq_lds64(u32 sa) {
+  u64 v;
+  asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(sa) : "memory");
+  return v;
+}
+__device__ __forceinline__ void evq_sts64(u32 sa, u64 v) {
+  asm volatile("st.volatile.shared.u64 [%0], %1;" :: "r"(sa), "l"(v) : "memory");
+}
+__device__ __forceinline__ u64 evq_cas_smem(u32 sa, u64 cmp, u64 val) {
+  u64 o;
+  asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(o) : "r"(sa), "l"(cmp), "l"(val) : "memory");
+  return o;
+}
+__device__ __forceinline__ u64 evq_add_ret_smem(u32 sa, u64 v) {
+  u64 o;
+  asm volatile("atom.shared.add.u64 %0, [%1], %2;" : "=l"(o) : "r"(sa), "l"(v) : "memory");
+  return o;
+}
+template <int OP>
+__device__ __forceinline__ void evq_state_atomic_smem(u32 sa, u64 v) {
+  switch (OP) {
+    case EVQ_OP_ADD_U64: {
+      // two NATIVE 32-bit atomics instead of a 64-bit compare-and-swap loop (whose lanes retry one after the other): the
+      // low words add up modulo 2^32, and the atomic that wraps the low word carries into the high word - every carry
+      // is seen by exactly one thread, so the final 64-bit sum is exact (nobody reads the word before the CTA's barrier)
+      const u32 lo = (u32) v;
+      u32 hi = (u32) (v >> 32);
+      u32 old;
+      asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(sa), "r"(lo) : "memory");
+      hi += (old + lo < old) ? 1u : 0u;
+      if (hi) asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(sa + 4u), "r"(hi) : "memory");
+      break;
+    }
+    case EVQ_OP_ADD_F64: asm volatile("red.shared.add.f64 [%0], %1;" :: "r"(sa), "d"(__longlong_as_double((i64) v)) : "memory"); break;
+    // minima / maxima change rarely once a group has seen a few rows: look first, update only when the value improves
+    case EVQ_OP_MIN_U64: if (v < evq_lds64(sa)) asm volatile("red.shared.min.u64 [%0], %1;" :: "r"(sa), "l"(v) : "memory"); break;
+    case EVQ_OP_MAX_U64: if (v > evq_lds64(sa)) asm volatile("red.shared.max.u64 [%0], %1;" :: "r"(sa), "l"(v) : "memory"); break;
+    case EVQ_OP_MIN_I64: if ((i64) v < (i64) evq_lds64(sa)) asm volatile("red.shared.min.s64 [%0], %1;" :: "r"(sa), "l"(v) : "memory"); break;
+    case EVQ_OP_MAX_I64: if ((i64) v > (i64) evq_lds64(sa)) asm volatile("red.shared.max.s64 [%0], %1;" :: "r"(sa), "l"(v) : "memory"); break;
+    case EVQ_OP_MIN_F64: {
+      const f64 x = __longlong_as_double((i64) v);
+      u64 old = evq_lds64(sa);
+      while (x < __longlong_as_double((i64) old)) {
+        const u64 prev = evq_cas_smem(sa, old, v);
+        if (prev == old) break;
+        old = prev;
+      }
+      break;
+    }
+    default: {
+      const f64 x = __longlong_as_double((i64) v);
+      u64 old = evq_lds64(sa);
+      while (x > __longlong_as_double((i64) old)) {
+        const u64 prev = evq_cas_smem(sa, old, v);
+        if (prev == old) break;
+        old = prev;
+      }
+      break;
+    }
+  }
+}
+
 // keep the (ordinal|tag, value) pair with the smallest first word (global memory, 16-byte aligned)
 __device__ __forceinline__ void evq_first_update(u64* pair, u64 ordtag, u64 value) {
   u64 cur = *(volatile u64*) pair;

@@ -1061,6 +1061,20 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
         !getenv("EVQGPU_NO_PARTITION")) {
       int bits = 1;
       while ((table_bytes >> bits) > slice && bits < 8) ++bits;
+      // table slices in shared memory (the default): slices of <= 100 KB of slot words, reached over two partitioning levels of
+      // at most 8 bits each; a table beyond that (or EVQGPU_NO_SMEM_SLICES) keeps the L2-resident form of pass 2
+      {
+        const uint64_t words = 1 + nk + q.state_ops.size();
+        uint64_t slots = 64;
+        while (slots * 2 * words * 8 <= 100 * 1024) slots *= 2;   // (two buffers of <= 100 KB: one CTA of 1024 threads per SM)
+        int need = 0;
+        while ((ht_want >> need) > slots) ++need;
+        if (need <= 16 && !getenv("EVQGPU_NO_SMEM_SLICES")) {
+          s.slice_slots = (int) slots;
+          bits = std::max(std::min(bits, need), need - 8);
+          if (bits < 1) bits = 1;
+        }
+      }
       s.part_bits = bits;
       std::vector<bool> used(q.input_columns.size(), false);
       for (const auto& g : q.group) collect_columns(g.get(), used);
@@ -1083,7 +1097,7 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
     std::string sig;
     char buf[160];
     snprintf(buf, sizeof(buf), "t%d g%d n%d s%d c%d f%d x%d N%d K%d P%d|", s.tier, s.g1, s.ncons, s.nstages, s.min_ctas, (int) s.fast,
-             (int) s.use_subidx, q.nnarrow, s.kt * 1000 + (s.filter_stream + 1) * 10 + (int) s.dense_global, s.part_bits);
+             (int) s.use_subidx, q.nnarrow, s.kt * 1000 + (s.filter_stream + 1) * 10 + (int) s.dense_global, s.part_bits + 100 * s.slice_slots);
     sig += buf;
     for (const auto& c : s.cols) {
       snprintf(buf, sizeof(buf), "%d.%u.%u.%d.%u.%u.%u%s.%d.%d.%d.%llu.%llu.%llu.%d;", (int) c.used, c.sql_type, c.kind, (int) c.nullable, c.dmax, c.bits,
@@ -1104,6 +1118,7 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
       std::vector<std::string> names = {"evq_scan", "evq_init", "evq_emit"};
       if (s.tier == 1 && !s.dense_global) names.push_back("evq_tail");
       if (s.part_bits > 0) names.push_back("evq_agg_part");
+      if (s.part_bits > 0 && s.slice_slots > 0) { names.push_back("evq_repart"); names.push_back("evq_agg_smem"); }
       q.module = jit_compile(ctx, q.kernel_source, names, &ms);
       q.module_sig = sig;
       if (ms > 0 && q.module->from_disk) q.stats.jit_disk_hits++;
@@ -1205,9 +1220,17 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
     uint64_t seg_cap = 0;
     // every partition is one flat array of records; it takes its share of the table's rows (+ 5 % and a constant: the
     // counts are binomial around rows / partitions); more is an overflow (heavily skewed keys) -> fallback
+    // a partition's capacity: its share of the rows + 25 % + 8 standard deviations of a binomial count + a constant (the
+    // rows of one group go together: with few groups per partition the counts spread far more than independent rows would)
+    auto cap_of = [](uint64_t rows, uint64_t nparts) {
+      const uint64_t avg = rows / nparts + 1;
+      return avg * 5 / 4 + 8 * (uint64_t) sqrt((double) avg) + 1024;
+    };
+    uint64_t table_rows = 0;
     auto before = [&](unsigned grid, uint64_t rows, EvqScanParams& P) {
       (void) grid;
-      seg_cap = rows / parts * 21 / 20 + 4096;
+      table_rows = rows;
+      seg_cap = cap_of(rows, parts);
       ensure(q.part_buf, parts * seg_cap * nrec * 8 + 256);
       ensure(q.part_cursor, round_up(parts * 4, 256) + 256);   // (+ the pass-2 progress counter behind the partition cursors)
       EVQ_CUDA(cudaMemsetAsync(q.part_cursor.p, 0, round_up(parts * 4, 256) + 256, ctx->stream));
@@ -1215,7 +1238,69 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
       P.part_cursor = q.part_cursor.as<u32>();
       P.part_cap = seg_cap;
     };
+    auto after_smem = [&](unsigned grid) {
+      (void) grid;
+      // the slice of a sub-partition: slice_slots slots, or the whole first-level slice when that is smaller already
+      u32 lgs = 0;
+      while ((1u << lgs) < (u32) s.slice_slots) ++lgs;
+      int sub_bits = (int) lg - (int) s.part_bits - (int) lgs;
+      u32 slice_slots = (u32) s.slice_slots;
+      if (sub_bits < 0) { sub_bits = 0; slice_slots = (u32) (base.ht.cap >> s.part_bits); }
+      const uint64_t nsub_total = parts << sub_bits;
+      const u64* buf = q.part_buf.as<u64>();
+      const u32* cursor = q.part_cursor.as<u32>();
+      uint64_t cap = seg_cap;
+      if (sub_bits > 0) {
+        cudaKernel_t rp = q.module->kernels.at("evq_repart");
+        const uint64_t cap2 = cap_of(table_rows, nsub_total);
+        ensure(q.part_buf2, nsub_total * cap2 * nrec * 8 + 256);
+        ensure(q.part_cursor2, nsub_total * 4 + 256);
+        EVQ_CUDA(cudaMemsetAsync(q.part_cursor2.p, 0, nsub_total * 4, ctx->stream));
+        RepartParams rpp;
+        memset(&rpp, 0, sizeof(rpp));
+        rpp.ht = base.ht;
+        rpp.in = buf;
+        rpp.in_cursor = cursor;
+        rpp.in_cap = seg_cap;
+        rpp.out = q.part_buf2.as<u64>();
+        rpp.out_cursor = q.part_cursor2.as<u32>();
+        rpp.out_cap = cap2;
+        rpp.status = base.status;
+        rpp.nparts = (u32) parts;
+        rpp.sub_bits = (u32) sub_bits;
+        rpp.sub_shift = lgs;
+        const size_t smem = 2048 * nrec * 8 + (3 * 256 + 8 + 260) * 4 + 2048 + 128;
+        EVQ_CUDA(cudaFuncSetAttribute((const void*) rp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        int per_sm = 0;
+        EVQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*) rp, 256, smem));
+        void* args[] = {&rpp};
+        launch(ctx, rp, dim3((unsigned) ctx->sm_count * (unsigned) std::max(1, per_sm)), dim3(256), smem, args);
+        q.stats.kernel_launches++;
+        buf = q.part_buf2.as<u64>();
+        cursor = q.part_cursor2.as<u32>();
+        cap = cap2;
+      }
+      cudaKernel_t ag = q.module->kernels.at("evq_agg_smem");
+      AggSmemParams ap;
+      memset(&ap, 0, sizeof(ap));
+      ap.ht = base.ht;
+      ap.buf = buf;
+      ap.cursor = cursor;
+      ap.cap = cap;
+      ap.status = base.status;
+      ap.nsub_total = (u32) nsub_total;
+      ap.slice_slots = slice_slots;
+      const size_t smem = 2 * (size_t) slice_slots * (1 + nk + nstate) * 8;   // (two buffers: the next slice is copied in meanwhile)
+      EVQ_CUDA(cudaFuncSetAttribute((const void*) ag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      int per_sm = 0;
+      EVQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*) ag, 1024, smem));
+      void* args[] = {&ap};
+      const unsigned g2 = (unsigned) std::min<uint64_t>(nsub_total, (uint64_t) ctx->sm_count * (uint64_t) std::max(1, per_sm));
+      launch(ctx, ag, dim3(g2), dim3(1024), smem, args);
+      q.stats.kernel_launches++;
+    };
     auto after = [&](unsigned grid) {
+      if (s.slice_slots > 0) return after_smem(grid);
       AggParams ap;
       memset(&ap, 0, sizeof(ap));
       ap.ht = base.ht;

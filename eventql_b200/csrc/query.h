@@ -75,6 +75,7 @@ struct KernelShape {
   int ngen = 0;        // fast kernel: LEB128 columns with leb_len >= 2 whose value boundaries are searched in the kernel
   int nnv = 0;         // fast kernel: optional columns decoded through a staging array (ColSig::nv_slot)
   int part_bits = 0;   // tier 2, fast kernel: > 0 = partitioned aggregation with 2^part_bits record partitions (query.cu)
+  int slice_slots = 0; // ... > 0 = second partitioning level + table slices of (at most) this many slots in shared memory
   std::vector<int> rec_cols;   // ... the input columns a record carries (read by the GROUP BY expressions and aggregate arguments)
   int filter_stream = -1;    // stream of the tables' external row filter (FastCSTableScan::setFilter), -1 = none
   bool use_subidx = false;   // fast kernel: variable-length columns take their decode entry points from Column::sub_index
@@ -127,6 +128,27 @@ struct AggParams {
   u32* bar;       // CTAs done per partition, summed (zeroed before the launch)
   u32 window;     // partitions a CTA may run ahead of the slowest one
   u32 pad;
+};
+
+struct RepartParams {   // codegen.cc EvqRepartParams
+  EvqHashTable ht;
+  const u64* in;
+  const u32* in_cursor;
+  u64 in_cap;
+  u64* out;
+  u32* out_cursor;
+  u64 out_cap;
+  u32* status;
+  u32 nparts, sub_bits, sub_shift, pad;
+};
+
+struct AggSmemParams {   // codegen.cc EvqAggSmemParams
+  EvqHashTable ht;
+  const u64* buf;
+  const u32* cursor;
+  u64 cap;
+  u32* status;
+  u32 nsub_total, slice_slots;
 };
 
 struct InitParams {
@@ -198,6 +220,7 @@ struct evqgpu_query {
 
   // device state, reused across executions
   evq::DevBuf merge_recv, merge_send, merge_slots, merge_counts, merge_status;
+  evq::DevBuf part_buf2, part_cursor2;   // ... second level (sub-partitions)
   evq::DevBuf part_buf, part_cursor;   // partitioned aggregation: the records of pass 1 and their per-partition counts
   bool no_partition = false;           // a partition overflowed once (skewed keys): this query keeps the direct hash tier
   uint64_t merge_cap = 0;           // capacity the merged table last needed (kept across executions)

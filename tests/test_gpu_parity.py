@@ -369,13 +369,18 @@ def test_first_row_items(gpu_ctx, tmp_path, shape):
             t.close()
 
 
+@pytest.mark.parametrize("form", ["smem_slices", "l2_slices"])
 @pytest.mark.parametrize("variant", ["uniform", "two_keys_nullable", "skewed_falls_back"])
-def test_partitioned_hash_aggregation(gpu_ctx, tmp_path, monkeypatch, variant):
+def test_partitioned_hash_aggregation(gpu_ctx, tmp_path, monkeypatch, variant, form):
     """Hash tier with a group table far beyond L2: pass 1 writes the passing rows as records into partitions by the top bits of
-    their group's home slot, pass 2 aggregates one partition (one L2-resident table slice) at a time.  Forced here on small
-    tables (EVQGPU_PART_MIN_MB / _SLICE_MB); a partition that overflows (every row the same key) falls back to the direct tier."""
+    their group's home slot.  Default form: the records are partitioned once more until a sub-partition's table slice fits
+    shared memory, and every slice is aggregated there (evq_repart + evq_agg_smem); the other form aggregates one first-level
+    partition (one L2-resident table slice) at a time.  Forced here on small tables (EVQGPU_PART_MIN_MB / _SLICE_MB); a
+    partition that overflows (every row the same key) falls back to the direct tier."""
     monkeypatch.setenv("EVQGPU_PART_MIN_MB", "0")
     monkeypatch.setenv("EVQGPU_PART_SLICE_MB", "1")
+    if form == "l2_slices":
+        monkeypatch.setenv("EVQGPU_NO_SMEM_SLICES", "1")
     cnt = P.call("count", P.lit(1))
     if variant == "uniform":
         spec = T.events_spec(5000)
