@@ -284,7 +284,7 @@ def referenced_columns(plan):
 
 
 STRATEGY = {0: "scan-only", 1: "dense (registers/shared memory)", 2: "global hash table", 3: "direct-addressed group array (L2 atomics)",
-            4: "global hash table, partitioned aggregation (records by home slot, one L2-resident table slice at a time)"}
+            4: "global hash table, partitioned aggregation (records by home slot over two levels, table slices aggregated in shared memory)"}
 
 
 class Job:

@@ -1373,7 +1373,12 @@ static std::string gen_group_kernels(const evqgpu_query& q, const KernelShape& s
   if (err) atomicOr(R.status, err);
 }
 struct EvqAggSmemParams { EvqHashTable ht; const u64* buf; const u32* cursor; u64 cap; u32* status; u32 nsub_total; u32 slice_slots; };
+#ifndef EVQ_AG_THREADS
 #define EVQ_AG_THREADS 1024
+#endif
+#ifndef EVQ_AG_NBUF
+#define EVQ_AG_NBUF 2
+#endif
 // the table slice of sub-partition sp into a shared-memory buffer: asynchronous 8-byte copies (all in flight at once), one commit group
 __device__ __forceinline__ void evq_slice_load(const EvqAggSmemParams& A, u32 sp, u32 dst_sa) {
   const u64* g = A.ht.slots + (u64) sp * A.slice_slots * A.ht.stride;
@@ -1401,24 +1406,32 @@ extern "C" __global__ void __launch_bounds__(EVQ_AG_THREADS) evq_agg_smem(const 
   if (sp < A.nsub_total) evq_slice_load(A, sp, tab_sa0);
   while (sp < A.nsub_total) {
     const u32 nsp = evq_next_sub(A, sp + gridDim.x);
+#if EVQ_AG_NBUF == 2
     if (nsp < A.nsub_total) {
       evq_slice_load(A, nsp, tab_sa0 + (cur_buf ^ 1u) * buf_bytes);
       asm volatile("cp.async.wait_group 1;" ::: "memory");
     } else {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
+#else
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
     __syncthreads();
     const u32 tab_sa = tab_sa0 + cur_buf * buf_bytes;
     const u32 cur = A.cursor[sp];
     const u32 n = cur < A.cap ? cur : (u32) A.cap;
     const u64* src = A.buf + (u64) sp * A.cap * EVQ_NREC;
-    // (the thread's next record is loaded while the current one is aggregated)
-    EvqRow nxt;
-    if (tid < n) evq_row_load(src + (u64) tid * EVQ_NREC, nxt);
+    // (the thread's next three records are on their way while the current one is aggregated)
+    EvqRow q0, q1, q2;
+    if (tid < n) evq_row_load(src + (u64) tid * EVQ_NREC, q0);
+    if (tid + EVQ_AG_THREADS < n) evq_row_load(src + (u64) (tid + EVQ_AG_THREADS) * EVQ_NREC, q1);
+    if (tid + 2u * EVQ_AG_THREADS < n) evq_row_load(src + (u64) (tid + 2u * EVQ_AG_THREADS) * EVQ_NREC, q2);
     for (u32 i = tid; i < n; i += EVQ_AG_THREADS) {
       {
-        const EvqRow rowj = nxt;
-        if (i + EVQ_AG_THREADS < n) evq_row_load(src + (u64) (i + EVQ_AG_THREADS) * EVQ_NREC, nxt);
+        const EvqRow rowj = q0;
+        q0 = q1;
+        q1 = q2;
+        if (i + 3u * EVQ_AG_THREADS < n) evq_row_load(src + (u64) (i + 3u * EVQ_AG_THREADS) * EVQ_NREC, q2);
         {
           u64 key[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
           u32 ktag[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
@@ -1465,7 +1478,11 @@ extern "C" __global__ void __launch_bounds__(EVQ_AG_THREADS) evq_agg_smem(const 
     }
     __syncthreads();
     sp = nsp;
+#if EVQ_AG_NBUF == 2
     cur_buf ^= 1u;
+#else
+    if (sp < A.nsub_total) evq_slice_load(A, sp, tab_sa0);
+#endif
   }
   if (err) atomicOr(A.status, err);
 }
@@ -1576,7 +1593,11 @@ std::string generate_source(const evqgpu_query& q, const KernelShape& shape_in) 
     bool any_null = false;
     for (int c : shape.rec_cols) any_null = any_null || shape.cols[c].nullable;
     os << "#define EVQ_PARTITION 1\n#define EVQ_MAX_PARTS " << (1 << shape.part_bits) << "\n#define EVQ_NREC " << shape.rec_cols.size() + (any_null ? 1 : 0) << "\n";
-    if (shape.slice_slots > 0) os << "#define EVQ_SMEM_SLICES 1\n";
+    if (shape.slice_slots > 0) {
+      os << "#define EVQ_SMEM_SLICES 1\n";
+      if (const char* e = getenv("EVQGPU_AGG_THREADS")) os << "#define EVQ_AG_THREADS " << atoi(e) << "\n";   // (sweep aids, scripts/c4_step.sh)
+      if (const char* e = getenv("EVQGPU_AGG_NBUF")) os << "#define EVQ_AG_NBUF " << atoi(e) << "\n";
+    }
   }
   if (getenv("EVQGPU_DRYRUN")) os << "#define EVQ_DRYRUN 1\n";
   if (shape.fast) os << "#define EVQ_KT " << shape.kt << "\n";

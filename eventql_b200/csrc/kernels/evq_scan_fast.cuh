@@ -860,8 +860,10 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
       }
     }
     evq_cons_sync();
+    constexpr u32 PER = EVQ_MAX_PARTS >= 32 ? EVQ_MAX_PARTS / 32 : 1;
+    u32 claim[PER];   // warp 0: the run starts claimed from the global cursors - asked for here, needed only for the copy-out,
+                      // so the round trip of the atomics overlaps with the staging of the records
     if (tid < 32u) {
-      constexpr u32 PER = EVQ_MAX_PARTS >= 32 ? EVQ_MAX_PARTS / 32 : 1;
       u32 n[PER], sum = 0;
 #pragma unroll
       for (u32 j = 0; j < PER; ++j) {
@@ -882,7 +884,7 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
         if (p < EVQ_MAX_PARTS) {
           scr->phist[p] = 0u;
           scr->pscan[p] = before;
-          scr->pbase[p] = n[j] ? atomicAdd(P.part_cursor + p, n[j]) : 0u;
+          claim[j] = n[j] ? atomicAdd(P.part_cursor + p, n[j]) : 0u;
           before += n[j];
         }
       }
@@ -899,6 +901,11 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
         evq_row_store(row, scr->prec + (size_t) at * EVQ_NREC);
         scr->ppart[at] = (u8) part;
       }
+    }
+    if (tid < 32u) {
+#pragma unroll
+      for (u32 j = 0; j < PER; ++j)
+        if (tid * PER + j < EVQ_MAX_PARTS) scr->pbase[tid * PER + j] = claim[j];
     }
     evq_cons_sync();
     {

@@ -1290,13 +1290,16 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
       ap.status = base.status;
       ap.nsub_total = (u32) nsub_total;
       ap.slice_slots = slice_slots;
-      const size_t smem = 2 * (size_t) slice_slots * (1 + nk + nstate) * 8;   // (two buffers: the next slice is copied in meanwhile)
+      int nbuf = 2, threads = 1024;   // (two buffers: the next slice is copied in meanwhile)
+      if (const char* e = getenv("EVQGPU_AGG_NBUF")) nbuf = atoi(e) == 1 ? 1 : 2;
+      if (const char* e = getenv("EVQGPU_AGG_THREADS")) threads = atoi(e);
+      const size_t smem = (size_t) nbuf * slice_slots * (1 + nk + nstate) * 8;
       EVQ_CUDA(cudaFuncSetAttribute((const void*) ag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
       int per_sm = 0;
-      EVQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*) ag, 1024, smem));
+      EVQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*) ag, threads, smem));
       void* args[] = {&ap};
       const unsigned g2 = (unsigned) std::min<uint64_t>(nsub_total, (uint64_t) ctx->sm_count * (uint64_t) std::max(1, per_sm));
-      launch(ctx, ag, dim3(g2), dim3(1024), smem, args);
+      launch(ctx, ag, dim3(g2), dim3((unsigned) threads), smem, args);
       q.stats.kernel_launches++;
     };
     auto after = [&](unsigned grid) {

@@ -480,8 +480,8 @@ typedef struct evqgpu_query_stats {
   uint32_t kernel_launches;      /* device kernels launched by the last execute */
   uint32_t strategy;             /* 0 scan-only, 1 register/shared-memory low-cardinality, 2 global hash table,
                                     3 direct-addressed group array in global memory (key tuples spanning a small box),
-                                    4 global hash table filled by partitioned aggregation (records partitioned by home slot,
-                                    one L2-resident table slice at a time) */
+                                    4 global hash table filled by partitioned aggregation (records partitioned by home slot over
+                                    two levels, every table slice aggregated in shared memory) */
   float jit_ms;                  /* time spent making the specialised kernel loadable in the last execute: NVRTC, or reading the
                                     cubin from the on-disk cache ($EVQGPU_CACHE_DIR, default ~/.cache/evqgpu); 0 = already loaded */
   float scan_ms;                 /* summed device time of the scan kernel launches since the last finish
