@@ -378,7 +378,11 @@ EVQGPU_API int evqgpu_query_fetch(evqgpu_query* q, uint64_t row0, uint64_t max_r
  *
  * String support of a plan (no CPU fallback for the rest - EVQGPU_ERR_UNSUPPORTED): eq / neq between string columns and
  * string literals (expressions/boolean.cc:235-257, 355-377: the NULL tag is dropped, a NULL compares as ""), bare string
- * columns as GROUP BY expressions and select items.  They run on dictionary codes shared by all tables of a context. */
+ * columns as GROUP BY expressions and select items - these run on dictionary codes shared by all tables of a context;
+ * lt / lte / gt / gte (strncmp over the shorter length, then the lengths) and startswith / endswith between a string
+ * column and a literal - evaluated once per dictionary entry, applied as a 1-byte-per-row verdict column.  In a
+ * multi-rank job evqgpu_query_prepare synchronises the ranks' dictionaries first, so string keys and predicates merge like
+ * integers.  LIKE raises "not yet implemented" in the reference and is refused here. */
 EVQGPU_API int evqgpu_query_fetch_strings(evqgpu_query* q, uint32_t column, uint64_t row0, uint64_t max_rows, void* dst,
                                           uint64_t cap, uint64_t* nrows_out, uint64_t* nbytes_out);
 
