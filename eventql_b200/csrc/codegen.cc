@@ -1376,17 +1376,24 @@ struct EvqAggSmemParams { EvqHashTable ht; const u64* buf; const u32* cursor; u6
 #ifndef EVQ_AG_THREADS
 #define EVQ_AG_THREADS 1024
 #endif
-#ifndef EVQ_AG_NBUF
-#define EVQ_AG_NBUF 2
-#endif
-// the table slice of sub-partition sp into a shared-memory buffer: asynchronous 8-byte copies (all in flight at once), one commit group
-__device__ __forceinline__ void evq_slice_load(const EvqAggSmemParams& A, u32 sp, u32 dst_sa) {
-  const u64* g = A.ht.slots + (u64) sp * A.slice_slots * A.ht.stride;
-  for (u32 i = threadIdx.x; i < A.slice_slots * EVQ_SLOT_WORDS; i += EVQ_AG_THREADS) {
-    const u64* src = g + (u64) (i / EVQ_SLOT_WORDS) * A.ht.stride + i % EVQ_SLOT_WORDS;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst_sa + 8u * i), "l"(src) : "memory");
+// The table of a sliced plan is COMPACT (stride == EVQ_SLOT_WORDS): a slice is one contiguous block, moved by the TMA -
+// one bulk copy in (completion on an mbarrier), one bulk copy out (bulk async-group) per sub-partition, issued by thread 0.
+#define EVQ_BULK_CHUNK 32768u
+__device__ __forceinline__ void evq_slice_load(const EvqAggSmemParams& A, u32 sp, u8* dst, u64* bar, u32 bytes) {
+  // (the bulk store that last read this buffer must be done reading it)
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  evq_mbar_arrive_expect_tx(bar, bytes);
+  const u8* g = (const u8*) (A.ht.slots + (u64) sp * A.slice_slots * EVQ_SLOT_WORDS);
+  for (u32 off = 0; off < bytes; off += EVQ_BULK_CHUNK)
+    evq_bulk_g2s(dst + off, g + off, bytes - off < EVQ_BULK_CHUNK ? bytes - off : EVQ_BULK_CHUNK, bar);
+}
+__device__ __forceinline__ void evq_slice_store(const EvqAggSmemParams& A, u32 sp, const u8* src, u32 bytes) {
+  u8* g = (u8*) (A.ht.slots + (u64) sp * A.slice_slots * EVQ_SLOT_WORDS);
+  for (u32 off = 0; off < bytes; off += EVQ_BULK_CHUNK) {
+    const u32 nb = bytes - off < EVQ_BULK_CHUNK ? bytes - off : EVQ_BULK_CHUNK;
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(g + off), "r"(evq_smem_u32(src + off)), "r"(nb) : "memory");
   }
-  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ u32 evq_next_sub(const EvqAggSmemParams& A, u32 sp) {   // the next sub-partition of this CTA that has records
   while (sp < A.nsub_total && A.cursor[sp] == 0u) sp += gridDim.x;
@@ -1395,29 +1402,27 @@ __device__ __forceinline__ u32 evq_next_sub(const EvqAggSmemParams& A, u32 sp) {
 extern "C" __global__ void __launch_bounds__(EVQ_AG_THREADS) evq_agg_smem(const __grid_constant__ EvqAggSmemParams A) {
   extern __shared__ __align__(128) u8 evq_smem[];
   // two slice buffers [slice_slots][EVQ_SLOT_WORDS] (fingerprint, keys, state words): the next sub-partition's slice is
-  // copied in while the current one is aggregated
-  const u32 tab_sa0 = evq_smem_u32(evq_smem);
+  // copied in while the current one is aggregated; behind them the two mbarriers of the copies
   const u32 buf_bytes = A.slice_slots * (EVQ_SLOT_WORDS * 8u);
+  u64* bars = (u64*) (evq_smem + 2u * buf_bytes);
   const u32 tid = threadIdx.x;
   const u32 S = A.slice_slots, smask = A.slice_slots - 1u;
   u32 err = 0;
+  if (tid == 0) {
+    evq_mbar_init(&bars[0], 1);
+    evq_mbar_init(&bars[1], 1);
+    evq_mbar_fence_init();
+  }
+  __syncthreads();
   u32 sp = evq_next_sub(A, blockIdx.x);
-  u32 cur_buf = 0;
-  if (sp < A.nsub_total) evq_slice_load(A, sp, tab_sa0);
+  u32 cur_buf = 0, parity = 0;   // bit b of parity: the phase buffer b's next copy completes
+  if (tid == 0 && sp < A.nsub_total) evq_slice_load(A, sp, evq_smem, &bars[0], buf_bytes);
   while (sp < A.nsub_total) {
     const u32 nsp = evq_next_sub(A, sp + gridDim.x);
-#if EVQ_AG_NBUF == 2
-    if (nsp < A.nsub_total) {
-      evq_slice_load(A, nsp, tab_sa0 + (cur_buf ^ 1u) * buf_bytes);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-#else
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-#endif
-    __syncthreads();
-    const u32 tab_sa = tab_sa0 + cur_buf * buf_bytes;
+    if (tid == 0 && nsp < A.nsub_total) evq_slice_load(A, nsp, evq_smem + (cur_buf ^ 1u) * buf_bytes, &bars[cur_buf ^ 1u], buf_bytes);
+    evq_mbar_wait(&bars[cur_buf], (parity >> cur_buf) & 1u);
+    parity ^= 1u << cur_buf;
+    const u32 tab_sa = evq_smem_u32(evq_smem) + cur_buf * buf_bytes;
     const u32 cur = A.cursor[sp];
     const u32 n = cur < A.cap ? cur : (u32) A.cap;
     const u64* src = A.buf + (u64) sp * A.cap * EVQ_NREC;
@@ -1427,63 +1432,53 @@ extern "C" __global__ void __launch_bounds__(EVQ_AG_THREADS) evq_agg_smem(const 
     if (tid + EVQ_AG_THREADS < n) evq_row_load(src + (u64) (tid + EVQ_AG_THREADS) * EVQ_NREC, q1);
     if (tid + 2u * EVQ_AG_THREADS < n) evq_row_load(src + (u64) (tid + 2u * EVQ_AG_THREADS) * EVQ_NREC, q2);
     for (u32 i = tid; i < n; i += EVQ_AG_THREADS) {
-      {
-        const EvqRow rowj = q0;
-        q0 = q1;
-        q1 = q2;
-        if (i + 3u * EVQ_AG_THREADS < n) evq_row_load(src + (u64) (i + 3u * EVQ_AG_THREADS) * EVQ_NREC, q2);
-        {
-          u64 key[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
-          u32 ktag[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
-          u64 fpv, slot;
-          evq_keys(rowj, key, ktag, err);
-          evq_ht_hash<EVQ_NKEYS>(A.ht, key, ktag, fpv, slot);
-          u32 l = (u32) slot & smask;
-          u32 found = 0;
-          bool have = false;
-          for (u32 probes = 0; probes < S; ++probes) {
-            const u32 sa = tab_sa + l * (EVQ_SLOT_WORDS * 8u);
-            u64 c = evq_lds64(sa);
-            if (c == 0ull) {
-              c = evq_cas_smem(sa, 0ull, fpv | 2ull);
-              if (c == 0ull) {   // claimed: keys, then the final fingerprint
+      const EvqRow rowj = q0;
+      q0 = q1;
+      q1 = q2;
+      if (i + 3u * EVQ_AG_THREADS < n) evq_row_load(src + (u64) (i + 3u * EVQ_AG_THREADS) * EVQ_NREC, q2);
+      u64 key[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
+      u32 ktag[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
+      u64 fpv, slot;
+      evq_keys(rowj, key, ktag, err);
+      evq_ht_hash<EVQ_NKEYS>(A.ht, key, ktag, fpv, slot);
+      u32 l = (u32) slot & smask;
+      u32 found = 0;
+      bool have = false;
+      for (u32 probes = 0; probes < S; ++probes) {
+        const u32 sa = tab_sa + l * (EVQ_SLOT_WORDS * 8u);
+        u64 c = evq_lds64(sa);
+        if (c == 0ull) {
+          c = evq_cas_smem(sa, 0ull, fpv | 2ull);
+          if (c == 0ull) {   // claimed: keys, then the final fingerprint
 #pragma unroll
-                for (int k = 0; k < EVQ_NKEYS; ++k) evq_sts64(sa + 8u * (1u + k), key[k]);
-                __threadfence_block();
-                evq_sts64(sa, fpv);
-                found = sa;
-                have = true;
-                break;
-              }
-            }
-            if ((c | 2ull) == (fpv | 2ull)) {
-              while (c & 2ull) c = evq_lds64(sa);   // the claimant is still writing the keys
-              bool same = true;
-#pragma unroll
-              for (int k = 0; k < EVQ_NKEYS; ++k) same = same && evq_lds64(sa + 8u * (1u + k)) == key[k];
-              if (same) { found = sa; have = true; break; }
-            }
-            l = (l + 1u) & smask;
+            for (int k = 0; k < EVQ_NKEYS; ++k) evq_sts64(sa + 8u * (1u + k), key[k]);
+            __threadfence_block();
+            evq_sts64(sa, fpv);
+            found = sa;
+            have = true;
+            break;
           }
-          if (!have) err |= EVQ_ERR_TABLE_FULL;
-          else evq_accumulate_smem(rowj, found + 8u * (1u + EVQ_NKEYS), err);
         }
+        if ((c | 2ull) == (fpv | 2ull)) {
+          while (c & 2ull) c = evq_lds64(sa);   // the claimant is still writing the keys
+          bool same = true;
+#pragma unroll
+          for (int k = 0; k < EVQ_NKEYS; ++k) same = same && evq_lds64(sa + 8u * (1u + k)) == key[k];
+          if (same) { found = sa; have = true; break; }
+        }
+        l = (l + 1u) & smask;
       }
+      if (!have) err |= EVQ_ERR_TABLE_FULL;
+      else evq_accumulate_smem(rowj, found + 8u * (1u + EVQ_NKEYS), err);
     }
+    // the slice goes back: the threads' shared-memory writes become visible to the async proxy, then ONE bulk store
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    {
-      u64* g = A.ht.slots + (u64) sp * S * A.ht.stride;
-      for (u32 i = tid; i < S * EVQ_SLOT_WORDS; i += EVQ_AG_THREADS)
-        g[(u64) (i / EVQ_SLOT_WORDS) * A.ht.stride + i % EVQ_SLOT_WORDS] = evq_lds64(tab_sa + 8u * i);
-    }
-    __syncthreads();
+    if (tid == 0) evq_slice_store(A, sp, evq_smem + cur_buf * buf_bytes, buf_bytes);
     sp = nsp;
-#if EVQ_AG_NBUF == 2
     cur_buf ^= 1u;
-#else
-    if (sp < A.nsub_total) evq_slice_load(A, sp, tab_sa0);
-#endif
   }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   if (err) atomicOr(A.status, err);
 }
 )EVQ";
@@ -1596,7 +1591,6 @@ std::string generate_source(const evqgpu_query& q, const KernelShape& shape_in) 
     if (shape.slice_slots > 0) {
       os << "#define EVQ_SMEM_SLICES 1\n";
       if (const char* e = getenv("EVQGPU_AGG_THREADS")) os << "#define EVQ_AG_THREADS " << atoi(e) << "\n";   // (sweep aids, scripts/c4_step.sh)
-      if (const char* e = getenv("EVQGPU_AGG_NBUF")) os << "#define EVQ_AG_NBUF " << atoi(e) << "\n";
     }
   }
   if (getenv("EVQGPU_DRYRUN")) os << "#define EVQ_DRYRUN 1\n";

@@ -44,11 +44,14 @@ void sha1(const uint8_t* data, size_t len, uint8_t out[20]) {
 
 namespace {
 
+// [off, off + size) inside a file of nbytes - written so that file-supplied 64-bit values cannot wrap the sum
+inline bool out_of_range(uint64_t off, uint64_t size, uint64_t nbytes) { return size > nbytes || off > nbytes - size; }
+
 struct Cursor {
   const uint8_t* p;
   uint64_t n, pos;
   void need(uint64_t k) const {
-    if (pos + k > n) fail(EVQGPU_ERR_FORMAT, "cstable: truncated file (need %llu bytes at offset %llu)",
+    if (pos > n || k > n - pos) fail(EVQGPU_ERR_FORMAT, "cstable: truncated file (need %llu bytes at offset %llu)",
                           (unsigned long long) k, (unsigned long long) pos);
   }
   template <typename T>
@@ -108,7 +111,7 @@ FileMeta parse_cstable(const uint8_t* file, uint64_t nbytes) {
       col.dlevel_max = c.rd<uint32_t>();
       col.body_offset = c.rd<uint64_t>();
       col.body_size = c.rd<uint64_t>();
-      if (col.body_offset + col.body_size > nbytes) fail(EVQGPU_ERR_FORMAT, "cstable: column body out of range");
+      if (out_of_range(col.body_offset, col.body_size, nbytes)) fail(EVQGPU_ERR_FORMAT, "cstable: column body out of range");
       meta.columns.push_back(col);
     }
     std::sort(meta.columns.begin(), meta.columns.end(),
@@ -154,12 +157,12 @@ FileMeta parse_cstable(const uint8_t* file, uint64_t nbytes) {
     col.dlevel_max = (uint32_t) c.varuint();
     meta.columns.push_back(col);
   }
-  if (index_offset + index_size > nbytes) fail(EVQGPU_ERR_FORMAT, "cstable: page index out of range");
+  if (out_of_range(index_offset, index_size, nbytes)) fail(EVQGPU_ERR_FORMAT, "cstable: page index out of range");
   Cursor ic{file, index_offset + index_size, index_offset};
   uint64_t n = ic.varuint();
   for (uint64_t i = 0; i < n; ++i) {
     uint64_t type = ic.varuint(), cid = ic.varuint(), off = ic.varuint(), size = ic.varuint();
-    if (off + size > nbytes) fail(EVQGPU_ERR_FORMAT, "cstable: page out of range");
+    if (out_of_range(off, size, nbytes)) fail(EVQGPU_ERR_FORMAT, "cstable: page out of range");
     for (auto& col : meta.columns) {
       if (col.column_id != cid) continue;
       PageRef pr{off, size};
@@ -203,7 +206,14 @@ StreamLayout stream_layout(const FileMeta& meta, const ColumnMeta& col, uint32_t
   uint64_t hdr[4];
   memcpy(hdr, file + col.body_offset, 32);
   const uint64_t rsz = hdr[1], dsz = hdr[2], datasz = hdr[3];
-  if (32 + rsz + dsz + datasz > col.body_size) fail(EVQGPU_ERR_FORMAT, "cstable v1: stream sizes exceed column body");
+  {   // (each size against what is left of the body: the sum of three file-supplied u64 may wrap)
+    uint64_t left = col.body_size - 32;
+    for (uint64_t part : {rsz, dsz, datasz}) {
+      if (part > left) fail(EVQGPU_ERR_FORMAT, "cstable v1: stream sizes exceed column body");
+      left -= part;
+    }
+    if (out_of_range(col.body_offset, col.body_size, nbytes)) fail(EVQGPU_ERR_FORMAT, "cstable v1: column body out of range");
+  }
   uint64_t off, sz;
   if (kind == EVQ_STREAM_RLEVEL) { off = 32; sz = rsz; L.bitpack_max = col.rlevel_max; }
   else if (kind == EVQ_STREAM_DLEVEL) { off = 32 + rsz; sz = dsz; L.bitpack_max = col.dlevel_max; }
@@ -218,7 +228,6 @@ StreamLayout stream_layout(const FileMeta& meta, const ColumnMeta& col, uint32_t
   if (sz) L.extents.push_back({col.body_offset + off, sz});
   L.total = sz;
   L.present = sz > 0;
-  (void) nbytes;
   return L;
 }
 

@@ -1173,7 +1173,9 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
   } else {
     const uint64_t want = ht_want;
     q.ht_cap = want;
-    const uint32_t stride = (uint32_t) round_up(1 + nk + nstate, 4);   // whole 32-byte sectors; 8 words = one 64-byte DRAM atom
+    // whole 32-byte sectors, 8 words = one 64-byte DRAM atom (a probe + its updates touch one atom); a table that is only ever
+    // touched slice-wise in shared memory (partitioned aggregation, evq_agg_smem) is compact: a slice is one contiguous block
+    const uint32_t stride = s.part_bits > 0 && s.slice_slots > 0 ? (uint32_t) (1 + nk + nstate) : (uint32_t) round_up(1 + nk + nstate, 4);
     ensure(q.ht_slots, want * 8 * stride);
     base.ht.slots = q.ht_slots.as<u64>();
     base.ht.stride = stride;
@@ -1290,10 +1292,9 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
       ap.status = base.status;
       ap.nsub_total = (u32) nsub_total;
       ap.slice_slots = slice_slots;
-      int nbuf = 2, threads = 1024;   // (two buffers: the next slice is copied in meanwhile)
-      if (const char* e = getenv("EVQGPU_AGG_NBUF")) nbuf = atoi(e) == 1 ? 1 : 2;
+      int threads = 1024;
       if (const char* e = getenv("EVQGPU_AGG_THREADS")) threads = atoi(e);
-      const size_t smem = (size_t) nbuf * slice_slots * (1 + nk + nstate) * 8;
+      const size_t smem = 2 * (size_t) slice_slots * (1 + nk + nstate) * 8 + 16;   // two buffers (the next slice is copied in meanwhile) + 2 mbarriers
       EVQ_CUDA(cudaFuncSetAttribute((const void*) ag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
       int per_sm = 0;
       EVQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*) ag, threads, smem));

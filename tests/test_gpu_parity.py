@@ -663,6 +663,36 @@ def test_errors_are_loud(gpu_ctx, tmp_path):
     t2.close()
 
 
+def test_corrupt_cstable_files_are_refused(gpu_ctx, tmp_path):
+    """Truncated files and file-supplied offsets / sizes that would wrap a 64-bit sum end in ERR_FORMAT, not in reads
+    beyond the buffer (the range checks are written overflow-safe: size > n || off > n - size)."""
+    import hashlib
+    import struct
+    p = str(tmp_path / "ok.cst")
+    T.write_table(p, T.lineitem_spec(), 5000)
+    good = np.fromfile(p, dtype=np.uint8)
+    gpu_ctx.open_table(good).close()
+    FORMAT = 5   # EVQGPU_ERR_FORMAT
+    for cut in (10, 100, 250, len(good) // 2, len(good) - 1):
+        with pytest.raises(capi.EvqError) as ei:
+            t = gpu_ctx.open_table(good[:cut].copy())
+            t.load(["price"])
+        assert ei.value.status == FORMAT, (cut, ei.value.message)
+    # the page index offset of both metablocks (cstable.cc:64-76: [txid u64][rows u64][index offset u64][index size u32][sha1]):
+    # offset + size wraps around 2^64 and would pass a naive `off + size > nbytes`
+    for ioff in (2 ** 64 - 8, 2 ** 64 - 1, len(good) + 1):
+        bad = good.copy()
+        for k in range(2):
+            at = 14 + 48 * k
+            blk = bytearray(bad[at:at + 28].tobytes())
+            blk[16:24] = struct.pack("<Q", ioff)
+            bad[at:at + 28] = np.frombuffer(bytes(blk), dtype=np.uint8)
+            bad[at + 28:at + 48] = np.frombuffer(hashlib.sha1(bytes(blk)).digest(), dtype=np.uint8)
+        with pytest.raises(capi.EvqError) as ei:
+            gpu_ctx.open_table(bad)
+        assert ei.value.status == FORMAT, (ioff, ei.value.message)
+
+
 # ---- BASELINE.json sizes: size-independent properties ------------------------------------------------------------------
 
 def _merge_partials(rows_list, plan):
