@@ -286,8 +286,10 @@ static void merge_hash(evqgpu_query& q) {
   DevBuf& slots = q.merge_slots;
   if (q.merge_status.bytes < 16) q.merge_status.alloc(16);
   EvqHashTable M = H;
+  // (the scan table of a sliced plan is compact; the merge table is probed with 16-byte vector accesses: whole sectors)
+  M.stride = (H.stride + 3u) & ~3u;
   for (;;) {
-    if (slots.bytes < cap * 8 * H.stride) slots.alloc(cap * 8 * H.stride);
+    if (slots.bytes < cap * 8 * M.stride) slots.alloc(cap * 8 * M.stride);
     M.slots = slots.as<u64>();
     M.cap = cap;
     k_merge_init<<<(unsigned) ((cap + 255) / 256), 256, 0, ctx->stream>>>(M, mo);

@@ -37,6 +37,11 @@ def main():
     c, names = T.cols_of(spec)
     cases.append(("highcard_hash", spec, P.QueryPlan(names, [c["ekey"], P.call("count", P.lit(1)), P.call("sum", c["v"]), P.call("mean", c["v"]),
                                                             P.call("min", c["v"]), P.call("max", c["v"])], where=c["v"] >= 0, group=[c["ekey"]])))
+    # the same through the partitioned form of the hash tier (two partitioning levels, table slices in shared memory, compact
+    # table), forced on a small table: its table must merge like any other
+    cases.append(("highcard_partitioned", spec, P.QueryPlan(names, [c["ekey"], P.call("count", P.lit(1)), P.call("sum", c["v"]), P.call("min", c["v"]),
+                                                                   P.call("max", c["v"])], where=c["v"] >= 0, group=[c["ekey"]],
+                                                            expected_groups=1 << 20)))
     spec = T.mixed_spec(null_every=5)
     c, names = T.cols_of(spec)
     cases.append(("minmax_float_dense", spec, P.QueryPlan(names, [c["bo"], P.call("count", P.lit(1)), P.call("sum", c["f"]), P.call("min", c["f"]),
@@ -140,12 +145,18 @@ def main():
         dev_spec = [s for s in spec if not (s["encoding"] == P.ENC_UINT32_BITPACKED and s.get("null_every"))]
         tables = [ctx.synthesize(rows, dev_spec, row_offset=p * rows) for p in mine]
         plan.flags |= P.QUERY_PARTIAL
+        if name == "highcard_partitioned":
+            os.environ["EVQGPU_PART_MIN_MB"], os.environ["EVQGPU_PART_SLICE_MB"] = "0", "1"
         q = ctx.query(plan)
         for _ in range(2):          # twice: the second run reuses the cached kernels and the agreed dense slot map
             q.execute(tables)
             q.merge()
             part = q.rows()
         stats = q.stats()
+        if name == "highcard_partitioned":
+            del os.environ["EVQGPU_PART_MIN_MB"], os.environ["EVQGPU_PART_SLICE_MB"]
+            if stats["strategy"] != 4:
+                failures.append("highcard_partitioned ran as strategy %d" % stats["strategy"])
         gathered = [None] * world
         dist.all_gather_object(gathered, part)
         if rank == 0:
@@ -158,7 +169,7 @@ def main():
                 cols.append(O.Vec(st, v, np.concatenate(ns).astype(np.uint8)))
             want = O.run_query_on(cols, n, plan).rows()
             if stats["strategy"] in (1, 3):
-                got_sets = gathered            # dense tiers: every rank ends with the full result
+                got_sets = gathered            # dense tiers: every rank ends with the full result (hash tiers 2 / 4: distributed)
             else:
                 got_sets = [sum(gathered, [])]  # hash tier: results stay distributed, each group on exactly one rank
             for got in got_sets:
