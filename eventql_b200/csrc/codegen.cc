@@ -1569,6 +1569,14 @@ int gen_chunks(const KernelShape& shape) {
   return (int) ((L * EVQ_TILE_ROWS + 15) / 16 + 2);
 }
 
+// pass 1 of the partitioned hash tier gathers a tile's records in one shared-memory bin per partition: twice the expected
+// records of a 1024-row tile, within 8 .. 64, halved while the bins exceed 48 KB (wide records)
+int part_bin_records(int part_bits, size_t nrec) {
+  int bin = std::max(8, std::min(64, 2048 >> part_bits));
+  while (((size_t) bin << part_bits) * nrec * 8 > 48 * 1024 && bin > 8) bin /= 2;
+  return bin;
+}
+
 std::string generate_source(const evqgpu_query& q, const KernelShape& shape_in) {
   KernelShape shape = shape_in;
   for (int col : q.narrow_col)
@@ -1587,7 +1595,8 @@ std::string generate_source(const evqgpu_query& q, const KernelShape& shape_in) 
   if (shape.part_bits > 0) {
     bool any_null = false;
     for (int c : shape.rec_cols) any_null = any_null || shape.cols[c].nullable;
-    os << "#define EVQ_PARTITION 1\n#define EVQ_MAX_PARTS " << (1 << shape.part_bits) << "\n#define EVQ_NREC " << shape.rec_cols.size() + (any_null ? 1 : 0) << "\n";
+    os << "#define EVQ_PARTITION 1\n#define EVQ_MAX_PARTS " << (1 << shape.part_bits) << "\n#define EVQ_NREC " << shape.rec_cols.size() + (any_null ? 1 : 0)
+       << "\n#define EVQ_PART_BIN " << part_bin_records(shape.part_bits, shape.rec_cols.size() + (any_null ? 1 : 0)) << "\n";
     if (shape.slice_slots > 0) {
       os << "#define EVQ_SMEM_SLICES 1\n";
       if (const char* e = getenv("EVQGPU_AGG_THREADS")) os << "#define EVQ_AG_THREADS " << atoi(e) << "\n";   // (sweep aids, scripts/c4_step.sh)

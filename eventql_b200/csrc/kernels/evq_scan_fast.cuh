@@ -41,12 +41,8 @@ struct EvqFastScratch {
   __align__(16) u32 nval[2][EVQ_NNV][EVQ_TILE_ROWS + 8];
 #endif
 #ifdef EVQ_PARTITION
-  __align__(16) u64 prec[EVQ_TILE_ROWS * EVQ_NREC];           // the tile's records, ordered by partition
+  __align__(16) u64 prec[EVQ_MAX_PARTS * EVQ_PART_BIN * EVQ_NREC];   // the tile's records: one bin of EVQ_PART_BIN records per partition
   u32 phist[EVQ_MAX_PARTS];                                   // records of the current tile per partition
-  u32 pscan[EVQ_MAX_PARTS];                                   // ... before the partition (where its run starts in prec)
-  u32 pbase[EVQ_MAX_PARTS];                                   // where the run goes in the partition (claimed from the global cursors)
-  u32 ptotal;
-  u8 ppart[EVQ_TILE_ROWS];                                    // the partition of every staged record
 #endif
 };
 
@@ -833,19 +829,18 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
 #elif EVQ_TIER == 2 && defined(EVQ_PARTITION)
     // partitioned aggregation, pass 1: the rows that pass WHERE become records (the columns the keys and the aggregate
     // arguments read), appended to the partition their group's home slot falls into.  Every partition is ONE flat array.
-    // Scattered 16-byte stores cost ~3x the kernel's other work (profiles/r02_c4_pass1_experiments.txt), so the tile is
-    // ordered by partition in shared memory first:
-    //   (1) count the tile's records per partition (the count before a row is its rank inside the partition's run)
-    //   (2) one warp: exclusive scan of the counts, and ONE global atomic per partition claims the run in the partition
-    //   (3) every row's record goes to run start + rank of the staging array
-    //   (4) the staging array is copied out in order: consecutive threads write consecutive addresses of one run
-    u32 pr[EVQ_RPT];   // partition | rank << 8, ~0 = the row did not pass
+    // Scattered 16-byte stores cost ~3x the kernel's other work (profiles/r02_c4_pass1_experiments.txt), so the tile's
+    // records are gathered per partition in shared memory first:
+    //   (1) a row takes the next place of its partition's bin (a shared-memory atomic on the bin's counter) and is stored
+    //       there at once - no scan, no second look at the row; a bin holds twice the expected records, the rare row
+    //       that finds it full goes to the partition directly (one global atomic, one scattered store)
+    //   (2) every warp takes its share of the partitions: ONE global atomic per partition claims the run for the bin,
+    //       then the bin is copied out as one contiguous run (8 bytes per lane: full-width coalesced stores)
 #pragma unroll
     for (int k = 0; k < EVQ_RPT; ++k) {
       EvqRow row;
       evq_fast_row(cols, k, row);
       const bool pass = ((u32) k < nvalid) && evq_where(row, err) && EVQ_ROW_KEPT(k);
-      pr[k] = ~0u;
       if (pass) {
         ++passed;
         u64 key[EVQ_NKEYS > 0 ? EVQ_NKEYS : 1];
@@ -855,81 +850,44 @@ evq_scan(const __grid_constant__ EvqScanParams P, const u32 stage_bytes) {
         evq_ht_hash<EVQ_NKEYS>(P.ht, key, ktag, fpv, slot);
         const u32 part = (u32) (slot >> P.part_shift);
         u32 rank;   // (an explicit shared-memory atomic: through the generic pointer it went down the global-memory path)
-        asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(rank) : "r"(phist_sa + 4u * part));
-        pr[k] = part | (rank << 8);
-      }
-    }
-    evq_cons_sync();
-    constexpr u32 PER = EVQ_MAX_PARTS >= 32 ? EVQ_MAX_PARTS / 32 : 1;
-    u32 claim[PER];   // warp 0: the run starts claimed from the global cursors - asked for here, needed only for the copy-out,
-                      // so the round trip of the atomics overlaps with the staging of the records
-    if (tid < 32u) {
-      u32 n[PER], sum = 0;
-#pragma unroll
-      for (u32 j = 0; j < PER; ++j) {
-        const u32 p = tid * PER + j;
-        n[j] = p < EVQ_MAX_PARTS ? scr->phist[p] : 0u;
-        sum += n[j];
-      }
-      u32 incl = sum;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const u32 v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (tid >= (u32) o) incl += v;
-      }
-      u32 before = incl - sum;
-#pragma unroll
-      for (u32 j = 0; j < PER; ++j) {
-        const u32 p = tid * PER + j;
-        if (p < EVQ_MAX_PARTS) {
-          scr->phist[p] = 0u;
-          scr->pscan[p] = before;
-          claim[j] = n[j] ? atomicAdd(P.part_cursor + p, n[j]) : 0u;
-          before += n[j];
+        asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(rank) : "r"(phist_sa + 4u * part) : "memory");
+        if (rank < EVQ_PART_BIN) {
+          evq_row_store(row, scr->prec + ((size_t) part * EVQ_PART_BIN + rank) * EVQ_NREC);
+        } else {
+          const u64 pos = atomicAdd(P.part_cursor + part, 1u);
+          if (pos < P.part_cap) evq_row_store(row, P.part_buf + ((u64) part * P.part_cap + pos) * EVQ_NREC);
+          else err |= EVQ_ERR_PART_FULL;
         }
       }
-      if (tid == 31u) scr->ptotal = incl;
-    }
-    evq_cons_sync();
-#pragma unroll
-    for (int k = 0; k < EVQ_RPT; ++k) {
-      if (pr[k] != ~0u) {
-        const u32 part = pr[k] & 255u;
-        const u32 at = scr->pscan[part] + (pr[k] >> 8);
-        EvqRow row;
-        evq_fast_row(cols, k, row);
-        evq_row_store(row, scr->prec + (size_t) at * EVQ_NREC);
-        scr->ppart[at] = (u8) part;
-      }
-    }
-    if (tid < 32u) {
-#pragma unroll
-      for (u32 j = 0; j < PER; ++j)
-        if (tid * PER + j < EVQ_MAX_PARTS) scr->pbase[tid * PER + j] = claim[j];
     }
     evq_cons_sync();
     {
-      const u32 total = scr->ptotal;
-#if EVQ_NREC % 2 == 0
-      constexpr u32 U = EVQ_NREC / 2;   // 16-byte units per record
-      const ulonglong2* src = (const ulonglong2*) scr->prec;
-      for (u32 j = tid; j < total * U; j += EVQ_NCONS) {
-        const u32 i = j / U, w = j % U;
-        const u32 part = scr->ppart[i];
-        const u64 pos = (u64) scr->pbase[part] + (i - scr->pscan[part]);
-        if (pos < P.part_cap) ((ulonglong2*) (P.part_buf + ((u64) part * P.part_cap + pos) * EVQ_NREC))[w] = src[j];
-        else err |= EVQ_ERR_PART_FULL;
+      constexpr u32 PER = (EVQ_MAX_PARTS + EVQ_NWARPS - 1) / EVQ_NWARPS;   // partitions per warp
+      const u32 lane = evq_lane(), warp = tid >> 5;
+#pragma unroll 1
+      for (u32 p0 = 0; p0 < PER; p0 += 32u) {
+        // lane l: count and claim of partition warp * PER + p0 + l (the atomics of up to 32 partitions are in flight together)
+        const u32 mine = warp * PER + p0 + lane;
+        u32 n_l = 0, base_l = 0;
+        if (p0 + lane < PER && mine < EVQ_MAX_PARTS) {
+          const u32 c = scr->phist[mine];
+          scr->phist[mine] = 0u;
+          n_l = c < EVQ_PART_BIN ? c : (u32) EVQ_PART_BIN;
+          if (n_l) base_l = atomicAdd(P.part_cursor + mine, n_l);
+        }
+        const u32 cnt = PER - p0 < 32u ? PER - p0 : 32u;
+        for (u32 l = 0; l < cnt; ++l) {
+          const u32 n = __shfl_sync(0xffffffffu, n_l, l), base = __shfl_sync(0xffffffffu, base_l, l);
+          if (n == 0u) continue;
+          const u32 part = warp * PER + p0 + l;
+          if ((u64) base + n > P.part_cap) { err |= EVQ_ERR_PART_FULL; continue; }
+          const u64* src = scr->prec + (size_t) part * EVQ_PART_BIN * EVQ_NREC;
+          u64* dst = P.part_buf + ((u64) part * P.part_cap + base) * EVQ_NREC;
+          for (u32 t = lane; t < n * EVQ_NREC; t += 32u) dst[t] = src[t];
+        }
       }
-#else
-      for (u32 j = tid; j < total * EVQ_NREC; j += EVQ_NCONS) {
-        const u32 i = j / EVQ_NREC, w = j % EVQ_NREC;
-        const u32 part = scr->ppart[i];
-        const u64 pos = (u64) scr->pbase[part] + (i - scr->pscan[part]);
-        if (pos < P.part_cap) P.part_buf[((u64) part * P.part_cap + pos) * EVQ_NREC + w] = scr->prec[j];
-        else err |= EVQ_ERR_PART_FULL;
-      }
-#endif
     }
+    evq_cons_sync();
 #elif EVQ_TIER == 2
     // hash tier: the group table lives in HBM, every probe is a DRAM round trip.  Rows are handled in quads: first the
     // home slots of all 4 rows are computed and their first probes issued, then the rows are resolved and their

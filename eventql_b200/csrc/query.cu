@@ -207,7 +207,8 @@ static size_t scratch_bytes(const KernelShape& s) {
     if (s.part_bits > 0) {
       bool any_null = false;
       for (int c : s.rec_cols) any_null = any_null || s.cols[c].nullable;
-      staging = (s.rec_cols.size() + (any_null ? 1 : 0)) * 8 * EVQ_TILE_ROWS + EVQ_TILE_ROWS + 32;
+      const size_t nrec = s.rec_cols.size() + (any_null ? 1 : 0);
+      staging = ((size_t) part_bin_records(s.part_bits, nrec) << s.part_bits) * nrec * 8 + 32;
     }
     return round_up(4 * ngen * nwarps + 4 * ngen * (size_t) gen_chunks(s) + 4 * nwarps + 8 * std::max(1, s.nnull) * nwarps +
                     (size_t) s.nnv * 2 * (EVQ_TILE_ROWS + 8) * 4 + 16 + parts * (2 * 4 + 2 * 8) + 16 + staging, 128) + 128;

@@ -267,6 +267,7 @@ struct evqgpu_query {
 namespace evq {
 // codegen.cc
 std::string generate_source(const evqgpu_query& q, const KernelShape& shape);
+int part_bin_records(int part_bits, size_t nrec);   // records per shared-memory bin of pass 1 of the partitioned hash tier
 std::string generate_coordinator_source(const evqgpu_query& q);   // evq_emit over a table keyed by the 20-byte group keys
 void layout_states(evqgpu_query& q, const KernelShape& shape);
 void layout_narrow(evqgpu_query& q, const KernelShape& shape);   // after tier / g1 are known
