@@ -205,8 +205,73 @@ static MergeOps merge_ops_of(const evqgpu_query& q) {
   return mo;
 }
 
+static uint64_t exchange_by_owner(evqgpu_query& q, const EvqHashTable& H, const MergeOps& mo, DevBuf& sendbuf, DevBuf& recvbuf);
+
+// count_distinct across ranks, dense tier (count_distinct_uint64_merge, aggregate.cc:102-108: the union of the sets).  A rank's
+// set of one distinct argument is a table of (dense slot, value) pairs; the slot assignment is the same on every rank, so
+// the pairs are exchanged by owner like groups, every owner inserts what it received into a fresh set and counts the NEW
+// pairs per slot - its share of the union - into the slot's (zeroed) state word; the dense merge then sums the shares.
+__global__ void k_distinct_zero(u64* __restrict__ state, u64 slots, int nstate, int word) {
+  const u64 g = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < slots) state[g * nstate + word] = 0ull;
+}
+
+__global__ void k_distinct_insert(EvqHashTable M, const u64* __restrict__ recs, u64 nrecs, u64* __restrict__ state, u64 slots, int nstate,
+                                  int word, u32* __restrict__ status) {
+  for (u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x; i < nrecs; i += (u64) gridDim.x * blockDim.x) {
+    const u64* src = recs + i * 3;   // [slot][value][tags]
+    u64 key[2] = {src[0], src[1]};
+    const u32 tag[2] = {0u, 0u};
+    if (key[0] >= slots) { atomicOr(status, EVQ_ERR_SLOT_RANGE); continue; }
+    if (!evq_ht_upsert<2>(M, key, tag, state + key[0] * nstate + word)) atomicOr(status, EVQ_ERR_TABLE_FULL);
+  }
+}
+
+static void merge_distinct_dense(evqgpu_query& q) {
+  evqgpu_ctx* ctx = q.ctx;
+  if (ctx->nranks > 16) fail(EVQGPU_ERR_UNSUPPORTED, "merge: at most 16 ranks");
+  if (q.pending) finish_query(q);   // the local sets must be complete (a full set is grown and the scan re-run there)
+  const int nstate = (int) q.state_ops.size();
+  const uint64_t slots = q.shape.g1 > 1 ? (uint64_t) q.shape.g1 : 1;
+  MergeOps mo;
+  memset(&mo, 0, sizeof(mo));
+  mo.nkeys = 2;
+  mo.nstate = 0;
+  if (q.merge_status.bytes < 16) q.merge_status.alloc(16);
+  for (size_t d = 0; d < q.distinct_args.size(); ++d) {
+    EvqHashTable H;
+    H.slots = q.dt_slots[d].as<u64>();
+    H.cap = q.dt_cap;
+    H.stride = 4;
+    H.nkeys = 2;
+    const uint64_t recv_total = exchange_by_owner(q, H, mo, q.merge_send, q.merge_recv);
+    k_distinct_zero<<<(unsigned) ((slots + 127) / 128), 128, 0, ctx->stream>>>(q.dense_base, slots, nstate, q.distinct_word[d]);
+    EVQ_CUDA(cudaGetLastError());
+    ctx->kernel_launches += 3;
+    q.stats.kernel_launches += 3;
+    if (!recv_total) continue;
+    EvqHashTable M = H;
+    M.cap = next_pow2_(std::max<uint64_t>(1024, recv_total * 2));
+    if (q.merge_slots.bytes < M.cap * 8 * M.stride) q.merge_slots.alloc(M.cap * 8 * M.stride);
+    M.slots = q.merge_slots.as<u64>();
+    EVQ_CUDA(cudaMemsetAsync(M.slots, 0, M.cap * 8 * M.stride, ctx->stream));
+    EVQ_CUDA(cudaMemsetAsync(q.merge_status.p, 0, 16, ctx->stream));
+    const unsigned grid = (unsigned) std::min<uint64_t>((recv_total + 255) / 256, (uint64_t) ctx->sm_count * 8);
+    k_distinct_insert<<<grid, 256, 0, ctx->stream>>>(M, q.merge_recv.as<u64>(), recv_total, q.dense_base, slots, nstate, q.distinct_word[d],
+                                                     q.merge_status.as<u32>());
+    EVQ_CUDA(cudaGetLastError());
+    ctx->kernel_launches++;
+    q.stats.kernel_launches++;
+    u32 mst = 0;
+    EVQ_CUDA(cudaMemcpyAsync(&mst, q.merge_status.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (mst) fail(EVQGPU_ERR_RUNTIME, "count_distinct merge: the union set overflowed or a slot was out of range (status %u)", mst);
+  }
+}
+
 static void merge_dense(evqgpu_query& q) {
   evqgpu_ctx* ctx = q.ctx;
+  if (!q.distinct_args.empty()) merge_distinct_dense(q);
   // the fused path: ONE kernel pushes this rank's few KB of state into the peers' buffers over NVLink, waits for theirs,
   // combines in rank order, emits and re-arms (query.cu launch_tail) - no NCCL call, no separate merge / emit kernels
   if (q.use_tail && ctx->p2p_ok && !getenv("EVQGPU_NO_P2P")) {
@@ -235,15 +300,13 @@ static void launch_insert(evqgpu_ctx* ctx, EvqHashTable H, const MergeOps& mo, c
   k_merge_insert<NK><<<grid, 256, 0, ctx->stream>>>(H, mo, recs, nrecs, counters, status);
 }
 
-static void merge_hash(evqgpu_query& q) {
+// The entries of an open-addressing table cross NVLink to their owners (owner = bits of the fingerprint mod nranks): packed
+// as [keys][tag word][state words] into sendbuf, one grouped ncclSend/ncclRecv, received into recvbuf.  Returns the number
+// of records this rank received.  Collective: every rank calls it.
+static uint64_t exchange_by_owner(evqgpu_query& q, const EvqHashTable& H, const MergeOps& mo, DevBuf& sendbuf, DevBuf& recvbuf) {
   evqgpu_ctx* ctx = q.ctx;
   const int n = ctx->nranks;
-  if (n > 16) fail(EVQGPU_ERR_UNSUPPORTED, "merge: at most 16 ranks");
-  const MergeOps mo = merge_ops_of(q);
   const int rec = mo.nkeys + 1 + mo.nstate;
-  if (q.pending) finish_query(q);   // the local table must be complete (and large enough) before it is shipped
-
-  EvqHashTable H = q.emit.ht;
   // 1. groups per owner
   DevBuf& counts = q.merge_counts;
   if (counts.bytes < 3 * 16 * 8) counts.alloc(3 * 16 * 8);   // [0..16) counts, [16..32) offsets, [32..48) cursors
@@ -270,8 +333,6 @@ static void merge_hash(evqgpu_query& q) {
   }
   // 3. pack per owner
   // exchange buffers and the merged table are kept across executions (cudaMalloc of hundreds of MB per step would dominate)
-  DevBuf& sendbuf = q.merge_send;
-  DevBuf& recvbuf = q.merge_recv;
   if (sendbuf.bytes < std::max<uint64_t>(send_total, 1) * rec * 8) sendbuf.alloc(std::max<uint64_t>(send_total, 1) * rec * 8 * 5 / 4);
   if (recvbuf.bytes < std::max<uint64_t>(recv_total, 1) * rec * 8) recvbuf.alloc(std::max<uint64_t>(recv_total, 1) * rec * 8 * 5 / 4);
   EVQ_CUDA(cudaMemcpyAsync(counts.as<u64>() + 16, offs.data(), 16 * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -279,6 +340,19 @@ static void merge_hash(evqgpu_query& q) {
   EVQ_CUDA(cudaGetLastError());
   // 4. all-to-all over NVLink
   comm_all_to_all(ctx, sendbuf.p, send_off.data(), send_bytes.data(), recvbuf.p, recv_off.data(), recv_bytes.data());
+  return recv_total;
+}
+
+static void merge_hash(evqgpu_query& q) {
+  evqgpu_ctx* ctx = q.ctx;
+  const int n = ctx->nranks;
+  if (n > 16) fail(EVQGPU_ERR_UNSUPPORTED, "merge: at most 16 ranks");
+  const MergeOps mo = merge_ops_of(q);
+  if (q.pending) finish_query(q);   // the local table must be complete (and large enough) before it is shipped
+
+  EvqHashTable H = q.emit.ht;
+  DevBuf& recvbuf = q.merge_recv;
+  const uint64_t recv_total = exchange_by_owner(q, H, mo, q.merge_send, recvbuf);
   // 5. owner-side merge into a fresh table.  The merged table has its own status word: a full MERGE table (a probe run
   // longer than the bound) is grown and refilled from the received records here - it must never be mistaken for a full
   // scan table, whose remedy (re-running the local scan) would leave the records un-merged.
