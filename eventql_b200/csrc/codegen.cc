@@ -1206,7 +1206,10 @@ static std::string gen_group_kernels(const evqgpu_query& q, const KernelShape& s
       else
         os << "    for (int b = 0; b < 8; ++b) msg[len++] = (u8) (key[" << i << "] >> (8 * b));\n    msg[len++] = (u8) ktag[" << i << "];\n";
     }
-    os << "    evq_sha1(msg, len, E.out_sha + out_row * 20);\n  }\n";
+    if (q.string_keys)   // (a string key's bytes are in the host's dictionary: the tuple travels, wire.cc hashes it)
+      os << "    for (u32 b = 0; b < len; ++b) E.out_sha[out_row * " << wire_key_stride(q) << " + b] = msg[b];\n  }\n";
+    else
+      os << "    evq_sha1(msg, len, E.out_sha + out_row * 20);\n  }\n";
     for (int s = 0; s < nstate; ++s) os << "  E.out_state[out_row * " << nstate << " + " << s << "] = st[" << s << "];\n";
   }
   os << "  (void) err;\n}\n";

@@ -357,13 +357,10 @@ void query_intake(evqgpu_query* q, const evqgpu_query_desc* desc) {
     ExprPtr g = parse_program(desc->group[i]);
     if (!g) fail(EVQGPU_ERR_ARG, "empty GROUP BY expression");
     if (find_aggregate(g.get())) fail(EVQGPU_ERR_ARG, "aggregate call in GROUP BY");
-    if (lower_bare_string_column(q, g.get())) {
-      if (q->flags & EVQGPU_QUERY_WIRE)
-        fail(EVQGPU_ERR_UNSUPPORTED, "string GROUP BY keys in the partial-aggregation row format (the key hash covers the string bytes)");
-      q->string_keys = true;
-    } else {
-      lower_strings(q, g.get());
-    }
+    const bool string_key = lower_bare_string_column(q, g.get());
+    if (string_key) q->string_keys = true;   // (wire rows: the key hash covers the string bytes - made on the host, wire.cc)
+    else lower_strings(q, g.get());
+    q->group_is_string.push_back(string_key);
     if (g->type == EVQ_STRING || g->type == EVQ_NIL) fail(EVQGPU_ERR_UNSUPPORTED, "GROUP BY key type is outside the numeric device path");
     q->group.push_back(std::move(g));
   }
@@ -832,7 +829,7 @@ void emit_results(evqgpu_query& q) {
   ep.out_capacity = out_cap;
   for (size_t i = 0; i < q.select.size(); ++i) ep.out_cols[i] = q.out_cols[i].as<u8>();
   if (q.flags & EVQGPU_QUERY_WIRE) {
-    ensure(q.out_sha, out_cap * 20 + 16);
+    ensure(q.out_sha, out_cap * wire_key_stride(q) + 16);
     ensure(q.out_state, out_cap * std::max<size_t>(1, q.state_ops.size()) * 8 + 16);
     ep.out_sha = q.out_sha.as<u8>();
     ep.out_state = q.out_state.as<u64>();
@@ -859,7 +856,7 @@ void launch_tail(evqgpu_query& q, bool merge) {
   tp.E.out_capacity = out_cap;
   for (size_t i = 0; i < q.select.size(); ++i) tp.E.out_cols[i] = q.out_cols[i].as<u8>();
   if (q.flags & EVQGPU_QUERY_WIRE) {
-    ensure(q.out_sha, out_cap * 20 + 16);
+    ensure(q.out_sha, out_cap * wire_key_stride(q) + 16);
     ensure(q.out_state, out_cap * std::max<size_t>(1, q.state_ops.size()) * 8 + 16);
     tp.E.out_sha = q.out_sha.as<u8>();
     tp.E.out_state = q.out_state.as<u64>();

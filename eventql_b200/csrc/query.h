@@ -212,6 +212,7 @@ struct evqgpu_query {
   std::vector<int> col_pred;         // plan input columns that are the verdict column of string_preds[i] (-1: not)
   std::vector<evq::StringPredicate> string_preds;
   bool string_keys = false;          // a GROUP BY expression is a string column
+  std::vector<bool> group_is_string; // ... which ones
   bool has_first = false;            // some select item takes the value of its group's first row (SelectItem::first)
   bool coordinator = false;          // EVQGPU_QUERY_COORDINATOR: no scan; merges shards' partial rows (merge.cu coordinator_*)
   std::vector<uint64_t> coord_records;   // parsed rows: [3 key words][tag word][state words], kept until merge_finish
@@ -266,6 +267,9 @@ struct evqgpu_query {
 
 namespace evq {
 // codegen.cc
+// EVQGPU_QUERY_WIRE: bytes per group in out_sha - the 20-byte SHA-1 of the key tuple, or (string GROUP BY keys: the hash covers
+// the string bytes, which only the host's dictionary has) the key tuple itself, 9 bytes per key, hashed in wire.cc
+inline size_t wire_key_stride(const evqgpu_query& q) { return q.string_keys ? std::max<size_t>(20, 9 * q.group.size()) : 20; }
 std::string generate_source(const evqgpu_query& q, const KernelShape& shape);
 int part_bin_records(int part_bits, size_t nrec);   // records per shared-memory bin of pass 1 of the partitioned hash tier
 std::string generate_coordinator_source(const evqgpu_query& q);   // evq_emit over a table keyed by the 20-byte group keys

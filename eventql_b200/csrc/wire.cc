@@ -59,7 +59,14 @@ extern "C" int evqgpu_query_fetch_partial(evqgpu_query* q, uint64_t row0, uint64
     std::vector<uint64_t> st(n * nstate);
     std::vector<std::vector<uint8_t>> cols(q->select.size());
     cudaStream_t s = q->ctx->stream;
-    EVQ_CUDA(cudaMemcpyAsync(keys, q->out_sha.as<u8>() + row0 * 20, n * 20, cudaMemcpyDeviceToHost, s));
+    const size_t kstride = wire_key_stride(*q);
+    std::vector<uint8_t> rawkeys;
+    if (q->string_keys) {
+      rawkeys.resize(n * kstride);
+      EVQ_CUDA(cudaMemcpyAsync(rawkeys.data(), q->out_sha.as<u8>() + row0 * kstride, n * kstride, cudaMemcpyDeviceToHost, s));
+    } else {
+      EVQ_CUDA(cudaMemcpyAsync(keys, q->out_sha.as<u8>() + row0 * 20, n * 20, cudaMemcpyDeviceToHost, s));
+    }
     EVQ_CUDA(cudaMemcpyAsync(st.data(), q->out_state.as<u64>() + row0 * nstate, n * nstate * 8, cudaMemcpyDeviceToHost, s));
     for (size_t i = 0; i < q->select.size(); ++i) {
       if (q->select[i].agg) continue;
@@ -68,12 +75,62 @@ extern "C" int evqgpu_query_fetch_partial(evqgpu_query* q, uint64_t row0, uint64
       EVQ_CUDA(cudaMemcpyAsync(cols[i].data(), q->out_cols[i].as<u8>() + row0 * w, n * w, cudaMemcpyDeviceToHost, s));
     }
     EVQ_CUDA(cudaStreamSynchronize(s));
+    const auto& dict = q->ctx->code_strings;
+    // a string as it lies on the VM stack and in an SVector: [u32 length][bytes][tag] (svalue.cc:1139-1177); a NULL has length 0
+    auto put_string = [&](std::vector<uint8_t>& b, uint64_t code, uint8_t tag) {
+      if (code >= dict.size()) fail(EVQGPU_ERR_RUNTIME, "string code %llu outside the dictionary", (unsigned long long) code);
+      const std::string empty;
+      const std::string& str = (tag & EVQ_STAG_NULL) ? empty : dict[code];
+      const uint32_t len = (uint32_t) str.size();
+      put_raw(b, &len, 4);
+      put_raw(b, str.data(), len);
+      b.push_back(tag);
+    };
+    if (q->string_keys) {
+      // the group key: SHA-1 of the group expressions' stack bytes, last expression first (groupby.cc:112-135); the device sent
+      // the tuple with dictionary codes in place of the strings
+      std::vector<uint8_t> msg;
+      for (uint64_t r = 0; r < n; ++r) {
+        const uint8_t* raw = &rawkeys[r * kstride];
+        msg.clear();
+        for (size_t i = q->group.size(); i-- > 0;) {
+          if (q->group[i]->type == EVQ_BOOL) {
+            put_raw(msg, raw, 2);
+            raw += 2;
+            continue;
+          }
+          if (i < q->group_is_string.size() && q->group_is_string[i]) {
+            uint64_t code;
+            memcpy(&code, raw, 8);
+            put_string(msg, code, raw[8]);
+          } else {
+            put_raw(msg, raw, 9);
+          }
+          raw += 9;
+        }
+        sha1(msg.data(), msg.size(), (uint8_t*) keys + r * 20);
+      }
+    }
     std::vector<uint8_t> out;
     out.reserve(n * 32);
     for (uint64_t r = 0; r < n; ++r) {
       const uint64_t* g = &st[r * nstate];
       for (size_t i = 0; i < q->select.size(); ++i) {
         const SelectItem& item = q->select[i];
+        if (!item.agg && item.is_string) {
+          // SValue::encode of a string: type, length, [u32 length][bytes][tag].  A packed value of exactly
+          // SValue::kInlineDataSize = 16 bytes carries STAG_INLINE in its tag byte: the tag of the packed string and the
+          // SValue's own flag byte are the same byte then (svalue.cc:346-365, svalue.h:55,66) - reproduced, it is on the wire
+          uint64_t code;
+          memcpy(&code, &cols[i][r * 9], 8);
+          std::vector<uint8_t> packed;
+          put_string(packed, code, cols[i][r * 9 + 8]);
+          if (packed.size() == 16) packed.back() |= 128;
+          out.push_back((uint8_t) EVQ_STRING);
+          put_varuint(out, packed.size());
+          put_raw(out, packed.data(), packed.size());
+          continue;
+        }
         if (!item.agg) {   // SValue::encode: type, length, packed value
           const uint64_t w = item.expr->type == EVQ_BOOL ? 2 : 9;
           out.push_back((uint8_t) item.expr->type);

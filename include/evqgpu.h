@@ -382,7 +382,8 @@ EVQGPU_API int evqgpu_query_fetch(evqgpu_query* q, uint64_t row0, uint64_t max_r
  * lt / lte / gt / gte (strncmp over the shorter length, then the lengths) and startswith / endswith between a string
  * column and a literal - evaluated once per dictionary entry, applied as a 1-byte-per-row verdict column.  In a
  * multi-rank job evqgpu_query_prepare synchronises the ranks' dictionaries first, so string keys and predicates merge like
- * integers.  LIKE raises "not yet implemented" in the reference and is refused here. */
+ * integers; in the partial-aggregation row format (evqgpu_query_fetch_partial) the key hash and a selected string key carry the
+ * string bytes as the reference's do.  LIKE raises "not yet implemented" in the reference and is refused here. */
 EVQGPU_API int evqgpu_query_fetch_strings(evqgpu_query* q, uint32_t column, uint64_t row0, uint64_t max_rows, void* dst,
                                           uint64_t cap, uint64_t* nrows_out, uint64_t* nbytes_out);
 

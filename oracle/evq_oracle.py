@@ -1055,6 +1055,9 @@ def run_partial_query(tables: Sequence[CSTableFile], plan: P.QueryPlan) -> List[
     def packed(v: Vec, i: int) -> bytes:
         if v.type == P.BOOL:
             return bytes([1 if v.values[i] else 0, int(v.tags[i])])
+        if v.type == P.STRING:                   # [u32 length][bytes][tag] (svalue.cc:1139-1177); a NULL has length 0
+            s = b"" if int(v.tags[i]) & 1 else bytes(v.values[i])
+            return struct.pack("<I", len(s)) + s + bytes([int(v.tags[i])])
         return struct.pack("<Q", int(v.bits64()[i])) + bytes([int(v.tags[i])])
 
     items = []                                   # per select item: list of ng byte strings
@@ -1066,6 +1069,10 @@ def run_partial_query(tables: Sequence[CSTableFile], plan: P.QueryPlan) -> List[
             enc = []
             for i in range(ng):
                 b = packed(col, i)
+                # a packed value of exactly SValue::kInlineDataSize = 16 bytes (a string of 11 bytes) carries STAG_INLINE in
+                # its tag byte: the packed tag and the SValue's own flag byte are the same byte (svalue.cc:346-365)
+                if col.type == P.STRING and len(b) == 16:
+                    b = b[:-1] + bytes([b[-1] | 128])
                 enc.append(bytes([col.type]) + _varuint(len(b)) + b)
             items.append(enc)
             continue

@@ -366,6 +366,33 @@ def partial_cases():
     return out
 
 
+def string_partial_cases():
+    """Partial aggregation (PartialGroupByExpression rows) with STRING group keys over the string fixture table: the key hash
+    covers [u32 length][bytes][tag] of the string (groupby.cc:112-135), a string select item travels as SValue::encode.
+    [(case, sql, plan)]"""
+    names = ["k", "s_req", "s_opt"]
+    k, s_req, s_opt = P.Col(0, P.UINT64), P.Col(1, P.STRING), P.Col(2, P.STRING)
+    cnt = P.call("count", P.lit(1))
+    W = P.QUERY_GROUPBY | P.QUERY_WIRE
+    return [
+        ("sp_null_key_selected", "select s_opt, count(1), sum(k) from t where k >= 0 group by s_opt;",
+         P.QueryPlan(names, [s_opt, cnt, P.call("sum", k)], where=k >= 0, group=[s_opt], flags=W)),
+        ("sp_string_and_numeric_key", "select count(1), sum(k), max(k) from t where k >= 0 group by s_req, k % 3;",
+         P.QueryPlan(names, [cnt, P.call("sum", k), P.call("max", k)], where=k >= 0, group=[s_req, k % 3], flags=W)),
+        ("sp_two_string_keys", "select s_req, k % 2, s_opt, count(1) from t where k >= 0 group by s_req, k % 2, s_opt;",
+         P.QueryPlan(names, [s_req, k % 2, s_opt, cnt], where=k >= 0, group=[s_req, k % 2, s_opt], flags=W)),
+    ]
+
+
+def digest_partial_rows(rows):
+    """[(key bytes, data bytes)] -> sorted [[key hex, data hex or sha1:<hex>:<length> for long data]] (the fixture has ~100 KB strings)"""
+    import hashlib
+    out = []
+    for kb, db in rows:
+        out.append([kb.hex(), db.hex() if len(db) <= 200 else "sha1:%s:%d" % (hashlib.sha1(db).hexdigest(), len(db))])
+    return sorted(out)
+
+
 def parse_partial_data(plan, data: bytes):
     """The saved states of one PartialGroupByExpression row as python values (floats stay floats: they are compared with the
     1e-9 tolerance, the summation order differs), following the select items of the plan."""

@@ -149,6 +149,18 @@ def main():
             ok, why = T.rows_equal(got, want)
             assert ok, (name, why)
         print("query %-28s %d rows" % (name, len(rows)))
+    # partial-aggregation rows with string group keys (evqlref sql -P: the reference's PartialGroupByExpression); the oracle's
+    # restatement must reproduce them byte for byte (integer aggregates only)
+    out["partial"] = {}
+    for name, sql, plan in T.string_partial_cases():
+        r = subprocess.run([EVQLREF, "sql", "-P", "-t", "t=" + rp, "-q", sql], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        lines = [ln for ln in r.stdout.split("\n") if ln]
+        assert r.returncode == 0 and lines[0].startswith("#") and "ERROR!" not in lines, (name, r.stdout[:300], r.stderr[-300:])
+        want = [(bytes.fromhex(kd.split(";")[0]), bytes.fromhex(kd.split(";")[1])) for kd in lines[1:]]
+        got = O.run_partial_query([f], plan)
+        assert sorted(got) == sorted(want), (name, len(got), len(want))
+        out["partial"][name] = {"sql": sql, "rows": T.digest_partial_rows(want)}
+        print("partial %-28s %d groups" % (name, len(want)))
     with open(os.path.join(HERE, "ref_strings.json"), "w") as fo:
         json.dump(out, fo, indent=0, sort_keys=True)
     print("wrote ref_strings.json")

@@ -182,6 +182,29 @@ def test_partial_group_by_rows_through_the_reference_planner(case):
     assert plan.get("fused_groupbys", 0) >= 1
 
 
+_SP = T.string_partial_cases()
+
+
+@needs_binary
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", _SP, ids=[c[0] for c in _SP])
+def test_partial_group_by_rows_with_string_keys_through_the_reference_planner(case, tmp_path):
+    """The shard side of a cluster GROUP BY on string keys, SQL text in, (SHA-1 key, saved states) rows out: byte for byte the
+    reference's PartialGroupByExpression rows (tests/golden/ref_strings.json 'partial')."""
+    name, sql, _plan = case
+    g = json.load(open(os.path.join(GOLD, "ref_strings.json")))["partial"][name]
+    assert g["sql"] == sql
+    p = str(tmp_path / "ref_strings_v2.cst")
+    with open(p, "wb") as fh:
+        fh.write(gzip.open(os.path.join(GOLD, "ref_strings_v2.cst.gz")).read())
+    res = run_sql([("t", p)], sql, extra=["-P"])
+    assert res[0] != "error", res
+    _types, rows, plan = res
+    got = [(bytes.fromhex(k), bytes.fromhex(d)) for k, d in rows]
+    assert T.digest_partial_rows(got) == g["rows"]
+    assert plan.get("fused_groupbys", 0) >= 1
+
+
 @needs_binary
 @pytest.mark.gpu
 def test_subquery_pass_through_is_fused(tmp_path):
