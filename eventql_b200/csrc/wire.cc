@@ -387,6 +387,20 @@ static void parse_row(const evqgpu_query& q, const uint8_t* p, uint64_t n, uint6
       const uint8_t type = p[pos++];
       const uint64_t len = get_varuint(p, n, pos);
       if (len > n - pos) fail(EVQGPU_ERR_FORMAT, "partial rows: truncated value");
+      if (item.is_string) {
+        // a string value: [u32 length][bytes][tag] (the tag may carry STAG_INLINE, svalue.cc:346-365); it enters the
+        // context's dictionary and travels on as its code, like a string column's value
+        uint32_t slen = 0;
+        if (type != (uint8_t) EVQ_STRING || len < 5) fail(EVQGPU_ERR_FORMAT, "partial rows: a value of type %u where the plan has a string", type);
+        memcpy(&slen, p + pos, 4);
+        if ((uint64_t) slen + 5 != len) fail(EVQGPU_ERR_FORMAT, "partial rows: string of %u bytes in a value of %llu", slen, (unsigned long long) len);
+        const uint64_t tag = p[pos + len - 1] & 1u;
+        const uint64_t code = tag ? 0 : string_code(q.ctx, std::string((const char*) p + pos + 4, slen));
+        pos += len;
+        st[item.state_first] = (arrival << 1) | tag;
+        st[item.state_first + 1] = code;
+        continue;
+      }
       const uint64_t want = item.expr->type == EVQ_BOOL ? 2 : 9;
       if (type != (uint8_t) item.expr->type || len != want)
         fail(EVQGPU_ERR_FORMAT, "partial rows: a value of type %u / %llu bytes where the plan has type %u", type, (unsigned long long) len, item.expr->type);

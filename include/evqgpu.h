@@ -456,7 +456,8 @@ EVQGPU_API int evqgpu_partial_frames_decode(const evqgpu_query_desc* desc, const
  * group key, the aggregates' merge functions as atomics (count / sum: +, min / max over the seen ones, mean: sums and counts
  * add; a non-aggregate item: the first row's value - all rows of a group carry the same one when it is a function of the
  * key) - and evaluates every select item's `get` side per group; the rows are then fetched like any result
- * (evqgpu_query_num_rows / _fetch / _order_by / _limit).  count_distinct states (value sets) are not taken and are refused. */
+ * (evqgpu_query_num_rows / _fetch / _order_by / _limit).  A string item's value enters the context's dictionary and is fetched with evqgpu_query_fetch_strings like a
+ * string column's.  count_distinct states (value sets) are not taken and are refused. */
 EVQGPU_API int evqgpu_query_merge_rows(evqgpu_query* q, const void* base, const uint64_t* row_starts, const uint64_t* row_ends,
                                        uint64_t nrows);
 EVQGPU_API int evqgpu_query_merge_finish(evqgpu_query* q);
