@@ -108,6 +108,14 @@ void layout_states(evqgpu_query& q, const KernelShape& shape) {
       const int ty = fi.args.empty() ? EVQ_NIL : fi.args[0];
       switch (fi.fn) {
         case Fn::COUNT: item.state0 = word("c" + id, OP_ADD_U64); break;
+        case Fn::COUNT_DISTINCT:   // the size of the union of the shards' sets, counted by merge.cu k_coord_distinct
+          if (q.distinct_args.size() >= EVQ_MAX_DISTINCT)
+            fail(EVQGPU_ERR_UNSUPPORTED, "more than %d count_distinct aggregates in one query", EVQ_MAX_DISTINCT);
+          item.state0 = word("cd" + id, OP_ADD_U64);
+          item.distinct = (int) q.distinct_args.size();
+          q.distinct_args.push_back(item.agg->args.empty() ? nullptr : item.agg->args[0].get());
+          q.distinct_word.push_back(item.state0);
+          break;
         case Fn::SUM: item.state0 = word("s" + id, fi.ret == EVQ_FLOAT64 ? OP_ADD_F64 : OP_ADD_U64); break;
         case Fn::MIN:
         case Fn::MAX:
@@ -1210,7 +1218,13 @@ static std::string gen_group_kernels(const evqgpu_query& q, const KernelShape& s
       os << "    for (u32 b = 0; b < len; ++b) E.out_sha[out_row * " << wire_key_stride(q) << " + b] = msg[b];\n  }\n";
     else
       os << "    evq_sha1(msg, len, E.out_sha + out_row * 20);\n  }\n";
-    for (int s = 0; s < nstate; ++s) os << "  E.out_state[out_row * " << nstate << " + " << s << "] = st[" << s << "];\n";
+    for (int s = 0; s < nstate; ++s) {
+      // count_distinct: the saved state is the SET (aggregate.cc:110-116), which the host reads from the (group id, value)
+      // table - the word carries the group's id there (its count is the size of the set)
+      const bool is_distinct = std::find(q.distinct_word.begin(), q.distinct_word.end(), s) != q.distinct_word.end();
+      const std::string v = !is_distinct ? "st[" + std::to_string(s) + "]" : (shape.tier == 1 || shape.dense_global) ? "slot" : "(u64) sp";
+      os << "  E.out_state[out_row * " << nstate << " + " << s << "] = " << v << ";\n";
+    }
   }
   os << "  (void) err;\n}\n";
   os << "extern \"C\" __global__ void evq_emit(const __grid_constant__ EvqEmitParams E) {\n";

@@ -413,6 +413,22 @@ static void merge_hash(evqgpu_query& q) {
 // The shards' rows were parsed into merge records on the host (wire.cc coordinator_parse_rows: the states are varuints,
 // which only a sequential walk can delimit); here they are merged - the same owner-side insert kernel as the cross-GPU hash
 // merge, keyed by the three words of the 20-byte SHA-1 group key - and emitted through the plan's own emit kernel.
+// count_distinct at the coordinator (count_distinct_uint64_merge, aggregate.cc:102-108: the union of the shards' sets): every
+// (group key, value) pair received goes into one device set; the thread that inserts a NEW pair counts it into the group's
+// state word of the merged table.
+__global__ void k_coord_distinct(EvqHashTable M, EvqHashTable S, const u64* __restrict__ pairs, u64 npairs, int word, u32* __restrict__ status) {
+  for (u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += (u64) gridDim.x * blockDim.x) {
+    const u64* p = pairs + i * 4;
+    u64 k3[3] = {p[0], p[1], p[2]};
+    const u32 t3[3] = {0u, 0u, 0u};
+    u64* sp = evq_ht_upsert<3>(M, k3, t3, (u64*) 0);   // (the group exists: its row was merged before)
+    if (!sp) { atomicOr(status, EVQ_ERR_TABLE_FULL); continue; }
+    u64 k4[4] = {p[0], p[1], p[2], p[3]};
+    const u32 t4[4] = {0u, 0u, 0u, 0u};
+    if (!evq_ht_upsert<4>(S, k4, t4, sp + 1 + 3 + word)) atomicOr(status, EVQ_ERR_TABLE_FULL);
+  }
+}
+
 void coordinator_finish(evqgpu_query& q) {
   evqgpu_ctx* ctx = q.ctx;
   use_device(ctx);
@@ -461,6 +477,30 @@ void coordinator_finish(evqgpu_query& q) {
     if (cap >= (1ull << 31)) fail(EVQGPU_ERR_NOMEM, "merged group table exceeds 2^31 slots");
     cap *= 4;
   }
+  for (size_t d = 0; d < q.coord_pairs.size() && d < q.distinct_args.size(); ++d) {
+    const uint64_t np = q.coord_pairs[d].size() / 4;
+    if (!np) continue;
+    DevBuf pairs, set;
+    pairs.alloc(np * 32);
+    EVQ_CUDA(cudaMemcpyAsync(pairs.p, q.coord_pairs[d].data(), np * 32, cudaMemcpyHostToDevice, ctx->stream));
+    EvqHashTable S;
+    S.stride = 8;   // fingerprint, 3 key words, value: two sectors
+    S.nkeys = 4;
+    S.cap = next_pow2_(std::max<uint64_t>(1024, np * 2));
+    set.alloc(S.cap * 8 * S.stride);
+    S.slots = set.as<u64>();
+    EVQ_CUDA(cudaMemsetAsync(S.slots, 0, S.cap * 8 * S.stride, ctx->stream));
+    EVQ_CUDA(cudaMemsetAsync(q.merge_status.p, 0, 16, ctx->stream));
+    const unsigned grid = (unsigned) std::min<uint64_t>((np + 255) / 256, (uint64_t) ctx->sm_count * 8);
+    k_coord_distinct<<<grid, 256, 0, ctx->stream>>>(M, S, pairs.as<u64>(), np, q.distinct_word[d], q.merge_status.as<u32>());
+    EVQ_CUDA(cudaGetLastError());
+    ctx->kernel_launches++;
+    u32 mst = 0;
+    EVQ_CUDA(cudaMemcpyAsync(&mst, q.merge_status.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (mst) fail(EVQGPU_ERR_RUNTIME, "count_distinct merge: the union set overflowed (status %u)", mst);
+  }
+  q.coord_pairs.clear();
   q.shape = KernelShape();
   q.shape.tier = 2;
   q.use_tail = false;

@@ -217,6 +217,7 @@ struct evqgpu_query {
   bool coordinator = false;          // EVQGPU_QUERY_COORDINATOR: no scan; merges shards' partial rows (merge.cu coordinator_*)
   std::vector<uint64_t> coord_records;   // parsed rows: [3 key words][tag word][state words], kept until merge_finish
   uint64_t coord_nrecords = 0;
+  std::vector<std::vector<uint64_t>> coord_pairs;   // per count_distinct argument: [3 key words][value] of every set member received
   u64* dense_base = nullptr;         // dense_state, offset by one word where that makes the first-row pairs 16-byte aligned
 
   // device state, reused across executions

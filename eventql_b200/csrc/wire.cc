@@ -10,7 +10,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "query.h"
@@ -45,9 +47,6 @@ extern "C" int evqgpu_query_fetch_partial(evqgpu_query* q, uint64_t row0, uint64
     if (q->pending) finish_query(*q);
     if (!q->emitted) fail(EVQGPU_ERR_ARG, "evqgpu_query_fetch_partial: the partial results of a multi-rank job are merged, not fetched");
     if (q->reordered) fail(EVQGPU_ERR_ARG, "evqgpu_query_fetch_partial after ORDER BY / LIMIT: the key hashes no longer match the rows");
-    for (const auto& item : q->select)
-      if (item.agg && item.agg->info().fn == Fn::COUNT_DISTINCT)
-        fail(EVQGPU_ERR_UNSUPPORTED, "count_distinct keeps no value sets: its partial state cannot be serialised");
     use_device(q->ctx);
     uint64_t n = 0;
     if (row0 < q->num_rows_out) n = std::min<uint64_t>(max_rows, q->num_rows_out - row0);
@@ -86,6 +85,17 @@ extern "C" int evqgpu_query_fetch_partial(evqgpu_query* q, uint64_t row0, uint64
       put_raw(b, str.data(), len);
       b.push_back(tag);
     };
+    // count_distinct: the saved state is the set (aggregate.cc:110-116: its size, then its members in std::set order).  The
+    // sets live in the (group id, value) tables of the scan; the emit kernel left every group's id in the state word
+    std::vector<std::unordered_map<uint64_t, std::vector<uint64_t>>> sets(q->distinct_args.size());
+    for (size_t d = 0; d < q->distinct_args.size(); ++d) {
+      std::vector<uint64_t> tab(q->dt_cap * 4);
+      EVQ_CUDA(cudaMemcpyAsync(tab.data(), q->dt_slots[d].p, tab.size() * 8, cudaMemcpyDeviceToHost, s));
+      EVQ_CUDA(cudaStreamSynchronize(s));
+      for (uint64_t i = 0; i < q->dt_cap; ++i)
+        if (tab[i * 4]) sets[d][tab[i * 4 + 1]].push_back(tab[i * 4 + 2]);
+      for (auto& kv : sets[d]) std::sort(kv.second.begin(), kv.second.end());
+    }
     if (q->string_keys) {
       // the group key: SHA-1 of the group expressions' stack bytes, last expression first (groupby.cc:112-135); the device sent
       // the tuple with dictionary codes in place of the strings
@@ -160,6 +170,15 @@ extern "C" int evqgpu_query_fetch_partial(evqgpu_query* q, uint64_t row0, uint64
             else memcpy(&sum, &s0, 8);
             put_raw(out, &sum, 8);
             put_raw(out, &seen, 8);
+            break;
+          }
+          case Fn::COUNT_DISTINCT: {                                                   // count_distinct_uint64_save
+            static const std::vector<uint64_t> none;
+            const auto& set = sets[(size_t) item.distinct];
+            const auto it = set.find(s0);   // (s0 = the group's id, see above)
+            const std::vector<uint64_t>& members = it == set.end() ? none : it->second;
+            put_varuint(out, members.size());
+            for (uint64_t v : members) put_varuint(out, v);
             break;
           }
           default: fail(EVQGPU_ERR_UNSUPPORTED, "aggregate %s has no partial state format", fi.symbol.c_str());
@@ -339,6 +358,11 @@ static void skip_states(const evqgpu_query& q, const uint8_t* p, uint64_t n, uin
     uint64_t fixed = 0;
     switch (fi.fn) {
       case Fn::COUNT: get_varuint(p, n, pos); break;
+      case Fn::COUNT_DISTINCT: {   // the set: its size, then its members
+        const uint64_t members = get_varuint(p, n, pos);
+        for (uint64_t i = 0; i < members; ++i) get_varuint(p, n, pos);
+        break;
+      }
       case Fn::SUM:
         if (fi.ret == EVQ_FLOAT64) fixed = 8;
         else get_varuint(p, n, pos);
@@ -355,7 +379,7 @@ static void skip_states(const evqgpu_query& q, const uint8_t* p, uint64_t n, uin
 
 // one shard row -> one merge record [3 key words][tag word][state words in the coordinator layout]: loadInstanceState of
 // every select item (groupby.cc:577-612), SValue::decode for the others (svalue.cc:311-315)
-static void parse_row(const evqgpu_query& q, const uint8_t* p, uint64_t n, uint64_t arrival, uint64_t* rec) {
+static void parse_row(evqgpu_query& q, const uint8_t* p, uint64_t n, uint64_t arrival, uint64_t* rec) {
   const size_t nstate = q.state_ops.size();
   if (n < 20) fail(EVQGPU_ERR_FORMAT, "partial rows: truncated group key");
   rec[0] = rec[1] = rec[2] = rec[3] = 0;
@@ -423,6 +447,19 @@ static void parse_row(const evqgpu_query& q, const uint8_t* p, uint64_t n, uint6
         break;
       }
       case Fn::MEAN: st[item.state0] = raw8(); st[item.state_seen] = raw8(); break;
+      case Fn::COUNT_DISTINCT: {
+        // count_distinct_uint64_load (aggregate.cc:118-124): the shard's set.  Its members are kept as (group key, value)
+        // pairs; merge_finish unites them on the device and counts every group's distinct pairs into this (zero) word
+        if (q.coord_pairs.size() < q.distinct_args.size()) q.coord_pairs.resize(q.distinct_args.size());
+        std::vector<uint64_t>& pairs = q.coord_pairs[(size_t) item.distinct];
+        const uint64_t members = get_varuint(p, n, pos);
+        if (members > n - pos) fail(EVQGPU_ERR_FORMAT, "partial rows: a set of %llu members in %llu bytes", (unsigned long long) members, (unsigned long long) (n - pos));
+        for (uint64_t i = 0; i < members; ++i) {
+          const uint64_t v = get_varuint(p, n, pos);
+          pairs.insert(pairs.end(), {rec[0], rec[1], rec[2], v});
+        }
+        break;
+      }
       default: fail(EVQGPU_ERR_UNSUPPORTED, "aggregate %s has no partial state format", fi.symbol.c_str());
     }
   }

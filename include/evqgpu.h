@@ -397,8 +397,8 @@ EVQGPU_API int evqgpu_query_fetch_strings(evqgpu_query* q, uint32_t column, uint
  *          sum<float64> raw, oracle/ref_tools/ext_aggregates.cc), any other item as SValue::encode (svalue.cc:306-309:
  *          type byte, length, packed value);  data_offsets[i] .. data_offsets[i + 1] is group i's slice.
  * Groups [row0, row0 + max_rows); *nrows_out = groups written, *data_bytes_out = bytes needed (nothing is written when
- * data_cap is too small).  count_distinct (saved state: the set's size and its values, aggregate.cc:110-116) is not produced
- * in this format and is refused; between GPUs its sets are merged by evqgpu_query_merge (dense tier). */
+ * data_cap is too small).  count_distinct travels as its value set (size, then the members in ascending order,
+ * aggregate.cc:110-116). */
 EVQGPU_API int evqgpu_query_fetch_partial(evqgpu_query* q, uint64_t row0, uint64_t max_rows, void* keys, void* data,
                                           uint64_t data_cap, uint64_t* data_offsets, uint64_t* nrows_out,
                                           uint64_t* data_bytes_out);
@@ -457,7 +457,7 @@ EVQGPU_API int evqgpu_partial_frames_decode(const evqgpu_query_desc* desc, const
  * add; a non-aggregate item: the first row's value - all rows of a group carry the same one when it is a function of the
  * key) - and evaluates every select item's `get` side per group; the rows are then fetched like any result
  * (evqgpu_query_num_rows / _fetch / _order_by / _limit).  A string item's value enters the context's dictionary and is fetched with evqgpu_query_fetch_strings like a
- * string column's.  count_distinct states (value sets) are not taken and are refused. */
+ * string column's.  count_distinct states (value sets) are united per group and counted. */
 EVQGPU_API int evqgpu_query_merge_rows(evqgpu_query* q, const void* base, const uint64_t* row_starts, const uint64_t* row_ends,
                                        uint64_t nrows);
 EVQGPU_API int evqgpu_query_merge_finish(evqgpu_query* q);

@@ -1080,9 +1080,18 @@ def run_partial_query(tables: Sequence[CSTableFile], plan: P.QueryPlan) -> List[
         if name == "count":
             items.append([_varuint(int(c)) for c in counts])
             continue
-        if name == "count_distinct":
-            raise OracleError("count_distinct: the value sets are not restated here")
         arg = eval_expr(agg.args[0], sinputs, m)
+        if name == "count_distinct":
+            # count_distinct_uint64_save (aggregate.cc:110-116): the size of the std::set, then its members in set order; a
+            # NULL argument counts as its value 0 (popUInt64 drops the tag, H7)
+            vals = arg.bits64()
+            ends = np.append(starts[1:], m)
+            enc = []
+            for a, b in zip(starts, ends):
+                members = np.unique(vals[a:b])
+                enc.append(_varuint(len(members)) + b"".join(_varuint(int(v)) for v in members))
+            items.append(enc)
+            continue
         present = (arg.tags & 1) == 0
         npres = np.add.reduceat(present.astype(np.uint64), starts)
         res = _aggregate(name, agg.type, arg, starts, m)
@@ -1147,6 +1156,13 @@ def parse_partial_states(plan: P.QueryPlan, data: bytes) -> List[tuple]:
             sm, n = struct.unpack_from("<dQ", data, pos)
             out.append(("mean", sm, n))
             pos += 16
+        elif agg.name == "count_distinct":       # count_distinct_uint64_load (aggregate.cc:118-124)
+            n, pos = _read_varuint_at(data, pos)
+            members = set()
+            for _ in range(n):
+                v, pos = _read_varuint_at(data, pos)
+                members.add(v)
+            out.append(("distinct", members))
         else:
             raise OracleError("aggregate %s has no partial state format" % agg.name)
     if pos != len(data):
@@ -1177,6 +1193,8 @@ def merge_partial_rows(plan: P.QueryPlan, row_lists: Sequence[Sequence[Tuple[byt
                     a[1] = (a[1] + b[1]) & M64
                 elif kind == "sum":
                     a[1] = (a[1] + b[1]) & M64 if isinstance(a[1], int) else a[1] + b[1]
+                elif kind == "distinct":         # count_distinct_uint64_merge (aggregate.cc:102-108): the union
+                    a[1] |= b[1]
                 elif kind == "mean":
                     a[1] += b[1]
                     a[2] = (a[2] + b[2]) & M64
@@ -1213,6 +1231,8 @@ def merge_partial_rows(plan: P.QueryPlan, row_lists: Sequence[Sequence[Tuple[byt
                 continue
             if a[0] == "count":
                 res = Vec(P.UINT64, np.array([a[1]], dtype=np.uint64), zt)
+            elif a[0] == "distinct":
+                res = Vec(P.UINT64, np.array([len(a[1])], dtype=np.uint64), zt)
             elif a[0] == "sum":
                 if agg.type == P.FLOAT64:
                     res = Vec(P.FLOAT64, np.array([a[1]], dtype=np.float64), zt)

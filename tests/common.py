@@ -360,6 +360,12 @@ def partial_cases():
     sk = P.call("to_int64", c["b"]) - 50
     out.append(("pa_int64_key", "select to_int64(b) - 50, count(1), sum(to_int64(b) - 50) from t where b < 9 group by to_int64(b) - 50;",
                 P.QueryPlan(names, [sk, cnt, P.call("sum", sk)], where=c["b"] < 9, group=[sk], flags=W)))
+    # count_distinct: the saved state is the value set (aggregate.cc:110-116), dense tier and hash tier
+    cd = lambda e: P.call("count_distinct", e)
+    out.append(("pa_count_distinct_dense", "select b % 3, count_distinct(c % 50), count_distinct(a), count(1) from t where b >= 0 and c >= 0 and a >= 0 group by b % 3;",
+                P.QueryPlan(names, [k0, cd(c["c"] % 50), cd(c["a"]), cnt], where=(c["b"] >= 0) & (c["c"] >= 0) & (c["a"] >= 0), group=[k0], flags=W)))
+    out.append(("pa_count_distinct_many_groups", "select d, count_distinct(c % 7), sum(c) from t where d >= 0 and c >= 0 group by d;",
+                P.QueryPlan(names, [c["d"], cd(c["c"] % 7), P.call("sum", c["c"])], where=(c["d"] >= 0) & (c["c"] >= 0), group=[c["d"]], flags=W)))
     out.append(("pa_many_groups_key_not_selected", "select count(1), sum(c), mean(b) from t where d >= 0 and c >= 0 and b >= 0 group by d;",
                 P.QueryPlan(names, [cnt, P.call("sum", c["c"]), P.call("mean", c["b"])], where=(c["d"] >= 0) & (c["c"] >= 0) & (c["b"] >= 0),
                             group=[c["d"]], flags=W)))
@@ -422,6 +428,10 @@ def parse_partial_data(plan, data: bytes):
             out.append((t, raw.hex()))
         elif agg.name in ("count",) or (agg.name == "sum" and agg.type != P.FLOAT64):
             out.append(varuint())
+        elif agg.name == "count_distinct":       # the set: its size, then its members in std::set order
+            n = varuint()
+            out.append(n)
+            out.append(tuple(varuint() for _ in range(n)))
         elif agg.name == "sum":
             out.append(struct.unpack_from("<d", data, pos)[0])
             pos += 8
