@@ -370,7 +370,7 @@ def test_first_row_items(gpu_ctx, tmp_path, shape):
 
 
 @pytest.mark.parametrize("form", ["smem_slices", "l2_slices"])
-@pytest.mark.parametrize("variant", ["uniform", "two_keys_nullable", "skewed_falls_back"])
+@pytest.mark.parametrize("variant", ["uniform", "two_keys_nullable", "odd_record_words", "skewed_falls_back"])
 def test_partitioned_hash_aggregation(gpu_ctx, tmp_path, monkeypatch, variant, form):
     """Hash tier with a group table far beyond L2: pass 1 writes the passing rows as records into partitions by the top bits of
     their group's home slot.  Default form: the records are partitioned once more until a sub-partition's table slice fits
@@ -389,7 +389,11 @@ def test_partitioned_hash_aggregation(gpu_ctx, tmp_path, monkeypatch, variant, f
     else:
         spec = T.mixed_spec()
         c, names = T.cols_of(spec)
-        if variant == "two_keys_nullable":
+        if variant == "odd_record_words":   # three required record columns: records of 3 words (the 8-byte copy paths)
+            key = c["big"] / 1_000_003
+            plan = P.QueryPlan(names, [key, cnt, P.call("sum", c["b"]), P.call("max", c["t"])], where=c["bo"] | (c["b"] < 50),
+                               group=[key], expected_groups=1 << 20)
+        elif variant == "two_keys_nullable":
             key = c["big"] / 1_000_003   # (spans far more than a direct-addressed array takes: the hash tier)
             plan = P.QueryPlan(names, [key, c["k"], cnt, P.call("sum", c["a"]), P.call("min", c["f"]), P.call("max", c["d"]),
                                        P.call("mean", c["big"])], where=c["b"] >= 1, group=[key, c["k"]], expected_groups=1 << 20)
@@ -415,7 +419,7 @@ def test_partitioned_hash_aggregation(gpu_ctx, tmp_path, monkeypatch, variant, f
         want = O.run_query([O.read_cstable(p) for p in files], plan).rows()
         compare(got, want, False)
         assert st["strategy"] == (2 if variant == "skewed_falls_back" else 4), st
-        assert st["rows_passed"] == sum(r[1 if variant != "two_keys_nullable" else 2] for r in want)
+        assert st["rows_passed"] == sum(r[2 if variant == "two_keys_nullable" else 1] for r in want)
     finally:
         for t in tables:
             t.close()
