@@ -806,23 +806,20 @@ static std::string gen_row_functions(const evqgpu_query& q, const KernelShape& s
 
   // ---- partitioned aggregation: a row that passed WHERE as a record (the columns the keys and aggregate arguments read)
   if (shape.part_bits > 0) {
-    const size_t nrec_cols = shape.rec_cols.size();
-    bool any_null = false;
-    for (int c : shape.rec_cols) any_null = any_null || shape.cols[c].nullable;
+    // the record is PACKED: every column takes the bits its largest value needs (the column statistics are part of the
+    // kernel's signature), a NULL-able column one more for its tag - C4's (24-bit key, 20-bit value) rows are ONE word
+    // instead of two, which halves the traffic of all three passes
+    const RecordLayout L = record_layout(shape);
+    std::vector<std::string> words(L.nwords, "0ull");
+    for (const auto& f : L.fields) {
+      const std::string ct = fast_ctype(shape.cols[f.col]);
+      std::string v = f.is_tag ? "(u64) row.t" + std::to_string(f.col)
+                               : (ct == "f64" ? "evq_bits(row.c" + std::to_string(f.col) + ")" : "(u64) row.c" + std::to_string(f.col));
+      if (f.is_tag) v = "(" + v + " & 1ull)";
+      words[f.word] += " | (" + v + " << " + std::to_string(f.shift) + ")";
+    }
     os << "__device__ __forceinline__ void evq_row_store(const EvqRow& row, u64* rec) {\n";
-    std::vector<std::string> words;
-    for (int c : shape.rec_cols) {
-      const std::string ct = fast_ctype(shape.cols[c]);
-      const std::string f = "row.c" + std::to_string(c);
-      words.push_back(ct == "f64" ? "evq_bits(" + f + ")" : "(u64) " + f);
-    }
-    if (any_null) {
-      std::string t = "0ull";
-      for (size_t j = 0; j < nrec_cols; ++j)
-        if (shape.cols[shape.rec_cols[j]].nullable) t += " | ((u64) row.t" + std::to_string(shape.rec_cols[j]) + " << " + std::to_string(j) + ")";
-      words.push_back(t);
-    }
-    if (words.size() == 2) {   // one 16-byte store (into the tile's staging array in shared memory)
+    if (words.size() == 2) {   // one 16-byte store (into the tile's bin in shared memory)
       os << "  *(ulonglong2*) rec = make_ulonglong2(" << words[0] << ", " << words[1] << ");\n";
     } else {
       for (size_t j = 0; j < words.size(); ++j) os << "  rec[" << j << "] = " << words[j] << ";\n";
@@ -835,11 +832,12 @@ static std::string gen_row_functions(const evqgpu_query& q, const KernelShape& s
       os << "  u64 w[" << words.size() << "];\n";
       for (size_t j = 0; j < words.size(); ++j) os << "  w[" << j << "] = __ldcs(rec + " << j << ");\n";
     }
-    for (size_t j = 0; j < nrec_cols; ++j) {
-      const int c = shape.rec_cols[j];
-      const std::string ct = fast_ctype(shape.cols[c]);
-      os << "  row.c" << c << " = " << (ct == "f64" ? "evq_f64(w[" + std::to_string(j) + "])" : "(" + ct + ") w[" + std::to_string(j) + "]") << ";\n";
-      if (shape.cols[c].nullable) os << "  row.t" << c << " = (u32) (w[" << nrec_cols << "] >> " << j << ") & 1u;\n";
+    for (const auto& f : L.fields) {
+      const std::string ct = fast_ctype(shape.cols[f.col]);
+      std::string x = "(w[" + std::to_string(f.word) + "] >> " + std::to_string(f.shift) + ")";
+      if (f.bits < 64) x = "(" + x + " & " + std::to_string((1ull << f.bits) - 1) + "ull)";
+      if (f.is_tag) os << "  row.t" << f.col << " = (u32) " << x << ";\n";
+      else os << "  row.c" << f.col << " = " << (ct == "f64" ? "evq_f64(" + x + ")" : "(" + ct + ") " + x) << ";\n";
     }
     os << "  row.ord = 0;\n}\n";
   }
@@ -1586,6 +1584,31 @@ int gen_chunks(const KernelShape& shape) {
   return (int) ((L * EVQ_TILE_ROWS + 15) / 16 + 2);
 }
 
+// the packed record of the partitioned hash tier: the columns the GROUP BY expressions and the aggregate arguments read, each
+// in the bits its largest value needs (+ a tag bit for a NULL-able column), fields never straddling a word
+RecordLayout record_layout(const KernelShape& shape) {
+  RecordLayout L;
+  int word = 0, used = 0;
+  auto place = [&](int col, int bits, bool is_tag) {
+    if (used + bits > 64) { ++word; used = 0; }
+    L.fields.push_back({col, word, used, bits, is_tag});
+    used += bits;
+  };
+  for (int c : shape.rec_cols) {
+    const ColSig& cs = shape.cols[c];
+    int bits = 64;
+    const bool wide = cs.sql_type == EVQ_FLOAT64 || cs.sql_type == EVQ_INT64 || getenv("EVQGPU_NO_PACKED_RECORDS");
+    if (!wide) {
+      bits = 1;
+      while (bits < 64 && (cs.vmax >> bits) != 0) ++bits;
+    }
+    place(c, bits, false);
+    if (cs.nullable) place(c, 1, true);
+  }
+  L.nwords = (size_t) word + 1;
+  return L;
+}
+
 // pass 1 of the partitioned hash tier gathers a tile's records in one shared-memory bin per partition: twice the expected
 // records of a 1024-row tile, within 8 .. 64, halved while the bins exceed 48 KB (wide records)
 int part_bin_records(int part_bits, size_t nrec) {
@@ -1610,10 +1633,9 @@ std::string generate_source(const evqgpu_query& q, const KernelShape& shape_in) 
      << shape.ngen << "\n#define EVQ_GEN_CHUNKS " << gen_chunks(shape) << "\n#define EVQ_NNV " << shape.nnv << "\n#define EVQ_NNARROW " << q.nnarrow << "\n#define EVQ_NG " << std::max(1, q.plane_groups) << "\n#define EVQ_NSTATE_SMEM " << q.nstate_smem << "\n#define EVQ_NSTATE_ALL "
      << std::max<size_t>(1, q.state_ops.size()) << "\n";
   if (shape.part_bits > 0) {
-    bool any_null = false;
-    for (int c : shape.rec_cols) any_null = any_null || shape.cols[c].nullable;
-    os << "#define EVQ_PARTITION 1\n#define EVQ_MAX_PARTS " << (1 << shape.part_bits) << "\n#define EVQ_NREC " << shape.rec_cols.size() + (any_null ? 1 : 0)
-       << "\n#define EVQ_PART_BIN " << part_bin_records(shape.part_bits, shape.rec_cols.size() + (any_null ? 1 : 0)) << "\n";
+    const size_t nrec = record_layout(shape).nwords;
+    os << "#define EVQ_PARTITION 1\n#define EVQ_MAX_PARTS " << (1 << shape.part_bits) << "\n#define EVQ_NREC " << nrec
+       << "\n#define EVQ_PART_BIN " << part_bin_records(shape.part_bits, nrec) << "\n";
     if (shape.slice_slots > 0) {
       os << "#define EVQ_SMEM_SLICES 1\n";
       if (const char* e = getenv("EVQGPU_AGG_THREADS")) os << "#define EVQ_AG_THREADS " << atoi(e) << "\n";   // (sweep aids, scripts/c4_step.sh)

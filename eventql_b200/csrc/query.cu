@@ -205,9 +205,7 @@ static size_t scratch_bytes(const KernelShape& s) {
     const size_t parts = s.part_bits > 0 ? ((size_t) 1 << s.part_bits) : 0;
     size_t staging = 0;   // partitioned aggregation: the tile's records ordered by partition + their partition bytes
     if (s.part_bits > 0) {
-      bool any_null = false;
-      for (int c : s.rec_cols) any_null = any_null || s.cols[c].nullable;
-      const size_t nrec = s.rec_cols.size() + (any_null ? 1 : 0);
+      const size_t nrec = record_layout(s).nwords;
       staging = ((size_t) part_bin_records(s.part_bits, nrec) << s.part_bits) * nrec * 8 + 32;
     }
     return round_up(4 * ngen * nwarps + 4 * ngen * (size_t) gen_chunks(s) + 4 * nwarps + 8 * std::max(1, s.nnull) * nwarps +
@@ -1211,9 +1209,7 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
 
   if (s.part_bits > 0) {
     const uint64_t parts = 1ull << s.part_bits;
-    bool any_null = false;
-    for (int c : s.rec_cols) any_null = any_null || s.cols[c].nullable;
-    const uint64_t nrec = s.rec_cols.size() + (any_null ? 1 : 0);
+    const uint64_t nrec = record_layout(s).nwords;
     base.part_bits = (u32) s.part_bits;
     u32 lg = 0;
     while ((1ull << lg) < base.ht.cap) ++lg;

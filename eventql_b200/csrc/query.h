@@ -272,6 +272,9 @@ namespace evq {
 // the string bytes, which only the host's dictionary has) the key tuple itself, 9 bytes per key, hashed in wire.cc
 inline size_t wire_key_stride(const evqgpu_query& q) { return q.string_keys ? std::max<size_t>(20, 9 * q.group.size()) : 20; }
 std::string generate_source(const evqgpu_query& q, const KernelShape& shape);
+struct RecordField { int col, word, shift, bits; bool is_tag; };
+struct RecordLayout { std::vector<RecordField> fields; size_t nwords = 1; };
+RecordLayout record_layout(const KernelShape& shape);   // the packed record of the partitioned hash tier (codegen.cc)
 int part_bin_records(int part_bits, size_t nrec);   // records per shared-memory bin of pass 1 of the partitioned hash tier
 std::string generate_coordinator_source(const evqgpu_query& q);   // evq_emit over a table keyed by the 20-byte group keys
 void layout_states(evqgpu_query& q, const KernelShape& shape);
