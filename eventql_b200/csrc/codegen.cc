@@ -1237,8 +1237,8 @@ static std::string gen_group_kernels(const evqgpu_query& q, const KernelShape& s
     os << "struct EvqAggParams { EvqHashTable ht; const u64* part_buf; const u32* part_cursor; u64 part_cap; u32 nparts; u32 nseg; u32* status; u64* counters; u32* bar; u32 window; u32 pad; };\n";
     os << "extern \"C\" __global__ void __launch_bounds__(256) evq_agg_part(const __grid_constant__ EvqAggParams A) {\n";
     os << "  u32 err = 0;\n";
-    // ONE (cooperative: all CTAs resident) launch walks the partitions in order; a CTA takes whole segments (what one
-    // pass-1 CTA appended to the partition).  The CTAs stay within `window` partitions of each other - before partition p
+    // ONE (cooperative: all CTAs resident) launch walks the partitions in order, all CTAs striding over a partition's
+    // records together.  The CTAs stay within `window` partitions of each other - before partition p
     // a CTA waits until every CTA is done with partition p - window (a counter every CTA bumps once per partition) - so
     // that at most window + 1 table slices are being worked on: they stay L2-resident, and nobody idles at a barrier.
     os << "  for (u32 part = 0; part < A.nparts; ++part) {\n";

@@ -88,13 +88,12 @@ struct EvqScanParams {
   u64 tile_row_base;                // first tile index of this table inside tile_counts
   u64 ord_base;                     // added to a row's ordinal (tile index * 1024 + row in tile): rank-major order of a multi-rank job
   // partitioned aggregation (tier 2, groups far beyond L2): pass 1 writes the rows that pass WHERE as records into
-  // 2^part_bits partitions by the top bits of their home slot; pass 2 (evq_agg_part) aggregates one partition at a time,
-  // whose slice of the group table stays L2-resident
-  // Every CTA of pass 1 owns one segment of every partition, so appending needs no global atomics and no barriers: the
-  // position inside the segment comes from a shared-memory cursor.
-  u64* part_buf;                    // [2^part_bits][gridDim.x][part_cap][EVQ_NREC] record words
+  // 2^part_bits flat partition arrays by the top bits of their home slot (a tile's records are gathered per partition in
+  // shared memory, one run per partition and tile is claimed from the cursors); the passes behind it (evq_repart +
+  // evq_agg_smem, or evq_agg_part) aggregate one table slice at a time in shared memory / L2
+  u64* part_buf;                    // [2^part_bits][part_cap][EVQ_NREC] record words
   u32* part_cursor;                 // [2^part_bits] records appended to every partition (runs are claimed with atomicAdd)
-  u64 part_cap;                     // records per segment
+  u64 part_cap;                     // records per partition
   u32 part_shift;                   // partition = home slot >> part_shift
   u32 part_bits;
 };

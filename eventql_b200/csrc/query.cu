@@ -1037,9 +1037,10 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
   if ((s.tier == 1 && s.g1 > 1) || s.dense_global) s.dense = dm;
   layout_narrow(q, s);
   // hash tier with a group table far beyond L2: partitioned aggregation.  Pass 1 (the scan) writes the rows that pass WHERE
-  // as records into 2^part_bits partitions by the top bits of their group's home slot; pass 2 aggregates one partition at a
-  // time, whose slice of the table (~24 MB) stays L2-resident - sequential record traffic instead of a random HBM sector pair
-  // (and its write-back) per row.  A partition that overflows (heavily skewed keys, for which the direct tier is the right
+  // as records into 2^part_bits partitions by the top bits of their group's home slot; the passes behind it aggregate one
+  // table slice at a time - in shared memory after a second partitioning level (evq_repart + evq_agg_smem, the default), or
+  // L2-resident (evq_agg_part) - sequential record traffic instead of a random HBM sector pair (and its write-back) per
+  // row.  A partition that overflows (heavily skewed keys, for which the direct tier is the right
   // one anyway: hot groups live in L2) makes the query fall back to the direct tier for good.
   uint64_t ht_want = 0, part_cap = 0;
   if (s.tier == 2 && !s.dense_global) {
@@ -1078,7 +1079,7 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
         if (item.agg) for (const auto& a : item.agg->args) collect_columns(a.get(), used);
       for (size_t i = 0; i < used.size(); ++i)
         if (used[i]) s.rec_cols.push_back((int) i);
-      part_cap = 1;   // (the segment capacity follows from every table's launch grid, see below)
+      part_cap = 1;   // (the partitions' capacity follows from every table's row count, see below)
     }
   }
   fit_shape(q, s, plans);
