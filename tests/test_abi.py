@@ -152,6 +152,21 @@ def test_first_row_select_item_compiles_with_one_128_bit_cas(native_lib):
         assert "evq_first_update(EVQ_GPTR(" in src and "atom.global.relaxed.gpu.cas.b128" in src and cubin_bytes > 1000
 
 
+def test_partitioned_hash_tier_kernels_compile(native_lib):
+    """The hash tier beyond L2 (strategy 4): pass 1 with per-partition shared-memory bins inside evq_scan, evq_repart, and
+    evq_agg_smem with TMA bulk copies of the table slices - NVRTC for sm_100a.  Narrow columns pack into one record word."""
+    spec = T.events_spec()
+    _, plan = T.q_highcard(spec)
+    for cols, nrec in ((_cols(spec), 2),                                                    # full-range 64-bit keys: two words
+                       ([(P.UINT64, P.ENC_UINT64_PLAIN, 0, 24, 0, 0, 0, 10_000_000),
+                         (P.UINT64, P.ENC_UINT64_LEB128, 0, 20, 3, 0, 0, 999_999)], 1)):      # 24-bit keys + 20-bit values: one
+        src, cubin_bytes = capi.debug_generate(plan, cols, tier=4, compile=True)
+        assert "#define EVQ_NREC %d\n" % nrec in src, [l for l in src.splitlines() if "EVQ_NREC" in l][:2]
+        for name in ("evq_repart", "evq_agg_smem", "evq_agg_part"):
+            assert "void __launch_bounds__" in src and name + "(" in src
+        assert "cp.async.bulk.global.shared::cta.bulk_group" in src and "atom.shared.add.u32" in src and cubin_bytes > 1000
+
+
 def test_context_without_device_raises(native_lib):
     """The product path has no host execution mode: no CUDA device -> hard error."""
     import torch

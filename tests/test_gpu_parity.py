@@ -370,7 +370,7 @@ def test_first_row_items(gpu_ctx, tmp_path, shape):
 
 
 @pytest.mark.parametrize("form", ["smem_slices", "l2_slices"])
-@pytest.mark.parametrize("variant", ["uniform", "two_keys_nullable", "odd_record_words", "skewed_falls_back"])
+@pytest.mark.parametrize("variant", ["uniform", "two_keys_nullable", "odd_record_words", "one_word_record", "skewed_falls_back"])
 def test_partitioned_hash_aggregation(gpu_ctx, tmp_path, monkeypatch, variant, form):
     """Hash tier with a group table far beyond L2: pass 1 writes the passing rows as records into partitions by the top bits of
     their group's home slot.  Default form: the records are partitioned once more until a sub-partition's table slice fits
@@ -393,6 +393,8 @@ def test_partitioned_hash_aggregation(gpu_ctx, tmp_path, monkeypatch, variant, f
             key = c["big"] / 1_000_003
             plan = P.QueryPlan(names, [key, cnt, P.call("sum", c["b"]), P.call("max", c["t"])], where=c["bo"] | (c["b"] < 50),
                                group=[key], expected_groups=1 << 20)
+        elif variant == "one_word_record":   # a 40-bit NULL-able key + its tag + a 7-bit argument: the packed record is ONE word
+            plan = P.QueryPlan(names, [c["a"], cnt, P.call("sum", c["b"])], where=c["b"] >= 0, group=[c["a"]], expected_groups=1 << 20)
         elif variant == "two_keys_nullable":
             key = c["big"] / 1_000_003   # (spans far more than a direct-addressed array takes: the hash tier)
             plan = P.QueryPlan(names, [key, c["k"], cnt, P.call("sum", c["a"]), P.call("min", c["f"]), P.call("max", c["d"]),
