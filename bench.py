@@ -431,7 +431,10 @@ def run_workload(job, name, steps, warmup, rows=0, parts=0, keep_tables=False, s
                                                     ("dense state over peer-mapped NVLink buffers, merged + emitted by the tail kernel" if stats["strategy"] == 1 else
                                                      "ncclAllReduce(sum) of the direct-addressed group array" if stats["strategy"] == 3 else
                                                      "hash repartition (all-to-all) + owner-side insert")),
-        "roofline": {"bound": "hbm", "kernel": "evq_scan", "achieved": achieved, "peak": job.peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm",
+                     # (strategy 4: the event pair of a table's scan also brackets the passes behind it)
+                     "kernel": "evq_scan + evq_repart + evq_agg_smem (per table)" if stats["strategy"] == 4 else "evq_scan",
+                     "achieved": achieved, "peak": job.peak, "unit": "GB/s",
                      "frac": (achieved / job.peak) if achieved else None, "traffic": None,
                      "traffic_note": "not measured in this run (needs ncu); per-kernel dram__bytes are in profiles/*ncu*.txt",
                      "peak_source": job.peak_src, "algorithmic_bytes_per_launch": per_launch, "launch_ms": scan_ms,
