@@ -28,6 +28,7 @@ struct MergeOps {
   int ops[72];        // EVQ_OP_* per state word
   int carry_of[72];   // for a carry word: the sum word whose 64-bit wraps it counts (exact 128-bit sums of mean()), else -1
   int carry_at[72];   // for a sum word: its carry word, else -1
+  unsigned char zero[72];   // hash merge: the word travels as 0 (count_distinct: the owner counts the union of the sets instead)
 };
 
 __device__ __forceinline__ u64 merge_identity(int op) {
@@ -133,7 +134,66 @@ __global__ void k_merge_pack(EvqHashTable H, int nranks, MergeOps mo, const u64*
       tags |= ((fp >> (2 + k)) & 1ull) << (8 * k);
     }
     dst[mo.nkeys] = tags;
-    for (int s = 0; s < mo.nstate; ++s) dst[mo.nkeys + 1 + s] = sp[1 + mo.nkeys + s];
+    for (int s = 0; s < mo.nstate; ++s) dst[mo.nkeys + 1 + s] = mo.zero[s] ? 0ull : sp[1 + mo.nkeys + s];
+  }
+}
+
+// count_distinct sets of the hash tier: a member (group, value) names its group by the address of the group's slot in this
+// rank's table.  It travels to the GROUP's owner as [group keys][tag word][value]; there the group is looked up in the merged
+// table and (merged slot, value) goes into a fresh set whose inserting threads count into the group's word.
+__global__ void k_dpair_count(EvqHashTable D, int nranks, u64* __restrict__ counts) {
+  __shared__ u32 local[16];
+  if (threadIdx.x < 16) local[threadIdx.x] = 0;
+  __syncthreads();
+  for (u64 slot = (u64) blockIdx.x * blockDim.x + threadIdx.x; slot < D.cap; slot += (u64) gridDim.x * blockDim.x) {
+    const u64* sp = D.slots + slot * D.stride;
+    if (!sp[0]) continue;
+    const u64* g = (const u64*) sp[1];
+    atomicAdd(&local[owner_of(g[0], nranks)], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < nranks && local[threadIdx.x]) atomicAdd(counts + threadIdx.x, (u64) local[threadIdx.x]);
+}
+
+__global__ void k_dpair_pack(EvqHashTable D, int gnk, int nranks, const u64* __restrict__ offsets, u64* __restrict__ cursors,
+                             u64* __restrict__ out) {
+  const int rec = gnk + 2;
+  for (u64 slot = (u64) blockIdx.x * blockDim.x + threadIdx.x; slot < D.cap; slot += (u64) gridDim.x * blockDim.x) {
+    const u64* sp = D.slots + slot * D.stride;
+    if (!sp[0]) continue;
+    const u64* g = (const u64*) sp[1];
+    const u64 gfp = g[0];
+    const u32 o = owner_of(gfp, nranks);
+    const u64 pos = offsets[o] + atomicAdd(cursors + o, 1ull);
+    u64* dst = out + pos * rec;
+    u64 tags = 0;
+    for (int k = 0; k < gnk; ++k) {
+      dst[k] = g[1 + k];
+      tags |= ((gfp >> (2 + k)) & 1ull) << (8 * k);
+    }
+    dst[gnk] = tags;
+    dst[gnk + 1] = sp[2];
+  }
+}
+
+template <int NK>
+__global__ void k_dpair_insert(EvqHashTable M, EvqHashTable S, const u64* __restrict__ recs, u64 nrecs, int word, u32* __restrict__ status) {
+  const int rec = NK + 2;
+  for (u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x; i < nrecs; i += (u64) gridDim.x * blockDim.x) {
+    const u64* src = recs + i * rec;
+    u64 key[NK > 0 ? NK : 1];
+    u32 tag[NK > 0 ? NK : 1];
+    const u64 tags = src[NK];
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      key[k] = src[k];
+      tag[k] = (u32) ((tags >> (8 * k)) & 0xffu);
+    }
+    u64* sp = evq_ht_upsert<NK>(M, key, tag, (u64*) 0);   // (the group is there: its record came from the same rank)
+    if (!sp) { atomicOr(status, EVQ_ERR_TABLE_FULL); continue; }
+    u64 k2[2] = {(u64) sp, src[NK + 1]};
+    const u32 t2[2] = {0u, 0u};
+    if (!evq_ht_upsert<2>(S, k2, t2, sp + 1 + NK + word)) atomicOr(status, EVQ_ERR_TABLE_FULL);
   }
 }
 
@@ -202,10 +262,13 @@ static MergeOps merge_ops_of(const evqgpu_query& q) {
     mo.carry_of[i] = q.state_carry_of[i];
     if (q.state_carry_of[i] >= 0) mo.carry_at[q.state_carry_of[i]] = i;
   }
+  for (int w : q.distinct_word)
+    if (w >= 0 && w < 72) mo.zero[w] = 1;
   return mo;
 }
 
-static uint64_t exchange_by_owner(evqgpu_query& q, const EvqHashTable& H, const MergeOps& mo, DevBuf& sendbuf, DevBuf& recvbuf);
+static uint64_t exchange_by_owner(evqgpu_query& q, const EvqHashTable& H, const MergeOps& mo, DevBuf& sendbuf, DevBuf& recvbuf,
+                                  int pairs_of_groups_with_keys = -1);
 
 // count_distinct across ranks, dense tier (count_distinct_uint64_merge, aggregate.cc:102-108: the union of the sets).  A rank's
 // set of one distinct argument is a table of (dense slot, value) pairs; the slot assignment is the same on every rank, so
@@ -303,16 +366,21 @@ static void launch_insert(evqgpu_ctx* ctx, EvqHashTable H, const MergeOps& mo, c
 // The entries of an open-addressing table cross NVLink to their owners (owner = bits of the fingerprint mod nranks): packed
 // as [keys][tag word][state words] into sendbuf, one grouped ncclSend/ncclRecv, received into recvbuf.  Returns the number
 // of records this rank received.  Collective: every rank calls it.
-static uint64_t exchange_by_owner(evqgpu_query& q, const EvqHashTable& H, const MergeOps& mo, DevBuf& sendbuf, DevBuf& recvbuf) {
+// (pairs_of_groups_with_keys >= 0: H is a count_distinct set of the hash tier, its members travel to their GROUP's owner as
+// [that many group keys][tag word][value], k_dpair_*)
+static uint64_t exchange_by_owner(evqgpu_query& q, const EvqHashTable& H, const MergeOps& mo, DevBuf& sendbuf, DevBuf& recvbuf,
+                                  int pairs_of_groups_with_keys) {
   evqgpu_ctx* ctx = q.ctx;
   const int n = ctx->nranks;
-  const int rec = mo.nkeys + 1 + mo.nstate;
+  const int gnk = pairs_of_groups_with_keys;
+  const int rec = gnk >= 0 ? gnk + 2 : mo.nkeys + 1 + mo.nstate;
   // 1. groups per owner
   DevBuf& counts = q.merge_counts;
   if (counts.bytes < 3 * 16 * 8) counts.alloc(3 * 16 * 8);   // [0..16) counts, [16..32) offsets, [32..48) cursors
   EVQ_CUDA(cudaMemsetAsync(counts.p, 0, counts.bytes, ctx->stream));
   const unsigned grid = (unsigned) std::min<uint64_t>((H.cap + 255) / 256, (uint64_t) ctx->sm_count * 8);
-  k_merge_count<<<grid, 256, 0, ctx->stream>>>(H, n, counts.as<u64>());
+  if (gnk >= 0) k_dpair_count<<<grid, 256, 0, ctx->stream>>>(H, n, counts.as<u64>());
+  else k_merge_count<<<grid, 256, 0, ctx->stream>>>(H, n, counts.as<u64>());
   EVQ_CUDA(cudaGetLastError());
   std::vector<uint64_t> mine(16, 0);
   EVQ_CUDA(cudaMemcpyAsync(mine.data(), counts.p, 16 * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -336,7 +404,8 @@ static uint64_t exchange_by_owner(evqgpu_query& q, const EvqHashTable& H, const 
   if (sendbuf.bytes < std::max<uint64_t>(send_total, 1) * rec * 8) sendbuf.alloc(std::max<uint64_t>(send_total, 1) * rec * 8 * 5 / 4);
   if (recvbuf.bytes < std::max<uint64_t>(recv_total, 1) * rec * 8) recvbuf.alloc(std::max<uint64_t>(recv_total, 1) * rec * 8 * 5 / 4);
   EVQ_CUDA(cudaMemcpyAsync(counts.as<u64>() + 16, offs.data(), 16 * 8, cudaMemcpyHostToDevice, ctx->stream));
-  k_merge_pack<<<grid, 256, 0, ctx->stream>>>(H, n, mo, counts.as<u64>() + 16, counts.as<u64>() + 32, sendbuf.as<u64>());
+  if (gnk >= 0) k_dpair_pack<<<grid, 256, 0, ctx->stream>>>(H, gnk, n, counts.as<u64>() + 16, counts.as<u64>() + 32, sendbuf.as<u64>());
+  else k_merge_pack<<<grid, 256, 0, ctx->stream>>>(H, n, mo, counts.as<u64>() + 16, counts.as<u64>() + 32, sendbuf.as<u64>());
   EVQ_CUDA(cudaGetLastError());
   // 4. all-to-all over NVLink
   comm_all_to_all(ctx, sendbuf.p, send_off.data(), send_bytes.data(), recvbuf.p, recv_off.data(), recv_bytes.data());
@@ -400,6 +469,46 @@ static void merge_hash(evqgpu_query& q) {
   q.merge_cap = cap;
   ctx->kernel_launches += 2;
   q.stats.kernel_launches += 2;
+  // count_distinct: the sets' members follow their groups (the groups' distinct words travelled as 0); every owner unites
+  // what it received per merged group and counts (count_distinct_uint64_merge, aggregate.cc:102-108)
+  for (size_t d = 0; d < q.distinct_args.size(); ++d) {
+    EvqHashTable D;
+    D.slots = q.dt_slots[d].as<u64>();
+    D.cap = q.dt_cap;
+    D.stride = 4;
+    D.nkeys = 2;
+    const uint64_t np = exchange_by_owner(q, D, mo, q.merge_send, q.merge_recv, mo.nkeys);
+    if (!np) continue;
+    EvqHashTable S = D;
+    S.cap = next_pow2_(std::max<uint64_t>(1024, np * 2));
+    DevBuf set;
+    set.alloc(S.cap * 8 * S.stride);
+    S.slots = set.as<u64>();
+    EVQ_CUDA(cudaMemsetAsync(S.slots, 0, S.cap * 8 * S.stride, ctx->stream));
+    EVQ_CUDA(cudaMemsetAsync(q.merge_status.p, 0, 16, ctx->stream));
+    const unsigned g2 = (unsigned) std::min<uint64_t>((np + 255) / 256, (uint64_t) ctx->sm_count * 8);
+    const u64* pr = q.merge_recv.as<u64>();
+    u32* st = q.merge_status.as<u32>();
+    const int word = q.distinct_word[d];
+    switch (mo.nkeys) {
+      case 0: k_dpair_insert<0><<<g2, 256, 0, ctx->stream>>>(M, S, pr, np, word, st); break;
+      case 1: k_dpair_insert<1><<<g2, 256, 0, ctx->stream>>>(M, S, pr, np, word, st); break;
+      case 2: k_dpair_insert<2><<<g2, 256, 0, ctx->stream>>>(M, S, pr, np, word, st); break;
+      case 3: k_dpair_insert<3><<<g2, 256, 0, ctx->stream>>>(M, S, pr, np, word, st); break;
+      case 4: k_dpair_insert<4><<<g2, 256, 0, ctx->stream>>>(M, S, pr, np, word, st); break;
+      case 5: k_dpair_insert<5><<<g2, 256, 0, ctx->stream>>>(M, S, pr, np, word, st); break;
+      case 6: k_dpair_insert<6><<<g2, 256, 0, ctx->stream>>>(M, S, pr, np, word, st); break;
+      case 7: k_dpair_insert<7><<<g2, 256, 0, ctx->stream>>>(M, S, pr, np, word, st); break;
+      default: k_dpair_insert<8><<<g2, 256, 0, ctx->stream>>>(M, S, pr, np, word, st); break;
+    }
+    EVQ_CUDA(cudaGetLastError());
+    ctx->kernel_launches += 3;
+    q.stats.kernel_launches += 3;
+    u32 mst = 0;
+    EVQ_CUDA(cudaMemcpyAsync(&mst, q.merge_status.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    EVQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (mst) fail(EVQGPU_ERR_RUNTIME, "count_distinct merge: the union set overflowed (status %u)", mst);
+  }
   // results are emitted from the merged table; the local table stays allocated for the next execution
   q.emit.ht = M;
   q.emit.slots = cap;

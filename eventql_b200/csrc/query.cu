@@ -1189,10 +1189,11 @@ static void execute_groupby(evqgpu_query& q, std::vector<TablePlan>& plans, std:
   }
   // count_distinct: one empty (group, value) set per distinct argument; grown x4 with the group table when it fills up
   if (!q.distinct_args.empty()) {
-    // across ranks the sets of the DENSE tier are merged (merge.cu merge_distinct_dense: the slot index names the group on
-    // every rank); in the other tiers a group is named by a rank-local address
-    if ((q.flags & EVQGPU_QUERY_PARTIAL) && ctx->nranks > 1 && !(s.tier == 1 && !s.dense_global))
-      fail(EVQGPU_ERR_UNSUPPORTED, "count_distinct over more groups than the dense tier holds is not merged across ranks");
+    // across ranks the sets are merged in the dense tier (merge.cu merge_distinct_dense: the slot index names the group on
+    // every rank) and in the hash tier (merge_hash: the members follow their group's keys to its owner); the
+    // direct-addressed array is merged by an all-reduce of sums, which a set count is not
+    if ((q.flags & EVQGPU_QUERY_PARTIAL) && ctx->nranks > 1 && s.dense_global)
+      fail(EVQGPU_ERR_UNSUPPORTED, "count_distinct in the direct-addressed tier is not merged across ranks");
     if (q.dt_cap == 0) {
       q.dt_cap = next_pow2(std::max<uint64_t>(1ull << 20, std::min<uint64_t>(total_rows, 1ull << 24) * 2));
       if (const char* e = getenv("EVQGPU_DT_CAP")) q.dt_cap = next_pow2(std::max<uint64_t>(1024, strtoull(e, nullptr, 10)));   // (tests: force growth)

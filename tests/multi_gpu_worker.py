@@ -58,6 +58,8 @@ def main():
     cd = lambda e: P.call("count_distinct", e)
     cases.append(("distinct_dense", spec, P.QueryPlan(names, [c["b"] % 3, cd(c["c"] % 50), cd(c["a"]), P.call("sum", c["b"]), P.call("count", P.lit(1))],
                                                       where=(c["b"] >= 0) & (c["c"] >= 0), group=[c["b"] % 3])))
+    cases.append(("distinct_hash", spec, P.QueryPlan(names, [c["c"] % 5003, cd(c["b"]), cd(c["a"] % 11), P.call("count", P.lit(1))], where=c["b"] >= 0,
+                                                     group=[c["c"] % 5003], expected_groups=1 << 25)))
     cases.append(("distinct_global", spec, P.QueryPlan(names, [cd(c["c"]), P.call("count", P.lit(1))], where=c["b"] >= 0)))
     spec = T.readings_spec(0)
     cases.append(("timeseries_direct_addressed", spec, T.q_timeseries(spec, expected_groups=1_440_000)[1]))
