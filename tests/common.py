@@ -362,8 +362,8 @@ def partial_cases():
                 P.QueryPlan(names, [sk, cnt, P.call("sum", sk)], where=c["b"] < 9, group=[sk], flags=W)))
     # count_distinct: the saved state is the value set (aggregate.cc:110-116), dense tier and hash tier
     cd = lambda e: P.call("count_distinct", e)
-    out.append(("pa_count_distinct_dense", "select b % 3, count_distinct(c % 50), count_distinct(a), count(1) from t where b >= 0 and c >= 0 and a >= 0 group by b % 3;",
-                P.QueryPlan(names, [k0, cd(c["c"] % 50), cd(c["a"]), cnt], where=(c["b"] >= 0) & (c["c"] >= 0) & (c["a"] >= 0), group=[k0], flags=W)))
+    out.append(("pa_count_distinct_dense", "select b % 3, count_distinct(c % 50), count_distinct(a % 97), count(1) from t where b >= 0 and c >= 0 and a >= 0 group by b % 3;",
+                P.QueryPlan(names, [k0, cd(c["c"] % 50), cd(c["a"] % 97), cnt], where=(c["b"] >= 0) & (c["c"] >= 0) & (c["a"] >= 0), group=[k0], flags=W)))
     out.append(("pa_count_distinct_many_groups", "select d, count_distinct(c % 7), sum(c) from t where d >= 0 and c >= 0 group by d;",
                 P.QueryPlan(names, [c["d"], cd(c["c"] % 7), P.call("sum", c["c"])], where=(c["d"] >= 0) & (c["c"] >= 0), group=[c["d"]], flags=W)))
     out.append(("pa_many_groups_key_not_selected", "select count(1), sum(c), mean(b) from t where d >= 0 and c >= 0 and b >= 0 group by d;",
